@@ -1,0 +1,308 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE ONLY.
+
+numpy/ctypes face over the two CPU checkers (same entry points, prefix ref_ / port_):
+
+  Oracle("ref")   oracle/_ref/libref_oracle.so  -- the unmodified reference compiled in place
+  Oracle("port")  oracle/libport_oracle.so      -- the plain-C restatement (oracle/sigproc_port.c)
+  Oracle("best")  ref when present, else port
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product (openbts_ttsou_b200) never does.
+Complex vectors are numpy complex64; bits uint8/int8 (one per bit); soft bits float32.
+"""
+import ctypes
+import os
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "libref_oracle.so")
+PORT_SO = os.path.join(HERE, "libport_oracle.so")
+
+c_f = ctypes.c_float
+c_i = ctypes.c_int
+c_l = ctypes.c_long
+c_p = ctypes.c_void_p
+
+FULL_SPAN, OVERLAP_ONLY, START_ONLY, WITH_TAIL, NO_DELAY = 0, 1, 2, 3, 4
+T_COS, T_SIN, T_ROT, T_REVROT, T_PULSE, T_MID_SEQ, T_MID_META, T_RACH_SEQ, T_RACH_META, T_LPF_RX, T_LPF_TX, T_OOB = range(12)
+
+
+def build(ref=True):
+    """(Re)build the checkers with oracle/Makefile.  ref is skipped by make when /root/reference is absent."""
+    subprocess.run(["make", "-C", HERE, "port"] + (["ref"] if ref else []), check=True,
+                   stdout=subprocess.DEVNULL)
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(c_p)
+
+
+def _c64(a):
+    return np.ascontiguousarray(a, dtype=np.complex64)
+
+
+class Oracle:
+    def __init__(self, kind="best", sps=1):
+        if kind == "best":
+            kind = "ref" if have_ref() else "port"
+        self.kind = kind
+        path = REF_SO if kind == "ref" else PORT_SO
+        if not os.path.exists(path):
+            if kind == "port":
+                build(ref=False)
+            else:
+                raise FileNotFoundError(path)
+        self.lib = ctypes.CDLL(path)
+        self.pfx = "ref_" if kind == "ref" else "port_"
+        for name in ("sinc", "sin_lookup", "cos_lookup"):
+            f = self._f(name)
+            f.restype = c_f
+            f.argtypes = [c_f]
+        self._f("modulate_stream").restype = c_l
+        self.sps = None
+        self.setup(sps)
+
+    def _f(self, name):
+        return getattr(self.lib, self.pfx + name)
+
+    def setup(self, sps):
+        if self.sps != sps:
+            self._f("setup")(c_i(sps))
+            self.sps = sps
+
+    # ---- tables
+    def table(self, tid, idx=0):
+        buf = np.zeros(4096, np.float32)
+        n = self._f("get_table")(c_i(tid), c_i(idx), _ptr(buf), c_i(buf.size))
+        assert n >= 0
+        out = buf[:n].copy()
+        if tid in (T_ROT, T_REVROT, T_PULSE, T_MID_SEQ, T_RACH_SEQ):
+            return out.view(np.complex64)
+        return out
+
+    def sinc(self, x):
+        return float(self._f("sinc")(c_f(x)))
+
+    def sin_lookup(self, x):
+        return float(self._f("sin_lookup")(c_f(x)))
+
+    def cos_lookup(self, x):
+        return float(self._f("cos_lookup")(c_f(x)))
+
+    # ---- single-vector functions (sigProcLib.h surface)
+    def modulate(self, bits, guard, sps=None):
+        sps = sps or self.sps
+        bits = np.ascontiguousarray(bits, dtype=np.int8)
+        out = np.zeros(sps * (bits.size + guard), np.complex64)
+        n = self._f("modulate")(_ptr(bits), c_i(bits.size), c_i(guard), c_i(sps), _ptr(out), c_i(out.size))
+        assert n == out.size
+        return out
+
+    def delay_vector(self, v, delay):
+        v = _c64(v).copy()
+        self._f("delay_vector")(_ptr(v), c_i(v.size), c_f(delay))
+        return v
+
+    def scale_vector(self, v, scale, real_only=False):
+        v = _c64(v).copy()
+        s = np.array([complex(scale)], np.complex64)
+        self._f("scale_vector")(_ptr(v), c_i(v.size), c_i(int(real_only)), _ptr(s))
+        return v
+
+    def _conv(self, name, a, b, span, a_real, b_real):
+        a, b = _c64(a), _c64(b)
+        out = np.zeros(a.size + b.size + 2, np.complex64)
+        n = self._f(name)(_ptr(a), c_i(a.size), c_i(int(a_real)), _ptr(b), c_i(b.size), c_i(int(b_real)),
+                          _ptr(out), c_i(out.size), c_i(span))
+        assert n >= 0
+        return out[:n].copy()
+
+    def convolve(self, a, b, span, a_real=False, b_real=False):
+        return self._conv("convolve", a, b, span, a_real, b_real)
+
+    def correlate(self, a, b, span, a_real=False, b_real=False):
+        return self._conv("correlate", a, b, span, a_real, b_real)
+
+    def peak_detect(self, v):
+        v = _c64(v)
+        pk = np.zeros(1, np.complex64)
+        idx, avg = c_f(), c_f()
+        self._f("peak_detect")(_ptr(v), c_i(v.size), _ptr(pk), ctypes.byref(idx), ctypes.byref(avg))
+        return pk[0], idx.value, avg.value
+
+    def interpolate_point(self, v, ix):
+        v = _c64(v)
+        pk = np.zeros(1, np.complex64)
+        self._f("interpolate_point")(_ptr(v), c_i(v.size), c_f(ix), _ptr(pk))
+        return pk[0]
+
+    def energy_detect(self, v, win, thr):
+        v = _c64(v)
+        avg = c_f()
+        ok = self._f("energy_detect")(_ptr(v), c_i(v.size), ctypes.c_uint(win), c_f(thr), ctypes.byref(avg))
+        return bool(ok), avg.value
+
+    def analyze(self, burst, tsc, thr, sps=None, request=True):
+        sps = sps or self.sps
+        burst = _c64(burst)
+        amp = np.zeros(1, np.complex64)
+        chan = np.zeros(6 * sps, np.complex64)
+        toa, off = c_f(), c_f()
+        ok = self._f("analyze")(_ptr(burst), c_i(burst.size), c_i(tsc), c_f(thr), c_i(sps), _ptr(amp),
+                                ctypes.byref(toa), c_i(int(request)), _ptr(chan), ctypes.byref(off))
+        return bool(ok), amp[0], toa.value, chan, off.value
+
+    def detect_rach(self, burst, thr, sps=None):
+        sps = sps or self.sps
+        burst = _c64(burst)
+        amp = np.zeros(1, np.complex64)
+        toa = c_f()
+        ok = self._f("detect_rach")(_ptr(burst), c_i(burst.size), c_f(thr), c_i(sps), _ptr(amp), ctypes.byref(toa))
+        return bool(ok), amp[0], toa.value
+
+    def design_dfe(self, chan, snr, nf=7):
+        chan = _c64(chan)
+        w = np.zeros(nf, np.complex64)
+        b = np.zeros(chan.size - 1, np.complex64)
+        self._f("design_dfe")(_ptr(chan), c_i(chan.size), c_f(snr), c_i(nf), _ptr(w), _ptr(b))
+        return w, b
+
+    def equalize(self, burst, toa, w, b, sps=1):
+        """returns (soft, burst_after) -- the reference delays the burst in place"""
+        burst = _c64(burst).copy()
+        w, b = _c64(w), _c64(b)
+        soft = np.zeros(burst.size, np.float32)
+        self._f("equalize")(_ptr(burst), c_i(burst.size), c_f(toa), c_i(sps), _ptr(w), c_i(w.size), _ptr(b),
+                            c_i(b.size), _ptr(soft))
+        return soft, burst
+
+    def demodulate(self, burst, amp, toa, sps=None):
+        sps = sps or self.sps
+        burst = _c64(burst)
+        a = np.array([amp], np.complex64)
+        soft = np.zeros(burst.size, np.float32)
+        n = self._f("demodulate")(_ptr(burst), c_i(burst.size), c_i(sps), _ptr(a), c_f(toa), _ptr(soft))
+        return soft[:n].copy()
+
+    def resample(self, x, P, Q, lpf):
+        x = _c64(x)
+        out = np.zeros(int(np.ceil(x.size * P / Q)) + 4, np.complex64)
+        n = self._f("resample")(_ptr(x), c_i(x.size), c_i(P), c_i(Q), c_i(lpf), _ptr(out), c_i(out.size))
+        return out[:n].copy()
+
+    # ---- batched caller glue; `threads` python threads each run a contiguous slice (ctypes drops the GIL)
+    @staticmethod
+    def _shard(n, threads):
+        threads = max(1, min(threads, n))
+        edges = np.linspace(0, n, threads + 1).astype(np.int64)
+        return [(int(edges[i]), int(edges[i + 1])) for i in range(threads) if edges[i + 1] > edges[i]]
+
+    @staticmethod
+    def _run(jobs, fn):
+        if len(jobs) == 1:
+            fn(*jobs[0])
+            return
+        with ThreadPoolExecutor(len(jobs)) as ex:
+            list(ex.map(lambda j: fn(*j), jobs))
+
+    def rx_normal_batch(self, bursts, lens, tsc, detect_thr=3.0, energy_thr=250.0, threads=1, debug=True):
+        """bursts: (n, pitch) complex64.  Returns dict(flag, amp, toa, chan, off, w, b, soft[n,160])."""
+        bursts = _c64(bursts)
+        n, pitch = bursts.shape
+        lens = np.ascontiguousarray(lens, np.int32)
+        tsc = np.ascontiguousarray(tsc, np.uint8)
+        r = dict(flag=np.zeros(n, np.int32), amp=np.zeros(n, np.complex64), toa=np.zeros(n, np.float32),
+                 soft=np.zeros((n, 160), np.float32))
+        if debug:
+            r.update(chan=np.zeros((n, 6), np.complex64), off=np.zeros(n, np.float32),
+                     w=np.zeros((n, 7), np.complex64), b=np.zeros((n, 5), np.complex64))
+        f = self._f("rx_normal_batch")
+
+        def job(lo, hi):
+            f(_ptr(bursts[lo:hi]), c_i(pitch), _ptr(lens[lo:hi]), _ptr(tsc[lo:hi]), c_l(hi - lo),
+              c_f(detect_thr), c_f(energy_thr), _ptr(r["flag"][lo:hi]), _ptr(r["amp"][lo:hi]), _ptr(r["toa"][lo:hi]),
+              _ptr(r["chan"][lo:hi]) if debug else None, _ptr(r["off"][lo:hi]) if debug else None,
+              _ptr(r["w"][lo:hi]) if debug else None, _ptr(r["b"][lo:hi]) if debug else None,
+              _ptr(r["soft"][lo:hi]), c_i(160))
+        self._run(self._shard(n, threads), job)
+        return r
+
+    def rx_rach_batch(self, bursts, lens, detect_thr=5.0, sps=1, threads=1):
+        bursts = _c64(bursts)
+        n, pitch = bursts.shape
+        lens = np.ascontiguousarray(lens, np.int32)
+        spitch = 160
+        r = dict(flag=np.zeros(n, np.int32), amp=np.zeros(n, np.complex64), toa=np.zeros(n, np.float32),
+                 soft=np.zeros((n, spitch), np.float32))
+        f = self._f("rx_rach_batch")
+
+        def job(lo, hi):
+            f(_ptr(bursts[lo:hi]), c_i(pitch), _ptr(lens[lo:hi]), c_l(hi - lo), c_f(detect_thr), c_i(sps),
+              _ptr(r["flag"][lo:hi]), _ptr(r["amp"][lo:hi]), _ptr(r["toa"][lo:hi]), _ptr(r["soft"][lo:hi]), c_i(spitch))
+        self._run(self._shard(n, threads), job)
+        return r
+
+    def rx_resample_stream(self, raw, threads=1):
+        """raw: complex64, length multiple of 864, stream starts at chunk 0 (zero history)."""
+        raw = _c64(raw)
+        nch = raw.size // 864
+        out = np.zeros(nch * 585, np.complex64)
+        f = self._f("rx_resample_stream")
+
+        def job(lo, hi):
+            f(_ptr(raw[lo * 864:]), c_l(lo), c_l(hi - lo), _ptr(out[lo * 585:]))
+        self._run(self._shard(nch, threads), job)
+        return out
+
+    def tx_resample_stream(self, x, threads=1):
+        """x: complex64 at 1 sps, length multiple of 585 -> int16 (n,2) at 400 kS/s, 864 per chunk."""
+        x = _c64(x)
+        nch = x.size // 585
+        out = np.zeros((nch * 864, 2), np.int16)
+        f = self._f("tx_resample_stream")
+
+        def job(lo, hi):
+            f(_ptr(x[lo * 585:]), c_l(lo), c_l(hi - lo), _ptr(out[lo * 864:]))
+        self._run(self._shard(nch, threads), job)
+        return out
+
+    def modulate_stream(self, bits148, tn0=0, threads=1):
+        """bits148: (n,148) -> complex64 stream of 157/156/156/156-sample bursts (n multiple of 4 per shard)."""
+        bits = np.ascontiguousarray(bits148, np.int8)
+        n = bits.shape[0]
+        out = np.zeros(stream_offset(n, tn0) + 0, np.complex64)
+        f = self._f("modulate_stream")
+        f.restype = c_l
+
+        def job(lo, hi):
+            f(_ptr(bits[lo:hi]), c_l(hi - lo), c_i((tn0 + lo) % 8), _ptr(out[stream_offset(lo, tn0):]))
+        jobs = [(lo - lo % 8, hi - hi % 8 if hi < n else hi) for lo, hi in self._shard(n, threads)]
+        self._run([j for j in jobs if j[1] > j[0]], job)
+        return out
+
+    def rx_stream_demod(self, resampled, nbursts, tsc, detect_thr=3.0, energy_thr=250.0, threads=1):
+        res = _c64(resampled)
+        tsc = np.ascontiguousarray(tsc, np.uint8)
+        assert stream_offset(nbursts) <= res.size
+        r = dict(flag=np.zeros(nbursts, np.int32), amp=np.zeros(nbursts, np.complex64),
+                 toa=np.zeros(nbursts, np.float32), soft=np.zeros((nbursts, 160), np.float32))
+        f = self._f("rx_stream_demod")
+
+        def job(lo, hi):
+            f(_ptr(res), c_l(lo), c_l(hi - lo), _ptr(tsc[lo:hi]), c_f(detect_thr), c_f(energy_thr),
+              _ptr(r["flag"][lo:hi]), _ptr(r["amp"][lo:hi]), _ptr(r["toa"][lo:hi]), _ptr(r["soft"][lo:hi]), c_i(160))
+        self._run(self._shard(nbursts, threads), job)
+        return r
+
+
+def stream_offset(burst, tn0=0):
+    """sample offset of burst `burst` in a 157/156/156/156 slot stream that starts at timeslot tn0 (tn0 % 4 == 0)."""
+    assert tn0 % 4 == 0
+    return (burst // 4) * 625 + (0, 157, 313, 469)[burst % 4]
