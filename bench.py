@@ -1,0 +1,329 @@
+#!/usr/bin/env python3
+"""bench.py -- GSM bursts/s through the receive hot path (RX resample -> slot cut -> detect -> DFE).
+
+Workload (BASELINE.json configs[1]): one ARFCN x 8 timeslots, a continuous 400 kS/s complex stream of
+~10^5 TDMA frames (855 blocks of 117 frames = 100 035 frames = 800 280 normal bursts = 213 750 resampler
+chunks = 1.48 GB of complex64), TSC 0, SNR 20 dB, synthetic.  A step = one pass over that stream.
+With --gpus N every rank processes its own stream of that size (weak scaling, no data-path collective).
+
+  value : whole-job bursts/s, inputs resident in HBM, timed with CUDA events on the launching stream
+  e2e   : the same through the host-buffer C-ABI call btsdsp_rx_stream_host (pinned host input,
+          H2D + kernels + D2H of soft bits inside the timed region)
+  roofline : the dominant kernel's algorithmic HBM bytes / its event-timed duration vs the measured peak;
+             `kernels` lists both kernels of the step
+  cpu_baseline : the compiled reference (oracle/_ref) or its C port on the host cores, same stream
+  --impl reference : only that CPU arm, as its own JSON line
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOCK_BURSTS, BLOCK_CHUNKS = 936, 250           # 117 frames: lcm of 625-sample slot groups and 585-sample chunks
+DEFAULT_BLOCKS = 855                            # 100 035 frames ~ BASELINE's 10^5
+SOFT_PITCH = 148
+# algorithmic HBM bytes (SURVEY 8d / DESIGN.md): per chunk 864 in + 585 out complex64; per burst 1250 B of
+# resampled samples in (156.25 x 8) + 148 soft f32 + flag/toa/amp (16 B) out
+RESAMPLE_BYTES_PER_CHUNK = (864 + 585) * 8
+DEMOD_BYTES_PER_BURST = 1250 + 148 * 4 + 16
+FUSED_BYTES_PER_BURST = 1846.2 + 608            # the ideal single-pass figure (raw in, soft out)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_arm(raw, nblocks, tsc, threads, repeat=1):
+    """the reference's CPU path over the first nblocks blocks of `raw` (complex64 numpy); returns (bursts/s, kind)"""
+    from oracle.oracle import Oracle
+    o = Oracle("best", sps=1)
+    nb, nch = nblocks * BLOCK_BURSTS, nblocks * BLOCK_CHUNKS
+    best = None
+    for _ in range(repeat):
+        t0 = time.perf_counter()
+        res = o.rx_resample_stream(raw[:nch * 864], threads=threads)
+        o.rx_stream_demod(res, nb, tsc[:nb], threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return nb / best, ("reference" if o.kind == "ref" else "port"), best
+
+
+def make_stream_cpu(nblocks, seed):
+    """reference arm without a GPU: build the stream with the oracle itself"""
+    from oracle.oracle import Oracle
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import synth
+    o = Oracle("best", sps=1)
+    rng = np.random.default_rng(seed)
+    nb = nblocks * BLOCK_BURSTS
+    bits = rng.integers(0, 2, (nb, 148)).astype(np.uint8)
+    bits[:, :3] = 0; bits[:, 145:] = 0
+    bits[:, 61:87] = synth.bits_of(synth.TSC[0])
+    th = os.cpu_count() or 1
+    iq = o.tx_resample_stream(o.modulate_stream(bits, threads=th), threads=th)
+    raw = (iq[:, 0] + 1j * iq[:, 1]).astype(np.complex64)
+    raw += (955.0 * (rng.standard_normal(raw.size) + 1j * rng.standard_normal(raw.size))).astype(np.complex64)
+    return raw
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # bounded sample: 400 blocks = 374 400 bursts ~ 12 core-seconds of the reference per step
+    nblocks = max(2, min(args.blocks, 400))
+    raw = make_stream_cpu(nblocks, 0xB2000002)
+    tsc = np.zeros(nblocks * BLOCK_BURSTS, np.uint8)
+    for _ in range(args.warmup):
+        cpu_arm(raw, min(nblocks, 4), tsc, cores)
+    times = []
+    kind = "port"
+    for _ in range(args.steps):
+        v, kind, dt = cpu_arm(raw, nblocks, tsc, cores)
+        times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = nblocks * BLOCK_BURSTS / (ms / 1e3)
+    sample = "%d of %d blocks of 117 frames (%d bursts) per step" % (nblocks, args.blocks, nblocks * BLOCK_BURSTS)
+    print(json.dumps({
+        "impl": "reference", "metric": "GSM bursts/sec (resample+detect+DFE)", "value": value, "unit": "bursts/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "bursts/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "bursts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def workload_config(args, n):
+    return {"workload": "configs[1]: 1 ARFCN x 8 TS continuous RX stream, rcv 65/96 polyphase resample (961-tap) + "
+                        "normal-burst detect + DFE demod", "frames": args.blocks * 117,
+            "bursts_per_gpu_per_step": args.blocks * BLOCK_BURSTS, "raw_samples_per_gpu": args.blocks * BLOCK_CHUNKS * 864,
+            "sps": 1, "tsc": 0, "snr_db": 20, "parallelism": "stream per GPU x%d, no data-path collective" % n,
+            "cache": "inputs_larger_than_l2 (1.48 GB stream per step)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--blocks", type=int, default=DEFAULT_BLOCKS, help="117-frame blocks per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import openbts_ttsou_b200 as pkg
+    from openbts_ttsou_b200.build import build
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    if rank == 0:
+        build()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    dsp = pkg.BtsDsp(local, 1)
+
+    nb, nch = args.blocks * BLOCK_BURSTS, args.blocks * BLOCK_CHUNKS
+    # ---- synthetic stream, built on the device with the product's own TX path (parity-tested)
+    g = torch.Generator(device=dev)
+    g.manual_seed(0xB2000002 + rank)
+    bits = torch.randint(0, 2, (nb, 148), generator=g, device=dev, dtype=torch.uint8)
+    bits[:, :3] = 0
+    bits[:, 145:] = 0
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import synth
+    bits[:, 61:87] = torch.from_numpy(synth.bits_of(synth.TSC[0]).copy()).to(dev)
+    iq = torch.empty(nch * 864 * 2, dtype=torch.int16, device=dev)
+    dsp.tx_stream_dev(bits, nb, iq, stream=torch.cuda.current_stream())
+    raw = iq.to(torch.float32)
+    del iq
+    raw.add_(torch.randn(raw.numel(), generator=g, device=dev), alpha=955.0)     # SNR 20 dB at amplitude 13500
+    tsc = torch.zeros(nb, dtype=torch.uint8, device=dev)
+    res = torch.empty(nch * 585 * 2, dtype=torch.float32, device=dev)
+    flag = torch.zeros(nb, dtype=torch.int32, device=dev)
+    amp = torch.zeros(nb * 2, dtype=torch.float32, device=dev)
+    toa = torch.zeros(nb, dtype=torch.float32, device=dev)
+    soft = torch.zeros(nb * SOFT_PITCH, dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step(evs=None):
+        if evs:
+            evs[0].record(stream)
+        dsp.resample_rx_dev(raw, nch, res, stream=stream)
+        if evs:
+            evs[1].record(stream)
+        dsp.demod_normal_dev(res, 0, tsc, nb, flag, amp, toa, soft, SOFT_PITCH, stream=stream)
+        if evs:
+            evs[2].record(stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    ber = float(((soft.reshape(nb, SOFT_PITCH) > 0.5).to(torch.uint8) != bits).float().mean())
+    detected = float(flag.float().mean())
+
+    # ---- timed region: device-resident
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = dsp.launch_count
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record(stream)
+    for k in range(args.steps):
+        step(evs[k])
+    t_end.record(stream)
+    torch.cuda.synchronize()
+    launches = dsp.launch_count - l0
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_total = t_start.elapsed_time(t_end)
+    ms_res = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    ms_dem = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax.item()) / args.steps
+    value = world * nb / (ms_step / 1e3)
+
+    # ---- e2e: host buffers through btsdsp_rx_stream_host
+    e2e = None
+    if not args.no_e2e:
+        raw_h = torch.empty(raw.numel(), dtype=torch.float32, pin_memory=True)
+        raw_h.copy_(raw)
+        tsc_h = np.zeros(nb, np.uint8)
+        flag_h = torch.empty(nb, dtype=torch.int32, pin_memory=True)
+        amp_h = torch.empty(nb * 2, dtype=torch.float32, pin_memory=True)
+        toa_h = torch.empty(nb, dtype=torch.float32, pin_memory=True)
+        soft_h = torch.empty(nb * SOFT_PITCH, dtype=torch.float32, pin_memory=True)
+
+        def e2e_step():
+            dsp.rx_stream_host(raw_h, nch, tsc_h, nb, flag_h, amp_h, toa_h, soft_h, SOFT_PITCH)
+        for _ in range(2):
+            e2e_step()
+        same = bool(torch.equal(soft_h, soft.cpu())) and bool(torch.equal(toa_h, toa.cpu()))
+        ke = max(3, min(args.steps, 10))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t0) / ke], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * nb / float(dt.item()), "unit": "bursts/s", "ms_per_step": 1e3 * float(dt.item()),
+               "h2d_bytes_per_step": int(raw.numel() * 4 + nb), "d2h_bytes_per_step": int(nb * (SOFT_PITCH * 4 + 16)),
+               "matches_device_path": same, "api": "btsdsp_rx_stream_host (pinned host buffers)"}
+
+    # ---- optional gather of SoftVectors over NCCL (outside the timed path, reported separately)
+    gather = None
+    if world > 1:
+        from openbts_ttsou_b200.shard import gather_soft
+        part = soft[:8192 * SOFT_PITCH].reshape(8192, SOFT_PITCH)
+        gather_soft(part)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            gather_soft(part)
+        b.record()
+        torch.cuda.synchronize()
+        gather = {"what": "all_gather of 8192 SoftVectors (148 f32) per rank over NCCL", "ms": a.elapsed_time(b) / 10}
+
+    # ---- CPU baseline on the same stream (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        nblk = max(2, min(args.blocks, int(20 * 3.0e4 * cores / BLOCK_BURSTS)))
+        raw_np = raw[:nblk * BLOCK_CHUNKS * 864 * 2].cpu().numpy().view(np.complex64)
+        v, kind, dt = cpu_arm(raw_np, nblk, np.zeros(nblk * BLOCK_BURSTS, np.uint8), cores, repeat=2)
+        cpu = {"value": v, "unit": "bursts/s", "cores": cores, "kind": kind, "seconds": dt,
+               "sample": "first %d of %d blocks of 117 frames (%d bursts), best of 2" % (nblk, args.blocks, nblk * BLOCK_BURSTS)}
+
+    if rank == 0:
+        peak, how = measured_peaks()
+        k_res = {"name": "k_resample_rx", "ms": ms_res, "algorithmic_bytes": nch * RESAMPLE_BYTES_PER_CHUNK}
+        k_dem = {"name": "k_demod_normal", "ms": ms_dem, "algorithmic_bytes": nb * DEMOD_BYTES_PER_BURST}
+        for k in (k_res, k_dem):
+            k["achieved_gbs"] = k["algorithmic_bytes"] / (k["ms"] * 1e-3) / 1e9
+            k["frac"] = k["achieved_gbs"] / peak
+        dom = k_dem if ms_dem >= ms_res else k_res
+        out = {
+            "metric": "GSM bursts/sec (resample+detect+DFE)", "value": value, "unit": "bursts/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "roofline": {"bound": "hbm", "kernel": dom["name"], "achieved": dom["achieved_gbs"], "peak": peak,
+                         "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": how,
+                         "kernels": [k_res, k_dem],
+                         "step_frac_of_fused_hbm_roof": (nb * FUSED_BYTES_PER_BURST / (ms_step * 1e-3) / 1e9) / peak},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "check": {"ber_tsc0": ber, "detected": detected}, "gather": gather,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,199 @@
+/*
+ * btsdsp.h -- C ABI of the B200-native OpenBTS transceiver burst-DSP library (libbtsdsp.so).
+ *
+ * This is the drop-in boundary for the hot path of the reference's software transceiver: the free
+ * functions of Transceiver/sigProcLib.h:101-384 (called from Transceiver.cpp:62-424 and
+ * radioInterface.cpp:137-245).  Three layers, all plain pointers and sizes (no CUDA or torch types):
+ *
+ *   1. single-vector calls with HOST pointers, synchronous -- one per sigProcLib.h function, same
+ *      argument meaning and error behaviour; openbts_ttsou_b200/host/sigProcLib.h re-wraps them in the
+ *      reference's C++ signatures (signalVector/BitVector/SoftVector) so Transceiver.cpp /
+ *      radioInterface.cpp link unchanged;
+ *   2. batched calls with DEVICE pointers and a CUDA stream (passed as void*), thousands of
+ *      (ARFCN, timeslot) bursts or resampler chunks per launch -- the throughput path;
+ *   3. batched calls with HOST pointers that run layer 2 behind pinned staging buffers and overlapped
+ *      copies -- what a radioInterface/Transceiver replacement (or bench.py's e2e leg) calls.
+ *
+ * Data: complex samples are interleaved float pairs {re, im} (== the reference's Complex<float>,
+ * Complex.h:39-44, == CUDA float2); bits are one byte per bit with the value in bit 0 (BitVector);
+ * soft bits are floats in [0,1] (SoftVector), hard bit = soft > 0.5F (BitVector.h:415-420).
+ * All functions return BTSDSP_OK (0) or a negative error; btsdsp_last_error() gives the text.
+ * There is no CPU fallback: without a CUDA device btsdsp_create() fails.
+ * Contexts are per device; a context's calls must not be issued concurrently from several host threads
+ * (layer-2 calls on distinct streams are asynchronous with respect to each other on the device).
+ */
+#ifndef BTSDSP_H
+#define BTSDSP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden; these are its exports */
+#endif
+
+typedef struct btsdsp_ctx btsdsp_ctx;
+typedef struct { float re, im; } btsdsp_cf32;
+
+enum {
+  BTSDSP_OK = 0,
+  BTSDSP_EINVAL = -1,       /* bad argument (null pointer, size out of range, sps not supported here) */
+  BTSDSP_ECUDA = -2,        /* CUDA runtime error; text in btsdsp_last_error() */
+  BTSDSP_ENOMEM = -3,
+  BTSDSP_EUNSUPPORTED = -4  /* e.g. the DFE path at sps != 1 (undefined in the reference too) */
+};
+
+/* ConvType, reference sigProcLib.h:40-47 */
+enum { BTSDSP_FULL_SPAN = 0, BTSDSP_OVERLAP_ONLY = 1, BTSDSP_START_ONLY = 2, BTSDSP_WITH_TAIL = 3, BTSDSP_NO_DELAY = 4 };
+
+/* table ids for btsdsp_get_table (parity inspection of the init-time globals, sigProcLib.cpp:39-59) */
+enum {
+  BTSDSP_T_COS = 0, BTSDSP_T_SIN = 1,            /* 1025 floats */
+  BTSDSP_T_ROT = 2, BTSDSP_T_REVROT = 3,         /* 157*sps complex: GMSKRotation / GMSKReverseRotation */
+  BTSDSP_T_PULSE = 4,                            /* 2*sps+1 complex: generateGSMPulse(2, sps) */
+  BTSDSP_T_MID_SEQ = 5, BTSDSP_T_MID_META = 6,   /* idx = TSC: 16*sps complex ; {TOA, gain.re, gain.im} */
+  BTSDSP_T_RACH_SEQ = 7, BTSDSP_T_RACH_META = 8, /* 41*sps complex ; {TOA, gain.re, gain.im} */
+  BTSDSP_T_LPF_RX = 9, BTSDSP_T_LPF_TX = 10      /* 961 / 651 floats: createLPF(.,961,65) / createLPF(.,651,96) */
+};
+
+/* ---- lifetime.  Replaces sigProcLibSetup + generateGSMPulse + generateMidamble x8 +
+ * generateRACHSequence + the two createLPF calls (sigProcLib.cpp:227,411,779,830,1102;
+ * Transceiver.cpp:62-64,424,553; radioInterface.cpp:134-138,230-234).  sps in {1,2,4}. */
+int btsdsp_create(btsdsp_ctx **ctx, int device, int sps);
+int btsdsp_destroy(btsdsp_ctx *ctx);                       /* sigProcLibDestroy, sigProcLib.cpp:61 */
+const char *btsdsp_last_error(const btsdsp_ctx *ctx);      /* ctx may be NULL: error of the last failed create */
+int btsdsp_version(void);
+int btsdsp_device(const btsdsp_ctx *ctx);
+int btsdsp_sps(const btsdsp_ctx *ctx);
+/* copies table `id` (entry idx for the per-TSC ones) to dst; returns the number of floats, or <0 */
+int btsdsp_get_table(btsdsp_ctx *ctx, int id, int idx, float *dst, int cap);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+long long btsdsp_launch_count(const btsdsp_ctx *ctx);
+int btsdsp_synchronize(btsdsp_ctx *ctx);
+
+/* ---- layer 1: single vectors, HOST pointers, synchronous ------------------------------------- */
+/* convolve / correlate, sigProcLib.cpp:267 / :474.  Returns the output length (c needs cap >= it). */
+int btsdsp_convolve(btsdsp_ctx *ctx, const btsdsp_cf32 *a, int la, int a_real, const btsdsp_cf32 *b, int lb,
+                    int b_real, btsdsp_cf32 *c, int cap, int span_type);
+int btsdsp_correlate(btsdsp_ctx *ctx, const btsdsp_cf32 *a, int la, int a_real, const btsdsp_cf32 *b, int lb,
+                     int b_real, btsdsp_cf32 *c, int cap, int span_type);
+/* scaleVector :713 (in place) */
+int btsdsp_scale_vector(btsdsp_ctx *ctx, btsdsp_cf32 *v, int n, int real_only, btsdsp_cf32 scale);
+/* delayVector :573 (in place) */
+int btsdsp_delay_vector(btsdsp_ctx *ctx, btsdsp_cf32 *v, int n, float delay);
+/* peakDetect :663 ; interpolatePoint :639 ; energyDetect :916 */
+int btsdsp_peak_detect(btsdsp_ctx *ctx, const btsdsp_cf32 *v, int n, btsdsp_cf32 *peak, float *peak_index,
+                       float *avg_power);
+int btsdsp_interpolate_point(btsdsp_ctx *ctx, const btsdsp_cf32 *v, int n, float ix, btsdsp_cf32 *out);
+int btsdsp_energy_detect(btsdsp_ctx *ctx, const btsdsp_cf32 *v, int n, unsigned window, float threshold,
+                         float *avg_power, int *detected);
+/* modulateBurst :521 with the library's GSM pulse; out gets sps*(nbits+guard) samples; returns that length */
+int btsdsp_modulate_burst(btsdsp_ctx *ctx, const uint8_t *bits, int nbits, int guard, btsdsp_cf32 *out, int cap);
+/* analyzeTrafficBurst :935.  chan (6*sps) / chan_offset are written only when request_channel && *detected. */
+int btsdsp_analyze_traffic_burst(btsdsp_ctx *ctx, const btsdsp_cf32 *burst, int n, unsigned tsc, float threshold,
+                                 btsdsp_cf32 *amplitude, float *toa, int request_channel, btsdsp_cf32 *chan,
+                                 float *chan_offset, int *detected);
+/* detectRACHBurst :860 */
+int btsdsp_detect_rach_burst(btsdsp_ctx *ctx, const btsdsp_cf32 *burst, int n, float threshold,
+                             btsdsp_cf32 *amplitude, float *toa, int *detected);
+/* designDFE :1246 (w: nf taps, b: nchan-1 taps) */
+int btsdsp_design_dfe(btsdsp_ctx *ctx, const btsdsp_cf32 *chan, int nchan, float snr, int nf, btsdsp_cf32 *w,
+                      btsdsp_cf32 *b);
+/* equalizeBurst :1343; like the reference it leaves the delayed burst in `burst`; soft gets n values. sps 1, nw 7, nb 5 */
+int btsdsp_equalize_burst(btsdsp_ctx *ctx, btsdsp_cf32 *burst, int n, float toa, const btsdsp_cf32 *w, int nw,
+                          const btsdsp_cf32 *b, int nb, float *soft);
+/* demodulateBurst :1056; soft gets n/sps values; returns that count */
+int btsdsp_demodulate_burst(btsdsp_ctx *ctx, const btsdsp_cf32 *burst, int n, btsdsp_cf32 channel, float toa,
+                            float *soft);
+/* polyphaseResampleVector :1157 with the library's filters: lpf 0 = RX (961 taps), 1 = TX (651 taps).
+ * Returns the output length ceil(n*P/Q). */
+int btsdsp_polyphase_resample(btsdsp_ctx *ctx, const btsdsp_cf32 *x, int n, int P, int Q, int lpf, btsdsp_cf32 *out,
+                              int cap);
+
+/* ---- layer 2: batched, DEVICE pointers, asynchronous on `stream` (a cudaStream_t; NULL = default) ---- */
+/* Burst addressing shared by the batched receive calls:
+ *   pitch > 0 : burst i starts at bursts + i*pitch samples; its length is lens[i], or when lens == NULL
+ *               (157 if (first+i)%4==0 else 156)*sps -- the reference's slot rule, radioInterface.cpp:375-378
+ *   pitch == 0: `bursts` is a continuous slot stream beginning on a 157-sample slot; burst g = first+i
+ *               starts at ((g/4)*625 + {0,157,313,469}[g%4])*sps.                                     */
+
+/* GMSK modulate n bursts of nbits bits (n x nbits bytes).  guard < 0: 8 + ((first+i)%4==0) per burst
+ * (Transceiver.cpp:105-106).  pitch as above (pitch == 0 writes a continuous slot stream). */
+int btsdsp_modulate_dev(btsdsp_ctx *ctx, const uint8_t *bits, int nbits, long long n, int guard, long long first,
+                        btsdsp_cf32 *out, long long pitch, void *stream);
+/* RX resampler (radioInterface.cpp:238-259): nchunks chunks of 864 raw samples -> 585 each.
+ * has_history != 0: raw[-192..-1] hold the previous samples; 0: the stream starts here (zeros). */
+int btsdsp_resample_rx_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, int has_history, long long nchunks,
+                           btsdsp_cf32 *out, void *stream);
+/* TX resampler (radioInterface.cpp:123-168 + USRPifyVector :74-89): nchunks chunks of 585 samples ->
+ * 864 int16 {I,Q} pairs each, scaled by 13500 and truncated like the reference's (short) cast. */
+int btsdsp_resample_tx_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *in, int has_history, long long nchunks, int16_t *out,
+                           void *stream);
+/* Normal bursts, fused energy gate -> analyzeTrafficBurst(request channel) -> designDFE(Nf 7) ->
+ * equalizeBurst, the TSC branch of Transceiver::pullRadioVector (Transceiver.cpp:298-396) with a channel
+ * estimate per burst.  gate_thr < 0 disables the energy gate; snr_thr is the energy threshold in the
+ * SNR estimate (:340).  Outputs per burst (any may be NULL): flag, amp, toa, soft[soft_pitch] (zeros when
+ * not detected) and for inspection chan[6] (after 1/amp), chan_off, w[7], b[5].  sps must be 1. */
+int btsdsp_demod_normal_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens,
+                            long long first, const uint8_t *tsc, long long n, float detect_thr, float gate_thr,
+                            float snr_thr, int32_t *flag, btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch,
+                            btsdsp_cf32 *chan, float *chan_off, btsdsp_cf32 *w, btsdsp_cf32 *b, void *stream);
+/* analyzeTrafficBurst alone (any sps). chan: 6*sps per burst. */
+int btsdsp_analyze_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens,
+                       long long first, const uint8_t *tsc, long long n, float detect_thr, int request_channel,
+                       int32_t *flag, btsdsp_cf32 *amp, float *toa, btsdsp_cf32 *chan, float *chan_off, void *stream);
+/* Access bursts: detectRACHBurst, then demodulateBurst when soft != NULL (Transceiver.cpp:360-389). */
+int btsdsp_rach_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens, long long first,
+                    long long n, float detect_thr, int32_t *flag, btsdsp_cf32 *amp, float *toa, float *soft,
+                    int soft_pitch, void *stream);
+/* designDFE for n channel estimates (chan n x 6, snr n) -> w n x 7, b n x 5 */
+int btsdsp_design_dfe_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *chan, const float *snr, long long n, btsdsp_cf32 *w,
+                          btsdsp_cf32 *b, void *stream);
+/* equalizeBurst with supplied taps (the cached-DFE mode, Transceiver.cpp:391-396); burst_out may be NULL */
+int btsdsp_equalize_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens,
+                        long long first, long long n, const float *toa, const btsdsp_cf32 *w, const btsdsp_cf32 *b,
+                        float *soft, int soft_pitch, btsdsp_cf32 *burst_out, long long out_pitch, void *stream);
+/* demodulateBurst alone with supplied amp/toa (any sps) */
+int btsdsp_demodulate_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens,
+                          long long first, long long n, const btsdsp_cf32 *amp, const float *toa, float *soft,
+                          int soft_pitch, void *stream);
+
+/* ---- layer 3: batched, HOST pointers, synchronous (copies overlapped with kernels internally) ---- */
+/* The north-star receive path end to end: raw 400 kS/s complex stream (nchunks x 864 samples, starting at
+ * stream time 0) -> RX resample -> 157/156/156/156 slot cutting -> fused normal-burst demod of the first
+ * nbursts slots (needs 625*nbursts/4 <= 585*nchunks).  tsc: one byte per burst.  Outputs as in
+ * btsdsp_demod_normal_dev.  Host buffers may be pageable or pinned (pinned is faster). */
+int btsdsp_rx_stream_host(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nchunks, const uint8_t *tsc,
+                          long long nbursts, float detect_thr, float gate_thr, float snr_thr, int32_t *flag,
+                          btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch);
+/* The same on DEVICE-resident input and outputs (no copies): resample into an internal buffer, then demod. */
+int btsdsp_rx_stream_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nchunks, const uint8_t *tsc,
+                         long long nbursts, float detect_thr, float gate_thr, float snr_thr, int32_t *flag,
+                         btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch, void *stream);
+/* The transmit path: n x 148 bits -> modulateBurst (guard 8/9 by slot) -> slot stream -> TX resample ->
+ * int16 {I,Q}.  n must be a multiple of 4 and 625*n/4 a multiple of 585 (n % 468 == 0), giving
+ * 864*(625*n/4/585) output pairs.  Host pointers. */
+int btsdsp_tx_stream_host(btsdsp_ctx *ctx, const uint8_t *bits148, long long n, int16_t *out);
+int btsdsp_tx_stream_dev(btsdsp_ctx *ctx, const uint8_t *bits148, long long n, int16_t *out, void *stream);
+/* Batched normal-burst demod / RACH detect+demod over HOST buffers (pitched bursts). */
+int btsdsp_demod_normal_host(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens,
+                             const uint8_t *tsc, long long n, float detect_thr, float gate_thr, float snr_thr,
+                             int32_t *flag, btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch,
+                             btsdsp_cf32 *chan, float *chan_off, btsdsp_cf32 *w, btsdsp_cf32 *b);
+int btsdsp_rach_host(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens, long long n,
+                     float detect_thr, int32_t *flag, btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch);
+
+/* pinned host memory helpers for layer-3 callers */
+void *btsdsp_host_alloc(size_t bytes);
+void btsdsp_host_free(void *p);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* BTSDSP_H */

@@ -1,0 +1,343 @@
+"""ctypes binding of libbtsdsp.so (include/btsdsp.h) -- the Python face used by tests/ and bench.py.
+
+The product is the shared library; this module only marshals pointers.  Layer-1 methods mirror the
+reference's sigProcLib.h functions on numpy arrays (host pointers); the *_dev methods take anything with
+a `.data_ptr()` (torch CUDA tensors) or a raw integer device address, plus a CUDA stream handle; the
+*_host methods run the batched pipelines over host buffers (numpy, or pinned torch tensors).
+There is no CPU fallback: if the library is missing or no B200 is visible, construction raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbtsdsp.so")
+
+FULL_SPAN, OVERLAP_ONLY, START_ONLY, WITH_TAIL, NO_DELAY = 0, 1, 2, 3, 4
+T_COS, T_SIN, T_ROT, T_REVROT, T_PULSE, T_MID_SEQ, T_MID_META, T_RACH_SEQ, T_RACH_META, T_LPF_RX, T_LPF_TX = range(11)
+
+_vp, _i, _ll, _f, _u = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_uint
+
+
+class _cf32(ctypes.Structure):
+    _fields_ = [("re", _f), ("im", _f)]
+
+
+_SIGS = {
+    "btsdsp_create": (_i, [ctypes.POINTER(_vp), _i, _i]),
+    "btsdsp_destroy": (_i, [_vp]),
+    "btsdsp_last_error": (ctypes.c_char_p, [_vp]),
+    "btsdsp_version": (_i, []),
+    "btsdsp_device": (_i, [_vp]),
+    "btsdsp_sps": (_i, [_vp]),
+    "btsdsp_get_table": (_i, [_vp, _i, _i, _vp, _i]),
+    "btsdsp_launch_count": (_ll, [_vp]),
+    "btsdsp_synchronize": (_i, [_vp]),
+    "btsdsp_convolve": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i]),
+    "btsdsp_correlate": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i]),
+    "btsdsp_scale_vector": (_i, [_vp, _vp, _i, _i, _cf32]),
+    "btsdsp_delay_vector": (_i, [_vp, _vp, _i, _f]),
+    "btsdsp_peak_detect": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "btsdsp_interpolate_point": (_i, [_vp, _vp, _i, _f, _vp]),
+    "btsdsp_energy_detect": (_i, [_vp, _vp, _i, _u, _f, _vp, _vp]),
+    "btsdsp_modulate_burst": (_i, [_vp, _vp, _i, _i, _vp, _i]),
+    "btsdsp_analyze_traffic_burst": (_i, [_vp, _vp, _i, _u, _f, _vp, _vp, _i, _vp, _vp, _vp]),
+    "btsdsp_detect_rach_burst": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp]),
+    "btsdsp_design_dfe": (_i, [_vp, _vp, _i, _f, _i, _vp, _vp]),
+    "btsdsp_equalize_burst": (_i, [_vp, _vp, _i, _f, _vp, _i, _vp, _i, _vp]),
+    "btsdsp_demodulate_burst": (_i, [_vp, _vp, _i, _cf32, _f, _vp]),
+    "btsdsp_polyphase_resample": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i]),
+    "btsdsp_modulate_dev": (_i, [_vp, _vp, _i, _ll, _i, _ll, _vp, _ll, _vp]),
+    "btsdsp_resample_rx_dev": (_i, [_vp, _vp, _i, _ll, _vp, _vp]),
+    "btsdsp_resample_tx_dev": (_i, [_vp, _vp, _i, _ll, _vp, _vp]),
+    "btsdsp_demod_normal_dev": (_i, [_vp, _vp, _ll, _vp, _ll, _vp, _ll, _f, _f, _f, _vp, _vp, _vp, _vp, _i, _vp, _vp,
+                                     _vp, _vp, _vp]),
+    "btsdsp_analyze_dev": (_i, [_vp, _vp, _ll, _vp, _ll, _vp, _ll, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "btsdsp_rach_dev": (_i, [_vp, _vp, _ll, _vp, _ll, _ll, _f, _vp, _vp, _vp, _vp, _i, _vp]),
+    "btsdsp_design_dfe_dev": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _vp]),
+    "btsdsp_equalize_dev": (_i, [_vp, _vp, _ll, _vp, _ll, _ll, _vp, _vp, _vp, _vp, _i, _vp, _ll, _vp]),
+    "btsdsp_demodulate_dev": (_i, [_vp, _vp, _ll, _vp, _ll, _ll, _vp, _vp, _vp, _i, _vp]),
+    "btsdsp_rx_stream_host": (_i, [_vp, _vp, _ll, _vp, _ll, _f, _f, _f, _vp, _vp, _vp, _vp, _i]),
+    "btsdsp_rx_stream_dev": (_i, [_vp, _vp, _ll, _vp, _ll, _f, _f, _f, _vp, _vp, _vp, _vp, _i, _vp]),
+    "btsdsp_tx_stream_host": (_i, [_vp, _vp, _ll, _vp]),
+    "btsdsp_tx_stream_dev": (_i, [_vp, _vp, _ll, _vp, _vp]),
+    "btsdsp_demod_normal_host": (_i, [_vp, _vp, _ll, _vp, _vp, _ll, _f, _f, _f, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp,
+                                      _vp]),
+    "btsdsp_rach_host": (_i, [_vp, _vp, _ll, _vp, _ll, _f, _vp, _vp, _vp, _vp, _i]),
+    "btsdsp_host_alloc": (_vp, [ctypes.c_size_t]),
+    "btsdsp_host_free": (None, [_vp]),
+}
+
+EXPORTS = sorted(_SIGS)
+_lib = None
+
+
+def load_library():
+    """dlopen libbtsdsp.so and declare every prototype.  Raises if the library was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libbtsdsp.so is not built (run `python -m openbts_ttsou_b200.build`); "
+                               "there is no CPU fallback")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class BtsDspError(RuntimeError):
+    pass
+
+
+def _p(a):
+    """address of a numpy array / torch tensor / int / None"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+def _c64(a):
+    return np.ascontiguousarray(a, dtype=np.complex64)
+
+
+def _stream(stream):
+    if stream is None:
+        return None
+    return getattr(stream, "cuda_stream", stream)
+
+
+class BtsDsp:
+    """One context = one GPU + one samples-per-symbol setting (btsdsp_create)."""
+
+    def __init__(self, device=0, sps=1):
+        self.lib = load_library()
+        h = _vp()
+        rc = self.lib.btsdsp_create(ctypes.byref(h), device, sps)
+        if rc != 0:
+            raise BtsDspError("btsdsp_create failed (%d): %s" % (rc, self.lib.btsdsp_last_error(None).decode()))
+        self.h = h
+        self.sps = sps
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.btsdsp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise BtsDspError("btsdsp error %d: %s" % (rc, self.lib.btsdsp_last_error(self.h).decode()))
+        return rc
+
+    @property
+    def launch_count(self):
+        return int(self.lib.btsdsp_launch_count(self.h))
+
+    def synchronize(self):
+        self._ck(self.lib.btsdsp_synchronize(self.h))
+
+    def table(self, tid, idx=0):
+        buf = np.zeros(4096, np.float32)
+        n = self._ck(self.lib.btsdsp_get_table(self.h, tid, idx, _p(buf), buf.size))
+        out = buf[:n].copy()
+        if tid in (T_ROT, T_REVROT, T_PULSE, T_MID_SEQ, T_RACH_SEQ):
+            return out.view(np.complex64)
+        return out
+
+    # ---- layer 1: the sigProcLib.h functions on host vectors -------------------------------------
+    def _conv(self, fn, a, b, span, a_real, b_real):
+        a, b = _c64(a), _c64(b)
+        out = np.zeros(a.size + b.size + 2, np.complex64)
+        n = self._ck(fn(self.h, _p(a), a.size, int(a_real), _p(b), b.size, int(b_real), _p(out), out.size, span))
+        return out[:n].copy()
+
+    def convolve(self, a, b, span, a_real=False, b_real=False):
+        return self._conv(self.lib.btsdsp_convolve, a, b, span, a_real, b_real)
+
+    def correlate(self, a, b, span, a_real=False, b_real=False):
+        return self._conv(self.lib.btsdsp_correlate, a, b, span, a_real, b_real)
+
+    def scale_vector(self, v, scale, real_only=False):
+        v = _c64(v).copy()
+        s = complex(scale)
+        self._ck(self.lib.btsdsp_scale_vector(self.h, _p(v), v.size, int(real_only), _cf32(s.real, s.imag)))
+        return v
+
+    def delay_vector(self, v, delay):
+        v = _c64(v).copy()
+        self._ck(self.lib.btsdsp_delay_vector(self.h, _p(v), v.size, float(delay)))
+        return v
+
+    def peak_detect(self, v):
+        v = _c64(v)
+        pk = np.zeros(1, np.complex64)
+        r = np.zeros(2, np.float32)
+        self._ck(self.lib.btsdsp_peak_detect(self.h, _p(v), v.size, _p(pk), _p(r[0:]), _p(r[1:])))
+        return pk[0], float(r[0]), float(r[1])
+
+    def interpolate_point(self, v, ix):
+        v = _c64(v)
+        pk = np.zeros(1, np.complex64)
+        self._ck(self.lib.btsdsp_interpolate_point(self.h, _p(v), v.size, float(ix), _p(pk)))
+        return pk[0]
+
+    def energy_detect(self, v, win, thr):
+        v = _c64(v)
+        avg = np.zeros(1, np.float32)
+        det = np.zeros(1, np.int32)
+        self._ck(self.lib.btsdsp_energy_detect(self.h, _p(v), v.size, int(win), float(thr), _p(avg), _p(det)))
+        return bool(det[0]), float(avg[0])
+
+    def modulate(self, bits, guard):
+        bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        out = np.zeros(self.sps * (bits.size + guard), np.complex64)
+        n = self._ck(self.lib.btsdsp_modulate_burst(self.h, _p(bits), bits.size, guard, _p(out), out.size))
+        assert n == out.size
+        return out
+
+    def analyze(self, burst, tsc, thr, request=True):
+        burst = _c64(burst)
+        amp = np.zeros(1, np.complex64)
+        chan = np.zeros(6 * self.sps, np.complex64)
+        r = np.zeros(2, np.float32)
+        det = np.zeros(1, np.int32)
+        self._ck(self.lib.btsdsp_analyze_traffic_burst(self.h, _p(burst), burst.size, int(tsc), float(thr), _p(amp),
+                                                       _p(r[0:]), int(request), _p(chan), _p(r[1:]), _p(det)))
+        return bool(det[0]), amp[0], float(r[0]), chan, float(r[1])
+
+    def detect_rach(self, burst, thr):
+        burst = _c64(burst)
+        amp = np.zeros(1, np.complex64)
+        toa = np.zeros(1, np.float32)
+        det = np.zeros(1, np.int32)
+        self._ck(self.lib.btsdsp_detect_rach_burst(self.h, _p(burst), burst.size, float(thr), _p(amp), _p(toa), _p(det)))
+        return bool(det[0]), amp[0], float(toa[0])
+
+    def design_dfe(self, chan, snr, nf=7):
+        chan = _c64(chan)
+        w = np.zeros(nf, np.complex64)
+        b = np.zeros(max(chan.size - 1, 1), np.complex64)
+        self._ck(self.lib.btsdsp_design_dfe(self.h, _p(chan), chan.size, float(snr), nf, _p(w), _p(b)))
+        return w, b[:chan.size - 1]
+
+    def equalize(self, burst, toa, w, b):
+        """returns (soft, burst_after): like the reference, the burst is delayed in place"""
+        burst = _c64(burst).copy()
+        w, b = _c64(w), _c64(b)
+        soft = np.zeros(burst.size, np.float32)
+        self._ck(self.lib.btsdsp_equalize_burst(self.h, _p(burst), burst.size, float(toa), _p(w), w.size, _p(b), b.size,
+                                                _p(soft)))
+        return soft, burst
+
+    def demodulate(self, burst, amp, toa):
+        burst = _c64(burst)
+        soft = np.zeros(burst.size, np.float32)
+        a = complex(amp)
+        n = self._ck(self.lib.btsdsp_demodulate_burst(self.h, _p(burst), burst.size, _cf32(a.real, a.imag), float(toa),
+                                                      _p(soft)))
+        return soft[:n].copy()
+
+    def resample(self, x, P, Q, lpf):
+        x = _c64(x)
+        out = np.zeros(int(np.ceil(x.size * P / Q)) + 4, np.complex64)
+        n = self._ck(self.lib.btsdsp_polyphase_resample(self.h, _p(x), x.size, P, Q, lpf, _p(out), out.size))
+        return out[:n].copy()
+
+    # ---- layer 2: device pointers ------------------------------------------------------------------
+    def modulate_dev(self, bits, nbits, n, out, pitch, guard=-1, first=0, stream=None):
+        self._ck(self.lib.btsdsp_modulate_dev(self.h, _p(bits), nbits, n, guard, first, _p(out), pitch, _stream(stream)))
+
+    def resample_rx_dev(self, raw, nchunks, out, has_history=False, stream=None):
+        self._ck(self.lib.btsdsp_resample_rx_dev(self.h, _p(raw), int(has_history), nchunks, _p(out), _stream(stream)))
+
+    def resample_tx_dev(self, x, nchunks, out, has_history=False, stream=None):
+        self._ck(self.lib.btsdsp_resample_tx_dev(self.h, _p(x), int(has_history), nchunks, _p(out), _stream(stream)))
+
+    def demod_normal_dev(self, bursts, pitch, tsc, n, flag, amp, toa, soft, soft_pitch=160, lens=None, first=0,
+                         detect_thr=3.0, gate_thr=-1.0, snr_thr=250.0, chan=None, off=None, w=None, b=None, stream=None):
+        self._ck(self.lib.btsdsp_demod_normal_dev(self.h, _p(bursts), pitch, _p(lens), first, _p(tsc), n, detect_thr,
+                                                  gate_thr, snr_thr, _p(flag), _p(amp), _p(toa), _p(soft), soft_pitch,
+                                                  _p(chan), _p(off), _p(w), _p(b), _stream(stream)))
+
+    def analyze_dev(self, bursts, pitch, tsc, n, flag, amp, toa, chan=None, off=None, lens=None, first=0,
+                    detect_thr=3.0, request=True, stream=None):
+        self._ck(self.lib.btsdsp_analyze_dev(self.h, _p(bursts), pitch, _p(lens), first, _p(tsc), n, detect_thr,
+                                             int(request), _p(flag), _p(amp), _p(toa), _p(chan), _p(off), _stream(stream)))
+
+    def rach_dev(self, bursts, pitch, n, flag, amp, toa, soft=None, soft_pitch=160, lens=None, first=0, detect_thr=5.0,
+                 stream=None):
+        self._ck(self.lib.btsdsp_rach_dev(self.h, _p(bursts), pitch, _p(lens), first, n, detect_thr, _p(flag), _p(amp),
+                                          _p(toa), _p(soft), soft_pitch, _stream(stream)))
+
+    def design_dfe_dev(self, chan, snr, n, w, b, stream=None):
+        self._ck(self.lib.btsdsp_design_dfe_dev(self.h, _p(chan), _p(snr), n, _p(w), _p(b), _stream(stream)))
+
+    def equalize_dev(self, bursts, pitch, n, toa, w, b, soft, soft_pitch=160, burst_out=None, out_pitch=0, lens=None,
+                     first=0, stream=None):
+        self._ck(self.lib.btsdsp_equalize_dev(self.h, _p(bursts), pitch, _p(lens), first, n, _p(toa), _p(w), _p(b),
+                                              _p(soft), soft_pitch, _p(burst_out), out_pitch, _stream(stream)))
+
+    def demodulate_dev(self, bursts, pitch, n, amp, toa, soft, soft_pitch=160, lens=None, first=0, stream=None):
+        self._ck(self.lib.btsdsp_demodulate_dev(self.h, _p(bursts), pitch, _p(lens), first, n, _p(amp), _p(toa), _p(soft),
+                                                soft_pitch, _stream(stream)))
+
+    def rx_stream_dev(self, raw, nchunks, tsc, nbursts, flag, amp, toa, soft, soft_pitch=148, detect_thr=3.0,
+                      gate_thr=-1.0, snr_thr=250.0, stream=None):
+        self._ck(self.lib.btsdsp_rx_stream_dev(self.h, _p(raw), nchunks, _p(tsc), nbursts, detect_thr, gate_thr, snr_thr,
+                                               _p(flag), _p(amp), _p(toa), _p(soft), soft_pitch, _stream(stream)))
+
+    def tx_stream_dev(self, bits148, n, out, stream=None):
+        self._ck(self.lib.btsdsp_tx_stream_dev(self.h, _p(bits148), n, _p(out), _stream(stream)))
+
+    # ---- layer 3: host buffers ---------------------------------------------------------------------
+    def rx_stream_host(self, raw, nchunks, tsc, nbursts, flag, amp, toa, soft, soft_pitch=148, detect_thr=3.0,
+                       gate_thr=-1.0, snr_thr=250.0):
+        self._ck(self.lib.btsdsp_rx_stream_host(self.h, _p(raw), nchunks, _p(tsc), nbursts, detect_thr, gate_thr, snr_thr,
+                                                _p(flag), _p(amp), _p(toa), _p(soft), soft_pitch))
+
+    def tx_stream_host(self, bits148, n, out):
+        self._ck(self.lib.btsdsp_tx_stream_host(self.h, _p(bits148), n, _p(out)))
+
+    def demod_normal_host(self, bursts, lens, tsc, detect_thr=3.0, gate_thr=-1.0, snr_thr=250.0, debug=True,
+                          soft_pitch=160):
+        """bursts (n, pitch) complex64 -> dict(flag, amp, toa, soft[, chan, off, w, b])"""
+        bursts = _c64(bursts)
+        n, pitch = bursts.shape
+        lens = None if lens is None else np.ascontiguousarray(lens, np.int32)
+        tsc = np.ascontiguousarray(tsc, np.uint8)
+        r = dict(flag=np.zeros(n, np.int32), amp=np.zeros(n, np.complex64), toa=np.zeros(n, np.float32),
+                 soft=np.zeros((n, soft_pitch), np.float32))
+        if debug:
+            r.update(chan=np.zeros((n, 6), np.complex64), off=np.zeros(n, np.float32),
+                     w=np.zeros((n, 7), np.complex64), b=np.zeros((n, 5), np.complex64))
+        self._ck(self.lib.btsdsp_demod_normal_host(
+            self.h, _p(bursts), pitch, _p(lens), _p(tsc), n, detect_thr, gate_thr, snr_thr, _p(r["flag"]), _p(r["amp"]),
+            _p(r["toa"]), _p(r["soft"]), soft_pitch, _p(r.get("chan")), _p(r.get("off")), _p(r.get("w")), _p(r.get("b"))))
+        return r
+
+    def rach_host(self, bursts, lens, detect_thr=5.0, demod=True, soft_pitch=160):
+        bursts = _c64(bursts)
+        n, pitch = bursts.shape
+        lens = None if lens is None else np.ascontiguousarray(lens, np.int32)
+        r = dict(flag=np.zeros(n, np.int32), amp=np.zeros(n, np.complex64), toa=np.zeros(n, np.float32))
+        if demod:
+            r["soft"] = np.zeros((n, soft_pitch), np.float32)
+        self._ck(self.lib.btsdsp_rach_host(self.h, _p(bursts), pitch, _p(lens), n, detect_thr, _p(r["flag"]),
+                                           _p(r["amp"]), _p(r["toa"]), _p(r.get("soft")), soft_pitch))
+        return r

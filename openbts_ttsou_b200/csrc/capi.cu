@@ -1,0 +1,829 @@
+// capi.cu -- the extern "C" surface declared in include/btsdsp.h: context, table construction,
+// single-vector calls (host pointers), batched calls (device pointers), host-buffer pipelines.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/btsdsp.h"
+#include "kernels.cuh"
+#include "tables_host.h"
+
+using namespace btsdsp;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct btsdsp_ctx {
+  int device = 0, sps = 1;
+  DevTables *T = nullptr;       // device
+  DevTables *hT = nullptr;      // host mirror (pinned)
+  cudaStream_t st = nullptr, st_in = nullptr, st_out = nullptr;
+  std::string err;
+  long long launches = 0;
+  DevBuf buf[12];               // grow-only device scratch, by role
+  DevBuf pin[4];                // grow-only pinned staging
+  std::vector<cudaEvent_t> events;
+};
+
+namespace {
+
+enum { B_A = 0, B_B, B_C, B_D, B_SCRATCH, B_RAW, B_RES, B_FLAG, B_AMP, B_TOA, B_SOFT, B_TSC };
+
+int fail(btsdsp_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess) {
+  char msg[512];
+  if (e != cudaSuccess) snprintf(msg, sizeof msg, "%s: %s", what, cudaGetErrorString(e));
+  else snprintf(msg, sizeof msg, "%s", what);
+  if (c) c->err = msg; else g_create_error = msg;
+  return code;
+}
+
+#define CK(call)                                                          \
+  do {                                                                    \
+    cudaError_t e__ = (call);                                             \
+    if (e__ != cudaSuccess) return fail(ctx, BTSDSP_ECUDA, #call, e__);   \
+  } while (0)
+
+#define ARG(cond)                                                                 \
+  do {                                                                            \
+    if (!(cond)) return fail(ctx, BTSDSP_EINVAL, "invalid argument: " #cond);     \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int grow(btsdsp_ctx *ctx, DevBuf &b, size_t bytes, bool pinned = false) {
+  if (bytes <= b.cap) return BTSDSP_OK;
+  size_t want = bytes + bytes / 8 + 256;
+  if (b.p) { if (pinned) cudaFreeHost(b.p); else cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+  cudaError_t e = pinned ? cudaMallocHost(&b.p, want) : cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) { b.p = nullptr; return fail(ctx, BTSDSP_ENOMEM, pinned ? "cudaMallocHost" : "cudaMalloc", e); }
+  b.cap = want;
+  return BTSDSP_OK;
+}
+#define GROW(slot, bytes)                                         \
+  do {                                                            \
+    int r__ = grow(ctx, ctx->buf[slot], (bytes));                 \
+    if (r__ != BTSDSP_OK) return r__;                             \
+  } while (0)
+
+template <class Tp> Tp *dbuf(btsdsp_ctx *ctx, int slot) { return (Tp *)ctx->buf[slot].p; }
+
+int check_launch(btsdsp_ctx *ctx, const char *what, int nlaunch = 1) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ctx, BTSDSP_ECUDA, what, e);
+  ctx->launches += nlaunch;
+  return BTSDSP_OK;
+}
+#define LAUNCHED(what, n)                              \
+  do {                                                 \
+    int r__ = check_launch(ctx, what, n);              \
+    if (r__ != BTSDSP_OK) return r__;                  \
+  } while (0)
+
+// Everything the reference computes at start-up.  Host: the libm-in-double parts (trig tables :207-212,
+// pulse :411-430) and the filter scaling; device: everything that is float arithmetic over the tables
+// (rotation tables, sinc grid, midamble / RACH autocorrelation peaks) -- through the product's own kernels.
+int build_tables(btsdsp_ctx *ctx) {
+  DevTables *h = ctx->hT;
+  const int sps = ctx->sps;
+  host_fill_tables(h, sps);
+
+  CK(cudaMemcpyAsync(ctx->T, h, sizeof(DevTables), cudaMemcpyHostToDevice, ctx->st));
+  launch_init_tables(ctx->T, ctx->st);
+  LAUNCHED("init tables", 2);
+
+  // generateMidamble :779-828 and generateRACHSequence :830-857 on the device
+  GROW(B_A, 64 * kMaxSps * sizeof(cf));
+  GROW(B_B, 64 * kMaxSps * sizeof(cf));
+  GROW(B_C, 64 * kMaxSps * sizeof(cf));
+  GROW(B_D, 256);
+  cf *dMid = dbuf<cf>(ctx, B_A), *dFull = dbuf<cf>(ctx, B_B), *dAc = dbuf<cf>(ctx, B_C);
+  uint8_t *dBits = dbuf<uint8_t>(ctx, B_D);
+  cf *dPeak = (cf *)(dBits + 64);
+  float *dIdx = (float *)(dBits + 128);
+  for (int t = 0; t < 8; t++) {
+    uint8_t bits[26];
+    for (int i = 0; i < 26; i++) bits[i] = kTSC[t][i] == '1';
+    CK(cudaMemcpyAsync(dBits, bits, 26, cudaMemcpyHostToDevice, ctx->st));
+    const int nmid = 16 * sps, nfull = 26 * sps;
+    launch_modulate_impulse(ctx->T, dBits + 5, 16, dMid, ctx->st);                                  // :794-797
+    launch_modulate(ctx->T, dBits, 26, 1, 0, nullptr, 0, dFull, nfull, ctx->st);                    // :798-801
+    launch_scale_vector(dMid, nmid, 0, mk(-1.0F, 0.0F), ctx->st);                                   // :811
+    launch_scale_vector(dFull, nfull, 0, mk(0.0F, 1.0F), ctx->st);                                  // :812
+    launch_convolve(dFull, nfull, 0, dMid, nmid, 0, dAc, (nmid % 2) ? nmid / 2 : nmid / 2 - 1, nfull, 1, ctx->st);  // :814
+    launch_peak_detect(ctx->T, dAc, nfull, dPeak, dIdx, nullptr, ctx->st);                          // :821
+    LAUNCHED("midamble init", 6);
+    cf gain; float toa;
+    CK(cudaMemcpyAsync(&gain, dPeak, sizeof(cf), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(&toa, dIdx, sizeof(float), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(ctx->T->mid_seq[t], dMid, nmid * sizeof(cf), cudaMemcpyDeviceToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    toa = toa - (float)(5 * sps);                                                                   // :822
+    CK(cudaMemcpy(&ctx->T->mid_toa[t], &toa, sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(&ctx->T->mid_gain[t], &gain, sizeof(cf), cudaMemcpyHostToDevice));
+  }
+  {
+    uint8_t bits[41];
+    for (int i = 0; i < 41; i++) bits[i] = kRACH[i] == '1';
+    CK(cudaMemcpyAsync(dBits, bits, 41, cudaMemcpyHostToDevice, ctx->st));
+    const int n = 41 * sps;
+    launch_modulate(ctx->T, dBits, 41, 1, 0, nullptr, 0, dFull, n, ctx->st);                        // :837-840
+    launch_convolve(dFull, n, 0, dFull, n, 0, dAc, (n % 2) ? n / 2 : n / 2 - 1, n, 1, ctx->st);      // :844
+    launch_peak_detect(ctx->T, dAc, n, dPeak, dIdx, nullptr, ctx->st);                              // :851
+    LAUNCHED("rach init", 3);
+    cf gain; float toa;
+    CK(cudaMemcpyAsync(&gain, dPeak, sizeof(cf), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(&toa, dIdx, sizeof(float), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(ctx->T->rach_seq, dFull, n * sizeof(cf), cudaMemcpyDeviceToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaMemcpy(&ctx->T->rach_toa, &toa, sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(&ctx->T->rach_gain, &gain, sizeof(cf), cudaMemcpyHostToDevice));
+  }
+  CK(cudaMemcpy(h, ctx->T, sizeof(DevTables), cudaMemcpyDeviceToHost));
+  return BTSDSP_OK;
+}
+
+BurstSrc make_src(const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens, long long first, int sps) {
+  BurstSrc s;
+  s.base = (const cf *)bursts; s.pitch = pitch; s.lens = lens; s.first = first; s.sps = sps;
+  return s;
+}
+
+int conv_sizes(int la, int lb, int span, int *start, int *outsz) {   // sigProcLib.cpp:278-304
+  switch (span) {
+    case BTSDSP_FULL_SPAN:    *start = 0;  *outsz = la + lb - 1; break;
+    case BTSDSP_OVERLAP_ONLY: *start = la; *outsz = abs(la - lb) + 1; break;
+    case BTSDSP_START_ONLY:   *start = 0;  *outsz = la; break;
+    case BTSDSP_WITH_TAIL:    *start = lb; *outsz = la; break;
+    case BTSDSP_NO_DELAY:     *start = (lb % 2) ? lb / 2 : lb / 2 - 1; *outsz = la; break;
+    default: return -1;
+  }
+  return 0;
+}
+
+int conv_or_corr(btsdsp_ctx *ctx, int corr, const btsdsp_cf32 *a, int la, int a_real, const btsdsp_cf32 *b, int lb,
+                 int b_real, btsdsp_cf32 *c, int cap, int span) {
+  ARG(ctx && a && b && la > 0 && lb > 0);
+  int start, outsz;
+  if (conv_sizes(la, lb, span, &start, &outsz)) return fail(ctx, BTSDSP_EINVAL, "unknown span type");
+  if (cap < outsz || !c) return outsz;
+  DeviceGuard g(ctx->device);
+  GROW(B_A, la * sizeof(cf)); GROW(B_B, lb * sizeof(cf)); GROW(B_C, outsz * sizeof(cf));
+  CK(cudaMemcpyAsync(dbuf<cf>(ctx, B_A), a, la * sizeof(cf), cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(dbuf<cf>(ctx, B_B), b, lb * sizeof(cf), cudaMemcpyHostToDevice, ctx->st));
+  launch_convolve(dbuf<cf>(ctx, B_A), la, a_real, dbuf<cf>(ctx, B_B), lb, b_real, dbuf<cf>(ctx, B_C), start, outsz, corr,
+                  ctx->st);
+  LAUNCHED("convolve", 1);
+  CK(cudaMemcpyAsync(c, dbuf<cf>(ctx, B_C), outsz * sizeof(cf), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return outsz;
+}
+
+}  // namespace
+
+extern "C" {
+
+int btsdsp_version(void) { return 100; }
+
+int btsdsp_create(btsdsp_ctx **out, int device, int sps) {
+  btsdsp_ctx *ctx = nullptr;
+  if (!out) return fail(nullptr, BTSDSP_EINVAL, "ctx pointer is null");
+  *out = nullptr;
+  if (!(sps == 1 || sps == 2 || sps == 4)) return fail(nullptr, BTSDSP_EINVAL, "sps must be 1, 2 or 4");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, BTSDSP_ECUDA, "no CUDA device: this library has no CPU fallback", e);
+  if (device < 0 || device >= ndev) return fail(nullptr, BTSDSP_EINVAL, "device index out of range");
+  DeviceGuard g(device);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(nullptr, BTSDSP_ECUDA, "cudaGetDeviceProperties", e);
+  if (prop.major < 10) return fail(nullptr, BTSDSP_ECUDA, "device is not sm_100 (B200) class; kernels are built for sm_100a only");
+  ctx = new btsdsp_ctx;
+  ctx->device = device;
+  ctx->sps = sps;
+  int rc = BTSDSP_OK;
+  auto setup = [&]() -> int {
+    CK(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->st_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->st_out, cudaStreamNonBlocking));
+    CK(cudaMalloc(&ctx->T, sizeof(DevTables)));
+    CK(cudaMallocHost(&ctx->hT, sizeof(DevTables)));
+    int ce = configure_kernels();
+    if (ce) return fail(ctx, BTSDSP_ECUDA, "cudaFuncSetAttribute", (cudaError_t)ce);
+    return build_tables(ctx);
+  };
+  rc = setup();
+  if (rc != BTSDSP_OK) {
+    g_create_error = ctx->err;
+    btsdsp_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return BTSDSP_OK;
+}
+
+int btsdsp_destroy(btsdsp_ctx *ctx) {
+  if (!ctx) return BTSDSP_OK;
+  DeviceGuard g(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto &b : ctx->buf) if (b.p) cudaFree(b.p);
+  for (auto &b : ctx->pin) if (b.p) cudaFreeHost(b.p);
+  for (auto ev : ctx->events) cudaEventDestroy(ev);
+  if (ctx->T) cudaFree(ctx->T);
+  if (ctx->hT) cudaFreeHost(ctx->hT);
+  if (ctx->st) cudaStreamDestroy(ctx->st);
+  if (ctx->st_in) cudaStreamDestroy(ctx->st_in);
+  if (ctx->st_out) cudaStreamDestroy(ctx->st_out);
+  delete ctx;
+  return BTSDSP_OK;
+}
+
+const char *btsdsp_last_error(const btsdsp_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+int btsdsp_device(const btsdsp_ctx *ctx) { return ctx ? ctx->device : -1; }
+int btsdsp_sps(const btsdsp_ctx *ctx) { return ctx ? ctx->sps : -1; }
+long long btsdsp_launch_count(const btsdsp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int btsdsp_synchronize(btsdsp_ctx *ctx) {
+  ARG(ctx);
+  DeviceGuard g(ctx->device);
+  CK(cudaDeviceSynchronize());
+  return BTSDSP_OK;
+}
+
+int btsdsp_get_table(btsdsp_ctx *ctx, int id, int idx, float *dst, int cap) {
+  ARG(ctx);
+  const DevTables *h = ctx->hT;
+  const int sps = ctx->sps;
+  const void *src = nullptr;
+  int n = 0;
+  float meta[3];
+  switch (id) {
+    case BTSDSP_T_COS: src = h->cosT; n = kTrig + 1; break;
+    case BTSDSP_T_SIN: src = h->sinT; n = kTrig + 1; break;
+    case BTSDSP_T_ROT: src = h->rot; n = 2 * 157 * sps; break;
+    case BTSDSP_T_REVROT: src = h->revrot; n = 2 * 157 * sps; break;
+    case BTSDSP_T_PULSE: src = h->pulse; n = 2 * h->pulse_len; break;
+    case BTSDSP_T_MID_SEQ: ARG(idx >= 0 && idx < 8); src = h->mid_seq[idx]; n = 2 * 16 * sps; break;
+    case BTSDSP_T_MID_META:
+      ARG(idx >= 0 && idx < 8);
+      meta[0] = h->mid_toa[idx]; meta[1] = h->mid_gain[idx].x; meta[2] = h->mid_gain[idx].y; src = meta; n = 3; break;
+    case BTSDSP_T_RACH_SEQ: src = h->rach_seq; n = 2 * 41 * sps; break;
+    case BTSDSP_T_RACH_META:
+      meta[0] = h->rach_toa; meta[1] = h->rach_gain.x; meta[2] = h->rach_gain.y; src = meta; n = 3; break;
+    case BTSDSP_T_LPF_RX: src = h->lpf_rx; n = kRxTaps; break;
+    case BTSDSP_T_LPF_TX: src = h->lpf_tx; n = kTxTaps; break;
+    default: return fail(ctx, BTSDSP_EINVAL, "unknown table id");
+  }
+  if (dst && cap >= n) memcpy(dst, src, n * sizeof(float));
+  return n;
+}
+
+void *btsdsp_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+void btsdsp_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---- layer 1 ---------------------------------------------------------------------------------------
+int btsdsp_convolve(btsdsp_ctx *ctx, const btsdsp_cf32 *a, int la, int a_real, const btsdsp_cf32 *b, int lb, int b_real,
+                    btsdsp_cf32 *c, int cap, int span) {
+  return conv_or_corr(ctx, 0, a, la, a_real, b, lb, b_real, c, cap, span);
+}
+int btsdsp_correlate(btsdsp_ctx *ctx, const btsdsp_cf32 *a, int la, int a_real, const btsdsp_cf32 *b, int lb, int b_real,
+                     btsdsp_cf32 *c, int cap, int span) {
+  return conv_or_corr(ctx, 1, a, la, a_real, b, lb, b_real, c, cap, span);
+}
+
+int btsdsp_scale_vector(btsdsp_ctx *ctx, btsdsp_cf32 *v, int n, int real_only, btsdsp_cf32 scale) {
+  ARG(ctx && v && n > 0);
+  DeviceGuard g(ctx->device);
+  GROW(B_A, n * sizeof(cf));
+  CK(cudaMemcpyAsync(dbuf<cf>(ctx, B_A), v, n * sizeof(cf), cudaMemcpyHostToDevice, ctx->st));
+  launch_scale_vector(dbuf<cf>(ctx, B_A), n, real_only, mk(scale.re, scale.im), ctx->st);
+  LAUNCHED("scale_vector", 1);
+  CK(cudaMemcpyAsync(v, dbuf<cf>(ctx, B_A), n * sizeof(cf), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return BTSDSP_OK;
+}
+
+int btsdsp_delay_vector(btsdsp_ctx *ctx, btsdsp_cf32 *v, int n, float delay) {
+  ARG(ctx && v && n > 0);
+  DeviceGuard g(ctx->device);
+  GROW(B_A, n * sizeof(cf)); GROW(B_B, n * sizeof(cf));
+  CK(cudaMemcpyAsync(dbuf<cf>(ctx, B_A), v, n * sizeof(cf), cudaMemcpyHostToDevice, ctx->st));
+  launch_delay_vector(ctx->T, dbuf<cf>(ctx, B_A), n, delay, dbuf<cf>(ctx, B_B), ctx->st);
+  LAUNCHED("delay_vector", 2);
+  CK(cudaMemcpyAsync(v, dbuf<cf>(ctx, B_A), n * sizeof(cf), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return BTSDSP_OK;
+}
+
+int btsdsp_peak_detect(btsdsp_ctx *ctx, const btsdsp_cf32 *v, int n, btsdsp_cf32 *peak, float *peak_index,
+                       float *avg_power) {
+  ARG(ctx && v && n > 1 && peak);
+  DeviceGuard g(ctx->device);
+  GROW(B_A, n * sizeof(cf)); GROW(B_D, 256);
+  cf *dp = dbuf<cf>(ctx, B_D);
+  float *di = (float *)(dp + 1), *da = di + 1;
+  CK(cudaMemcpyAsync(dbuf<cf>(ctx, B_A), v, n * sizeof(cf), cudaMemcpyHostToDevice, ctx->st));
+  launch_peak_detect(ctx->T, dbuf<cf>(ctx, B_A), n, dp, di, da, ctx->st);
+  LAUNCHED("peak_detect", 1);
+  float res[4];
+  CK(cudaMemcpyAsync(res, dp, 16, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  peak->re = res[0]; peak->im = res[1];
+  if (peak_index) *peak_index = res[2];
+  if (avg_power) *avg_power = res[3];
+  return BTSDSP_OK;
+}
+
+int btsdsp_interpolate_point(btsdsp_ctx *ctx, const btsdsp_cf32 *v, int n, float ix, btsdsp_cf32 *out) {
+  ARG(ctx && v && n > 0 && out);
+  DeviceGuard g(ctx->device);
+  GROW(B_A, n * sizeof(cf)); GROW(B_D, 256);
+  CK(cudaMemcpyAsync(dbuf<cf>(ctx, B_A), v, n * sizeof(cf), cudaMemcpyHostToDevice, ctx->st));
+  launch_interp_point(ctx->T, dbuf<cf>(ctx, B_A), n, ix, dbuf<cf>(ctx, B_D), ctx->st);
+  LAUNCHED("interpolate_point", 1);
+  CK(cudaMemcpyAsync(out, dbuf<cf>(ctx, B_D), sizeof(cf), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return BTSDSP_OK;
+}
+
+int btsdsp_energy_detect(btsdsp_ctx *ctx, const btsdsp_cf32 *v, int n, unsigned window, float threshold,
+                         float *avg_power, int *detected) {
+  ARG(ctx && v && n > 0 && detected);
+  DeviceGuard g(ctx->device);
+  GROW(B_A, n * sizeof(cf)); GROW(B_D, 256);
+  float *da = dbuf<float>(ctx, B_D);
+  int *df = (int *)(da + 1);
+  CK(cudaMemcpyAsync(dbuf<cf>(ctx, B_A), v, n * sizeof(cf), cudaMemcpyHostToDevice, ctx->st));
+  launch_energy_detect(dbuf<cf>(ctx, B_A), n, window, threshold, da, df, ctx->st);
+  LAUNCHED("energy_detect", 1);
+  float res[2];
+  CK(cudaMemcpyAsync(res, da, 8, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  if (avg_power) *avg_power = res[0];
+  memcpy(detected, &res[1], 4);
+  return BTSDSP_OK;
+}
+
+int btsdsp_modulate_burst(btsdsp_ctx *ctx, const uint8_t *bits, int nbits, int guard, btsdsp_cf32 *out, int cap) {
+  ARG(ctx && bits && nbits > 0 && guard >= 0);
+  const int n = ctx->sps * (nbits + guard);
+  ARG(n <= 157 * ctx->sps);            // the rotation table is 157*sps long (sigProcLib.cpp:215)
+  if (cap < n || !out) return n;
+  DeviceGuard g(ctx->device);
+  GROW(B_D, nbits + 64); GROW(B_A, n * sizeof(cf));
+  CK(cudaMemcpyAsync(dbuf<uint8_t>(ctx, B_D), bits, nbits, cudaMemcpyHostToDevice, ctx->st));
+  launch_modulate(ctx->T, dbuf<uint8_t>(ctx, B_D), nbits, 1, guard, nullptr, 0, dbuf<cf>(ctx, B_A), n, ctx->st);
+  LAUNCHED("modulate", 1);
+  CK(cudaMemcpyAsync(out, dbuf<cf>(ctx, B_A), n * sizeof(cf), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return n;
+}
+
+int btsdsp_analyze_traffic_burst(btsdsp_ctx *ctx, const btsdsp_cf32 *burst, int n, unsigned tsc, float threshold,
+                                 btsdsp_cf32 *amplitude, float *toa, int request_channel, btsdsp_cf32 *chan,
+                                 float *chan_offset, int *detected) {
+  ARG(ctx && burst && amplitude && toa && detected && tsc < 8);
+  const int sps = ctx->sps;
+  ARG(n >= 92 * sps);                   // the correlation window is samples [56*sps, 92*sps) (:951)
+  DeviceGuard g(ctx->device);
+  GROW(B_A, n * sizeof(cf)); GROW(B_D, 1024); GROW(B_SCRATCH, scratch_per_burst(sps) * sizeof(cf));
+  uint8_t *d = dbuf<uint8_t>(ctx, B_D);
+  struct { int32_t len; int32_t flag; cf amp; float toa; float off; cf chan[6 * kMaxSps]; uint8_t tsc; } hres;
+  int32_t *dLen = (int32_t *)d, *dFlag = dLen + 1;
+  cf *dAmp = (cf *)(d + 8);
+  float *dToa = (float *)(d + 16), *dOff = dToa + 1;
+  cf *dChan = (cf *)(d + 24);
+  uint8_t *dTsc = d + 24 + sizeof(cf) * 6 * kMaxSps;
+  hres.len = n; hres.tsc = (uint8_t)tsc;
+  CK(cudaMemcpyAsync(dbuf<cf>(ctx, B_A), burst, n * sizeof(cf), cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(dLen, &hres.len, 4, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(dTsc, &hres.tsc, 1, cudaMemcpyHostToDevice, ctx->st));
+  NormalOut o = {dFlag, dAmp, dToa, dChan, dOff, nullptr, nullptr, nullptr, 0};
+  launch_analyze(ctx->T, make_src((const btsdsp_cf32 *)dbuf<cf>(ctx, B_A), n, dLen, 0, sps), dTsc, 1, threshold,
+                 request_channel, o, dbuf<cf>(ctx, B_SCRATCH), n > kBurstRows, ctx->st);
+  LAUNCHED("analyze", 1);
+  CK(cudaMemcpyAsync(&hres, d, 24 + sizeof(cf) * 6 * kMaxSps, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  *detected = hres.flag;
+  amplitude->re = hres.amp.x; amplitude->im = hres.amp.y;
+  *toa = hres.toa;
+  if (request_channel && hres.flag) {
+    if (chan) memcpy(chan, hres.chan, sizeof(cf) * 6 * sps);
+    if (chan_offset) *chan_offset = hres.off;
+  }
+  return BTSDSP_OK;
+}
+
+int btsdsp_detect_rach_burst(btsdsp_ctx *ctx, const btsdsp_cf32 *burst, int n, float threshold, btsdsp_cf32 *amplitude,
+                             float *toa, int *detected) {
+  ARG(ctx && burst && amplitude && toa && detected && n > 1);
+  const int sps = ctx->sps;
+  ARG(n <= 157 * sps);
+  DeviceGuard g(ctx->device);
+  GROW(B_A, n * sizeof(cf)); GROW(B_D, 1024); GROW(B_SCRATCH, scratch_per_burst(sps) * sizeof(cf));
+  uint8_t *d = dbuf<uint8_t>(ctx, B_D);
+  int32_t *dLen = (int32_t *)d, *dFlag = dLen + 1;
+  cf *dAmp = (cf *)(d + 8);
+  float *dToa = (float *)(d + 16);
+  struct { int32_t len, flag; cf amp; float toa; } hres;
+  hres.len = n;
+  CK(cudaMemcpyAsync(dbuf<cf>(ctx, B_A), burst, n * sizeof(cf), cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(dLen, &hres.len, 4, cudaMemcpyHostToDevice, ctx->st));
+  NormalOut o = {dFlag, dAmp, dToa, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+  launch_rach(ctx->T, make_src((const btsdsp_cf32 *)dbuf<cf>(ctx, B_A), n, dLen, 0, sps), 1, threshold, 0, o,
+              dbuf<cf>(ctx, B_SCRATCH), 0, ctx->st);
+  LAUNCHED("detect_rach", 1);
+  CK(cudaMemcpyAsync(&hres, d, 20, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  *detected = hres.flag;
+  amplitude->re = hres.amp.x; amplitude->im = hres.amp.y;
+  *toa = hres.toa;
+  return BTSDSP_OK;
+}
+
+int btsdsp_design_dfe(btsdsp_ctx *ctx, const btsdsp_cf32 *chan, int nchan, float snr, int nf, btsdsp_cf32 *w,
+                      btsdsp_cf32 *b) {
+  ARG(ctx && chan && w && b);
+  ARG(nf >= 1 && nf <= kDfeMax && nchan >= 1 && nchan <= nf);   // the reference overruns G1 when nchan > Nf
+  DeviceGuard g(ctx->device);
+  GROW(B_D, 1024);
+  cf *d = dbuf<cf>(ctx, B_D);
+  cf *dW = d + 32, *dB = d + 64;
+  CK(cudaMemcpyAsync(d, chan, nchan * sizeof(cf), cudaMemcpyHostToDevice, ctx->st));
+  launch_design_dfe_generic(d, nchan, snr, nf, dW, dB, ctx->st);
+  LAUNCHED("design_dfe", 1);
+  CK(cudaMemcpyAsync(w, dW, nf * sizeof(cf), cudaMemcpyDeviceToHost, ctx->st));
+  if (nchan > 1) CK(cudaMemcpyAsync(b, dB, (nchan - 1) * sizeof(cf), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return BTSDSP_OK;
+}
+
+int btsdsp_equalize_burst(btsdsp_ctx *ctx, btsdsp_cf32 *burst, int n, float toa, const btsdsp_cf32 *w, int nw,
+                          const btsdsp_cf32 *b, int nb, float *soft) {
+  ARG(ctx && burst && w && b && soft);
+  if (ctx->sps != 1) return fail(ctx, BTSDSP_EUNSUPPORTED, "equalizeBurst assumes symbol-rate sampling (sps == 1)");
+  ARG(n > 0 && n <= 157 && nw >= 1 && nw <= kDfeMax && nb >= 0 && nb <= kDfeMax);
+  DeviceGuard g(ctx->device);
+  GROW(B_A, n * sizeof(cf)); GROW(B_B, (n + kDfeMax) * sizeof(cf)); GROW(B_C, n * sizeof(float)); GROW(B_D, 1024);
+  cf *d = dbuf<cf>(ctx, B_D);
+  CK(cudaMemcpyAsync(dbuf<cf>(ctx, B_A), burst, n * sizeof(cf), cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(d, w, nw * sizeof(cf), cudaMemcpyHostToDevice, ctx->st));
+  if (nb) CK(cudaMemcpyAsync(d + 32, b, nb * sizeof(cf), cudaMemcpyHostToDevice, ctx->st));
+  launch_equalize_generic(ctx->T, dbuf<cf>(ctx, B_A), n, toa, d, nw, d + 32, nb, dbuf<cf>(ctx, B_B),
+                          dbuf<float>(ctx, B_C), ctx->st);
+  LAUNCHED("equalize", 1);
+  CK(cudaMemcpyAsync(burst, dbuf<cf>(ctx, B_A), n * sizeof(cf), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaMemcpyAsync(soft, dbuf<float>(ctx, B_C), n * sizeof(float), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return BTSDSP_OK;
+}
+
+int btsdsp_demodulate_burst(btsdsp_ctx *ctx, const btsdsp_cf32 *burst, int n, btsdsp_cf32 channel, float toa,
+                            float *soft) {
+  ARG(ctx && burst && soft && n > 0);
+  const int sps = ctx->sps;
+  ARG(n <= 157 * sps);
+  DeviceGuard g(ctx->device);
+  const int ns = (sps > 1) ? n / sps : n;
+  GROW(B_A, n * sizeof(cf)); GROW(B_C, (n + 8) * sizeof(float)); GROW(B_D, 1024);
+  GROW(B_SCRATCH, scratch_per_burst(sps) * sizeof(cf));
+  uint8_t *d = dbuf<uint8_t>(ctx, B_D);
+  struct { int32_t len; int32_t pad; cf amp; float toa; } h;
+  h.len = n; h.pad = 0; h.amp = mk(channel.re, channel.im); h.toa = toa;
+  CK(cudaMemcpyAsync(dbuf<cf>(ctx, B_A), burst, n * sizeof(cf), cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(d, &h, sizeof h, cudaMemcpyHostToDevice, ctx->st));
+  launch_demodulate(ctx->T, make_src((const btsdsp_cf32 *)dbuf<cf>(ctx, B_A), n, (const int32_t *)d, 0, sps), 1,
+                    (const cf *)(d + 8), (const float *)(d + 16), dbuf<float>(ctx, B_C), ns, dbuf<cf>(ctx, B_SCRATCH),
+                    ctx->st);
+  LAUNCHED("demodulate", 1);
+  CK(cudaMemcpyAsync(soft, dbuf<float>(ctx, B_C), ns * sizeof(float), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return ns;
+}
+
+int btsdsp_polyphase_resample(btsdsp_ctx *ctx, const btsdsp_cf32 *x, int n, int P, int Q, int lpf, btsdsp_cf32 *out,
+                              int cap) {
+  ARG(ctx && x && n > 0 && P > 0 && Q > 0 && (lpf == 0 || lpf == 1));
+  const int outn = (int)ceil(n * (float)P / (float)Q);     // :1171
+  if (cap < outn || !out) return outn;
+  DeviceGuard g(ctx->device);
+  GROW(B_A, n * sizeof(cf)); GROW(B_B, outn * sizeof(cf));
+  CK(cudaMemcpyAsync(dbuf<cf>(ctx, B_A), x, n * sizeof(cf), cudaMemcpyHostToDevice, ctx->st));
+  launch_resample_generic(dbuf<cf>(ctx, B_A), n, P, Q, lpf ? ctx->T->lpf_tx : ctx->T->lpf_rx, lpf ? kTxTaps : kRxTaps,
+                          dbuf<cf>(ctx, B_B), outn, ctx->st);
+  LAUNCHED("polyphase_resample", 1);
+  CK(cudaMemcpyAsync(out, dbuf<cf>(ctx, B_B), outn * sizeof(cf), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return outn;
+}
+
+// ---- layer 2 ---------------------------------------------------------------------------------------
+int btsdsp_modulate_dev(btsdsp_ctx *ctx, const uint8_t *bits, int nbits, long long n, int guard, long long first,
+                        btsdsp_cf32 *out, long long pitch, void *stream) {
+  ARG(ctx && bits && out && nbits > 0 && n >= 0 && pitch >= 0);
+  ARG(nbits + (guard < 0 ? 9 : guard) <= 157);
+  if (pitch == 0) ARG(nbits == 148 && guard < 0);
+  DeviceGuard g(ctx->device);
+  launch_modulate(ctx->T, bits, nbits, n, guard, nullptr, first, (cf *)out, pitch, (cudaStream_t)stream);
+  LAUNCHED("modulate", n > 0);
+  return BTSDSP_OK;
+}
+
+int btsdsp_resample_rx_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, int has_history, long long nchunks,
+                           btsdsp_cf32 *out, void *stream) {
+  ARG(ctx && raw && out && nchunks >= 0);
+  DeviceGuard g(ctx->device);
+  launch_resample_rx(ctx->T, (const cf *)raw, has_history, nchunks, (cf *)out, (cudaStream_t)stream);
+  LAUNCHED("resample_rx", nchunks > 0);
+  return BTSDSP_OK;
+}
+
+int btsdsp_resample_tx_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *in, int has_history, long long nchunks, int16_t *out,
+                           void *stream) {
+  ARG(ctx && in && out && nchunks >= 0);
+  DeviceGuard g(ctx->device);
+  launch_resample_tx(ctx->T, (const cf *)in, has_history, nchunks, out, (cudaStream_t)stream);
+  LAUNCHED("resample_tx", nchunks > 0);
+  return BTSDSP_OK;
+}
+
+int btsdsp_demod_normal_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens,
+                            long long first, const uint8_t *tsc, long long n, float detect_thr, float gate_thr,
+                            float snr_thr, int32_t *flag, btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch,
+                            btsdsp_cf32 *chan, float *chan_off, btsdsp_cf32 *w, btsdsp_cf32 *b, void *stream) {
+  ARG(ctx && bursts && tsc && n >= 0 && pitch >= 0);
+  if (ctx->sps != 1) return fail(ctx, BTSDSP_EUNSUPPORTED, "the DFE path assumes symbol-rate sampling (sps == 1)");
+  ARG(!soft || soft_pitch >= 148);
+  DeviceGuard g(ctx->device);
+  NormalOut o = {flag, (cf *)amp, toa, (cf *)chan, chan_off, (cf *)w, (cf *)b, soft, soft_pitch};
+  launch_demod_normal(ctx->T, make_src(bursts, pitch, lens, first, 1), tsc, n, detect_thr, gate_thr, snr_thr, o,
+                      (cudaStream_t)stream);
+  LAUNCHED("demod_normal", n > 0);
+  return BTSDSP_OK;
+}
+
+int btsdsp_analyze_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens,
+                       long long first, const uint8_t *tsc, long long n, float detect_thr, int request_channel,
+                       int32_t *flag, btsdsp_cf32 *amp, float *toa, btsdsp_cf32 *chan, float *chan_off, void *stream) {
+  ARG(ctx && bursts && tsc && n >= 0 && pitch >= 0);
+  DeviceGuard g(ctx->device);
+  if (ctx->sps != 1) GROW(B_SCRATCH, (size_t)n * scratch_per_burst(ctx->sps) * sizeof(cf));
+  NormalOut o = {flag, (cf *)amp, toa, (cf *)chan, chan_off, nullptr, nullptr, nullptr, 0};
+  launch_analyze(ctx->T, make_src(bursts, pitch, lens, first, ctx->sps), tsc, n, detect_thr, request_channel, o,
+                 dbuf<cf>(ctx, B_SCRATCH), 0, (cudaStream_t)stream);
+  LAUNCHED("analyze", n > 0);
+  return BTSDSP_OK;
+}
+
+int btsdsp_rach_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens, long long first,
+                    long long n, float detect_thr, int32_t *flag, btsdsp_cf32 *amp, float *toa, float *soft,
+                    int soft_pitch, void *stream) {
+  ARG(ctx && bursts && n >= 0 && pitch >= 0);
+  ARG(!soft || soft_pitch >= 157);
+  DeviceGuard g(ctx->device);
+  if (ctx->sps != 1) GROW(B_SCRATCH, (size_t)n * scratch_per_burst(ctx->sps) * sizeof(cf));
+  NormalOut o = {flag, (cf *)amp, toa, nullptr, nullptr, nullptr, nullptr, soft, soft_pitch};
+  launch_rach(ctx->T, make_src(bursts, pitch, lens, first, ctx->sps), n, detect_thr, soft != nullptr, o,
+              dbuf<cf>(ctx, B_SCRATCH), 0, (cudaStream_t)stream);
+  LAUNCHED("rach", n > 0);
+  return BTSDSP_OK;
+}
+
+int btsdsp_design_dfe_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *chan, const float *snr, long long n, btsdsp_cf32 *w,
+                          btsdsp_cf32 *b, void *stream) {
+  ARG(ctx && chan && snr && w && b && n >= 0);
+  DeviceGuard g(ctx->device);
+  launch_design_dfe((const cf *)chan, snr, n, (cf *)w, (cf *)b, (cudaStream_t)stream);
+  LAUNCHED("design_dfe", n > 0);
+  return BTSDSP_OK;
+}
+
+int btsdsp_equalize_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens,
+                        long long first, long long n, const float *toa, const btsdsp_cf32 *w, const btsdsp_cf32 *b,
+                        float *soft, int soft_pitch, btsdsp_cf32 *burst_out, long long out_pitch, void *stream) {
+  ARG(ctx && bursts && toa && w && b && soft && n >= 0 && pitch >= 0 && soft_pitch >= 148);
+  if (ctx->sps != 1) return fail(ctx, BTSDSP_EUNSUPPORTED, "equalizeBurst assumes symbol-rate sampling (sps == 1)");
+  DeviceGuard g(ctx->device);
+  launch_equalize(ctx->T, make_src(bursts, pitch, lens, first, 1), n, toa, (const cf *)w, (const cf *)b, soft,
+                  soft_pitch, (cf *)burst_out, out_pitch, (cudaStream_t)stream);
+  LAUNCHED("equalize", n > 0);
+  return BTSDSP_OK;
+}
+
+int btsdsp_demodulate_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens,
+                          long long first, long long n, const btsdsp_cf32 *amp, const float *toa, float *soft,
+                          int soft_pitch, void *stream) {
+  ARG(ctx && bursts && amp && toa && soft && n >= 0 && pitch >= 0 && soft_pitch >= 157);
+  DeviceGuard g(ctx->device);
+  GROW(B_SCRATCH, (size_t)n * scratch_per_burst(ctx->sps) * sizeof(cf));
+  launch_demodulate(ctx->T, make_src(bursts, pitch, lens, first, ctx->sps), n, (const cf *)amp, toa, soft, soft_pitch,
+                    dbuf<cf>(ctx, B_SCRATCH), (cudaStream_t)stream);
+  LAUNCHED("demodulate", n > 0);
+  return BTSDSP_OK;
+}
+
+// ---- layer 3 ---------------------------------------------------------------------------------------
+int btsdsp_rx_stream_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nchunks, const uint8_t *tsc,
+                         long long nbursts, float detect_thr, float gate_thr, float snr_thr, int32_t *flag,
+                         btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch, void *stream) {
+  ARG(ctx && raw && tsc && nchunks > 0 && nbursts >= 0);
+  if (ctx->sps != 1) return fail(ctx, BTSDSP_EUNSUPPORTED, "the RX stream path runs at sps == 1");
+  ARG(((nbursts + 3) / 4) * 625 <= nchunks * 585);
+  DeviceGuard g(ctx->device);
+  GROW(B_RES, (size_t)nchunks * 585 * sizeof(cf));
+  cudaStream_t st = (cudaStream_t)stream;
+  launch_resample_rx(ctx->T, (const cf *)raw, 0, nchunks, dbuf<cf>(ctx, B_RES), st);
+  NormalOut o = {flag, (cf *)amp, toa, nullptr, nullptr, nullptr, nullptr, soft, soft_pitch};
+  launch_demod_normal(ctx->T, make_src((const btsdsp_cf32 *)dbuf<cf>(ctx, B_RES), 0, nullptr, 0, 1), tsc, nbursts,
+                      detect_thr, gate_thr, snr_thr, o, st);
+  LAUNCHED("rx_stream", 1 + (nbursts > 0));
+  return BTSDSP_OK;
+}
+
+// Host-buffer receive pipeline: the stream is cut into segments of whole frame groups; segment s is
+// copied H2D on st_in while segment s-1 is resampled + demodulated on st and segment s-2's results
+// return D2H on st_out.  The whole raw / resampled stream stays resident on the device so the
+// resampler's 192-sample history and bursts straddling segment borders need no special casing.
+int btsdsp_rx_stream_host(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nchunks, const uint8_t *tsc,
+                          long long nbursts, float detect_thr, float gate_thr, float snr_thr, int32_t *flag,
+                          btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch) {
+  ARG(ctx && raw && tsc && nchunks > 0 && nbursts >= 0);
+  if (ctx->sps != 1) return fail(ctx, BTSDSP_EUNSUPPORTED, "the RX stream path runs at sps == 1");
+  ARG(((nbursts + 3) / 4) * 625 <= nchunks * 585);
+  ARG(!soft || soft_pitch >= 148);
+  DeviceGuard g(ctx->device);
+  GROW(B_RAW, (size_t)nchunks * 864 * sizeof(cf));
+  GROW(B_RES, (size_t)nchunks * 585 * sizeof(cf));
+  GROW(B_TSC, (size_t)nbursts + 16);
+  GROW(B_FLAG, (size_t)(nbursts + 1) * sizeof(int32_t));
+  GROW(B_AMP, (size_t)(nbursts + 1) * sizeof(cf));
+  GROW(B_TOA, (size_t)(nbursts + 1) * sizeof(float));
+  if (soft) GROW(B_SOFT, (size_t)(nbursts + 1) * soft_pitch * sizeof(float));
+  cf *dRaw = dbuf<cf>(ctx, B_RAW), *dRes = dbuf<cf>(ctx, B_RES);
+  uint8_t *dTsc = dbuf<uint8_t>(ctx, B_TSC);
+  int32_t *dFlag = dbuf<int32_t>(ctx, B_FLAG);
+  cf *dAmp = dbuf<cf>(ctx, B_AMP);
+  float *dToa = dbuf<float>(ctx, B_TOA), *dSoft = soft ? dbuf<float>(ctx, B_SOFT) : nullptr;
+
+  const long long seg = 4000;                       // chunks per segment: 27.6 MB of raw samples
+  const long long nseg = (nchunks + seg - 1) / seg;
+  while ((long long)ctx->events.size() < 2 * nseg + 2) {
+    cudaEvent_t ev;
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    ctx->events.push_back(ev);
+  }
+  CK(cudaMemcpyAsync(dTsc, tsc, (size_t)nbursts, cudaMemcpyHostToDevice, ctx->st_in));
+  long long done_bursts = 0;
+  for (long long s = 0; s < nseg; s++) {
+    const long long c0 = s * seg, c1 = (c0 + seg < nchunks) ? c0 + seg : nchunks;
+    cudaEvent_t evIn = ctx->events[2 * s], evK = ctx->events[2 * s + 1];
+    CK(cudaMemcpyAsync(dRaw + c0 * 864, raw + c0 * 864, (size_t)(c1 - c0) * 864 * sizeof(cf), cudaMemcpyHostToDevice,
+                       ctx->st_in));
+    CK(cudaEventRecord(evIn, ctx->st_in));
+    CK(cudaStreamWaitEvent(ctx->st, evIn, 0));
+    launch_resample_rx(ctx->T, dRaw + c0 * 864, c0 > 0, c1 - c0, dRes + c0 * 585, ctx->st);
+    // bursts wholly inside the samples resampled so far: groups of 4 slots = 625 samples
+    long long avail = (c1 * 585 / 625) * 4;
+    if (avail > nbursts || c1 == nchunks) avail = nbursts;
+    const long long nb = avail - done_bursts;
+    int nl = 1;
+    if (nb > 0) {
+      NormalOut o = {dFlag + done_bursts, dAmp + done_bursts, dToa + done_bursts, nullptr, nullptr, nullptr, nullptr,
+                     dSoft ? dSoft + done_bursts * soft_pitch : nullptr, soft_pitch};
+      launch_demod_normal(ctx->T, make_src((const btsdsp_cf32 *)dRes, 0, nullptr, done_bursts, 1), dTsc + done_bursts,
+                          nb, detect_thr, gate_thr, snr_thr, o, ctx->st);
+      nl = 2;
+    }
+    LAUNCHED("rx_stream_host", nl);
+    CK(cudaEventRecord(evK, ctx->st));
+    if (nb > 0) {
+      CK(cudaStreamWaitEvent(ctx->st_out, evK, 0));
+      if (flag) CK(cudaMemcpyAsync(flag + done_bursts, dFlag + done_bursts, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->st_out));
+      if (amp) CK(cudaMemcpyAsync(amp + done_bursts, dAmp + done_bursts, nb * sizeof(cf), cudaMemcpyDeviceToHost, ctx->st_out));
+      if (toa) CK(cudaMemcpyAsync(toa + done_bursts, dToa + done_bursts, nb * sizeof(float), cudaMemcpyDeviceToHost, ctx->st_out));
+      if (soft) CK(cudaMemcpyAsync(soft + done_bursts * soft_pitch, dSoft + done_bursts * soft_pitch,
+                                   (size_t)nb * soft_pitch * sizeof(float), cudaMemcpyDeviceToHost, ctx->st_out));
+    }
+    done_bursts = avail;
+  }
+  CK(cudaStreamSynchronize(ctx->st_out));
+  CK(cudaStreamSynchronize(ctx->st));
+  return BTSDSP_OK;
+}
+
+int btsdsp_tx_stream_dev(btsdsp_ctx *ctx, const uint8_t *bits148, long long n, int16_t *out, void *stream) {
+  ARG(ctx && bits148 && out && n > 0);
+  if (ctx->sps != 1) return fail(ctx, BTSDSP_EUNSUPPORTED, "the TX stream path runs at sps == 1");
+  ARG(n % 4 == 0 && (n / 4 * 625) % 585 == 0);
+  DeviceGuard g(ctx->device);
+  const long long nsamp = n / 4 * 625, nchunks = nsamp / 585;
+  GROW(B_RES, (size_t)nsamp * sizeof(cf));
+  cudaStream_t st = (cudaStream_t)stream;
+  launch_modulate(ctx->T, bits148, 148, n, -1, nullptr, 0, dbuf<cf>(ctx, B_RES), 0, st);
+  launch_resample_tx(ctx->T, dbuf<cf>(ctx, B_RES), 0, nchunks, out, st);
+  LAUNCHED("tx_stream", 2);
+  return BTSDSP_OK;
+}
+
+int btsdsp_tx_stream_host(btsdsp_ctx *ctx, const uint8_t *bits148, long long n, int16_t *out) {
+  ARG(ctx && bits148 && out && n > 0);
+  ARG(n % 4 == 0 && (n / 4 * 625) % 585 == 0);
+  DeviceGuard g(ctx->device);
+  const long long nchunks = n / 4 * 625 / 585;
+  GROW(B_TSC, (size_t)n * 148);
+  GROW(B_RAW, (size_t)nchunks * 864 * 2 * sizeof(int16_t));
+  CK(cudaMemcpyAsync(dbuf<uint8_t>(ctx, B_TSC), bits148, (size_t)n * 148, cudaMemcpyHostToDevice, ctx->st));
+  int r = btsdsp_tx_stream_dev(ctx, dbuf<uint8_t>(ctx, B_TSC), n, dbuf<int16_t>(ctx, B_RAW), ctx->st);
+  if (r != BTSDSP_OK) return r;
+  CK(cudaMemcpyAsync(out, dbuf<int16_t>(ctx, B_RAW), (size_t)nchunks * 864 * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost,
+                     ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return BTSDSP_OK;
+}
+
+int btsdsp_demod_normal_host(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens,
+                             const uint8_t *tsc, long long n, float detect_thr, float gate_thr, float snr_thr,
+                             int32_t *flag, btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch,
+                             btsdsp_cf32 *chan, float *chan_off, btsdsp_cf32 *w, btsdsp_cf32 *b) {
+  ARG(ctx && bursts && tsc && n > 0 && pitch >= 157);
+  ARG(!soft || soft_pitch >= 148);
+  if (ctx->sps != 1) return fail(ctx, BTSDSP_EUNSUPPORTED, "the DFE path assumes symbol-rate sampling (sps == 1)");
+  DeviceGuard g(ctx->device);
+  // one flat device arena: bursts | lens | tsc | flag | amp | toa | off | chan | w | b | soft
+  size_t total = 0;
+  auto take = [&total](size_t bytes) { size_t o = (total + 255) & ~(size_t)255; total = o + bytes; return o; };
+  const size_t o_b = take((size_t)n * pitch * sizeof(cf)), o_len = take((size_t)n * 4), o_tsc = take((size_t)n),
+               o_flag = take((size_t)n * 4), o_amp = take((size_t)n * 8), o_toa = take((size_t)n * 4),
+               o_off = take((size_t)n * 4), o_chan = take((size_t)n * 48), o_w = take((size_t)n * 56),
+               o_fb = take((size_t)n * 40), o_soft = take((size_t)n * soft_pitch * 4);
+  GROW(B_RAW, total);
+  uint8_t *d = dbuf<uint8_t>(ctx, B_RAW);
+  cudaStream_t st = ctx->st;
+  CK(cudaMemcpyAsync(d + o_b, bursts, (size_t)n * pitch * sizeof(cf), cudaMemcpyHostToDevice, st));
+  if (lens) CK(cudaMemcpyAsync(d + o_len, lens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_tsc, tsc, (size_t)n, cudaMemcpyHostToDevice, st));
+  int r = btsdsp_demod_normal_dev(ctx, (const btsdsp_cf32 *)(d + o_b), pitch, lens ? (const int32_t *)(d + o_len) : nullptr,
+                                  0, d + o_tsc, n, detect_thr, gate_thr, snr_thr, (int32_t *)(d + o_flag),
+                                  (btsdsp_cf32 *)(d + o_amp), (float *)(d + o_toa), soft ? (float *)(d + o_soft) : nullptr,
+                                  soft_pitch, chan ? (btsdsp_cf32 *)(d + o_chan) : nullptr,
+                                  chan_off ? (float *)(d + o_off) : nullptr, w ? (btsdsp_cf32 *)(d + o_w) : nullptr,
+                                  b ? (btsdsp_cf32 *)(d + o_fb) : nullptr, st);
+  if (r != BTSDSP_OK) return r;
+  if (flag) CK(cudaMemcpyAsync(flag, d + o_flag, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (amp) CK(cudaMemcpyAsync(amp, d + o_amp, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  if (toa) CK(cudaMemcpyAsync(toa, d + o_toa, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (chan_off) CK(cudaMemcpyAsync(chan_off, d + o_off, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (chan) CK(cudaMemcpyAsync(chan, d + o_chan, (size_t)n * 48, cudaMemcpyDeviceToHost, st));
+  if (w) CK(cudaMemcpyAsync(w, d + o_w, (size_t)n * 56, cudaMemcpyDeviceToHost, st));
+  if (b) CK(cudaMemcpyAsync(b, d + o_fb, (size_t)n * 40, cudaMemcpyDeviceToHost, st));
+  if (soft) CK(cudaMemcpyAsync(soft, d + o_soft, (size_t)n * soft_pitch * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return BTSDSP_OK;
+}
+
+int btsdsp_rach_host(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens, long long n,
+                     float detect_thr, int32_t *flag, btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch) {
+  ARG(ctx && bursts && n > 0 && pitch >= 157 * ctx->sps);
+  ARG(!soft || soft_pitch >= 157);
+  DeviceGuard g(ctx->device);
+  size_t total = 0;
+  auto take = [&total](size_t bytes) { size_t o = (total + 255) & ~(size_t)255; total = o + bytes; return o; };
+  const size_t o_b = take((size_t)n * pitch * sizeof(cf)), o_len = take((size_t)n * 4), o_flag = take((size_t)n * 4),
+               o_amp = take((size_t)n * 8), o_toa = take((size_t)n * 4), o_soft = take((size_t)n * soft_pitch * 4);
+  GROW(B_RAW, total);
+  uint8_t *d = dbuf<uint8_t>(ctx, B_RAW);
+  cudaStream_t st = ctx->st;
+  CK(cudaMemcpyAsync(d + o_b, bursts, (size_t)n * pitch * sizeof(cf), cudaMemcpyHostToDevice, st));
+  if (lens) CK(cudaMemcpyAsync(d + o_len, lens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  int r = btsdsp_rach_dev(ctx, (const btsdsp_cf32 *)(d + o_b), pitch, lens ? (const int32_t *)(d + o_len) : nullptr, 0, n,
+                          detect_thr, (int32_t *)(d + o_flag), (btsdsp_cf32 *)(d + o_amp), (float *)(d + o_toa),
+                          soft ? (float *)(d + o_soft) : nullptr, soft_pitch, st);
+  if (r != BTSDSP_OK) return r;
+  if (flag) CK(cudaMemcpyAsync(flag, d + o_flag, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (amp) CK(cudaMemcpyAsync(amp, d + o_amp, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  if (toa) CK(cudaMemcpyAsync(toa, d + o_toa, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (soft) CK(cudaMemcpyAsync(soft, d + o_soft, (size_t)n * soft_pitch * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return BTSDSP_OK;
+}
+
+}  // extern "C"

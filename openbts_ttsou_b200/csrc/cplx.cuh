@@ -1,0 +1,66 @@
+// cplx.cuh -- exact (never contracted) complex<float> arithmetic for the burst-DSP kernels.
+//
+// Bit-parity with the reference's scalar IEEE binary32 arithmetic (reference Transceiver/Complex.h)
+// is the contract: every product and sum is rounded separately, in the reference's operand order.
+// The __f*_rn intrinsics are never fused into FMAs by nvcc, independent of -fmad.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace btsdsp {
+
+#define BTS_HD __host__ __device__ __forceinline__
+
+typedef float2 cf;   // .x = real, .y = imag ; same memory layout as the reference's Complex<float>
+
+BTS_HD cf mk(float r, float i) { return make_float2(r, i); }
+
+#ifdef __CUDA_ARCH__
+#define BTS_MUL(a, b) __fmul_rn((a), (b))
+#define BTS_ADD(a, b) __fadd_rn((a), (b))
+#define BTS_SUB(a, b) __fsub_rn((a), (b))
+#define BTS_DIV(a, b) __fdiv_rn((a), (b))
+#define BTS_SQRT(a) __fsqrt_rn((a))
+#else
+#define BTS_MUL(a, b) ((a) * (b))
+#define BTS_ADD(a, b) ((a) + (b))
+#define BTS_SUB(a, b) ((a) - (b))
+#define BTS_DIV(a, b) ((a) / (b))
+#define BTS_SQRT(a) sqrtf((a))
+#endif
+
+// Complex.h:79  operator+
+BTS_HD cf cadd(cf a, cf b) { return mk(BTS_ADD(a.x, b.x), BTS_ADD(a.y, b.y)); }
+BTS_HD cf csub(cf a, cf b) { return mk(BTS_SUB(a.x, b.x), BTS_SUB(a.y, b.y)); }
+// Complex.h:83  operator*(Complex): (r*a.r - i*a.i, r*a.i + i*a.r)
+BTS_HD cf cmul(cf a, cf b) {
+  return mk(BTS_SUB(BTS_MUL(a.x, b.x), BTS_MUL(a.y, b.y)), BTS_ADD(BTS_MUL(a.x, b.y), BTS_MUL(a.y, b.x)));
+}
+// Complex.h:84  operator*(Real)
+BTS_HD cf cmulr(cf a, float s) { return mk(BTS_MUL(a.x, s), BTS_MUL(a.y, s)); }
+// Complex.h:86  operator/(Real)
+BTS_HD cf cdivr(cf a, float s) { return mk(BTS_DIV(a.x, s), BTS_DIV(a.y, s)); }
+BTS_HD cf cconj(cf a) { return mk(a.x, -a.y); }
+// Complex.h:122 norm2 = i*i + r*r  (imaginary product first)
+BTS_HD float cnorm2(cf a) { return BTS_ADD(BTS_MUL(a.y, a.y), BTS_MUL(a.x, a.x)); }
+// Complex.h:154-160 inv = (r/n, -i/n)
+BTS_HD cf cinv(cf a) {
+  float n = cnorm2(a);
+  return mk(BTS_DIV(a.x, n), BTS_DIV(-a.y, n));
+}
+// Complex.h:85  operator/(Complex) = *this * a.inv()
+BTS_HD cf cdiv(cf a, cf b) { return cmul(a, cinv(b)); }
+// Complex.h:131 abs = sqrt(norm2)
+BTS_HD float cabs_(cf a) { return BTS_SQRT(cnorm2(a)); }
+
+// Strided view of a complex vector.  S = 1 for ordinary (global) vectors; S = 33 for the per-lane
+// columns of the transposed shared-memory tiles used by the one-burst-per-thread kernels.
+template <int S>
+struct View {
+  cf *p;
+  BTS_HD cf ld(int i) const { return p[i * S]; }
+  BTS_HD void st(int i, cf v) const { p[i * S] = v; }
+  BTS_HD View<S> at(int k) const { return View<S>{p + k * S}; }
+};
+
+}  // namespace btsdsp

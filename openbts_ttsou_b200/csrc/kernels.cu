@@ -1,0 +1,501 @@
+// kernels.cu -- sm_100a kernels of the burst-DSP path (everything but the resamplers).
+//
+// Layout in HBM: bursts are interleaved complex-float I/Q (float2), either pitched (one burst every
+// `pitch` samples) or cut on the fly from a continuous 157/156/156/156 slot stream (BurstSrc).
+// The batched receive kernels run ONE BURST PER THREAD: a warp stages its 32 bursts with coalesced
+// loads into a transposed shared-memory tile (row = sample index, column = lane, row stride 33 so
+// both the transposing store and the per-lane column walk are bank-conflict free), then every lane
+// runs the reference's scalar algorithm over its own column (sigproc_device.cuh).  That keeps each
+// comparison bit-identical to the reference while all 32 lanes of every instruction do useful work;
+// throughput comes from bursts in flight, not from splitting one burst across lanes.
+#include "kernels.cuh"
+#include "sigproc_device.cuh"
+
+namespace btsdsp {
+
+// ------------------------------------------------------------------------------------------------
+// burst addressing
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void burst_loc(const BurstSrc &s, long long i, long long *start, int *len) {
+  const long long g = s.first + i;
+  const int q = (int)(g & 3);
+  const int rule_len = (q == 0 ? 157 : 156) * s.sps;
+  if (s.pitch > 0) {
+    *start = i * s.pitch;
+    *len = s.lens ? s.lens[i] : rule_len;
+  } else {
+    const int off = q == 0 ? 0 : (q == 1 ? 157 : (q == 2 ? 313 : 469));
+    *start = ((g >> 2) * 625 + off) * s.sps;
+    *len = rule_len;
+  }
+}
+
+// warp-cooperative: copy the warp's nv bursts into tile rows (transposed), coalesced 8-byte loads
+__device__ __forceinline__ void stage_in(cf *tile, const BurstSrc &src, long long w0, int nv, int lane) {
+  for (int j = 0; j < nv; j++) {
+    long long start; int len;
+    burst_loc(src, w0 + j, &start, &len);
+    if (len > kBurstRows) len = kBurstRows;
+    const cf *g = src.base + start;
+    for (int i = lane; i < len; i += 32) tile[i * kTileStride + j] = __ldg(g + i);
+  }
+  __syncwarp();
+}
+
+// warp-cooperative: write the soft bits held in column j of `tile` (.x of each row) to global
+__device__ __forceinline__ void stage_out_soft(const cf *tile, float *soft, int soft_pitch, long long w0, int nv,
+                                               int lane, bool ok, int len) {
+  __syncwarp();
+  const float *tf = (const float *)tile;
+  for (int j = 0; j < nv; j++) {
+    const bool okj = __shfl_sync(0xffffffffu, (int)ok, j) != 0;
+    const int lenj = __shfl_sync(0xffffffffu, len, j);
+    float *dst = soft + (w0 + j) * (long long)soft_pitch;
+    for (int m = lane; m < soft_pitch; m += 32)
+      dst[m] = (okj && m < lenj) ? tf[(m * kTileStride + j) * 2] : 0.0F;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// table construction (init only; single thread, same serial order as the reference's init code)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_init_tables(DevTables *T) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // initGMSKRotationTables, sigProcLib.cpp:214-225
+  float phase = 0.0F;
+  const float inc = BTS_DIV(BTS_DIV(kPiF, 2.0F), (float)T->sps);
+  for (int i = 0; i < 157 * T->sps; i++) {
+    T->rot[i] = expj_lookup(T, phase);
+    T->revrot[i] = expj_lookup(T, -phase);
+    phase = BTS_ADD(phase, inc);
+  }
+}
+__global__ void k_init_sinc_grid(DevTables *T) {
+  const int j = blockIdx.x, i = threadIdx.x;          // 512 blocks x 24 threads
+  float v = 0.0F;
+  if (i < 21) {
+    // sinc(M_PI_F*(i-10-frac)) (:588) == sinc(M_PI_F*(i'-ix)) (:651) for frac = j/512: the float
+    // difference (i-10) - j/512 is exact either way.
+    const float d = BTS_SUB((float)(i - 10), (float)j * (1.0F / (float)kSincGrid));
+    v = sinc_exact(T, BTS_MUL(kPiF, d));
+  }
+  T->sinc_grid[j][i] = v;
+}
+void launch_init_tables(DevTables *T, cudaStream_t st) {
+  k_init_tables<<<1, 32, 0, st>>>(T);
+  k_init_sinc_grid<<<kSincGrid, 24, 0, st>>>(T);
+}
+
+// ------------------------------------------------------------------------------------------------
+// single vectors in global memory
+// ------------------------------------------------------------------------------------------------
+// convolve / correlate, all four realOnly branches of sigProcLib.cpp:319-367; one thread per output.
+__global__ void k_convolve(const cf *a, int la, int a_real, const cf *b, int lb, int b_real, cf *c, int start,
+                           int outsz, int corr) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= outsz) return;
+  const int t = start + n;
+  cf sum = mk(0.0F, 0.0F);
+  float rsum = 0.0F;
+  for (int k = 0; k < lb; k++) {
+    const int ai = t - k;
+    if (ai < 0) break;
+    if (ai >= la) continue;
+    cf tap = corr ? (b_real ? mk(b[lb - 1 - k].x, 0.0F) : cconj(b[lb - 1 - k])) : b[k];
+    const cf av = a[ai];
+    if (a_real && b_real) rsum = BTS_ADD(rsum, BTS_MUL(av.x, tap.x));
+    else if (a_real) sum = cadd(sum, cmulr(tap, av.x));
+    else if (b_real) sum = cadd(sum, cmulr(av, tap.x));
+    else sum = cadd(sum, cmul(av, tap));
+  }
+  c[n] = (a_real && b_real) ? mk(rsum, 0.0F) : sum;
+}
+void launch_convolve(const cf *a, int la, int a_real, const cf *b, int lb, int b_real, cf *c, int start, int outsz,
+                     int corr, cudaStream_t st) {
+  k_convolve<<<(outsz + 127) / 128, 128, 0, st>>>(a, la, a_real, b, lb, b_real, c, start, outsz, corr);
+}
+
+__global__ void k_peak_detect(const DevTables *T, const cf *v, int n, cf *peak, float *idx, float *avg) {
+  if (threadIdx.x != 0) return;
+  *peak = peak_detect<1, false>(T, View<1>{(cf *)v}, n, idx, avg);
+}
+void launch_peak_detect(const DevTables *T, const cf *v, int n, cf *peak, float *idx, float *avg, cudaStream_t st) {
+  k_peak_detect<<<1, 32, 0, st>>>(T, v, n, peak, idx, avg);
+}
+
+__global__ void k_interp_point(const DevTables *T, const cf *v, int n, float ix, cf *out) {
+  if (threadIdx.x != 0) return;
+  *out = interp_point<1>(T, View<1>{(cf *)v}, n, ix);
+}
+void launch_interp_point(const DevTables *T, const cf *v, int n, float ix, cf *out, cudaStream_t st) {
+  k_interp_point<<<1, 32, 0, st>>>(T, v, n, ix, out);
+}
+
+// delayVector on one long vector: fractional FIR one thread per sample into tmp, then the integer shift.
+__global__ void k_delay_frac(const DevTables *T, const cf *v, int n, float frac, cf *tmp) {
+  __shared__ float taps[21];
+  if (threadIdx.x == 0) delay_taps(T, frac, taps);
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tmp[i] = conv_cr_at<1>(View<1>{(cf *)v}, n, taps, 21, i + 10);
+}
+__global__ void k_delay_shift(const cf *src, cf *dst, int n, int intOffset) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = i - intOffset;                          // dst[i] = src[i - intOffset], zero outside
+  dst[i] = (s >= 0 && s < n) ? src[s] : mk(0.0F, 0.0F);
+}
+void launch_delay_vector(const DevTables *T, cf *v, int n, float delay, cf *tmp, cudaStream_t st) {
+  const int intOffset = (int)floorf(delay);
+  const float frac = delay - (float)intOffset;
+  const int nb = (n + 127) / 128;
+  if ((double)fabsf(frac) > 1e-2) {
+    k_delay_frac<<<nb, 128, 0, st>>>(T, v, n, frac, tmp);
+    k_delay_shift<<<nb, 128, 0, st>>>(tmp, v, n, intOffset);
+  } else if (intOffset != 0) {
+    cudaMemcpyAsync(tmp, v, (size_t)n * sizeof(cf), cudaMemcpyDeviceToDevice, st);
+    k_delay_shift<<<nb, 128, 0, st>>>(tmp, v, n, intOffset);
+  }
+}
+
+__global__ void k_scale_vector(cf *v, int n, int real_only, cf s) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = real_only ? cmulr(s, v[i].x) : cmul(v[i], s);      // scaleVector :713-730
+}
+void launch_scale_vector(cf *v, int n, int real_only, cf s, cudaStream_t st) {
+  k_scale_vector<<<(n + 127) / 128, 128, 0, st>>>(v, n, real_only, s);
+}
+
+__global__ void k_energy_detect(const cf *v, int n, unsigned win, float thr, float *avg, int *flag) {
+  if (threadIdx.x != 0) return;
+  *flag = energy_detect<1>(View<1>{(cf *)v}, n, win, thr, avg) ? 1 : 0;
+}
+void launch_energy_detect(const cf *v, int n, unsigned win, float thr, float *avg, int *flag, cudaStream_t st) {
+  k_energy_detect<<<1, 32, 0, st>>>(v, n, win, thr, avg, flag);
+}
+
+__global__ void k_design_dfe_generic(const cf *chan, int nchan, float snr, int nf, cf *w, cf *b) {
+  if (threadIdx.x != 0) return;
+  cf ch[kDfeMax], W[kDfeMax], B[kDfeMax];
+  for (int i = 0; i < nchan; i++) ch[i] = chan[i];
+  design_dfe<0, 0>(ch, nchan - 1, snr, nf, W, B);
+  for (int i = 0; i < nf; i++) w[i] = W[i];
+  for (int i = 0; i < nchan - 1; i++) b[i] = B[i];
+}
+void launch_design_dfe_generic(const cf *chan, int nchan, float snr, int nf, cf *w, cf *b, cudaStream_t st) {
+  k_design_dfe_generic<<<1, 32, 0, st>>>(chan, nchan, snr, nf, w, b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GMSK modulation, batched: one thread per output sample (modulateBurst :521-565)
+// guard = guards[i] when given, else 8 + ((first+i) % 4 == 0)  (Transceiver.cpp:105-106)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_modulate(const DevTables *__restrict__ T, const uint8_t *__restrict__ bits, int nbits,
+                           long long nbursts, int guard_rule, const uint8_t *__restrict__ guards, long long first,
+                           cf *__restrict__ out, long long pitch) {
+  const int sps = T->sps;
+  const long long i = blockIdx.x;
+  for (long long bi = i; bi < nbursts; bi += gridDim.x) {
+    const long long g = first + bi;
+    const int guard = guards ? guards[bi] : (guard_rule >= 0 ? guard_rule : 8 + ((g & 3) == 0));
+    const int n = sps * (nbits + guard);
+    long long start;
+    if (pitch > 0) start = bi * pitch;
+    else {
+      const int q = (int)(g & 3);
+      start = ((g >> 2) * 625 + (q == 0 ? 0 : (q == 1 ? 157 : (q == 2 ? 313 : 469)))) * sps;
+    }
+    const uint8_t *bb = bits + bi * nbits;
+    for (int t = threadIdx.x; t < n; t += blockDim.x)
+      out[start + t] = modulate_at(T, bb, nbits, n, sps, T->pulse, T->pulse_len, true, t);
+  }
+}
+void launch_modulate(const DevTables *T, const uint8_t *bits, int nbits, long long nbursts, int guard_rule,
+                     const uint8_t *guards, long long first, cf *out, long long pitch, cudaStream_t st) {
+  if (nbursts <= 0) return;
+  const int grid = (int)(nbursts < 148 * 64 ? nbursts : 148 * 64);
+  k_modulate<<<grid, 160, 0, st>>>(T, bits, nbits, nbursts, guard_rule, guards, first, out, pitch);
+}
+// the impulse-pulse variant generateMidamble needs (:794-797): pulse = {1.0} complex, guard 0
+__global__ void k_modulate_impulse(const DevTables *T, const uint8_t *bits, int nbits, cf *out) {
+  const int sps = T->sps, n = sps * nbits;
+  const cf one = mk(1.0F, 0.0F);
+  for (int t = threadIdx.x; t < n; t += blockDim.x) out[t] = modulate_at(T, bits, nbits, n, sps, &one, 1, false, t);
+}
+void launch_modulate_impulse(const DevTables *T, const uint8_t *bits, int nbits, cf *out, cudaStream_t st) {
+  k_modulate_impulse<<<1, 128, 0, st>>>(T, bits, nbits, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// normal-burst receive, fused: energy gate -> analyzeTrafficBurst -> designDFE -> equalizeBurst
+// (reference Transceiver.cpp:298-396 with estimateChannel == true for every burst); sps == 1.
+// One warp per CTA, one burst per lane.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCorrRows = 36;
+constexpr size_t kDemodSmem = (size_t)(2 * kBurstRows + kCorrRows) * kTileStride * sizeof(cf);
+
+__global__ void __launch_bounds__(32) k_demod_normal(const DevTables *__restrict__ T, BurstSrc src,
+                                                     const uint8_t *__restrict__ tsc, long long n, float detect_thr,
+                                                     float gate_thr, float snr_thr, NormalOut out) {
+  extern __shared__ cf tile[];
+  cf *A = tile, *B = tile + kBurstRows * kTileStride, *C = B + kBurstRows * kTileStride;
+  const int lane = threadIdx.x;
+  const long long w0 = (long long)blockIdx.x * 32;
+  const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
+  stage_in(A, src, w0, nv, lane);
+
+  const long long i = w0 + lane;
+  bool ok = false;
+  int len = 0;
+  if (lane < nv) {
+    long long start;
+    burst_loc(src, i, &start, &len);
+    const View<kTileStride> a{A + lane}, b{B + lane}, c{C + lane};
+    cf amp = mk(0.0F, 0.0F), chan[6], w[7], fb[5];
+    float toa = 0.0F, off = 0.0F;
+    bool pass = true;
+    if (gate_thr >= 0.0F) pass = energy_detect<kTileStride>(a, len, 20, gate_thr, nullptr);     // Transceiver.cpp:298
+    if (pass) ok = analyze_traffic<kTileStride, true>(T, a, tsc[i], detect_thr, 1, c, b, &amp, &toa, true, chan, &off);
+    if (ok) {
+      // Transceiver.cpp:340  SNRestimate = amplitude.norm2()/(thr*thr + 1.0)  (double division)
+      const float SNR = (float)((double)cnorm2(amp) / ((double)BTS_MUL(snr_thr, snr_thr) + 1.0));
+      const cf ia = cdiv(mk(1.0F, 0.0F), amp);
+#pragma unroll
+      for (int j = 0; j < 6; j++) chan[j] = cmul(chan[j], ia);                                  // :346
+      design_dfe<7, 5>(chan, 5, SNR, 7, w, fb);                                                 // :347
+      for (int m = 0; m < len; m++) a.st(m, cmul(a.ld(m), ia));                                 // :391
+      equalize_burst<kTileStride, 2 * kTileStride>(T, a, len, BTS_SUB(toa, off), w, 7, fb, 5, b,
+                                                   (float *)(B + lane));                      // :392-396
+    }
+    if (out.flag) out.flag[i] = ok ? 1 : 0;
+    if (out.amp) out.amp[i] = amp;
+    if (out.toa) out.toa[i] = toa;
+    if (out.off) out.off[i] = ok ? off : 0.0F;
+    if (out.chan) for (int j = 0; j < 6; j++) out.chan[i * 6 + j] = ok ? chan[j] : mk(0.0F, 0.0F);
+    if (out.w) for (int j = 0; j < 7; j++) out.w[i * 7 + j] = ok ? w[j] : mk(0.0F, 0.0F);
+    if (out.b) for (int j = 0; j < 5; j++) out.b[i * 5 + j] = ok ? fb[j] : mk(0.0F, 0.0F);
+  }
+  if (out.soft) stage_out_soft(B, out.soft, out.soft_pitch, w0, nv, lane, ok, len);
+}
+int launch_demod_normal(const DevTables *T, BurstSrc src, const uint8_t *tsc, long long n, float detect_thr,
+                        float gate_thr, float snr_thr, NormalOut out, cudaStream_t st) {
+  if (n <= 0) return 0;
+  k_demod_normal<<<(unsigned)((n + 31) / 32), 32, kDemodSmem, st>>>(T, src, tsc, n, detect_thr, gate_thr, snr_thr, out);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// analyzeTrafficBurst alone, batched.  SM = true: sps == 1, shared-memory tiles.  SM = false: any
+// sps, one thread per burst over global scratch (the functional path for sps = 4).
+// ------------------------------------------------------------------------------------------------
+template <bool SM>
+__global__ void __launch_bounds__(32) k_analyze(const DevTables *__restrict__ T, BurstSrc src,
+                                                const uint8_t *__restrict__ tsc, long long n, float detect_thr,
+                                                int request, NormalOut out, cf *scratch) {
+  extern __shared__ cf tile[];
+  const int lane = threadIdx.x, sps = src.sps;
+  const long long w0 = (long long)blockIdx.x * 32;
+  const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
+  if (SM) stage_in(tile, src, w0, nv, lane);
+  if (lane >= nv) return;
+  const long long i = w0 + lane;
+  long long start; int len;
+  burst_loc(src, i, &start, &len);
+  cf amp = mk(0.0F, 0.0F), chan[6 * kMaxSps];
+  float toa = 0.0F, off = 0.0F;
+  bool ok;
+  if (SM) {
+    cf *B = tile + kBurstRows * kTileStride, *C = B + kCorrRows * kTileStride;
+    ok = analyze_traffic<kTileStride, true>(T, View<kTileStride>{tile + lane}, tsc[i], detect_thr, 1,
+                                            View<kTileStride>{B + lane}, View<kTileStride>{C + lane}, &amp, &toa,
+                                            request != 0, chan, &off);
+  } else {
+    cf *s = scratch + (size_t)i * scratch_per_burst(sps);
+    ok = analyze_traffic<1, true>(T, View<1>{(cf *)src.base + start}, tsc[i], detect_thr, sps, View<1>{s},
+                                  View<1>{s + 36 * sps}, &amp, &toa, request != 0, chan, &off);
+  }
+  if (out.flag) out.flag[i] = ok ? 1 : 0;
+  if (out.amp) out.amp[i] = amp;
+  if (out.toa) out.toa[i] = toa;
+  const bool have = ok && request;
+  if (out.off) out.off[i] = have ? off : 0.0F;
+  if (out.chan) for (int j = 0; j < 6 * sps; j++) out.chan[i * 6 * sps + j] = have ? chan[j] : mk(0.0F, 0.0F);
+}
+constexpr size_t kAnalyzeSmem = (size_t)(kBurstRows + 2 * kCorrRows) * kTileStride * sizeof(cf);
+int launch_analyze(const DevTables *T, BurstSrc src, const uint8_t *tsc, long long n, float detect_thr, int request,
+                   NormalOut out, cf *scratch, int force_generic, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const unsigned grid = (unsigned)((n + 31) / 32);
+  if (src.sps == 1 && !force_generic) {
+    k_analyze<true><<<grid, 32, kAnalyzeSmem, st>>>(T, src, tsc, n, detect_thr, request, out, scratch);
+  } else {
+    k_analyze<false><<<grid, 32, 0, st>>>(T, src, tsc, n, detect_thr, request, out, scratch);
+  }
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// access bursts: detectRACHBurst (+ demodulateBurst when demod != 0), Transceiver.cpp:360-389
+// ------------------------------------------------------------------------------------------------
+template <bool SM>
+__global__ void __launch_bounds__(32) k_rach(const DevTables *__restrict__ T, BurstSrc src, long long n,
+                                             float detect_thr, int demod, NormalOut out, cf *scratch) {
+  extern __shared__ cf tile[];
+  const int lane = threadIdx.x, sps = src.sps;
+  const long long w0 = (long long)blockIdx.x * 32;
+  const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
+  if (SM) stage_in(tile, src, w0, nv, lane);
+  const long long i = w0 + lane;
+  bool ok = false;
+  int len = 0, nsoft = 0;
+  cf *B = tile + kBurstRows * kTileStride;
+  if (lane < nv) {
+    long long start;
+    burst_loc(src, i, &start, &len);
+    cf amp = mk(0.0F, 0.0F);
+    float toa = 0.0F;
+    if (SM) {
+      const View<kTileStride> a{tile + lane}, b{B + lane};
+      ok = detect_rach<kTileStride, true>(T, a, len, detect_thr, 1, b, &amp, &toa);
+      if (ok && demod) nsoft = demodulate_burst<kTileStride, 2 * kTileStride>(T, a, len, 1, amp, toa, b, (float *)(B + lane));
+    } else {
+      cf *s = scratch + (size_t)i * scratch_per_burst(sps);
+      const View<1> corr{s}, x{s + 157 * sps};
+      ok = detect_rach<1, true>(T, View<1>{(cf *)src.base + start}, len, detect_thr, sps, corr, &amp, &toa);
+      if (ok && demod) {
+        for (int m = 0; m < len; m++) x.st(m, src.base[start + m]);
+        float *sp = out.soft + i * (long long)out.soft_pitch;
+        nsoft = demodulate_burst<1, 1>(T, x, len, sps, amp, toa, corr, sp);
+        for (int m = nsoft; m < out.soft_pitch; m++) sp[m] = 0.0F;
+      } else if (demod && out.soft) {
+        float *sp = out.soft + i * (long long)out.soft_pitch;
+        for (int m = 0; m < out.soft_pitch; m++) sp[m] = 0.0F;
+      }
+    }
+    if (out.flag) out.flag[i] = ok ? 1 : 0;
+    if (out.amp) out.amp[i] = amp;
+    if (out.toa) out.toa[i] = toa;
+  }
+  if (SM && demod && out.soft) stage_out_soft(B, out.soft, out.soft_pitch, w0, nv, lane, ok, nsoft);
+}
+constexpr size_t kRachSmem = (size_t)(2 * kBurstRows) * kTileStride * sizeof(cf);
+int launch_rach(const DevTables *T, BurstSrc src, long long n, float detect_thr, int demod, NormalOut out, cf *scratch,
+                int force_generic, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const unsigned grid = (unsigned)((n + 31) / 32);
+  if (src.sps == 1 && !force_generic) {
+    k_rach<true><<<grid, 32, kRachSmem, st>>>(T, src, n, detect_thr, demod, out, scratch);
+  } else {
+    k_rach<false><<<grid, 32, 0, st>>>(T, src, n, detect_thr, demod, out, scratch);
+  }
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// equalizeBurst with caller-supplied DFE taps (the cached-filter mode of Transceiver.cpp:391-396);
+// sps == 1.  burst_out (optional) receives the delayed burst: the reference mutates its input.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_equalize(const DevTables *__restrict__ T, BurstSrc src, long long n,
+                                                 const float *__restrict__ toa, const cf *__restrict__ w,
+                                                 const cf *__restrict__ b, float *soft, int soft_pitch,
+                                                 cf *burst_out, long long out_pitch) {
+  extern __shared__ cf tile[];
+  cf *A = tile, *B = tile + kBurstRows * kTileStride;
+  const int lane = threadIdx.x;
+  const long long w0 = (long long)blockIdx.x * 32;
+  const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
+  stage_in(A, src, w0, nv, lane);
+  const long long i = w0 + lane;
+  int len = 0;
+  if (lane < nv) {
+    long long start;
+    burst_loc(src, i, &start, &len);
+    cf W[7], F[5];
+    for (int j = 0; j < 7; j++) W[j] = w[i * 7 + j];
+    for (int j = 0; j < 5; j++) F[j] = b[i * 5 + j];
+    equalize_burst<kTileStride, 2 * kTileStride>(T, View<kTileStride>{A + lane}, len, toa[i], W, 7, F, 5,
+                                                 View<kTileStride>{B + lane}, (float *)(B + lane));
+  }
+  stage_out_soft(B, soft, soft_pitch, w0, nv, lane, lane < nv, len);
+  if (burst_out) {
+    for (int j = 0; j < nv; j++) {
+      const int lenj = __shfl_sync(0xffffffffu, len, j);
+      for (int m = lane; m < lenj; m += 32) burst_out[(w0 + j) * out_pitch + m] = A[m * kTileStride + j];
+    }
+  }
+}
+int launch_equalize(const DevTables *T, BurstSrc src, long long n, const float *toa, const cf *w, const cf *b,
+                    float *soft, int soft_pitch, cf *burst_out, long long out_pitch, cudaStream_t st) {
+  if (n <= 0) return 0;
+  k_equalize<<<(unsigned)((n + 31) / 32), 32, kRachSmem, st>>>(T, src, n, toa, w, b, soft, soft_pitch, burst_out, out_pitch);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// demodulateBurst alone (slicer path), any sps: one thread per burst over global scratch
+// ------------------------------------------------------------------------------------------------
+__global__ void k_demodulate(const DevTables *__restrict__ T, BurstSrc src, long long n, const cf *__restrict__ amp,
+                             const float *__restrict__ toa, float *soft, int soft_pitch, cf *scratch) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long start; int len;
+  burst_loc(src, i, &start, &len);
+  cf *s = scratch + (size_t)i * scratch_per_burst(src.sps);
+  const View<1> x{s}, tmp{s + 157 * src.sps};
+  for (int m = 0; m < len; m++) x.st(m, src.base[start + m]);
+  float *sp = soft + i * (long long)soft_pitch;
+  const int ns = demodulate_burst<1, 1>(T, x, len, src.sps, amp[i], toa[i], tmp, sp);
+  for (int m = ns; m < soft_pitch; m++) sp[m] = 0.0F;
+}
+int launch_demodulate(const DevTables *T, BurstSrc src, long long n, const cf *amp, const float *toa, float *soft,
+                      int soft_pitch, cf *scratch, cudaStream_t st) {
+  if (n <= 0) return 0;
+  k_demodulate<<<(unsigned)((n + 31) / 32), 32, 0, st>>>(T, src, n, amp, toa, soft, soft_pitch, scratch);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// designDFE batched (Nf = 7, nu = 5): one thread per channel estimate, registers only
+// ------------------------------------------------------------------------------------------------
+__global__ void k_design_dfe(const cf *__restrict__ chan, const float *__restrict__ snr, long long n, cf *w, cf *b) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  cf ch[6], W[7], F[5];
+  for (int j = 0; j < 6; j++) ch[j] = chan[i * 6 + j];
+  design_dfe<7, 5>(ch, 5, snr[i], 7, W, F);
+  for (int j = 0; j < 7; j++) w[i * 7 + j] = W[j];
+  for (int j = 0; j < 5; j++) b[i * 5 + j] = F[j];
+}
+int launch_design_dfe(const cf *chan, const float *snr, long long n, cf *w, cf *b, cudaStream_t st) {
+  if (n <= 0) return 0;
+  k_design_dfe<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(chan, snr, n, w, b);
+  return 1;
+}
+
+// equalizeBurst on one vector with arbitrary tap counts (the sigProcLib.h entry point); one thread.
+__global__ void k_equalize_generic(const DevTables *T, cf *burst, int n, float toa, const cf *w, int nw, const cf *b,
+                                   int nb, cf *tmp, float *soft) {
+  if (threadIdx.x != 0) return;
+  cf W[kDfeMax], F[kDfeMax];
+  for (int i = 0; i < nw; i++) W[i] = w[i];
+  for (int i = 0; i < nb; i++) F[i] = b[i];
+  equalize_burst<1, 1>(T, View<1>{burst}, n, toa, W, nw, F, nb, View<1>{tmp}, soft);
+}
+void launch_equalize_generic(const DevTables *T, cf *burst, int n, float toa, const cf *w, int nw, const cf *b, int nb,
+                             cf *tmp, float *soft, cudaStream_t st) {
+  k_equalize_generic<<<1, 32, 0, st>>>(T, burst, n, toa, w, nw, b, nb, tmp, soft);
+}
+
+int configure_kernels() {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(k_demod_normal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDemodSmem);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_analyze<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAnalyzeSmem);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_rach<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRachSmem);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_equalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRachSmem);
+  return (int)e;
+}
+
+}  // namespace btsdsp

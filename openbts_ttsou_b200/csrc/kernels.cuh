@@ -1,0 +1,78 @@
+// kernels.cuh -- launchers of the sm_100a kernels (definitions in kernels.cu / resample.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "tables.h"
+
+namespace btsdsp {
+
+// Where the bursts of a batch live.  pitch > 0: burst i starts at base + i*pitch (complex samples),
+// its length is lens[i] or, when lens is null, the GSM 157/156/156/156 rule on (first + i).
+// pitch == 0: base is a continuous slot stream that begins on a 157-sample slot; burst g = first + i
+// starts at (g/4)*625*sps + {0,157,313,469}[g%4]*sps  (reference radioInterface.cpp:370-394).
+struct BurstSrc {
+  const cf *base;
+  long long pitch;
+  const int *lens;
+  long long first;
+  int sps;
+};
+
+struct NormalOut {      // per burst; null pointers are skipped
+  int *flag;            // detection flag                                   (analyzeTrafficBurst return)
+  cf *amp;              // amplitude estimate
+  float *toa;           // TOA estimate, symbols
+  cf *chan;             // [6*sps] channel response after the caller's 1/amp scaling (demod) or raw (analyze)
+  float *off;           // channelResponseOffset
+  cf *w;                // [7] DFE feed-forward taps
+  cf *b;                // [5] DFE feedback taps
+  float *soft;          // [soft_pitch] soft bits, zeros when not detected
+  int soft_pitch;
+};
+
+constexpr int kTileStride = 33;      // complex samples between rows of a transposed tile (32 lanes + 1 pad)
+constexpr int kBurstRows = 160;      // >= 157
+
+// -- per-device kernel attributes (dynamic shared memory sizes); call once per device
+int configure_kernels();
+
+// -- table construction (init only)
+void launch_init_tables(DevTables *T, cudaStream_t st);
+void launch_modulate_impulse(const DevTables *T, const uint8_t *bits, int nbits, cf *out, cudaStream_t st);
+
+// -- single vectors in global memory (sigProcLib.h surface); one thread or one thread per output
+void launch_convolve(const cf *a, int la, int a_real, const cf *b, int lb, int b_real, cf *c, int start, int outsz,
+                     int corr, cudaStream_t st);
+void launch_peak_detect(const DevTables *T, const cf *v, int n, cf *peak, float *idx, float *avg, cudaStream_t st);
+void launch_interp_point(const DevTables *T, const cf *v, int n, float ix, cf *out, cudaStream_t st);
+void launch_delay_vector(const DevTables *T, cf *v, int n, float delay, cf *tmp, cudaStream_t st);
+void launch_scale_vector(cf *v, int n, int real_only, cf s, cudaStream_t st);
+void launch_energy_detect(const cf *v, int n, unsigned win, float thr, float *avg, int *flag, cudaStream_t st);
+void launch_resample_generic(const cf *x, int n, int P, int Q, const float *lpf, int L, cf *out, int outn,
+                             cudaStream_t st);
+void launch_equalize_generic(const DevTables *T, cf *burst, int n, float toa, const cf *w, int nw, const cf *b, int nb,
+                             cf *tmp, float *soft, cudaStream_t st);
+void launch_design_dfe_generic(const cf *chan, int nchan, float snr, int nf, cf *w, cf *b, cudaStream_t st);
+
+// -- batched
+void launch_modulate(const DevTables *T, const uint8_t *bits, int nbits, long long nbursts, int guard_rule,
+                     const uint8_t *guards, long long first, cf *out, long long pitch, cudaStream_t st);
+void launch_resample_rx(const DevTables *T, const cf *in, int has_history, long long nchunks, cf *out, cudaStream_t st);
+void launch_resample_tx(const DevTables *T, const cf *in, int has_history, long long nchunks, int16_t *out,
+                        cudaStream_t st);
+int launch_demod_normal(const DevTables *T, BurstSrc src, const uint8_t *tsc, long long n, float detect_thr,
+                        float gate_thr, float snr_thr, NormalOut out, cudaStream_t st);
+int launch_analyze(const DevTables *T, BurstSrc src, const uint8_t *tsc, long long n, float detect_thr, int request,
+                   NormalOut out, cf *scratch, int force_generic, cudaStream_t st);
+int launch_rach(const DevTables *T, BurstSrc src, long long n, float detect_thr, int demod, NormalOut out, cf *scratch,
+                int force_generic, cudaStream_t st);
+int launch_equalize(const DevTables *T, BurstSrc src, long long n, const float *toa, const cf *w, const cf *b,
+                    float *soft, int soft_pitch, cf *burst_out, long long out_pitch, cudaStream_t st);
+int launch_demodulate(const DevTables *T, BurstSrc src, long long n, const cf *amp, const float *toa, float *soft,
+                      int soft_pitch, cf *scratch, cudaStream_t st);
+int launch_design_dfe(const cf *chan, const float *snr, long long n, cf *w, cf *b, cudaStream_t st);
+
+// scratch (complex samples) the generic-sps global-memory variants need per burst
+__host__ __device__ inline size_t scratch_per_burst(int sps) { return (size_t)(2 * 157 + 36) * sps + 64; }
+
+}  // namespace btsdsp

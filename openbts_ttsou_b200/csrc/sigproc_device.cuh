@@ -1,0 +1,446 @@
+// sigproc_device.cuh -- the burst-DSP algorithms as thread-serial functions over strided views.
+//
+// One CUDA thread owns one burst (or one vector) and walks it in exactly the order the reference's
+// scalar loops do, so every comparison the reference makes (peak search, early/late balancing,
+// detection thresholds, symbol decisions) sees bit-identical floats.  Parallelism comes from the
+// batch: 32 bursts per warp, each lane reading its own column of a transposed shared-memory tile
+// (View<33>, conflict-free), thousands of warps per launch.  The same functions run over plain
+// global vectors (View<1>) for the single-vector sigProcLib.h surface.
+//
+// All functions are __host__ __device__ so tests/hostemu can replay the kernels' control flow on a
+// CPU without a GPU; the product never calls them on the host.
+//
+// Reference lines are cited per function (Transceiver/sigProcLib.cpp unless another file is named).
+#pragma once
+#include "cplx.cuh"
+#include "tables.h"
+
+namespace btsdsp {
+
+constexpr float kPiF = (float)3.14159265358979323846;                 // M_PI_F   :43
+constexpr float k2PiF = (float)(2.0 * 3.14159265358979323846);        // M_2PI_F  :44
+constexpr float k1_2PiF = 1 / k2PiF;                                   // M_1_2PI_F :45
+
+// cosLookup / sinLookup :163-188.  The reference range-reduces with `while (arg > 1) arg -= 1;
+// while (arg < 0) arg += 1;`.  Every step of those loops but the last +1 is exact (the magnitude
+// shrinks on the same ulp grid), so one subtraction of ceil(arg)-1, or one rounded addition of
+// ceil(-arg), yields the same float -- and cannot spin on Inf/NaN/huge inputs as the loops would.
+BTS_HD float trig_lookup(const float *__restrict__ T, float x) {
+  float arg = BTS_MUL(x, k1_2PiF);
+  if (arg > 1.0F) arg = BTS_SUB(arg, BTS_SUB(ceilf(arg), 1.0F));
+  else if (arg < 0.0F) arg = BTS_ADD(arg, ceilf(-arg));
+  const float argT = BTS_MUL(arg, (float)kTrig);
+  int argI = (int)argT;
+  argI = argI < 0 ? 0 : (argI > kTrig ? kTrig : argI);                 // only NaN/Inf get here out of range
+  const float delta = BTS_SUB(argT, (float)argI);
+  const float iDelta = BTS_SUB(1.0F, delta);
+  return BTS_ADD(BTS_MUL(iDelta, T[argI]), BTS_MUL(delta, T[argI + 1]));
+}
+
+// sinc :567-571
+BTS_HD float sinc_exact(const DevTables *__restrict__ T, float x) {
+  if ((x >= 0.01F) || (x <= -0.01F)) return BTS_DIV(trig_lookup(T->sinT, x), x);
+  return 1.0F;
+}
+
+// expjLookup :192-204
+BTS_HD cf expj_lookup(const DevTables *__restrict__ T, float x) {
+  return mk(trig_lookup(T->cosT, x), trig_lookup(T->sinT, x));
+}
+
+// One output sample of convolve() :267-408 (symmetry NONE), complex data x complex taps.
+// c[t] = sum_{k=0..lb-1} a[t-k]*b[k], taps with t-k >= la skipped, loop ends at t-k < 0.
+// `corr` applies correlate()'s tap transform on the fly (:474-503): tap k = conj(b[lb-1-k]).
+template <int S>
+BTS_HD cf conv_cc_at(View<S> a, int la, const cf *__restrict__ b, int lb, int t, bool corr) {
+  cf sum = mk(0.0F, 0.0F);
+  for (int k = 0; k < lb; k++) {
+    int ai = t - k;
+    if (ai < 0) break;
+    if (ai < la) {
+      cf tap = corr ? cconj(b[lb - 1 - k]) : b[k];
+      sum = cadd(sum, cmul(a.ld(ai), tap));
+    }
+  }
+  return sum;
+}
+
+// Same, complex data x real taps (the `b->isRealOnly()` branch :345-354): sum += a * b.real().
+template <int S>
+BTS_HD cf conv_cr_at(View<S> a, int la, const float *__restrict__ b, int lb, int t) {
+  cf sum = mk(0.0F, 0.0F);
+  for (int k = 0; k < lb; k++) {
+    int ai = t - k;
+    if (ai < 0) break;
+    if (ai < la) sum = cadd(sum, cmulr(a.ld(ai), b[k]));
+  }
+  return sum;
+}
+
+BTS_HD int no_delay_start(int lb) { return (lb % 2) ? lb / 2 : lb / 2 - 1; }   // :295-301
+
+// interpolatePoint :639-659 (complex input).
+template <int S>
+BTS_HD cf interp_point(const DevTables *__restrict__ T, View<S> sig, int n, float ix) {
+  int start = (int)(floorf(ix) - 10);
+  if (start < 0) start = 0;
+  int end = (int)(floorf(ix) + 11);
+  if ((unsigned long long)(unsigned)end > (unsigned long long)n - 1) end = n - 1;
+  cf p = mk(0.0F, 0.0F);
+  for (int i = start; i < end; i++)
+    p = cadd(p, cmulr(sig.ld(i), sinc_exact(T, BTS_MUL(kPiF, BTS_SUB((float)i, ix)))));
+  return p;
+}
+
+// interpolatePoint for ix on the 1/512 grid (all peakDetect ever asks for): the 21 sinc values are a
+// row of DevTables::sinc_grid; identical floats, no trig/divide in the loop.
+template <int S>
+BTS_HD cf interp_point_grid(const float *__restrict__ row, View<S> sig, int n, int I) {
+  int start = I - 10;
+  if (start < 0) start = 0;
+  int end = I + 11;
+  if ((unsigned long long)(unsigned)end > (unsigned long long)n - 1) end = n - 1;
+  cf p = mk(0.0F, 0.0F);
+  for (int i = start; i < end; i++) p = cadd(p, cmulr(sig.ld(i), row[i - I + 10]));
+  return p;
+}
+
+// peakDetect :663-711.  Returns the interpolated peak; *peakIndex in samples (integer + k/512).
+// GRID selects the table-driven interpolator (exactly equal; see DevTables::sinc_grid).
+template <int S, bool GRID>
+BTS_HD cf peak_detect(const DevTables *__restrict__ T, View<S> v, int n, float *peakIndex, float *avgPwr) {
+  float maxVal = 0.0F, maxIndex = -1.0F, sumPower = 0.0F;
+  for (int i = 0; i < n; i++) {
+    float p = cnorm2(v.ld(i));
+    if (p > maxVal) { maxVal = p; maxIndex = (float)i; }
+    sumPower = BTS_ADD(sumPower, p);
+  }
+  float early = BTS_SUB(maxIndex, 1.0F), late = BTS_ADD(maxIndex, 1.0F), incr = 0.5F;
+  cf pk;
+  if (GRID) {
+    // early = I + j/512 exactly; late = early + 2 shares the row; so does the final early + 1.
+    int e512 = ((int)maxIndex - 1) * kSincGrid;                        // early * 512, exact integer
+    int step = kSincGrid / 2;
+    while (step >= 1) {
+      int I = e512 >> 9, j = e512 & (kSincGrid - 1);                   // floor and fraction (two's complement ok)
+      const float *row = T->sinc_grid[j];
+      float e = cnorm2(interp_point_grid<S>(row, v, n, I)), l = cnorm2(interp_point_grid<S>(row, v, n, I + 2));
+      if (e < l) e512 += step;
+      else if (e > l) e512 -= step;
+      else break;
+      step >>= 1;
+    }
+    int I = (e512 >> 9) + 1, j = e512 & (kSincGrid - 1);
+    maxIndex = BTS_ADD((float)e512 * (1.0F / kSincGrid), 1.0F);        // exact: |e512| < 2^24
+    pk = interp_point_grid<S>(T->sinc_grid[j], v, n, I);
+  } else {
+    while (incr > 1.0F / 1024.0F) {
+      float e = cnorm2(interp_point<S>(T, v, n, early)), l = cnorm2(interp_point<S>(T, v, n, late));
+      if (e < l) early = BTS_ADD(early, incr);
+      else if (e > l) early = BTS_SUB(early, incr);
+      else break;
+      incr = incr * 0.5F;
+      late = BTS_ADD(early, 2.0F);
+    }
+    maxIndex = BTS_ADD(early, 1.0F);
+    pk = interp_point<S>(T, v, n, maxIndex);
+  }
+  if (peakIndex) *peakIndex = maxIndex;
+  if (avgPwr) *avgPwr = BTS_DIV(BTS_SUB(sumPower, cnorm2(pk)), (float)(n - 1));
+  return pk;
+}
+
+// The 21 sinc taps of delayVector :583-588 for fractional offset `frac`.
+BTS_HD void delay_taps(const DevTables *__restrict__ T, float frac, float *taps) {
+  float f512 = frac * (float)kSincGrid;
+  int j = (int)f512;
+  if ((float)j == f512 && j >= 0 && j < kSincGrid) {                   // on the 1/512 grid: table row, reversed role:
+    // tap i multiplies sinc(pi*(i-10-frac)) = sinc(pi*(m - j/512)) with m = i-10
+    const float *row = T->sinc_grid[j];
+    for (int i = 0; i < 21; i++) taps[i] = row[i];
+  } else {
+    for (int i = 0; i < 21; i++) taps[i] = sinc_exact(T, BTS_MUL(kPiF, BTS_SUB((float)(i - 10), frac)));
+  }
+}
+
+// delayVector :573-616, in place on v with scratch tmp (same length).  v_real is never set on the path.
+template <int S>
+BTS_HD void delay_vector(const DevTables *__restrict__ T, View<S> v, int n, float delay, View<S> tmp) {
+  int intOffset = (int)floorf(delay);
+  float frac = BTS_SUB(delay, (float)intOffset);
+  bool shifted = false;
+  if ((double)fabsf(frac) > 1e-2) {
+    float taps[21];
+    delay_taps(T, frac, taps);
+    for (int i = 0; i < n; i++) tmp.st(i, conv_cr_at<S>(v, n, taps, 21, i + 10));   // NO_DELAY, Lb = 21 -> start 10
+    shifted = true;
+  }
+  // integer part :597-613 (reads `tmp` when the fractional filter ran, else v itself, in a safe order)
+  if (intOffset < 0) {
+    int io = -intOffset, w = 0;
+    for (int s = io; s < n; s++) v.st(w++, shifted ? tmp.ld(s) : v.ld(s));
+    while (w < n) v.st(w++, mk(0.0F, 0.0F));
+  } else {
+    int w = n - 1;
+    for (int s = n - 1 - intOffset; s >= 0; s--) v.st(w--, shifted ? tmp.ld(s) : v.ld(s));
+    while (w >= 0) v.st(w--, mk(0.0F, 0.0F));
+  }
+}
+
+
+// vectorSlicer :507-519 on one value
+BTS_HD float soft_slice(float x) {
+  float s = BTS_MUL(0.5F, BTS_ADD(x, 1.0F));        // 0.5*(x+1.0F): the double product is an exact scaling
+  if (s > 1.0F) s = 1.0F;
+  if (s < 0.0F) s = 0.0F;
+  return s;
+}
+
+// energyDetect :916-932
+template <int S>
+BTS_HD bool energy_detect(View<S> v, int n, unsigned win, float thr, float *avg) {
+  float energy = 0.0F;
+  if (win > (unsigned)n) win = n;
+  for (unsigned i = 0; i < win; i++) energy = BTS_ADD(energy, cnorm2(v.ld(i)));
+  float a = BTS_DIV(energy, (float)win);
+  if (avg) *avg = a;
+  return a > BTS_MUL(thr, thr);
+}
+
+// analyzeTrafficBurst :935-1037.  burst = the whole received slot; corr/tmp = scratch of 36*sps samples.
+// chan (6*sps, thread-local) and *chanOff are written only when request && detected.
+template <int S, bool GRID>
+BTS_HD bool analyze_traffic(const DevTables *__restrict__ T, View<S> burst, int tsc, float thr, int sps,
+                            View<S> corr, View<S> tmp, cf *amplitude, float *TOA, bool request, cf *chan,
+                            float *chanOff) {
+  const int L = 36 * sps, lb = 16 * sps;
+  View<S> seg = burst.at(56 * sps);
+  const cf *seq = T->mid_seq[tsc];
+  const int start = no_delay_start(lb);
+  for (int i = 0; i < L; i++) corr.st(i, conv_cc_at<S>(seg, L, seq, lb, start + i, true));
+  float toa;
+  cf amp = peak_detect<S, GRID>(T, corr, L, &toa, nullptr);
+  if ((toa < 0.0F) || (toa > (float)L)) { *amplitude = mk(0.0F, 0.0F); *TOA = toa; return false; }
+  const int p = (int)rintf(toa);
+  float valley = 0.0F;
+  int numRms = 0;
+  for (int i = 2 * sps; i <= 5 * sps; i++) {
+    if (p - i >= 0) { valley = BTS_ADD(valley, cnorm2(corr.ld(p - i))); numRms++; }
+    if (p + i < L)  { valley = BTS_ADD(valley, cnorm2(corr.ld(p + i))); numRms++; }
+  }
+  if (numRms < 2) { *amplitude = mk(0.0F, 0.0F); *TOA = toa; return false; }
+  const float RMS = (float)((double)BTS_SQRT(BTS_DIV(valley, (float)numRms)) + 0.00001);
+  const float peakToMean = BTS_DIV(cabs_(amp), RMS);
+  amp = cdiv(amp, T->mid_gain[tsc]);
+  toa = BTS_SUB(toa, T->mid_toa[tsc]);
+  toa = BTS_SUB(toa, (float)((66 - 56) * sps));
+  *amplitude = amp;
+  *TOA = toa;
+  const bool detected = peakToMean > thr;
+  if (request && detected) {
+    const float TOAoffset = BTS_ADD(T->mid_toa[tsc], (float)((66 - 56) * sps));
+    delay_vector<S>(T, corr, L, -toa, tmp);
+    const int clen = 6 * sps;
+    float maxEnergy = -1.0F;
+    int maxI = -1;
+    for (int i = 0; i < 7; i++) {
+      const float pos = BTS_ADD(TOAoffset, (float)((i - 5) * sps));
+      if (BTS_ADD(pos, (float)clen) > (float)L) continue;
+      if (pos < 0.0F) continue;
+      const int s0 = (int)floorf(pos);
+      float energy = 0.0F;
+      for (int j = 0; j < clen; j++) energy = BTS_ADD(energy, cnorm2(corr.ld(s0 + j)));
+      if ((double)energy > 0.95 * (double)maxEnergy) { maxI = i; maxEnergy = energy; }
+    }
+    const int s0 = (int)floorf(BTS_ADD(TOAoffset, (float)((maxI - 5) * sps)));
+    const cf g = cdiv(mk(1.0F, 0.0F), T->mid_gain[tsc]);
+    for (int j = 0; j < clen; j++) chan[j] = cmul(corr.ld(s0 + j), g);
+    *chanOff = (float)(5 * sps - maxI);
+  }
+  return detected;
+}
+
+// detectRACHBurst :860-914.  corr = scratch of n samples.
+template <int S, bool GRID>
+BTS_HD bool detect_rach(const DevTables *__restrict__ T, View<S> burst, int n, float thr, int sps, View<S> corr,
+                        cf *amplitude, float *TOA) {
+  const int lb = 41 * sps;
+  const int start = no_delay_start(lb);
+  for (int i = 0; i < n; i++) corr.st(i, conv_cc_at<S>(burst, n, T->rach_seq, lb, start + i, true));
+  float toa;
+  cf pk = peak_detect<S, GRID>(T, corr, n, &toa, nullptr);
+  if ((toa < 0.0F) || (toa > (float)n)) { *amplitude = mk(0.0F, 0.0F); *TOA = toa; return false; }
+  const int p = (int)rintf(toa);
+  float valley = 0.0F, numSamples = 0.0F;
+  for (int i = 57 * sps; i <= 107 * sps; i++) {
+    if (p + i >= n) break;
+    valley = BTS_ADD(valley, cnorm2(corr.ld(p + i)));
+    numSamples = numSamples + 1.0F;
+  }
+  if (numSamples < 2.0F) { *amplitude = mk(0.0F, 0.0F); *TOA = toa; return false; }
+  const float RMS = (float)((double)BTS_SQRT(BTS_DIV(valley, numSamples)) + 0.00001);
+  const float peakToMean = BTS_DIV(cabs_(pk), RMS);
+  *amplitude = cdiv(pk, T->rach_gain);
+  *TOA = BTS_SUB(BTS_SUB(toa, T->rach_toa), (float)(8 * sps));
+  return peakToMean > thr;
+}
+
+// designDFE :1246-1340 (Al-Dhahir & Cioffi fast Cholesky recursion).  NF/NU > 0 fix the sizes at compile
+// time (everything unrolls into registers); NF == 0 takes them from nf/nu at run time (<= kDfeMax).
+template <int NF, int NU>
+BTS_HD void design_dfe(const cf *chan, int nu_rt, float SNR, int nf_rt, cf *w, cf *b) {
+  const int Nf = NF ? NF : nf_rt, nu = NF ? NU : nu_rt;
+  constexpr int MF = NF ? NF : kDfeMax, ML = NF ? NF + NU : 2 * kDfeMax;
+  cf G0[MF], G1[MF], G0n[MF], G1n[MF], v[MF];
+  cf L[MF][ML];
+#pragma unroll
+  for (int j = 0; j < MF; j++) { G0[j] = mk(0.0F, 0.0F); G1[j] = mk(0.0F, 0.0F); }
+#pragma unroll
+  for (int i = 0; i < MF; i++)
+#pragma unroll
+    for (int j = 0; j < ML; j++) L[i][j] = mk(0.0F, 0.0F);
+  G0[0] = mk(BTS_DIV(1.0F, BTS_SQRT(SNR)), 0.0F);                      // 1.0/sqrtf(SNR) :1261 (double div is innocuous)
+#pragma unroll
+  for (int j = 0; j < MF; j++) if (j <= nu && j < Nf) G1[j] = cconj(chan[j]);
+  float d = 0.0F;
+#pragma unroll
+  for (int i = 0; i < MF; i++) {
+    if (i < Nf) {
+      d = BTS_ADD(cnorm2(G0[0]), cnorm2(G1[0]));
+      const cf g0c = cconj(G0[0]), g1c = cconj(G1[0]);
+#pragma unroll
+      for (int j = 0; j < MF; j++)
+        if (j < Nf && i + j < Nf + nu) L[i][i + j] = cdivr(cadd(cmul(G0[j], g0c), cmul(G1[j], g1c)), d);
+      const cf k = cdiv(G1[0], G0[0]);
+      if (i != Nf - 1) {
+        const cf kc = cconj(k), nk = cmulr(k, -1.0F);
+#pragma unroll
+        for (int j = 0; j < MF; j++) if (j < Nf) {
+          G0n[j] = cadd(cmul(G1[j], kc), G0[j]);
+          G1n[j] = cadd(cmul(G0[j], nk), G1[j]);
+        }
+        const cf s = mk(BTS_DIV(1.0F, BTS_SQRT(BTS_ADD(1.0F, cnorm2(k)))), 0.0F);   // :1294-1295
+#pragma unroll
+        for (int j = 0; j < MF; j++) if (j < Nf) {
+          G0[j] = cmul(G0n[j], s);
+          G1[j] = cmul((j + 1 < Nf) ? G1n[j + 1] : mk(0.0F, 0.0F), s);             // delayVector(G1new,-1.0)
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < (NF ? NU : kDfeMax); j++)
+    if (j < nu) b[j] = cconj(cmul(L[Nf - 1][Nf + j], mk(-1.0F, 0.0F)));
+  v[Nf - 1] = mk(1.0F, 0.0F);
+#pragma unroll
+  for (int kk = MF - 2; kk >= 0; kk--) {
+    if (kk <= Nf - 2) {
+      cf vk = mk(0.0F, 0.0F);
+#pragma unroll
+      for (int j = 1; j < MF; j++) if (j >= kk + 1 && j < Nf) vk = csub(vk, cmul(v[j], L[kk][j]));
+      v[kk] = vk;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MF; i++) {
+    if (i < Nf) {
+      cf wi = mk(0.0F, 0.0F);
+      const int endPt = (nu < (Nf - 1 - i)) ? nu : (Nf - 1 - i);
+#pragma unroll
+      for (int k = 0; k < MF; k++) if (k < endPt + 1 && i + k < MF) wi = cadd(wi, cmul(v[i + k], cconj(chan[k])));
+      w[i] = cdivr(wi, d);
+    }
+  }
+}
+
+// equalizeBurst :1343-1399.  burst is delayed in place (as the reference does), tmp = scratch of n
+// samples that ends up holding the post-feedback symbols; soft[m*SS] receives the n soft bits.
+template <int S, int SS>
+BTS_HD void equalize_burst(const DevTables *__restrict__ T, View<S> burst, int n, float TOA, const cf *w, int nw,
+                           const cf *b, int nb, View<S> tmp, float *soft) {
+  delay_vector<S>(T, burst, n, -TOA, tmp);
+  // feed-forward: FULL_SPAN convolution, samples nw-1 .. nw-1+n kept  :1352-1356
+  for (int m = 0; m < n; m++) tmp.st(m, conv_cc_at<S>(burst, n, w, nw, m + nw - 1, false));
+  // decision feedback :1367-1384.  The reference overwrites postForward[m] with the decided symbol and
+  // reads the previous nb of them back; only those nb are ever needed, so they live in registers and
+  // tmp[m] is free to receive the soft bit (soft may alias tmp: it is written after tmp[m] is read).
+  cf hist[kDfeMax];
+#pragma unroll
+  for (int k = 0; k < kDfeMax; k++) hist[k] = mk(0.0F, 0.0F);
+  for (int m = 0; m < n; m++) {
+    cf y = tmp.ld(m);
+#pragma unroll
+    for (int k = 0; k < kDfeMax; k++)
+      if (k < nb && m - 1 - k >= 0) y = cadd(y, cmul(b[k], hist[k]));
+    y = cmul(y, T->revrot[m]);
+    const float out = y.x;
+#pragma unroll
+    for (int k = kDfeMax - 1; k >= 1; k--) if (k < nb) hist[k] = hist[k - 1];
+    hist[0] = cmul(mk((out > 0.0F) ? 1.0F : -1.0F, 0.0F), T->rot[m]);
+    soft[m * SS] = soft_slice(out);
+  }
+}
+
+// demodulateBurst :1056-1097 (+ decimateVector :1039-1053).  x = private copy of the burst (modified),
+// tmp = scratch; returns the number of soft bits written.
+template <int S, int SS>
+BTS_HD int demodulate_burst(const DevTables *__restrict__ T, View<S> x, int n, int sps, cf channel, float TOA,
+                            View<S> tmp, float *soft) {
+  const cf s = cdiv(mk(1.0F, 0.0F), channel);
+  for (int i = 0; i < n; i++) x.st(i, cmul(x.ld(i), s));
+  delay_vector<S>(T, x, n, -TOA, tmp);
+  const int m = (sps > 1) ? n / sps : n;
+  for (int i = 0; i < m; i++) {
+    cf r = cmul(T->revrot[i * sps], x.ld(i * sps));
+    soft[i * SS] = soft_slice(r.x);
+  }
+  return m;
+}
+
+// One output sample of modulateBurst :521-565 = GMSKRotate (:232-247, real-only branch) followed by
+// convolve(.., pulse, NO_DELAY) with the real-only pulse.  bits: one per byte, value in bit 0.
+BTS_HD cf modulate_at(const DevTables *__restrict__ T, const unsigned char *__restrict__ bits, int nbits, int n,
+                      int sps, const cf *__restrict__ pulse, int plen, bool pulse_real, int t) {
+  cf sum = mk(0.0F, 0.0F);
+  const int start = no_delay_start(plen);
+  for (int k = 0; k < plen; k++) {
+    int ai = t + start - k;
+    if (ai < 0) break;
+    if (ai < n) {
+      float sym = 0.0F;
+      if (ai % sps == 0 && ai / sps < nbits) sym = (bits[ai / sps] & 0x01) ? 1.0F : -1.0F;   // 2.0*(bit&1)-1.0 :548
+      cf x = cmulr(T->rot[ai], sym);
+      sum = cadd(sum, pulse_real ? cmulr(x, pulse[k].x) : cmul(x, pulse[k]));
+    }
+  }
+  return sum;
+}
+
+
+// One output of the per-chunk polyphase resampler (polyphaseResampleVector :1157-1210 as called per
+// chunk by radioInterface.cpp:142 / :245).  x = the chunk's input incl. history (nin samples),
+// hp[k*HP + branch] = lpf[branch + P*k].  m = index among the KEPT outputs (drop already removed).
+// Outputs whose first taps would read past the chunk (in >= nin) skip those taps (:1183-1186).
+template <int P, int Q, int NTAPS, int NPOLY, int HP>
+BTS_HD cf resample_at(const cf *__restrict__ x, int nin, const float *__restrict__ hp, int drop, int m) {
+  const int t = Q * (m + drop + (NTAPS - 1) / 2 / Q);                   // outputIx*Q, outputIx0 = (L-1)/2/Q :1177
+  const int br = t % P;
+  int ix = t / P;
+  int k = 0;
+  if (ix >= nin) { k = ix - (nin - 1); ix = nin - 1; }
+  cf sum = mk(0.0F, 0.0F);
+  for (; k < NPOLY && br + P * k < NTAPS && ix >= 0; k++, ix--) sum = cadd(sum, cmulr(x[ix], hp[k * HP + br]));
+  return sum;
+}
+
+// TX tail: scaleVector(.,13500.0) (radioInterface.cpp:148) then USRPifyVector's (short) casts (:74-89);
+// the x86 cast converts to int32 toward zero and keeps the low 16 bits.
+BTS_HD short2 tx_quantise(cf sum) {
+  const cf s = cmul(sum, mk(13500.0F, 0.0F));
+  short2 o;
+  o.x = (short)(int)s.x;
+  o.y = (short)(int)s.y;
+  return o;
+}
+
+}  // namespace btsdsp

@@ -1,0 +1,44 @@
+// tables.h -- the write-once constant tables of the burst-DSP library, resident in HBM.
+//
+// These are the reference's init-time globals (reference Transceiver/sigProcLib.cpp:39-59:
+// cosTable/sinTable, GMSKRotation/GMSKReverseRotation, gMidambles[8], gRACHSequence) plus the GSM
+// pulse (Transceiver.cpp:62) and the two resampler filters (radioInterface.cpp:134-138, :230-234).
+// They are DATA computed once at btsdsp_create() with the reference's exact arithmetic (SURVEY F6:
+// never "more accurately") and read-only afterwards, so any number of streams may share them.
+#pragma once
+#include "cplx.cuh"
+
+namespace btsdsp {
+
+constexpr int kMaxSps = 4;
+constexpr int kTrig = 1024;                 // TABLESIZE, sigProcLib.cpp:36
+constexpr int kRxTaps = 961, kRxP = 65, kRxQ = 96, kRxPoly = 15;   // RX: x65/96 through the 961-tap table
+constexpr int kTxTaps = 651, kTxP = 96, kTxQ = 65, kTxPoly = 7;    // TX: x96/65 through the 651-tap table
+constexpr int kDfeMax = 16;                // largest DFE filter the generic designDFE / equalizeBurst accept
+constexpr int kSincGrid = 512;              // peakDetect resolves TOA to 1/512 symbol (9 halvings)
+
+struct DevTables {
+  int sps;
+  int pulse_len;
+  float sinT[kTrig + 4];                    // [1025] = 0: the element the reference reads times delta == 0
+  float cosT[kTrig + 4];
+  cf rot[157 * kMaxSps];                    // GMSKRotation
+  cf revrot[157 * kMaxSps];                 // GMSKReverseRotation
+  cf pulse[2 * kMaxSps + 1];                // generateGSMPulse(2, sps), real-only
+  cf mid_seq[8][16 * kMaxSps];              // gMidambles[t]->sequence
+  float mid_toa[8];
+  cf mid_gain[8];
+  cf rach_seq[41 * kMaxSps];                // gRACHSequence->sequence
+  float rach_toa;
+  cf rach_gain;
+  float lpf_rx[kRxTaps + 3];                // createLPF(.,961,65)
+  float lpf_tx[kTxTaps + 1];                // createLPF(.,651,96)
+  float rx_poly[kRxP][16];                  // rx_poly[br][k] = lpf_rx[br + 65 k], zero past the end
+  float tx_poly[kTxP][8];                   // tx_poly[br][k] = lpf_tx[br + 96 k]
+  // sinc(pi*(m - j/512)) for m = -10..10 (index m+10), j = 0..511: every fractional delay the path
+  // itself produces lies on the 1/512 grid (peakDetect's early-late search), so these 21-tap rows
+  // are the only interpolators the batched kernels ever need.  Row pitch 24 floats (96 B).
+  float sinc_grid[kSincGrid][24];
+};
+
+}  // namespace btsdsp

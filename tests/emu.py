@@ -1,0 +1,109 @@
+"""numpy face over tests/hostemu/libhostemu.so (the kernels' bodies compiled for the CPU); test infrastructure."""
+import ctypes
+
+import numpy as np
+
+c_p, c_i, c_ll, c_f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+
+
+def P(a):
+    return None if a is None else a.ctypes.data_as(c_p)
+
+
+class Emu:
+    def __init__(self, lib, sps=1):
+        self.lib = lib
+        self.sps = None
+        self.setup(sps)
+
+    def setup(self, sps):
+        if sps != self.sps:
+            self.lib.emu_setup(sps)
+            self.sps = sps
+
+    def table(self, tid, idx=0):
+        buf = np.zeros(4096, np.float32)
+        n = self.lib.emu_get_table(tid, idx, P(buf), 4096)
+        out = buf[:n].copy()
+        return out.view(np.complex64) if tid in (2, 3, 4, 5, 7) else out
+
+    def rx_normal_batch(self, bursts, lens, tsc, detect_thr=3.0, gate_thr=-1.0, snr_thr=250.0, first=0, pitch=None):
+        bursts = np.ascontiguousarray(bursts, np.complex64)
+        n = len(tsc)
+        pitch = bursts.shape[1] if pitch is None else pitch
+        lens = None if lens is None else np.ascontiguousarray(lens, np.int32)
+        tsc = np.ascontiguousarray(tsc, np.uint8)
+        r = dict(flag=np.zeros(n, np.int32), amp=np.zeros(n, np.complex64), toa=np.zeros(n, np.float32),
+                 soft=np.zeros((n, 160), np.float32), chan=np.zeros((n, 6), np.complex64), off=np.zeros(n, np.float32),
+                 w=np.zeros((n, 7), np.complex64), b=np.zeros((n, 5), np.complex64))
+        self.lib.emu_demod_normal(P(bursts), c_ll(pitch), P(lens), c_ll(first), P(tsc), c_ll(n), c_f(detect_thr),
+                                  c_f(gate_thr), c_f(snr_thr), P(r["flag"]), P(r["amp"]), P(r["toa"]), P(r["soft"]),
+                                  c_i(160), P(r["chan"]), P(r["off"]), P(r["w"]), P(r["b"]))
+        return r
+
+    def rx_rach_batch(self, bursts, lens, detect_thr=5.0, tiles=True):
+        bursts = np.ascontiguousarray(bursts, np.complex64)
+        n, pitch = bursts.shape
+        lens = np.ascontiguousarray(lens, np.int32)
+        r = dict(flag=np.zeros(n, np.int32), amp=np.zeros(n, np.complex64), toa=np.zeros(n, np.float32),
+                 soft=np.zeros((n, 160 * (1 if tiles else self.sps)), np.float32))
+        self.lib.emu_rach(P(bursts), c_ll(pitch), P(lens), c_ll(0), c_ll(n), c_f(detect_thr), c_i(self.sps),
+                          c_i(int(tiles)), P(r["flag"]), P(r["amp"]), P(r["toa"]), P(r["soft"]), c_i(r["soft"].shape[1]))
+        return r
+
+    def analyze_batch(self, bursts, lens, tsc, detect_thr=3.0, request=True):
+        bursts = np.ascontiguousarray(bursts, np.complex64)
+        n, pitch = bursts.shape
+        lens = np.ascontiguousarray(lens, np.int32)
+        tsc = np.ascontiguousarray(tsc, np.uint8)
+        r = dict(flag=np.zeros(n, np.int32), amp=np.zeros(n, np.complex64), toa=np.zeros(n, np.float32),
+                 chan=np.zeros((n, 6 * self.sps), np.complex64), off=np.zeros(n, np.float32))
+        self.lib.emu_analyze(P(bursts), c_ll(pitch), P(lens), c_ll(0), P(tsc), c_ll(n), c_f(detect_thr), c_i(int(request)),
+                             c_i(self.sps), P(r["flag"]), P(r["amp"]), P(r["toa"]), P(r["chan"]), P(r["off"]))
+        return r
+
+    def peak_detect(self, v, grid=False):
+        v = np.ascontiguousarray(v, np.complex64)
+        pk = np.zeros(1, np.complex64)
+        idx, avg = c_f(), c_f()
+        (self.lib.emu_peak_detect_grid if grid else self.lib.emu_peak_detect)(P(v), c_i(v.size), P(pk), ctypes.byref(idx),
+                                                                              ctypes.byref(avg))
+        return pk[0], idx.value, avg.value
+
+    def delay_vector(self, v, delay):
+        v = np.ascontiguousarray(v, np.complex64).copy()
+        self.lib.emu_delay_vector(P(v), c_i(v.size), c_f(delay))
+        return v
+
+    def design_dfe(self, chan, snr, nf=7, fixed=False):
+        chan = np.ascontiguousarray(chan, np.complex64)
+        w, b = np.zeros(nf, np.complex64), np.zeros(max(chan.size - 1, 1), np.complex64)
+        self.lib.emu_design_dfe(P(chan), c_i(chan.size), c_f(snr), c_i(nf), P(w), P(b), c_i(int(fixed)))
+        return w, b[:chan.size - 1]
+
+    def equalize(self, burst, toa, w, b):
+        burst = np.ascontiguousarray(burst, np.complex64).copy()
+        w, b = np.ascontiguousarray(w, np.complex64), np.ascontiguousarray(b, np.complex64)
+        soft = np.zeros(burst.size, np.float32)
+        self.lib.emu_equalize(P(burst), c_i(burst.size), c_f(toa), P(w), c_i(w.size), P(b), c_i(b.size), P(soft))
+        return soft, burst
+
+    def modulate(self, bits, guard):
+        bits = np.ascontiguousarray(bits, np.uint8)
+        out = np.zeros(self.sps * (bits.size + guard), np.complex64)
+        self.lib.emu_modulate(P(bits), c_i(bits.size), c_i(guard), P(out))
+        return out
+
+    def rx_resample_stream(self, raw):
+        raw = np.ascontiguousarray(raw, np.complex64)
+        nch = raw.size // 864
+        out = np.zeros(nch * 585, np.complex64)
+        self.lib.emu_resample_rx(P(raw), c_i(0), c_ll(nch), P(out))
+        return out
+
+    def tx_resample_stream(self, x):
+        x = np.ascontiguousarray(x, np.complex64)
+        nch = x.size // 585
+        out = np.zeros((nch * 864, 2), np.int16)
+        self.lib.emu_resample_tx(P(x), c_i(0), c_ll(nch), P(out))
+        return out

@@ -1,0 +1,289 @@
+// tests/hostemu/hostemu.cu -- TEST INFRASTRUCTURE ONLY.
+//
+// Replays the product's kernels on a CPU: the same __host__ __device__ functions of
+// openbts_ttsou_b200/csrc/sigproc_device.cuh, driven with the same views (stride-33 transposed tiles,
+// 32 "lanes" per warp processed one after another) and the same table-construction order as
+// capi.cu::build_tables.  It lets the `-m "not gpu"` suite check the kernels' control flow, indexing
+// and arithmetic order against the oracle without a GPU.  It is never loaded by the product, is not a
+// fallback (libbtsdsp.so has none) and says nothing about device-only behaviour (intrinsic rounding,
+// warp staging), which the `-m gpu` tests cover through the C ABI.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../openbts_ttsou_b200/csrc/kernels.cuh"
+#include "../../openbts_ttsou_b200/csrc/sigproc_device.cuh"
+#include "../../openbts_ttsou_b200/csrc/tables_host.h"
+
+using namespace btsdsp;
+
+static DevTables *T = nullptr;
+
+static void burst_loc_h(const cf *base, long long pitch, const int *lens, long long first, int sps, long long i,
+                        long long *start, int *len) {
+  const long long g = first + i;
+  const int q = (int)(g & 3);
+  const int rule_len = (q == 0 ? 157 : 156) * sps;
+  if (pitch > 0) { *start = i * pitch; *len = lens ? lens[i] : rule_len; }
+  else {
+    const int off = q == 0 ? 0 : (q == 1 ? 157 : (q == 2 ? 313 : 469));
+    *start = ((g >> 2) * 625 + off) * sps; *len = rule_len;
+  }
+}
+
+extern "C" {
+
+int emu_setup(int sps) {
+  if (!T) T = (DevTables *)malloc(sizeof(DevTables));
+  host_fill_tables(T, sps);
+  // k_init_tables
+  float phase = 0.0F;
+  const float inc = BTS_DIV(BTS_DIV(kPiF, 2.0F), (float)sps);
+  for (int i = 0; i < 157 * sps; i++) {
+    T->rot[i] = expj_lookup(T, phase);
+    T->revrot[i] = expj_lookup(T, -phase);
+    phase = BTS_ADD(phase, inc);
+  }
+  // k_init_sinc_grid
+  for (int j = 0; j < kSincGrid; j++)
+    for (int i = 0; i < 24; i++) {
+      float v = 0.0F;
+      if (i < 21) {
+        const float d = BTS_SUB((float)(i - 10), (float)j * (1.0F / (float)kSincGrid));
+        v = sinc_exact(T, BTS_MUL(kPiF, d));
+      }
+      T->sinc_grid[j][i] = v;
+    }
+  // midambles / RACH as in capi.cu::build_tables
+  const cf one = mk(1.0F, 0.0F);
+  for (int t = 0; t < 8; t++) {
+    uint8_t bits[26];
+    for (int i = 0; i < 26; i++) bits[i] = kTSC[t][i] == '1';
+    const int nmid = 16 * sps, nfull = 26 * sps;
+    std::vector<cf> mid(nmid), full(nfull), ac(nfull);
+    for (int i = 0; i < nmid; i++) mid[i] = modulate_at(T, bits + 5, 16, nmid, sps, &one, 1, false, i);
+    for (int i = 0; i < nfull; i++) full[i] = modulate_at(T, bits, 26, nfull, sps, T->pulse, T->pulse_len, true, i);
+    for (int i = 0; i < nmid; i++) mid[i] = cmul(mid[i], mk(-1.0F, 0.0F));
+    for (int i = 0; i < nfull; i++) full[i] = cmul(full[i], mk(0.0F, 1.0F));
+    const int start = no_delay_start(nmid);
+    for (int i = 0; i < nfull; i++) ac[i] = conv_cc_at<1>(View<1>{full.data()}, nfull, mid.data(), nmid, start + i, true);
+    float toa;
+    T->mid_gain[t] = peak_detect<1, false>(T, View<1>{ac.data()}, nfull, &toa, nullptr);
+    T->mid_toa[t] = toa - (float)(5 * sps);
+    memcpy(T->mid_seq[t], mid.data(), nmid * sizeof(cf));
+  }
+  {
+    uint8_t bits[41];
+    for (int i = 0; i < 41; i++) bits[i] = kRACH[i] == '1';
+    const int n = 41 * sps;
+    std::vector<cf> seq(n), ac(n);
+    for (int i = 0; i < n; i++) seq[i] = modulate_at(T, bits, 41, n, sps, T->pulse, T->pulse_len, true, i);
+    const int start = no_delay_start(n);
+    for (int i = 0; i < n; i++) ac[i] = conv_cc_at<1>(View<1>{seq.data()}, n, seq.data(), n, start + i, true);
+    float toa;
+    T->rach_gain = peak_detect<1, false>(T, View<1>{ac.data()}, n, &toa, nullptr);
+    T->rach_toa = toa;
+    memcpy(T->rach_seq, seq.data(), n * sizeof(cf));
+  }
+  return 0;
+}
+
+int emu_get_table(int id, int idx, float *dst, int cap) {
+  const int sps = T->sps;
+  const void *src = nullptr;
+  int n = 0;
+  float meta[3];
+  switch (id) {
+    case 0: src = T->cosT; n = kTrig + 1; break;
+    case 1: src = T->sinT; n = kTrig + 1; break;
+    case 2: src = T->rot; n = 2 * 157 * sps; break;
+    case 3: src = T->revrot; n = 2 * 157 * sps; break;
+    case 4: src = T->pulse; n = 2 * T->pulse_len; break;
+    case 5: src = T->mid_seq[idx]; n = 2 * 16 * sps; break;
+    case 6: meta[0] = T->mid_toa[idx]; meta[1] = T->mid_gain[idx].x; meta[2] = T->mid_gain[idx].y; src = meta; n = 3; break;
+    case 7: src = T->rach_seq; n = 2 * 41 * sps; break;
+    case 8: meta[0] = T->rach_toa; meta[1] = T->rach_gain.x; meta[2] = T->rach_gain.y; src = meta; n = 3; break;
+    case 9: src = T->lpf_rx; n = kRxTaps; break;
+    case 10: src = T->lpf_tx; n = kTxTaps; break;
+    default: return -1;
+  }
+  if (cap >= n) memcpy(dst, src, n * sizeof(float));
+  return n;
+}
+
+float emu_sinc(float x) { return sinc_exact(T, x); }
+float emu_sin_lookup(float x) { return trig_lookup(T->sinT, x); }
+float emu_cos_lookup(float x) { return trig_lookup(T->cosT, x); }
+
+// the sinc grid must equal sinc_exact at the arguments the reference would form
+int emu_check_sinc_grid(void) {
+  int bad = 0;
+  for (int j = 0; j < kSincGrid; j++)
+    for (int m = -10; m <= 10; m++) {
+      const float frac = (float)j / 512.0F;
+      const float a = sinc_exact(T, BTS_MUL(kPiF, BTS_SUB((float)m, frac)));
+      uint32_t x, y;
+      memcpy(&x, &a, 4); memcpy(&y, &T->sinc_grid[j][m + 10], 4);
+      bad += x != y;
+    }
+  return bad;
+}
+
+// k_demod_normal, warp by warp, lane by lane
+void emu_demod_normal(const float *bursts, long long pitch, const int *lens, long long first, const uint8_t *tsc,
+                      long long n, float detect_thr, float gate_thr, float snr_thr, int *flag, float *amp, float *toa,
+                      float *soft, int soft_pitch, float *chan_o, float *off_o, float *w_o, float *b_o) {
+  std::vector<cf> tile((2 * kBurstRows + 36) * kTileStride);
+  cf *A = tile.data(), *B = A + kBurstRows * kTileStride, *C = B + kBurstRows * kTileStride;
+  for (long long w0 = 0; w0 < n; w0 += 32) {
+    const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
+    for (int j = 0; j < nv; j++) {
+      long long start; int len;
+      burst_loc_h((const cf *)bursts, pitch, lens, first, 1, w0 + j, &start, &len);
+      for (int i = 0; i < len; i++) A[i * kTileStride + j] = ((const cf *)bursts)[start + i];
+    }
+    for (int lane = 0; lane < nv; lane++) {
+      const long long i = w0 + lane;
+      long long start; int len;
+      burst_loc_h((const cf *)bursts, pitch, lens, first, 1, i, &start, &len);
+      const View<kTileStride> a{A + lane}, b{B + lane}, c{C + lane};
+      cf ampv = mk(0.0F, 0.0F), chan[6], w[7], fb[5];
+      float toav = 0.0F, off = 0.0F;
+      bool pass = true, ok = false;
+      if (gate_thr >= 0.0F) pass = energy_detect<kTileStride>(a, len, 20, gate_thr, nullptr);
+      if (pass) ok = analyze_traffic<kTileStride, true>(T, a, tsc[i], detect_thr, 1, c, b, &ampv, &toav, true, chan, &off);
+      if (ok) {
+        const float SNR = (float)((double)cnorm2(ampv) / ((double)BTS_MUL(snr_thr, snr_thr) + 1.0));
+        const cf ia = cdiv(mk(1.0F, 0.0F), ampv);
+        for (int j = 0; j < 6; j++) chan[j] = cmul(chan[j], ia);
+        design_dfe<7, 5>(chan, 5, SNR, 7, w, fb);
+        for (int m = 0; m < len; m++) a.st(m, cmul(a.ld(m), ia));
+        equalize_burst<kTileStride, 2 * kTileStride>(T, a, len, BTS_SUB(toav, off), w, 7, fb, 5, b, (float *)(B + lane));
+      }
+      flag[i] = ok; amp[2 * i] = ampv.x; amp[2 * i + 1] = ampv.y; toa[i] = toav;
+      if (off_o) off_o[i] = ok ? off : 0.0F;
+      for (int j = 0; j < 6 && chan_o; j++) ((cf *)chan_o)[i * 6 + j] = ok ? chan[j] : mk(0.0F, 0.0F);
+      for (int j = 0; j < 7 && w_o; j++) ((cf *)w_o)[i * 7 + j] = ok ? w[j] : mk(0.0F, 0.0F);
+      for (int j = 0; j < 5 && b_o; j++) ((cf *)b_o)[i * 5 + j] = ok ? fb[j] : mk(0.0F, 0.0F);
+      const float *tf = (const float *)B;
+      for (int m = 0; m < soft_pitch; m++)
+        soft[i * soft_pitch + m] = (ok && m < len) ? tf[(m * kTileStride + lane) * 2] : 0.0F;
+    }
+  }
+}
+
+// k_rach<true> (sps 1, tiles) or k_rach<false> (any sps, global scratch)
+void emu_rach(const float *bursts, long long pitch, const int *lens, long long first, long long n, float detect_thr,
+              int sps, int tiles, int *flag, float *amp, float *toa, float *soft, int soft_pitch) {
+  std::vector<cf> tile(2 * kBurstRows * kTileStride), scratch(scratch_per_burst(sps));
+  cf *A = tile.data(), *B = A + kBurstRows * kTileStride;
+  for (long long i = 0; i < n; i++) {
+    long long start; int len;
+    burst_loc_h((const cf *)bursts, pitch, lens, first, sps, i, &start, &len);
+    const cf *src = (const cf *)bursts + start;
+    cf ampv = mk(0.0F, 0.0F);
+    float toav = 0.0F;
+    bool ok;
+    int ns = 0;
+    float *sp = soft + i * soft_pitch;
+    for (int m = 0; m < soft_pitch; m++) sp[m] = 0.0F;
+    if (tiles) {
+      const int lane = (int)(i & 31);
+      for (int m = 0; m < len; m++) A[m * kTileStride + lane] = src[m];
+      const View<kTileStride> a{A + lane}, b{B + lane};
+      ok = detect_rach<kTileStride, true>(T, a, len, detect_thr, 1, b, &ampv, &toav);
+      if (ok) {
+        ns = demodulate_burst<kTileStride, 2 * kTileStride>(T, a, len, 1, ampv, toav, b, (float *)(B + lane));
+        for (int m = 0; m < ns; m++) sp[m] = ((const float *)B)[(m * kTileStride + lane) * 2];
+      }
+    } else {
+      cf *s = scratch.data();
+      const View<1> corr{s}, x{s + 157 * sps};
+      ok = detect_rach<1, true>(T, View<1>{(cf *)src}, len, detect_thr, sps, corr, &ampv, &toav);
+      if (ok) {
+        for (int m = 0; m < len; m++) x.st(m, src[m]);
+        ns = demodulate_burst<1, 1>(T, x, len, sps, ampv, toav, corr, sp);
+      }
+    }
+    flag[i] = ok; amp[2 * i] = ampv.x; amp[2 * i + 1] = ampv.y; toa[i] = toav;
+  }
+}
+
+// k_analyze<false>: any sps
+void emu_analyze(const float *bursts, long long pitch, const int *lens, long long first, const uint8_t *tsc, long long n,
+                 float detect_thr, int request, int sps, int *flag, float *amp, float *toa, float *chan_o, float *off_o) {
+  std::vector<cf> scratch(scratch_per_burst(sps));
+  for (long long i = 0; i < n; i++) {
+    long long start; int len;
+    burst_loc_h((const cf *)bursts, pitch, lens, first, sps, i, &start, &len);
+    cf ampv = mk(0.0F, 0.0F), chan[6 * kMaxSps];
+    float toav = 0.0F, off = 0.0F;
+    cf *s = scratch.data();
+    bool ok = analyze_traffic<1, true>(T, View<1>{(cf *)bursts + start}, tsc[i], detect_thr, sps, View<1>{s},
+                                       View<1>{s + 36 * sps}, &ampv, &toav, request != 0, chan, &off);
+    flag[i] = ok; amp[2 * i] = ampv.x; amp[2 * i + 1] = ampv.y; toa[i] = toav;
+    const bool have = ok && request;
+    if (off_o) off_o[i] = have ? off : 0.0F;
+    for (int j = 0; j < 6 * sps && chan_o; j++) ((cf *)chan_o)[i * 6 * sps + j] = have ? chan[j] : mk(0.0F, 0.0F);
+  }
+}
+
+// generic single-vector pieces
+void emu_peak_detect(const float *v, int n, float *peak, float *idx, float *avg) {
+  cf p = peak_detect<1, false>(T, View<1>{(cf *)v}, n, idx, avg);
+  peak[0] = p.x; peak[1] = p.y;
+}
+void emu_peak_detect_grid(const float *v, int n, float *peak, float *idx, float *avg) {
+  cf p = peak_detect<1, true>(T, View<1>{(cf *)v}, n, idx, avg);
+  peak[0] = p.x; peak[1] = p.y;
+}
+void emu_delay_vector(float *v, int n, float delay) {
+  std::vector<cf> tmp(n);
+  delay_vector<1>(T, View<1>{(cf *)v}, n, delay, View<1>{tmp.data()});
+}
+void emu_design_dfe(const float *chan, int nchan, float snr, int nf, float *w, float *b, int fixed) {
+  cf ch[kDfeMax], W[kDfeMax], F[kDfeMax];
+  for (int i = 0; i < nchan; i++) ch[i] = ((const cf *)chan)[i];
+  if (fixed) design_dfe<7, 5>(ch, 5, snr, 7, W, F);
+  else design_dfe<0, 0>(ch, nchan - 1, snr, nf, W, F);
+  for (int i = 0; i < nf; i++) ((cf *)w)[i] = W[i];
+  for (int i = 0; i < nchan - 1; i++) ((cf *)b)[i] = F[i];
+}
+void emu_equalize(float *burst, int n, float toa, const float *w, int nw, const float *b, int nb, float *soft) {
+  std::vector<cf> tmp(n + kDfeMax);
+  equalize_burst<1, 1>(T, View<1>{(cf *)burst}, n, toa, (const cf *)w, nw, (const cf *)b, nb, View<1>{tmp.data()}, soft);
+}
+int emu_modulate(const uint8_t *bits, int nbits, int guard, float *out) {
+  const int sps = T->sps, n = sps * (nbits + guard);
+  for (int t = 0; t < n; t++) ((cf *)out)[t] = modulate_at(T, bits, nbits, n, sps, T->pulse, T->pulse_len, true, t);
+  return n;
+}
+
+// k_resample_rx / k_resample_tx chunk loops
+void emu_resample_rx(const float *in, int has_history, long long nchunks, float *out) {
+  std::vector<cf> x(192 + 864);
+  std::vector<float> hp(kRxPoly * (kRxP + 1));
+  for (int i = 0; i < kRxPoly * kRxP; i++) hp[(i / kRxP) * (kRxP + 1) + i % kRxP] = T->rx_poly[i % kRxP][i / kRxP];
+  for (long long c = 0; c < nchunks; c++) {
+    const cf *src = (const cf *)in + c * 864;
+    for (int i = 0; i < 192 + 864; i++) x[i] = (i >= 192 || has_history || c > 0) ? src[i - 192] : mk(0.0F, 0.0F);
+    for (int m = 0; m < 585; m++)
+      ((cf *)out)[c * 585 + m] = resample_at<kRxP, kRxQ, kRxTaps, kRxPoly, kRxP + 1>(x.data(), 192 + 864, hp.data(), 130, m);
+  }
+}
+void emu_resample_tx(const float *in, int has_history, long long nchunks, short *out) {
+  std::vector<cf> x(130 + 585);
+  std::vector<float> hp(kTxPoly * (kTxP + 1));
+  for (int i = 0; i < kTxPoly * kTxP; i++) hp[(i / kTxP) * (kTxP + 1) + i % kTxP] = T->tx_poly[i % kTxP][i / kTxP];
+  for (long long c = 0; c < nchunks; c++) {
+    const cf *src = (const cf *)in + c * 585;
+    for (int i = 0; i < 130 + 585; i++) x[i] = (i >= 130 || has_history || c > 0) ? src[i - 130] : mk(0.0F, 0.0F);
+    for (int m = 0; m < 864; m++) {
+      short2 o = tx_quantise(resample_at<kTxP, kTxQ, kTxTaps, kTxPoly, kTxP + 1>(x.data(), 130 + 585, hp.data(), 192, m));
+      out[(c * 864 + m) * 2] = o.x; out[(c * 864 + m) * 2 + 1] = o.y;
+    }
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,331 @@
+"""Parity of the CUDA path with the reference, through the C ABI (libbtsdsp.so) on cuda:0.
+
+Checker: oracle_best = the compiled reference (oracle/_ref, travels with the repo) when present, else the
+plain-C port.  Bar (BASELINE.json north_star): detection flags, integer TOA and hard bits exact; soft bits,
+amplitudes and fractional TOA within 1e-4 relative.  The kernels are designed to be bit-identical, so the
+tests assert exact equality of every float and would only fall back to the stated tolerance knowingly
+(REL_TOL below is the contract's alarm threshold, not used unless EXACT is switched off).
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_same, golden
+import synth
+
+pytestmark = pytest.mark.gpu
+
+EXACT = True
+REL_TOL = 1e-4          # north_star tolerance for soft bits / amplitudes / fractional TOA
+
+
+def same(a, b, what):
+    if EXACT:
+        assert_same(a, b, what)
+    else:
+        a, b = np.asarray(a), np.asarray(b)
+        scale = max(float(np.abs(b).max()), 1e-30)
+        assert np.all(np.abs(a - b) <= REL_TOL * np.maximum(np.abs(b), 1e-6 * scale)), what
+
+
+def check_batch(got, ref, keys):
+    same(got["flag"], ref["flag"], "detection flags")
+    same(np.rint(got["toa"]), np.rint(ref["toa"]), "integer TOA")
+    if "soft" in keys:
+        same(got["soft"][:, :148] > 0.5, ref["soft"][:, :148] > 0.5, "hard bits")
+    for k in keys:
+        same(got[k], ref[k][..., :got[k].shape[-1]] if got[k].ndim > 1 else ref[k], k)
+
+
+# ---------------------------------------------------------------------------------------------- tables
+@pytest.mark.parametrize("sps", [1, 4])
+def test_tables(dsp, dsp4, sps):
+    d = dsp if sps == 1 else dsp4
+    g = golden("tables_sps%d.npz" % sps)
+    for t, k in enumerate(["cos", "sin", "rot", "revrot", "pulse"]):
+        assert_same(d.table(t), g[k], k)
+    for i in range(8):
+        assert_same(d.table(5, i), g["mid_seq"][i], "mid_seq %d" % i)
+        assert_same(d.table(6, i), g["mid_meta"][i], "mid_meta %d" % i)
+    assert_same(d.table(7), g["rach_seq"], "rach_seq")
+    assert_same(d.table(8), g["rach_meta"], "rach_meta")
+    assert_same(d.table(9), g["lpf_rx"], "lpf_rx")
+    assert_same(d.table(10), g["lpf_tx"], "lpf_tx")
+
+
+# ------------------------------------------------------------------------- layer 1: sigProcLib.h surface
+def test_config1_flow_matches_golden(dsp):
+    """Transceiver/sigProcLibTest.cpp's flow (SURVEY config 1) at sps 1, every intermediate pinned"""
+    g = golden("config1_sps1.npz")
+    from openbts_ttsou_b200 import NO_DELAY, FULL_SPAN
+    tx = dsp.modulate(g["bits"], 8)
+    same(tx, g["tx"], "modulateBurst")
+    same(dsp.delay_vector(tx, 6.932), g["delayed"], "delayVector")
+    same(dsp.convolve(g["delayed"], np.array([9000, 3600, 0, 0], np.complex64), NO_DELAY), g["chan_out"], "convolve")
+    ok, amp, toa, chan, off = dsp.analyze(g["rx"], 0, 8.0, request=True)
+    assert ok == bool(g["ok"]) and amp == g["amp"] and toa == float(g["toa"]) and off == float(g["off"])
+    same(chan, g["chan"], "channel")
+    same(dsp.demodulate(g["rx"], amp, toa), g["soft_slicer"], "demodulateBurst")
+    w, b = dsp.design_dfe(chan, 1.0 / 0.001, 7)
+    same(w, g["w"], "w"); same(b, g["b"], "b")
+    soft, after = dsp.equalize(g["rx"], toa - off, w, b)
+    same(soft, g["soft_dfe"], "equalizeBurst"); same(after, g["rx_after"], "burst after equalizeBurst")
+    pk, idx, avg = dsp.peak_detect(dsp.correlate(g["rx"][56:92], dsp.table(5, 0), NO_DELAY))
+    assert pk == g["pk"] and idx == float(g["pidx"]) and avg == float(g["pavg"])
+    same(dsp.convolve(g["rx"], w, FULL_SPAN), g["full"], "FULL_SPAN convolve")
+    assert ((soft[:148] > 0.5) == g["bits"].astype(bool)).all()
+
+
+def test_single_vector_functions_randomised(dsp, oracle_best):
+    o = oracle_best
+    rng = np.random.default_rng(17)
+    for n, lb in ((36, 16), (156, 41), (157, 7), (20, 21), (5, 9), (1000, 33)):
+        a = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        b = (rng.standard_normal(lb) + 1j * rng.standard_normal(lb)).astype(np.complex64)
+        for span in range(5):
+            for ar, br in ((False, False), (True, False), (False, True), (True, True)):
+                same(dsp.convolve(a, b, span, ar, br), o.convolve(a, b, span, ar, br), "convolve")
+                same(dsp.correlate(a, b, span, ar, br), o.correlate(a, b, span, ar, br), "correlate")
+        for d in (0.0, 0.005, 0.3, 6.932, -2.75, -0.999, 3.0, 7 / 512, 5 / 512, 200.0, -2000.0):
+            same(dsp.delay_vector(a, d), o.delay_vector(a, d), "delay %r" % d)
+        assert dsp.peak_detect(a) == o.peak_detect(a)
+        for ix in (-3.2, 0.0, 4.37, n - 1.5, n + 4.0):
+            assert dsp.interpolate_point(a, ix) == o.interpolate_point(a, ix)
+        assert dsp.energy_detect(a, 20, 0.9) == o.energy_detect(a, 20, 0.9)
+        same(dsp.scale_vector(a, 0.3 - 1.7j), o.scale_vector(a, 0.3 - 1.7j), "scaleVector")
+        same(dsp.scale_vector(a, 0.3 - 1.7j, True), o.scale_vector(a, 0.3 - 1.7j, True), "scaleVector real")
+    for nchan, nf in ((6, 7), (4, 7), (2, 5), (1, 3), (7, 7)):
+        ch = (rng.standard_normal(nchan) + 1j * rng.standard_normal(nchan)).astype(np.complex64) * 0.4
+        ch[0] += 1
+        for x, y in zip(dsp.design_dfe(ch, 37.5, nf), o.design_dfe(ch, 37.5, nf)):
+            same(x, y, "designDFE %d/%d" % (nchan, nf))
+    x = (rng.standard_normal(1056) + 1j * rng.standard_normal(1056)).astype(np.complex64)
+    same(dsp.resample(x, 65, 96, 0), o.resample(x, 65, 96, 0), "polyphaseResampleVector rx")
+    same(dsp.resample(x[:715], 96, 65, 1), o.resample(x[:715], 96, 65, 1), "polyphaseResampleVector tx")
+    for guard in (0, 8, 9):
+        bits = rng.integers(0, 2, 148).astype(np.uint8)
+        same(dsp.modulate(bits, guard), o.modulate(bits, guard), "modulateBurst")
+
+
+def test_error_behaviour(dsp, dsp4):
+    import openbts_ttsou_b200 as pkg
+    x = np.ones(156, np.complex64)
+    with pytest.raises(pkg.BtsDspError):           # DFE path is undefined off symbol rate
+        dsp4.equalize(np.ones(624, np.complex64), 0.0, np.ones(7, np.complex64), np.ones(5, np.complex64))
+    with pytest.raises(pkg.BtsDspError):
+        dsp.analyze(x[:50], 0, 3.0)                # shorter than the correlation window
+    with pytest.raises(pkg.BtsDspError):
+        dsp.analyze(x, 9, 3.0)                     # TSC out of range (the reference asserts)
+    ok, amp, toa = dsp.detect_rach(np.zeros(156, np.complex64), 5.0)
+    assert not ok and amp == 0
+
+
+# -------------------------------------------------------------------------------- batched, host buffers
+def test_normal_batch_matches_golden(dsp):
+    g = golden("normal_sps1.npz")
+    r = dsp.demod_normal_host(g["bursts"], g["lens"], g["tsc"])
+    check_batch(r, g, ("amp", "toa", "chan", "off", "w", "b", "soft"))
+
+
+def test_normal_batch_config4_random(dsp, oracle_best):
+    """1024 ARFCN x 8 TS, mixed TSC 0-7 (hits SURVEY F6), multipath, SNR 10-30 dB, some empty slots"""
+    mod = lambda b, gd: oracle_best.modulate(b, gd)  # noqa: E731
+    bursts, lens, tsc, bits = synth.make_normal_batch(mod, 8192, seed=0xC4, noise_only=0.05)
+    ref = oracle_best.rx_normal_batch(bursts, lens, tsc, threads=8)
+    r = dsp.demod_normal_host(bursts, lens, tsc)
+    check_batch(r, ref, ("amp", "toa", "chan", "off", "w", "b", "soft"))
+    r2 = dsp.demod_normal_host(bursts, None, tsc, debug=False, soft_pitch=148)    # rule-based lengths, packed soft
+    same(r2["soft"], ref["soft"][:, :148], "soft (pitch 148)")
+    det = ref["flag"] == 1
+    good = det & np.isin(tsc, (0, 2, 6, 7))
+    ber = ((r["soft"][good, :148] > 0.5) != bits[good].astype(bool)).mean()
+    assert det.mean() > 0.9 and ber < 0.01
+
+
+def test_normal_batch_edge_cases(dsp, oracle_best):
+    rng = np.random.default_rng(9)
+    n = 70                                          # ragged: not a multiple of 32
+    bursts = np.zeros((n, 160), np.complex64)
+    lens = np.where(np.arange(n) % 4 == 0, 157, 156).astype(np.int32)
+    tsc = (np.arange(n) % 8).astype(np.uint8)
+    bursts[1] = 1e-3                                # constant -> flat correlation
+    bursts[2, :156] = (rng.standard_normal(156) + 1j * rng.standard_normal(156)) * 1e4
+    bursts[3, 60] = 5000                            # a single impulse inside the correlation window
+    bursts[4, 91] = 5000 + 1j                       # impulse at the window edge
+    b = synth.normal_burst_bits(rng, 3)
+    bursts[5, :156] = oracle_best.modulate(b, 8) * 3000          # clean, no delay, no noise
+    bursts[6, :156] = oracle_best.delay_vector(oracle_best.modulate(b, 8) * 3000, -2.5)   # early
+    bursts[7, :156] = oracle_best.delay_vector(oracle_best.modulate(b, 8) * 3000, 9.25)   # late
+    for i in range(8, n):
+        bursts[i, :lens[i]] = (rng.standard_normal(lens[i]) + 1j * rng.standard_normal(lens[i])) * rng.uniform(1, 3000)
+    ref = oracle_best.rx_normal_batch(bursts, lens, tsc)
+    r = dsp.demod_normal_host(bursts, lens, tsc)
+    check_batch(r, ref, ("amp", "toa", "chan", "off", "w", "b", "soft"))
+    one = dsp.demod_normal_host(bursts[5:6], lens[5:6], tsc[5:6])                  # batch of one
+    same(one["soft"], ref["soft"][5:6], "batch of 1")
+    gate = dsp.demod_normal_host(bursts, lens, tsc, gate_thr=500.0)
+    eg = np.array([oracle_best.energy_detect(bursts[i, :lens[i]], 20, 500.0)[0] for i in range(n)])
+    same(gate["flag"], ref["flag"] & eg, "energy gate")
+
+
+def test_rach_batch(dsp, oracle_best):
+    g = golden("rach_sps1.npz")
+    r = dsp.rach_host(g["bursts"], g["lens"])
+    check_batch(r, g, ("amp", "toa", "soft"))
+    mod = lambda b, gd: oracle_best.modulate(b, gd)  # noqa: E731
+    bursts, lens, bits, delays = synth.make_rach_batch(mod, 4096, seed=0xC3)       # config 3: TOA 0-63, SNR -5..20
+    ref = oracle_best.rx_rach_batch(bursts, lens, threads=8)
+    r = dsp.rach_host(bursts, lens)
+    check_batch(r, ref, ("amp", "toa", "soft"))
+    only = dsp.rach_host(bursts, lens, demod=False)
+    same(only["flag"], ref["flag"], "detect only")
+    assert 0.3 < ref["flag"].mean() < 1.0
+    det = ref["flag"] == 1
+    assert np.abs(ref["toa"][det] - delays[det]).max() < 1.5
+
+
+def test_sps4_functions(dsp4):
+    g = golden("sps4.npz")
+    for i in range(g["rx"].shape[0]):
+        ok, amp, toa, chan, off = dsp4.analyze(g["rx"][i], int(g["tsc"][i]), 3.0, request=True)
+        assert ok == bool(g["ok"][i]) and amp == g["amp"][i] and toa == g["toa"][i] and off == g["off"][i]
+        same(chan, g["chan"][i], "chan")
+        same(dsp4.demodulate(g["rx"][i], amp, toa), g["soft"][i], "demodulateBurst sps4")
+    same(dsp4.modulate(golden("config1_sps1.npz")["bits"], 8).size, 4 * 156, "modulated length at sps 4")
+
+
+# ------------------------------------------------------------------------------------- streams (config 2/5)
+def test_stream_kernels_match_golden(dsp):
+    import torch
+    g = golden("stream_sps1.npz")
+    dev = torch.device("cuda:0")
+    x = torch.from_numpy(g["stream_head"].view(np.float32).copy()).to(dev)
+    iq = torch.zeros(20 * 864 * 2, dtype=torch.int16, device=dev)
+    dsp.resample_tx_dev(x, 20, iq)
+    same(iq.cpu().numpy().reshape(-1, 2), g["iq_head"], "TX resample")
+    raw = torch.from_numpy(g["raw_head"].view(np.float32).copy()).to(dev)
+    nch = g["raw_head"].size // 864
+    res = torch.zeros(nch * 585 * 2, dtype=torch.float32, device=dev)
+    dsp.resample_rx_dev(raw, nch, res)
+    same(res.cpu().numpy().view(np.complex64), g["res_head"], "RX resample")
+    # a later part of the stream with real history == the same samples computed from the start
+    res2 = torch.zeros((nch - 3) * 585 * 2, dtype=torch.float32, device=dev)
+    dsp.resample_rx_dev(raw[3 * 864 * 2:], nch - 3, res2, has_history=True)
+    same(res2.cpu().numpy().view(np.complex64), g["res_head"][3 * 585:], "RX resample with history")
+    nb = 64
+    tsc = torch.zeros(nb, dtype=torch.uint8, device=dev)
+    flag = torch.zeros(nb, dtype=torch.int32, device=dev)
+    amp = torch.zeros(nb * 2, dtype=torch.float32, device=dev)
+    toa = torch.zeros(nb, dtype=torch.float32, device=dev)
+    soft = torch.zeros(nb * 160, dtype=torch.float32, device=dev)
+    dsp.demod_normal_dev(res, 0, tsc, nb, flag, amp, toa, soft, 160)       # pitch 0 = slot-stream addressing
+    torch.cuda.synchronize()
+    same(flag.cpu().numpy(), g["flag"], "flag"); same(amp.cpu().numpy().view(np.complex64), g["amp"], "amp")
+    same(toa.cpu().numpy(), g["toa"], "toa"); same(soft.cpu().numpy().reshape(nb, 160), g["soft"], "soft")
+    bits = torch.from_numpy(g["bits"].copy()).to(dev)
+    st = torch.zeros(16 * 625 * 2, dtype=torch.float32, device=dev)
+    dsp.modulate_dev(bits, 148, 64, st, 0)
+    same(st.cpu().numpy().view(np.complex64), g["stream_head"][:16 * 625], "modulate to slot stream")
+
+
+def test_stream_end_to_end_host_roundtrip(dsp, oracle_best):
+    """TX (bits -> modulate -> 96/65 resample -> int16) then RX (65/96 resample -> slot cut -> demod), through the
+    host-buffer entry points, checked (a) bit-exactly against the oracle on every burst and (b) by the round-trip
+    property: clean TSC-0 bursts come back with zero bit errors."""
+    rng = np.random.default_rng(0xC2)
+    nb = 936 * 4                                    # 4 blocks of 117 frames = 1000 chunks
+    bits = np.stack([synth.normal_burst_bits(rng, 0) for _ in range(nb)])
+    iq = np.zeros((1000 * 864, 2), np.int16)
+    dsp.tx_stream_host(bits, nb, iq)
+    same(iq, oracle_best.tx_resample_stream(oracle_best.modulate_stream(bits, threads=4), threads=4), "TX stream")
+    raw = (iq[:, 0] + 1j * iq[:, 1]).astype(np.complex64)
+    raw = (raw + 30.0 * (rng.standard_normal(raw.size) + 1j * rng.standard_normal(raw.size))).astype(np.complex64)
+    tsc = np.zeros(nb, np.uint8)
+    flag, amp, toa = np.zeros(nb, np.int32), np.zeros(nb, np.complex64), np.zeros(nb, np.float32)
+    soft = np.zeros((nb, 148), np.float32)
+    dsp.rx_stream_host(raw, 1000, tsc, nb, flag, amp, toa, soft, 148)
+    ref = oracle_best.rx_stream_demod(oracle_best.rx_resample_stream(raw, threads=4), nb, tsc, threads=8)
+    same(flag, ref["flag"], "flag"); same(amp, ref["amp"], "amp"); same(toa, ref["toa"], "toa")
+    same(soft, ref["soft"][:, :148], "soft")
+    assert flag.all() and ((soft > 0.5) == bits.astype(bool)).all()
+
+
+def test_full_size_properties(dsp):
+    """BASELINE config-2 scale without the oracle: 10^5-frame-class stream, size-independent properties --
+    TX->RX round trip recovers every bit, every burst detected, TOA on the 1/512 grid, and the result does not
+    depend on how the stream is cut into launches (device-resident call vs segmented host pipeline)."""
+    import torch
+    dev = torch.device("cuda:0")
+    nblocks = 64                                    # 64 * 936 = 59 904 bursts, 16 000 chunks, 110 MB of raw samples
+    nb, nch = 936 * nblocks, 250 * nblocks
+    g = torch.Generator(device=dev); g.manual_seed(2)
+    bits = torch.randint(0, 2, (nb, 148), generator=g, device=dev, dtype=torch.uint8)
+    bits[:, :3] = 0; bits[:, 145:] = 0
+    mid = torch.from_numpy(synth.bits_of(synth.TSC[0]).copy()).to(dev)
+    bits[:, 61:87] = mid
+    iq = torch.zeros(nch * 864 * 2, dtype=torch.int16, device=dev)
+    dsp.tx_stream_dev(bits, nb, iq)
+    raw = iq.to(torch.float32) + 20.0 * torch.randn(iq.numel(), generator=g, device=dev)
+    tsc = torch.zeros(nb, dtype=torch.uint8, device=dev)
+    flag = torch.zeros(nb, dtype=torch.int32, device=dev); amp = torch.zeros(nb * 2, device=dev)
+    toa = torch.zeros(nb, device=dev); soft = torch.zeros(nb * 148, device=dev)
+    dsp.rx_stream_dev(raw, nch, tsc, nb, flag, amp, toa, soft, 148)
+    torch.cuda.synchronize()
+    hard = (soft.reshape(nb, 148) > 0.5).to(torch.uint8)
+    assert bool(flag.all()) and bool((hard == bits).all())
+    assert bool(((toa * 512) == torch.round(toa * 512)).all()) and float(toa.abs().max()) < 1.0
+    raw_h = raw.cpu().numpy().view(np.complex64)
+    f2, a2, t2 = np.zeros(nb, np.int32), np.zeros(nb, np.complex64), np.zeros(nb, np.float32)
+    s2 = np.zeros((nb, 148), np.float32)
+    dsp.rx_stream_host(raw_h, nch, tsc.cpu().numpy(), nb, f2, a2, t2, s2, 148)
+    same(s2, soft.cpu().numpy().reshape(nb, 148), "host pipeline == device call")
+    same(t2, toa.cpu().numpy(), "toa"); same(a2.view(np.float32), amp.cpu().numpy(), "amp")
+
+
+def test_cached_dfe_mode(dsp, oracle_best):
+    """analyze -> designDFE -> equalize as three batched device calls (the cached-filter mode of
+    Transceiver.cpp:315-396) gives the same result as the fused kernel"""
+    import torch
+    dev = torch.device("cuda:0")
+    g = golden("normal_sps1.npz")
+    n = g["bursts"].shape[0]
+    bursts = torch.from_numpy(g["bursts"].view(np.float32).copy()).to(dev)
+    lens = torch.from_numpy(g["lens"].copy()).to(dev); tsc = torch.from_numpy(g["tsc"].copy()).to(dev)
+    flag = torch.zeros(n, dtype=torch.int32, device=dev); amp = torch.zeros(n * 2, device=dev)
+    toa = torch.zeros(n, device=dev); chan = torch.zeros(n * 12, device=dev); off = torch.zeros(n, device=dev)
+    dsp.analyze_dev(bursts, 160, tsc, n, flag, amp, toa, chan, off, lens=lens)
+    torch.cuda.synchronize()
+    a = amp.cpu().numpy().view(np.complex64); ok = flag.cpu().numpy() == 1
+    same(flag.cpu().numpy(), g["flag"], "flag"); same(a, g["amp"], "amp"); same(toa.cpu().numpy(), g["toa"], "toa")
+    same(off.cpu().numpy(), g["off"], "off")
+    # caller glue (Transceiver.cpp:340-347, :391) on the host in float32, op for op
+    f32 = np.float32
+    ar, ai = a.real.astype(f32), a.imag.astype(f32)
+    with np.errstate(all="ignore"):
+        n2 = ai * ai + ar * ar
+        ia_r, ia_i = ar / n2, (-ai) / n2                                   # complex(1,0)/amplitude
+        snr = (n2.astype(np.float64) / (np.float64(f32(250.0) * f32(250.0)) + 1.0)).astype(f32)
+
+    def cmul(xr, xi, sr, si):
+        return xr * sr - xi * si, xr * si + xi * sr
+    c_all = chan.cpu().numpy().view(np.complex64).reshape(n, 6)
+    cr, ci = cmul(c_all.real.astype(f32), c_all.imag.astype(f32), ia_r[:, None], ia_i[:, None])
+    chs = (cr + 1j * ci).astype(np.complex64)
+    same(chs[ok], g["chan"][ok], "channel after 1/amp")
+    br, bi = cmul(g["bursts"].real.astype(f32), g["bursts"].imag.astype(f32), ia_r[:, None], ia_i[:, None])
+    scaled = np.where(ok[:, None], (br + 1j * bi).astype(np.complex64), 0).astype(np.complex64)
+    snr = np.where(ok, snr, 1.0).astype(f32)
+    chs = np.where(ok[:, None], chs, 0).astype(np.complex64); chs[~ok, 0] = 1
+    w = torch.zeros(n * 14, device=dev); b = torch.zeros(n * 10, device=dev)
+    dsp.design_dfe_dev(torch.from_numpy(chs.view(f32).copy()).to(dev), torch.from_numpy(snr).to(dev), n, w, b)
+    soft = torch.zeros(n * 160, device=dev); after = torch.zeros(n * 160 * 2, device=dev)
+    toa_eq = torch.from_numpy((g["toa"] - g["off"]).astype(f32)).to(dev)
+    dsp.equalize_dev(torch.from_numpy(scaled.view(f32).copy()).to(dev), 160, n, toa_eq, w, b, soft, 160,
+                     burst_out=after, out_pitch=160, lens=lens)
+    torch.cuda.synchronize()
+    same(w.cpu().numpy().view(np.complex64).reshape(n, 7)[ok], g["w"][ok], "w")
+    same(b.cpu().numpy().view(np.complex64).reshape(n, 5)[ok], g["b"][ok], "b")
+    same(soft.cpu().numpy().reshape(n, 160)[ok], g["soft"][ok], "soft via analyze + designDFE + equalize")
+    # and the stand-alone equalizeBurst on one of them leaves the same delayed burst behind
+    i = int(np.flatnonzero(ok)[0])
+    s1, after1 = oracle_best.equalize(scaled[i, :g["lens"][i]], float(g["toa"][i] - g["off"][i]), g["w"][i], g["b"][i])
+    same(after.cpu().numpy().view(np.complex64).reshape(n, 160)[i, :g["lens"][i]], after1, "burst after equalize")
