@@ -1,0 +1,67 @@
+"""The sigProcLib.h-compatible C++ shim (openbts_ttsou_b200/host) driving the reference's own test flow on the GPU;
+every stage it produces is replayed through the oracle on the same inputs."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_same
+
+pytestmark = pytest.mark.gpu
+
+
+def read_dump(path):
+    out, data = {}, open(path, "rb").read()
+    pos = 0
+    while pos < len(data):
+        tag = data[pos:pos + 8].split(b"\0")[0].decode()
+        n = struct.unpack("<I", data[pos + 8:pos + 12])[0]
+        out[tag] = data[pos + 12:pos + 12 + n]
+        pos += 12 + n
+    return out
+
+
+def test_reference_test_flow_through_the_shim(tmp_path, oracle_best):
+    from openbts_ttsou_b200.build import build
+    lib = build()
+    host = os.path.join(ROOT, "openbts_ttsou_b200", "host")
+    exe = str(tmp_path / "flow")
+    subprocess.run(["g++", "-std=c++11", "-O2", "-I", os.path.join(ROOT, "include"), "-I", host,
+                    os.path.join(ROOT, "tests", "cpp", "sigproc_flow_test.cpp"), os.path.join(host, "sigProcLib.cpp"),
+                    "-L", os.path.dirname(lib), "-lbtsdsp", "-Wl,-rpath," + os.path.dirname(lib), "-o", exe], check=True)
+    dump = str(tmp_path / "flow.bin")
+    r = subprocess.run([exe, dump], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    d = read_dump(dump)
+    c64 = lambda k: np.frombuffer(d[k], np.complex64)  # noqa: E731
+    f32 = lambda k: np.frombuffer(d[k], np.float32)  # noqa: E731
+    o = oracle_best
+    bits = np.array([int(c) for c in "0000101010100111110010101010010110101110011000111001101010000"
+                     "00100101110000100010010111" "0000101010100111110010101010010110101110011000111001101010000"], np.uint8)
+    assert_same(c64("tx"), o.modulate(bits, 8), "modulateBurst")
+    assert_same(c64("up"), o.resample(c64("tx"), 96, 65, 1), "polyphaseResampleVector 96/65")
+    assert_same(c64("down"), o.resample(c64("up"), 65, 96, 0), "polyphaseResampleVector 65/96")
+    rx = c64("rx")
+    ok, amp, toa, chan, off = o.analyze(rx, 0, 8.0, request=True)
+    meta = f32("meta")
+    assert bool(meta[0]) == ok and np.complex64(complex(meta[1], meta[2])) == amp and meta[3] == np.float32(toa) and meta[4] == off
+    assert_same(c64("chan"), chan, "channel response")
+    assert_same(f32("slicer"), o.demodulate(rx, amp, toa), "demodulateBurst")
+    # complex(1,0)/amp with the reference's inv(): (r/n, -i/n)
+    n2 = np.float32(amp.imag) * np.float32(amp.imag) + np.float32(amp.real) * np.float32(amp.real)
+    s = np.complex64(complex(np.float32(amp.real) / n2, -np.float32(amp.imag) / n2))
+    chs = o.scale_vector(chan, s)
+    snr = np.float32(np.float64(n2) / (np.float64(np.float32(250.0) * np.float32(250.0)) + 1.0))
+    w, b = o.design_dfe(chs, float(snr), 7)
+    assert_same(c64("w"), w, "DFE feed-forward"); assert_same(c64("b"), b, "DFE feedback")
+    soft, after = o.equalize(o.scale_vector(rx, s), toa - off, w, b)
+    assert_same(f32("soft"), soft, "equalizeBurst"); assert_same(c64("after"), after, "burst after equalizeBurst")
+    rok, ramp, rtoa = o.detect_rach(c64("rachrx"), 5.0)
+    rm = f32("rachmeta")
+    assert bool(rm[0]) == rok and np.complex64(complex(rm[1], rm[2])) == ramp and rm[3] == np.float32(rtoa)
+    e = f32("energy")
+    eo = o.energy_detect(rx, 20, 250.0)
+    assert bool(e[0]) == eo[0] and e[1] == np.float32(eo[1])
+    assert "DFE bit errors=0" in r.stdout
