@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbtsdsp.so")
 SOURCES = ["capi.cu", "kernels.cu", "resample.cu"]
-HEADERS = ["cplx.cuh", "tables.h", "sigproc_device.cuh", "kernels.cuh", "lpf_taps.inc", "tables_host.h", "../../include/btsdsp.h"]
+HEADERS = ["cplx.cuh", "tables.h", "sigproc_device.cuh", "demod_fast.cuh", "kernels.cuh", "lpf_taps.inc", "tables_host.h", "../../include/btsdsp.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",

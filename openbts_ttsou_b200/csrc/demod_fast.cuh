@@ -1,0 +1,343 @@
+// demod_fast.cuh -- the tuned one-burst-per-thread receive path for sps == 1 (k_demod_normal).
+//
+// Same arithmetic, operand order and accumulation order as sigproc_device.cuh (which restates the reference
+// loop by loop) -- only the *schedule* differs:
+//   * FIRs are register-blocked: a thread produces 4 (or 12) consecutive outputs per sweep over its column of
+//     the transposed tile, so a sample is loaded once per 4 outputs instead of once per tap, the tap loops are
+//     fully unrolled (no loop-carried index arithmetic, no bounds branches on interior blocks) and the 8
+//     independent accumulation chains give a single warp enough ILP to keep its scheduler busy;
+//   * the equaliser is streamed: delayVector's 21-tap fractional FIR, the 7-tap feed-forward filter and the
+//     decision-feedback recursion run as one pipeline over the burst with a 10-sample register window, so the
+//     delayed burst and the feed-forward output never exist in memory (one tile per warp instead of three);
+//   * the channel-window search needs only 12 samples of the delayed correlation, so only those are computed;
+//   * all sinc interpolators are rows of the 1/512-grid table (see tables.h) held in shared memory.
+// Every function is __host__ __device__: tests/hostemu replays them on the CPU against the oracle.
+#pragma once
+#include "sigproc_device.cuh"
+
+namespace btsdsp {
+
+constexpr int kGridPitch = 21;      // floats per sinc-grid row in the compact (shared-memory) copy
+
+BTS_HD void load_grid_row(const float *__restrict__ grid, int j, float s[21]) {
+#pragma unroll
+  for (int t = 0; t < 21; t++) s[t] = grid[j * kGridPitch + t];
+}
+
+// taps of correlate(window, midamble) (:474-503): tap[k] = conj(seq[15-k])
+BTS_HD void load_corr_taps(const DevTables *__restrict__ T, int tsc, cf tap[16]) {
+#pragma unroll
+  for (int k = 0; k < 16; k++) tap[k] = cconj(T->mid_seq[tsc][15 - k]);
+}
+
+// correlate(burst[56..92), midamble, NO_DELAY): 36 outputs x 16 complex taps, start index 7 (:295-301).
+// c[n] = sum_k win[n+7-k]*tap[k], window indices outside [0,36) are not part of the vector.
+template <int S>
+BTS_HD void corr36(View<S> win, View<S> out, const cf tap[16]) {
+  for (int n0 = 0; n0 < 36; n0 += 4) {
+    cf acc[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) acc[r] = mk(0.0F, 0.0F);
+#pragma unroll
+    for (int j = 0; j < 19; j++) {
+      const int idx = n0 + 10 - j;                       // descending window index == ascending tap index
+      if ((unsigned)idx < 36u) {
+        const cf v = win.ld(idx);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const int k = j + r - 3;                       // = (n0 + r + 7) - idx
+          if (k >= 0 && k < 16) acc[r] = cadd(acc[r], cmul(v, tap[k]));
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) out.st(n0 + r, acc[r]);
+  }
+}
+
+// interpolatePoint (:639-659) at ix = I + j/512 with the grid row s[] (s[t] = sinc(pi*((t-10) - j/512)))
+template <int S>
+BTS_HD cf interp21(const float s[21], View<S> c, int n, int I) {
+  int start = I - 10;
+  if (start < 0) start = 0;
+  int end = I + 11;
+  if ((unsigned long long)(unsigned)end > (unsigned long long)n - 1) end = n - 1;
+  cf p = mk(0.0F, 0.0F);
+#pragma unroll
+  for (int t = 0; t < 21; t++) {
+    const int i = I - 10 + t;
+    if (i >= start && i < end) p = cadd(p, cmulr(c.ld(i), s[t]));
+  }
+  return p;
+}
+
+// peakDetect (:663-711) on the 1/512 grid; avgPwr is not needed by analyzeTrafficBurst
+template <int S>
+BTS_HD cf peak_detect_fast(const float *__restrict__ grid, View<S> c, int n, float *peakIndex) {
+  float maxVal = 0.0F;
+  int imax = -1;
+  for (int i = 0; i < n; i++) {
+    const float p = cnorm2(c.ld(i));
+    if (p > maxVal) { maxVal = p; imax = i; }
+  }
+  int e512 = (imax - 1) * kSincGrid;                     // earlyIndex * 512
+  float s[21];
+  for (int step = kSincGrid / 2; step >= 1; step >>= 1) {
+    const int I = e512 >> 9, j = e512 & (kSincGrid - 1);
+    load_grid_row(grid, j, s);
+    const float e = cnorm2(interp21<S>(s, c, n, I)), l = cnorm2(interp21<S>(s, c, n, I + 2));
+    if (e < l) e512 += step;
+    else if (e > l) e512 -= step;
+    else break;
+  }
+  load_grid_row(grid, e512 & (kSincGrid - 1), s);
+  *peakIndex = BTS_ADD((float)e512 * (1.0F / kSincGrid), 1.0F);
+  return interp21<S>(s, c, n, (e512 >> 9) + 1);
+}
+
+// the 21 taps of delayVector's fractional filter (:583-588); on the grid they are a table row
+BTS_HD void load_delay_taps(const float *__restrict__ grid, const DevTables *__restrict__ T, float frac, float s[21]) {
+  const float f512 = frac * (float)kSincGrid;
+  const int j = (int)f512;
+  if ((float)j == f512 && j >= 0 && j < kSincGrid) load_grid_row(grid, j, s);
+  else {
+#pragma unroll
+    for (int i = 0; i < 21; i++) s[i] = sinc_exact(T, BTS_MUL(kPiF, BTS_SUB((float)(i - 10), frac)));
+  }
+}
+
+// delayVector(corr, delay) (:573-616) evaluated only at the 12 positions [smin, smin+12) the channel-window
+// search of analyzeTrafficBurst reads: out[n] = F[n - io] with F = the 21-tap filtered vector (or corr itself
+// when the fraction is <= 0.01), zero where n - io falls outside the vector.
+template <int S>
+BTS_HD void delayed12(const float *__restrict__ grid, const DevTables *__restrict__ T, View<S> c, int L, float delay,
+                      int smin, cf dl[12]) {
+  const int io = (int)floorf(delay);
+  const float frac = BTS_SUB(delay, (float)io);
+  const int x0 = smin - io;
+  if ((double)fabsf(frac) > 1e-2) {
+    float s[21];
+    load_delay_taps(grid, T, frac, s);
+    cf acc[12];
+#pragma unroll
+    for (int q = 0; q < 12; q++) acc[q] = mk(0.0F, 0.0F);
+#pragma unroll
+    for (int jj = 0; jj < 32; jj++) {
+      const int row = x0 + 21 - jj;
+      if ((unsigned)row < (unsigned)L) {
+        const cf v = c.ld(row);
+#pragma unroll
+        for (int q = 0; q < 12; q++) {
+          const int k = q - 11 + jj;                     // = (x0 + q + 10) - row
+          if (k >= 0 && k <= 20) acc[q] = cadd(acc[q], cmulr(v, s[k]));
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 12; q++) dl[q] = ((unsigned)(x0 + q) < (unsigned)L) ? acc[q] : mk(0.0F, 0.0F);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 12; q++) dl[q] = ((unsigned)(x0 + q) < (unsigned)L) ? c.ld(x0 + q) : mk(0.0F, 0.0F);
+  }
+}
+
+// analyzeTrafficBurst (:935-1037) at sps == 1 with requestChannel == true.  win = burst rows 56..91,
+// corr = 36 scratch rows.  Same outputs as analyze_traffic<S, true>.
+template <int S>
+BTS_HD bool analyze_fast(const float *__restrict__ grid, const DevTables *__restrict__ T, View<S> win, View<S> corr,
+                         int tsc, float thr, cf *amplitude, float *TOA, cf chan[6], float *chanOff) {
+  constexpr int L = 36;
+  {
+    cf tap[16];
+    load_corr_taps(T, tsc, tap);
+    corr36<S>(win, corr, tap);
+  }
+  float toa;
+  cf amp = peak_detect_fast<S>(grid, corr, L, &toa);
+  if ((toa < 0.0F) || (toa > (float)L)) { *amplitude = mk(0.0F, 0.0F); *TOA = toa; return false; }
+  const int p = (int)rintf(toa);
+  float valley = 0.0F;
+  int numRms = 0;
+#pragma unroll
+  for (int i = 2; i <= 5; i++) {
+    if (p - i >= 0) { valley = BTS_ADD(valley, cnorm2(corr.ld(p - i))); numRms++; }
+    if (p + i < L)  { valley = BTS_ADD(valley, cnorm2(corr.ld(p + i))); numRms++; }
+  }
+  if (numRms < 2) { *amplitude = mk(0.0F, 0.0F); *TOA = toa; return false; }
+  const float RMS = (float)((double)BTS_SQRT(BTS_DIV(valley, (float)numRms)) + 0.00001);
+  const float peakToMean = BTS_DIV(cabs_(amp), RMS);
+  const float mtoa = T->mid_toa[tsc];
+  const cf gain = T->mid_gain[tsc];
+  amp = cdiv(amp, gain);
+  toa = BTS_SUB(BTS_SUB(toa, mtoa), 10.0F);
+  *amplitude = amp;
+  *TOA = toa;
+  if (!(peakToMean > thr)) return false;
+  // channel estimate :1005-1031
+  const float TOAoffset = BTS_ADD(mtoa, 10.0F);
+  const int smin = (int)floorf(BTS_ADD(TOAoffset, -5.0F));          // window i starts at smin + i (mtoa = 8 +- k/512)
+  cf dl[12];
+  delayed12<S>(grid, T, corr, L, -toa, smin, dl);
+  float maxEnergy = -1.0F;
+  int maxI = -1;
+#pragma unroll
+  for (int i = 0; i < 7; i++) {
+    const float pos = BTS_ADD(TOAoffset, (float)(i - 5));
+    if (BTS_ADD(pos, 6.0F) > (float)L) continue;
+    if (pos < 0.0F) continue;
+    float energy = 0.0F;
+#pragma unroll
+    for (int j = 0; j < 6; j++) energy = BTS_ADD(energy, cnorm2(dl[i + j]));
+    if ((double)energy > 0.95 * (double)maxEnergy) { maxI = i; maxEnergy = energy; }
+  }
+  const cf g = cdiv(mk(1.0F, 0.0F), gain);
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    cf v = dl[j];
+#pragma unroll
+    for (int i = 1; i < 7; i++) if (maxI == i) v = dl[i + j];
+    chan[j] = cmul(v, g);
+  }
+  *chanOff = (float)(5 - maxI);
+  return true;
+}
+
+// equalizeBurst (:1343-1399) as a streaming pipeline over one lane's column `a` (the burst, already scaled by
+// 1/amplitude).  F = delayVector's fractional FIR output, D[n] = F[n - io] the delayed burst, y = feed-forward
+// output, then decision feedback.  Window Fw[i] = F[q0 + i], q0 = m0 - io for the block of outputs m0..m0+3.
+template <int S>
+struct EqLane {
+  View<S> a;
+  int N, io;
+  bool nofrac;
+  float s[21];
+  cf w[7], b[5], hist[5], Fw[10];
+
+  BTS_HD void init(const float *__restrict__ grid, const DevTables *__restrict__ T, View<S> burst, int n, float TOA,
+                   const cf *w_, const cf *b_) {
+    a = burst;
+    N = n;
+    const float delay = -TOA;                                     // delayVector(rxBurst, -TOA) :1350
+    io = (int)floorf(delay);
+    const float frac = BTS_SUB(delay, (float)io);
+    nofrac = !((double)fabsf(frac) > 1e-2);
+    if (nofrac) {
+#pragma unroll
+      for (int t = 0; t < 21; t++) s[t] = 0.0F;
+    } else {
+      load_delay_taps(grid, T, frac, s);
+    }
+#pragma unroll
+    for (int k = 0; k < 7; k++) w[k] = w_[k];
+#pragma unroll
+    for (int k = 0; k < 5; k++) { b[k] = b_[k]; hist[k] = mk(0.0F, 0.0F); }
+    // window for the first block: F[-io .. -io+5]
+    cf t4[4];
+    newF4<true>(-io - 2, t4);
+    Fw[0] = t4[2]; Fw[1] = t4[3];
+    newF4<true>(-io + 2, &Fw[2]);
+  }
+
+  // F[x0..x0+3]; CHECKED = rows/indices may fall outside the burst
+  template <bool CHECKED>
+  BTS_HD void newF4(int x0, cf out[4]) const {
+    cf acc[4], center[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) { acc[r] = mk(0.0F, 0.0F); center[r] = mk(0.0F, 0.0F); }
+#pragma unroll
+    for (int jj = 0; jj < 24; jj++) {
+      const int row = x0 + 13 - jj;
+      const bool inr = CHECKED ? ((unsigned)row < (unsigned)N) : true;
+      if (inr) {
+        const cf v = a.ld(row);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const int k = r - 3 + jj;                               // = (x0 + r + 10) - row
+          if (k >= 0 && k <= 20) acc[r] = cadd(acc[r], cmulr(v, s[k]));
+          if (k == 10) center[r] = v;                             // row == x0 + r
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      cf f = nofrac ? center[r] : acc[r];
+      if (CHECKED) {
+        const int x = x0 + r;
+        if (!((unsigned)x < (unsigned)N && (unsigned)(x + io) < (unsigned)N)) f = mk(0.0F, 0.0F);
+      }
+      out[r] = f;
+    }
+  }
+
+  BTS_HD bool interior(int m0) const {
+    const int x0 = m0 - io + 6;
+    return x0 - 10 >= 0 && x0 + 13 <= N - 1 && m0 + 9 <= N - 1;
+  }
+
+  // feed-forward outputs y[m0..m0+3] (consumes the window, then slides it by 4)
+  template <bool CHECKED>
+  BTS_HD void compute_y(int m0, cf y[4]) {
+    newF4<CHECKED>(m0 - io + 6, &Fw[6]);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      cf sum = mk(0.0F, 0.0F);
+#pragma unroll
+      for (int k = 0; k < 7; k++) sum = cadd(sum, cmul(Fw[r + 6 - k], w[k]));
+      y[r] = sum;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) Fw[i] = Fw[i + 4];
+  }
+
+  // decision feedback + slicer for m = m0..m0+3 (:1367-1386)
+  BTS_HD void feedback4(const DevTables *__restrict__ T, int m0, const cf y[4], float soft[4]) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int m = m0 + r;
+      cf v = y[r];
+#pragma unroll
+      for (int k = 0; k < 5; k++)
+        if (m - 1 - k >= 0) v = cadd(v, cmul(b[k], hist[k]));
+      const int mi = m < 157 ? m : 156;                           // the tail block may run past the burst
+      const cf rr = T->revrot[mi];
+      const float out = BTS_SUB(BTS_MUL(v.x, rr.x), BTS_MUL(v.y, rr.y));   // real part of v * revrot[m]
+#pragma unroll
+      for (int k = 4; k >= 1; k--) hist[k] = hist[k - 1];
+      hist[0] = cmul(mk((out > 0.0F) ? 1.0F : -1.0F, 0.0F), T->rot[mi]);
+      soft[r] = soft_slice(out);
+    }
+  }
+
+  // one pipeline step: feed-forward for the NEXT block (independent work) + feedback for the current one
+  template <bool CHECKED>
+  BTS_HD void step(const DevTables *__restrict__ T, int m0, bool have_next, cf ycur[4], float soft[4]) {
+    cf ynext[4];
+    if (have_next) compute_y<CHECKED>(m0 + 4, ynext);
+    feedback4(T, m0, ycur, soft);
+    if (have_next) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) ycur[r] = ynext[r];
+    }
+  }
+};
+
+// The whole per-lane equaliser on the host side of the emulation (and the reference loop for the kernel):
+// soft[m] for m < n.  The kernel drives the same steps but votes `interior` across the warp.
+template <int S>
+BTS_HD void equalize_fast_lane(const float *__restrict__ grid, const DevTables *__restrict__ T, View<S> burst, int n,
+                               float TOA, const cf *w, const cf *b, float *soft) {
+  EqLane<S> eq;
+  eq.init(grid, T, burst, n, TOA, w, b);
+  cf ycur[4];
+  if (eq.interior(0)) eq.template compute_y<false>(0, ycur);
+  else eq.template compute_y<true>(0, ycur);
+  for (int m0 = 0; m0 < n; m0 += 4) {
+    float s4[4];
+    const bool have_next = m0 + 4 < n;
+    if (have_next && eq.interior(m0 + 4)) eq.template step<false>(T, m0, have_next, ycur, s4);
+    else eq.template step<true>(T, m0, have_next, ycur, s4);
+    for (int r = 0; r < 4; r++) if (m0 + r < n) soft[m0 + r] = s4[r];
+  }
+}
+
+}  // namespace btsdsp

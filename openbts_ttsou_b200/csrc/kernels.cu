@@ -10,6 +10,7 @@
 // throughput comes from bursts in flight, not from splitting one burst across lanes.
 #include "kernels.cuh"
 #include "sigproc_device.cuh"
+#include "demod_fast.cuh"
 
 namespace btsdsp {
 
@@ -229,43 +230,74 @@ void launch_modulate_impulse(const DevTables *T, const uint8_t *bits, int nbits,
 // ------------------------------------------------------------------------------------------------
 // normal-burst receive, fused: energy gate -> analyzeTrafficBurst -> designDFE -> equalizeBurst
 // (reference Transceiver.cpp:298-396 with estimateChannel == true for every burst); sps == 1.
-// One warp per CTA, one burst per lane.
+// One burst per lane, WARPS independent warps per CTA sharing one shared-memory copy of the sinc grid.
+// Shared memory per warp: ONE transposed tile of 160 rows (42 KB).  Phase 1 (detect, channel, DFE design)
+// stages only the 36-sample midamble window (rows 56..91; rows 0..19 too when the energy gate is on) and
+// keeps the correlation in rows 100..135; phase 2 re-stages the detected bursts in full, scaled by
+// 1/amplitude on the way in, and runs the streaming equaliser of demod_fast.cuh.
 // ------------------------------------------------------------------------------------------------
 constexpr int kCorrRows = 36;
-constexpr size_t kDemodSmem = (size_t)(2 * kBurstRows + kCorrRows) * kTileStride * sizeof(cf);
+constexpr int kCorrBase = 100;
+constexpr size_t kGridBytes = (size_t)kSincGrid * kGridPitch * sizeof(float);
+constexpr size_t kTileBytes = (size_t)kBurstRows * kTileStride * sizeof(cf);
+template <int WARPS> constexpr size_t demod_smem() { return kGridBytes + WARPS * kTileBytes; }
 
-__global__ void __launch_bounds__(32) k_demod_normal(const DevTables *__restrict__ T, BurstSrc src,
-                                                     const uint8_t *__restrict__ tsc, long long n, float detect_thr,
-                                                     float gate_thr, float snr_thr, NormalOut out) {
-  extern __shared__ cf tile[];
-  cf *A = tile, *B = tile + kBurstRows * kTileStride, *C = B + kBurstRows * kTileStride;
-  const int lane = threadIdx.x;
-  const long long w0 = (long long)blockIdx.x * 32;
+__device__ __forceinline__ void store_soft_row(float *row, int pitch, int m0, const float s4[4], int len) {
+  // m0 is a multiple of 4; vector path when the row is 16-byte aligned
+  if (((reinterpret_cast<uintptr_t>(row) | (uintptr_t)(pitch * 4)) & 15) == 0 && m0 + 3 < len && m0 + 3 < pitch) {
+    *reinterpret_cast<float4 *>(row + m0) = make_float4(s4[0], s4[1], s4[2], s4[3]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; r++) if (m0 + r < len && m0 + r < pitch) row[m0 + r] = s4[r];
+  }
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_demod_normal(const DevTables *__restrict__ T, BurstSrc src,
+                                                             const uint8_t *__restrict__ tsc, long long n,
+                                                             float detect_thr, float gate_thr, float snr_thr,
+                                                             NormalOut out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float *grid = reinterpret_cast<float *>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  cf *A = reinterpret_cast<cf *>(smem_raw + kGridBytes) + (size_t)warp * kBurstRows * kTileStride;
+  for (int i = threadIdx.x; i < kSincGrid * kGridPitch; i += WARPS * 32) grid[i] = T->sinc_grid[i / kGridPitch][i % kGridPitch];
+  __syncthreads();
+  const long long w0 = ((long long)blockIdx.x * WARPS + warp) * 32;
+  if (w0 >= n) return;
   const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
-  stage_in(A, src, w0, nv, lane);
+  const bool gated = gate_thr >= 0.0F;
+
+  // ---- phase 1 staging: the midamble window (and the energy-gate window)
+  for (int j = 0; j < nv; j++) {
+    long long start; int len;
+    burst_loc(src, w0 + j, &start, &len);
+    const cf *g = src.base + start;
+    for (int i = lane; i < 36; i += 32) A[(56 + i) * kTileStride + j] = __ldg(g + 56 + i);
+    if (gated && lane < 20) A[lane * kTileStride + j] = __ldg(g + lane);
+  }
+  __syncwarp();
 
   const long long i = w0 + lane;
+  const View<kTileStride> a{A + lane};
   bool ok = false;
   int len = 0;
+  long long start = 0;
+  cf amp = mk(0.0F, 0.0F), ia = mk(0.0F, 0.0F), chan[6], w[7], fb[5];
+  float toa = 0.0F, off = 0.0F;
   if (lane < nv) {
-    long long start;
     burst_loc(src, i, &start, &len);
-    const View<kTileStride> a{A + lane}, b{B + lane}, c{C + lane};
-    cf amp = mk(0.0F, 0.0F), chan[6], w[7], fb[5];
-    float toa = 0.0F, off = 0.0F;
+    if (len > kBurstRows - 3) len = kBurstRows - 3;
     bool pass = true;
-    if (gate_thr >= 0.0F) pass = energy_detect<kTileStride>(a, len, 20, gate_thr, nullptr);     // Transceiver.cpp:298
-    if (pass) ok = analyze_traffic<kTileStride, true>(T, a, tsc[i], detect_thr, 1, c, b, &amp, &toa, true, chan, &off);
+    if (gated) pass = energy_detect<kTileStride>(a, len, 20, gate_thr, nullptr);                 // Transceiver.cpp:298
+    if (pass) ok = analyze_fast<kTileStride>(grid, T, a.at(56), a.at(kCorrBase), tsc[i], detect_thr, &amp, &toa, chan, &off);
     if (ok) {
       // Transceiver.cpp:340  SNRestimate = amplitude.norm2()/(thr*thr + 1.0)  (double division)
       const float SNR = (float)((double)cnorm2(amp) / ((double)BTS_MUL(snr_thr, snr_thr) + 1.0));
-      const cf ia = cdiv(mk(1.0F, 0.0F), amp);
+      ia = cdiv(mk(1.0F, 0.0F), amp);
 #pragma unroll
       for (int j = 0; j < 6; j++) chan[j] = cmul(chan[j], ia);                                  // :346
       design_dfe<7, 5>(chan, 5, SNR, 7, w, fb);                                                 // :347
-      for (int m = 0; m < len; m++) a.st(m, cmul(a.ld(m), ia));                                 // :391
-      equalize_burst<kTileStride, 2 * kTileStride>(T, a, len, BTS_SUB(toa, off), w, 7, fb, 5, b,
-                                                   (float *)(B + lane));                      // :392-396
     }
     if (out.flag) out.flag[i] = ok ? 1 : 0;
     if (out.amp) out.amp[i] = amp;
@@ -275,12 +307,55 @@ __global__ void __launch_bounds__(32) k_demod_normal(const DevTables *__restrict
     if (out.w) for (int j = 0; j < 7; j++) out.w[i * 7 + j] = ok ? w[j] : mk(0.0F, 0.0F);
     if (out.b) for (int j = 0; j < 5; j++) out.b[i * 5 + j] = ok ? fb[j] : mk(0.0F, 0.0F);
   }
-  if (out.soft) stage_out_soft(B, out.soft, out.soft_pitch, w0, nv, lane, ok, len);
+  if (!out.soft) return;
+
+  // ---- phase 2 staging: detected bursts in full, scaled by 1/amplitude (scaleVector, Transceiver.cpp:391)
+  __syncwarp();
+  const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+  for (unsigned rem = okmask; rem; rem &= rem - 1) {
+    const int j = __ffs(rem) - 1;
+    const cf iaj = mk(__shfl_sync(0xffffffffu, ia.x, j), __shfl_sync(0xffffffffu, ia.y, j));
+    const long long sj = __shfl_sync(0xffffffffu, start, j);
+    const int lj = __shfl_sync(0xffffffffu, len, j);
+    const cf *g = src.base + sj;
+    for (int r = lane; r < lj; r += 32) A[r * kTileStride + j] = cmul(__ldg(g + r), iaj);
+  }
+  __syncwarp();
+
+  float *row = out.soft + i * (long long)out.soft_pitch;
+  if (ok) {
+    EqLane<kTileStride> eq;
+    eq.init(grid, T, a, len, BTS_SUB(toa, off), w, fb);                                         // :392-396
+    const int nmax = __reduce_max_sync(okmask, len);
+    cf ycur[4];
+    if (__all_sync(okmask, eq.interior(0))) eq.template compute_y<false>(0, ycur);
+    else eq.template compute_y<true>(0, ycur);
+    for (int m0 = 0; m0 < nmax; m0 += 4) {
+      float s4[4];
+      const bool have_next = m0 + 4 < nmax;
+      if (__all_sync(okmask, have_next && eq.interior(m0 + 4))) eq.template step<false>(T, m0, have_next, ycur, s4);
+      else eq.template step<true>(T, m0, have_next, ycur, s4);
+      store_soft_row(row, out.soft_pitch, m0, s4, len);
+    }
+    for (int m = len; m < out.soft_pitch; m++) row[m] = 0.0F;
+  } else if (lane < nv) {
+    if (((reinterpret_cast<uintptr_t>(row) | (uintptr_t)(out.soft_pitch * 4)) & 15) == 0) {
+      for (int m = 0; m < out.soft_pitch; m += 4) *reinterpret_cast<float4 *>(row + m) = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
+    } else {
+      for (int m = 0; m < out.soft_pitch; m++) row[m] = 0.0F;
+    }
+  }
 }
 int launch_demod_normal(const DevTables *T, BurstSrc src, const uint8_t *tsc, long long n, float detect_thr,
                         float gate_thr, float snr_thr, NormalOut out, cudaStream_t st) {
   if (n <= 0) return 0;
-  k_demod_normal<<<(unsigned)((n + 31) / 32), 32, kDemodSmem, st>>>(T, src, tsc, n, detect_thr, gate_thr, snr_thr, out);
+  const long long nwarps = (n + 31) / 32;
+  if (nwarps >= 148 * 4) {
+    k_demod_normal<4><<<(unsigned)((nwarps + 3) / 4), 128, demod_smem<4>(), st>>>(T, src, tsc, n, detect_thr, gate_thr,
+                                                                                snr_thr, out);
+  } else {
+    k_demod_normal<1><<<(unsigned)nwarps, 32, demod_smem<1>(), st>>>(T, src, tsc, n, detect_thr, gate_thr, snr_thr, out);
+  }
   return 1;
 }
 
@@ -488,7 +563,9 @@ void launch_equalize_generic(const DevTables *T, cf *burst, int n, float toa, co
 
 int configure_kernels() {
   cudaError_t e;
-  e = cudaFuncSetAttribute(k_demod_normal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDemodSmem);
+  e = cudaFuncSetAttribute(k_demod_normal<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)demod_smem<4>());
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_demod_normal<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)demod_smem<1>());
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_analyze<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAnalyzeSmem);
   if (e != cudaSuccess) return (int)e;

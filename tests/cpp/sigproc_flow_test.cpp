@@ -84,7 +84,7 @@ int main(int argc, char **argv) {
   complex ramp; float rtoa = 0;
   bool rok = detectRACHBurst(rrx, 5.0F, sps, &ramp, &rtoa);
   float rmeta[4] = {(float)rok, ramp.real(), ramp.imag(), rtoa};
-  put(f, "rachmeta", rmeta, sizeof rmeta);
+  put(f, "rachm", rmeta, sizeof rmeta);
   float avg = 0;
   bool e = energyDetect(*faded, 20 * sps, 250.0F, &avg);
   float emeta[2] = {(float)e, avg};

@@ -14,6 +14,7 @@
 
 #include "../../openbts_ttsou_b200/csrc/kernels.cuh"
 #include "../../openbts_ttsou_b200/csrc/sigproc_device.cuh"
+#include "../../openbts_ttsou_b200/csrc/demod_fast.cuh"
 #include "../../openbts_ttsou_b200/csrc/tables_host.h"
 
 using namespace btsdsp;
@@ -130,45 +131,67 @@ int emu_check_sinc_grid(void) {
   return bad;
 }
 
-// k_demod_normal, warp by warp, lane by lane
+// k_demod_normal (demod_fast.cuh), warp by warp, lane by lane: one tile per warp, phase 1 on the midamble
+// window with the correlation in rows 100..135, phase 2 on the re-staged, 1/amp-scaled burst.
 void emu_demod_normal(const float *bursts, long long pitch, const int *lens, long long first, const uint8_t *tsc,
                       long long n, float detect_thr, float gate_thr, float snr_thr, int *flag, float *amp, float *toa,
                       float *soft, int soft_pitch, float *chan_o, float *off_o, float *w_o, float *b_o) {
-  std::vector<cf> tile((2 * kBurstRows + 36) * kTileStride);
-  cf *A = tile.data(), *B = A + kBurstRows * kTileStride, *C = B + kBurstRows * kTileStride;
+  std::vector<float> grid(kSincGrid * kGridPitch);
+  for (int i = 0; i < kSincGrid * kGridPitch; i++) grid[i] = T->sinc_grid[i / kGridPitch][i % kGridPitch];
+  std::vector<cf> tile(kBurstRows * kTileStride);
+  cf *A = tile.data();
+  const bool gated = gate_thr >= 0.0F;
   for (long long w0 = 0; w0 < n; w0 += 32) {
     const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
+    for (size_t k = 0; k < tile.size(); k++) A[k] = mk(1e30F, -1e30F);       // poison: catch reads of unstaged rows
     for (int j = 0; j < nv; j++) {
       long long start; int len;
       burst_loc_h((const cf *)bursts, pitch, lens, first, 1, w0 + j, &start, &len);
-      for (int i = 0; i < len; i++) A[i * kTileStride + j] = ((const cf *)bursts)[start + i];
+      const cf *g = (const cf *)bursts + start;
+      for (int i = 0; i < 36; i++) A[(56 + i) * kTileStride + j] = g[56 + i];
+      if (gated) for (int i = 0; i < 20; i++) A[i * kTileStride + j] = g[i];
     }
+    bool okv[32]; int lenv[32]; long long startv[32]; cf iav[32], wv[32][7], fbv[32][5]; float toav[32], offv[32];
     for (int lane = 0; lane < nv; lane++) {
       const long long i = w0 + lane;
       long long start; int len;
       burst_loc_h((const cf *)bursts, pitch, lens, first, 1, i, &start, &len);
-      const View<kTileStride> a{A + lane}, b{B + lane}, c{C + lane};
-      cf ampv = mk(0.0F, 0.0F), chan[6], w[7], fb[5];
-      float toav = 0.0F, off = 0.0F;
+      if (len > kBurstRows - 3) len = kBurstRows - 3;
+      const View<kTileStride> a{A + lane};
+      cf ampv = mk(0.0F, 0.0F), ia = mk(0.0F, 0.0F), chan[6], w[7], fb[5];
+      float tv = 0.0F, off = 0.0F;
       bool pass = true, ok = false;
-      if (gate_thr >= 0.0F) pass = energy_detect<kTileStride>(a, len, 20, gate_thr, nullptr);
-      if (pass) ok = analyze_traffic<kTileStride, true>(T, a, tsc[i], detect_thr, 1, c, b, &ampv, &toav, true, chan, &off);
+      if (gated) pass = energy_detect<kTileStride>(a, len, 20, gate_thr, nullptr);
+      if (pass) ok = analyze_fast<kTileStride>(grid.data(), T, a.at(56), a.at(100), tsc[i], detect_thr, &ampv, &tv, chan, &off);
       if (ok) {
         const float SNR = (float)((double)cnorm2(ampv) / ((double)BTS_MUL(snr_thr, snr_thr) + 1.0));
-        const cf ia = cdiv(mk(1.0F, 0.0F), ampv);
+        ia = cdiv(mk(1.0F, 0.0F), ampv);
         for (int j = 0; j < 6; j++) chan[j] = cmul(chan[j], ia);
         design_dfe<7, 5>(chan, 5, SNR, 7, w, fb);
-        for (int m = 0; m < len; m++) a.st(m, cmul(a.ld(m), ia));
-        equalize_burst<kTileStride, 2 * kTileStride>(T, a, len, BTS_SUB(toav, off), w, 7, fb, 5, b, (float *)(B + lane));
       }
-      flag[i] = ok; amp[2 * i] = ampv.x; amp[2 * i + 1] = ampv.y; toa[i] = toav;
+      flag[i] = ok; amp[2 * i] = ampv.x; amp[2 * i + 1] = ampv.y; toa[i] = tv;
       if (off_o) off_o[i] = ok ? off : 0.0F;
       for (int j = 0; j < 6 && chan_o; j++) ((cf *)chan_o)[i * 6 + j] = ok ? chan[j] : mk(0.0F, 0.0F);
       for (int j = 0; j < 7 && w_o; j++) ((cf *)w_o)[i * 7 + j] = ok ? w[j] : mk(0.0F, 0.0F);
       for (int j = 0; j < 5 && b_o; j++) ((cf *)b_o)[i * 5 + j] = ok ? fb[j] : mk(0.0F, 0.0F);
-      const float *tf = (const float *)B;
-      for (int m = 0; m < soft_pitch; m++)
-        soft[i * soft_pitch + m] = (ok && m < len) ? tf[(m * kTileStride + lane) * 2] : 0.0F;
+      okv[lane] = ok; lenv[lane] = len; startv[lane] = start; iav[lane] = ia; toav[lane] = tv; offv[lane] = off;
+      for (int j = 0; j < 7; j++) wv[lane][j] = w[j];
+      for (int j = 0; j < 5; j++) fbv[lane][j] = fb[j];
+    }
+    for (int j = 0; j < nv; j++) {
+      if (!okv[j]) continue;
+      const cf *g = (const cf *)bursts + startv[j];
+      for (int r = 0; r < lenv[j]; r++) A[r * kTileStride + j] = cmul(g[r], iav[j]);
+    }
+    for (int lane = 0; lane < nv; lane++) {
+      const long long i = w0 + lane;
+      float *row = soft + i * soft_pitch;
+      for (int m = 0; m < soft_pitch; m++) row[m] = 0.0F;
+      if (!okv[lane]) continue;
+      std::vector<float> s(lenv[lane] + 4);
+      equalize_fast_lane<kTileStride>(grid.data(), T, View<kTileStride>{A + lane}, lenv[lane], BTS_SUB(toav[lane], offv[lane]),
+                                      wv[lane], fbv[lane], s.data());
+      for (int m = 0; m < lenv[lane] && m < soft_pitch; m++) row[m] = s[m];
     }
   }
 }

@@ -112,3 +112,34 @@ def make_rach_batch(modulate, n, seed=2, pitch=160, snr=(-5, 20), max_delay=63):
         bits[i] = b
         delays[i] = d
     return bursts, lens, bits, delays
+
+
+def make_edge_batch(o, n=70, seed=9):
+    """hand-made hard cases for the normal-burst path: flat input, pure noise, impulses in / at the edge of the
+    correlation window, clean bursts with zero / early / late timing, ragged count (not a multiple of 32).
+    `o` supplies modulate() and delay_vector() (the oracle)."""
+    rng = np.random.default_rng(seed)
+    bursts = np.zeros((n, 160), np.complex64)
+    lens = np.where(np.arange(n) % 4 == 0, 157, 156).astype(np.int32)
+    tsc = (np.arange(n) % 8).astype(np.uint8)
+    bursts[1] = 1e-3
+    bursts[2, :156] = (rng.standard_normal(156) + 1j * rng.standard_normal(156)) * 1e4
+    bursts[3, 60] = 5000
+    bursts[4, 91] = 5000 + 1j
+    for i, (t, d) in enumerate([(3, 0.0), (3, -2.5), (3, 9.25), (0, -7.0), (0, 7.5), (2, 12.0), (6, -11.3), (7, 3.0),
+                                (0, 5 / 512), (0, 6 / 512), (2, -4 + 3 / 512), (6, 1.999), (7, -0.001)]):
+        b = normal_burst_bits(rng, t)
+        k = 5 + i
+        tsc[k] = t
+        x = o.modulate(b, 8 + (k % 4 == 0)) * np.complex64(3000 * np.exp(1j * i))
+        bursts[k, :lens[k]] = o.delay_vector(x, d)
+    for i in range(18, n):
+        if i % 3 == 0:
+            b = normal_burst_bits(rng, tsc[i])
+            x = o.modulate(b, 8 + (i % 4 == 0)) * np.complex64(rng.uniform(30, 30000))
+            y = o.delay_vector(x, rng.uniform(-6, 6))
+            y = y + (rng.standard_normal(y.size) + 1j * rng.standard_normal(y.size)) * rng.uniform(0, 300)
+            bursts[i, :lens[i]] = y.astype(np.complex64)
+        else:
+            bursts[i, :lens[i]] = (rng.standard_normal(lens[i]) + 1j * rng.standard_normal(lens[i])) * rng.uniform(1, 3000)
+    return bursts, lens, tsc

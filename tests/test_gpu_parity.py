@@ -142,29 +142,20 @@ def test_normal_batch_config4_random(dsp, oracle_best):
 
 
 def test_normal_batch_edge_cases(dsp, oracle_best):
-    rng = np.random.default_rng(9)
-    n = 70                                          # ragged: not a multiple of 32
-    bursts = np.zeros((n, 160), np.complex64)
-    lens = np.where(np.arange(n) % 4 == 0, 157, 156).astype(np.int32)
-    tsc = (np.arange(n) % 8).astype(np.uint8)
-    bursts[1] = 1e-3                                # constant -> flat correlation
-    bursts[2, :156] = (rng.standard_normal(156) + 1j * rng.standard_normal(156)) * 1e4
-    bursts[3, 60] = 5000                            # a single impulse inside the correlation window
-    bursts[4, 91] = 5000 + 1j                       # impulse at the window edge
-    b = synth.normal_burst_bits(rng, 3)
-    bursts[5, :156] = oracle_best.modulate(b, 8) * 3000          # clean, no delay, no noise
-    bursts[6, :156] = oracle_best.delay_vector(oracle_best.modulate(b, 8) * 3000, -2.5)   # early
-    bursts[7, :156] = oracle_best.delay_vector(oracle_best.modulate(b, 8) * 3000, 9.25)   # late
-    for i in range(8, n):
-        bursts[i, :lens[i]] = (rng.standard_normal(lens[i]) + 1j * rng.standard_normal(lens[i])) * rng.uniform(1, 3000)
+    bursts, lens, tsc = synth.make_edge_batch(oracle_best)
+    n = len(lens)
     ref = oracle_best.rx_normal_batch(bursts, lens, tsc)
+    assert ref["flag"].sum() > 10
     r = dsp.demod_normal_host(bursts, lens, tsc)
     check_batch(r, ref, ("amp", "toa", "chan", "off", "w", "b", "soft"))
     one = dsp.demod_normal_host(bursts[5:6], lens[5:6], tsc[5:6])                  # batch of one
     same(one["soft"], ref["soft"][5:6], "batch of 1")
+    odd = dsp.demod_normal_host(bursts, lens, tsc, debug=False, soft_pitch=157)    # unaligned soft rows
+    same(odd["soft"], ref["soft"][:, :157], "soft pitch 157")
     gate = dsp.demod_normal_host(bursts, lens, tsc, gate_thr=500.0)
     eg = np.array([oracle_best.energy_detect(bursts[i, :lens[i]], 20, 500.0)[0] for i in range(n)])
     same(gate["flag"], ref["flag"] & eg, "energy gate")
+    same(gate["soft"], ref["soft"] * eg[:, None], "energy gate soft")
 
 
 def test_rach_batch(dsp, oracle_best):

@@ -59,7 +59,7 @@ def test_reference_test_flow_through_the_shim(tmp_path, oracle_best):
     soft, after = o.equalize(o.scale_vector(rx, s), toa - off, w, b)
     assert_same(f32("soft"), soft, "equalizeBurst"); assert_same(c64("after"), after, "burst after equalizeBurst")
     rok, ramp, rtoa = o.detect_rach(c64("rachrx"), 5.0)
-    rm = f32("rachmeta")
+    rm = f32("rachm")
     assert bool(rm[0]) == rok and np.complex64(complex(rm[1], rm[2])) == ramp and rm[3] == np.float32(rtoa)
     e = f32("energy")
     eo = o.energy_detect(rx, 20, 250.0)

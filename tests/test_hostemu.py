@@ -108,6 +108,14 @@ def test_demod_normal_kernel_logic_random(emu, oracle_port):
     assert (a["flag"] == (b["flag"] & gate)).all() and 0 < gate.sum() < gate.size
 
 
+def test_demod_normal_kernel_logic_edge_cases(emu, oracle_port):
+    bursts, lens, tsc = synth.make_edge_batch(oracle_port)
+    a, b = emu.rx_normal_batch(bursts, lens, tsc), oracle_port.rx_normal_batch(bursts, lens, tsc)
+    assert b["flag"].sum() > 10
+    for k in b:
+        assert_same(a[k], b[k], k)
+
+
 def test_rach_kernel_logic(emu, oracle_port):
     g = golden("rach_sps1.npz")
     for tiles in (True, False):
