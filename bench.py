@@ -57,6 +57,9 @@ class ClockSampler:
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 10:      # nvidia-smi needs a moment before its first sample
+                time.sleep(0.05)
         except OSError:
             self.proc = None
 
@@ -149,7 +152,7 @@ def workload_config(args, n):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--blocks", type=int, default=DEFAULT_BLOCKS, help="117-frame blocks per GPU per step")
@@ -211,6 +214,7 @@ def main():
         if evs:
             evs[2].record(stream)
 
+    sampler = ClockSampler(local) if rank == 0 else None     # runs from warm-up to the end of the e2e region
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
@@ -222,7 +226,6 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = dsp.launch_count
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
@@ -234,7 +237,6 @@ def main():
     launches = dsp.launch_count - l0
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop() if sampler else None
     ms_total = t_start.elapsed_time(t_end)
     ms_res = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
     ms_dem = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
@@ -274,6 +276,8 @@ def main():
         e2e = {"value": world * nb / float(dt.item()), "unit": "bursts/s", "ms_per_step": 1e3 * float(dt.item()),
                "h2d_bytes_per_step": int(raw.numel() * 4 + nb), "d2h_bytes_per_step": int(nb * (SOFT_PITCH * 4 + 16)),
                "matches_device_path": same, "api": "btsdsp_rx_stream_host (pinned host buffers)"}
+
+    clocks = sampler.stop() if sampler else None
 
     # ---- optional gather of SoftVectors over NCCL (outside the timed path, reported separately)
     gather = None

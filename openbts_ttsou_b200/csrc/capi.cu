@@ -31,14 +31,14 @@ struct btsdsp_ctx {
   cudaStream_t st = nullptr, st_in = nullptr, st_out = nullptr;
   std::string err;
   long long launches = 0;
-  DevBuf buf[12];               // grow-only device scratch, by role
+  DevBuf buf[16];               // grow-only device scratch, by role
   DevBuf pin[4];                // grow-only pinned staging
   std::vector<cudaEvent_t> events;
 };
 
 namespace {
 
-enum { B_A = 0, B_B, B_C, B_D, B_SCRATCH, B_RAW, B_RES, B_FLAG, B_AMP, B_TOA, B_SOFT, B_TSC };
+enum { B_A = 0, B_B, B_C, B_D, B_SCRATCH, B_RAW, B_RES, B_FLAG, B_AMP, B_TOA, B_SOFT, B_TSC, B_EQP };
 
 int fail(btsdsp_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess) {
   char msg[512];
@@ -575,9 +575,10 @@ int btsdsp_demod_normal_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long lon
   ARG(!soft || soft_pitch >= 148);
   DeviceGuard g(ctx->device);
   NormalOut o = {flag, (cf *)amp, toa, (cf *)chan, chan_off, (cf *)w, (cf *)b, soft, soft_pitch};
-  launch_demod_normal(ctx->T, make_src(bursts, pitch, lens, first, 1), tsc, n, detect_thr, gate_thr, snr_thr, o,
-                      (cudaStream_t)stream);
-  LAUNCHED("demod_normal", n > 0);
+  GROW(B_EQP, demod_scratch_bytes(n));
+  const int nl = launch_demod_normal(ctx->T, make_src(bursts, pitch, lens, first, 1), tsc, n, detect_thr, gate_thr,
+                                     snr_thr, o, dbuf<void>(ctx, B_EQP), (cudaStream_t)stream);
+  LAUNCHED("demod_normal", nl);
   return BTSDSP_OK;
 }
 
@@ -653,9 +654,10 @@ int btsdsp_rx_stream_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nchu
   cudaStream_t st = (cudaStream_t)stream;
   launch_resample_rx(ctx->T, (const cf *)raw, 0, nchunks, dbuf<cf>(ctx, B_RES), st);
   NormalOut o = {flag, (cf *)amp, toa, nullptr, nullptr, nullptr, nullptr, soft, soft_pitch};
-  launch_demod_normal(ctx->T, make_src((const btsdsp_cf32 *)dbuf<cf>(ctx, B_RES), 0, nullptr, 0, 1), tsc, nbursts,
-                      detect_thr, gate_thr, snr_thr, o, st);
-  LAUNCHED("rx_stream", 1 + (nbursts > 0));
+  GROW(B_EQP, demod_scratch_bytes(nbursts));
+  const int nl = launch_demod_normal(ctx->T, make_src((const btsdsp_cf32 *)dbuf<cf>(ctx, B_RES), 0, nullptr, 0, 1), tsc,
+                                     nbursts, detect_thr, gate_thr, snr_thr, o, dbuf<void>(ctx, B_EQP), st);
+  LAUNCHED("rx_stream", 1 + nl);
   return BTSDSP_OK;
 }
 
@@ -678,6 +680,7 @@ int btsdsp_rx_stream_host(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nch
   GROW(B_AMP, (size_t)(nbursts + 1) * sizeof(cf));
   GROW(B_TOA, (size_t)(nbursts + 1) * sizeof(float));
   if (soft) GROW(B_SOFT, (size_t)(nbursts + 1) * soft_pitch * sizeof(float));
+  GROW(B_EQP, demod_scratch_bytes(nbursts + 1));
   cf *dRaw = dbuf<cf>(ctx, B_RAW), *dRes = dbuf<cf>(ctx, B_RES);
   uint8_t *dTsc = dbuf<uint8_t>(ctx, B_TSC);
   int32_t *dFlag = dbuf<int32_t>(ctx, B_FLAG);
@@ -709,9 +712,9 @@ int btsdsp_rx_stream_host(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nch
     if (nb > 0) {
       NormalOut o = {dFlag + done_bursts, dAmp + done_bursts, dToa + done_bursts, nullptr, nullptr, nullptr, nullptr,
                      dSoft ? dSoft + done_bursts * soft_pitch : nullptr, soft_pitch};
-      launch_demod_normal(ctx->T, make_src((const btsdsp_cf32 *)dRes, 0, nullptr, done_bursts, 1), dTsc + done_bursts,
-                          nb, detect_thr, gate_thr, snr_thr, o, ctx->st);
-      nl = 2;
+      nl = 1 + launch_demod_normal(ctx->T, make_src((const btsdsp_cf32 *)dRes, 0, nullptr, done_bursts, 1),
+                                   dTsc + done_bursts, nb, detect_thr, gate_thr, snr_thr, o,
+                                   dbuf<unsigned char>(ctx, B_EQP) + demod_scratch_bytes(done_bursts), ctx->st);
     }
     LAUNCHED("rx_stream_host", nl);
     CK(cudaEventRecord(evK, ctx->st));

@@ -19,9 +19,15 @@ namespace btsdsp {
 
 constexpr int kGridPitch = 21;      // floats per sinc-grid row in the compact (shared-memory) copy
 
-BTS_HD void load_grid_row(const float *__restrict__ grid, int j, float s[21]) {
+// a sinc-grid table and its row pitch: the compact shared-memory copy (pitch 21) or DevTables::sinc_grid (pitch 24)
+struct Grid {
+  const float *p;
+  int pitch;
+};
+
+BTS_HD void load_grid_row(Grid grid, int j, float s[21]) {
 #pragma unroll
-  for (int t = 0; t < 21; t++) s[t] = grid[j * kGridPitch + t];
+  for (int t = 0; t < 21; t++) s[t] = grid.p[j * grid.pitch + t];
 }
 
 // taps of correlate(window, midamble) (:474-503): tap[k] = conj(seq[15-k])
@@ -73,7 +79,7 @@ BTS_HD cf interp21(const float s[21], View<S> c, int n, int I) {
 
 // peakDetect (:663-711) on the 1/512 grid; avgPwr is not needed by analyzeTrafficBurst
 template <int S>
-BTS_HD cf peak_detect_fast(const float *__restrict__ grid, View<S> c, int n, float *peakIndex) {
+BTS_HD cf peak_detect_fast(Grid grid, View<S> c, int n, float *peakIndex) {
   float maxVal = 0.0F;
   int imax = -1;
   for (int i = 0; i < n; i++) {
@@ -96,7 +102,7 @@ BTS_HD cf peak_detect_fast(const float *__restrict__ grid, View<S> c, int n, flo
 }
 
 // the 21 taps of delayVector's fractional filter (:583-588); on the grid they are a table row
-BTS_HD void load_delay_taps(const float *__restrict__ grid, const DevTables *__restrict__ T, float frac, float s[21]) {
+BTS_HD void load_delay_taps(Grid grid, const DevTables *__restrict__ T, float frac, float s[21]) {
   const float f512 = frac * (float)kSincGrid;
   const int j = (int)f512;
   if ((float)j == f512 && j >= 0 && j < kSincGrid) load_grid_row(grid, j, s);
@@ -110,7 +116,7 @@ BTS_HD void load_delay_taps(const float *__restrict__ grid, const DevTables *__r
 // search of analyzeTrafficBurst reads: out[n] = F[n - io] with F = the 21-tap filtered vector (or corr itself
 // when the fraction is <= 0.01), zero where n - io falls outside the vector.
 template <int S>
-BTS_HD void delayed12(const float *__restrict__ grid, const DevTables *__restrict__ T, View<S> c, int L, float delay,
+BTS_HD void delayed12(Grid grid, const DevTables *__restrict__ T, View<S> c, int L, float delay,
                       int smin, cf dl[12]) {
   const int io = (int)floorf(delay);
   const float frac = BTS_SUB(delay, (float)io);
@@ -144,7 +150,7 @@ BTS_HD void delayed12(const float *__restrict__ grid, const DevTables *__restric
 // analyzeTrafficBurst (:935-1037) at sps == 1 with requestChannel == true.  win = burst rows 56..91,
 // corr = 36 scratch rows.  Same outputs as analyze_traffic<S, true>.
 template <int S>
-BTS_HD bool analyze_fast(const float *__restrict__ grid, const DevTables *__restrict__ T, View<S> win, View<S> corr,
+BTS_HD bool analyze_fast(Grid grid, const DevTables *__restrict__ T, View<S> win, View<S> corr,
                          int tsc, float thr, cf *amplitude, float *TOA, cf chan[6], float *chanOff) {
   constexpr int L = 36;
   {
@@ -213,7 +219,7 @@ struct EqLane {
   float s[21];
   cf w[7], b[5], hist[5], Fw[10];
 
-  BTS_HD void init(const float *__restrict__ grid, const DevTables *__restrict__ T, View<S> burst, int n, float TOA,
+  BTS_HD void init(Grid grid, const DevTables *__restrict__ T, View<S> burst, int n, float TOA,
                    const cf *w_, const cf *b_) {
     a = burst;
     N = n;
@@ -231,11 +237,10 @@ struct EqLane {
     for (int k = 0; k < 7; k++) w[k] = w_[k];
 #pragma unroll
     for (int k = 0; k < 5; k++) { b[k] = b_[k]; hist[k] = mk(0.0F, 0.0F); }
-    // window for the first block: F[-io .. -io+5]
-    cf t4[4];
-    newF4<true>(-io - 2, t4);
-    Fw[0] = t4[2]; Fw[1] = t4[3];
-    newF4<true>(-io + 2, &Fw[2]);
+#pragma unroll
+    for (int i = 0; i < 10; i++) Fw[i] = mk(0.0F, 0.0F);
+    // the window is primed by running the pipeline from m0 = -12: compute_y(-8) and compute_y(-4) leave
+    // F[-io .. -io+5] in Fw[0..5]; their feed-forward outputs (m < 0) are discarded by feedback4
   }
 
   // F[x0..x0+3]; CHECKED = rows/indices may fall outside the burst
@@ -294,6 +299,7 @@ struct EqLane {
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       const int m = m0 + r;
+      if (m < 0) { soft[r] = 0.0F; continue; }                    // pipeline priming blocks
       cf v = y[r];
 #pragma unroll
       for (int k = 0; k < 5; k++)
@@ -308,35 +314,34 @@ struct EqLane {
     }
   }
 
-  // one pipeline step: feed-forward for the NEXT block (independent work) + feedback for the current one
+  // one pipeline step: feed-forward for the NEXT block (independent work) + feedback for the current one.
+  // The pipeline starts at m0 = kEqStart (three priming steps whose feedback is a no-op).
   template <bool CHECKED>
-  BTS_HD void step(const DevTables *__restrict__ T, int m0, bool have_next, cf ycur[4], float soft[4]) {
+  BTS_HD void step(const DevTables *__restrict__ T, int m0, cf ycur[4], float soft[4]) {
     cf ynext[4];
-    if (have_next) compute_y<CHECKED>(m0 + 4, ynext);
+    compute_y<CHECKED>(m0 + 4, ynext);
     feedback4(T, m0, ycur, soft);
-    if (have_next) {
 #pragma unroll
-      for (int r = 0; r < 4; r++) ycur[r] = ynext[r];
-    }
+    for (int r = 0; r < 4; r++) ycur[r] = ynext[r];
   }
 };
+constexpr int kEqStart = -12;
 
 // The whole per-lane equaliser on the host side of the emulation (and the reference loop for the kernel):
 // soft[m] for m < n.  The kernel drives the same steps but votes `interior` across the warp.
 template <int S>
-BTS_HD void equalize_fast_lane(const float *__restrict__ grid, const DevTables *__restrict__ T, View<S> burst, int n,
+BTS_HD void equalize_fast_lane(Grid grid, const DevTables *__restrict__ T, View<S> burst, int n,
                                float TOA, const cf *w, const cf *b, float *soft) {
   EqLane<S> eq;
   eq.init(grid, T, burst, n, TOA, w, b);
   cf ycur[4];
-  if (eq.interior(0)) eq.template compute_y<false>(0, ycur);
-  else eq.template compute_y<true>(0, ycur);
-  for (int m0 = 0; m0 < n; m0 += 4) {
+#pragma unroll
+  for (int r = 0; r < 4; r++) ycur[r] = mk(0.0F, 0.0F);
+  for (int m0 = kEqStart; m0 < n; m0 += 4) {
     float s4[4];
-    const bool have_next = m0 + 4 < n;
-    if (have_next && eq.interior(m0 + 4)) eq.template step<false>(T, m0, have_next, ycur, s4);
-    else eq.template step<true>(T, m0, have_next, ycur, s4);
-    for (int r = 0; r < 4; r++) if (m0 + r < n) soft[m0 + r] = s4[r];
+    if (eq.interior(m0 + 4)) eq.template step<false>(T, m0, ycur, s4);
+    else eq.template step<true>(T, m0, ycur, s4);
+    for (int r = 0; r < 4; r++) if (m0 + r >= 0 && m0 + r < n) soft[m0 + r] = s4[r];
   }
 }
 

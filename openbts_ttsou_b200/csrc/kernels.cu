@@ -228,137 +228,238 @@ void launch_modulate_impulse(const DevTables *T, const uint8_t *bits, int nbits,
 }
 
 // ------------------------------------------------------------------------------------------------
-// normal-burst receive, fused: energy gate -> analyzeTrafficBurst -> designDFE -> equalizeBurst
+// normal-burst receive: energy gate -> analyzeTrafficBurst -> designDFE -> equalizeBurst
 // (reference Transceiver.cpp:298-396 with estimateChannel == true for every burst); sps == 1.
-// One burst per lane, WARPS independent warps per CTA sharing one shared-memory copy of the sinc grid.
-// Shared memory per warp: ONE transposed tile of 160 rows (42 KB).  Phase 1 (detect, channel, DFE design)
-// stages only the 36-sample midamble window (rows 56..91; rows 0..19 too when the energy gate is on) and
-// keeps the correlation in rows 100..135; phase 2 re-stages the detected bursts in full, scaled by
-// 1/amplitude on the way in, and runs the streaming equaliser of demod_fast.cuh.
+// One burst per lane.  Two kernels so that each runs at the occupancy its working set allows:
+//   k_detect_design : stages only the 36-sample midamble window (+ the 20-sample energy-gate window), keeps the
+//                     correlation next to it (72 tile rows = 19 KB per warp, 8 warps per CTA share one
+//                     shared-memory copy of the sinc grid), and leaves {1/amp, TOA - offset, w[7], b[5]} per burst
+//                     in an EqParams record;
+//   k_equalize_fast : stages the detected bursts in full, scaled by 1/amp on the way in (one 160-row tile = 42 KB
+//                     per warp, 5 warps per SM), and runs the streaming equaliser of demod_fast.cuh.
+// Staging loads are issued in batches (36 / 20 independent loads per lane) before their shared-memory stores so a
+// warp has many requests in flight instead of one.
 // ------------------------------------------------------------------------------------------------
-constexpr int kCorrRows = 36;
-constexpr int kCorrBase = 100;
+struct __align__(16) EqParams {       // 28 floats = 112 B per burst
+  float ia_x, ia_y, toa_eq, ok;
+  cf w[7];
+  cf b[5];
+};
 constexpr size_t kGridBytes = (size_t)kSincGrid * kGridPitch * sizeof(float);
-constexpr size_t kTileBytes = (size_t)kBurstRows * kTileStride * sizeof(cf);
-template <int WARPS> constexpr size_t demod_smem() { return kGridBytes + WARPS * kTileBytes; }
-
-__device__ __forceinline__ void store_soft_row(float *row, int pitch, int m0, const float s4[4], int len) {
-  // m0 is a multiple of 4; vector path when the row is 16-byte aligned
-  if (((reinterpret_cast<uintptr_t>(row) | (uintptr_t)(pitch * 4)) & 15) == 0 && m0 + 3 < len && m0 + 3 < pitch) {
-    *reinterpret_cast<float4 *>(row + m0) = make_float4(s4[0], s4[1], s4[2], s4[3]);
-  } else {
-#pragma unroll
-    for (int r = 0; r < 4; r++) if (m0 + r < len && m0 + r < pitch) row[m0 + r] = s4[r];
-  }
-}
+constexpr int kDetRows = 72;          // rows 0..35: burst samples 56..91; rows 36..71: correlation (gate window first)
+constexpr size_t kDetTileBytes = (size_t)kDetRows * kTileStride * sizeof(cf);
+constexpr size_t kEqTileBytes = (size_t)kBurstRows * kTileStride * sizeof(cf);
+template <int WARPS> constexpr size_t detect_smem() { return kGridBytes + WARPS * kDetTileBytes; }
+template <int WARPS> constexpr size_t equalize_smem() { return WARPS * kEqTileBytes; }
 
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_demod_normal(const DevTables *__restrict__ T, BurstSrc src,
-                                                             const uint8_t *__restrict__ tsc, long long n,
-                                                             float detect_thr, float gate_thr, float snr_thr,
-                                                             NormalOut out) {
+__global__ void __launch_bounds__(WARPS * 32) k_detect_design(const DevTables *__restrict__ T, BurstSrc src,
+                                                              const uint8_t *__restrict__ tsc, long long n,
+                                                              float detect_thr, float gate_thr, float snr_thr,
+                                                              NormalOut out, EqParams *__restrict__ eqp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float *grid = reinterpret_cast<float *>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  cf *A = reinterpret_cast<cf *>(smem_raw + kGridBytes) + (size_t)warp * kBurstRows * kTileStride;
+  cf *A = reinterpret_cast<cf *>(smem_raw + kGridBytes) + (size_t)warp * kDetRows * kTileStride;
   for (int i = threadIdx.x; i < kSincGrid * kGridPitch; i += WARPS * 32) grid[i] = T->sinc_grid[i / kGridPitch][i % kGridPitch];
   __syncthreads();
   const long long w0 = ((long long)blockIdx.x * WARPS + warp) * 32;
   if (w0 >= n) return;
   const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
   const bool gated = gate_thr >= 0.0F;
+  const long long i = w0 + lane;
+  long long start = 0;
+  int len = 0;
+  if (lane < nv) burst_loc(src, i, &start, &len);
 
-  // ---- phase 1 staging: the midamble window (and the energy-gate window)
-  for (int j = 0; j < nv; j++) {
-    long long start; int len;
-    burst_loc(src, w0 + j, &start, &len);
-    const cf *g = src.base + start;
-    for (int i = lane; i < 36; i += 32) A[(56 + i) * kTileStride + j] = __ldg(g + 56 + i);
-    if (gated && lane < 20) A[lane * kTileStride + j] = __ldg(g + lane);
+  // ---- staging: element e = it*32 + lane of the warp's nv x 36 window samples (burst e/36, sample 56 + e%36)
+  {
+    cf v[36];
+#pragma unroll
+    for (int it = 0; it < 36; it++) {
+      const int e = it * 32 + lane, j = e / 36, r = e - j * 36;
+      const long long sj = __shfl_sync(0xffffffffu, start, j);
+      v[it] = (j < nv) ? __ldg(src.base + sj + 56 + r) : mk(0.0F, 0.0F);
+    }
+#pragma unroll
+    for (int it = 0; it < 36; it++) {
+      const int e = it * 32 + lane, j = e / 36, r = e - j * 36;
+      A[r * kTileStride + j] = v[it];
+    }
+    if (gated) {
+#pragma unroll
+      for (int it = 0; it < 20; it++) {
+        const int e = it * 32 + lane, j = e / 20, r = e - j * 20;
+        const long long sj = __shfl_sync(0xffffffffu, start, j);
+        v[it] = (j < nv) ? __ldg(src.base + sj + r) : mk(0.0F, 0.0F);
+      }
+#pragma unroll
+      for (int it = 0; it < 20; it++) {
+        const int e = it * 32 + lane, j = e / 20, r = e - j * 20;
+        A[(36 + r) * kTileStride + j] = v[it];
+      }
+    }
   }
   __syncwarp();
+  if (lane >= nv) return;
 
-  const long long i = w0 + lane;
   const View<kTileStride> a{A + lane};
+  const Grid g{grid, kGridPitch};
   bool ok = false;
-  int len = 0;
-  long long start = 0;
   cf amp = mk(0.0F, 0.0F), ia = mk(0.0F, 0.0F), chan[6], w[7], fb[5];
   float toa = 0.0F, off = 0.0F;
+  bool pass = true;
+  if (gated) pass = energy_detect<kTileStride>(a.at(36), len, 20, gate_thr, nullptr);           // Transceiver.cpp:298
+  if (pass) ok = analyze_fast<kTileStride>(g, T, a, a.at(36), tsc[i], detect_thr, &amp, &toa, chan, &off);
+  if (ok) {
+    // Transceiver.cpp:340  SNRestimate = amplitude.norm2()/(thr*thr + 1.0)  (double division)
+    const float SNR = (float)((double)cnorm2(amp) / ((double)BTS_MUL(snr_thr, snr_thr) + 1.0));
+    ia = cdiv(mk(1.0F, 0.0F), amp);
+#pragma unroll
+    for (int j = 0; j < 6; j++) chan[j] = cmul(chan[j], ia);                                    // :346
+    design_dfe<7, 5>(chan, 5, SNR, 7, w, fb);                                                   // :347
+  } else {
+#pragma unroll
+    for (int j = 0; j < 7; j++) w[j] = mk(0.0F, 0.0F);
+#pragma unroll
+    for (int j = 0; j < 5; j++) fb[j] = mk(0.0F, 0.0F);
+  }
+  if (out.flag) out.flag[i] = ok ? 1 : 0;
+  if (out.amp) out.amp[i] = amp;
+  if (out.toa) out.toa[i] = toa;
+  if (out.off) out.off[i] = ok ? off : 0.0F;
+  if (out.chan) for (int j = 0; j < 6; j++) out.chan[i * 6 + j] = ok ? chan[j] : mk(0.0F, 0.0F);
+  if (out.w) for (int j = 0; j < 7; j++) out.w[i * 7 + j] = w[j];
+  if (out.b) for (int j = 0; j < 5; j++) out.b[i * 5 + j] = fb[j];
+  if (eqp) {
+    float4 *q = reinterpret_cast<float4 *>(eqp + i);
+    q[0] = make_float4(ia.x, ia.y, BTS_SUB(toa, off), ok ? 1.0F : 0.0F);                        // TOA - chanRespOffset :393
+    q[1] = make_float4(w[0].x, w[0].y, w[1].x, w[1].y);
+    q[2] = make_float4(w[2].x, w[2].y, w[3].x, w[3].y);
+    q[3] = make_float4(w[4].x, w[4].y, w[5].x, w[5].y);
+    q[4] = make_float4(w[6].x, w[6].y, fb[0].x, fb[0].y);
+    q[5] = make_float4(fb[1].x, fb[1].y, fb[2].x, fb[2].y);
+    q[6] = make_float4(fb[3].x, fb[3].y, fb[4].x, fb[4].y);
+  }
+}
+
+__device__ __forceinline__ void store_soft4(float *row, bool vec, int pitch, int m0, const float s4[4], int len) {
+  if (vec && m0 >= 0 && m0 + 3 < len && m0 + 3 < pitch) {
+    *reinterpret_cast<float4 *>(row + m0) = make_float4(s4[0], s4[1], s4[2], s4[3]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; r++) if (m0 + r >= 0 && m0 + r < len && m0 + r < pitch) row[m0 + r] = s4[r];
+  }
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_equalize_fast(const DevTables *__restrict__ T, BurstSrc src, long long n,
+                                                              const EqParams *__restrict__ eqp, float *__restrict__ soft,
+                                                              int soft_pitch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  cf *A = reinterpret_cast<cf *>(smem_raw) + (size_t)warp * kBurstRows * kTileStride;
+  const long long w0 = ((long long)blockIdx.x * WARPS + warp) * 32;
+  if (w0 >= n) return;
+  const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
+  const long long i = w0 + lane;
+  long long start = 0;
+  int len = 0;
+  bool ok = false;
+  cf ia = mk(0.0F, 0.0F), w[7], fb[5];
+  float toa_eq = 0.0F;
   if (lane < nv) {
     burst_loc(src, i, &start, &len);
     if (len > kBurstRows - 3) len = kBurstRows - 3;
-    bool pass = true;
-    if (gated) pass = energy_detect<kTileStride>(a, len, 20, gate_thr, nullptr);                 // Transceiver.cpp:298
-    if (pass) ok = analyze_fast<kTileStride>(grid, T, a.at(56), a.at(kCorrBase), tsc[i], detect_thr, &amp, &toa, chan, &off);
+    const float4 *q = reinterpret_cast<const float4 *>(eqp + i);
+    const float4 q0 = __ldg(q);
+    ok = q0.w != 0.0F;
     if (ok) {
-      // Transceiver.cpp:340  SNRestimate = amplitude.norm2()/(thr*thr + 1.0)  (double division)
-      const float SNR = (float)((double)cnorm2(amp) / ((double)BTS_MUL(snr_thr, snr_thr) + 1.0));
-      ia = cdiv(mk(1.0F, 0.0F), amp);
-#pragma unroll
-      for (int j = 0; j < 6; j++) chan[j] = cmul(chan[j], ia);                                  // :346
-      design_dfe<7, 5>(chan, 5, SNR, 7, w, fb);                                                 // :347
+      const float4 q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4), q5 = __ldg(q + 5), q6 = __ldg(q + 6);
+      ia = mk(q0.x, q0.y); toa_eq = q0.z;
+      w[0] = mk(q1.x, q1.y); w[1] = mk(q1.z, q1.w); w[2] = mk(q2.x, q2.y); w[3] = mk(q2.z, q2.w);
+      w[4] = mk(q3.x, q3.y); w[5] = mk(q3.z, q3.w); w[6] = mk(q4.x, q4.y);
+      fb[0] = mk(q4.z, q4.w); fb[1] = mk(q5.x, q5.y); fb[2] = mk(q5.z, q5.w); fb[3] = mk(q6.x, q6.y); fb[4] = mk(q6.z, q6.w);
     }
-    if (out.flag) out.flag[i] = ok ? 1 : 0;
-    if (out.amp) out.amp[i] = amp;
-    if (out.toa) out.toa[i] = toa;
-    if (out.off) out.off[i] = ok ? off : 0.0F;
-    if (out.chan) for (int j = 0; j < 6; j++) out.chan[i * 6 + j] = ok ? chan[j] : mk(0.0F, 0.0F);
-    if (out.w) for (int j = 0; j < 7; j++) out.w[i * 7 + j] = ok ? w[j] : mk(0.0F, 0.0F);
-    if (out.b) for (int j = 0; j < 5; j++) out.b[i * 5 + j] = ok ? fb[j] : mk(0.0F, 0.0F);
   }
-  if (!out.soft) return;
-
-  // ---- phase 2 staging: detected bursts in full, scaled by 1/amplitude (scaleVector, Transceiver.cpp:391)
-  __syncwarp();
   const unsigned okmask = __ballot_sync(0xffffffffu, ok);
-  for (unsigned rem = okmask; rem; rem &= rem - 1) {
-    const int j = __ffs(rem) - 1;
-    const cf iaj = mk(__shfl_sync(0xffffffffu, ia.x, j), __shfl_sync(0xffffffffu, ia.y, j));
-    const long long sj = __shfl_sync(0xffffffffu, start, j);
-    const int lj = __shfl_sync(0xffffffffu, len, j);
-    const cf *g = src.base + sj;
-    for (int r = lane; r < lj; r += 32) A[r * kTileStride + j] = cmul(__ldg(g + r), iaj);
+
+  // ---- staging: detected bursts in full, scaled by 1/amplitude (scaleVector, Transceiver.cpp:391);
+  //      four bursts (20 loads per lane) in flight at a time
+  for (unsigned rem = okmask; rem;) {
+    int js[4]; cf iaj[4]; long long sj[4]; int lj[4];
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      js[b] = rem ? __ffs(rem) - 1 : -1;
+      if (rem) rem &= rem - 1;
+      const int jj = js[b] < 0 ? 0 : js[b];
+      iaj[b] = mk(__shfl_sync(0xffffffffu, ia.x, jj), __shfl_sync(0xffffffffu, ia.y, jj));
+      sj[b] = __shfl_sync(0xffffffffu, start, jj);
+      lj[b] = js[b] < 0 ? 0 : __shfl_sync(0xffffffffu, len, jj);
+    }
+    cf v[4][5];
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+#pragma unroll
+      for (int k = 0; k < 5; k++) {
+        const int r = lane + 32 * k;
+        v[b][k] = (r < lj[b]) ? __ldg(src.base + sj[b] + r) : mk(0.0F, 0.0F);
+      }
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+#pragma unroll
+      for (int k = 0; k < 5; k++) {
+        const int r = lane + 32 * k;
+        if (r < lj[b]) A[r * kTileStride + js[b]] = cmul(v[b][k], iaj[b]);
+      }
   }
   __syncwarp();
+  if (lane >= nv) return;
 
-  float *row = out.soft + i * (long long)out.soft_pitch;
+  float *row = soft + i * (long long)soft_pitch;
+  const bool vec = ((reinterpret_cast<uintptr_t>(row) | (uintptr_t)(soft_pitch * 4)) & 15) == 0;
   if (ok) {
     EqLane<kTileStride> eq;
-    eq.init(grid, T, a, len, BTS_SUB(toa, off), w, fb);                                         // :392-396
+    eq.init(Grid{&T->sinc_grid[0][0], 24}, T, View<kTileStride>{A + lane}, len, toa_eq, w, fb);  // :392-396
     const int nmax = __reduce_max_sync(okmask, len);
     cf ycur[4];
-    if (__all_sync(okmask, eq.interior(0))) eq.template compute_y<false>(0, ycur);
-    else eq.template compute_y<true>(0, ycur);
-    for (int m0 = 0; m0 < nmax; m0 += 4) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) ycur[r] = mk(0.0F, 0.0F);
+    for (int m0 = kEqStart; m0 < nmax; m0 += 4) {
       float s4[4];
-      const bool have_next = m0 + 4 < nmax;
-      if (__all_sync(okmask, have_next && eq.interior(m0 + 4))) eq.template step<false>(T, m0, have_next, ycur, s4);
-      else eq.template step<true>(T, m0, have_next, ycur, s4);
-      store_soft_row(row, out.soft_pitch, m0, s4, len);
+      if (__all_sync(okmask, eq.interior(m0 + 4))) eq.template step<false>(T, m0, ycur, s4);
+      else eq.template step<true>(T, m0, ycur, s4);
+      store_soft4(row, vec, soft_pitch, m0, s4, len);
     }
-    for (int m = len; m < out.soft_pitch; m++) row[m] = 0.0F;
-  } else if (lane < nv) {
-    if (((reinterpret_cast<uintptr_t>(row) | (uintptr_t)(out.soft_pitch * 4)) & 15) == 0) {
-      for (int m = 0; m < out.soft_pitch; m += 4) *reinterpret_cast<float4 *>(row + m) = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
-    } else {
-      for (int m = 0; m < out.soft_pitch; m++) row[m] = 0.0F;
-    }
-  }
-}
-int launch_demod_normal(const DevTables *T, BurstSrc src, const uint8_t *tsc, long long n, float detect_thr,
-                        float gate_thr, float snr_thr, NormalOut out, cudaStream_t st) {
-  if (n <= 0) return 0;
-  const long long nwarps = (n + 31) / 32;
-  if (nwarps >= 148 * 4) {
-    k_demod_normal<4><<<(unsigned)((nwarps + 3) / 4), 128, demod_smem<4>(), st>>>(T, src, tsc, n, detect_thr, gate_thr,
-                                                                                snr_thr, out);
+    for (int m = len; m < soft_pitch; m++) row[m] = 0.0F;
+  } else if (vec) {
+    for (int m = 0; m < soft_pitch; m += 4) *reinterpret_cast<float4 *>(row + m) = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
   } else {
-    k_demod_normal<1><<<(unsigned)nwarps, 32, demod_smem<1>(), st>>>(T, src, tsc, n, detect_thr, gate_thr, snr_thr, out);
+    for (int m = 0; m < soft_pitch; m++) row[m] = 0.0F;
   }
-  return 1;
 }
 
+size_t demod_scratch_bytes(long long n) { return (size_t)n * sizeof(EqParams); }
+
+int launch_demod_normal(const DevTables *T, BurstSrc src, const uint8_t *tsc, long long n, float detect_thr,
+                        float gate_thr, float snr_thr, NormalOut out, void *scratch, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const long long nwarps = (n + 31) / 32;
+  EqParams *eqp = out.soft ? reinterpret_cast<EqParams *>(scratch) : nullptr;
+  if (nwarps >= 148 * 8)
+    k_detect_design<8><<<(unsigned)((nwarps + 7) / 8), 256, detect_smem<8>(), st>>>(T, src, tsc, n, detect_thr, gate_thr,
+                                                                                 snr_thr, out, eqp);
+  else
+    k_detect_design<1><<<(unsigned)nwarps, 32, detect_smem<1>(), st>>>(T, src, tsc, n, detect_thr, gate_thr, snr_thr, out, eqp);
+  if (!out.soft) return 1;
+  if (nwarps >= 148 * 5)
+    k_equalize_fast<5><<<(unsigned)((nwarps + 4) / 5), 160, equalize_smem<5>(), st>>>(T, src, n, eqp, out.soft, out.soft_pitch);
+  else
+    k_equalize_fast<1><<<(unsigned)nwarps, 32, equalize_smem<1>(), st>>>(T, src, n, eqp, out.soft, out.soft_pitch);
+  return 2;
+}
+
+constexpr int kCorrRowsA = 36;
 // ------------------------------------------------------------------------------------------------
 // analyzeTrafficBurst alone, batched.  SM = true: sps == 1, shared-memory tiles.  SM = false: any
 // sps, one thread per burst over global scratch (the functional path for sps = 4).
@@ -380,7 +481,7 @@ __global__ void __launch_bounds__(32) k_analyze(const DevTables *__restrict__ T,
   float toa = 0.0F, off = 0.0F;
   bool ok;
   if (SM) {
-    cf *B = tile + kBurstRows * kTileStride, *C = B + kCorrRows * kTileStride;
+    cf *B = tile + kBurstRows * kTileStride, *C = B + kCorrRowsA * kTileStride;
     ok = analyze_traffic<kTileStride, true>(T, View<kTileStride>{tile + lane}, tsc[i], detect_thr, 1,
                                             View<kTileStride>{B + lane}, View<kTileStride>{C + lane}, &amp, &toa,
                                             request != 0, chan, &off);
@@ -396,6 +497,7 @@ __global__ void __launch_bounds__(32) k_analyze(const DevTables *__restrict__ T,
   if (out.off) out.off[i] = have ? off : 0.0F;
   if (out.chan) for (int j = 0; j < 6 * sps; j++) out.chan[i * 6 * sps + j] = have ? chan[j] : mk(0.0F, 0.0F);
 }
+constexpr int kCorrRows = 36;
 constexpr size_t kAnalyzeSmem = (size_t)(kBurstRows + 2 * kCorrRows) * kTileStride * sizeof(cf);
 int launch_analyze(const DevTables *T, BurstSrc src, const uint8_t *tsc, long long n, float detect_thr, int request,
                    NormalOut out, cf *scratch, int force_generic, cudaStream_t st) {
@@ -563,9 +665,13 @@ void launch_equalize_generic(const DevTables *T, cf *burst, int n, float toa, co
 
 int configure_kernels() {
   cudaError_t e;
-  e = cudaFuncSetAttribute(k_demod_normal<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)demod_smem<4>());
+  e = cudaFuncSetAttribute(k_detect_design<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<8>());
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(k_demod_normal<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)demod_smem<1>());
+  e = cudaFuncSetAttribute(k_detect_design<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<1>());
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_equalize_fast<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)equalize_smem<5>());
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_equalize_fast<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)equalize_smem<1>());
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_analyze<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAnalyzeSmem);
   if (e != cudaSuccess) return (int)e;

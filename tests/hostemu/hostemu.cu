@@ -131,38 +131,40 @@ int emu_check_sinc_grid(void) {
   return bad;
 }
 
-// k_demod_normal (demod_fast.cuh), warp by warp, lane by lane: one tile per warp, phase 1 on the midamble
-// window with the correlation in rows 100..135, phase 2 on the re-staged, 1/amp-scaled burst.
+// k_detect_design + k_equalize_fast (kernels.cu / demod_fast.cuh), warp by warp, lane by lane:
+// phase 1 on a 72-row tile (rows 0..35 = burst samples 56..91, rows 36..71 = correlation, gate window staged
+// into rows 36..55 first), phase 2 on a 160-row tile holding the detected bursts scaled by 1/amp.
 void emu_demod_normal(const float *bursts, long long pitch, const int *lens, long long first, const uint8_t *tsc,
                       long long n, float detect_thr, float gate_thr, float snr_thr, int *flag, float *amp, float *toa,
                       float *soft, int soft_pitch, float *chan_o, float *off_o, float *w_o, float *b_o) {
-  std::vector<float> grid(kSincGrid * kGridPitch);
-  for (int i = 0; i < kSincGrid * kGridPitch; i++) grid[i] = T->sinc_grid[i / kGridPitch][i % kGridPitch];
-  std::vector<cf> tile(kBurstRows * kTileStride);
-  cf *A = tile.data();
+  std::vector<float> gridv(kSincGrid * kGridPitch);
+  for (int i = 0; i < kSincGrid * kGridPitch; i++) gridv[i] = T->sinc_grid[i / kGridPitch][i % kGridPitch];
+  const Grid gsm{gridv.data(), kGridPitch}, ggl{&T->sinc_grid[0][0], 24};
+  std::vector<cf> tileA(72 * kTileStride), tileB(kBurstRows * kTileStride);
+  cf *A = tileA.data(), *B = tileB.data();
   const bool gated = gate_thr >= 0.0F;
   for (long long w0 = 0; w0 < n; w0 += 32) {
     const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
-    for (size_t k = 0; k < tile.size(); k++) A[k] = mk(1e30F, -1e30F);       // poison: catch reads of unstaged rows
+    for (size_t k = 0; k < tileA.size(); k++) A[k] = mk(1e30F, -1e30F);       // poison: catch reads of unstaged rows
+    for (size_t k = 0; k < tileB.size(); k++) B[k] = mk(1e30F, -1e30F);
     for (int j = 0; j < nv; j++) {
       long long start; int len;
       burst_loc_h((const cf *)bursts, pitch, lens, first, 1, w0 + j, &start, &len);
       const cf *g = (const cf *)bursts + start;
-      for (int i = 0; i < 36; i++) A[(56 + i) * kTileStride + j] = g[56 + i];
-      if (gated) for (int i = 0; i < 20; i++) A[i * kTileStride + j] = g[i];
+      for (int i = 0; i < 36; i++) A[i * kTileStride + j] = g[56 + i];
+      if (gated) for (int i = 0; i < 20; i++) A[(36 + i) * kTileStride + j] = g[i];
     }
-    bool okv[32]; int lenv[32]; long long startv[32]; cf iav[32], wv[32][7], fbv[32][5]; float toav[32], offv[32];
+    bool okv[32]; int lenv[32]; long long startv[32]; cf iav[32], wv[32][7], fbv[32][5]; float teq[32];
     for (int lane = 0; lane < nv; lane++) {
       const long long i = w0 + lane;
       long long start; int len;
       burst_loc_h((const cf *)bursts, pitch, lens, first, 1, i, &start, &len);
-      if (len > kBurstRows - 3) len = kBurstRows - 3;
       const View<kTileStride> a{A + lane};
       cf ampv = mk(0.0F, 0.0F), ia = mk(0.0F, 0.0F), chan[6], w[7], fb[5];
       float tv = 0.0F, off = 0.0F;
       bool pass = true, ok = false;
-      if (gated) pass = energy_detect<kTileStride>(a, len, 20, gate_thr, nullptr);
-      if (pass) ok = analyze_fast<kTileStride>(grid.data(), T, a.at(56), a.at(100), tsc[i], detect_thr, &ampv, &tv, chan, &off);
+      if (gated) pass = energy_detect<kTileStride>(a.at(36), len, 20, gate_thr, nullptr);
+      if (pass) ok = analyze_fast<kTileStride>(gsm, T, a, a.at(36), tsc[i], detect_thr, &ampv, &tv, chan, &off);
       if (ok) {
         const float SNR = (float)((double)cnorm2(ampv) / ((double)BTS_MUL(snr_thr, snr_thr) + 1.0));
         ia = cdiv(mk(1.0F, 0.0F), ampv);
@@ -174,14 +176,15 @@ void emu_demod_normal(const float *bursts, long long pitch, const int *lens, lon
       for (int j = 0; j < 6 && chan_o; j++) ((cf *)chan_o)[i * 6 + j] = ok ? chan[j] : mk(0.0F, 0.0F);
       for (int j = 0; j < 7 && w_o; j++) ((cf *)w_o)[i * 7 + j] = ok ? w[j] : mk(0.0F, 0.0F);
       for (int j = 0; j < 5 && b_o; j++) ((cf *)b_o)[i * 5 + j] = ok ? fb[j] : mk(0.0F, 0.0F);
-      okv[lane] = ok; lenv[lane] = len; startv[lane] = start; iav[lane] = ia; toav[lane] = tv; offv[lane] = off;
+      if (len > kBurstRows - 3) len = kBurstRows - 3;
+      okv[lane] = ok; lenv[lane] = len; startv[lane] = start; iav[lane] = ia; teq[lane] = BTS_SUB(tv, off);
       for (int j = 0; j < 7; j++) wv[lane][j] = w[j];
       for (int j = 0; j < 5; j++) fbv[lane][j] = fb[j];
     }
     for (int j = 0; j < nv; j++) {
       if (!okv[j]) continue;
       const cf *g = (const cf *)bursts + startv[j];
-      for (int r = 0; r < lenv[j]; r++) A[r * kTileStride + j] = cmul(g[r], iav[j]);
+      for (int r = 0; r < lenv[j]; r++) B[r * kTileStride + j] = cmul(g[r], iav[j]);
     }
     for (int lane = 0; lane < nv; lane++) {
       const long long i = w0 + lane;
@@ -189,8 +192,7 @@ void emu_demod_normal(const float *bursts, long long pitch, const int *lens, lon
       for (int m = 0; m < soft_pitch; m++) row[m] = 0.0F;
       if (!okv[lane]) continue;
       std::vector<float> s(lenv[lane] + 4);
-      equalize_fast_lane<kTileStride>(grid.data(), T, View<kTileStride>{A + lane}, lenv[lane], BTS_SUB(toav[lane], offv[lane]),
-                                      wv[lane], fbv[lane], s.data());
+      equalize_fast_lane<kTileStride>(ggl, T, View<kTileStride>{B + lane}, lenv[lane], teq[lane], wv[lane], fbv[lane], s.data());
       for (int m = 0; m < lenv[lane] && m < soft_pitch; m++) row[m] = s[m];
     }
   }
