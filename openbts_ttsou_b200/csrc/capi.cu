@@ -154,6 +154,8 @@ int build_tables(btsdsp_ctx *ctx) {
     CK(cudaMemcpy(&ctx->T->rach_gain, &gain, sizeof(cf), cudaMemcpyHostToDevice));
   }
   CK(cudaMemcpy(h, ctx->T, sizeof(DevTables), cudaMemcpyDeviceToHost));
+  upload_resampler_taps(h);
+  CK(cudaGetLastError());
   return BTSDSP_OK;
 }
 
@@ -225,6 +227,7 @@ int btsdsp_create(btsdsp_ctx **out, int device, int sps) {
     CK(cudaMalloc(&ctx->T, sizeof(DevTables)));
     CK(cudaMallocHost(&ctx->hT, sizeof(DevTables)));
     int ce = configure_kernels();
+    if (!ce) ce = configure_resamplers();
     if (ce) return fail(ctx, BTSDSP_ECUDA, "cudaFuncSetAttribute", (cudaError_t)ce);
     return build_tables(ctx);
   };

@@ -33,8 +33,10 @@ struct NormalOut {      // per burst; null pointers are skipped
 constexpr int kTileStride = 33;      // complex samples between rows of a transposed tile (32 lanes + 1 pad)
 constexpr int kBurstRows = 160;      // >= 157
 
-// -- per-device kernel attributes (dynamic shared memory sizes); call once per device
+// -- per-device kernel attributes (dynamic shared memory sizes) and constant-memory tables; call once per device
 int configure_kernels();
+int configure_resamplers();
+void upload_resampler_taps(const DevTables *hostT);
 
 // -- table construction (init only)
 void launch_init_tables(DevTables *T, cudaStream_t st);

@@ -46,10 +46,106 @@ __global__ void __launch_bounds__(256) k_resample_rx(const DevTables *__restrict
       out[c * kRxOut + m] = resample_at<kRxP, kRxQ, kRxTaps, kRxPoly, kRxP + 1>(x, kRxIn, &hp[0][0], kRxDrop, m);
   }
 }
+// ------------------------------------------------------------------------------------------------
+// RX resampler, tuned kernel.
+//
+// 585 = 9 x 65 outputs and 864 = 9 x 96 inputs per chunk: the chunked reference loop is periodic with period
+// (65 outputs, 96 inputs).  For global period G (= 9*chunk + q) and phase r = 0..64:
+//     output 65 G + r  =  sum_{k} raw[96 G - 192 + ix_r - k] * h[br_r + 65 k],   ix_r = (96 (r+135)) / 65,
+//                                                                               br_r = (96 (r+135)) % 65,
+// with two chunk effects kept exactly: raw indices before the stream start read as zero (no history), and in
+// the last period of every chunk (q == 8) phases r >= 60 lose their first ix_r - 287 taps (the reference cannot
+// see samples of the next chunk; sigProcLib.cpp:1183-1186).
+//
+// Mapping: one lane = one period, one warp = 32 consecutive periods, ALL 65 phases per lane.  Because the phase
+// is the same across a warp, every tap is a warp-uniform constant: the taps live in __constant__ memory and are
+// read as immediate c[bank][offset] operands of the multiplies (no tap loads at all), and the whole 65-phase
+// body is unrolled into straight-line code with compile-time sample offsets.  Phases are processed in groups of
+// five adjacent outputs whose input windows overlap (15 + ~6 samples), so a lane loads ~22 samples per five
+// outputs as aligned 16-byte pairs instead of 75.
+// Shared memory per warp: the 32-period input tile, stored in rows of 96 samples padded to 98 (lane stride
+// 98 samples = 49 x 16 B, odd in 16-byte units -> conflict-free LDS.128), and a 32 x 65 output tile (lane
+// stride 65, odd -> conflict-free) that is written back as one contiguous, fully coalesced 16.6 KB block.
+// ------------------------------------------------------------------------------------------------
+__constant__ float c_rx_poly[kRxP * 16];          // [r][k] = lpf_rx[br_r + 65 k], zero past the end
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, bool valid) {   // zero-fills when !valid
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+constexpr size_t kRxV2Smem = (size_t)(kRxTileIn + kRxTileOut) * sizeof(cf);
+
+__global__ void __launch_bounds__(32) k_resample_rx_v2(const cf *__restrict__ in, int has_history, long long nperiods,
+                                                       long long nsamples, cf *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf *xt = reinterpret_cast<cf *>(smem_raw);
+  cf *ot = xt + kRxTileIn;
+  const int lane = threadIdx.x;
+  for (long long tile = blockIdx.x; tile * 32 < nperiods; tile += gridDim.x) {
+    const long long G0 = tile * 32;
+    const long long raw0 = 96 * G0 - 96;                               // tile origin: sample (G, r, k) sits at 96*l + ix_r - k - 96
+    // ---- load 34 rows x 96 samples as 16-byte cp.async copies (global -> shared, no registers, all 51 per lane
+    //      in flight at once); samples outside [lo, nsamples) are zero-filled by the copy's src-size operand
+    const long long lo = has_history ? -192 : 0;
+    __syncwarp();
+    for (int i4 = lane; i4 < kRxTileRows * 48; i4 += 32) {
+      const int row = i4 / 48, c4 = i4 - row * 48;
+      const long long s = raw0 + (long long)row * 96 + 2 * c4;
+      cf *dst = xt + row * kRxRowPitch + 2 * c4;
+      if (s >= lo && s + 1 < nsamples) cp_async16(dst, in + s);
+      else {
+        cp_async8(dst, in + (s >= lo && s < nsamples ? s : 0), s >= lo && s < nsamples);
+        cp_async8(dst + 1, in + (s + 1 >= lo && s + 1 < nsamples ? s + 1 : 0), s + 1 >= lo && s + 1 < nsamples);
+      }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    // ---- 65 phases for this lane's period
+    const long long G = G0 + lane;
+    const bool q8 = (G % 9) == 8;
+    const cf *xl = xt + lane * kRxRowPitch;
+    cf *ol = ot + lane * kRxP;
+    rx_period(c_rx_poly, xl, ol, q8);
+    __syncwarp();
+    // ---- write the 32 x 65 outputs back: contiguous in both shared and global memory
+    const long long nvalid = (nperiods - G0 < 32 ? nperiods - G0 : 32) * kRxP;
+    cf *og = out + G0 * kRxP;
+    for (int i4 = lane; i4 < kRxTileOut / 2; i4 += 32) {
+      if (2 * i4 + 1 < nvalid) *reinterpret_cast<float4 *>(og + 2 * i4) = *reinterpret_cast<const float4 *>(ot + 2 * i4);
+      else if (2 * i4 < nvalid) og[2 * i4] = ot[2 * i4];
+    }
+  }
+}
+
+void upload_resampler_taps(const DevTables *hostT) {
+  float h[kRxP * 16];
+  rx_fill_taps(hostT, h);
+  cudaMemcpyToSymbol(c_rx_poly, h, sizeof h);
+}
+
 void launch_resample_rx(const DevTables *T, const cf *in, int has_history, long long nchunks, cf *out, cudaStream_t st) {
   if (nchunks <= 0) return;
-  const unsigned grid = (unsigned)(nchunks < 148 * 32 ? nchunks : 148 * 32);
-  k_resample_rx<<<grid, 256, 0, st>>>(T, in, has_history, nchunks, out);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (aligned) {
+    const long long nperiods = nchunks * 9, ntiles = (nperiods + 31) / 32;
+    const unsigned grid = (unsigned)(ntiles < 148 * 5 * 8 ? ntiles : 148 * 5 * 8);
+    k_resample_rx_v2<<<grid, 32, kRxV2Smem, st>>>(in, has_history, nperiods, nchunks * 864, out);
+  } else {
+    const unsigned grid = (unsigned)(nchunks < 148 * 32 ? nchunks : 148 * 32);
+    k_resample_rx<<<grid, 256, 0, st>>>(T, in, has_history, nchunks, out);
+  }
+}
+int configure_resamplers() {
+  return (int)cudaFuncSetAttribute(k_resample_rx_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRxV2Smem);
 }
 
 // TX: also applies the x13500 scaling and int16 truncation (tx_quantise).

@@ -443,4 +443,64 @@ BTS_HD short2 tx_quantise(cf sum) {
   return o;
 }
 
+// ---- tuned RX resampler (see resample.cu for the derivation and the kernel) --------------------------------------
+constexpr int kRxDropC = 130;   // INHISTORY outputs dropped per chunk (radioInterface.cpp:249-252)
+__host__ __device__ constexpr int rx_ix(int r) { return (kRxQ * (r + kRxDropC + 5)) / kRxP; }
+__host__ __device__ constexpr int rx_br(int r) { return (kRxQ * (r + kRxDropC + 5)) % kRxP; }
+__host__ __device__ constexpr int rx_ntaps(int r) { return (kRxTaps - 1 - rx_br(r)) / kRxP + 1; }
+__host__ __device__ constexpr int rx_trunc(int r) { return rx_ix(r) > 287 ? rx_ix(r) - 287 : 0; }   // 1055 - 96*8 = 287
+// sample offset of (phase r, tap k) relative to the tile origin of the lane's period, then its padded address
+__host__ __device__ constexpr int rx_c(int r, int k) { return rx_ix(r) - k - 96; }
+__host__ __device__ constexpr int rx_pad(int c) { return c + 2 * (c / 96); }
+
+constexpr int kRxTileRows = 34, kRxRowPitch = 98;                      // samples
+constexpr int kRxTileIn = kRxTileRows * kRxRowPitch;                   // 3332 samples
+constexpr int kRxTileOut = 32 * kRxP;                                  // 2080 samples
+
+template <int R0>
+BTS_HD void rx_group(const float *__restrict__ taps, const cf *__restrict__ xl, cf *__restrict__ ol, bool q8) {
+  constexpr int NR = 5;
+  constexpr int CLO = (rx_c(R0, 14)) & ~1;                             // even-aligned lowest sample offset
+  constexpr int CHI = rx_c(R0 + NR - 1, 0);
+  constexpr int NP = (CHI - CLO) / 2 + 1;                              // 16-byte pairs
+  cf win[2 * NP];
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    const float4 v = *reinterpret_cast<const float4 *>(xl + rx_pad(CLO + 2 * p));
+    win[2 * p] = mk(v.x, v.y);
+    win[2 * p + 1] = mk(v.z, v.w);
+  }
+#pragma unroll
+  for (int d = 0; d < NR; d++) {
+    const int r = R0 + d;
+    cf sum = mk(0.0F, 0.0F);
+#pragma unroll
+    for (int k = 0; k < 15; k++) {
+      if (k < rx_ntaps(r)) {
+        const cf x = win[rx_c(r, k) - CLO];
+        cf p = cmulr(x, taps[r * 16 + k]);
+        if (k < rx_trunc(r)) {                                         // only phases 60..64: dropped in period q == 8
+          p.x = q8 ? 0.0F : p.x;
+          p.y = q8 ? 0.0F : p.y;
+        }
+        sum = cadd(sum, p);
+      }
+    }
+    ol[r] = sum;
+  }
+}
+
+// all 65 phases of one period: xl = the lane's row of the padded input tile, ol = its 65 outputs
+BTS_HD void rx_period(const float *__restrict__ taps, const cf *__restrict__ xl, cf *__restrict__ ol, bool q8) {
+  rx_group<0>(taps, xl, ol, q8);  rx_group<5>(taps, xl, ol, q8);  rx_group<10>(taps, xl, ol, q8); rx_group<15>(taps, xl, ol, q8);
+  rx_group<20>(taps, xl, ol, q8); rx_group<25>(taps, xl, ol, q8); rx_group<30>(taps, xl, ol, q8); rx_group<35>(taps, xl, ol, q8);
+  rx_group<40>(taps, xl, ol, q8); rx_group<45>(taps, xl, ol, q8); rx_group<50>(taps, xl, ol, q8); rx_group<55>(taps, xl, ol, q8);
+  rx_group<60>(taps, xl, ol, q8);
+}
+// taps[r*16 + k] = lpf_rx[br_r + 65 k] from the [branch][k] table
+inline void rx_fill_taps(const DevTables *hostT, float *taps) {
+  for (int r = 0; r < kRxP; r++)
+    for (int k = 0; k < 16; k++) taps[r * 16 + k] = hostT->rx_poly[rx_br(r)][k];
+}
+
 }  // namespace btsdsp

@@ -101,6 +101,14 @@ class Emu:
         self.lib.emu_resample_rx(P(raw), c_i(0), c_ll(nch), P(out))
         return out
 
+    def rx_resample_stream_v2(self, raw, has_history=False, offset=0):
+        """the tuned kernel's logic; with has_history the 192 samples before raw[offset] are read as history"""
+        raw = np.ascontiguousarray(raw, np.complex64)
+        nch = (raw.size - offset) // 864
+        out = np.zeros(nch * 585, np.complex64)
+        self.lib.emu_resample_rx_v2(ctypes.c_void_p(raw.ctypes.data + 8 * offset), c_i(int(has_history)), c_ll(nch), P(out))
+        return out
+
     def tx_resample_stream(self, x):
         x = np.ascontiguousarray(x, np.complex64)
         nch = x.size // 585

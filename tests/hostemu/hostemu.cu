@@ -297,6 +297,30 @@ void emu_resample_rx(const float *in, int has_history, long long nchunks, float 
       ((cf *)out)[c * 585 + m] = resample_at<kRxP, kRxQ, kRxTaps, kRxPoly, kRxP + 1>(x.data(), 192 + 864, hp.data(), 130, m);
   }
 }
+// k_resample_rx_v2: 32-period tiles, padded rows, all 65 phases per "lane"
+void emu_resample_rx_v2(const float *in_, int has_history, long long nchunks, float *out_) {
+  const cf *in = (const cf *)in_;
+  cf *out = (cf *)out_;
+  std::vector<float> taps(kRxP * 16);
+  rx_fill_taps(T, taps.data());
+  const long long nperiods = nchunks * 9, nsamples = nchunks * 864;
+  std::vector<cf> xt(kRxTileIn), ot(kRxTileOut);
+  for (long long G0 = 0; G0 < nperiods; G0 += 32) {
+    const long long raw0 = 96 * G0 - 96, lo = has_history ? -192 : 0;
+    for (size_t k = 0; k < xt.size(); k++) xt[k] = mk(1e30F, 1e30F);
+    for (int row = 0; row < kRxTileRows; row++)
+      for (int c = 0; c < 96; c++) {
+        const long long s = raw0 + (long long)row * 96 + c;
+        xt[row * kRxRowPitch + c] = (s >= lo && s < nsamples) ? in[s] : mk(0.0F, 0.0F);
+      }
+    for (int lane = 0; lane < 32; lane++) {
+      const long long G = G0 + lane;
+      rx_period(taps.data(), xt.data() + lane * kRxRowPitch, ot.data() + lane * kRxP, (G % 9) == 8);
+    }
+    const long long nvalid = (nperiods - G0 < 32 ? nperiods - G0 : 32) * kRxP;
+    for (long long i = 0; i < nvalid; i++) out[G0 * kRxP + i] = ot[i];
+  }
+}
 void emu_resample_tx(const float *in, int has_history, long long nchunks, short *out) {
   std::vector<cf> x(130 + 585);
   std::vector<float> hp(kTxPoly * (kTxP + 1));

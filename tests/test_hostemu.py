@@ -144,3 +144,17 @@ def test_stream_kernels_logic(emu):
         assert_same(r[k], g[k], k)
     b = g["bits"][0]
     assert_same(emu.modulate(b, 9), g["stream_head"][:157], "modulate")
+
+
+def test_tuned_rx_resampler_logic(emu, oracle_port):
+    """period/phase formulation of the chunked reference loop: zero history, right-edge truncation of every chunk,
+    tiles that are not a multiple of a chunk, a stream that does not fill the last tile"""
+    g = golden("stream_sps1.npz")
+    assert_same(emu.rx_resample_stream_v2(g["raw_head"]), g["res_head"], "v2 == golden")
+    rng = np.random.default_rng(8)
+    for nch in (1, 2, 3, 4, 7, 11, 36):
+        raw = ((rng.standard_normal(nch * 864) + 1j * rng.standard_normal(nch * 864)) * 3000).astype(np.complex64)
+        ref = oracle_port.rx_resample_stream(raw)
+        assert_same(emu.rx_resample_stream_v2(raw), ref, "v2 %d chunks" % nch)
+        if nch > 2:
+            assert_same(emu.rx_resample_stream_v2(raw, has_history=True, offset=2 * 864), ref[2 * 585:], "v2 with history")

@@ -22,7 +22,8 @@ def main():
     ia, ie, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples")
     isrc = hdr.index("Source")
     per_addr = []
-    for r in rows[hi + 1:]:
+    end = next((i for i in range(hi + 1, len(rows)) if rows[i] and rows[i][0] in ("Address", "Kernel Name")), len(rows))
+    for r in rows[hi + 1:end]:
         if len(r) > ie and r[ie] not in ("", None):
             per_addr.append((r[isrc], float(r[ie] or 0), float(r[isamp] or 0)))
     # address -> line from nvdisasm (instruction order is the same as in the ncu page)
