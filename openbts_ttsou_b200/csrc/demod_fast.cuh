@@ -208,9 +208,14 @@ BTS_HD bool analyze_fast(Grid grid, const DevTables *__restrict__ T, View<S> win
   return true;
 }
 
-// equalizeBurst (:1343-1399) as a streaming pipeline over one lane's column `a` (the burst, already scaled by
-// 1/amplitude).  F = delayVector's fractional FIR output, D[n] = F[n - io] the delayed burst, y = feed-forward
-// output, then decision feedback.  Window Fw[i] = F[q0 + i], q0 = m0 - io for the block of outputs m0..m0+3.
+// equalizeBurst (:1343-1399) as a streaming pipeline over one lane's column of a ROLLING tile (the burst,
+// already scaled by 1/amplitude; rows outside the burst hold zeros).  F = delayVector's fractional FIR output,
+// D[n] = F[n - io] the delayed burst, y = feed-forward output, then decision feedback.
+// Window Fw[i] = F[q0 + i], q0 = m0 - io for the block of outputs m0..m0+3.  `base` = burst row held in tile row 0.
+constexpr int kEqRows = 72;          // rows of the rolling tile (19 KB per warp)
+constexpr int kEqStart = -12;        // first pipeline step: three priming steps fill the window
+constexpr int kEqLook = 23;          // step(m0) reads burst rows m0 - io .. m0 - io + 23
+
 template <int S>
 struct EqLane {
   View<S> a;
@@ -219,9 +224,8 @@ struct EqLane {
   float s[21];
   cf w[7], b[5], hist[5], Fw[10];
 
-  BTS_HD void init(Grid grid, const DevTables *__restrict__ T, View<S> burst, int n, float TOA,
-                   const cf *w_, const cf *b_) {
-    a = burst;
+  BTS_HD void init(Grid grid, const DevTables *__restrict__ T, View<S> tile, int n, float TOA, const cf *w_, const cf *b_) {
+    a = tile;
     N = n;
     const float delay = -TOA;                                     // delayVector(rxBurst, -TOA) :1350
     io = (int)floorf(delay);
@@ -239,28 +243,27 @@ struct EqLane {
     for (int k = 0; k < 5; k++) { b[k] = b_[k]; hist[k] = mk(0.0F, 0.0F); }
 #pragma unroll
     for (int i = 0; i < 10; i++) Fw[i] = mk(0.0F, 0.0F);
-    // the window is primed by running the pipeline from m0 = -12: compute_y(-8) and compute_y(-4) leave
+    // the window is primed by running the pipeline from m0 = kEqStart: compute_y(-8) and compute_y(-4) leave
     // F[-io .. -io+5] in Fw[0..5]; their feed-forward outputs (m < 0) are discarded by feedback4
   }
 
-  // F[x0..x0+3]; CHECKED = rows/indices may fall outside the burst
+  // F[x0..x0+3].  Rows outside the burst read as zero from the tile (a zero sample adds +-0 where the reference
+  // skips the tap).  CHECKED additionally zeroes F where x or x + io falls outside the burst (delayVector's zero
+  // fill and the vector ends).
   template <bool CHECKED>
-  BTS_HD void newF4(int x0, cf out[4]) const {
+  BTS_HD void newF4(int base, int x0, cf out[4]) const {
     cf acc[4], center[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) { acc[r] = mk(0.0F, 0.0F); center[r] = mk(0.0F, 0.0F); }
+    const View<S> t = a.at(x0 + 13 - base);
 #pragma unroll
     for (int jj = 0; jj < 24; jj++) {
-      const int row = x0 + 13 - jj;
-      const bool inr = CHECKED ? ((unsigned)row < (unsigned)N) : true;
-      if (inr) {
-        const cf v = a.ld(row);
+      const cf v = t.ld(-jj);                                     // burst row x0 + 13 - jj
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-          const int k = r - 3 + jj;                               // = (x0 + r + 10) - row
-          if (k >= 0 && k <= 20) acc[r] = cadd(acc[r], cmulr(v, s[k]));
-          if (k == 10) center[r] = v;                             // row == x0 + r
-        }
+      for (int r = 0; r < 4; r++) {
+        const int k = r - 3 + jj;                                 // = (x0 + r + 10) - row
+        if (k >= 0 && k <= 20) acc[r] = cadd(acc[r], cmulr(v, s[k]));
+        if (k == 10) center[r] = v;                               // row == x0 + r
       }
     }
 #pragma unroll
@@ -274,15 +277,15 @@ struct EqLane {
     }
   }
 
-  BTS_HD bool interior(int m0) const {
+  BTS_HD bool interior(int m0) const {                            // every F of block m0 is a sample of the delayed burst
     const int x0 = m0 - io + 6;
-    return x0 - 10 >= 0 && x0 + 13 <= N - 1 && m0 + 9 <= N - 1;
+    return x0 >= 0 && x0 + 3 <= N - 1 && m0 + 6 >= 0 && m0 + 9 <= N - 1;
   }
 
   // feed-forward outputs y[m0..m0+3] (consumes the window, then slides it by 4)
   template <bool CHECKED>
-  BTS_HD void compute_y(int m0, cf y[4]) {
-    newF4<CHECKED>(m0 - io + 6, &Fw[6]);
+  BTS_HD void compute_y(int base, int m0, cf y[4]) {
+    newF4<CHECKED>(base, m0 - io + 6, &Fw[6]);
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       cf sum = mk(0.0F, 0.0F);
@@ -294,8 +297,8 @@ struct EqLane {
     for (int i = 0; i < 6; i++) Fw[i] = Fw[i + 4];
   }
 
-  // decision feedback + slicer for m = m0..m0+3 (:1367-1386)
-  BTS_HD void feedback4(const DevTables *__restrict__ T, int m0, const cf y[4], float soft[4]) {
+  // decision feedback + slicer for m = m0..m0+3 (:1367-1386); rot/revrot = the table entries for those m
+  BTS_HD void feedback4(int m0, const cf y[4], const cf rot[4], const cf revrot[4], float soft[4]) {
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       const int m = m0 + r;
@@ -304,45 +307,36 @@ struct EqLane {
 #pragma unroll
       for (int k = 0; k < 5; k++)
         if (m - 1 - k >= 0) v = cadd(v, cmul(b[k], hist[k]));
-      const int mi = m < 157 ? m : 156;                           // the tail block may run past the burst
-      const cf rr = T->revrot[mi];
-      const float out = BTS_SUB(BTS_MUL(v.x, rr.x), BTS_MUL(v.y, rr.y));   // real part of v * revrot[m]
+      const float out = BTS_SUB(BTS_MUL(v.x, revrot[r].x), BTS_MUL(v.y, revrot[r].y));   // real part of v * revrot[m]
 #pragma unroll
       for (int k = 4; k >= 1; k--) hist[k] = hist[k - 1];
-      hist[0] = cmul(mk((out > 0.0F) ? 1.0F : -1.0F, 0.0F), T->rot[mi]);
+      hist[0] = cmul(mk((out > 0.0F) ? 1.0F : -1.0F, 0.0F), rot[r]);
       soft[r] = soft_slice(out);
     }
   }
 
-  // one pipeline step: feed-forward for the NEXT block (independent work) + feedback for the current one.
-  // The pipeline starts at m0 = kEqStart (three priming steps whose feedback is a no-op).
+  // one pipeline step: feed-forward for the NEXT block (independent work) + feedback for the current one
   template <bool CHECKED>
-  BTS_HD void step(const DevTables *__restrict__ T, int m0, cf ycur[4], float soft[4]) {
+  BTS_HD void step(const DevTables *__restrict__ T, int base, int m0, cf ycur[4], float soft[4]) {
+    cf rot[4], revrot[4];                                         // fetched first: off the feedback chain's critical path
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int mi = m0 + r < 0 ? 0 : (m0 + r > 156 ? 156 : m0 + r);
+      rot[r] = T->rot[mi];
+      revrot[r] = T->revrot[mi];
+    }
     cf ynext[4];
-    compute_y<CHECKED>(m0 + 4, ynext);
-    feedback4(T, m0, ycur, soft);
+    compute_y<CHECKED>(base, m0 + 4, ynext);
+    feedback4(m0, ycur, rot, revrot, soft);
 #pragma unroll
     for (int r = 0; r < 4; r++) ycur[r] = ynext[r];
   }
 };
-constexpr int kEqStart = -12;
 
-// The whole per-lane equaliser on the host side of the emulation (and the reference loop for the kernel):
-// soft[m] for m < n.  The kernel drives the same steps but votes `interior` across the warp.
-template <int S>
-BTS_HD void equalize_fast_lane(Grid grid, const DevTables *__restrict__ T, View<S> burst, int n,
-                               float TOA, const cf *w, const cf *b, float *soft) {
-  EqLane<S> eq;
-  eq.init(grid, T, burst, n, TOA, w, b);
-  cf ycur[4];
-#pragma unroll
-  for (int r = 0; r < 4; r++) ycur[r] = mk(0.0F, 0.0F);
-  for (int m0 = kEqStart; m0 < n; m0 += 4) {
-    float s4[4];
-    if (eq.interior(m0 + 4)) eq.template step<false>(T, m0, ycur, s4);
-    else eq.template step<true>(T, m0, ycur, s4);
-    for (int r = 0; r < 4; r++) if (m0 + r >= 0 && m0 + r < n) soft[m0 + r] = s4[r];
-  }
+// warp-uniform rolling-tile policy shared by the kernel and the host emulation: before step(m0) the tile must hold
+// burst rows [m0 - io_max, m0 - io_min + kEqLook]; when it does not, re-stage with row (m0 - io_max) at tile row 0.
+BTS_HD bool eq_needs_restage(int base, int m0, int io_min, int io_max) {
+  return (m0 - io_max < base) || (m0 - io_min + kEqLook >= base + kEqRows);
 }
 
 }  // namespace btsdsp

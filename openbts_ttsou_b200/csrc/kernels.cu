@@ -235,8 +235,9 @@ void launch_modulate_impulse(const DevTables *T, const uint8_t *bits, int nbits,
 //                     correlation next to it (72 tile rows = 19 KB per warp, 8 warps per CTA share one
 //                     shared-memory copy of the sinc grid), and leaves {1/amp, TOA - offset, w[7], b[5]} per burst
 //                     in an EqParams record;
-//   k_equalize_fast : stages the detected bursts in full, scaled by 1/amp on the way in (one 160-row tile = 42 KB
-//                     per warp, 5 warps per SM), and runs the streaming equaliser of demod_fast.cuh.
+//   k_equalize_fast : streams the detected bursts, scaled by 1/amp on the way in, through a ROLLING 72-row tile
+//                     (19 KB per warp, re-staged every ~47 rows; 11 warps per SM) under the pipelined equaliser
+//                     of demod_fast.cuh.
 // Staging loads are issued in batches (36 / 20 independent loads per lane) before their shared-memory stores so a
 // warp has many requests in flight instead of one.
 // ------------------------------------------------------------------------------------------------
@@ -248,7 +249,7 @@ struct __align__(16) EqParams {       // 28 floats = 112 B per burst
 constexpr size_t kGridBytes = (size_t)kSincGrid * kGridPitch * sizeof(float);
 constexpr int kDetRows = 72;          // rows 0..35: burst samples 56..91; rows 36..71: correlation (gate window first)
 constexpr size_t kDetTileBytes = (size_t)kDetRows * kTileStride * sizeof(cf);
-constexpr size_t kEqTileBytes = (size_t)kBurstRows * kTileStride * sizeof(cf);
+constexpr size_t kEqTileBytes = (size_t)kEqRows * kTileStride * sizeof(cf);
 template <int WARPS> constexpr size_t detect_smem() { return kGridBytes + WARPS * kDetTileBytes; }
 template <int WARPS> constexpr size_t equalize_smem() { return WARPS * kEqTileBytes; }
 
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_equalize_fast(const DevTables *_
                                                               int soft_pitch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  cf *A = reinterpret_cast<cf *>(smem_raw) + (size_t)warp * kBurstRows * kTileStride;
+  cf *A = reinterpret_cast<cf *>(smem_raw) + (size_t)warp * kEqRows * kTileStride;
   const long long w0 = ((long long)blockIdx.x * WARPS + warp) * 32;
   if (w0 >= n) return;
   const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
@@ -382,61 +383,72 @@ __global__ void __launch_bounds__(WARPS * 32) k_equalize_fast(const DevTables *_
       fb[0] = mk(q4.z, q4.w); fb[1] = mk(q5.x, q5.y); fb[2] = mk(q5.z, q5.w); fb[3] = mk(q6.x, q6.y); fb[4] = mk(q6.z, q6.w);
     }
   }
-  const unsigned okmask = __ballot_sync(0xffffffffu, ok);
-
-  // ---- staging: detected bursts in full, scaled by 1/amplitude (scaleVector, Transceiver.cpp:391);
-  //      four bursts (20 loads per lane) in flight at a time
-  for (unsigned rem = okmask; rem;) {
-    int js[4]; cf iaj[4]; long long sj[4]; int lj[4];
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-      js[b] = rem ? __ffs(rem) - 1 : -1;
-      if (rem) rem &= rem - 1;
-      const int jj = js[b] < 0 ? 0 : js[b];
-      iaj[b] = mk(__shfl_sync(0xffffffffu, ia.x, jj), __shfl_sync(0xffffffffu, ia.y, jj));
-      sj[b] = __shfl_sync(0xffffffffu, start, jj);
-      lj[b] = js[b] < 0 ? 0 : __shfl_sync(0xffffffffu, len, jj);
-    }
-    cf v[4][5];
-#pragma unroll
-    for (int b = 0; b < 4; b++)
-#pragma unroll
-      for (int k = 0; k < 5; k++) {
-        const int r = lane + 32 * k;
-        v[b][k] = (r < lj[b]) ? __ldg(src.base + sj[b] + r) : mk(0.0F, 0.0F);
-      }
-#pragma unroll
-    for (int b = 0; b < 4; b++)
-#pragma unroll
-      for (int k = 0; k < 5; k++) {
-        const int r = lane + 32 * k;
-        if (r < lj[b]) A[r * kTileStride + js[b]] = cmul(v[b][k], iaj[b]);
-      }
-  }
-  __syncwarp();
-  if (lane >= nv) return;
-
   float *row = soft + i * (long long)soft_pitch;
   const bool vec = ((reinterpret_cast<uintptr_t>(row) | (uintptr_t)(soft_pitch * 4)) & 15) == 0;
-  if (ok) {
-    EqLane<kTileStride> eq;
-    eq.init(Grid{&T->sinc_grid[0][0], 24}, T, View<kTileStride>{A + lane}, len, toa_eq, w, fb);  // :392-396
-    const int nmax = __reduce_max_sync(okmask, len);
-    cf ycur[4];
+  if (!ok && lane < nv) {                       // undetected: the row is all zeros (written while the others equalise)
+    if (vec) for (int m = 0; m < soft_pitch; m += 4) *reinterpret_cast<float4 *>(row + m) = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
+    else for (int m = 0; m < soft_pitch; m++) row[m] = 0.0F;
+  }
+  const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+  if (okmask == 0) return;
+
+  EqLane<kTileStride> eq;
+  if (ok) eq.init(Grid{&T->sinc_grid[0][0], 24}, T, View<kTileStride>{A + lane}, len, toa_eq, w, fb);      // :392-396
+  else eq.io = 0;
+  const int io_min = __reduce_min_sync(0xffffffffu, ok ? eq.io : 0x7fffffff);
+  const int io_max = __reduce_max_sync(0xffffffffu, ok ? eq.io : (int)0x80000000);
+  const int nmax = __reduce_max_sync(0xffffffffu, ok ? len : 0);
+  int base = 0;
+  bool staged = false;
+  cf ycur[4];
 #pragma unroll
-    for (int r = 0; r < 4; r++) ycur[r] = mk(0.0F, 0.0F);
-    for (int m0 = kEqStart; m0 < nmax; m0 += 4) {
+  for (int r = 0; r < 4; r++) ycur[r] = mk(0.0F, 0.0F);
+
+  for (int m0 = kEqStart; m0 < nmax; m0 += 4) {
+    if (!staged || eq_needs_restage(base, m0, io_min, io_max)) {
+      // ---- roll the tile: rows [base, base + kEqRows) of every detected burst, scaled by 1/amplitude
+      //      (scaleVector, Transceiver.cpp:391), zeros outside the burst; 4 bursts x 3 rows per lane in flight
+      base = m0 - io_max;
+      staged = true;
+      __syncwarp();
+      for (unsigned rem = okmask; rem;) {
+        int js[4]; cf iaj[4]; long long sj[4]; int lj[4];
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          js[b] = rem ? __ffs(rem) - 1 : -1;
+          if (rem) rem &= rem - 1;
+          const int jj = js[b] < 0 ? 0 : js[b];
+          iaj[b] = mk(__shfl_sync(0xffffffffu, ia.x, jj), __shfl_sync(0xffffffffu, ia.y, jj));
+          sj[b] = __shfl_sync(0xffffffffu, start, jj);
+          lj[b] = js[b] < 0 ? 0 : __shfl_sync(0xffffffffu, len, jj);
+        }
+        cf v[4][3];
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            const int r = base + lane + 32 * k;
+            v[b][k] = ((unsigned)r < (unsigned)lj[b] && lane + 32 * k < kEqRows) ? __ldg(src.base + sj[b] + r) : mk(0.0F, 0.0F);
+          }
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            const int tr = lane + 32 * k, r = base + tr;
+            if (js[b] >= 0 && tr < kEqRows)
+              A[tr * kTileStride + js[b]] = ((unsigned)r < (unsigned)lj[b]) ? cmul(v[b][k], iaj[b]) : mk(0.0F, 0.0F);
+          }
+      }
+      __syncwarp();
+    }
+    if (ok) {
       float s4[4];
-      if (__all_sync(okmask, eq.interior(m0 + 4))) eq.template step<false>(T, m0, ycur, s4);
-      else eq.template step<true>(T, m0, ycur, s4);
+      if (__all_sync(okmask, eq.interior(m0 + 4))) eq.template step<false>(T, base, m0, ycur, s4);
+      else eq.template step<true>(T, base, m0, ycur, s4);
       store_soft4(row, vec, soft_pitch, m0, s4, len);
     }
-    for (int m = len; m < soft_pitch; m++) row[m] = 0.0F;
-  } else if (vec) {
-    for (int m = 0; m < soft_pitch; m += 4) *reinterpret_cast<float4 *>(row + m) = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
-  } else {
-    for (int m = 0; m < soft_pitch; m++) row[m] = 0.0F;
   }
+  if (ok) for (int m = len; m < soft_pitch; m++) row[m] = 0.0F;
 }
 
 size_t demod_scratch_bytes(long long n) { return (size_t)n * sizeof(EqParams); }
@@ -452,10 +464,8 @@ int launch_demod_normal(const DevTables *T, BurstSrc src, const uint8_t *tsc, lo
   else
     k_detect_design<1><<<(unsigned)nwarps, 32, detect_smem<1>(), st>>>(T, src, tsc, n, detect_thr, gate_thr, snr_thr, out, eqp);
   if (!out.soft) return 1;
-  if (nwarps >= 148 * 5)
-    k_equalize_fast<5><<<(unsigned)((nwarps + 4) / 5), 160, equalize_smem<5>(), st>>>(T, src, n, eqp, out.soft, out.soft_pitch);
-  else
-    k_equalize_fast<1><<<(unsigned)nwarps, 32, equalize_smem<1>(), st>>>(T, src, n, eqp, out.soft, out.soft_pitch);
+  // one-warp CTAs: 19 KB of shared memory each, 11 resident per SM
+  k_equalize_fast<1><<<(unsigned)nwarps, 32, equalize_smem<1>(), st>>>(T, src, n, eqp, out.soft, out.soft_pitch);
   return 2;
 }
 
@@ -668,8 +678,6 @@ int configure_kernels() {
   e = cudaFuncSetAttribute(k_detect_design<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<8>());
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_detect_design<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<1>());
-  if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(k_equalize_fast<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)equalize_smem<5>());
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_equalize_fast<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)equalize_smem<1>());
   if (e != cudaSuccess) return (int)e;

@@ -84,20 +84,20 @@ __device__ __forceinline__ void cp_async_wait_all() {
 
 constexpr size_t kRxV2Smem = (size_t)(kRxTileIn + kRxTileOut) * sizeof(cf);
 
-__global__ void __launch_bounds__(32) k_resample_rx_v2(const cf *__restrict__ in, int has_history, long long nperiods,
+__global__ void __launch_bounds__(64) k_resample_rx_v2(const cf *__restrict__ in, int has_history, long long nperiods,
                                                        long long nsamples, cf *__restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf *xt = reinterpret_cast<cf *>(smem_raw);
   cf *ot = xt + kRxTileIn;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;      // two warps share a tile: each does half the phases
   for (long long tile = blockIdx.x; tile * 32 < nperiods; tile += gridDim.x) {
     const long long G0 = tile * 32;
     const long long raw0 = 96 * G0 - 96;                               // tile origin: sample (G, r, k) sits at 96*l + ix_r - k - 96
     // ---- load 34 rows x 96 samples as 16-byte cp.async copies (global -> shared, no registers, all 51 per lane
     //      in flight at once); samples outside [lo, nsamples) are zero-filled by the copy's src-size operand
     const long long lo = has_history ? -192 : 0;
-    __syncwarp();
-    for (int i4 = lane; i4 < kRxTileRows * 48; i4 += 32) {
+    __syncthreads();                                                    // previous tile fully written back
+    for (int i4 = threadIdx.x; i4 < kRxTileRows * 48; i4 += 64) {
       const int row = i4 / 48, c4 = i4 - row * 48;
       const long long s = raw0 + (long long)row * 96 + 2 * c4;
       cf *dst = xt + row * kRxRowPitch + 2 * c4;
@@ -108,18 +108,19 @@ __global__ void __launch_bounds__(32) k_resample_rx_v2(const cf *__restrict__ in
       }
     }
     cp_async_wait_all();
-    __syncwarp();
+    __syncthreads();
     // ---- 65 phases for this lane's period
     const long long G = G0 + lane;
     const bool q8 = (G % 9) == 8;
     const cf *xl = xt + lane * kRxRowPitch;
     cf *ol = ot + lane * kRxP;
-    rx_period(c_rx_poly, xl, ol, q8);
-    __syncwarp();
+    if (warp == 0) rx_half<0>(c_rx_poly, xl, ol, q8);
+    else rx_half<1>(c_rx_poly, xl, ol, q8);
+    __syncthreads();
     // ---- write the 32 x 65 outputs back: contiguous in both shared and global memory
     const long long nvalid = (nperiods - G0 < 32 ? nperiods - G0 : 32) * kRxP;
     cf *og = out + G0 * kRxP;
-    for (int i4 = lane; i4 < kRxTileOut / 2; i4 += 32) {
+    for (int i4 = threadIdx.x; i4 < kRxTileOut / 2; i4 += 64) {
       if (2 * i4 + 1 < nvalid) *reinterpret_cast<float4 *>(og + 2 * i4) = *reinterpret_cast<const float4 *>(ot + 2 * i4);
       else if (2 * i4 < nvalid) og[2 * i4] = ot[2 * i4];
     }
@@ -138,7 +139,7 @@ void launch_resample_rx(const DevTables *T, const cf *in, int has_history, long 
   if (aligned) {
     const long long nperiods = nchunks * 9, ntiles = (nperiods + 31) / 32;
     const unsigned grid = (unsigned)(ntiles < 148 * 5 * 8 ? ntiles : 148 * 5 * 8);
-    k_resample_rx_v2<<<grid, 32, kRxV2Smem, st>>>(in, has_history, nperiods, nchunks * 864, out);
+    k_resample_rx_v2<<<grid, 64, kRxV2Smem, st>>>(in, has_history, nperiods, nchunks * 864, out);
   } else {
     const unsigned grid = (unsigned)(nchunks < 148 * 32 ? nchunks : 148 * 32);
     k_resample_rx<<<grid, 256, 0, st>>>(T, in, has_history, nchunks, out);

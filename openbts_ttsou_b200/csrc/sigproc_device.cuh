@@ -497,6 +497,17 @@ BTS_HD void rx_period(const float *__restrict__ taps, const cf *__restrict__ xl,
   rx_group<40>(taps, xl, ol, q8); rx_group<45>(taps, xl, ol, q8); rx_group<50>(taps, xl, ol, q8); rx_group<55>(taps, xl, ol, q8);
   rx_group<60>(taps, xl, ol, q8);
 }
+// the same split in two for a pair of warps sharing one tile: phases 0..34 and 35..64
+template <int HALF>
+BTS_HD void rx_half(const float *__restrict__ taps, const cf *__restrict__ xl, cf *__restrict__ ol, bool q8) {
+  if (HALF == 0) {
+    rx_group<0>(taps, xl, ol, q8);  rx_group<5>(taps, xl, ol, q8);  rx_group<10>(taps, xl, ol, q8); rx_group<15>(taps, xl, ol, q8);
+    rx_group<20>(taps, xl, ol, q8); rx_group<25>(taps, xl, ol, q8); rx_group<30>(taps, xl, ol, q8);
+  } else {
+    rx_group<35>(taps, xl, ol, q8); rx_group<40>(taps, xl, ol, q8); rx_group<45>(taps, xl, ol, q8); rx_group<50>(taps, xl, ol, q8);
+    rx_group<55>(taps, xl, ol, q8); rx_group<60>(taps, xl, ol, q8);
+  }
+}
 // taps[r*16 + k] = lpf_rx[br_r + 65 k] from the [branch][k] table
 inline void rx_fill_taps(const DevTables *hostT, float *taps) {
   for (int r = 0; r < kRxP; r++)

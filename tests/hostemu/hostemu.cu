@@ -140,13 +140,12 @@ void emu_demod_normal(const float *bursts, long long pitch, const int *lens, lon
   std::vector<float> gridv(kSincGrid * kGridPitch);
   for (int i = 0; i < kSincGrid * kGridPitch; i++) gridv[i] = T->sinc_grid[i / kGridPitch][i % kGridPitch];
   const Grid gsm{gridv.data(), kGridPitch}, ggl{&T->sinc_grid[0][0], 24};
-  std::vector<cf> tileA(72 * kTileStride), tileB(kBurstRows * kTileStride);
+  std::vector<cf> tileA(72 * kTileStride), tileB(kEqRows * kTileStride);
   cf *A = tileA.data(), *B = tileB.data();
   const bool gated = gate_thr >= 0.0F;
   for (long long w0 = 0; w0 < n; w0 += 32) {
     const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
     for (size_t k = 0; k < tileA.size(); k++) A[k] = mk(1e30F, -1e30F);       // poison: catch reads of unstaged rows
-    for (size_t k = 0; k < tileB.size(); k++) B[k] = mk(1e30F, -1e30F);
     for (int j = 0; j < nv; j++) {
       long long start; int len;
       burst_loc_h((const cf *)bursts, pitch, lens, first, 1, w0 + j, &start, &len);
@@ -181,19 +180,52 @@ void emu_demod_normal(const float *bursts, long long pitch, const int *lens, lon
       for (int j = 0; j < 7; j++) wv[lane][j] = w[j];
       for (int j = 0; j < 5; j++) fbv[lane][j] = fb[j];
     }
-    for (int j = 0; j < nv; j++) {
-      if (!okv[j]) continue;
-      const cf *g = (const cf *)bursts + startv[j];
-      for (int r = 0; r < lenv[j]; r++) B[r * kTileStride + j] = cmul(g[r], iav[j]);
-    }
+    // ---- k_equalize_fast: the 32 lanes advance together through the pipeline; the tile rolls when any lane's
+    //      look-ahead leaves it (warp-uniform decision from io_min / io_max)
     for (int lane = 0; lane < nv; lane++) {
-      const long long i = w0 + lane;
-      float *row = soft + i * soft_pitch;
+      float *row = soft + (w0 + lane) * soft_pitch;
       for (int m = 0; m < soft_pitch; m++) row[m] = 0.0F;
+    }
+    EqLane<kTileStride> eq[32];
+    cf ycur[32][4];
+    int io_min = 0x7fffffff, io_max = (int)0x80000000, nmax = 0;
+    bool any = false;
+    for (int lane = 0; lane < nv; lane++) {
       if (!okv[lane]) continue;
-      std::vector<float> s(lenv[lane] + 4);
-      equalize_fast_lane<kTileStride>(ggl, T, View<kTileStride>{B + lane}, lenv[lane], teq[lane], wv[lane], fbv[lane], s.data());
-      for (int m = 0; m < lenv[lane] && m < soft_pitch; m++) row[m] = s[m];
+      any = true;
+      eq[lane].init(ggl, T, View<kTileStride>{B + lane}, lenv[lane], teq[lane], wv[lane], fbv[lane]);
+      io_min = eq[lane].io < io_min ? eq[lane].io : io_min;
+      io_max = eq[lane].io > io_max ? eq[lane].io : io_max;
+      nmax = lenv[lane] > nmax ? lenv[lane] : nmax;
+      for (int r = 0; r < 4; r++) ycur[lane][r] = mk(0.0F, 0.0F);
+    }
+    if (!any) continue;
+    int base = 0;
+    bool staged = false;
+    for (int m0 = kEqStart; m0 < nmax; m0 += 4) {
+      if (!staged || eq_needs_restage(base, m0, io_min, io_max)) {
+        base = m0 - io_max;
+        staged = true;
+        for (size_t k = 0; k < (size_t)kEqRows * kTileStride; k++) B[k] = mk(1e30F, -1e30F);
+        for (int j = 0; j < nv; j++) {
+          if (!okv[j]) continue;
+          const cf *g = (const cf *)bursts + startv[j];
+          for (int tr = 0; tr < kEqRows; tr++) {
+            const int r = base + tr;
+            B[tr * kTileStride + j] = ((unsigned)r < (unsigned)lenv[j]) ? cmul(g[r], iav[j]) : mk(0.0F, 0.0F);
+          }
+        }
+      }
+      bool all_int = true;
+      for (int lane = 0; lane < nv; lane++) if (okv[lane]) all_int = all_int && eq[lane].interior(m0 + 4);
+      for (int lane = 0; lane < nv; lane++) {
+        if (!okv[lane]) continue;
+        float s4[4];
+        if (all_int) eq[lane].template step<false>(T, base, m0, ycur[lane], s4);
+        else eq[lane].template step<true>(T, base, m0, ycur[lane], s4);
+        float *row = soft + (w0 + lane) * soft_pitch;
+        for (int r = 0; r < 4; r++) if (m0 + r >= 0 && m0 + r < lenv[lane] && m0 + r < soft_pitch) row[m0 + r] = s4[r];
+      }
     }
   }
 }
