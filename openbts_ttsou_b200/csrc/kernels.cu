@@ -241,6 +241,15 @@ void launch_modulate_impulse(const DevTables *T, const uint8_t *bits, int nbits,
 // Staging loads are issued in batches (36 / 20 independent loads per lane) before their shared-memory stores so a
 // warp has many requests in flight instead of one.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8z(void *smem_dst, const void *gsrc, bool valid) {   // zero-fills when !valid
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int nbytes = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
 struct __align__(16) EqParams {       // 28 floats = 112 B per burst
   float ia_x, ia_y, toa_eq, ok;
   cf w[7];
@@ -406,40 +415,31 @@ __global__ void __launch_bounds__(WARPS * 32) k_equalize_fast(const DevTables *_
 
   for (int m0 = kEqStart; m0 < nmax; m0 += 4) {
     if (!staged || eq_needs_restage(base, m0, io_min, io_max)) {
-      // ---- roll the tile: rows [base, base + kEqRows) of every detected burst, scaled by 1/amplitude
-      //      (scaleVector, Transceiver.cpp:391), zeros outside the burst; 4 bursts x 3 rows per lane in flight
+      // ---- roll the tile: rows [base, base + kEqRows) of every detected burst (zeros outside the burst) arrive
+      //      by cp.async, then each lane scales its column by 1/amplitude (scaleVector, Transceiver.cpp:391)
       base = m0 - io_max;
       staged = true;
       __syncwarp();
-      for (unsigned rem = okmask; rem;) {
-        int js[4]; cf iaj[4]; long long sj[4]; int lj[4];
+      for (unsigned rem = okmask; rem; rem &= rem - 1) {            // raw samples, global -> shared, all in flight
+        const int j = __ffs(rem) - 1;
+        const long long sj = __shfl_sync(0xffffffffu, start, j);
+        const int lj = __shfl_sync(0xffffffffu, len, j);
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-          js[b] = rem ? __ffs(rem) - 1 : -1;
-          if (rem) rem &= rem - 1;
-          const int jj = js[b] < 0 ? 0 : js[b];
-          iaj[b] = mk(__shfl_sync(0xffffffffu, ia.x, jj), __shfl_sync(0xffffffffu, ia.y, jj));
-          sj[b] = __shfl_sync(0xffffffffu, start, jj);
-          lj[b] = js[b] < 0 ? 0 : __shfl_sync(0xffffffffu, len, jj);
+        for (int k = 0; k < 3; k++) {
+          const int tr = lane + 32 * k, r = base + tr;
+          if (tr < kEqRows) {
+            const bool valid = (unsigned)r < (unsigned)lj;
+            cp_async8z(A + tr * kTileStride + j, src.base + sj + (valid ? r : 0), valid);
+          }
         }
-        cf v[4][3];
-#pragma unroll
-        for (int b = 0; b < 4; b++)
-#pragma unroll
-          for (int k = 0; k < 3; k++) {
-            const int r = base + lane + 32 * k;
-            v[b][k] = ((unsigned)r < (unsigned)lj[b] && lane + 32 * k < kEqRows) ? __ldg(src.base + sj[b] + r) : mk(0.0F, 0.0F);
-          }
-#pragma unroll
-        for (int b = 0; b < 4; b++)
-#pragma unroll
-          for (int k = 0; k < 3; k++) {
-            const int tr = lane + 32 * k, r = base + tr;
-            if (js[b] >= 0 && tr < kEqRows)
-              A[tr * kTileStride + js[b]] = ((unsigned)r < (unsigned)lj[b]) ? cmul(v[b][k], iaj[b]) : mk(0.0F, 0.0F);
-          }
       }
+      cp_async_wait_all();
       __syncwarp();
+      if (ok) {                                                     // scale the lane's own column in place
+        const View<kTileStride> a{A + lane};
+#pragma unroll 8
+        for (int tr = 0; tr < kEqRows; tr++) a.st(tr, cmul(a.ld(tr), ia));
+      }
     }
     if (ok) {
       float s4[4];
