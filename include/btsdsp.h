@@ -73,6 +73,10 @@ int btsdsp_get_table(btsdsp_ctx *ctx, int id, int idx, float *dst, int cap);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 long long btsdsp_launch_count(const btsdsp_ctx *ctx);
 int btsdsp_synchronize(btsdsp_ctx *ctx);
+/* measurement aid: when enabled, btsdsp_demod_normal_dev brackets its two kernels (detect + DFE design, streaming
+ * equaliser) with CUDA events on the caller's stream; btsdsp_get_timing returns the last call's durations in ms */
+int btsdsp_set_timing(btsdsp_ctx *ctx, int enable);
+int btsdsp_get_timing(btsdsp_ctx *ctx, float *detect_ms, float *equalize_ms);
 
 /* ---- layer 1: single vectors, HOST pointers, synchronous ------------------------------------- */
 /* convolve / correlate, sigProcLib.cpp:267 / :474.  Returns the output length (c needs cap >= it). */

@@ -34,6 +34,8 @@ _SIGS = {
     "btsdsp_get_table": (_i, [_vp, _i, _i, _vp, _i]),
     "btsdsp_launch_count": (_ll, [_vp]),
     "btsdsp_synchronize": (_i, [_vp]),
+    "btsdsp_set_timing": (_i, [_vp, _i]),
+    "btsdsp_get_timing": (_i, [_vp, _vp, _vp]),
     "btsdsp_convolve": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i]),
     "btsdsp_correlate": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i]),
     "btsdsp_scale_vector": (_i, [_vp, _vp, _i, _i, _cf32]),
@@ -151,6 +153,15 @@ class BtsDsp:
 
     def synchronize(self):
         self._ck(self.lib.btsdsp_synchronize(self.h))
+
+    def set_timing(self, enable=True):
+        self._ck(self.lib.btsdsp_set_timing(self.h, int(enable)))
+
+    def get_timing(self):
+        """(detect_ms, equalize_ms) of the last timed demod_normal_dev call"""
+        t = np.zeros(2, np.float32)
+        self._ck(self.lib.btsdsp_get_timing(self.h, _p(t[0:]), _p(t[1:])))
+        return float(t[0]), float(t[1])
 
     def table(self, tid, idx=0):
         buf = np.zeros(4096, np.float32)

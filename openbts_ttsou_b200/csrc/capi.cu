@@ -34,6 +34,9 @@ struct btsdsp_ctx {
   DevBuf buf[16];               // grow-only device scratch, by role
   DevBuf pin[4];                // grow-only pinned staging
   std::vector<cudaEvent_t> events;
+  bool timing = false;          // btsdsp_set_timing: bracket the kernels of the receive path with events
+  cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int tev_used = 0;
 };
 
 namespace {
@@ -248,6 +251,7 @@ int btsdsp_destroy(btsdsp_ctx *ctx) {
   for (auto &b : ctx->buf) if (b.p) cudaFree(b.p);
   for (auto &b : ctx->pin) if (b.p) cudaFreeHost(b.p);
   for (auto ev : ctx->events) cudaEventDestroy(ev);
+  for (auto ev : ctx->tev) if (ev) cudaEventDestroy(ev);
   if (ctx->T) cudaFree(ctx->T);
   if (ctx->hT) cudaFreeHost(ctx->hT);
   if (ctx->st) cudaStreamDestroy(ctx->st);
@@ -261,6 +265,25 @@ const char *btsdsp_last_error(const btsdsp_ctx *ctx) { return ctx ? ctx->err.c_s
 int btsdsp_device(const btsdsp_ctx *ctx) { return ctx ? ctx->device : -1; }
 int btsdsp_sps(const btsdsp_ctx *ctx) { return ctx ? ctx->sps : -1; }
 long long btsdsp_launch_count(const btsdsp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+/* optional per-kernel timing of btsdsp_demod_normal_dev: events around k_detect_design and k_equalize_fast */
+int btsdsp_set_timing(btsdsp_ctx *ctx, int enable) {
+  ARG(ctx);
+  DeviceGuard g(ctx->device);
+  if (enable && !ctx->tev[0])
+    for (int i = 0; i < 4; i++) CK(cudaEventCreate(&ctx->tev[i]));
+  ctx->timing = enable != 0;
+  ctx->tev_used = 0;
+  return BTSDSP_OK;
+}
+int btsdsp_get_timing(btsdsp_ctx *ctx, float *detect_ms, float *equalize_ms) {
+  ARG(ctx && detect_ms && equalize_ms);
+  if (!ctx->timing || ctx->tev_used < 3) return fail(ctx, BTSDSP_EINVAL, "no timed btsdsp_demod_normal_dev call recorded");
+  DeviceGuard g(ctx->device);
+  CK(cudaEventSynchronize(ctx->tev[2]));
+  CK(cudaEventElapsedTime(detect_ms, ctx->tev[0], ctx->tev[1]));
+  CK(cudaEventElapsedTime(equalize_ms, ctx->tev[1], ctx->tev[2]));
+  return BTSDSP_OK;
+}
 int btsdsp_synchronize(btsdsp_ctx *ctx) {
   ARG(ctx);
   DeviceGuard g(ctx->device);
@@ -579,8 +602,11 @@ int btsdsp_demod_normal_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long lon
   DeviceGuard g(ctx->device);
   NormalOut o = {flag, (cf *)amp, toa, (cf *)chan, chan_off, (cf *)w, (cf *)b, soft, soft_pitch};
   GROW(B_EQP, demod_scratch_bytes(n));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ctx->timing) CK(cudaEventRecord(ctx->tev[0], st));
   const int nl = launch_demod_normal(ctx->T, make_src(bursts, pitch, lens, first, 1), tsc, n, detect_thr, gate_thr,
-                                     snr_thr, o, dbuf<void>(ctx, B_EQP), (cudaStream_t)stream);
+                                     snr_thr, o, dbuf<void>(ctx, B_EQP), st, ctx->timing ? ctx->tev[1] : nullptr);
+  if (ctx->timing) { CK(cudaEventRecord(ctx->tev[2], st)); ctx->tev_used = 3; }
   LAUNCHED("demod_normal", nl);
   return BTSDSP_OK;
 }

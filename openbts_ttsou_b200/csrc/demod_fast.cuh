@@ -11,7 +11,7 @@
 //     delayed burst and the feed-forward output never exist in memory (one tile per warp instead of three);
 //   * the channel-window search needs only 12 samples of the delayed correlation, so only those are computed;
 //   * all sinc interpolators are rows of the 1/512-grid table (see tables.h) held in shared memory.
-// Every function is __host__ __device__: tests/hostemu replays them on the CPU against the oracle.
+// Every function is __host__ __device__: tests/hostemu replays them on the CPU against the reference outputs.
 #pragma once
 #include "sigproc_device.cuh"
 

@@ -453,8 +453,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_equalize_fast(const DevTables *_
 
 size_t demod_scratch_bytes(long long n) { return (size_t)n * sizeof(EqParams); }
 
+// The two launches of the normal-burst receive path; `between` (optional) is recorded between them so a caller
+// can time the kernels separately.
 int launch_demod_normal(const DevTables *T, BurstSrc src, const uint8_t *tsc, long long n, float detect_thr,
-                        float gate_thr, float snr_thr, NormalOut out, void *scratch, cudaStream_t st) {
+                        float gate_thr, float snr_thr, NormalOut out, void *scratch, cudaStream_t st,
+                        cudaEvent_t between) {
   if (n <= 0) return 0;
   const long long nwarps = (n + 31) / 32;
   EqParams *eqp = out.soft ? reinterpret_cast<EqParams *>(scratch) : nullptr;
@@ -463,6 +466,7 @@ int launch_demod_normal(const DevTables *T, BurstSrc src, const uint8_t *tsc, lo
                                                                                  snr_thr, out, eqp);
   else
     k_detect_design<1><<<(unsigned)nwarps, 32, detect_smem<1>(), st>>>(T, src, tsc, n, detect_thr, gate_thr, snr_thr, out, eqp);
+  if (between) cudaEventRecord(between, st);
   if (!out.soft) return 1;
   // one-warp CTAs: 19 KB of shared memory each, 11 resident per SM
   k_equalize_fast<1><<<(unsigned)nwarps, 32, equalize_smem<1>(), st>>>(T, src, n, eqp, out.soft, out.soft_pitch);

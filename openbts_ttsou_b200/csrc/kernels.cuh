@@ -64,7 +64,8 @@ void launch_resample_tx(const DevTables *T, const cf *in, int has_history, long 
                         cudaStream_t st);
 size_t demod_scratch_bytes(long long n);   // per-launch scratch of launch_demod_normal (EqParams records)
 int launch_demod_normal(const DevTables *T, BurstSrc src, const uint8_t *tsc, long long n, float detect_thr,
-                        float gate_thr, float snr_thr, NormalOut out, void *scratch, cudaStream_t st);
+                        float gate_thr, float snr_thr, NormalOut out, void *scratch, cudaStream_t st,
+                        cudaEvent_t between = nullptr);
 int launch_analyze(const DevTables *T, BurstSrc src, const uint8_t *tsc, long long n, float detect_thr, int request,
                    NormalOut out, cf *scratch, int force_generic, cudaStream_t st);
 int launch_rach(const DevTables *T, BurstSrc src, long long n, float detect_thr, int demod, NormalOut out, cf *scratch,
