@@ -131,7 +131,7 @@ def run_reference(args, rank):
     ms = 1e3 * float(np.mean(times))
     value = nblocks * BLOCK_BURSTS / (ms / 1e3)
     sample = "%d of %d blocks of 117 frames (%d bursts) per step" % (nblocks, args.blocks, nblocks * BLOCK_BURSTS)
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "GSM bursts/sec (resample+detect+DFE)", "value": value, "unit": "bursts/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -147,6 +147,15 @@ def workload_config(args, n):
             "bursts_per_gpu_per_step": args.blocks * BLOCK_BURSTS, "raw_samples_per_gpu": args.blocks * BLOCK_CHUNKS * 864,
             "sps": 1, "tsc": 0, "snr_db": 20, "parallelism": "stream per GPU x%d, no data-path collective" % n,
             "cache": "inputs_larger_than_l2 (1.48 GB stream per step)"}
+
+
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else this process (or NCCL) prints goes to stderr"""
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
@@ -339,7 +348,7 @@ def main():
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "check": {"ber_tsc0": ber, "detected": detected}, "gather": gather,
         }
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
