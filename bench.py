@@ -297,6 +297,33 @@ def main():
                "h2d_bytes_per_step": int(raw.numel() * 4 + nb), "d2h_bytes_per_step": int(nb * (SOFT_PITCH * 4 + 16)),
                "matches_device_path": same, "api": "btsdsp_rx_stream_host (pinned host buffers)"}
 
+    # ---- e2e at the reference's wire formats: int16 {I,Q} in, 148 soft bytes out (btsdsp_rx_stream_wire_host).
+    #      The stream is re-quantised to int16 (what an ADC delivers), so it is its own input, checked by its own BER.
+    e2e_wire = None
+    if not args.no_e2e:
+        iq_h = torch.empty(raw.numel(), dtype=torch.int16, pin_memory=True)
+        iq_h.copy_(raw.round().clamp_(-32768, 32767).to(torch.int16))
+        u8_h = torch.empty(nb * 148, dtype=torch.uint8, pin_memory=True)
+
+        def wire_step():
+            dsp.rx_stream_wire_host(iq_h, nch, tsc_h, nb, flag_h, amp_h, toa_h, u8_h)
+        for _ in range(2):
+            wire_step()
+        wire_ber = float(((u8_h.reshape(nb, 148) > 127).to(torch.uint8) != bits.cpu()).float().mean())
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            wire_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t0) / ke], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_wire = {"value": world * nb / float(dt.item()), "unit": "bursts/s", "ms_per_step": 1e3 * float(dt.item()),
+                    "h2d_bytes_per_step": int(raw.numel() * 2 + nb), "d2h_bytes_per_step": int(nb * (148 + 16)),
+                    "ber_tsc0": wire_ber, "detected": float(flag_h.float().mean()),
+                    "api": "btsdsp_rx_stream_wire_host (int16 I/Q in, 148 soft bytes + flag/amp/toa out, pinned host buffers)"}
     clocks = sampler.stop() if sampler else None
 
     # ---- optional gather of SoftVectors over NCCL (outside the timed path, reported separately)
@@ -345,7 +372,7 @@ def main():
                          "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": how,
                          "kernels": [k_res, k_det, k_eq, k_dem],
                          "step_frac_of_fused_hbm_roof": (nb * FUSED_BYTES_PER_BURST / (ms_step * 1e-3) / 1e9) / peak},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "e2e_wire": e2e_wire, "gpu_launches": int(launches), "clocks": clocks,
             "check": {"ber_tsc0": ber, "detected": detected}, "gather": gather,
         }
         emit(json.dumps(out))

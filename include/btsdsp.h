@@ -132,6 +132,11 @@ int btsdsp_modulate_dev(btsdsp_ctx *ctx, const uint8_t *bits, int nbits, long lo
  * has_history != 0: raw[-192..-1] hold the previous samples; 0: the stream starts here (zeros). */
 int btsdsp_resample_rx_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, int has_history, long long nchunks,
                            btsdsp_cf32 *out, void *stream);
+/* The same from the radio's own sample format: interleaved int16 {I,Q} (4 B per sample), converted as
+ * unUSRPifyVector does (radioInterface.cpp:91-116); swap_iq != 0 for the Q-first order of real USRP hardware,
+ * 0 for the SWLOOPBACK order.  iq must be 16-byte aligned; has_history: iq[-384..-1] (192 samples) are valid. */
+int btsdsp_resample_rx_i16_dev(btsdsp_ctx *ctx, const int16_t *iq, int swap_iq, int has_history, long long nchunks,
+                               btsdsp_cf32 *out, void *stream);
 /* TX resampler (radioInterface.cpp:123-168 + USRPifyVector :74-89): nchunks chunks of 585 samples ->
  * 864 int16 {I,Q} pairs each, scaled by 13500 and truncated like the reference's (short) cast. */
 int btsdsp_resample_tx_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *in, int has_history, long long nchunks, int16_t *out,
@@ -145,6 +150,12 @@ int btsdsp_demod_normal_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long lon
                             long long first, const uint8_t *tsc, long long n, float detect_thr, float gate_thr,
                             float snr_thr, int32_t *flag, btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch,
                             btsdsp_cf32 *chan, float *chan_off, btsdsp_cf32 *w, btsdsp_cf32 *b, void *stream);
+/* The same with the soft bits in the RX datagram's wire format: (char) round(soft*255.0), 148 bytes per burst
+ * (Transceiver::driveReceiveFIFO, Transceiver.cpp:668-670); rows soft_pitch_bytes apart (multiple of 4, >= 148). */
+int btsdsp_demod_normal_u8_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens,
+                               long long first, const uint8_t *tsc, long long n, float detect_thr, float gate_thr,
+                               float snr_thr, int32_t *flag, btsdsp_cf32 *amp, float *toa, uint8_t *soft_u8,
+                               int soft_pitch_bytes, void *stream);
 /* analyzeTrafficBurst alone (any sps). chan: 6*sps per burst. */
 int btsdsp_analyze_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens,
                        long long first, const uint8_t *tsc, long long n, float detect_thr, int request_channel,
@@ -173,6 +184,12 @@ int btsdsp_demodulate_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long 
 int btsdsp_rx_stream_host(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nchunks, const uint8_t *tsc,
                           long long nbursts, float detect_thr, float gate_thr, float snr_thr, int32_t *flag,
                           btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch);
+/* The same pipeline at the reference's wire formats on both sides: int16 {I,Q} samples in (what USRPDevice::readSamples
+ * delivers, radioInterface.cpp:213-227), 148 soft bytes per burst out (what goes into the UDP datagram,
+ * Transceiver.cpp:659-674).  Half the H2D bytes and a quarter of the D2H bytes of the float call. */
+int btsdsp_rx_stream_wire_host(btsdsp_ctx *ctx, const int16_t *iq, int swap_iq, long long nchunks, const uint8_t *tsc,
+                               long long nbursts, float detect_thr, float gate_thr, float snr_thr, int32_t *flag,
+                               btsdsp_cf32 *amp, float *toa, uint8_t *soft_u8);
 /* The same on DEVICE-resident input and outputs (no copies): resample into an internal buffer, then demod. */
 int btsdsp_rx_stream_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nchunks, const uint8_t *tsc,
                          long long nbursts, float detect_thr, float gate_thr, float snr_thr, int32_t *flag,

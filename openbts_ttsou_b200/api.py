@@ -53,6 +53,9 @@ _SIGS = {
     "btsdsp_modulate_dev": (_i, [_vp, _vp, _i, _ll, _i, _ll, _vp, _ll, _vp]),
     "btsdsp_resample_rx_dev": (_i, [_vp, _vp, _i, _ll, _vp, _vp]),
     "btsdsp_resample_tx_dev": (_i, [_vp, _vp, _i, _ll, _vp, _vp]),
+    "btsdsp_resample_rx_i16_dev": (_i, [_vp, _vp, _i, _i, _ll, _vp, _vp]),
+    "btsdsp_demod_normal_u8_dev": (_i, [_vp, _vp, _ll, _vp, _ll, _vp, _ll, _f, _f, _f, _vp, _vp, _vp, _vp, _i, _vp]),
+    "btsdsp_rx_stream_wire_host": (_i, [_vp, _vp, _i, _ll, _vp, _ll, _f, _f, _f, _vp, _vp, _vp, _vp]),
     "btsdsp_demod_normal_dev": (_i, [_vp, _vp, _ll, _vp, _ll, _vp, _ll, _f, _f, _f, _vp, _vp, _vp, _vp, _i, _vp, _vp,
                                      _vp, _vp, _vp]),
     "btsdsp_analyze_dev": (_i, [_vp, _vp, _ll, _vp, _ll, _vp, _ll, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -276,6 +279,21 @@ class BtsDsp:
 
     def resample_rx_dev(self, raw, nchunks, out, has_history=False, stream=None):
         self._ck(self.lib.btsdsp_resample_rx_dev(self.h, _p(raw), int(has_history), nchunks, _p(out), _stream(stream)))
+
+    def resample_rx_i16_dev(self, iq, nchunks, out, swap_iq=False, has_history=False, stream=None):
+        self._ck(self.lib.btsdsp_resample_rx_i16_dev(self.h, _p(iq), int(swap_iq), int(has_history), nchunks, _p(out),
+                                                     _stream(stream)))
+
+    def demod_normal_u8_dev(self, bursts, pitch, tsc, n, flag, amp, toa, soft_u8, soft_pitch=148, lens=None, first=0,
+                            detect_thr=3.0, gate_thr=-1.0, snr_thr=250.0, stream=None):
+        self._ck(self.lib.btsdsp_demod_normal_u8_dev(self.h, _p(bursts), pitch, _p(lens), first, _p(tsc), n, detect_thr,
+                                                     gate_thr, snr_thr, _p(flag), _p(amp), _p(toa), _p(soft_u8), soft_pitch,
+                                                     _stream(stream)))
+
+    def rx_stream_wire_host(self, iq, nchunks, tsc, nbursts, flag, amp, toa, soft_u8, swap_iq=False, detect_thr=3.0,
+                            gate_thr=-1.0, snr_thr=250.0):
+        self._ck(self.lib.btsdsp_rx_stream_wire_host(self.h, _p(iq), int(swap_iq), nchunks, _p(tsc), nbursts, detect_thr,
+                                                     gate_thr, snr_thr, _p(flag), _p(amp), _p(toa), _p(soft_u8)))
 
     def resample_tx_dev(self, x, nchunks, out, has_history=False, stream=None):
         self._ck(self.lib.btsdsp_resample_tx_dev(self.h, _p(x), int(has_history), nchunks, _p(out), _stream(stream)))

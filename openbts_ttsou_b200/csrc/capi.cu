@@ -583,6 +583,33 @@ int btsdsp_resample_rx_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, int has_hist
   return BTSDSP_OK;
 }
 
+int btsdsp_resample_rx_i16_dev(btsdsp_ctx *ctx, const int16_t *iq, int swap_iq, int has_history, long long nchunks,
+                               btsdsp_cf32 *out, void *stream) {
+  ARG(ctx && iq && out && nchunks >= 0);
+  DeviceGuard g(ctx->device);
+  const int r = launch_resample_rx_i16(iq, swap_iq, has_history, nchunks, (cf *)out, (cudaStream_t)stream);
+  if (r < 0) return fail(ctx, BTSDSP_EINVAL, "int16 ingest needs 16-byte aligned pointers");
+  LAUNCHED("resample_rx_i16", r);
+  return BTSDSP_OK;
+}
+
+int btsdsp_demod_normal_u8_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens,
+                               long long first, const uint8_t *tsc, long long n, float detect_thr, float gate_thr,
+                               float snr_thr, int32_t *flag, btsdsp_cf32 *amp, float *toa, uint8_t *soft_u8,
+                               int soft_pitch_bytes, void *stream) {
+  ARG(ctx && bursts && tsc && soft_u8 && n >= 0 && pitch >= 0 && soft_pitch_bytes >= 148 && soft_pitch_bytes % 4 == 0);
+  ARG((reinterpret_cast<uintptr_t>(soft_u8) & 3) == 0);
+  if (ctx->sps != 1) return fail(ctx, BTSDSP_EUNSUPPORTED, "the DFE path assumes symbol-rate sampling (sps == 1)");
+  DeviceGuard g(ctx->device);
+  NormalOut o = {flag, (cf *)amp, toa, nullptr, nullptr, nullptr, nullptr, nullptr, soft_pitch_bytes};
+  o.soft_u8 = soft_u8;
+  GROW(B_EQP, demod_scratch_bytes(n));
+  const int nl = launch_demod_normal(ctx->T, make_src(bursts, pitch, lens, first, 1), tsc, n, detect_thr, gate_thr,
+                                     snr_thr, o, dbuf<void>(ctx, B_EQP), (cudaStream_t)stream);
+  LAUNCHED("demod_normal_u8", nl);
+  return BTSDSP_OK;
+}
+
 int btsdsp_resample_tx_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *in, int has_history, long long nchunks, int16_t *out,
                            void *stream) {
   ARG(ctx && in && out && nchunks >= 0);
@@ -694,27 +721,34 @@ int btsdsp_rx_stream_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nchu
 // copied H2D on st_in while segment s-1 is resampled + demodulated on st and segment s-2's results
 // return D2H on st_out.  The whole raw / resampled stream stays resident on the device so the
 // resampler's 192-sample history and bursts straddling segment borders need no special casing.
-int btsdsp_rx_stream_host(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nchunks, const uint8_t *tsc,
-                          long long nbursts, float detect_thr, float gate_thr, float snr_thr, int32_t *flag,
-                          btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch) {
-  ARG(ctx && raw && tsc && nchunks > 0 && nbursts >= 0);
+// `raw` holds complex64 samples (i16 == 0) or int16 {I,Q} pairs (i16 != 0); `soft` receives floats (u8 == 0, pitch
+// in floats) or the datagram bytes (u8 != 0, pitch in bytes).
+static int rx_stream_host_impl(btsdsp_ctx *ctx, const void *raw_, int i16, int swap_iq, long long nchunks,
+                               const uint8_t *tsc, long long nbursts, float detect_thr, float gate_thr, float snr_thr,
+                               int32_t *flag, btsdsp_cf32 *amp, float *toa, void *soft_, int u8, int soft_pitch) {
+  ARG(ctx && raw_ && tsc && nchunks > 0 && nbursts >= 0);
+  const size_t in_sz = i16 ? 4 : 8, soft_sz = u8 ? 1 : 4;
+  const unsigned char *raw = (const unsigned char *)raw_;
+  unsigned char *soft = (unsigned char *)soft_;
   if (ctx->sps != 1) return fail(ctx, BTSDSP_EUNSUPPORTED, "the RX stream path runs at sps == 1");
   ARG(((nbursts + 3) / 4) * 625 <= nchunks * 585);
-  ARG(!soft || soft_pitch >= 148);
+  ARG(!soft || (soft_pitch >= 148 && (!u8 || soft_pitch % 4 == 0)));
   DeviceGuard g(ctx->device);
-  GROW(B_RAW, (size_t)nchunks * 864 * sizeof(cf));
+  GROW(B_RAW, (size_t)nchunks * 864 * in_sz);
   GROW(B_RES, (size_t)nchunks * 585 * sizeof(cf));
   GROW(B_TSC, (size_t)nbursts + 16);
   GROW(B_FLAG, (size_t)(nbursts + 1) * sizeof(int32_t));
   GROW(B_AMP, (size_t)(nbursts + 1) * sizeof(cf));
   GROW(B_TOA, (size_t)(nbursts + 1) * sizeof(float));
-  if (soft) GROW(B_SOFT, (size_t)(nbursts + 1) * soft_pitch * sizeof(float));
+  if (soft) GROW(B_SOFT, (size_t)(nbursts + 1) * soft_pitch * soft_sz);
   GROW(B_EQP, demod_scratch_bytes(nbursts + 1));
-  cf *dRaw = dbuf<cf>(ctx, B_RAW), *dRes = dbuf<cf>(ctx, B_RES);
+  unsigned char *dRaw = dbuf<unsigned char>(ctx, B_RAW);
+  cf *dRes = dbuf<cf>(ctx, B_RES);
   uint8_t *dTsc = dbuf<uint8_t>(ctx, B_TSC);
   int32_t *dFlag = dbuf<int32_t>(ctx, B_FLAG);
   cf *dAmp = dbuf<cf>(ctx, B_AMP);
-  float *dToa = dbuf<float>(ctx, B_TOA), *dSoft = soft ? dbuf<float>(ctx, B_SOFT) : nullptr;
+  float *dToa = dbuf<float>(ctx, B_TOA);
+  unsigned char *dSoft = soft ? dbuf<unsigned char>(ctx, B_SOFT) : nullptr;
 
   const long long seg = 4000;                       // chunks per segment: 27.6 MB of raw samples
   const long long nseg = (nchunks + seg - 1) / seg;
@@ -728,11 +762,12 @@ int btsdsp_rx_stream_host(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nch
   for (long long s = 0; s < nseg; s++) {
     const long long c0 = s * seg, c1 = (c0 + seg < nchunks) ? c0 + seg : nchunks;
     cudaEvent_t evIn = ctx->events[2 * s], evK = ctx->events[2 * s + 1];
-    CK(cudaMemcpyAsync(dRaw + c0 * 864, raw + c0 * 864, (size_t)(c1 - c0) * 864 * sizeof(cf), cudaMemcpyHostToDevice,
-                       ctx->st_in));
+    CK(cudaMemcpyAsync(dRaw + c0 * 864 * in_sz, raw + c0 * 864 * in_sz, (size_t)(c1 - c0) * 864 * in_sz,
+                       cudaMemcpyHostToDevice, ctx->st_in));
     CK(cudaEventRecord(evIn, ctx->st_in));
     CK(cudaStreamWaitEvent(ctx->st, evIn, 0));
-    launch_resample_rx(ctx->T, dRaw + c0 * 864, c0 > 0, c1 - c0, dRes + c0 * 585, ctx->st);
+    if (i16) launch_resample_rx_i16((const int16_t *)(dRaw + c0 * 864 * in_sz), swap_iq, c0 > 0, c1 - c0, dRes + c0 * 585, ctx->st);
+    else launch_resample_rx(ctx->T, (const cf *)(dRaw + c0 * 864 * in_sz), c0 > 0, c1 - c0, dRes + c0 * 585, ctx->st);
     // bursts wholly inside the samples resampled so far: groups of 4 slots = 625 samples
     long long avail = (c1 * 585 / 625) * 4;
     if (avail > nbursts || c1 == nchunks) avail = nbursts;
@@ -740,7 +775,9 @@ int btsdsp_rx_stream_host(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nch
     int nl = 1;
     if (nb > 0) {
       NormalOut o = {dFlag + done_bursts, dAmp + done_bursts, dToa + done_bursts, nullptr, nullptr, nullptr, nullptr,
-                     dSoft ? dSoft + done_bursts * soft_pitch : nullptr, soft_pitch};
+                     nullptr, soft_pitch};
+      if (dSoft && u8) o.soft_u8 = dSoft + done_bursts * soft_pitch;
+      else if (dSoft) o.soft = (float *)(dSoft + done_bursts * soft_pitch * soft_sz);
       nl = 1 + launch_demod_normal(ctx->T, make_src((const btsdsp_cf32 *)dRes, 0, nullptr, done_bursts, 1),
                                    dTsc + done_bursts, nb, detect_thr, gate_thr, snr_thr, o,
                                    dbuf<unsigned char>(ctx, B_EQP) + demod_scratch_bytes(done_bursts), ctx->st);
@@ -752,14 +789,28 @@ int btsdsp_rx_stream_host(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nch
       if (flag) CK(cudaMemcpyAsync(flag + done_bursts, dFlag + done_bursts, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->st_out));
       if (amp) CK(cudaMemcpyAsync(amp + done_bursts, dAmp + done_bursts, nb * sizeof(cf), cudaMemcpyDeviceToHost, ctx->st_out));
       if (toa) CK(cudaMemcpyAsync(toa + done_bursts, dToa + done_bursts, nb * sizeof(float), cudaMemcpyDeviceToHost, ctx->st_out));
-      if (soft) CK(cudaMemcpyAsync(soft + done_bursts * soft_pitch, dSoft + done_bursts * soft_pitch,
-                                   (size_t)nb * soft_pitch * sizeof(float), cudaMemcpyDeviceToHost, ctx->st_out));
+      if (soft) CK(cudaMemcpyAsync(soft + done_bursts * soft_pitch * soft_sz, dSoft + done_bursts * soft_pitch * soft_sz,
+                                   (size_t)nb * soft_pitch * soft_sz, cudaMemcpyDeviceToHost, ctx->st_out));
     }
     done_bursts = avail;
   }
   CK(cudaStreamSynchronize(ctx->st_out));
   CK(cudaStreamSynchronize(ctx->st));
   return BTSDSP_OK;
+}
+
+int btsdsp_rx_stream_host(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nchunks, const uint8_t *tsc,
+                          long long nbursts, float detect_thr, float gate_thr, float snr_thr, int32_t *flag,
+                          btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch) {
+  return rx_stream_host_impl(ctx, raw, 0, 0, nchunks, tsc, nbursts, detect_thr, gate_thr, snr_thr, flag, amp, toa, soft, 0,
+                             soft_pitch);
+}
+
+int btsdsp_rx_stream_wire_host(btsdsp_ctx *ctx, const int16_t *iq, int swap_iq, long long nchunks, const uint8_t *tsc,
+                               long long nbursts, float detect_thr, float gate_thr, float snr_thr, int32_t *flag,
+                               btsdsp_cf32 *amp, float *toa, uint8_t *soft_u8) {
+  return rx_stream_host_impl(ctx, iq, 1, swap_iq, nchunks, tsc, nbursts, detect_thr, gate_thr, snr_thr, flag, amp, toa,
+                             soft_u8, 1, 148);
 }
 
 int btsdsp_tx_stream_dev(btsdsp_ctx *ctx, const uint8_t *bits148, long long n, int16_t *out, void *stream) {

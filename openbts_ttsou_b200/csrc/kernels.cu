@@ -362,10 +362,17 @@ __device__ __forceinline__ void store_soft4(float *row, bool vec, int pitch, int
   }
 }
 
-template <int WARPS>
+// the wire format of the reference's RX datagram: (char) round(soft * 255.0) (Transceiver.cpp:669), 148 per burst
+__device__ __forceinline__ unsigned soft_u8(float s) { return (unsigned)(int)round((double)s * 255.0) & 0xffu; }
+
+// U8 = false: soft bits as float, row pitch soft_pitch floats.  U8 = true: soft bits as the datagram's bytes,
+// row pitch soft_pitch BYTES (a multiple of 4), 148 per burst.
+template <int WARPS, bool U8>
 __global__ void __launch_bounds__(WARPS * 32) k_equalize_fast(const DevTables *__restrict__ T, BurstSrc src, long long n,
-                                                              const EqParams *__restrict__ eqp, float *__restrict__ soft,
+                                                              const EqParams *__restrict__ eqp, void *__restrict__ soft_,
                                                               int soft_pitch) {
+  float *soft = reinterpret_cast<float *>(soft_);
+  unsigned char *soft8 = reinterpret_cast<unsigned char *>(soft_);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   cf *A = reinterpret_cast<cf *>(smem_raw) + (size_t)warp * kEqRows * kTileStride;
@@ -393,9 +400,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_equalize_fast(const DevTables *_
     }
   }
   float *row = soft + i * (long long)soft_pitch;
+  unsigned *row8 = reinterpret_cast<unsigned *>(soft8 + i * (long long)soft_pitch);
   const bool vec = ((reinterpret_cast<uintptr_t>(row) | (uintptr_t)(soft_pitch * 4)) & 15) == 0;
   if (!ok && lane < nv) {                       // undetected: the row is all zeros (written while the others equalise)
-    if (vec) for (int m = 0; m < soft_pitch; m += 4) *reinterpret_cast<float4 *>(row + m) = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
+    if (U8) for (int m = 0; m < soft_pitch / 4; m++) row8[m] = 0u;
+    else if (vec) for (int m = 0; m < soft_pitch; m += 4) *reinterpret_cast<float4 *>(row + m) = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
     else for (int m = 0; m < soft_pitch; m++) row[m] = 0.0F;
   }
   const unsigned okmask = __ballot_sync(0xffffffffu, ok);
@@ -445,10 +454,18 @@ __global__ void __launch_bounds__(WARPS * 32) k_equalize_fast(const DevTables *_
       float s4[4];
       if (__all_sync(okmask, eq.interior(m0 + 4))) eq.template step<false>(T, base, m0, ycur, s4);
       else eq.template step<true>(T, base, m0, ycur, s4);
-      store_soft4(row, vec, soft_pitch, m0, s4, len);
+      if (U8) {
+        if (m0 >= 0 && m0 + 3 < 148)
+          row8[m0 >> 2] = soft_u8(s4[0]) | (soft_u8(s4[1]) << 8) | (soft_u8(s4[2]) << 16) | (soft_u8(s4[3]) << 24);
+      } else {
+        store_soft4(row, vec, soft_pitch, m0, s4, len);
+      }
     }
   }
-  if (ok) for (int m = len; m < soft_pitch; m++) row[m] = 0.0F;
+  if (ok) {
+    if (U8) for (int m = 37; m < soft_pitch / 4; m++) row8[m] = 0u;
+    else for (int m = len; m < soft_pitch; m++) row[m] = 0.0F;
+  }
 }
 
 size_t demod_scratch_bytes(long long n) { return (size_t)n * sizeof(EqParams); }
@@ -460,16 +477,19 @@ int launch_demod_normal(const DevTables *T, BurstSrc src, const uint8_t *tsc, lo
                         cudaEvent_t between) {
   if (n <= 0) return 0;
   const long long nwarps = (n + 31) / 32;
-  EqParams *eqp = out.soft ? reinterpret_cast<EqParams *>(scratch) : nullptr;
+  EqParams *eqp = (out.soft || out.soft_u8) ? reinterpret_cast<EqParams *>(scratch) : nullptr;
   if (nwarps >= 148 * 8)
     k_detect_design<8><<<(unsigned)((nwarps + 7) / 8), 256, detect_smem<8>(), st>>>(T, src, tsc, n, detect_thr, gate_thr,
                                                                                  snr_thr, out, eqp);
   else
     k_detect_design<1><<<(unsigned)nwarps, 32, detect_smem<1>(), st>>>(T, src, tsc, n, detect_thr, gate_thr, snr_thr, out, eqp);
   if (between) cudaEventRecord(between, st);
-  if (!out.soft) return 1;
+  if (!out.soft && !out.soft_u8) return 1;
   // one-warp CTAs: 19 KB of shared memory each, 11 resident per SM
-  k_equalize_fast<1><<<(unsigned)nwarps, 32, equalize_smem<1>(), st>>>(T, src, n, eqp, out.soft, out.soft_pitch);
+  if (out.soft_u8)
+    k_equalize_fast<1, true><<<(unsigned)nwarps, 32, equalize_smem<1>(), st>>>(T, src, n, eqp, out.soft_u8, out.soft_pitch);
+  else
+    k_equalize_fast<1, false><<<(unsigned)nwarps, 32, equalize_smem<1>(), st>>>(T, src, n, eqp, out.soft, out.soft_pitch);
   return 2;
 }
 
@@ -683,7 +703,9 @@ int configure_kernels() {
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_detect_design<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<1>());
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(k_equalize_fast<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)equalize_smem<1>());
+  e = cudaFuncSetAttribute(k_equalize_fast<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)equalize_smem<1>());
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_equalize_fast<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)equalize_smem<1>());
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_analyze<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAnalyzeSmem);
   if (e != cudaSuccess) return (int)e;

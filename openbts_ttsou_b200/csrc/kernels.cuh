@@ -27,7 +27,8 @@ struct NormalOut {      // per burst; null pointers are skipped
   cf *w;                // [7] DFE feed-forward taps
   cf *b;                // [5] DFE feedback taps
   float *soft;          // [soft_pitch] soft bits, zeros when not detected
-  int soft_pitch;
+  int soft_pitch;       // floats (soft) or bytes (soft_u8)
+  unsigned char *soft_u8 = nullptr;   // alternative output: the RX datagram's bytes, round(soft*255), 148 per burst
 };
 
 constexpr int kTileStride = 33;      // complex samples between rows of a transposed tile (32 lanes + 1 pad)
@@ -60,6 +61,7 @@ void launch_design_dfe_generic(const cf *chan, int nchan, float snr, int nf, cf 
 void launch_modulate(const DevTables *T, const uint8_t *bits, int nbits, long long nbursts, int guard_rule,
                      const uint8_t *guards, long long first, cf *out, long long pitch, cudaStream_t st);
 void launch_resample_rx(const DevTables *T, const cf *in, int has_history, long long nchunks, cf *out, cudaStream_t st);
+int launch_resample_rx_i16(const int16_t *in, int swap_iq, int has_history, long long nchunks, cf *out, cudaStream_t st);
 void launch_resample_tx(const DevTables *T, const cf *in, int has_history, long long nchunks, int16_t *out,
                         cudaStream_t st);
 size_t demod_scratch_bytes(long long n);   // per-launch scratch of launch_demod_normal (EqParams records)

@@ -78,14 +78,25 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, bool
   const int n = valid ? 8 : 0;
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
 }
+__device__ __forceinline__ void cp_async16z(void *smem_dst, const void *gsrc, bool valid) {  // zero-fills when !valid
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 constexpr size_t kRxV2Smem = (size_t)(kRxTileIn + kRxTileOut) * sizeof(cf);
 
-__global__ void __launch_bounds__(64) k_resample_rx_v2(const cf *__restrict__ in, int has_history, long long nperiods,
-                                                       long long nsamples, cf *__restrict__ out) {
+// I16 = the radio's own sample format: interleaved int16 {I,Q} pairs (4 B per sample, `swap_iq` for the Q-first
+// order of real USRP hardware), converted exactly as unUSRPifyVector does (radioInterface.cpp:91-116) while the
+// tile is built -- the raw samples land in the (still unused) output tile via cp.async and are expanded to float.
+template <bool I16>
+__global__ void __launch_bounds__(64) k_resample_rx_v2(const void *__restrict__ in_, int has_history, int swap_iq,
+                                                       long long nperiods, long long nsamples, cf *__restrict__ out) {
+  const cf *in = reinterpret_cast<const cf *>(in_);
+  const short2 *in16 = reinterpret_cast<const short2 *>(in_);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf *xt = reinterpret_cast<cf *>(smem_raw);
   cf *ot = xt + kRxTileIn;
@@ -97,18 +108,42 @@ __global__ void __launch_bounds__(64) k_resample_rx_v2(const cf *__restrict__ in
     //      in flight at once); samples outside [lo, nsamples) are zero-filled by the copy's src-size operand
     const long long lo = has_history ? -192 : 0;
     __syncthreads();                                                    // previous tile fully written back
-    for (int i4 = threadIdx.x; i4 < kRxTileRows * 48; i4 += 64) {
-      const int row = i4 / 48, c4 = i4 - row * 48;
-      const long long s = raw0 + (long long)row * 96 + 2 * c4;
-      cf *dst = xt + row * kRxRowPitch + 2 * c4;
-      if (s >= lo && s + 1 < nsamples) cp_async16(dst, in + s);
-      else {
-        cp_async8(dst, in + (s >= lo && s < nsamples ? s : 0), s >= lo && s < nsamples);
-        cp_async8(dst + 1, in + (s + 1 >= lo && s + 1 < nsamples ? s + 1 : 0), s + 1 >= lo && s + 1 < nsamples);
+    if (!I16) {
+      for (int i4 = threadIdx.x; i4 < kRxTileRows * 48; i4 += 64) {
+        const int row = i4 / 48, c4 = i4 - row * 48;
+        const long long s = raw0 + (long long)row * 96 + 2 * c4;
+        cf *dst = xt + row * kRxRowPitch + 2 * c4;
+        if (s >= lo && s + 1 < nsamples) cp_async16(dst, in + s);
+        else {
+          cp_async8(dst, in + (s >= lo && s < nsamples ? s : 0), s >= lo && s < nsamples);
+          cp_async8(dst + 1, in + (s + 1 >= lo && s + 1 < nsamples ? s + 1 : 0), s + 1 >= lo && s + 1 < nsamples);
+        }
       }
+      cp_async_wait_all();
+      __syncthreads();
+    } else {
+      // raw0, lo and nsamples are multiples of 4 samples, so every 16-byte group is wholly inside or outside
+      short2 *stage = reinterpret_cast<short2 *>(ot);
+      for (int i = threadIdx.x; i < kRxTileRows * 24; i += 64) {
+        const long long s = raw0 + 4LL * i;
+        const bool valid = s >= lo && s < nsamples;
+        cp_async16z(stage + 4 * i, in16 + (valid ? s : 0), valid);
+      }
+      cp_async_wait_all();
+      __syncthreads();
+      for (int i = threadIdx.x; i < kRxTileRows * 24; i += 64) {
+        const int row = i / 24, c = 4 * (i - row * 24);
+        const int4 v = *reinterpret_cast<const int4 *>(stage + 4 * i);
+        const int w[4] = {v.x, v.y, v.z, v.w};
+        cf *dst = xt + row * kRxRowPitch + c;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const float a = (float)(short)(w[k] & 0xffff), b = (float)(short)(w[k] >> 16);     // first, second int16
+          dst[k] = swap_iq ? mk(b, a) : mk(a, b);
+        }
+      }
+      __syncthreads();
     }
-    cp_async_wait_all();
-    __syncthreads();
     // ---- 65 phases for this lane's period
     const long long G = G0 + lane;
     const bool q8 = (G % 9) == 8;
@@ -139,14 +174,25 @@ void launch_resample_rx(const DevTables *T, const cf *in, int has_history, long 
   if (aligned) {
     const long long nperiods = nchunks * 9, ntiles = (nperiods + 31) / 32;
     const unsigned grid = (unsigned)(ntiles < 148 * 5 * 8 ? ntiles : 148 * 5 * 8);
-    k_resample_rx_v2<<<grid, 64, kRxV2Smem, st>>>(in, has_history, nperiods, nchunks * 864, out);
+    k_resample_rx_v2<false><<<grid, 64, kRxV2Smem, st>>>(in, has_history, 0, nperiods, nchunks * 864, out);
   } else {
     const unsigned grid = (unsigned)(nchunks < 148 * 32 ? nchunks : 148 * 32);
     k_resample_rx<<<grid, 256, 0, st>>>(T, in, has_history, nchunks, out);
   }
 }
+// int16 {I,Q} ingest (the radio's format); `in` must be 16-byte aligned
+int launch_resample_rx_i16(const int16_t *in, int swap_iq, int has_history, long long nchunks, cf *out, cudaStream_t st) {
+  if (nchunks <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return -1;
+  const long long nperiods = nchunks * 9, ntiles = (nperiods + 31) / 32;
+  const unsigned grid = (unsigned)(ntiles < 148 * 5 * 8 ? ntiles : 148 * 5 * 8);
+  k_resample_rx_v2<true><<<grid, 64, kRxV2Smem, st>>>(in, has_history, swap_iq, nperiods, nchunks * 864, out);
+  return 1;
+}
 int configure_resamplers() {
-  return (int)cudaFuncSetAttribute(k_resample_rx_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRxV2Smem);
+  cudaError_t e = cudaFuncSetAttribute(k_resample_rx_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRxV2Smem);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaFuncSetAttribute(k_resample_rx_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRxV2Smem);
 }
 
 // TX: also applies the x13500 scaling and int16 truncation (tx_quantise).

@@ -241,6 +241,45 @@ def test_stream_end_to_end_host_roundtrip(dsp, oracle_best):
     assert flag.all() and ((soft > 0.5) == bits.astype(bool)).all()
 
 
+def test_wire_formats(dsp, oracle_best):
+    """int16 {I,Q} in (unUSRPifyVector, radioInterface.cpp:91-116) and 148 soft bytes out ((char) round(soft*255.0),
+    Transceiver.cpp:668-670): the wire-format entry points against the oracle fed the converted floats"""
+    import torch
+    rng = np.random.default_rng(0xC2F)
+    nb = 936 * 2
+    bits = np.stack([synth.normal_burst_bits(rng, 0) for _ in range(nb)])
+    iq = np.zeros((500 * 864, 2), np.int16)
+    dsp.tx_stream_host(bits, nb, iq)
+    iq = np.clip(iq + np.rint(300.0 * rng.standard_normal(iq.shape)), -32768, 32767).astype(np.int16)   # ADC noise
+    raw = (iq[:, 0].astype(np.float32) + 1j * iq[:, 1].astype(np.float32)).astype(np.complex64)
+    tsc = np.zeros(nb, np.uint8)
+    ref = oracle_best.rx_stream_demod(oracle_best.rx_resample_stream(raw, threads=4), nb, tsc, threads=8)
+    ref_u8 = np.floor(ref["soft"][:, :148].astype(np.float64) * 255.0 + 0.5).astype(np.uint8)   # C round() for x >= 0
+    for swap in (False, True):
+        src = np.ascontiguousarray(iq[:, ::-1] if swap else iq)
+        flag, amp, toa = np.zeros(nb, np.int32), np.zeros(nb, np.complex64), np.zeros(nb, np.float32)
+        u8 = np.zeros((nb, 148), np.uint8)
+        dsp.rx_stream_wire_host(src, 500, tsc, nb, flag, amp, toa, u8, swap_iq=swap)
+        same(flag, ref["flag"], "flag"); same(amp, ref["amp"], "amp"); same(toa, ref["toa"], "toa")
+        same(u8, ref_u8, "soft bytes (swap_iq=%s)" % swap)
+    assert flag.all() and ((u8 > 127) == bits.astype(bool)).all()
+    # device-level pieces
+    dev = torch.device("cuda:0")
+    d_iq = torch.from_numpy(iq.copy()).to(dev)
+    res = torch.zeros(500 * 585 * 2, device=dev)
+    dsp.resample_rx_i16_dev(d_iq, 500, res)
+    same(res.cpu().numpy().view(np.complex64), oracle_best.rx_resample_stream(raw, threads=4), "int16 ingest resample")
+    res2 = torch.zeros(400 * 585 * 2, device=dev)
+    dsp.resample_rx_i16_dev(d_iq[100 * 864:], 400, res2, has_history=True)
+    same(res2.cpu().numpy(), res.cpu().numpy()[100 * 585 * 2:], "int16 ingest with history")
+    d_flag = torch.zeros(nb, dtype=torch.int32, device=dev); d_amp = torch.zeros(nb * 2, device=dev)
+    d_toa = torch.zeros(nb, device=dev); d_u8 = torch.full((nb, 152), 7, dtype=torch.uint8, device=dev)
+    dsp.demod_normal_u8_dev(res, 0, torch.zeros(nb, dtype=torch.uint8, device=dev), nb, d_flag, d_amp, d_toa, d_u8, 152)
+    torch.cuda.synchronize()
+    same(d_u8.cpu().numpy()[:, :148], ref_u8, "u8 rows at pitch 152")
+    assert (d_u8.cpu().numpy()[:, 148:] == 0).all()
+
+
 def test_full_size_properties(dsp):
     """BASELINE config-2 scale without the oracle: 10^5-frame-class stream, size-independent properties --
     TX->RX round trip recovers every bit, every burst detected, TOA on the 1/512 grid, and the result does not
