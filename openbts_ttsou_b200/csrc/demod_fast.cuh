@@ -277,9 +277,11 @@ struct EqLane {
     }
   }
 
-  BTS_HD bool interior(int m0) const {                            // every F of block m0 is a sample of the delayed burst
+  // step(m0 - 4) may take the unchecked path: every F of block m0 is a sample of the delayed burst, and the block
+  // fed back in that step (m0 - 4) has five past decisions (m0 - 4 >= 8 keeps the EDGE feedback for the first blocks)
+  BTS_HD bool interior(int m0) const {
     const int x0 = m0 - io + 6;
-    return x0 >= 0 && x0 + 3 <= N - 1 && m0 + 6 >= 0 && m0 + 9 <= N - 1;
+    return x0 >= 0 && x0 + 3 <= N - 1 && m0 + 9 <= N - 1 && m0 - 4 >= 8;
   }
 
   // feed-forward outputs y[m0..m0+3] (consumes the window, then slides it by 4)
@@ -297,16 +299,20 @@ struct EqLane {
     for (int i = 0; i < 6; i++) Fw[i] = Fw[i + 4];
   }
 
-  // decision feedback + slicer for m = m0..m0+3 (:1367-1386); rot/revrot = the table entries for those m
+  // decision feedback + slicer for m = m0..m0+3 (:1367-1386); rot/revrot = the table entries for those m.
+  // EDGE = the block may contain m < 0 (pipeline priming) or m < 5 (fewer than five past decisions exist: the
+  // reference's `dBackPtr >= begin` test); every later block runs the branch-free form, which lets the compiler
+  // schedule this serial chain in the same basic block as the next block's feed-forward MACs.
+  template <bool EDGE>
   BTS_HD void feedback4(int m0, const cf y[4], const cf rot[4], const cf revrot[4], float soft[4]) {
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       const int m = m0 + r;
-      if (m < 0) { soft[r] = 0.0F; continue; }                    // pipeline priming blocks
+      if (EDGE && m < 0) { soft[r] = 0.0F; continue; }
       cf v = y[r];
 #pragma unroll
       for (int k = 0; k < 5; k++)
-        if (m - 1 - k >= 0) v = cadd(v, cmul(b[k], hist[k]));
+        if (!EDGE || m - 1 - k >= 0) v = cadd(v, cmul(b[k], hist[k]));
       const float out = BTS_SUB(BTS_MUL(v.x, revrot[r].x), BTS_MUL(v.y, revrot[r].y));   // real part of v * revrot[m]
 #pragma unroll
       for (int k = 4; k >= 1; k--) hist[k] = hist[k - 1];
@@ -327,7 +333,8 @@ struct EqLane {
     }
     cf ynext[4];
     compute_y<CHECKED>(base, m0 + 4, ynext);
-    feedback4(m0, ycur, rot, revrot, soft);
+    if (CHECKED && m0 < 8) feedback4<true>(m0, ycur, rot, revrot, soft);
+    else feedback4<false>(m0, ycur, rot, revrot, soft);
 #pragma unroll
     for (int r = 0; r < 4; r++) ycur[r] = ynext[r];
   }
