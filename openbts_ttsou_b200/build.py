@@ -46,6 +46,12 @@ def build(force=False, verbose=False):
         if r.returncode:
             raise RuntimeError("nvcc failed on %s" % src)
         objs.append(obj)
+    # parity fence: packed multiplies are used for code density, but a fused packed multiply-add would break the
+    # reference's separately-rounded arithmetic -- none may appear in any kernel
+    for obj in objs:
+        sass = subprocess.run([os.path.join(os.path.dirname(nvcc), "cuobjdump"), "-sass", obj], capture_output=True, text=True)
+        if sass.returncode == 0 and "FFMA2" in sass.stdout:
+            raise RuntimeError("%s contains FFMA2: a packed mul+add was fused, results would not be bit-exact" % obj)
     cmd = [nvcc, "-shared", "-cudart", "shared", "-o", LIB] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:

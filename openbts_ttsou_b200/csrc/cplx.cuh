@@ -32,12 +32,32 @@ BTS_HD cf mk(float r, float i) { return make_float2(r, i); }
 // Complex.h:79  operator+
 BTS_HD cf cadd(cf a, cf b) { return mk(BTS_ADD(a.x, b.x), BTS_ADD(a.y, b.y)); }
 BTS_HD cf csub(cf a, cf b) { return mk(BTS_SUB(a.x, b.x), BTS_SUB(a.y, b.y)); }
+// Packed products.  sm_100 has FMUL2 (mul.rn.f32x2): two independent, separately rounded binary32 products in one
+// instruction = bit-identical to two FMULs.  It issues at half rate, so it saves instruction BYTES (the unrolled
+// kernels are instruction-cache bound), not issue slots.  Its result must only feed SCALAR adds: ptxas 12.9 fuses
+// mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false (tools/microbench_fp32x2.cu); the build checks
+// that no FFMA2 was emitted.
+BTS_HD cf pmul(cf a, float s) {                 // (a.x*s, a.y*s)
+#ifdef __CUDA_ARCH__
+  unsigned long long pa, ps, pr;
+  cf r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ps) : "f"(s));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(pr) : "l"(pa), "l"(ps));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(pr));
+  return r;
+#else
+  return mk(a.x * s, a.y * s);
+#endif
+}
 // Complex.h:83  operator*(Complex): (r*a.r - i*a.i, r*a.i + i*a.r)
 BTS_HD cf cmul(cf a, cf b) {
-  return mk(BTS_SUB(BTS_MUL(a.x, b.x), BTS_MUL(a.y, b.y)), BTS_ADD(BTS_MUL(a.x, b.y), BTS_MUL(a.y, b.x)));
+  const cf t1 = pmul(a, b.x), t2 = pmul(a, b.y);        // (a.x*b.x, a.y*b.x), (a.x*b.y, a.y*b.y)
+  return mk(BTS_SUB(t1.x, t2.y), BTS_ADD(t2.x, t1.y));
 }
 // Complex.h:84  operator*(Real)
-BTS_HD cf cmulr(cf a, float s) { return mk(BTS_MUL(a.x, s), BTS_MUL(a.y, s)); }
+BTS_HD cf cmulr(cf a, float s) { return pmul(a, s); }
+BTS_HD cf cmulr_packed(cf a, float s) { return pmul(a, s); }
 // Complex.h:86  operator/(Real)
 BTS_HD cf cdivr(cf a, float s) { return mk(BTS_DIV(a.x, s), BTS_DIV(a.y, s)); }
 BTS_HD cf cconj(cf a) { return mk(a.x, -a.y); }

@@ -478,7 +478,7 @@ BTS_HD void rx_group(const float *__restrict__ taps, const cf *__restrict__ xl, 
     for (int k = 0; k < 15; k++) {
       if (k < rx_ntaps(r)) {
         const cf x = win[rx_c(r, k) - CLO];
-        cf p = cmulr(x, taps[r * 16 + k]);
+        cf p = cmulr_packed(x, taps[r * 16 + k]);
         if (k < rx_trunc(r)) {                                         // only phases 60..64: dropped in period q == 8
           p.x = q8 ? 0.0F : p.x;
           p.y = q8 ? 0.0F : p.y;

@@ -1,0 +1,74 @@
+#!/usr/bin/env python3
+"""Throughput of the kernels outside the headline bench (configs 3-5): RACH detect+demod, pitched normal-burst
+demod (1024 ARFCN x 8 TS per launch), GMSK modulate, TX resample.  Device-resident, CUDA events.  Measurement aid."""
+import json, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+import openbts_ttsou_b200 as pkg
+import synth
+
+dev = torch.device("cuda:0")
+dsp = pkg.BtsDsp(0, 1)
+st = torch.cuda.current_stream()
+
+
+def timeit(fn, reps=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(st)
+    for _ in range(reps):
+        fn()
+    b.record(st)
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+out = {}
+g = torch.Generator(device=dev); g.manual_seed(5)
+# --- TX: 936*64 bursts -> modulate -> TX resample
+nb = 936 * 256
+bits = torch.randint(0, 2, (nb, 148), generator=g, device=dev, dtype=torch.uint8)
+bits[:, 61:87] = torch.from_numpy(synth.bits_of(synth.TSC[0]).copy()).to(dev)
+stream = torch.zeros(nb // 4 * 625 * 2, device=dev)
+nch = nb // 4 * 625 // 585
+iq = torch.zeros(nch * 864 * 2, dtype=torch.int16, device=dev)
+ms = timeit(lambda: dsp.modulate_dev(bits, 148, nb, stream, 0, stream=st))
+out["modulate"] = {"bursts": nb, "ms": ms, "bursts_per_s": nb / ms * 1e3, "gbs": nb * 1398 / ms / 1e6}
+ms = timeit(lambda: dsp.resample_tx_dev(stream, nch, iq, stream=st))
+out["resample_tx"] = {"chunks": nch, "ms": ms, "burst_eq_per_s": nb / ms * 1e3, "gbs": nch * 8136 / ms / 1e6}
+# --- config 4: 8192 pitched bursts per launch (mixed TSC), from a stream demod of the TX signal re-cut to pitch 160
+raw = iq.to(torch.float32) + 400.0 * torch.randn(iq.numel(), generator=g, device=dev)
+res = torch.zeros(nch * 585 * 2, device=dev)
+dsp.resample_rx_dev(raw, nch, res, stream=st)
+torch.cuda.synchronize()
+n4 = 8192
+host = res.cpu().numpy().view(np.complex64)
+pitched = np.zeros((n4, 160), np.complex64)
+for i in range(n4):
+    o = (i // 4) * 625 + (0, 157, 313, 469)[i % 4]
+    pitched[i, :157 if i % 4 == 0 else 156] = host[o:o + (157 if i % 4 == 0 else 156)]
+dp = torch.from_numpy(pitched.view(np.float32).copy()).to(dev)
+tsc = torch.zeros(n4, dtype=torch.uint8, device=dev)
+flag = torch.zeros(n4, dtype=torch.int32, device=dev); amp = torch.zeros(n4 * 2, device=dev)
+toa = torch.zeros(n4, device=dev); soft = torch.zeros(n4 * 148, device=dev)
+ms = timeit(lambda: dsp.demod_normal_dev(dp, 160, tsc, n4, flag, amp, toa, soft, 148, stream=st), reps=50)
+out["demod_normal_8192_per_launch"] = {"bursts": n4, "ms": ms, "bursts_per_s": n4 / ms * 1e3, "detected": float(flag.float().mean())}
+# --- config 3: access bursts
+nr = 65536
+rb = torch.zeros(nr, 160, 2, device=dev)
+rbits = np.zeros(88, np.uint8); rbits[:8] = synth.bits_of(synth.RACH_EXT_TAIL); rbits[8:49] = synth.bits_of(synth.RACH_SYNC)
+x = dsp.modulate(rbits, 156 - 88)
+xr = torch.from_numpy(np.stack([x.real, x.imag], -1).astype(np.float32)).to(dev) * 1000.0
+rb[:, :156] = xr[None] + 100.0 * torch.randn(nr, 156, 2, generator=g, device=dev)
+rflag = torch.zeros(nr, dtype=torch.int32, device=dev); ramp = torch.zeros(nr * 2, device=dev)
+rtoa = torch.zeros(nr, device=dev); rsoft = torch.zeros(nr * 160, device=dev)
+ms = timeit(lambda: dsp.rach_dev(rb, 160, nr, rflag, ramp, rtoa, rsoft, 160, stream=st), reps=5)
+out["rach_detect_demod"] = {"bursts": nr, "ms": ms, "bursts_per_s": nr / ms * 1e3, "detected": float(rflag.float().mean()),
+                            "gbs": nr * 1272 / ms / 1e6}
+ms = timeit(lambda: dsp.rach_dev(rb, 160, nr, rflag, ramp, rtoa, None, 160, stream=st), reps=5)
+out["rach_detect_only"] = {"bursts": nr, "ms": ms, "bursts_per_s": nr / ms * 1e3}
+print(json.dumps(out, indent=1))
