@@ -231,9 +231,9 @@ void launch_modulate_impulse(const DevTables *T, const uint8_t *bits, int nbits,
 // normal-burst receive: energy gate -> analyzeTrafficBurst -> designDFE -> equalizeBurst
 // (reference Transceiver.cpp:298-396 with estimateChannel == true for every burst); sps == 1.
 // One burst per lane.  Two kernels so that each runs at the occupancy its working set allows:
-//   k_detect_design : stages only the 36-sample midamble window (+ the 20-sample energy-gate window), keeps the
-//                     correlation next to it (72 tile rows = 19 KB per warp, 8 warps per CTA share one
-//                     shared-memory copy of the sinc grid), and leaves {1/amp, TOA - offset, w[7], b[5]} per burst
+//   k_detect_design : stages only the 36-sample midamble window (the 20-sample energy-gate window first, when
+//                     gated), writes the correlation in place (45 tile rows = 12 KB per warp, 15 warps per CTA share
+//                     one shared-memory copy of the sinc grid), and leaves {1/amp, TOA - offset, w[7], b[5]} per burst
 //                     in an EqParams record;
 //   k_equalize_fast : streams the detected bursts, scaled by 1/amp on the way in, through a ROLLING 72-row tile
 //                     (19 KB per warp, re-staged every ~47 rows; 11 warps per SM) under the pipelined equaliser
@@ -256,7 +256,8 @@ struct __align__(16) EqParams {       // 28 floats = 112 B per burst
   cf b[5];
 };
 constexpr size_t kGridBytes = (size_t)kSincGrid * kGridPitch * sizeof(float);
-constexpr int kDetRows = 72;          // rows 0..35: burst samples 56..91; rows 36..71: correlation (gate window first)
+constexpr int kDetRows = 45;          // burst samples 56..91 in rows 9..44; the correlation is written IN PLACE to rows 0..35
+constexpr int kDetWin = 9;           // (output n only needs window samples >= n - 8, so row n is dead when c[n] is stored)
 constexpr size_t kDetTileBytes = (size_t)kDetRows * kTileStride * sizeof(cf);
 constexpr size_t kEqTileBytes = (size_t)kEqRows * kTileStride * sizeof(cf);
 template <int WARPS> constexpr size_t detect_smem() { return kGridBytes + WARPS * kDetTileBytes; }
@@ -282,6 +283,25 @@ __global__ void __launch_bounds__(WARPS * 32) k_detect_design(const DevTables *_
   int len = 0;
   if (lane < nv) burst_loc(src, i, &start, &len);
 
+  // ---- energy gate first (its 20-sample window shares the tile): stage, evaluate, then overwrite
+  bool pass = true;
+  if (gated) {
+    cf v[20];
+#pragma unroll
+    for (int it = 0; it < 20; it++) {
+      const int e = it * 32 + lane, j = e / 20, r = e - j * 20;
+      const long long sj = __shfl_sync(0xffffffffu, start, j);
+      v[it] = (j < nv) ? __ldg(src.base + sj + r) : mk(0.0F, 0.0F);
+    }
+#pragma unroll
+    for (int it = 0; it < 20; it++) {
+      const int e = it * 32 + lane, j = e / 20, r = e - j * 20;
+      A[r * kTileStride + j] = v[it];
+    }
+    __syncwarp();
+    if (lane < nv) pass = energy_detect<kTileStride>(View<kTileStride>{A + lane}, len, 20, gate_thr, nullptr);   // Transceiver.cpp:298
+    __syncwarp();
+  }
   // ---- staging: element e = it*32 + lane of the warp's nv x 36 window samples (burst e/36, sample 56 + e%36)
   {
     cf v[36];
@@ -294,20 +314,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_detect_design(const DevTables *_
 #pragma unroll
     for (int it = 0; it < 36; it++) {
       const int e = it * 32 + lane, j = e / 36, r = e - j * 36;
-      A[r * kTileStride + j] = v[it];
-    }
-    if (gated) {
-#pragma unroll
-      for (int it = 0; it < 20; it++) {
-        const int e = it * 32 + lane, j = e / 20, r = e - j * 20;
-        const long long sj = __shfl_sync(0xffffffffu, start, j);
-        v[it] = (j < nv) ? __ldg(src.base + sj + r) : mk(0.0F, 0.0F);
-      }
-#pragma unroll
-      for (int it = 0; it < 20; it++) {
-        const int e = it * 32 + lane, j = e / 20, r = e - j * 20;
-        A[(36 + r) * kTileStride + j] = v[it];
-      }
+      A[(kDetWin + r) * kTileStride + j] = v[it];
     }
   }
   __syncwarp();
@@ -318,9 +325,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_detect_design(const DevTables *_
   bool ok = false;
   cf amp = mk(0.0F, 0.0F), ia = mk(0.0F, 0.0F), chan[6], w[7], fb[5];
   float toa = 0.0F, off = 0.0F;
-  bool pass = true;
-  if (gated) pass = energy_detect<kTileStride>(a.at(36), len, 20, gate_thr, nullptr);           // Transceiver.cpp:298
-  if (pass) ok = analyze_fast<kTileStride>(g, T, a, a.at(36), tsc[i], detect_thr, &amp, &toa, chan, &off);
+  if (pass) ok = analyze_fast<kTileStride>(g, T, a.at(kDetWin), a, tsc[i], detect_thr, &amp, &toa, chan, &off);
   if (ok) {
     // Transceiver.cpp:340  SNRestimate = amplitude.norm2()/(thr*thr + 1.0)  (double division)
     const float SNR = (float)((double)cnorm2(amp) / ((double)BTS_MUL(snr_thr, snr_thr) + 1.0));
@@ -478,8 +483,8 @@ int launch_demod_normal(const DevTables *T, BurstSrc src, const uint8_t *tsc, lo
   if (n <= 0) return 0;
   const long long nwarps = (n + 31) / 32;
   EqParams *eqp = (out.soft || out.soft_u8) ? reinterpret_cast<EqParams *>(scratch) : nullptr;
-  if (nwarps >= 148 * 8)
-    k_detect_design<8><<<(unsigned)((nwarps + 7) / 8), 256, detect_smem<8>(), st>>>(T, src, tsc, n, detect_thr, gate_thr,
+  if (nwarps >= 148 * 15)
+    k_detect_design<15><<<(unsigned)((nwarps + 14) / 15), 480, detect_smem<15>(), st>>>(T, src, tsc, n, detect_thr, gate_thr,
                                                                                  snr_thr, out, eqp);
   else
     k_detect_design<1><<<(unsigned)nwarps, 32, detect_smem<1>(), st>>>(T, src, tsc, n, detect_thr, gate_thr, snr_thr, out, eqp);
@@ -699,7 +704,7 @@ void launch_equalize_generic(const DevTables *T, cf *burst, int n, float toa, co
 
 int configure_kernels() {
   cudaError_t e;
-  e = cudaFuncSetAttribute(k_detect_design<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<8>());
+  e = cudaFuncSetAttribute(k_detect_design<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<15>());
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_detect_design<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<1>());
   if (e != cudaSuccess) return (int)e;

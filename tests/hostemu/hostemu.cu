@@ -132,26 +132,41 @@ int emu_check_sinc_grid(void) {
 }
 
 // k_detect_design + k_equalize_fast (kernels.cu / demod_fast.cuh), warp by warp, lane by lane:
-// phase 1 on a 72-row tile (rows 0..35 = burst samples 56..91, rows 36..71 = correlation, gate window staged
-// into rows 36..55 first), phase 2 on a 160-row tile holding the detected bursts scaled by 1/amp.
+// phase 1 on a 45-row tile (burst samples 56..91 in rows 9..44, the correlation written in place to rows 0..35,
+// the energy-gate window staged into rows 0..19 and evaluated first), phase 2 on a 160-row tile holding the detected bursts scaled by 1/amp.
 void emu_demod_normal(const float *bursts, long long pitch, const int *lens, long long first, const uint8_t *tsc,
                       long long n, float detect_thr, float gate_thr, float snr_thr, int *flag, float *amp, float *toa,
                       float *soft, int soft_pitch, float *chan_o, float *off_o, float *w_o, float *b_o) {
   std::vector<float> gridv(kSincGrid * kGridPitch);
   for (int i = 0; i < kSincGrid * kGridPitch; i++) gridv[i] = T->sinc_grid[i / kGridPitch][i % kGridPitch];
   const Grid gsm{gridv.data(), kGridPitch}, ggl{&T->sinc_grid[0][0], 24};
-  std::vector<cf> tileA(72 * kTileStride), tileB(kEqRows * kTileStride);
+  std::vector<cf> tileA(45 * kTileStride), tileB(kEqRows * kTileStride);
   cf *A = tileA.data(), *B = tileB.data();
   const bool gated = gate_thr >= 0.0F;
   for (long long w0 = 0; w0 < n; w0 += 32) {
     const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
     for (size_t k = 0; k < tileA.size(); k++) A[k] = mk(1e30F, -1e30F);       // poison: catch reads of unstaged rows
+    bool passv[32];
+    for (int j = 0; j < 32; j++) passv[j] = true;
+    if (gated) {
+      for (int j = 0; j < nv; j++) {
+        long long start; int len;
+        burst_loc_h((const cf *)bursts, pitch, lens, first, 1, w0 + j, &start, &len);
+        const cf *g = (const cf *)bursts + start;
+        for (int i = 0; i < 20; i++) A[i * kTileStride + j] = g[i];
+      }
+      for (int j = 0; j < nv; j++) {
+        long long start; int len;
+        burst_loc_h((const cf *)bursts, pitch, lens, first, 1, w0 + j, &start, &len);
+        passv[j] = energy_detect<kTileStride>(View<kTileStride>{A + j}, len, 20, gate_thr, nullptr);
+      }
+      for (size_t k = 0; k < tileA.size(); k++) A[k] = mk(1e30F, -1e30F);
+    }
     for (int j = 0; j < nv; j++) {
       long long start; int len;
       burst_loc_h((const cf *)bursts, pitch, lens, first, 1, w0 + j, &start, &len);
       const cf *g = (const cf *)bursts + start;
-      for (int i = 0; i < 36; i++) A[i * kTileStride + j] = g[56 + i];
-      if (gated) for (int i = 0; i < 20; i++) A[(36 + i) * kTileStride + j] = g[i];
+      for (int i = 0; i < 36; i++) A[(9 + i) * kTileStride + j] = g[56 + i];
     }
     bool okv[32]; int lenv[32]; long long startv[32]; cf iav[32], wv[32][7], fbv[32][5]; float teq[32];
     for (int lane = 0; lane < nv; lane++) {
@@ -161,9 +176,8 @@ void emu_demod_normal(const float *bursts, long long pitch, const int *lens, lon
       const View<kTileStride> a{A + lane};
       cf ampv = mk(0.0F, 0.0F), ia = mk(0.0F, 0.0F), chan[6], w[7], fb[5];
       float tv = 0.0F, off = 0.0F;
-      bool pass = true, ok = false;
-      if (gated) pass = energy_detect<kTileStride>(a.at(36), len, 20, gate_thr, nullptr);
-      if (pass) ok = analyze_fast<kTileStride>(gsm, T, a, a.at(36), tsc[i], detect_thr, &ampv, &tv, chan, &off);
+      bool pass = passv[lane], ok = false;
+      if (pass) ok = analyze_fast<kTileStride>(gsm, T, a.at(9), a, tsc[i], detect_thr, &ampv, &tv, chan, &off);
       if (ok) {
         const float SNR = (float)((double)cnorm2(ampv) / ((double)BTS_MUL(snr_thr, snr_thr) + 1.0));
         ia = cdiv(mk(1.0F, 0.0F), ampv);
