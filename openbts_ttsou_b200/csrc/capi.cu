@@ -158,6 +158,7 @@ int build_tables(btsdsp_ctx *ctx) {
   }
   CK(cudaMemcpy(h, ctx->T, sizeof(DevTables), cudaMemcpyDeviceToHost));
   upload_resampler_taps(h);
+  if (sps == 1) upload_rach_taps(h);   // the tuned access-burst kernels are sps == 1 only; __constant__ data is per device
   CK(cudaGetLastError());
   return BTSDSP_OK;
 }
@@ -659,9 +660,10 @@ int btsdsp_rach_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch,
   DeviceGuard g(ctx->device);
   if (ctx->sps != 1) GROW(B_SCRATCH, (size_t)n * scratch_per_burst(ctx->sps) * sizeof(cf));
   NormalOut o = {flag, (cf *)amp, toa, nullptr, nullptr, nullptr, nullptr, soft, soft_pitch};
-  launch_rach(ctx->T, make_src(bursts, pitch, lens, first, ctx->sps), n, detect_thr, soft != nullptr, o,
-              dbuf<cf>(ctx, B_SCRATCH), 0, (cudaStream_t)stream);
-  LAUNCHED("rach", n > 0);
+  GROW(B_EQP, demod_scratch_bytes(n));
+  const int nl = launch_rach(ctx->T, make_src(bursts, pitch, lens, first, ctx->sps), n, detect_thr, soft != nullptr, o,
+                             dbuf<cf>(ctx, B_SCRATCH), 0, (cudaStream_t)stream, dbuf<void>(ctx, B_EQP));
+  LAUNCHED("rach", nl);
   return BTSDSP_OK;
 }
 

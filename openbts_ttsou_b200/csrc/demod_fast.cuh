@@ -346,4 +346,92 @@ BTS_HD bool eq_needs_restage(int base, int m0, int io_min, int io_max) {
   return (m0 - io_max < base) || (m0 - io_min + kEqLook >= base + kEqRows);
 }
 
+// ---- access bursts (sps == 1) -----------------------------------------------------------------------------------
+// correlate(burst, RACH sequence, NO_DELAY) (:867-869): c[n] = sum_{k=0..40} r[n+20-k] * tap[k], tap[k] =
+// conj(seq[40-k]), burst indices outside [0, N) not part of the vector.  Written IN PLACE: the burst sits in tile
+// rows 21..21+N-1 (rows 0..20 zero), c[n] goes to row n -- r[n-21] is dead by the time c[n] is stored.
+constexpr int kRachOff = 21;
+constexpr int kRachRows = 157 + kRachOff;                 // 178 rows = 47 KB per warp
+
+template <int S, bool CHECKED>
+BTS_HD void rach_corr4(View<S> t, int N, const cf *__restrict__ tap, int n0) {
+  cf acc[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) acc[r] = mk(0.0F, 0.0F);
+#pragma unroll
+  for (int j = 0; j < 44; j++) {
+    const int idx = n0 + 23 - j;                          // burst index, descending == ascending tap index
+    cf v;
+    if (CHECKED) v = ((unsigned)idx < (unsigned)N) ? t.ld(idx + kRachOff) : mk(0.0F, 0.0F);
+    else v = t.ld(idx + kRachOff);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int k = j + r - 3;                            // = (n0 + r + 20) - idx
+      if (k >= 0 && k <= 40) acc[r] = cadd(acc[r], cmul(v, tap[k]));
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++) if (n0 + r < N) t.st(n0 + r, acc[r]);
+}
+
+// detectRACHBurst (:860-914) with the correlation in place; `all_interior(n0)` tells whether every lane of the warp
+// can run block n0 unchecked (the kernel votes, the host emulation answers per lane)
+template <int S, class Vote>
+BTS_HD bool detect_rach_fast(Grid grid, const DevTables *__restrict__ T, View<S> t, int N, int nmax, float thr,
+                             const cf *__restrict__ tap, Vote all_interior, cf *amplitude, float *TOA) {
+  for (int n0 = 0; n0 < nmax; n0 += 4) {
+    // rows n0-20 .. n0+23 all inside the burst?  (rows below 0 read the zeroed pad rows, which is fine unchecked)
+    if (all_interior(n0 + 23 < N)) rach_corr4<S, false>(t, N, tap, n0);
+    else rach_corr4<S, true>(t, N, tap, n0);
+  }
+  float toa;
+  const cf pk = peak_detect_fast<S>(grid, t, N, &toa);
+  if ((toa < 0.0F) || (toa > (float)N)) { *amplitude = mk(0.0F, 0.0F); *TOA = toa; return false; }
+  const int p = (int)rintf(toa);
+  float valley = 0.0F, numSamples = 0.0F;
+  for (int i = 57; i <= 107; i++) {
+    if (p + i >= N) break;
+    valley = BTS_ADD(valley, cnorm2(t.ld(p + i)));
+    numSamples = numSamples + 1.0F;
+  }
+  if (numSamples < 2.0F) { *amplitude = mk(0.0F, 0.0F); *TOA = toa; return false; }
+  const float RMS = (float)((double)BTS_SQRT(BTS_DIV(valley, numSamples)) + 0.00001);
+  const float peakToMean = BTS_DIV(cabs_(pk), RMS);
+  *amplitude = cdiv(pk, T->rach_gain);
+  *TOA = BTS_SUB(BTS_SUB(toa, T->rach_toa), 8.0F);
+  return peakToMean > thr;
+}
+
+// demodulateBurst (:1056-1097) at sps == 1 as a stream over the rolling tile (the burst already scaled by
+// 1/channel).  The warp walks the FILTER index x in lockstep (rows x-10..x+13 are then the same for every lane,
+// whatever its TOA -- access-burst TOAs spread over the whole slot), and each lane places F[x] at its own output
+// m = x + io: soft[m] = slice(Re(revrot[m] * F[m - io])).  Outputs no x reaches are delayVector's zero fill:
+// slice(Re(revrot * 0)) = 0.5 exactly, which the caller pre-fills.
+template <int S>
+struct SlicerLane {
+  EqLane<S> f;          // reuses the fractional-delay block filter (newF4) and its tap/offset set-up
+  BTS_HD void init(Grid grid, const DevTables *__restrict__ T, View<S> tile, int n, float TOA) {
+    cf zw[7], zb[5];
+#pragma unroll
+    for (int k = 0; k < 7; k++) zw[k] = mk(0.0F, 0.0F);
+#pragma unroll
+    for (int k = 0; k < 5; k++) zb[k] = mk(0.0F, 0.0F);
+    f.init(grid, T, tile, n, TOA, zw, zb);
+  }
+  // F[x0..x0+3] -> soft[4] for outputs m = x0 + io + r; valid[r] tells which of them exist
+  BTS_HD void step(const DevTables *__restrict__ T, int base, int x0, float soft[4], bool valid[4]) {
+    cf d[4];
+    f.template newF4<false>(base, x0, d);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int x = x0 + r, m = x + f.io;
+      valid[r] = (unsigned)x < (unsigned)f.N && (unsigned)m < (unsigned)f.N;
+      const cf rr = T->revrot[valid[r] ? m : 0];
+      soft[r] = soft_slice(BTS_SUB(BTS_MUL(rr.x, d[r].x), BTS_MUL(rr.y, d[r].y)));     // Re(revrot[m] * D[m]) :232-264
+    }
+  }
+};
+// rows step(x0) reads: x0 - 10 .. x0 + 13 (the same for every lane)
+BTS_HD bool slicer_needs_restage(int base, int x0) { return x0 + 13 >= base + kEqRows; }
+
 }  // namespace btsdsp

@@ -551,6 +551,134 @@ int launch_analyze(const DevTables *T, BurstSrc src, const uint8_t *tsc, long lo
 }
 
 // ------------------------------------------------------------------------------------------------
+// access bursts, sps == 1, tuned: k_rach_detect (detectRACHBurst, one burst per lane, 157 x 41 correlation
+// register-blocked and written in place over the burst: 178-row tile = 47 KB per warp, taps warp-uniform from
+// __constant__ memory) then k_slicer_fast (demodulateBurst as a stream over the rolling tile).
+// ------------------------------------------------------------------------------------------------
+__constant__ cf c_rach_taps[41];                  // conj(rach_seq[40-k]) (:474-503)
+constexpr size_t kRachTileBytes = (size_t)kRachRows * kTileStride * sizeof(cf);
+
+struct WarpVote {
+  unsigned mask;
+  __device__ __forceinline__ bool operator()(bool x) const { return __all_sync(mask, x) != 0; }
+};
+
+__global__ void __launch_bounds__(32) k_rach_detect(const DevTables *__restrict__ T, BurstSrc src, long long n,
+                                                    float detect_thr, NormalOut out, EqParams *__restrict__ eqp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf *A = reinterpret_cast<cf *>(smem_raw);
+  const int lane = threadIdx.x;
+  const long long w0 = (long long)blockIdx.x * 32;
+  const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
+  const long long i = w0 + lane;
+  long long start = 0;
+  int len = 0;
+  if (lane < nv) { burst_loc(src, i, &start, &len); if (len > 157) len = 157; }
+  // ---- staging: zero pad rows 0..20, bursts (raw) in rows 21.., zeros past each burst's end; cp.async, all in flight
+  for (int r = lane; r < kRachOff * kTileStride; r += 32) A[r] = mk(0.0F, 0.0F);
+  for (int j = 0; j < nv; j++) {
+    const long long sj = __shfl_sync(0xffffffffu, start, j);
+    const int lj = __shfl_sync(0xffffffffu, len, j);
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      const int r = lane + 32 * k;
+      if (r < 157) cp_async8z(A + (kRachOff + r) * kTileStride + j, src.base + sj + (r < lj ? r : 0), r < lj);
+    }
+  }
+  cp_async_wait_all();
+  __syncwarp();
+  const unsigned active = __ballot_sync(0xffffffffu, lane < nv);
+  if (lane >= nv) return;
+  const int nmax = __reduce_max_sync(active, len);
+  cf amp = mk(0.0F, 0.0F);
+  float toa = 0.0F;
+  const bool ok = detect_rach_fast<kTileStride>(Grid{&T->sinc_grid[0][0], 24}, T, View<kTileStride>{A + lane}, len, nmax,
+                                                detect_thr, c_rach_taps, WarpVote{active}, &amp, &toa);
+  if (out.flag) out.flag[i] = ok ? 1 : 0;
+  if (out.amp) out.amp[i] = amp;
+  if (out.toa) out.toa[i] = toa;
+  if (eqp) {
+    const cf ia = ok ? cdiv(mk(1.0F, 0.0F), amp) : mk(0.0F, 0.0F);          // ((complex) 1.0)/channel :1066
+    reinterpret_cast<float4 *>(eqp + i)[0] = make_float4(ia.x, ia.y, toa, ok ? 1.0F : 0.0F);
+  }
+}
+
+__global__ void __launch_bounds__(32) k_slicer_fast(const DevTables *__restrict__ T, BurstSrc src, long long n,
+                                                    const EqParams *__restrict__ eqp, float *__restrict__ soft, int soft_pitch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf *A = reinterpret_cast<cf *>(smem_raw);
+  const int lane = threadIdx.x;
+  const long long w0 = (long long)blockIdx.x * 32;
+  const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
+  const long long i = w0 + lane;
+  long long start = 0;
+  int len = 0;
+  bool ok = false;
+  cf ia = mk(0.0F, 0.0F);
+  float toa = 0.0F;
+  if (lane < nv) {
+    burst_loc(src, i, &start, &len);
+    if (len > 157) len = 157;
+    const float4 q0 = __ldg(reinterpret_cast<const float4 *>(eqp + i));
+    ok = q0.w != 0.0F; ia = mk(q0.x, q0.y); toa = q0.z;
+  }
+  float *row = soft + i * (long long)soft_pitch;
+  if (lane < nv) {                              // not detected: zeros; detected: delayVector's zero fill slices to 0.5
+    for (int m = 0; m < soft_pitch; m++) row[m] = (ok && m < len) ? 0.5F : 0.0F;
+  }
+  const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+  if (okmask == 0) return;
+  SlicerLane<kTileStride> sl;
+  if (ok) sl.init(Grid{&T->sinc_grid[0][0], 24}, T, View<kTileStride>{A + lane}, len, toa);
+  const int nmax = __reduce_max_sync(0xffffffffu, ok ? len : 0);
+  int base = 0;
+  bool staged = false;
+  for (int x0 = 0; x0 < nmax; x0 += 4) {
+    if (!staged || slicer_needs_restage(base, x0)) {
+      base = x0 - 10;
+      staged = true;
+      __syncwarp();
+      for (unsigned rem = okmask; rem; rem &= rem - 1) {
+        const int j = __ffs(rem) - 1;
+        const long long sj = __shfl_sync(0xffffffffu, start, j);
+        const int lj = __shfl_sync(0xffffffffu, len, j);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const int tr = lane + 32 * k, r = base + tr;
+          if (tr < kEqRows) {
+            const bool valid = (unsigned)r < (unsigned)lj;
+            cp_async8z(A + tr * kTileStride + j, src.base + sj + (valid ? r : 0), valid);
+          }
+        }
+      }
+      cp_async_wait_all();
+      __syncwarp();
+      if (ok) {
+        const View<kTileStride> a{A + lane};
+#pragma unroll 8
+        for (int tr = 0; tr < kEqRows; tr++) a.st(tr, cmul(a.ld(tr), ia));           // scaleVector :1066
+      }
+    }
+    if (ok) {
+      float s4[4];
+      bool valid[4];
+      sl.step(T, base, x0, s4, valid);
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int m = x0 + r + sl.f.io;
+        if (valid[r] && m < soft_pitch) row[m] = s4[r];
+      }
+    }
+  }
+}
+
+void upload_rach_taps(const DevTables *hostT) {
+  cf h[41];
+  for (int k = 0; k < 41; k++) h[k] = mk(hostT->rach_seq[40 - k].x, -hostT->rach_seq[40 - k].y);
+  cudaMemcpyToSymbol(c_rach_taps, h, sizeof h);
+}
+
+// ------------------------------------------------------------------------------------------------
 // access bursts: detectRACHBurst (+ demodulateBurst when demod != 0), Transceiver.cpp:360-389
 // ------------------------------------------------------------------------------------------------
 template <bool SM>
@@ -596,14 +724,17 @@ __global__ void __launch_bounds__(32) k_rach(const DevTables *__restrict__ T, Bu
 }
 constexpr size_t kRachSmem = (size_t)(2 * kBurstRows) * kTileStride * sizeof(cf);
 int launch_rach(const DevTables *T, BurstSrc src, long long n, float detect_thr, int demod, NormalOut out, cf *scratch,
-                int force_generic, cudaStream_t st) {
+                int force_generic, cudaStream_t st, void *eq_scratch) {
   if (n <= 0) return 0;
   const unsigned grid = (unsigned)((n + 31) / 32);
-  if (src.sps == 1 && !force_generic) {
-    k_rach<true><<<grid, 32, kRachSmem, st>>>(T, src, n, detect_thr, demod, out, scratch);
-  } else {
-    k_rach<false><<<grid, 32, 0, st>>>(T, src, n, detect_thr, demod, out, scratch);
+  if (src.sps == 1 && !force_generic && eq_scratch) {
+    EqParams *eqp = reinterpret_cast<EqParams *>(eq_scratch);
+    k_rach_detect<<<grid, 32, kRachTileBytes, st>>>(T, src, n, detect_thr, out, (demod && out.soft) ? eqp : nullptr);
+    if (!(demod && out.soft)) return 1;
+    k_slicer_fast<<<grid, 32, kEqTileBytes, st>>>(T, src, n, eqp, out.soft, out.soft_pitch);
+    return 2;
   }
+  k_rach<false><<<grid, 32, 0, st>>>(T, src, n, detect_thr, demod, out, scratch);
   return 1;
 }
 
@@ -714,7 +845,9 @@ int configure_kernels() {
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_analyze<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAnalyzeSmem);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(k_rach<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRachSmem);
+  e = cudaFuncSetAttribute(k_rach_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRachTileBytes);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_slicer_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEqTileBytes);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_equalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRachSmem);
   return (int)e;

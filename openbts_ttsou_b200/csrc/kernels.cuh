@@ -71,7 +71,8 @@ int launch_demod_normal(const DevTables *T, BurstSrc src, const uint8_t *tsc, lo
 int launch_analyze(const DevTables *T, BurstSrc src, const uint8_t *tsc, long long n, float detect_thr, int request,
                    NormalOut out, cf *scratch, int force_generic, cudaStream_t st);
 int launch_rach(const DevTables *T, BurstSrc src, long long n, float detect_thr, int demod, NormalOut out, cf *scratch,
-                int force_generic, cudaStream_t st);
+                int force_generic, cudaStream_t st, void *eq_scratch = nullptr);
+void upload_rach_taps(const DevTables *hostT);
 int launch_equalize(const DevTables *T, BurstSrc src, long long n, const float *toa, const cf *w, const cf *b,
                     float *soft, int soft_pitch, cf *burst_out, long long out_pitch, cudaStream_t st);
 int launch_demodulate(const DevTables *T, BurstSrc src, long long n, const cf *amp, const float *toa, float *soft,

@@ -244,40 +244,104 @@ void emu_demod_normal(const float *bursts, long long pitch, const int *lens, lon
   }
 }
 
-// k_rach<true> (sps 1, tiles) or k_rach<false> (any sps, global scratch)
+// tiles != 0: k_rach_detect + k_slicer_fast (sps 1, in-place correlation, rolling-tile slicer), warp by warp;
+// tiles == 0: k_rach<false> (any sps, global scratch)
+struct LaneVote { bool operator()(bool x) const { return x; } };
+
 void emu_rach(const float *bursts, long long pitch, const int *lens, long long first, long long n, float detect_thr,
               int sps, int tiles, int *flag, float *amp, float *toa, float *soft, int soft_pitch) {
-  std::vector<cf> tile(2 * kBurstRows * kTileStride), scratch(scratch_per_burst(sps));
-  cf *A = tile.data(), *B = A + kBurstRows * kTileStride;
-  for (long long i = 0; i < n; i++) {
-    long long start; int len;
-    burst_loc_h((const cf *)bursts, pitch, lens, first, sps, i, &start, &len);
-    const cf *src = (const cf *)bursts + start;
-    cf ampv = mk(0.0F, 0.0F);
-    float toav = 0.0F;
-    bool ok;
-    int ns = 0;
-    float *sp = soft + i * soft_pitch;
-    for (int m = 0; m < soft_pitch; m++) sp[m] = 0.0F;
-    if (tiles) {
-      const int lane = (int)(i & 31);
-      for (int m = 0; m < len; m++) A[m * kTileStride + lane] = src[m];
-      const View<kTileStride> a{A + lane}, b{B + lane};
-      ok = detect_rach<kTileStride, true>(T, a, len, detect_thr, 1, b, &ampv, &toav);
-      if (ok) {
-        ns = demodulate_burst<kTileStride, 2 * kTileStride>(T, a, len, 1, ampv, toav, b, (float *)(B + lane));
-        for (int m = 0; m < ns; m++) sp[m] = ((const float *)B)[(m * kTileStride + lane) * 2];
-      }
-    } else {
+  if (!tiles) {
+    std::vector<cf> scratch(scratch_per_burst(sps));
+    for (long long i = 0; i < n; i++) {
+      long long start; int len;
+      burst_loc_h((const cf *)bursts, pitch, lens, first, sps, i, &start, &len);
+      const cf *src = (const cf *)bursts + start;
+      cf ampv = mk(0.0F, 0.0F);
+      float toav = 0.0F;
+      float *sp = soft + i * soft_pitch;
+      for (int m = 0; m < soft_pitch; m++) sp[m] = 0.0F;
       cf *s = scratch.data();
       const View<1> corr{s}, x{s + 157 * sps};
-      ok = detect_rach<1, true>(T, View<1>{(cf *)src}, len, detect_thr, sps, corr, &ampv, &toav);
+      const bool ok = detect_rach<1, true>(T, View<1>{(cf *)src}, len, detect_thr, sps, corr, &ampv, &toav);
       if (ok) {
         for (int m = 0; m < len; m++) x.st(m, src[m]);
-        ns = demodulate_burst<1, 1>(T, x, len, sps, ampv, toav, corr, sp);
+        demodulate_burst<1, 1>(T, x, len, sps, ampv, toav, corr, sp);
+      }
+      flag[i] = ok; amp[2 * i] = ampv.x; amp[2 * i + 1] = ampv.y; toa[i] = toav;
+    }
+    return;
+  }
+  const Grid ggl{&T->sinc_grid[0][0], 24};
+  cf taps[41];
+  for (int k = 0; k < 41; k++) taps[k] = mk(T->rach_seq[40 - k].x, -T->rach_seq[40 - k].y);
+  std::vector<cf> tileA(kRachRows * kTileStride), tileB(kEqRows * kTileStride);
+  cf *A = tileA.data(), *B = tileB.data();
+  for (long long w0 = 0; w0 < n; w0 += 32) {
+    const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
+    for (size_t k = 0; k < tileA.size(); k++) A[k] = mk(1e30F, -1e30F);
+    for (int r = 0; r < kRachOff * kTileStride; r++) A[r] = mk(0.0F, 0.0F);
+    long long startv[32]; int lenv[32]; bool okv[32]; cf iav[32]; float toav[32];
+    for (int j = 0; j < nv; j++) {
+      burst_loc_h((const cf *)bursts, pitch, lens, first, 1, w0 + j, &startv[j], &lenv[j]);
+      if (lenv[j] > 157) lenv[j] = 157;
+      const cf *g = (const cf *)bursts + startv[j];
+      for (int r = 0; r < 157; r++) A[(kRachOff + r) * kTileStride + j] = r < lenv[j] ? g[r] : mk(0.0F, 0.0F);
+    }
+    int nmax = 0;
+    for (int j = 0; j < nv; j++) nmax = lenv[j] > nmax ? lenv[j] : nmax;
+    for (int lane = 0; lane < nv; lane++) {
+      const long long i = w0 + lane;
+      cf ampv = mk(0.0F, 0.0F);
+      float tv = 0.0F;
+      okv[lane] = detect_rach_fast<kTileStride>(ggl, T, View<kTileStride>{A + lane}, lenv[lane], nmax, detect_thr, taps,
+                                                LaneVote(), &ampv, &tv);
+      flag[i] = okv[lane]; amp[2 * i] = ampv.x; amp[2 * i + 1] = ampv.y; toa[i] = tv;
+      iav[lane] = okv[lane] ? cdiv(mk(1.0F, 0.0F), ampv) : mk(0.0F, 0.0F);
+      toav[lane] = tv;
+      float *row = soft + i * soft_pitch;
+      for (int m = 0; m < soft_pitch; m++) row[m] = 0.0F;
+    }
+    // slicer: the warp walks the filter index x0; each lane writes at its own m = x + io
+    SlicerLane<kTileStride> sl[32];
+    int nm = 0;
+    bool any = false;
+    for (int lane = 0; lane < nv; lane++) {
+      if (!okv[lane]) continue;
+      any = true;
+      sl[lane].init(ggl, T, View<kTileStride>{B + lane}, lenv[lane], toav[lane]);
+      nm = lenv[lane] > nm ? lenv[lane] : nm;
+      float *row = soft + (w0 + lane) * soft_pitch;
+      for (int m = 0; m < soft_pitch; m++) row[m] = m < lenv[lane] ? 0.5F : 0.0F;
+    }
+    if (!any) continue;
+    int base = 0;
+    bool staged = false;
+    for (int x0 = 0; x0 < nm; x0 += 4) {
+      if (!staged || slicer_needs_restage(base, x0)) {
+        base = x0 - 10;
+        staged = true;
+        for (size_t k = 0; k < tileB.size(); k++) B[k] = mk(1e30F, -1e30F);
+        for (int j = 0; j < nv; j++) {
+          if (!okv[j]) continue;
+          const cf *g = (const cf *)bursts + startv[j];
+          for (int tr = 0; tr < kEqRows; tr++) {
+            const int r = base + tr;
+            B[tr * kTileStride + j] = cmul(((unsigned)r < (unsigned)lenv[j]) ? g[r] : mk(0.0F, 0.0F), iav[j]);
+          }
+        }
+      }
+      for (int lane = 0; lane < nv; lane++) {
+        if (!okv[lane]) continue;
+        float s4[4];
+        bool valid[4];
+        sl[lane].step(T, base, x0, s4, valid);
+        float *row = soft + (w0 + lane) * soft_pitch;
+        for (int r = 0; r < 4; r++) {
+          const int m = x0 + r + sl[lane].f.io;
+          if (valid[r] && m < soft_pitch) row[m] = s4[r];
+        }
       }
     }
-    flag[i] = ok; amp[2 * i] = ampv.x; amp[2 * i + 1] = ampv.y; toa[i] = toav;
   }
 }
 

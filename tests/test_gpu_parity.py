@@ -158,7 +158,9 @@ def test_normal_batch_edge_cases(dsp, oracle_best):
     same(gate["soft"], ref["soft"] * eg[:, None], "energy gate soft")
 
 
-def test_rach_batch(dsp, oracle_best):
+def test_rach_batch(dsp, dsp4, oracle_best):
+    # dsp4 (an sps = 4 context on the same device) exists by now: per-device __constant__ tables must not be clobbered
+    assert dsp4.sps == 4
     g = golden("rach_sps1.npz")
     r = dsp.rach_host(g["bursts"], g["lens"])
     check_batch(r, g, ("amp", "toa", "soft"))
