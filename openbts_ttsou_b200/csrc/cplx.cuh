@@ -36,7 +36,7 @@ BTS_HD cf csub(cf a, cf b) { return mk(BTS_SUB(a.x, b.x), BTS_SUB(a.y, b.y)); }
 // instruction = bit-identical to two FMULs.  It issues at half rate, so it saves instruction BYTES (the unrolled
 // kernels are instruction-cache bound), not issue slots.  Its result must only feed SCALAR adds: ptxas 12.9 fuses
 // mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false (tools/microbench_fp32x2.cu); the build checks
-// that no FFMA2 was emitted.
+// that no FFMA2 with a live addend was emitted (see pmul0 below for the one allowed form).
 BTS_HD cf pmul(cf a, float s) {                 // (a.x*s, a.y*s)
 #ifdef __CUDA_ARCH__
   unsigned long long pa, ps, pr;
@@ -48,6 +48,39 @@ BTS_HD cf pmul(cf a, float s) {                 // (a.x*s, a.y*s)
   return r;
 #else
   return mk(a.x * s, a.y * s);
+#endif
+}
+// Packed multiply-then-add for accumulating real-tap FIRs (sum += x * h) in TWO instructions per tap, still
+// with two roundings: the product is taken as fma.rn.f32x2(x, h, +0) -- an FFMA2 whose addend is the zero register,
+// which ptxas cannot merge with the add that follows (an FMA is not contractable) -- and accumulated with
+// add.rn.f32x2 (FADD2).  RN(x*h + 0) == RN(x*h) except that a -0 product becomes +0, and adding either zero to an
+// accumulator that started at +0 gives the same bits (such an accumulator is never -0), so sums are bit-identical
+// to the scalar mul-then-add.  The build accepts FFMA2 only in this zero-addend form.
+BTS_HD cf pmul0(cf a, float s) {                // (a.x*s, a.y*s); a -0 product may come back as +0
+#ifdef __CUDA_ARCH__
+  unsigned long long pa, ps, pz, pr;
+  cf r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ps) : "f"(s));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(pz) : "f"(0.0F));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pr) : "l"(pa), "l"(ps), "l"(pz));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(pr));
+  return r;
+#else
+  return mk(a.x * s, a.y * s);
+#endif
+}
+BTS_HD cf padd(cf a, cf b) {                    // (a.x+b.x, a.y+b.y): only for sums fed by pmul0 or by loads
+#ifdef __CUDA_ARCH__
+  unsigned long long pa, pb, pr;
+  cf r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(pr) : "l"(pa), "l"(pb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(pr));
+  return r;
+#else
+  return mk(a.x + b.x, a.y + b.y);
 #endif
 }
 // Complex.h:83  operator*(Complex): (r*a.r - i*a.i, r*a.i + i*a.r)

@@ -87,32 +87,47 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-constexpr size_t kRxV2Smem = (size_t)(kRxTileIn + kRxTileOut) * sizeof(cf);
+#ifndef BTS_RXV2_WARPS
+#define BTS_RXV2_WARPS 4
+#endif
+#ifndef BTS_RXV2_TILES
+#define BTS_RXV2_TILES 2
+#endif
+// A CTA works on kRxV2Tiles consecutive 32-period tiles at once (one super-tile of 32*T + 2 input rows); warp w does
+// phase part w % kRxV2Warps of tile w / kRxV2Warps.  With kRxV2Warps = 4 the warps that share an SM sub-partition
+// (w % 4) all run the SAME quarter of the unrolled phase code, released together by the barrier, so they walk the
+// instruction stream in near lock-step and share its fetches.
+constexpr int kRxV2Warps = BTS_RXV2_WARPS, kRxV2Tiles = BTS_RXV2_TILES, kRxV2Threads = 32 * kRxV2Warps * kRxV2Tiles;
+constexpr int kRxV2Periods = 32 * kRxV2Tiles, kRxV2Rows = kRxV2Periods + 2;
+constexpr int kRxV2In = kRxV2Rows * kRxRowPitch, kRxV2Out = kRxV2Periods * kRxP;
+constexpr size_t kRxV2Smem = (size_t)(kRxV2In + kRxV2Out) * sizeof(cf);
+constexpr int kRxV2CtasPerSm = (int)(227 * 1024 / (kRxV2Smem + 1024)) < 2048 / kRxV2Threads ? (int)(227 * 1024 / (kRxV2Smem + 1024)) : 2048 / kRxV2Threads;
 
 // I16 = the radio's own sample format: interleaved int16 {I,Q} pairs (4 B per sample, `swap_iq` for the Q-first
 // order of real USRP hardware), converted exactly as unUSRPifyVector does (radioInterface.cpp:91-116) while the
 // tile is built -- the raw samples land in the (still unused) output tile via cp.async and are expanded to float.
 template <bool I16>
-__global__ void __launch_bounds__(64) k_resample_rx_v2(const void *__restrict__ in_, int has_history, int swap_iq,
+__global__ void __launch_bounds__(kRxV2Threads) k_resample_rx_v2(const void *__restrict__ in_, int has_history, int swap_iq,
                                                        long long nperiods, long long nsamples, cf *__restrict__ out) {
   const cf *in = reinterpret_cast<const cf *>(in_);
   const short2 *in16 = reinterpret_cast<const short2 *>(in_);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf *xt = reinterpret_cast<cf *>(smem_raw);
-  cf *ot = xt + kRxTileIn;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;      // two warps share a tile: each does half the phases
-  for (long long tile = blockIdx.x; tile * 32 < nperiods; tile += gridDim.x) {
-    const long long G0 = tile * 32;
+  cf *ot = xt + kRxV2In;
+  const int warp = threadIdx.x >> 5, part = warp % kRxV2Warps;
+  const int row = (warp / kRxV2Warps) * 32 + (threadIdx.x & 31);      // this lane's period within the super-tile
+  for (long long tile = blockIdx.x; tile * kRxV2Periods < nperiods; tile += gridDim.x) {
+    const long long G0 = tile * kRxV2Periods;
     const long long raw0 = 96 * G0 - 96;                               // tile origin: sample (G, r, k) sits at 96*l + ix_r - k - 96
     // ---- load 34 rows x 96 samples as 16-byte cp.async copies (global -> shared, no registers, all 51 per lane
     //      in flight at once); samples outside [lo, nsamples) are zero-filled by the copy's src-size operand
     const long long lo = has_history ? -192 : 0;
     __syncthreads();                                                    // previous tile fully written back
     if (!I16) {
-      for (int i4 = threadIdx.x; i4 < kRxTileRows * 48; i4 += 64) {
-        const int row = i4 / 48, c4 = i4 - row * 48;
-        const long long s = raw0 + (long long)row * 96 + 2 * c4;
-        cf *dst = xt + row * kRxRowPitch + 2 * c4;
+      for (int i4 = threadIdx.x; i4 < kRxV2Rows * 48; i4 += kRxV2Threads) {
+        const int rw = i4 / 48, c4 = i4 - rw * 48;
+        const long long s = raw0 + (long long)rw * 96 + 2 * c4;
+        cf *dst = xt + rw * kRxRowPitch + 2 * c4;
         if (s >= lo && s + 1 < nsamples) cp_async16(dst, in + s);
         else {
           cp_async8(dst, in + (s >= lo && s < nsamples ? s : 0), s >= lo && s < nsamples);
@@ -124,18 +139,18 @@ __global__ void __launch_bounds__(64) k_resample_rx_v2(const void *__restrict__ 
     } else {
       // raw0, lo and nsamples are multiples of 4 samples, so every 16-byte group is wholly inside or outside
       short2 *stage = reinterpret_cast<short2 *>(ot);
-      for (int i = threadIdx.x; i < kRxTileRows * 24; i += 64) {
+      for (int i = threadIdx.x; i < kRxV2Rows * 24; i += kRxV2Threads) {
         const long long s = raw0 + 4LL * i;
         const bool valid = s >= lo && s < nsamples;
         cp_async16z(stage + 4 * i, in16 + (valid ? s : 0), valid);
       }
       cp_async_wait_all();
       __syncthreads();
-      for (int i = threadIdx.x; i < kRxTileRows * 24; i += 64) {
-        const int row = i / 24, c = 4 * (i - row * 24);
+      for (int i = threadIdx.x; i < kRxV2Rows * 24; i += kRxV2Threads) {
+        const int rw = i / 24, c = 4 * (i - rw * 24);
         const int4 v = *reinterpret_cast<const int4 *>(stage + 4 * i);
         const int w[4] = {v.x, v.y, v.z, v.w};
-        cf *dst = xt + row * kRxRowPitch + c;
+        cf *dst = xt + rw * kRxRowPitch + c;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           const float a = (float)(short)(w[k] & 0xffff), b = (float)(short)(w[k] >> 16);     // first, second int16
@@ -145,22 +160,178 @@ __global__ void __launch_bounds__(64) k_resample_rx_v2(const void *__restrict__ 
       __syncthreads();
     }
     // ---- 65 phases for this lane's period
-    const long long G = G0 + lane;
+    const long long G = G0 + row;
     const bool q8 = (G % 9) == 8;
-    const cf *xl = xt + lane * kRxRowPitch;
-    cf *ol = ot + lane * kRxP;
-    if (warp == 0) rx_half<0>(c_rx_poly, xl, ol, q8);
-    else rx_half<1>(c_rx_poly, xl, ol, q8);
+    const cf *xl = xt + row * kRxRowPitch;
+    cf *ol = ot + row * kRxP;
+    rx_part<kRxV2Warps>(part, c_rx_poly, xl, ol, q8);
     __syncthreads();
     // ---- write the 32 x 65 outputs back: contiguous in both shared and global memory
-    const long long nvalid = (nperiods - G0 < 32 ? nperiods - G0 : 32) * kRxP;
+    const long long nvalid = (nperiods - G0 < kRxV2Periods ? nperiods - G0 : kRxV2Periods) * kRxP;
     cf *og = out + G0 * kRxP;
-    for (int i4 = threadIdx.x; i4 < kRxTileOut / 2; i4 += 64) {
+    for (int i4 = threadIdx.x; i4 < kRxV2Out / 2; i4 += kRxV2Threads) {
       if (2 * i4 + 1 < nvalid) *reinterpret_cast<float4 *>(og + 2 * i4) = *reinterpret_cast<const float4 *>(ot + 2 * i4);
       else if (2 * i4 < nvalid) og[2 * i4] = ot[2 * i4];
     }
   }
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// v3: one persistent CTA per SM, T tiles per step, software-pipelined.
+// v2 loses a third of its issue slots waiting for instruction fetches: the unrolled 65-phase body is ~60 KB and
+// five independent CTAs per SM walk it at unrelated places.  Here a CTA owns T consecutive tiles; warp w runs
+// phase quarter w % 4 of tile w / 4, so the warps of one SM sub-partition all run the SAME quarter and are released
+// together by the barrier -- they walk the code in near lock-step and share its fetches.  What the single CTA
+// loses in load/compute overlap is put back explicitly:
+//   float input : two input buffers; the cp.async loads of super-tile s+1 are in flight while s is computed;
+//   int16 input : the raw int16 rows of s+1 land in a staging buffer while s is computed, and are widened to
+//                 float (unUSRPifyVector, radioInterface.cpp:94-110) into the single float tile at the next step;
+//   output      : the finished 32T x 65 block is contiguous in shared AND global memory and leaves as ONE bulk
+//                 async copy (cp.async.bulk, issued by one thread) that overlaps the next step.
+// ------------------------------------------------------------------------------------------------
+template <bool I16, int T>
+struct RxV3 {
+  static constexpr int kPeriods = 32 * T, kRows = kPeriods + 2;
+  static constexpr int kIn = kRows * kRxRowPitch, kOut = kPeriods * kRxP;         // samples
+  static constexpr int kThreads = 128 * T;
+  static constexpr size_t kSmem = I16 ? (size_t)(kIn + kOut) * sizeof(cf) + (size_t)kRows * 96 * 4
+                                      : (size_t)(2 * kIn + kOut) * sizeof(cf);
+};
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigned bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\ncp.async.bulk.commit_group;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// issue (not wait for) the loads of the super-tile whose first raw sample is raw0
+template <int ROWS>
+__device__ __forceinline__ void rxv3_load_f32(cf *xt, const cf *__restrict__ in, long long raw0, long long lo, long long nsamples) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (raw0 >= lo && raw0 + (long long)ROWS * 96 <= nsamples) {                      // interior: no bounds tests
+    const cf *src = in + raw0;
+    for (int rw = warp; rw < ROWS; rw += nw) {
+      cp_async16(xt + rw * kRxRowPitch + 2 * lane, src + rw * 96 + 2 * lane);
+      if (lane < 16) cp_async16(xt + rw * kRxRowPitch + 64 + 2 * lane, src + rw * 96 + 64 + 2 * lane);
+    }
+  } else {
+    for (int i4 = threadIdx.x; i4 < ROWS * 48; i4 += blockDim.x) {
+      const int rw = i4 / 48, c4 = i4 - rw * 48;
+      const long long s = raw0 + (long long)rw * 96 + 2 * c4;
+      cf *dst = xt + rw * kRxRowPitch + 2 * c4;
+      if (s >= lo && s + 1 < nsamples) cp_async16(dst, in + s);
+      else {
+        cp_async8(dst, in + (s >= lo && s < nsamples ? s : 0), s >= lo && s < nsamples);
+        cp_async8(dst + 1, in + (s + 1 >= lo && s + 1 < nsamples ? s + 1 : 0), s + 1 >= lo && s + 1 < nsamples);
+      }
+    }
+  }
+}
+// raw0, lo and nsamples are multiples of 4 samples, so every 16-byte group of int16 pairs is wholly in or out
+template <int ROWS>
+__device__ __forceinline__ void rxv3_load_i16(short2 *stage, const short2 *__restrict__ in16, long long raw0, long long lo, long long nsamples) {
+  for (int i = threadIdx.x; i < ROWS * 24; i += blockDim.x) {
+    const long long s = raw0 + 4LL * i;
+    const bool valid = s >= lo && s < nsamples;
+    cp_async16z(stage + 4 * i, in16 + (valid ? s : 0), valid);
+  }
+}
+template <int ROWS>
+__device__ __forceinline__ void rxv3_widen(cf *xt, const short2 *stage, int swap_iq) {
+  for (int i = threadIdx.x; i < ROWS * 24; i += blockDim.x) {
+    const int rw = i / 24, c = 4 * (i - rw * 24);
+    const int4 v = *reinterpret_cast<const int4 *>(stage + 4 * i);
+    const int w[4] = {v.x, v.y, v.z, v.w};
+    cf *dst = xt + rw * kRxRowPitch + c;
+#pragma unroll
+    for (int k = 0; k < 4; k += 2) {
+      const float a0 = (float)(short)(w[k] & 0xffff), b0 = (float)(short)(w[k] >> 16);       // first, second int16
+      const float a1 = (float)(short)(w[k + 1] & 0xffff), b1 = (float)(short)(w[k + 1] >> 16);
+      *reinterpret_cast<float4 *>(dst + k) = swap_iq ? make_float4(b0, a0, b1, a1) : make_float4(a0, b0, a1, b1);
+    }
+  }
+}
+
+template <bool I16, int T>
+__global__ void __launch_bounds__(128 * T, 1) k_resample_rx_v3(const void *__restrict__ in_, int has_history, int swap_iq,
+                                                              long long nperiods, long long nsamples, cf *__restrict__ out) {
+  using C = RxV3<I16, T>;
+  const cf *in = reinterpret_cast<const cf *>(in_);
+  const short2 *in16 = reinterpret_cast<const short2 *>(in_);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf *ot = reinterpret_cast<cf *>(smem_raw);                             // output block first: 16-byte aligned for the bulk copy
+  cf *xbuf = ot + C::kOut;                                               // float: two input buffers; int16: one + staging
+  short2 *stage = reinterpret_cast<short2 *>(xbuf + C::kIn);
+  const int warp = threadIdx.x >> 5, part = warp & 3;
+  const int row = (warp >> 2) * 32 + (threadIdx.x & 31);                 // this lane's period within the super-tile
+  const long long lo = has_history ? -192 : 0;
+  const long long ntiles = (nperiods + C::kPeriods - 1) / C::kPeriods;
+  bool store_pending = false;
+  long long tile = blockIdx.x;
+  // prologue: loads of the first super-tile
+  if (tile < ntiles) {
+    const long long raw0 = 96 * tile * C::kPeriods - 96;                 // sample (G, r, k) sits at 96*l + ix_r - k - 96
+    if (I16) rxv3_load_i16<C::kRows>(stage, in16, raw0, lo, nsamples);
+    else rxv3_load_f32<C::kRows>(xbuf, in, raw0, lo, nsamples);
+  }
+  cp_async_commit();
+  for (int s = 0; tile < ntiles; tile += gridDim.x, s++) {
+    const long long G0 = tile * C::kPeriods;
+    const long long next = tile + gridDim.x;
+    cf *xt = xbuf;
+    if (I16) {
+      cp_async_wait_group<0>();
+      __syncthreads();                                                   // staging complete, previous compute done with xt
+      rxv3_widen<C::kRows>(xt, stage, swap_iq);
+      if (threadIdx.x == 0 && store_pending) bulk_store_wait_read();
+      __syncthreads();                                                   // xt ready, staging and ot free
+      if (next < ntiles) rxv3_load_i16<C::kRows>(stage, in16, 96 * next * C::kPeriods - 96, lo, nsamples);
+      cp_async_commit();
+    } else {
+      xt = xbuf + (s & 1) * C::kIn;
+      if (next < ntiles) rxv3_load_f32<C::kRows>(xbuf + ((s + 1) & 1) * C::kIn, in, 96 * next * C::kPeriods - 96, lo, nsamples);
+      cp_async_commit();
+      cp_async_wait_group<1>();                                          // this step's tile (the older group) has landed
+      if (threadIdx.x == 0 && store_pending) bulk_store_wait_read();
+      __syncthreads();                                                   // xt ready, ot free
+    }
+    // ---- this warp's quarter of the 65 phases for this lane's period
+    const long long G = G0 + row;
+    const bool q8 = (G % 9) == 8;
+    rx_part<4>(part, c_rx_poly, xt + row * kRxRowPitch, ot + row * kRxP, q8);
+    // ---- the 32T x 65 outputs are contiguous in shared and global memory
+    const long long nvalid = (nperiods - G0 < C::kPeriods ? nperiods - G0 : C::kPeriods) * kRxP;
+    cf *og = out + G0 * kRxP;
+    if (nvalid == C::kOut) {
+      fence_async_smem();
+      __syncthreads();                                                   // all outputs written; all reads of xt done
+      if (threadIdx.x == 0) bulk_store(og, ot, (unsigned)(C::kOut * sizeof(cf)));
+      store_pending = true;
+    } else {
+      __syncthreads();
+      for (int i = threadIdx.x; i < nvalid; i += blockDim.x) og[i] = ot[i];
+      store_pending = false;
+      __syncthreads();
+    }
+  }
+  cp_async_wait_group<0>();
+  if (threadIdx.x == 0 && store_pending) bulk_store_wait_all();
+}
+
+#ifndef BTS_RXV3_TILES_F32
+#define BTS_RXV3_TILES_F32 3
+#endif
+#ifndef BTS_RXV3_TILES_I16
+#define BTS_RXV3_TILES_I16 3
+#endif
+constexpr int kRxV3TilesF32 = BTS_RXV3_TILES_F32, kRxV3TilesI16 = BTS_RXV3_TILES_I16;
+static int g_num_sms = 148;
 
 void upload_resampler_taps(const DevTables *hostT) {
   float h[kRxP * 16];
@@ -172,9 +343,10 @@ void launch_resample_rx(const DevTables *T, const cf *in, int has_history, long 
   if (nchunks <= 0) return;
   const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
   if (aligned) {
-    const long long nperiods = nchunks * 9, ntiles = (nperiods + 31) / 32;
-    const unsigned grid = (unsigned)(ntiles < 148 * 5 * 8 ? ntiles : 148 * 5 * 8);
-    k_resample_rx_v2<false><<<grid, 64, kRxV2Smem, st>>>(in, has_history, 0, nperiods, nchunks * 864, out);
+    using C = RxV3<false, kRxV3TilesF32>;
+    const long long nperiods = nchunks * 9, ntiles = (nperiods + C::kPeriods - 1) / C::kPeriods;
+    const unsigned grid = (unsigned)(ntiles < g_num_sms ? ntiles : g_num_sms);
+    k_resample_rx_v3<false, kRxV3TilesF32><<<grid, C::kThreads, C::kSmem, st>>>(in, has_history, 0, nperiods, nchunks * 864, out);
   } else {
     const unsigned grid = (unsigned)(nchunks < 148 * 32 ? nchunks : 148 * 32);
     k_resample_rx<<<grid, 256, 0, st>>>(T, in, has_history, nchunks, out);
@@ -184,15 +356,21 @@ void launch_resample_rx(const DevTables *T, const cf *in, int has_history, long 
 int launch_resample_rx_i16(const int16_t *in, int swap_iq, int has_history, long long nchunks, cf *out, cudaStream_t st) {
   if (nchunks <= 0) return 0;
   if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return -1;
-  const long long nperiods = nchunks * 9, ntiles = (nperiods + 31) / 32;
-  const unsigned grid = (unsigned)(ntiles < 148 * 5 * 8 ? ntiles : 148 * 5 * 8);
-  k_resample_rx_v2<true><<<grid, 64, kRxV2Smem, st>>>(in, has_history, swap_iq, nperiods, nchunks * 864, out);
+  using C = RxV3<true, kRxV3TilesI16>;
+  const long long nperiods = nchunks * 9, ntiles = (nperiods + C::kPeriods - 1) / C::kPeriods;
+  const unsigned grid = (unsigned)(ntiles < g_num_sms ? ntiles : g_num_sms);
+  k_resample_rx_v3<true, kRxV3TilesI16><<<grid, C::kThreads, C::kSmem, st>>>(in, has_history, swap_iq, nperiods, nchunks * 864, out);
   return 1;
 }
 int configure_resamplers() {
-  cudaError_t e = cudaFuncSetAttribute(k_resample_rx_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRxV2Smem);
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) g_num_sms = sms;
+  cudaError_t e = cudaFuncSetAttribute(k_resample_rx_v3<false, kRxV3TilesF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)RxV3<false, kRxV3TilesF32>::kSmem);
   if (e != cudaSuccess) return (int)e;
-  return (int)cudaFuncSetAttribute(k_resample_rx_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRxV2Smem);
+  return (int)cudaFuncSetAttribute(k_resample_rx_v3<true, kRxV3TilesI16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)RxV3<true, kRxV3TilesI16>::kSmem);
 }
 
 // TX: also applies the x13500 scaling and int16 truncation (tx_quantise).

@@ -457,9 +457,8 @@ constexpr int kRxTileRows = 34, kRxRowPitch = 98;                      // sample
 constexpr int kRxTileIn = kRxTileRows * kRxRowPitch;                   // 3332 samples
 constexpr int kRxTileOut = 32 * kRxP;                                  // 2080 samples
 
-template <int R0>
+template <int R0, int NR = 5>
 BTS_HD void rx_group(const float *__restrict__ taps, const cf *__restrict__ xl, cf *__restrict__ ol, bool q8) {
-  constexpr int NR = 5;
   constexpr int CLO = (rx_c(R0, 14)) & ~1;                             // even-aligned lowest sample offset
   constexpr int CHI = rx_c(R0 + NR - 1, 0);
   constexpr int NP = (CHI - CLO) / 2 + 1;                              // 16-byte pairs
@@ -478,12 +477,12 @@ BTS_HD void rx_group(const float *__restrict__ taps, const cf *__restrict__ xl, 
     for (int k = 0; k < 15; k++) {
       if (k < rx_ntaps(r)) {
         const cf x = win[rx_c(r, k) - CLO];
-        cf p = cmulr_packed(x, taps[r * 16 + k]);
+        cf p = pmul0(x, taps[r * 16 + k]);
         if (k < rx_trunc(r)) {                                         // only phases 60..64: dropped in period q == 8
           p.x = q8 ? 0.0F : p.x;
           p.y = q8 ? 0.0F : p.y;
         }
-        sum = cadd(sum, p);
+        sum = padd(sum, p);
       }
     }
     ol[r] = sum;
@@ -507,6 +506,18 @@ BTS_HD void rx_half(const float *__restrict__ taps, const cf *__restrict__ xl, c
     rx_group<35>(taps, xl, ol, q8); rx_group<40>(taps, xl, ol, q8); rx_group<45>(taps, xl, ol, q8); rx_group<50>(taps, xl, ol, q8);
     rx_group<55>(taps, xl, ol, q8); rx_group<60>(taps, xl, ol, q8);
   }
+}
+// ... or across NW warps: warp w does phases [65 w / NW, 65 (w+1) / NW), cut into register-blocked groups of <= 6
+template <int A, int B>
+BTS_HD void rx_range(const float *__restrict__ taps, const cf *__restrict__ xl, cf *__restrict__ ol, bool q8) {
+  constexpr int n = B - A, ng = (n + 5) / 6, first = (n + ng - 1) / ng;
+  rx_group<A, first>(taps, xl, ol, q8);
+  if constexpr (n > first) rx_range<A + first, B>(taps, xl, ol, q8);
+}
+template <int NW, int W = 0>
+BTS_HD void rx_part(int warp, const float *__restrict__ taps, const cf *__restrict__ xl, cf *__restrict__ ol, bool q8) {
+  if (warp == W) rx_range<kRxP * W / NW, kRxP * (W + 1) / NW>(taps, xl, ol, q8);
+  else if constexpr (W + 1 < NW) rx_part<NW, W + 1>(warp, taps, xl, ol, q8);
 }
 // taps[r*16 + k] = lpf_rx[br_r + 65 k] from the [branch][k] table
 inline void rx_fill_taps(const DevTables *hostT, float *taps) {
