@@ -194,8 +194,8 @@ template <bool I16, int T>
 struct RxV3 {
   static constexpr int kPeriods = 32 * T, kRows = kPeriods + 2;
   static constexpr int kIn = kRows * kRxRowPitch, kOut = kPeriods * kRxP;         // samples
-  static constexpr int kThreads = 128 * T;
-  static constexpr size_t kSmem = I16 ? (size_t)(kIn + kOut) * sizeof(cf) + (size_t)kRows * 96 * 4
+  static constexpr int kThreads = 128 * T + 32;                                // 4T compute warps + the producer warp
+  static constexpr size_t kSmem = I16 ? (size_t)(kIn + kOut) * sizeof(cf) + (size_t)2 * kRows * 96 * 4
                                       : (size_t)(2 * kIn + kOut) * sizeof(cf);
 };
 
@@ -210,41 +210,71 @@ __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// issue (not wait for) the loads of the super-tile whose first raw sample is raw0
+// ---- mbarriers between the producer warp (cp.async loads) and the compute warps
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrives (without raising the expected count) once all of this thread's earlier cp.async copies have landed
+__device__ __forceinline__ void mbar_arrive_after_cp_async(unsigned long long *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(
+          smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+template <int NTHREADS>
+__device__ __forceinline__ void compute_warps_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
+
+// Producer warp: issue (not wait for) the loads of the super-tile whose first raw sample is raw0.
+// Samples outside [lo, nsamples) are zero-filled by the copies' src-size operand.
 template <int ROWS>
 __device__ __forceinline__ void rxv3_load_f32(cf *xt, const cf *__restrict__ in, long long raw0, long long lo, long long nsamples) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
   if (raw0 >= lo && raw0 + (long long)ROWS * 96 <= nsamples) {                      // interior: no bounds tests
-    const cf *src = in + raw0;
-    for (int rw = warp; rw < ROWS; rw += nw) {
-      cp_async16(xt + rw * kRxRowPitch + 2 * lane, src + rw * 96 + 2 * lane);
-      if (lane < 16) cp_async16(xt + rw * kRxRowPitch + 64 + 2 * lane, src + rw * 96 + 64 + 2 * lane);
+    const cf *src = in + raw0 + 2 * lane;
+    cf *dst = xt + 2 * lane;
+#pragma unroll 2
+    for (int rw = 0; rw < ROWS; rw++) {
+      cp_async16(dst + rw * kRxRowPitch, src + rw * 96);
+      if (lane < 16) cp_async16(dst + rw * kRxRowPitch + 64, src + rw * 96 + 64);
     }
   } else {
-    for (int i4 = threadIdx.x; i4 < ROWS * 48; i4 += blockDim.x) {
+    for (int i4 = lane; i4 < ROWS * 48; i4 += 32) {
       const int rw = i4 / 48, c4 = i4 - rw * 48;
       const long long s = raw0 + (long long)rw * 96 + 2 * c4;
-      cf *dst = xt + rw * kRxRowPitch + 2 * c4;
-      if (s >= lo && s + 1 < nsamples) cp_async16(dst, in + s);
-      else {
-        cp_async8(dst, in + (s >= lo && s < nsamples ? s : 0), s >= lo && s < nsamples);
-        cp_async8(dst + 1, in + (s + 1 >= lo && s + 1 < nsamples ? s + 1 : 0), s + 1 >= lo && s + 1 < nsamples);
-      }
+      const bool ok = s >= lo && s < nsamples;                                     // bounds are even: both samples or none
+      cp_async16z(xt + rw * kRxRowPitch + 2 * c4, in + (ok ? s : 0), ok);
     }
   }
 }
-// raw0, lo and nsamples are multiples of 4 samples, so every 16-byte group of int16 pairs is wholly in or out
 template <int ROWS>
-__device__ __forceinline__ void rxv3_load_i16(short2 *stage, const short2 *__restrict__ in16, long long raw0, long long lo, long long nsamples) {
-  for (int i = threadIdx.x; i < ROWS * 24; i += blockDim.x) {
-    const long long s = raw0 + 4LL * i;
-    const bool valid = s >= lo && s < nsamples;
-    cp_async16z(stage + 4 * i, in16 + (valid ? s : 0), valid);
+__device__ __forceinline__ void rxv3_load_i16(short2 *stage, const short2 *__restrict__ in16, long long raw0, long long lo,
+                                              long long nsamples) {
+  const int lane = threadIdx.x & 31;
+  if (raw0 >= lo && raw0 + (long long)ROWS * 96 <= nsamples) {
+    const short2 *src = in16 + raw0 + 4 * lane;
+    short2 *dst = stage + 4 * lane;
+#pragma unroll 4
+    for (int i = 0; i < ROWS * 24 / 32; i++) cp_async16(dst + 128 * i, src + 128 * i);
+    if (lane < ROWS * 24 % 32) cp_async16(dst + 128 * (ROWS * 24 / 32), src + 128 * (ROWS * 24 / 32));
+  } else {
+    for (int i = lane; i < ROWS * 24; i += 32) {
+      const long long s = raw0 + 4LL * i;
+      const bool ok = s >= lo && s < nsamples;
+      cp_async16z(stage + 4 * i, in16 + (ok ? s : 0), ok);
+    }
   }
 }
-template <int ROWS>
+template <int ROWS, int NTHREADS>
 __device__ __forceinline__ void rxv3_widen(cf *xt, const short2 *stage, int swap_iq) {
-  for (int i = threadIdx.x; i < ROWS * 24; i += blockDim.x) {
+  for (int i = threadIdx.x; i < ROWS * 24; i += NTHREADS) {
     const int rw = i / 24, c = 4 * (i - rw * 24);
     const int4 v = *reinterpret_cast<const int4 *>(stage + 4 * i);
     const int w[4] = {v.x, v.y, v.z, v.w};
@@ -259,68 +289,86 @@ __device__ __forceinline__ void rxv3_widen(cf *xt, const short2 *stage, int swap
 }
 
 template <bool I16, int T>
-__global__ void __launch_bounds__(128 * T, 1) k_resample_rx_v3(const void *__restrict__ in_, int has_history, int swap_iq,
-                                                              long long nperiods, long long nsamples, cf *__restrict__ out) {
+__global__ void __launch_bounds__(128 * T + 32, 1) k_resample_rx_v3(const void *__restrict__ in_, int has_history, int swap_iq,
+                                                                   long long nperiods, long long nsamples, cf *__restrict__ out) {
   using C = RxV3<I16, T>;
+  constexpr int NC = 128 * T;                                            // compute threads; warp 4T is the producer
   const cf *in = reinterpret_cast<const cf *>(in_);
   const short2 *in16 = reinterpret_cast<const short2 *>(in_);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf *ot = reinterpret_cast<cf *>(smem_raw);                             // output block first: 16-byte aligned for the bulk copy
-  cf *xbuf = ot + C::kOut;                                               // float: two input buffers; int16: one + staging
+  cf *xbuf = ot + C::kOut;                                               // float: two input buffers; int16: one + 2 staging
   short2 *stage = reinterpret_cast<short2 *>(xbuf + C::kIn);
-  const int warp = threadIdx.x >> 5, part = warp & 3;
-  const int row = (warp >> 2) * 32 + (threadIdx.x & 31);                 // this lane's period within the super-tile
+  __shared__ __align__(8) unsigned long long full[2], empty[2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long lo = has_history ? -192 : 0;
   const long long ntiles = (nperiods + C::kPeriods - 1) / C::kPeriods;
-  bool store_pending = false;
-  long long tile = blockIdx.x;
-  // prologue: loads of the first super-tile
-  if (tile < ntiles) {
-    const long long raw0 = 96 * tile * C::kPeriods - 96;                 // sample (G, r, k) sits at 96*l + ix_r - k - 96
-    if (I16) rxv3_load_i16<C::kRows>(stage, in16, raw0, lo, nsamples);
-    else rxv3_load_f32<C::kRows>(xbuf, in, raw0, lo, nsamples);
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 32);
+    mbar_init(&full[1], 32);
+    mbar_init(&empty[0], 4 * T);
+    mbar_init(&empty[1], 4 * T);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  cp_async_commit();
-  for (int s = 0; tile < ntiles; tile += gridDim.x, s++) {
+  __syncthreads();
+  if (warp == 4 * T) {
+    // ---- producer: keeps up to two super-tiles in flight ahead of the compute warps
+    int s = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, s++) {
+      const int b = s & 1;
+      if (s >= 2) mbar_wait(&empty[b], ((s >> 1) - 1) & 1);              // the compute warps are done with this buffer
+      const long long raw0 = 96 * tile * C::kPeriods - 96;               // sample (G, r, k) sits at 96*l + ix_r - k - 96
+      if (I16) rxv3_load_i16<C::kRows>(stage + b * (C::kRows * 96), in16, raw0, lo, nsamples);
+      else rxv3_load_f32<C::kRows>(xbuf + b * C::kIn, in, raw0, lo, nsamples);
+      mbar_arrive_after_cp_async(&full[b]);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    return;
+  }
+  // ---- compute warps: warp w runs phase quarter w % 4 of tile w / 4
+  const int part = warp & 3;
+  const int row = (warp >> 2) * 32 + lane;                               // this lane's period within the super-tile
+  bool store_pending = false;
+  int s = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, s++) {
     const long long G0 = tile * C::kPeriods;
-    const long long next = tile + gridDim.x;
+    const int b = s & 1;
     cf *xt = xbuf;
     if (I16) {
-      cp_async_wait_group<0>();
-      __syncthreads();                                                   // staging complete, previous compute done with xt
-      rxv3_widen<C::kRows>(xt, stage, swap_iq);
+      mbar_wait(&full[b], (s >> 1) & 1);                                 // raw int16 rows have landed
+      rxv3_widen<C::kRows, NC>(xt, stage + b * (C::kRows * 96), swap_iq);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[b]);
       if (threadIdx.x == 0 && store_pending) bulk_store_wait_read();
-      __syncthreads();                                                   // xt ready, staging and ot free
-      if (next < ntiles) rxv3_load_i16<C::kRows>(stage, in16, 96 * next * C::kPeriods - 96, lo, nsamples);
-      cp_async_commit();
+      compute_warps_sync<NC>();                                          // xt ready, ot free
     } else {
-      xt = xbuf + (s & 1) * C::kIn;
-      if (next < ntiles) rxv3_load_f32<C::kRows>(xbuf + ((s + 1) & 1) * C::kIn, in, 96 * next * C::kPeriods - 96, lo, nsamples);
-      cp_async_commit();
-      cp_async_wait_group<1>();                                          // this step's tile (the older group) has landed
+      xt = xbuf + b * C::kIn;
       if (threadIdx.x == 0 && store_pending) bulk_store_wait_read();
-      __syncthreads();                                                   // xt ready, ot free
+      compute_warps_sync<NC>();                                          // ot free
+      mbar_wait(&full[b], (s >> 1) & 1);                                 // this step's tile has landed
     }
-    // ---- this warp's quarter of the 65 phases for this lane's period
     const long long G = G0 + row;
     const bool q8 = (G % 9) == 8;
     rx_part<4>(part, c_rx_poly, xt + row * kRxRowPitch, ot + row * kRxP, q8);
+    if (!I16) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[b]);
+    }
     // ---- the 32T x 65 outputs are contiguous in shared and global memory
     const long long nvalid = (nperiods - G0 < C::kPeriods ? nperiods - G0 : C::kPeriods) * kRxP;
     cf *og = out + G0 * kRxP;
     if (nvalid == C::kOut) {
       fence_async_smem();
-      __syncthreads();                                                   // all outputs written; all reads of xt done
+      compute_warps_sync<NC>();                                          // all outputs written; all reads of xt done
       if (threadIdx.x == 0) bulk_store(og, ot, (unsigned)(C::kOut * sizeof(cf)));
       store_pending = true;
     } else {
-      __syncthreads();
-      for (int i = threadIdx.x; i < nvalid; i += blockDim.x) og[i] = ot[i];
+      compute_warps_sync<NC>();
+      for (int i = threadIdx.x; i < nvalid; i += NC) og[i] = ot[i];
       store_pending = false;
-      __syncthreads();
+      compute_warps_sync<NC>();
     }
   }
-  cp_async_wait_group<0>();
   if (threadIdx.x == 0 && store_pending) bulk_store_wait_all();
 }
 
