@@ -368,14 +368,14 @@ def main():
 
     if rank == 0:
         peak, how = measured_peaks()
-        k_res = {"name": "k_resample_rx_v2", "ms": ms_res, "algorithmic_bytes": nch * RESAMPLE_BYTES_PER_CHUNK}
+        k_res = {"name": "k_resample_rx_v3", "ms": ms_res, "algorithmic_bytes": nch * RESAMPLE_BYTES_PER_CHUNK}
         # k_detect_design reads the 36-sample midamble window (288 B) and writes flag/amp/toa (16 B) + the 112 B
         # EqParams record; k_equalize_fast reads the burst (1250 B) + EqParams and writes 148 soft bits
         k_det = {"name": "k_detect_design", "ms": ms_det, "algorithmic_bytes": nb * (288 + 16 + 112)}
         k_eq = {"name": "k_equalize_fast", "ms": ms_eq, "algorithmic_bytes": nb * (1250 + 112 + 148 * 4)}
         k_dem = {"name": "demod (detect_design + equalize_fast)", "ms": ms_dem, "algorithmic_bytes": nb * DEMOD_BYTES_PER_BURST}
         traffic = ncu_traffic(args.blocks)
-        k_res["traffic"] = traffic.get("k_resample_rx_v2")
+        k_res["traffic"] = traffic.get("k_resample_rx_v3")
         k_det["traffic"] = traffic.get("k_detect_design")
         k_eq["traffic"] = traffic.get("k_equalize_fast")
         for k in (k_res, k_det, k_eq, k_dem):

@@ -16,6 +16,8 @@
 // Kernel shape: one CTA per chunk; the 1056 (715) input samples are staged in shared memory with
 // coalesced 16-byte loads, the polyphase taps sit in shared memory transposed [k][branch] so that a
 // warp's tap reads are spread over the banks; each thread produces outputs n, n+256, ...
+#include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through the runtime, no -lcuda)
+
 #include "kernels.cuh"
 #include "sigproc_device.cuh"
 
@@ -57,151 +59,72 @@ __global__ void __launch_bounds__(256) k_resample_rx(const DevTables *__restrict
 // the last period of every chunk (q == 8) phases r >= 60 lose their first ix_r - 287 taps (the reference cannot
 // see samples of the next chunk; sigProcLib.cpp:1183-1186).
 //
-// Mapping: one lane = one period, one warp = 32 consecutive periods, ALL 65 phases per lane.  Because the phase
-// is the same across a warp, every tap is a warp-uniform constant: the taps live in __constant__ memory and are
-// read as immediate c[bank][offset] operands of the multiplies (no tap loads at all), and the whole 65-phase
-// body is unrolled into straight-line code with compile-time sample offsets.  Phases are processed in groups of
-// five adjacent outputs whose input windows overlap (15 + ~6 samples), so a lane loads ~22 samples per five
-// outputs as aligned 16-byte pairs instead of 75.
-// Shared memory per warp: the 32-period input tile, stored in rows of 96 samples padded to 98 (lane stride
-// 98 samples = 49 x 16 B, odd in 16-byte units -> conflict-free LDS.128), and a 32 x 65 output tile (lane
-// stride 65, odd -> conflict-free) that is written back as one contiguous, fully coalesced 16.6 KB block.
+// Mapping: one lane = one period, one warp = 32 consecutive periods (a "tile").  Because the phase is the same
+// across a warp, every tap is warp-uniform and the 65-phase body is unrolled into straight-line code with
+// compile-time sample offsets.  Phases are processed in groups of 4-6 adjacent outputs whose input windows overlap
+// (15 + ~6 samples), so a lane loads ~22 samples per five outputs as aligned 16-byte pairs instead of 75.  Each tap
+// costs TWO instructions: FFMA2 (x * h + 0, both components) and FADD2 (see cplx.cuh pmul0/padd) -- bit-identical
+// to the reference's separately rounded multiply and add.
+// Shared memory: the input tile in rows of 96 samples at a 98-sample pitch (lane stride 49 x 16 B, odd ->
+// conflict-free LDS.128), and a 32 x 65 output tile (lane stride 65, odd -> conflict-free) that leaves as one
+// contiguous, fully coalesced block.
 // ------------------------------------------------------------------------------------------------
 __constant__ float c_rx_poly[kRxP * 16];          // [r][k] = lpf_rx[br_r + 65 k], zero past the end
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, bool valid) {   // zero-fills when !valid
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  const int n = valid ? 8 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_async16z(void *smem_dst, const void *gsrc, bool valid) {  // zero-fills when !valid
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  const int n = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-
-#ifndef BTS_RXV2_WARPS
-#define BTS_RXV2_WARPS 4
-#endif
-#ifndef BTS_RXV2_TILES
-#define BTS_RXV2_TILES 2
-#endif
-// A CTA works on kRxV2Tiles consecutive 32-period tiles at once (one super-tile of 32*T + 2 input rows); warp w does
-// phase part w % kRxV2Warps of tile w / kRxV2Warps.  With kRxV2Warps = 4 the warps that share an SM sub-partition
-// (w % 4) all run the SAME quarter of the unrolled phase code, released together by the barrier, so they walk the
-// instruction stream in near lock-step and share its fetches.
-constexpr int kRxV2Warps = BTS_RXV2_WARPS, kRxV2Tiles = BTS_RXV2_TILES, kRxV2Threads = 32 * kRxV2Warps * kRxV2Tiles;
-constexpr int kRxV2Periods = 32 * kRxV2Tiles, kRxV2Rows = kRxV2Periods + 2;
-constexpr int kRxV2In = kRxV2Rows * kRxRowPitch, kRxV2Out = kRxV2Periods * kRxP;
-constexpr size_t kRxV2Smem = (size_t)(kRxV2In + kRxV2Out) * sizeof(cf);
-constexpr int kRxV2CtasPerSm = (int)(227 * 1024 / (kRxV2Smem + 1024)) < 2048 / kRxV2Threads ? (int)(227 * 1024 / (kRxV2Smem + 1024)) : 2048 / kRxV2Threads;
-
-// I16 = the radio's own sample format: interleaved int16 {I,Q} pairs (4 B per sample, `swap_iq` for the Q-first
-// order of real USRP hardware), converted exactly as unUSRPifyVector does (radioInterface.cpp:91-116) while the
-// tile is built -- the raw samples land in the (still unused) output tile via cp.async and are expanded to float.
-template <bool I16>
-__global__ void __launch_bounds__(kRxV2Threads) k_resample_rx_v2(const void *__restrict__ in_, int has_history, int swap_iq,
-                                                       long long nperiods, long long nsamples, cf *__restrict__ out) {
-  const cf *in = reinterpret_cast<const cf *>(in_);
-  const short2 *in16 = reinterpret_cast<const short2 *>(in_);
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cf *xt = reinterpret_cast<cf *>(smem_raw);
-  cf *ot = xt + kRxV2In;
-  const int warp = threadIdx.x >> 5, part = warp % kRxV2Warps;
-  const int row = (warp / kRxV2Warps) * 32 + (threadIdx.x & 31);      // this lane's period within the super-tile
-  for (long long tile = blockIdx.x; tile * kRxV2Periods < nperiods; tile += gridDim.x) {
-    const long long G0 = tile * kRxV2Periods;
-    const long long raw0 = 96 * G0 - 96;                               // tile origin: sample (G, r, k) sits at 96*l + ix_r - k - 96
-    // ---- load 34 rows x 96 samples as 16-byte cp.async copies (global -> shared, no registers, all 51 per lane
-    //      in flight at once); samples outside [lo, nsamples) are zero-filled by the copy's src-size operand
-    const long long lo = has_history ? -192 : 0;
-    __syncthreads();                                                    // previous tile fully written back
-    if (!I16) {
-      for (int i4 = threadIdx.x; i4 < kRxV2Rows * 48; i4 += kRxV2Threads) {
-        const int rw = i4 / 48, c4 = i4 - rw * 48;
-        const long long s = raw0 + (long long)rw * 96 + 2 * c4;
-        cf *dst = xt + rw * kRxRowPitch + 2 * c4;
-        if (s >= lo && s + 1 < nsamples) cp_async16(dst, in + s);
-        else {
-          cp_async8(dst, in + (s >= lo && s < nsamples ? s : 0), s >= lo && s < nsamples);
-          cp_async8(dst + 1, in + (s + 1 >= lo && s + 1 < nsamples ? s + 1 : 0), s + 1 >= lo && s + 1 < nsamples);
-        }
-      }
-      cp_async_wait_all();
-      __syncthreads();
-    } else {
-      // raw0, lo and nsamples are multiples of 4 samples, so every 16-byte group is wholly inside or outside
-      short2 *stage = reinterpret_cast<short2 *>(ot);
-      for (int i = threadIdx.x; i < kRxV2Rows * 24; i += kRxV2Threads) {
-        const long long s = raw0 + 4LL * i;
-        const bool valid = s >= lo && s < nsamples;
-        cp_async16z(stage + 4 * i, in16 + (valid ? s : 0), valid);
-      }
-      cp_async_wait_all();
-      __syncthreads();
-      for (int i = threadIdx.x; i < kRxV2Rows * 24; i += kRxV2Threads) {
-        const int rw = i / 24, c = 4 * (i - rw * 24);
-        const int4 v = *reinterpret_cast<const int4 *>(stage + 4 * i);
-        const int w[4] = {v.x, v.y, v.z, v.w};
-        cf *dst = xt + rw * kRxRowPitch + c;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const float a = (float)(short)(w[k] & 0xffff), b = (float)(short)(w[k] >> 16);     // first, second int16
-          dst[k] = swap_iq ? mk(b, a) : mk(a, b);
-        }
-      }
-      __syncthreads();
-    }
-    // ---- 65 phases for this lane's period
-    const long long G = G0 + row;
-    const bool q8 = (G % 9) == 8;
-    const cf *xl = xt + row * kRxRowPitch;
-    cf *ol = ot + row * kRxP;
-    rx_part<kRxV2Warps>(part, c_rx_poly, xl, ol, q8);
-    __syncthreads();
-    // ---- write the 32 x 65 outputs back: contiguous in both shared and global memory
-    const long long nvalid = (nperiods - G0 < kRxV2Periods ? nperiods - G0 : kRxV2Periods) * kRxP;
-    cf *og = out + G0 * kRxP;
-    for (int i4 = threadIdx.x; i4 < kRxV2Out / 2; i4 += kRxV2Threads) {
-      if (2 * i4 + 1 < nvalid) *reinterpret_cast<float4 *>(og + 2 * i4) = *reinterpret_cast<const float4 *>(ot + 2 * i4);
-      else if (2 * i4 < nvalid) og[2 * i4] = ot[2 * i4];
-    }
-  }
-}
-
-
 // ------------------------------------------------------------------------------------------------
-// v3: one persistent CTA per SM, T tiles per step, software-pipelined.
-// v2 loses a third of its issue slots waiting for instruction fetches: the unrolled 65-phase body is ~60 KB and
-// five independent CTAs per SM walk it at unrelated places.  Here a CTA owns T consecutive tiles; warp w runs
-// phase quarter w % 4 of tile w / 4, so the warps of one SM sub-partition all run the SAME quarter and are released
-// together by the barrier -- they walk the code in near lock-step and share its fetches.  What the single CTA
-// loses in load/compute overlap is put back explicitly:
-//   float input : two input buffers; the cp.async loads of super-tile s+1 are in flight while s is computed;
-//   int16 input : the raw int16 rows of s+1 land in a staging buffer while s is computed, and are widened to
-//                 float (unUSRPifyVector, radioInterface.cpp:94-110) into the single float tile at the next step;
-//   output      : the finished 32T x 65 block is contiguous in shared AND global memory and leaves as ONE bulk
-//                 async copy (cp.async.bulk, issued by one thread) that overlaps the next step.
+// k_resample_rx_v3: one persistent, warp-specialised CTA per SM.
+//   * T consecutive tiles per step (a "super-tile" of 32T periods, 32T + 2 input rows).
+//   * producer: ONE thread issues ONE 2-D tensor (TMA) copy per super-tile into a ring of input buffers, gated by
+//     full/empty mbarriers.  The tensor map describes the stream as rows of 96 samples and the box is 98 samples
+//     wide, so the copy engine itself writes the rows at the conflict-free pitch; rows outside the stream arrive as
+//     zeros (= the reference's zero history and nothing past the end).
+//   * compute warps: warp w runs phase part w % P of tile w / P; they synchronise among themselves on a named
+//     barrier.  Warps of one SM sub-partition (w % 4) run the same part of the unrolled code, released together, so
+//     they share its instruction fetches.  The taps come from shared memory (uniform-address LDS.128): as constant-
+//     bank operands the 4 KB table thrashes the per-SM constant cache and every miss stalls a warp for ~100 cycles.
+//   * int16 input (the radio's format): the raw rows land in a staging ring and are widened to float
+//     (unUSRPifyVector, radioInterface.cpp:94-110) into the single float tile at the start of each step.
+//   * output: the finished 32T x 65 block is contiguous in shared AND global memory and leaves as one bulk async
+//     copy (cp.async.bulk) that drains while the next step waits for its input.
+// History (profiles/README.md, r2): five independent 2-warp CTAs per SM 0.714 ms -> lock-step quarters 0.65 ->
+// 2-instruction taps 0.615 -> producer warp 0.52 -> shared-memory taps + tensor copy ~0.50 ms (213 750 chunks).
+// tools/rxv3_trace.cu prints per-step timestamps of one CTA (build with -DBTS_RXV3_TRACE).
 // ------------------------------------------------------------------------------------------------
+#ifndef BTS_RXV3_PARTS
+#define BTS_RXV3_PARTS 8
+#endif
+constexpr int kRxV3Parts = BTS_RXV3_PARTS;         // warps per 32-period tile (each does 65/kRxV3Parts phases)
+#ifndef BTS_RXV3_RING
+#define BTS_RXV3_RING 2
+#endif
+constexpr int kRxV3Ring = BTS_RXV3_RING;           // input buffers in flight (float tiles, or int16 staging rows)
+#ifndef BTS_RXV3_SPLIT
+#define BTS_RXV3_SPLIT 1
+#endif
+// Phase split across CTAs (build-time experiment, default off): with S > 1, CTA c handles phases [65 h / S, 65 (h+1) / S),
+// h = c % S, of the super-tiles c / S, c / S + grid / S, ...; the S CTAs sharing a super-tile are independent, each
+// loads the whole input tile and writes its own 32/33-sample run of every period.  An SM then executes only 1/S of
+// the unrolled code (resident in the instruction cache), but every input byte crosses the L2 -> SM fabric S times;
+// measured at S = 2: 0.92 ms against 0.50 ms for S = 1 (per-GPC fabric bandwidth, see profiles/README.md r2).
+constexpr int kRxV3Split = BTS_RXV3_SPLIT;
+constexpr int kRxV3OutW = (kRxP + kRxV3Split - 1) / kRxV3Split;                 // output-tile row: 65 or 33 (odd: conflict-free)
+static_assert(kRxV3OutW % 2 == 1, "output tile pitch must be odd");
 template <bool I16, int T>
 struct RxV3 {
   static constexpr int kPeriods = 32 * T, kRows = kPeriods + 2;
-  static constexpr int kIn = kRows * kRxRowPitch, kOut = kPeriods * kRxP;         // samples
-  static constexpr int kThreads = 128 * T + 32;                                // 4T compute warps + the producer warp
-  static constexpr size_t kSmem = I16 ? (size_t)(kIn + kOut) * sizeof(cf) + (size_t)2 * kRows * 96 * 4
-                                      : (size_t)(2 * kIn + kOut) * sizeof(cf);
+  static constexpr int kIn = kRows * kRxRowPitch, kOut = kPeriods * kRxV3OutW;   // samples
+  static constexpr int kInSlot = (kIn + 15) & ~15;                               // ring slots start on 128-byte lines (TMA)
+  static constexpr int kThreads = 32 * kRxV3Parts * T + 32;                      // compute warps + the producer warp
+  static constexpr int kStage = kRows * 96;                                      // int16 pairs per staging buffer
+  static constexpr unsigned kTileBytes = I16 ? kStage * 4u : kIn * 8u;           // what one tensor copy delivers
+  static constexpr int kOutBufs = kRxV3Split == 1 ? 1 : 2;                       // see the store paths in the kernel
+  // output block(s); then float: kRxV3Ring input tiles / int16: one float tile + kRxV3Ring staging buffers
+  static constexpr size_t kSmem = 128 + (I16 ? (size_t)(kOutBufs * kOut + kInSlot) * sizeof(cf) + (size_t)kRxV3Ring * kStage * 4
+                                             : (size_t)(kOutBufs * kOut + kRxV3Ring * kInSlot) * sizeof(cf));
+  static_assert((kOut * sizeof(cf)) % 128 == 0 && (kStage * 4) % 128 == 0, "TMA destinations must be 128-byte aligned");
+  static_assert(kSmem + 6 * 1024 <= 227 * 1024, "resampler tile does not fit in shared memory");
 };
 
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigned bytes) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\ncp.async.bulk.commit_group;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
@@ -218,10 +141,6 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned coun
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// arrives (without raising the expected count) once all of this thread's earlier cp.async copies have landed
-__device__ __forceinline__ void mbar_arrive_after_cp_async(unsigned long long *bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
   asm volatile(
       "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(
@@ -232,45 +151,21 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 template <int NTHREADS>
 __device__ __forceinline__ void compute_warps_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
-// Producer warp: issue (not wait for) the loads of the super-tile whose first raw sample is raw0.
-// Samples outside [lo, nsamples) are zero-filled by the copies' src-size operand.
-template <int ROWS>
-__device__ __forceinline__ void rxv3_load_f32(cf *xt, const cf *__restrict__ in, long long raw0, long long lo, long long nsamples) {
-  const int lane = threadIdx.x & 31;
-  if (raw0 >= lo && raw0 + (long long)ROWS * 96 <= nsamples) {                      // interior: no bounds tests
-    const cf *src = in + raw0 + 2 * lane;
-    cf *dst = xt + 2 * lane;
-#pragma unroll 2
-    for (int rw = 0; rw < ROWS; rw++) {
-      cp_async16(dst + rw * kRxRowPitch, src + rw * 96);
-      if (lane < 16) cp_async16(dst + rw * kRxRowPitch + 64, src + rw * 96 + 64);
-    }
-  } else {
-    for (int i4 = lane; i4 < ROWS * 48; i4 += 32) {
-      const int rw = i4 / 48, c4 = i4 - rw * 48;
-      const long long s = raw0 + (long long)rw * 96 + 2 * c4;
-      const bool ok = s >= lo && s < nsamples;                                     // bounds are even: both samples or none
-      cp_async16z(xt + rw * kRxRowPitch + 2 * c4, in + (ok ? s : 0), ok);
-    }
-  }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-template <int ROWS>
-__device__ __forceinline__ void rxv3_load_i16(short2 *stage, const short2 *__restrict__ in16, long long raw0, long long lo,
-                                              long long nsamples) {
-  const int lane = threadIdx.x & 31;
-  if (raw0 >= lo && raw0 + (long long)ROWS * 96 <= nsamples) {
-    const short2 *src = in16 + raw0 + 4 * lane;
-    short2 *dst = stage + 4 * lane;
-#pragma unroll 4
-    for (int i = 0; i < ROWS * 24 / 32; i++) cp_async16(dst + 128 * i, src + 128 * i);
-    if (lane < ROWS * 24 % 32) cp_async16(dst + 128 * (ROWS * 24 / 32), src + 128 * (ROWS * 24 / 32));
-  } else {
-    for (int i = lane; i < ROWS * 24; i += 32) {
-      const long long s = raw0 + 4LL * i;
-      const bool ok = s >= lo && s < nsamples;
-      cp_async16z(stage + 4 * i, in16 + (ok ? s : 0), ok);
-    }
-  }
+
+// One tensor (TMA) copy brings in a whole super-tile.  The tensor map describes the raw stream as rows of 96 samples;
+// the box is ROWS x 98 samples for float input -- two samples wider than the tensor, so the copy itself lays the rows
+// down at the 98-sample pitch that keeps the compute warps' LDS.128 conflict-free (the two extra columns are
+// out-of-bounds and arrive as zeros) -- and ROWS x 96 int16 pairs for int16 input.  Rows before the start of a
+// history-less stream and past its end are out of bounds too and arrive as zeros, which is exactly the reference's
+// zero history / truncated right edge.  One thread issues it; completion is counted in bytes on the mbarrier.
+__device__ __forceinline__ void tma_load_tile(void *sdst, const CUtensorMap *tmap, int row0, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(sdst)),
+               "l"(tmap), "r"(0), "r"(row0), "r"(smem_u32(bar))
+               : "memory");
 }
 template <int ROWS, int NTHREADS>
 __device__ __forceinline__ void rxv3_widen(cf *xt, const short2 *stage, int swap_iq) {
@@ -288,88 +183,133 @@ __device__ __forceinline__ void rxv3_widen(cf *xt, const short2 *stage, int swap
   }
 }
 
+#ifdef BTS_RXV3_TRACE            // tools/rxv3_trace.cu: per-iteration timestamps of CTA 0 (debug builds only)
+__device__ long long g_rx_trace[2][64][8];
+__device__ long long g_rx_cta[256][4];
+#ifndef BTS_RXV3_TRACE_CTA
+#define BTS_RXV3_TRACE_CTA 0
+#endif
+#define RX_TRACE(who, it, slot) do { if (blockIdx.x == BTS_RXV3_TRACE_CTA && (who == 1 || threadIdx.x == 0) && (it) < 64) g_rx_trace[who][it][slot] = clock64(); } while (0)
+#else
+#define RX_TRACE(who, it, slot) do { } while (0)
+#endif
 template <bool I16, int T>
-__global__ void __launch_bounds__(128 * T + 32, 1) k_resample_rx_v3(const void *__restrict__ in_, int has_history, int swap_iq,
-                                                                   long long nperiods, long long nsamples, cf *__restrict__ out) {
+__global__ void __launch_bounds__(32 * kRxV3Parts * T + 32, 1) k_resample_rx_v3(const __grid_constant__ CUtensorMap tmap, int row_bias, int swap_iq,
+                                                                             long long nperiods, cf *__restrict__ out) {
   using C = RxV3<I16, T>;
-  constexpr int NC = 128 * T;                                            // compute threads; warp 4T is the producer
-  const cf *in = reinterpret_cast<const cf *>(in_);
-  const short2 *in16 = reinterpret_cast<const short2 *>(in_);
+  constexpr int NW = kRxV3Parts * T, NC = 32 * NW, R = kRxV3Ring;        // compute warps / threads; warp NW is the producer
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cf *ot = reinterpret_cast<cf *>(smem_raw);                             // output block first: 16-byte aligned for the bulk copy
-  cf *xbuf = ot + C::kOut;                                               // float: two input buffers; int16: one + 2 staging
-  short2 *stage = reinterpret_cast<short2 *>(xbuf + C::kIn);
-  __shared__ __align__(8) unsigned long long full[2], empty[2];
+  cf *obuf = reinterpret_cast<cf *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);   // 128-byte lines
+  cf *xbuf = obuf + C::kOutBufs * C::kOut;
+  short2 *stage = reinterpret_cast<short2 *>(xbuf + C::kInSlot);
+  __shared__ __align__(8) unsigned long long full[R], empty[R];
+  // the taps are read from shared memory (uniform-address LDS.128, ~30 cycles) rather than as constant-bank operands:
+  // 4 KB of taps cycled through by 12+ warps misses the small per-SM constant cache and each miss stalls a warp ~100s
+  // of cycles on the LDCU that feeds its next four multiplies
+  __shared__ __align__(16) float s_taps[kRxP * 16];
+  for (int i = threadIdx.x; i < kRxP * 16; i += blockDim.x) s_taps[i] = c_rx_poly[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long lo = has_history ? -192 : 0;
   const long long ntiles = (nperiods + C::kPeriods - 1) / C::kPeriods;
+  const int half = blockIdx.x % kRxV3Split;                              // which share of the phases
+  const long long first = blockIdx.x / kRxV3Split, stride = gridDim.x / kRxV3Split;
   if (threadIdx.x == 0) {
-    mbar_init(&full[0], 32);
-    mbar_init(&full[1], 32);
-    mbar_init(&empty[0], 4 * T);
-    mbar_init(&empty[1], 4 * T);
+    for (int i = 0; i < R; i++) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], NW);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (warp == 4 * T) {
-    // ---- producer: keeps up to two super-tiles in flight ahead of the compute warps
-    int s = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, s++) {
-      const int b = s & 1;
-      if (s >= 2) mbar_wait(&empty[b], ((s >> 1) - 1) & 1);              // the compute warps are done with this buffer
-      const long long raw0 = 96 * tile * C::kPeriods - 96;               // sample (G, r, k) sits at 96*l + ix_r - k - 96
-      if (I16) rxv3_load_i16<C::kRows>(stage + b * (C::kRows * 96), in16, raw0, lo, nsamples);
-      else rxv3_load_f32<C::kRows>(xbuf + b * C::kIn, in, raw0, lo, nsamples);
-      mbar_arrive_after_cp_async(&full[b]);
+  if (warp == NW) {
+    // ---- producer: one thread keeps up to R super-tiles in flight ahead of the compute warps
+    if (lane == 0) {
+      int b = 0, use = 0, it = 0;                                        // ring slot and how many times it has been used
+      for (long long tile = first; tile < ntiles; tile += stride, it++) {
+        RX_TRACE(1, it, 0);
+        if (use > 0) mbar_wait(&empty[b], (use - 1) & 1);                // the compute warps are done with this slot
+        RX_TRACE(1, it, 1);
+        // sample (G, r, k) sits at 96*l + ix_r - k - 96 from the tile origin: the tile starts one row before period G0
+        mbar_expect_tx(&full[b], C::kTileBytes);
+        tma_load_tile(I16 ? (void *)(stage + b * C::kStage) : (void *)(xbuf + b * C::kInSlot), &tmap,
+                      (int)(tile * C::kPeriods) - 1 + row_bias, &full[b]);
+        RX_TRACE(1, it, 2);
+        if (++b == R) { b = 0; use++; }
+      }
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
     return;
   }
-  // ---- compute warps: warp w runs phase quarter w % 4 of tile w / 4
-  const int part = warp & 3;
-  const int row = (warp >> 2) * 32 + lane;                               // this lane's period within the super-tile
+  // ---- compute warps: warp w runs phase part w % kRxV3Parts (of this CTA's share) of tile w / kRxV3Parts
+  const int part = half * kRxV3Parts + warp % kRxV3Parts;
+  const int r_lo = kRxP * half / kRxV3Split, nr = kRxP * (half + 1) / kRxV3Split - r_lo;
+  const int tl = warp / kRxV3Parts;
+  const int row = tl * 32 + lane;                                        // this lane's period within the super-tile
+  int b = 0, use = 0, ob = 0;
   bool store_pending = false;
-  int s = 0;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, s++) {
+  int it = 0;
+#ifdef BTS_RXV3_TRACE
+  if (threadIdx.x == 0) g_rx_cta[blockIdx.x][0] = clock64();
+#endif
+  for (long long tile = first; tile < ntiles; tile += stride, it++) {
     const long long G0 = tile * C::kPeriods;
-    const int b = s & 1;
-    cf *xt = xbuf;
+    cf *xt = xbuf, *ot = obuf + ob * C::kOut;
+    RX_TRACE(0, it, 0);
+    if (kRxV3Split == 1) {                                               // single output block: wait until it has drained
+      if (threadIdx.x == 0 && store_pending) bulk_store_wait_read();
+      compute_warps_sync<NC>();
+    }
+    mbar_wait(&full[b], use & 1);                                        // this step's input has landed
+    RX_TRACE(0, it, 1);
     if (I16) {
-      mbar_wait(&full[b], (s >> 1) & 1);                                 // raw int16 rows have landed
-      rxv3_widen<C::kRows, NC>(xt, stage + b * (C::kRows * 96), swap_iq);
+      rxv3_widen<C::kRows, NC>(xt, stage + b * C::kStage, swap_iq);      // previous compute left xt at the closing barrier
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[b]);
-      if (threadIdx.x == 0 && store_pending) bulk_store_wait_read();
-      compute_warps_sync<NC>();                                          // xt ready, ot free
+      compute_warps_sync<NC>();                                          // xt ready
     } else {
-      xt = xbuf + b * C::kIn;
-      if (threadIdx.x == 0 && store_pending) bulk_store_wait_read();
-      compute_warps_sync<NC>();                                          // ot free
-      mbar_wait(&full[b], (s >> 1) & 1);                                 // this step's tile has landed
+      xt = xbuf + b * C::kInSlot;
     }
     const long long G = G0 + row;
     const bool q8 = (G % 9) == 8;
-    rx_part<4>(part, c_rx_poly, xt + row * kRxRowPitch, ot + row * kRxP, q8);
+    RX_TRACE(0, it, 2);
+    rx_part<kRxV3Split * kRxV3Parts>(part, s_taps, xt + row * kRxRowPitch, ot + row * kRxV3OutW - r_lo, q8);
+    RX_TRACE(0, it, 3);
     if (!I16) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[b]);
     }
-    // ---- the 32T x 65 outputs are contiguous in shared and global memory
-    const long long nvalid = (nperiods - G0 < C::kPeriods ? nperiods - G0 : C::kPeriods) * kRxP;
-    cf *og = out + G0 * kRxP;
-    if (nvalid == C::kOut) {
+    if (++b == R) { b = 0; use++; }
+    const long long nper = nperiods - G0 < C::kPeriods ? nperiods - G0 : C::kPeriods;
+    if (kRxV3Split == 1) {
+      // the 32T x 65 outputs are contiguous in shared and global memory: one bulk copy, issued by one thread,
+      // that drains while the next step waits for its input
+      cf *og = out + G0 * kRxP;
       fence_async_smem();
       compute_warps_sync<NC>();                                          // all outputs written; all reads of xt done
-      if (threadIdx.x == 0) bulk_store(og, ot, (unsigned)(C::kOut * sizeof(cf)));
-      store_pending = true;
+      if (nper == C::kPeriods) {
+        if (threadIdx.x == 0) bulk_store(og, ot, (unsigned)(C::kOut * sizeof(cf)));
+        store_pending = true;
+      } else {
+        for (int i = threadIdx.x; i < nper * kRxP; i += NC) og[i] = ot[i];
+        store_pending = false;
+      }
     } else {
-      compute_warps_sync<NC>();
-      for (int i = threadIdx.x; i < nvalid; i += NC) og[i] = ot[i];
-      store_pending = false;
-      compute_warps_sync<NC>();
+      // each period's run of nr outputs: one coalesced 8-byte store per lane (and lane 0 again for a 33rd sample).
+      // The other output block is written next step, and this block's reads are fenced by that step's barrier.
+      compute_warps_sync<NC>();                                          // all outputs written; all reads of xt done
+      RX_TRACE(0, it, 4);
+      for (int p = warp; p < nper; p += NW) {
+        cf *og = out + (G0 + p) * kRxP + r_lo;
+        const cf *os = ot + p * kRxV3OutW;
+        og[lane] = os[lane];
+        if (lane + 32 < nr) og[lane + 32] = os[lane + 32];
+      }
     }
+    ob ^= C::kOutBufs - 1;
+    RX_TRACE(0, it, 5);
   }
   if (threadIdx.x == 0 && store_pending) bulk_store_wait_all();
+#ifdef BTS_RXV3_TRACE
+  if (threadIdx.x == 0) { g_rx_cta[blockIdx.x][1] = clock64(); g_rx_cta[blockIdx.x][2] = it; unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); g_rx_cta[blockIdx.x][3] = sm; }
+#endif
 }
 
 #ifndef BTS_RXV3_TILES_F32
@@ -380,6 +320,10 @@ __global__ void __launch_bounds__(128 * T + 32, 1) k_resample_rx_v3(const void *
 #endif
 constexpr int kRxV3TilesF32 = BTS_RXV3_TILES_F32, kRxV3TilesI16 = BTS_RXV3_TILES_I16;
 static int g_num_sms = 148;
+static unsigned rxv3_grid(long long ntiles) {        // a multiple of the phase split, at most one CTA per SM
+  const long long groups = g_num_sms / kRxV3Split;
+  return (unsigned)((ntiles < groups ? ntiles : groups) * kRxV3Split);
+}
 
 void upload_resampler_taps(const DevTables *hostT) {
   float h[kRxP * 16];
@@ -387,14 +331,39 @@ void upload_resampler_taps(const DevTables *hostT) {
   cudaMemcpyToSymbol(c_rx_poly, h, sizeof h);
 }
 
+// Tensor map over the raw stream as [rows][96 samples]; with history the map starts two rows (192 samples) before `in`.
+// Returns the row bias to add to a period index (tile origin = period - 1).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+template <bool I16, int T>
+static int rxv3_make_map(CUtensorMap *map, const void *in, int has_history, long long nchunks) {
+  using C = RxV3<I16, T>;
+  if (!g_encode_tiled) return -1;
+  const size_t sample = I16 ? 4 : 8;
+  const char *base = reinterpret_cast<const char *>(in) - (has_history ? 192 * sample : 0);
+  const cuuint64_t rows = (cuuint64_t)nchunks * 9 + (has_history ? 2 : 0);
+  // float: 32-bit elements, 192 per row, box 196 wide (= 98 samples); int16: one 32-bit element per I/Q pair
+  const cuuint64_t gdim[2] = {I16 ? 96u : 192u, rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)(96 * sample)};
+  const cuuint32_t box[2] = {I16 ? 96u : 2u * kRxRowPitch, (cuuint32_t)C::kRows};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult r = g_encode_tiled(map, I16 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                                    const_cast<char *>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? (has_history ? 2 : 0) : -1;
+}
+
 void launch_resample_rx(const DevTables *T, const cf *in, int has_history, long long nchunks, cf *out, cudaStream_t st) {
   if (nchunks <= 0) return;
   const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
-  if (aligned) {
+  alignas(64) CUtensorMap map;
+  const int bias = aligned ? rxv3_make_map<false, kRxV3TilesF32>(&map, in, has_history, nchunks) : -1;
+  if (bias >= 0) {
     using C = RxV3<false, kRxV3TilesF32>;
     const long long nperiods = nchunks * 9, ntiles = (nperiods + C::kPeriods - 1) / C::kPeriods;
-    const unsigned grid = (unsigned)(ntiles < g_num_sms ? ntiles : g_num_sms);
-    k_resample_rx_v3<false, kRxV3TilesF32><<<grid, C::kThreads, C::kSmem, st>>>(in, has_history, 0, nperiods, nchunks * 864, out);
+    k_resample_rx_v3<false, kRxV3TilesF32><<<rxv3_grid(ntiles), C::kThreads, C::kSmem, st>>>(map, bias, 0, nperiods, out);
   } else {
     const unsigned grid = (unsigned)(nchunks < 148 * 32 ? nchunks : 148 * 32);
     k_resample_rx<<<grid, 256, 0, st>>>(T, in, has_history, nchunks, out);
@@ -405,15 +374,24 @@ int launch_resample_rx_i16(const int16_t *in, int swap_iq, int has_history, long
   if (nchunks <= 0) return 0;
   if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return -1;
   using C = RxV3<true, kRxV3TilesI16>;
+  alignas(64) CUtensorMap map;
+  const int bias = rxv3_make_map<true, kRxV3TilesI16>(&map, in, has_history, nchunks);
+  if (bias < 0) return -1;
   const long long nperiods = nchunks * 9, ntiles = (nperiods + C::kPeriods - 1) / C::kPeriods;
-  const unsigned grid = (unsigned)(ntiles < g_num_sms ? ntiles : g_num_sms);
-  k_resample_rx_v3<true, kRxV3TilesI16><<<grid, C::kThreads, C::kSmem, st>>>(in, has_history, swap_iq, nperiods, nchunks * 864, out);
+  k_resample_rx_v3<true, kRxV3TilesI16><<<rxv3_grid(ntiles), C::kThreads, C::kSmem, st>>>(map, bias, swap_iq, nperiods, out);
   return 1;
 }
 int configure_resamplers() {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) g_num_sms = sms;
+  if (!g_encode_tiled) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+    if (!g_encode_tiled) return -1;
+  }
   cudaError_t e = cudaFuncSetAttribute(k_resample_rx_v3<false, kRxV3TilesF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)RxV3<false, kRxV3TilesF32>::kSmem);
   if (e != cudaSuccess) return (int)e;

@@ -425,7 +425,8 @@ void emu_resample_rx_v2(const float *in_, int has_history, long long nchunks, fl
       }
     for (int lane = 0; lane < 32; lane++) {
       const long long G = G0 + lane;
-      rx_period(taps.data(), xt.data() + lane * kRxRowPitch, ot.data() + lane * kRxP, (G % 9) == 8);
+      for (int part = 0; part < 8; part++)      // the kernel's split of the 65 phases over eight warps
+        rx_part<8>(part, taps.data(), xt.data() + lane * kRxRowPitch, ot.data() + lane * kRxP, (G % 9) == 8);
     }
     const long long nvalid = (nperiods - G0 < 32 ? nperiods - G0 : 32) * kRxP;
     for (long long i = 0; i < nvalid; i++) out[G0 * kRxP + i] = ot[i];
