@@ -208,6 +208,36 @@ int btsdsp_rach_host(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch
                      float detect_thr, int32_t *flag, btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch);
 
 /* pinned host memory helpers for layer-3 callers */
+/* ---- caller policy: Transceiver::pullRadioVector + driveReceiveFIFO over batches ----
+ * A btsdsp_trx holds, on the device, the receive-side state of `narfcn` Transceiver objects (one per ARFCN):
+ * adaptive mEnergyThreshold, prevFalseDetectionTime, and per timeslot the cached channel estimate's DFE, offset,
+ * SNR and timestamp (Transceiver.h:127-142; initial values Transceiver.cpp:72-89).  tsc: mTSC per ARFCN;
+ * chan_type: mChanType per (ARFCN, TN), 0 NONE, 1..7 = I..VII, 8 LOOPBACK (Transceiver.h ChannelCombination).
+ *
+ * pull: one batch of nframes x narfcn x 8 received slots, laid out [frame][arfcn][tn] at `pitch` samples
+ * (slot length 157 if tn%4==0 else 156), FN = fn0 + frame, processed with exactly the reference's burst-by-burst
+ * semantics per ARFCN (Transceiver.cpp:271-410): slot map (expectedCorrType :207-269), energy gate against the
+ * adaptive threshold and its updates (:298-304, :338-339, :353-357, :369-376), channel re-estimation every 50 frames
+ * or after a miss (:315-350), equalisation with the cached DFE (:391-396) or RACH demodulation (:383-389).
+ * Per burst: valid[i] (a datagram would be sent) and the 158-byte RX datagram of driveReceiveFIFO (:659-673) at
+ * dgram + i*dgram_pitch: TN, FN (4 bytes, big endian), RSSI, timing offset (2 bytes, 1/256 symbol), 148 soft bytes,
+ * 2 zero bytes.  Rows of invalid bursts are zero.  State carries over to the next pull. */
+typedef struct btsdsp_trx btsdsp_trx;
+int btsdsp_trx_create(btsdsp_ctx *ctx, int narfcn, const uint8_t *tsc, const uint8_t *chan_type, int start_fn,
+                      btsdsp_trx **out);
+int btsdsp_trx_destroy(btsdsp_ctx *ctx, btsdsp_trx *trx);
+int btsdsp_trx_set_slot(btsdsp_ctx *ctx, btsdsp_trx *trx, int arfcn, int tn, int chan_type);   /* SETSLOT, Transceiver.cpp:549 */
+/* state of one ARFCN for inspection: { double thr; int32 prev_false_fn, tsc, chan_type[8], est_fn[8], have[8];
+ * float snr[8], chan_off[8]; cf32 w[8][7], b[8][5]; }  (btsdsp_trx_state_bytes() bytes) */
+int btsdsp_trx_state_bytes(void);
+int btsdsp_trx_get_state(btsdsp_ctx *ctx, btsdsp_trx *trx, int arfcn, void *dst, int cap);
+/* device pointers, asynchronous on `stream`; dgram 8-byte aligned, dgram_pitch >= 160 and a multiple of 4 */
+int btsdsp_trx_pull_dev(btsdsp_ctx *ctx, btsdsp_trx *trx, const btsdsp_cf32 *bursts, long long pitch, int nframes,
+                        int fn0, int32_t *valid, uint8_t *dgram, int dgram_pitch, void *stream);
+/* host pointers, synchronous; dgram_pitch >= 158 */
+int btsdsp_trx_pull_host(btsdsp_ctx *ctx, btsdsp_trx *trx, const btsdsp_cf32 *bursts, long long pitch, int nframes,
+                         int fn0, int32_t *valid, uint8_t *dgram, int dgram_pitch);
+
 void *btsdsp_host_alloc(size_t bytes);
 void btsdsp_host_free(void *p);
 

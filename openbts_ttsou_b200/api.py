@@ -70,6 +70,13 @@ _SIGS = {
     "btsdsp_demod_normal_host": (_i, [_vp, _vp, _ll, _vp, _vp, _ll, _f, _f, _f, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp,
                                       _vp]),
     "btsdsp_rach_host": (_i, [_vp, _vp, _ll, _vp, _ll, _f, _vp, _vp, _vp, _vp, _i]),
+    "btsdsp_trx_create": (_i, [_vp, _i, _vp, _vp, _i, _vp]),
+    "btsdsp_trx_destroy": (_i, [_vp, _vp]),
+    "btsdsp_trx_set_slot": (_i, [_vp, _vp, _i, _i, _i]),
+    "btsdsp_trx_state_bytes": (_i, []),
+    "btsdsp_trx_get_state": (_i, [_vp, _vp, _i, _vp, _i]),
+    "btsdsp_trx_pull_dev": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i, _vp]),
+    "btsdsp_trx_pull_host": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i]),
     "btsdsp_host_alloc": (_vp, [ctypes.c_size_t]),
     "btsdsp_host_free": (None, [_vp]),
 }
@@ -359,6 +366,43 @@ class BtsDsp:
             self.h, _p(bursts), pitch, _p(lens), _p(tsc), n, detect_thr, gate_thr, snr_thr, _p(r["flag"]), _p(r["amp"]),
             _p(r["toa"]), _p(r["soft"]), soft_pitch, _p(r.get("chan")), _p(r.get("off")), _p(r.get("w")), _p(r.get("b"))))
         return r
+
+    # ---- caller policy: Transceiver::pullRadioVector + driveReceiveFIFO over batches ----
+    TRX_STATE_DTYPE = np.dtype([("thr", np.float64), ("prev_false_fn", np.int32), ("tsc", np.int32),
+                                ("chan_type", np.int32, 8), ("est_fn", np.int32, 8), ("have", np.int32, 8),
+                                ("snr", np.float32, 8), ("chan_off", np.float32, 8),
+                                ("w", np.complex64, (8, 7)), ("b", np.complex64, (8, 5))], align=True)
+
+    def trx_create(self, tsc, chan_type, start_fn=0):
+        """tsc: (narfcn,) midamble codes; chan_type: (narfcn, 8) channel combinations.  Returns an opaque handle."""
+        tsc = np.ascontiguousarray(tsc, np.uint8)
+        ct = np.ascontiguousarray(chan_type, np.uint8).reshape(tsc.size, 8)
+        h = ctypes.c_void_p()
+        self._ck(self.lib.btsdsp_trx_create(self.h, tsc.size, _p(tsc), _p(ct), start_fn, ctypes.byref(h)))
+        assert self.lib.btsdsp_trx_state_bytes() == self.TRX_STATE_DTYPE.itemsize
+        return (h, tsc.size)
+
+    def trx_destroy(self, trx):
+        self._ck(self.lib.btsdsp_trx_destroy(self.h, trx[0]))
+
+    def trx_set_slot(self, trx, arfcn, tn, chan_type):
+        self._ck(self.lib.btsdsp_trx_set_slot(self.h, trx[0], arfcn, tn, chan_type))
+
+    def trx_state(self, trx):
+        st = np.zeros(trx[1], self.TRX_STATE_DTYPE)
+        for a in range(trx[1]):
+            self._ck(self.lib.btsdsp_trx_get_state(self.h, trx[0], a, _p(st[a:a + 1]), st.itemsize))
+        return st
+
+    def trx_pull_host(self, trx, bursts, fn0):
+        """bursts: (nframes*narfcn*8, pitch) complex64 laid out [frame][arfcn][tn].  Returns (valid[n], dgram[n,158])."""
+        bursts = _c64(bursts)
+        n, pitch = bursts.shape
+        assert n % (8 * trx[1]) == 0
+        valid = np.zeros(n, np.int32)
+        dg = np.zeros((n, 158), np.uint8)
+        self._ck(self.lib.btsdsp_trx_pull_host(self.h, trx[0], _p(bursts), pitch, n // (8 * trx[1]), fn0, _p(valid), _p(dg), 158))
+        return valid, dg
 
     def rach_host(self, bursts, lens, detect_thr=5.0, demod=True, soft_pitch=160):
         bursts = _c64(bursts)

@@ -911,4 +911,145 @@ int btsdsp_rach_host(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch
   return BTSDSP_OK;
 }
 
+/* ---- caller policy: Transceiver::pullRadioVector + driveReceiveFIFO over batches (trx_policy.cuh) ---- */
+struct btsdsp_trx {
+  int narfcn = 0;
+  TrxState *d_state = nullptr;
+  std::vector<uint8_t> tsc;             // [narfcn]
+  std::vector<uint8_t> chan_type;       // [narfcn][8]
+  DevBuf meta, scratch, io;             // device: per-burst kind/tsc/rach maps; pass scratch; host-API staging
+  DevBuf pin;                           // pinned host staging of the maps
+  cudaEvent_t meta_done = nullptr;      // the previous call's map upload has been consumed
+};
+
+int btsdsp_trx_create(btsdsp_ctx *ctx, int narfcn, const uint8_t *tsc, const uint8_t *chan_type, int start_fn,
+                      btsdsp_trx **out) {
+  ARG(ctx && out && narfcn > 0 && tsc && chan_type && start_fn >= 0 && start_fn < kHyperframe);
+  if (ctx->sps != 1) return fail(ctx, BTSDSP_EUNSUPPORTED, "the receive policy assumes symbol-rate sampling (sps == 1)");
+  for (int a = 0; a < narfcn; a++) {
+    ARG(tsc[a] < 8);
+    for (int tn = 0; tn < 8; tn++) ARG(chan_type[a * 8 + tn] <= CT_LOOPBACK);
+  }
+  DeviceGuard g(ctx->device);
+  btsdsp_trx *t = new btsdsp_trx;
+  t->narfcn = narfcn;
+  t->tsc.assign(tsc, tsc + narfcn);
+  t->chan_type.assign(chan_type, chan_type + (size_t)narfcn * 8);
+  std::vector<TrxState> h(narfcn);
+  memset(h.data(), 0, h.size() * sizeof(TrxState));
+  for (int a = 0; a < narfcn; a++) {                       // Transceiver::Transceiver, Transceiver.cpp:72-89
+    h[a].thr = 250.0;
+    h[a].prev_false_fn = start_fn;
+    h[a].tsc = tsc[a];
+    for (int tn = 0; tn < 8; tn++) { h[a].chan_type[tn] = chan_type[a * 8 + tn]; h[a].est_fn[tn] = start_fn; }
+  }
+  cudaError_t e = cudaMalloc(&t->d_state, h.size() * sizeof(TrxState));
+  if (e == cudaSuccess) e = cudaMemcpy(t->d_state, h.data(), h.size() * sizeof(TrxState), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->meta_done, cudaEventDisableTiming);
+  if (e != cudaSuccess) { if (t->d_state) cudaFree(t->d_state); delete t; return fail(ctx, BTSDSP_ECUDA, "trx_create", e); }
+  *out = t;
+  return BTSDSP_OK;
+}
+
+int btsdsp_trx_destroy(btsdsp_ctx *ctx, btsdsp_trx *t) {
+  ARG(ctx && t);
+  DeviceGuard g(ctx->device);
+  cudaDeviceSynchronize();
+  if (t->d_state) cudaFree(t->d_state);
+  if (t->meta.p) cudaFree(t->meta.p);
+  if (t->scratch.p) cudaFree(t->scratch.p);
+  if (t->io.p) cudaFree(t->io.p);
+  if (t->pin.p) cudaFreeHost(t->pin.p);
+  if (t->meta_done) cudaEventDestroy(t->meta_done);
+  delete t;
+  return BTSDSP_OK;
+}
+
+int btsdsp_trx_state_bytes(void) { return (int)sizeof(TrxState); }
+
+int btsdsp_trx_get_state(btsdsp_ctx *ctx, btsdsp_trx *t, int arfcn, void *dst, int cap) {
+  ARG(ctx && t && dst && arfcn >= 0 && arfcn < t->narfcn && cap >= (int)sizeof(TrxState));
+  DeviceGuard g(ctx->device);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(dst, t->d_state + arfcn, sizeof(TrxState), cudaMemcpyDeviceToHost));
+  return BTSDSP_OK;
+}
+
+int btsdsp_trx_set_slot(btsdsp_ctx *ctx, btsdsp_trx *t, int arfcn, int tn, int chan_type) {   /* SETSLOT, Transceiver.cpp:549 */
+  ARG(ctx && t && arfcn >= 0 && arfcn < t->narfcn && tn >= 0 && tn < 8 && chan_type >= 0 && chan_type <= CT_LOOPBACK);
+  DeviceGuard g(ctx->device);
+  CK(cudaDeviceSynchronize());
+  t->chan_type[(size_t)arfcn * 8 + tn] = (uint8_t)chan_type;
+  CK(cudaMemcpy(&t->d_state[arfcn].chan_type[tn], &chan_type, sizeof(int), cudaMemcpyHostToDevice));
+  return BTSDSP_OK;
+}
+
+int btsdsp_trx_pull_dev(btsdsp_ctx *ctx, btsdsp_trx *t, const btsdsp_cf32 *bursts, long long pitch, int nframes, int fn0,
+                        int32_t *valid, uint8_t *dgram, int dgram_pitch, void *stream) {
+  ARG(ctx && t && bursts && valid && dgram && nframes > 0 && pitch >= 157 && fn0 >= 0);
+  fn0 %= kHyperframe;
+  ARG(dgram_pitch >= 160 && dgram_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(dgram) & 7) == 0);
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int A = t->narfcn;
+  const long long n = (long long)nframes * A * 8;
+  ARG(n < (1LL << 31));
+  // the slot map is a pure function of (channel combination, FN): evaluate it here, upload one byte per burst
+  auto grow_buf = [&](DevBuf &b, size_t bytes, bool pinned) { return grow(ctx, b, bytes, pinned); };
+  const size_t o_kind = 0, o_tsc = (size_t)((n + 255) & ~255LL), o_slot = 2 * o_tsc, o_idx = o_slot + (size_t)n * 4;
+  const size_t meta_bytes = o_idx + (size_t)n * 4 + 256;
+  int r = grow_buf(t->pin, meta_bytes, true);
+  if (r != BTSDSP_OK) return r;
+  r = grow_buf(t->meta, meta_bytes, false);
+  if (r != BTSDSP_OK) return r;
+  CK(cudaEventSynchronize(t->meta_done));                  // staging is free again
+  uint8_t *hp = (uint8_t *)t->pin.p;
+  uint8_t *kind = hp + o_kind, *tscb = hp + o_tsc;
+  int *slot = (int *)(hp + o_slot), *idx = (int *)(hp + o_idx);
+  long long nr = 0;
+  for (int f = 0; f < nframes; f++) {
+    const int fn = (int)(((long long)fn0 + f) % kHyperframe);
+    for (int a = 0; a < A; a++) {
+      const long long i0 = ((long long)f * A + a) * 8;
+      for (int tn = 0; tn < 8; tn++) {
+        const int c = expected_corr_type(t->chan_type[(size_t)a * 8 + tn], fn);
+        kind[i0 + tn] = (uint8_t)c;
+        tscb[i0 + tn] = t->tsc[a];
+        if (c == CORR_RACH) { slot[i0 + tn] = (int)nr; idx[nr++] = (int)(i0 + tn); } else slot[i0 + tn] = -1;
+      }
+    }
+  }
+  uint8_t *dm = (uint8_t *)t->meta.p;
+  CK(cudaMemcpyAsync(dm, hp, meta_bytes, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(t->meta_done, st));
+  r = grow_buf(t->scratch, trx_scratch_bytes(n, nr, A), false);
+  if (r != BTSDSP_OK) return r;
+  const int nl = launch_trx_pull(ctx->T, t->d_state, A, nframes, fn0, (const cf *)bursts, pitch, dm + o_kind, dm + o_tsc,
+                                 (const int *)(dm + o_idx), (const int *)(dm + o_slot), nr, t->scratch.p, valid, dgram,
+                                 dgram_pitch, st);
+  LAUNCHED("trx_pull", nl);
+  return BTSDSP_OK;
+}
+
+int btsdsp_trx_pull_host(btsdsp_ctx *ctx, btsdsp_trx *t, const btsdsp_cf32 *bursts, long long pitch, int nframes, int fn0,
+                         int32_t *valid, uint8_t *dgram, int dgram_pitch) {
+  ARG(ctx && t && bursts && valid && dgram && nframes > 0 && pitch >= 157 && dgram_pitch >= 158);
+  DeviceGuard g(ctx->device);
+  const long long n = (long long)nframes * t->narfcn * 8;
+  size_t total = 0;
+  auto take = [&total](size_t bytes) { size_t o = (total + 255) & ~(size_t)255; total = o + bytes; return o; };
+  const size_t o_b = take((size_t)n * pitch * sizeof(cf)), o_v = take((size_t)n * 4), o_d = take((size_t)n * 160);
+  int r = grow(ctx, t->io, total, false);
+  if (r != BTSDSP_OK) return r;
+  uint8_t *d = (uint8_t *)t->io.p;
+  cudaStream_t st = ctx->st;
+  CK(cudaMemcpyAsync(d + o_b, bursts, (size_t)n * pitch * sizeof(cf), cudaMemcpyHostToDevice, st));
+  r = btsdsp_trx_pull_dev(ctx, t, (const btsdsp_cf32 *)(d + o_b), pitch, nframes, fn0, (int32_t *)(d + o_v), d + o_d, 160, st);
+  if (r != BTSDSP_OK) return r;
+  CK(cudaMemcpyAsync(valid, d + o_v, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpy2DAsync(dgram, dgram_pitch, d + o_d, 160, 158, (size_t)n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return BTSDSP_OK;
+}
+
 }  // extern "C"

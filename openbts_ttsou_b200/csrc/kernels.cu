@@ -18,6 +18,7 @@ namespace btsdsp {
 // burst addressing
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void burst_loc(const BurstSrc &s, long long i, long long *start, int *len) {
+  if (s.gather) i = s.gather[i];
   const long long g = s.first + i;
   const int q = (int)(g & 3);
   const int rule_len = (q == 0 ? 157 : 156) * s.sps;
@@ -263,11 +264,15 @@ constexpr size_t kEqTileBytes = (size_t)kEqRows * kTileStride * sizeof(cf);
 template <int WARPS> constexpr size_t detect_smem() { return kGridBytes + WARPS * kDetTileBytes; }
 template <int WARPS> constexpr size_t equalize_smem() { return WARPS * kEqTileBytes; }
 
-template <int WARPS>
+// POLICY = pass 1 of the caller-policy pipeline (trx_policy.cuh): the energy is measured but not judged, the analysis
+// runs on the slots `kind` marks as TSC, and the results go to a DetRec instead of into a DFE design.
+template <int WARPS, bool POLICY = false>
 __global__ void __launch_bounds__(WARPS * 32) k_detect_design(const DevTables *__restrict__ T, BurstSrc src,
                                                               const uint8_t *__restrict__ tsc, long long n,
                                                               float detect_thr, float gate_thr, float snr_thr,
-                                                              NormalOut out, EqParams *__restrict__ eqp) {
+                                                              NormalOut out, EqParams *__restrict__ eqp,
+                                                              const uint8_t *__restrict__ kind = nullptr,
+                                                              DetRec *__restrict__ det = nullptr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float *grid = reinterpret_cast<float *>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_detect_design(const DevTables *_
   const long long w0 = ((long long)blockIdx.x * WARPS + warp) * 32;
   if (w0 >= n) return;
   const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
-  const bool gated = gate_thr >= 0.0F;
+  const bool gated = POLICY || gate_thr >= 0.0F;
   const long long i = w0 + lane;
   long long start = 0;
   int len = 0;
@@ -285,6 +290,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_detect_design(const DevTables *_
 
   // ---- energy gate first (its 20-sample window shares the tile): stage, evaluate, then overwrite
   bool pass = true;
+  float avg_pwr = 0.0F;
   if (gated) {
     cf v[20];
 #pragma unroll
@@ -299,7 +305,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_detect_design(const DevTables *_
       A[r * kTileStride + j] = v[it];
     }
     __syncwarp();
-    if (lane < nv) pass = energy_detect<kTileStride>(View<kTileStride>{A + lane}, len, 20, gate_thr, nullptr);   // Transceiver.cpp:298
+    if (lane < nv) pass = energy_detect<kTileStride>(View<kTileStride>{A + lane}, len, 20, gate_thr, POLICY ? &avg_pwr : nullptr);   // Transceiver.cpp:298
+    if (POLICY && lane < nv) pass = kind[i] == CORR_TSC;
     __syncwarp();
   }
   // ---- staging: element e = it*32 + lane of the warp's nv x 36 window samples (burst e/36, sample 56 + e%36)
@@ -326,6 +333,15 @@ __global__ void __launch_bounds__(WARPS * 32) k_detect_design(const DevTables *_
   cf amp = mk(0.0F, 0.0F), ia = mk(0.0F, 0.0F), chan[6], w[7], fb[5];
   float toa = 0.0F, off = 0.0F;
   if (pass) ok = analyze_fast<kTileStride>(g, T, a.at(kDetWin), a, tsc[i], detect_thr, &amp, &toa, chan, &off);
+  if (POLICY) {
+    float4 *q = reinterpret_cast<float4 *>(det + i);
+    q[0] = make_float4(avg_pwr, ok ? 1.0F : 0.0F, amp.x, amp.y);
+    q[1] = make_float4(toa, ok ? off : 0.0F, 0.0F, 0.0F);
+    q[2] = ok ? make_float4(chan[0].x, chan[0].y, chan[1].x, chan[1].y) : make_float4(0.F, 0.F, 0.F, 0.F);
+    q[3] = ok ? make_float4(chan[2].x, chan[2].y, chan[3].x, chan[3].y) : make_float4(0.F, 0.F, 0.F, 0.F);
+    q[4] = ok ? make_float4(chan[4].x, chan[4].y, chan[5].x, chan[5].y) : make_float4(0.F, 0.F, 0.F, 0.F);
+    return;
+  }
   if (ok) {
     // Transceiver.cpp:340  SNRestimate = amplitude.norm2()/(thr*thr + 1.0)  (double division)
     const float SNR = (float)((double)cnorm2(amp) / ((double)BTS_MUL(snr_thr, snr_thr) + 1.0));
@@ -375,7 +391,8 @@ __device__ __forceinline__ unsigned soft_u8(float s) { return (unsigned)(int)rou
 template <int WARPS, bool U8>
 __global__ void __launch_bounds__(WARPS * 32) k_equalize_fast(const DevTables *__restrict__ T, BurstSrc src, long long n,
                                                               const EqParams *__restrict__ eqp, void *__restrict__ soft_,
-                                                              int soft_pitch) {
+                                                              int soft_pitch, int row_bytes = 0) {
+  const int row_words = (row_bytes > 0 ? row_bytes : soft_pitch) / 4;   // U8: bytes of each row this kernel owns
   float *soft = reinterpret_cast<float *>(soft_);
   unsigned char *soft8 = reinterpret_cast<unsigned char *>(soft_);
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -408,7 +425,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_equalize_fast(const DevTables *_
   unsigned *row8 = reinterpret_cast<unsigned *>(soft8 + i * (long long)soft_pitch);
   const bool vec = ((reinterpret_cast<uintptr_t>(row) | (uintptr_t)(soft_pitch * 4)) & 15) == 0;
   if (!ok && lane < nv) {                       // undetected: the row is all zeros (written while the others equalise)
-    if (U8) for (int m = 0; m < soft_pitch / 4; m++) row8[m] = 0u;
+    if (U8) for (int m = 0; m < row_words; m++) row8[m] = 0u;
     else if (vec) for (int m = 0; m < soft_pitch; m += 4) *reinterpret_cast<float4 *>(row + m) = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
     else for (int m = 0; m < soft_pitch; m++) row[m] = 0.0F;
   }
@@ -468,7 +485,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_equalize_fast(const DevTables *_
     }
   }
   if (ok) {
-    if (U8) for (int m = 37; m < soft_pitch / 4; m++) row8[m] = 0u;
+    if (U8) for (int m = 37; m < row_words; m++) row8[m] = 0u;
     else for (int m = len; m < soft_pitch; m++) row[m] = 0.0F;
   }
 }
@@ -833,8 +850,14 @@ void launch_equalize_generic(const DevTables *T, cf *burst, int n, float toa, co
   k_equalize_generic<<<1, 32, 0, st>>>(T, burst, n, toa, w, nw, b, nb, tmp, soft);
 }
 
+#include "trx_kernels.cuh"
+
 int configure_kernels() {
   cudaError_t e;
+  e = cudaFuncSetAttribute(k_detect_design<15, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<15>());
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_detect_design<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<1>());
+  if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_detect_design<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<15>());
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_detect_design<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<1>());

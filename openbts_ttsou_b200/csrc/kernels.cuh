@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "tables.h"
+#include "trx_policy.cuh"
 
 namespace btsdsp {
 
@@ -16,6 +17,7 @@ struct BurstSrc {
   const int *lens;
   long long first;
   int sps;
+  const int *gather = nullptr;   // optional: burst i of the call is burst gather[i] of the array (outputs stay compact)
 };
 
 struct NormalOut {      // per burst; null pointers are skipped
@@ -78,6 +80,11 @@ int launch_equalize(const DevTables *T, BurstSrc src, long long n, const float *
 int launch_demodulate(const DevTables *T, BurstSrc src, long long n, const cf *amp, const float *toa, float *soft,
                       int soft_pitch, cf *scratch, cudaStream_t st);
 int launch_design_dfe(const cf *chan, const float *snr, long long n, cf *w, cf *b, cudaStream_t st);
+// the caller-policy pipeline (trx_policy.cuh / trx_kernels.cuh)
+size_t trx_scratch_bytes(long long n, long long nr, int narfcn);
+int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, int fn0, const cf *bursts, long long pitch,
+                    const uint8_t *kind, const uint8_t *tsc, const int *rach_idx, const int *rach_slot, long long nr,
+                    void *scratch, int *valid, unsigned char *dgram, int dgram_pitch, cudaStream_t stream);
 
 // scratch (complex samples) the generic-sps global-memory variants need per burst
 __host__ __device__ inline size_t scratch_per_burst(int sps) { return (size_t)(2 * 157 + 36) * sps + 64; }

@@ -39,6 +39,9 @@ struct DevTables {
   // itself produces lies on the 1/512 grid (peakDetect's early-late search), so these 21-tap rows
   // are the only interpolators the batched kernels ever need.  Row pitch 24 floats (96 B).
   float sinc_grid[kSincGrid][24];
+  // exp(-n), n = 0..1023, as the host's libm rounds it: the adaptive energy threshold of the caller policy
+  // (Transceiver.cpp:355) is a double that must evolve exactly as on the CPU
+  double exp_neg[1024];
 };
 
 }  // namespace btsdsp

@@ -49,6 +49,7 @@ inline void host_fill_tables(DevTables *h, int sps) {
     for (int k = 0; k < 16; k++) h->rx_poly[br][k] = (br + kRxP * k < kRxTaps) ? h->lpf_rx[br + kRxP * k] : 0.0F;
   for (int br = 0; br < kTxP; br++)
     for (int k = 0; k < 8; k++) h->tx_poly[br][k] = (br + kTxP * k < kTxTaps) ? h->lpf_tx[br + kTxP * k] : 0.0F;
+  for (int n = 0; n < 1024; n++) h->exp_neg[n] = exp(-(double)n);   // Transceiver.cpp:355 exp(-framesElapsed), host libm
 }
 
 }  // namespace btsdsp

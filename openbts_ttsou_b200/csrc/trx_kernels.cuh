@@ -1,0 +1,214 @@
+// trx_kernels.cuh -- kernels of the caller-policy pipeline (see trx_policy.cuh); included by kernels.cu.
+// A batch is nframes x narfcn x 8 bursts laid out [frame][arfcn][tn] at a fixed pitch; FN = fn0 + frame.
+
+struct __align__(16) DfeRec {           // a designed equaliser, by the index of the burst it was estimated from
+  cf w[7];
+  cf b[5];
+  float off, pad[3];
+};
+
+// pass 2: one thread per ARFCN walks its bursts in FIFO order
+__global__ void k_trx_policy(const DevTables *__restrict__ T, TrxState *__restrict__ st, int narfcn, int nframes, int fn0,
+                             const DetRec *__restrict__ det, const int *__restrict__ rach_slot,
+                             const int *__restrict__ rach_flag, int *__restrict__ act, float *__restrict__ snr,
+                             int *__restrict__ commit) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= narfcn) return;
+  TrxState s = st[a];
+  int cm[8];
+  trx_policy_arfcn(s, nframes, fn0, narfcn, a, det, rach_slot, rach_flag, T->exp_neg, act, snr, cm);
+  // w, b and chan_off of the state are committed by k_trx_commit once pass 3 has designed them
+  st[a].thr = s.thr;
+  st[a].prev_false_fn = s.prev_false_fn;
+  for (int tn = 0; tn < 8; tn++) {
+    st[a].est_fn[tn] = s.est_fn[tn];
+    st[a].have[tn] = s.have[tn];
+    st[a].snr[tn] = s.snr[tn];
+    commit[a * 8 + tn] = cm[tn];
+  }
+}
+
+// pass 3a: designDFE for the bursts that re-estimate (Transceiver.cpp:346-347)
+__global__ void k_trx_design(long long n, const DetRec *__restrict__ det, const int *__restrict__ act,
+                             const float *__restrict__ snr, DfeRec *__restrict__ dfe) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || act[i] != (int)i) return;
+  const DetRec d = det[i];
+  const cf ia = cdiv(mk(1.0F, 0.0F), mk(d.amp_x, d.amp_y));
+  cf ch[6], w[7], fb[5];
+#pragma unroll
+  for (int j = 0; j < 6; j++) ch[j] = cmul(d.chan[j], ia);                               // scaleVector :346
+  design_dfe<7, 5>(ch, 5, snr[i], 7, w, fb);                                             // :347
+  DfeRec r;
+#pragma unroll
+  for (int j = 0; j < 7; j++) r.w[j] = w[j];
+#pragma unroll
+  for (int j = 0; j < 5; j++) r.b[j] = fb[j];
+  r.off = d.off;
+  r.pad[0] = r.pad[1] = r.pad[2] = 0.0F;
+  dfe[i] = r;
+}
+
+// pass 3b: the equaliser's per-burst parameters: 1/amplitude, TOA - chanRespOffset, the (possibly cached) taps (:391-396)
+__global__ void k_trx_eqparams(long long n, int narfcn, const DetRec *__restrict__ det, const int *__restrict__ act,
+                               const DfeRec *__restrict__ dfe, const TrxState *__restrict__ st, EqParams *__restrict__ eqp) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  EqParams e;
+  const int a = act[i];
+  if (a >= 0 || a == ACT_CARRIED) {
+    const DetRec d = det[i];
+    const cf ia = cdiv(mk(1.0F, 0.0F), mk(d.amp_x, d.amp_y));
+    float off;
+    if (a >= 0) {
+      const DfeRec r = dfe[a];
+#pragma unroll
+      for (int j = 0; j < 7; j++) e.w[j] = r.w[j];
+#pragma unroll
+      for (int j = 0; j < 5; j++) e.b[j] = r.b[j];
+      off = r.off;
+    } else {
+      const int arfcn = (int)((i >> 3) % narfcn), tn = (int)(i & 7);
+#pragma unroll
+      for (int j = 0; j < 7; j++) e.w[j] = st[arfcn].w[tn][j];
+#pragma unroll
+      for (int j = 0; j < 5; j++) e.b[j] = st[arfcn].b[tn][j];
+      off = st[arfcn].chan_off[tn];
+    }
+    e.ia_x = ia.x; e.ia_y = ia.y; e.toa_eq = BTS_SUB(d.toa, off); e.ok = 1.0F;
+  } else {
+    e.ia_x = e.ia_y = e.toa_eq = e.ok = 0.0F;
+#pragma unroll
+    for (int j = 0; j < 7; j++) e.w[j] = mk(0.0F, 0.0F);
+#pragma unroll
+    for (int j = 0; j < 5; j++) e.b[j] = mk(0.0F, 0.0F);
+  }
+  eqp[i] = e;
+}
+
+// RACH bursts the policy did not accept (energy gate) must not be demodulated
+__global__ void k_trx_rach_veto(long long nr, const int *__restrict__ rach_idx, const int *__restrict__ act,
+                                EqParams *__restrict__ eqp_r) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nr) return;
+  if (act[rach_idx[j]] != ACT_RACH) reinterpret_cast<float4 *>(eqp_r + j)[0].w = 0.0F;
+}
+
+// pass 3c: RX datagrams (Transceiver.cpp:400-402, 659-673): one warp per burst.  The equaliser has already written the
+// 148 soft bytes of the normal bursts (and zeros elsewhere) at dgram + 8; RACH soft bits come from the compact float rows.
+__global__ void k_trx_datagram(long long n, int narfcn, int fn0, const DetRec *__restrict__ det, const int *__restrict__ act,
+                               const int *__restrict__ rach_slot, const cf *__restrict__ rach_amp,
+                               const float *__restrict__ rach_toa, const float *__restrict__ rach_soft, int rach_soft_pitch,
+                               int *__restrict__ valid, unsigned char *__restrict__ dgram, int dgram_pitch) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  unsigned char *dg = dgram + i * (long long)dgram_pitch;
+  const int a = act[i];
+  if (a == ACT_NONE) {                      // bytes 8..159 were zeroed by the equaliser
+    if (lane < 8) dg[lane] = 0;
+    if (lane == 8) valid[i] = 0;
+    return;
+  }
+  const int tn = (int)(i & 7), fn = (int)((fn0 + i / (8LL * narfcn)) % kHyperframe);
+  cf amp;
+  float toa;
+  if (a == ACT_RACH) {
+    const int j = rach_slot[i];
+    amp = rach_amp[j]; toa = rach_toa[j];
+    const float *sp = rach_soft + (long long)j * rach_soft_pitch;
+    for (int m = lane; m < 148; m += 32) dg[8 + m] = trx_soft_byte(sp[m]);
+  } else {
+    amp = mk(det[i].amp_x, det[i].amp_y); toa = det[i].toa;
+  }
+  if (lane == 0) {
+    trx_datagram_header(dg, tn, fn, amp, toa, 1);
+    valid[i] = 1;
+  }
+}
+
+// after pass 3: the cache entries that changed in this batch become the state carried to the next one
+__global__ void k_trx_commit(int narfcn, const int *__restrict__ commit, const DfeRec *__restrict__ dfe, TrxState *__restrict__ st) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= narfcn * 8) return;
+  const int src = commit[k];
+  if (src < 0) return;
+  const int a = k >> 3, tn = k & 7;
+  const DfeRec r = dfe[src];
+  for (int j = 0; j < 7; j++) st[a].w[tn][j] = r.w[j];
+  for (int j = 0; j < 5; j++) st[a].b[tn][j] = r.b[j];
+  st[a].chan_off[tn] = r.off;
+}
+
+struct TrxScratch {                     // device scratch of one pull (caller-owned, sized by trx_scratch_bytes)
+  DetRec *det; int *act; float *snr; DfeRec *dfe; EqParams *eqp; int *commit;
+  int *rach_flag; cf *rach_amp; float *rach_toa; float *rach_soft; EqParams *eqp_r;
+};
+constexpr int kTrxRachSoftPitch = 160;
+size_t trx_scratch_bytes(long long n, long long nr, int narfcn) {
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  return up(n * sizeof(DetRec)) + up(n * 4) + up(n * 4) + up(n * sizeof(DfeRec)) + up(n * sizeof(EqParams)) + up((size_t)narfcn * 8 * 4) +
+         up(nr * 4 + 4) + up(nr * 8 + 8) + up(nr * 4 + 4) + up(nr * kTrxRachSoftPitch * 4 + 4) + up(nr * sizeof(EqParams) + 16);
+}
+static TrxScratch trx_carve(void *base, long long n, long long nr, int narfcn) {
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  char *p = reinterpret_cast<char *>(base);
+  TrxScratch s;
+  s.det = (DetRec *)p; p += up(n * sizeof(DetRec));
+  s.act = (int *)p; p += up(n * 4);
+  s.snr = (float *)p; p += up(n * 4);
+  s.dfe = (DfeRec *)p; p += up(n * sizeof(DfeRec));
+  s.eqp = (EqParams *)p; p += up(n * sizeof(EqParams));
+  s.commit = (int *)p; p += up((size_t)narfcn * 8 * 4);
+  s.rach_flag = (int *)p; p += up(nr * 4 + 4);
+  s.rach_amp = (cf *)p; p += up(nr * 8 + 8);
+  s.rach_toa = (float *)p; p += up(nr * 4 + 4);
+  s.rach_soft = (float *)p; p += up(nr * kTrxRachSoftPitch * 4 + 4);
+  s.eqp_r = (EqParams *)p;
+  return s;
+}
+
+// The whole pull for one batch.  kind / tsc: one byte per burst (CorrType, midamble code); rach_idx: the nr bursts in
+// RACH slots; rach_slot: per burst, its index in rach_idx or -1.  All device pointers.  Returns the launch count.
+int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, int fn0, const cf *bursts, long long pitch,
+                    const uint8_t *kind, const uint8_t *tsc, const int *rach_idx, const int *rach_slot, long long nr,
+                    void *scratch, int *valid, unsigned char *dgram, int dgram_pitch, cudaStream_t stream) {
+  const long long n = (long long)nframes * narfcn * 8;
+  if (n <= 0) return 0;
+  const TrxScratch s = trx_carve(scratch, n, nr, narfcn);
+  BurstSrc src{bursts, pitch, nullptr, 0, 1};
+  int launches = 0;
+  const long long nwarps = (n + 31) / 32;
+  NormalOut none{};
+  // pass 1
+  if (nwarps >= 148 * 15)
+    k_detect_design<15, true><<<(unsigned)((nwarps + 14) / 15), 480, detect_smem<15>(), stream>>>(T, src, tsc, n, 3.0F, 0.0F, 0.0F, none,
+                                                                                             nullptr, kind, s.det);
+  else
+    k_detect_design<1, true><<<(unsigned)nwarps, 32, detect_smem<1>(), stream>>>(T, src, tsc, n, 3.0F, 0.0F, 0.0F, none, nullptr, kind, s.det);
+  launches++;
+  BurstSrc rsrc = src;
+  rsrc.gather = rach_idx;
+  if (nr > 0) {
+    NormalOut ro{};
+    ro.flag = s.rach_flag; ro.amp = s.rach_amp; ro.toa = s.rach_toa;
+    k_rach_detect<<<(unsigned)((nr + 31) / 32), 32, kRachTileBytes, stream>>>(T, rsrc, nr, 5.0F, ro, s.eqp_r);
+    launches++;
+  }
+  // pass 2
+  k_trx_policy<<<(narfcn + 31) / 32, 32, 0, stream>>>(T, st, narfcn, nframes, fn0, s.det, rach_slot, s.rach_flag, s.act, s.snr, s.commit);
+  // pass 3
+  k_trx_design<<<(unsigned)((n + 63) / 64), 64, 0, stream>>>(n, s.det, s.act, s.snr, s.dfe);
+  k_trx_eqparams<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, narfcn, s.det, s.act, s.dfe, st, s.eqp);
+  k_equalize_fast<1, true><<<(unsigned)nwarps, 32, equalize_smem<1>(), stream>>>(T, src, n, s.eqp, dgram + 8, dgram_pitch, 152);
+  launches += 4;
+  if (nr > 0) {
+    k_trx_rach_veto<<<(unsigned)((nr + 127) / 128), 128, 0, stream>>>(nr, rach_idx, s.act, s.eqp_r);
+    k_slicer_fast<<<(unsigned)((nr + 31) / 32), 32, kEqTileBytes, stream>>>(T, rsrc, nr, s.eqp_r, s.rach_soft, kTrxRachSoftPitch);
+    launches += 2;
+  }
+  k_trx_datagram<<<(unsigned)((n * 32 + 127) / 128), 128, 0, stream>>>(n, narfcn, fn0, s.det, s.act, rach_slot, s.rach_amp, s.rach_toa,
+                                                                      s.rach_soft, kTrxRachSoftPitch, valid, dgram, dgram_pitch);
+  k_trx_commit<<<(narfcn * 8 + 127) / 128, 128, 0, stream>>>(narfcn, s.commit, s.dfe, st);
+  return launches + 2;
+}

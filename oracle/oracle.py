@@ -234,6 +234,38 @@ class Oracle:
         self._run(self._shard(n, threads), job)
         return r
 
+    # ---- Transceiver::pullRadioVector policy + RX datagram ----
+    TRX_STATE_DTYPE = np.dtype([("thr", np.float64), ("prev_false_fn", np.int32), ("tsc", np.int32),
+                                ("chan_type", np.int32, 8), ("est_fn", np.int32, 8), ("have", np.int32, 8),
+                                ("snr", np.float32, 8), ("chan_off", np.float32, 8),
+                                ("w", np.complex64, (8, 7)), ("b", np.complex64, (8, 5))], align=True)
+
+    def expected_corr_type(self, chan_type, fn):
+        f = self._f("expected_corr_type")
+        f.restype = ctypes.c_int
+        return f(c_i(chan_type), c_i(fn))
+
+    def trx_new(self, tsc, chan_type, start_fn=0):
+        """one Transceiver object's receive-side state (one ARFCN)"""
+        f = self._f("trx_state_bytes")
+        f.restype = ctypes.c_int
+        assert f() == self.TRX_STATE_DTYPE.itemsize, (f(), self.TRX_STATE_DTYPE.itemsize)
+        st = np.zeros(1, self.TRX_STATE_DTYPE)
+        ct = np.ascontiguousarray(chan_type, np.int32)
+        self._f("trx_init")(_ptr(st), c_i(tsc), _ptr(ct), c_i(start_fn))
+        return st
+
+    def trx_pull(self, st, bursts, fn0):
+        """bursts: (nframes*8, pitch) complex64 in FIFO order (frame-major, TN 0..7).  Updates st in place.
+        Returns (valid[n] int32, dgram[n,160] uint8: 158 datagram bytes + 2 pad)."""
+        bursts = _c64(bursts)
+        n, pitch = bursts.shape
+        assert n % 8 == 0
+        valid = np.zeros(n, np.int32)
+        dg = np.zeros((n, 160), np.uint8)
+        self._f("trx_pull")(_ptr(st), _ptr(bursts), c_i(pitch), c_i(n // 8), c_i(fn0), _ptr(valid), _ptr(dg), c_i(160))
+        return valid, dg
+
     def rx_rach_batch(self, bursts, lens, detect_thr=5.0, sps=1, threads=1):
         bursts = _c64(bursts)
         n, pitch = bursts.shape

@@ -345,4 +345,162 @@ void ref_rx_stream_demod(const float *resampled, long first_burst, long nbursts,
   }
 }
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Transceiver::pullRadioVector + driveReceiveFIFO (Transceiver.cpp:207-269, 271-410, 641-676), the caller policy
+ * around the path: slot map, adaptive energy threshold, 50-frame channel/DFE cache, RSSI / timing integerisation
+ * and the RX datagram.  Transceiver.cpp itself cannot be compiled here (needs libusrp headers), so its glue is
+ * restated below line by line; every DSP call is the real reference function from sigProcLib.cpp.
+ *
+ * One `trx` = one Transceiver object (one ARFCN).  State layout (doubles/ints, mirrored by the port and the CUDA
+ * side):  thr (mEnergyThreshold, double), prev_false_fn, per TN: est_fn, have (channelResponse != NULL),
+ * snr (float), chan_off (float), chan_amp[2] (unused downstream), w[14], b[10].
+ * Bursts arrive in FIFO order: frame f = 0..nframes-1 (FN = fn0 + f), TN = 0..7, at
+ * bursts + 2*pitch*((f*8)+tn) floats, length 157 if tn%4==0 else 156 (sps 1).
+ * Output per burst: valid[i], and a 158-byte datagram at dgram + dgram_pitch*i (byte 156 is never written by the
+ * reference; it is set to 0 here).
+ * ------------------------------------------------------------------------------------------------ */
+struct ref_trx_state {
+  double thr;
+  int prev_false_fn;
+  int tsc;
+  int chan_type[8];
+  int est_fn[8];
+  int have[8];
+  float snr[8];
+  float chan_off[8];
+  float w[8][14];
+  float b[8][10];
+};
+enum { CT_NONE = 0, CT_I, CT_II, CT_III, CT_IV, CT_V, CT_VI, CT_VII, CT_LOOPBACK };   /* Transceiver.h ChannelCombination */
+enum { CORR_OFF = 0, CORR_TSC, CORR_RACH, CORR_IDLE };
+static const int kHyper = 2048 * 26 * 51;
+static int fn_delta(int v1, int v2) {                     /* GSM::FNDelta, GSMCommon.cpp:161-168 */
+  const int half = kHyper / 2;
+  int d = v1 - v2;
+  if (d >= half) d -= kHyper; else if (d < -half) d += kHyper;
+  return d;
+}
+int ref_expected_corr_type(int chan_type, int fn) {       /* Transceiver.cpp:207-269 */
+  switch (chan_type) {
+    case CT_NONE: return CORR_OFF;
+    case CT_I: return CORR_TSC;
+    case CT_II: return (fn % 2 == 1) ? CORR_IDLE : CORR_TSC;
+    case CT_III: return CORR_TSC;
+    case CT_IV: case CT_VI: return ((fn % 51) % 10 < 2) ? CORR_RACH : CORR_OFF;
+    case CT_V: {
+      int m = fn % 51;
+      if (m <= 36 && m >= 14) return CORR_RACH;
+      if (m == 4 || m == 5) return CORR_RACH;
+      if (m == 45 || m == 46) return CORR_RACH;
+      return CORR_TSC;
+    }
+    case CT_VII: {
+      int m = fn % 51;
+      if (m == 12 || m == 13 || m == 14) return CORR_IDLE;
+      return CORR_TSC;
+    }
+    case CT_LOOPBACK: {
+      int m = fn % 51;
+      return (m <= 50 && m >= 48) ? CORR_IDLE : CORR_TSC;
+    }
+    default: return CORR_OFF;
+  }
+}
+int ref_trx_state_bytes(void) { return (int)sizeof(ref_trx_state); }
+void ref_trx_init(ref_trx_state *st, int tsc, const int *chan_type, int start_fn) {   /* Transceiver.cpp:40-90 */
+  memset(st, 0, sizeof *st);
+  st->thr = 250.0;
+  st->prev_false_fn = start_fn;
+  st->tsc = tsc;
+  for (int i = 0; i < 8; i++) { st->chan_type[i] = chan_type[i]; st->est_fn[i] = start_fn; st->have[i] = 0; }
+}
+void ref_trx_pull(ref_trx_state *st, const float *bursts, int pitch, int nframes, int fn0,
+                  int *valid, unsigned char *dgram, int dgram_pitch) {
+  for (int f = 0; f < nframes; f++) {
+    const int fn = (fn0 + f) % kHyper;
+    for (int tn = 0; tn < 8; tn++) {
+      const long i = (long)f * 8 + tn;
+      valid[i] = 0;
+      unsigned char *dg = dgram + (size_t)dgram_pitch * i;
+      memset(dg, 0, 158);
+      const int corr = ref_expected_corr_type(st->chan_type[tn], fn);
+      if (corr == CORR_OFF || corr == CORR_IDLE) continue;                               /* :290-293 */
+      const int len = (tn % 4 == 0) ? 157 : 156;
+      signalVector burst(len);
+      memcpy(burst.begin(), bursts + 2 * (size_t)pitch * i, len * sizeof(complex));
+      complex amplitude = 0.0;
+      float TOA = 0.0F, avgPwr = 0.0F;
+      if (!energyDetect(burst, 20, st->thr, &avgPwr)) {                                  /* :298 (double -> float thr) */
+        double framesElapsed = fn_delta(fn, st->prev_false_fn);
+        if (framesElapsed > 50) { st->thr -= 10.0; st->prev_false_fn = fn; }           /* :300-304 */
+        continue;
+      }
+      bool success = false;
+      if (corr == CORR_TSC) {
+        double framesElapsed = fn_delta(fn, st->est_fn[tn]);
+        bool estimateChannel = false;
+        if (framesElapsed > 50 || !st->have[tn]) { st->have[tn] = 0; estimateChannel = true; }   /* :317-326 */
+        signalVector *channelResp = NULL;
+        float chanOffset = 0.0F;
+        success = analyzeTrafficBurst(burst, st->tsc, 3.0, 1, &amplitude, &TOA, estimateChannel, &channelResp, &chanOffset);
+        if (success) {
+          st->thr -= 1.0F;
+          if (st->thr < 0.0) st->thr = 0.0;
+          st->snr[tn] = amplitude.norm2() / (st->thr * st->thr + 1.0);                   /* :340 */
+          if (estimateChannel) {
+            st->have[tn] = 1;
+            st->chan_off[tn] = chanOffset;
+            scaleVector(*channelResp, complex(1.0, 0.0) / amplitude);
+            signalVector *W = NULL, *B = NULL;
+            designDFE(*channelResp, st->snr[tn], 7, &W, &B);
+            put(*W, st->w[tn]); put(*B, st->b[tn]);
+            delete W; delete B;
+            st->est_fn[tn] = fn;
+          }
+        } else {
+          double fe = fn_delta(fn, st->prev_false_fn);
+          st->thr += 10.0F * exp(-fe);                                                   /* :355 */
+          st->prev_false_fn = fn;
+          st->have[tn] = 0;                                                              /* :357 channelResponse = NULL */
+        }
+        if (channelResp) delete channelResp;
+      } else {
+        success = detectRACHBurst(burst, 5.0, 1, &amplitude, &TOA);
+        if (success) {
+          st->thr -= 1.0F;
+          if (st->thr < 0.0) st->thr = 0.0;
+          st->have[tn] = 0;                                                              /* :371 */
+        } else {
+          double fe = fn_delta(fn, st->prev_false_fn);
+          st->thr += 10.0F * exp(-fe);
+          st->prev_false_fn = fn;
+        }
+      }
+      if (!success) continue;
+      SoftVector *soft;
+      if (corr == CORR_RACH) {
+        soft = demodulateBurst(burst, *gPulse, 1, amplitude, TOA);
+      } else {
+        scaleVector(burst, complex(1.0, 0.0) / amplitude);
+        signalVector W(7), B(5);
+        memcpy(W.begin(), st->w[tn], 7 * sizeof(complex));
+        memcpy(B.begin(), st->b[tn], 5 * sizeof(complex));
+        soft = equalizeBurst(burst, TOA - st->chan_off[tn], 1, W, B);
+      }
+      const int RSSI = (int)floor(20.0 * log10(9450.0 / amplitude.abs()));               /* :400 */
+      const int timingOffset = (int)round(TOA * 256.0 / 1);                              /* :402 */
+      valid[i] = 1;
+      dg[0] = tn;                                                                        /* :659-673 */
+      for (int k = 0; k < 4; k++) dg[1 + k] = (fn >> ((3 - k) * 8)) & 0x0ff;
+      dg[5] = RSSI;
+      dg[6] = (timingOffset >> 8) & 0x0ff;
+      dg[7] = timingOffset & 0x0ff;
+      SoftVector::iterator it = soft->begin();
+      for (int k = 0; k < 148; k++) dg[8 + k] = (char)round((*it++) * 255.0);
+      delete soft;
+    }
+  }
+}
+
 }  // extern "C"

@@ -648,3 +648,136 @@ void port_rx_stream_demod(const float *resampled, long first_burst, long nbursts
                          soft + (size_t)soft_pitch * i, soft_pitch);
   }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Transceiver::pullRadioVector + driveReceiveFIFO restated (Transceiver.cpp:207-269, 271-410, 641-676):
+ * slot map, adaptive energy threshold, 50-frame channel/DFE cache, RSSI / timing integerisation, RX datagram.
+ * Same state layout and entry points as oracle/ref_shim.cpp's ref_trx_*.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  double thr;
+  int prev_false_fn;
+  int tsc;
+  int chan_type[8];
+  int est_fn[8];
+  int have[8];
+  float snr[8];
+  float chan_off[8];
+  float w[8][14];
+  float b[8][10];
+} port_trx_state;
+enum { CT_NONE = 0, CT_I, CT_II, CT_III, CT_IV, CT_V, CT_VI, CT_VII, CT_LOOPBACK };
+enum { CORR_OFF = 0, CORR_TSC, CORR_RACH, CORR_IDLE };
+#define HYPERFRAME (2048 * 26 * 51)
+static int fn_delta(int v1, int v2) {                     /* GSM::FNDelta, GSMCommon.cpp:161-168 */
+  const int half = HYPERFRAME / 2;
+  int d = v1 - v2;
+  if (d >= half) d -= HYPERFRAME; else if (d < -half) d += HYPERFRAME;
+  return d;
+}
+int port_expected_corr_type(int chan_type, int fn) {      /* Transceiver.cpp:207-269 */
+  int m = fn % 51;
+  switch (chan_type) {
+    case CT_NONE: return CORR_OFF;
+    case CT_I: return CORR_TSC;
+    case CT_II: return (fn % 2 == 1) ? CORR_IDLE : CORR_TSC;
+    case CT_III: return CORR_TSC;
+    case CT_IV: case CT_VI: return (m % 10 < 2) ? CORR_RACH : CORR_OFF;
+    case CT_V:
+      if ((m <= 36 && m >= 14) || m == 4 || m == 5 || m == 45 || m == 46) return CORR_RACH;
+      return CORR_TSC;
+    case CT_VII: return (m == 12 || m == 13 || m == 14) ? CORR_IDLE : CORR_TSC;
+    case CT_LOOPBACK: return (m <= 50 && m >= 48) ? CORR_IDLE : CORR_TSC;
+    default: return CORR_OFF;
+  }
+}
+int port_trx_state_bytes(void) { return (int)sizeof(port_trx_state); }
+void port_trx_init(void *state, int tsc, const int *chan_type, int start_fn) {   /* Transceiver.cpp:40-90 */
+  port_trx_state *st = (port_trx_state *)state;
+  memset(st, 0, sizeof *st);
+  st->thr = 250.0;
+  st->prev_false_fn = start_fn;
+  st->tsc = tsc;
+  for (int i = 0; i < 8; i++) { st->chan_type[i] = chan_type[i]; st->est_fn[i] = start_fn; st->have[i] = 0; }
+}
+void port_trx_pull(void *state, const float *bursts, int pitch, int nframes, int fn0,
+                   int *valid, unsigned char *dgram, int dgram_pitch) {
+  port_trx_state *st = (port_trx_state *)state;
+  for (int f = 0; f < nframes; f++) {
+    const int fn = (fn0 + f) % HYPERFRAME;
+    for (int tn = 0; tn < 8; tn++) {
+      const long i = (long)f * 8 + tn;
+      unsigned char *dg = dgram + (size_t)dgram_pitch * i;
+      valid[i] = 0;
+      memset(dg, 0, 158);
+      const int corr = port_expected_corr_type(st->chan_type[tn], fn);
+      if (corr == CORR_OFF || corr == CORR_IDLE) continue;                               /* :290-293 */
+      const int len = (tn % 4 == 0) ? 157 : 156;
+      cpx burst[160];
+      memcpy(burst, bursts + 2 * (size_t)pitch * i, len * sizeof(cpx));
+      cpx amplitude = C(0, 0);
+      float TOA = 0.0F, avgPwr = 0.0F;
+      if (!port_energy_detect((const float *)burst, len, 20, (float)st->thr, &avgPwr)) { /* :298 */
+        double framesElapsed = fn_delta(fn, st->prev_false_fn);
+        if (framesElapsed > 50) { st->thr -= 10.0; st->prev_false_fn = fn; }           /* :300-304 */
+        continue;
+      }
+      int success = 0;
+      if (corr == CORR_TSC) {
+        double framesElapsed = fn_delta(fn, st->est_fn[tn]);
+        int estimateChannel = 0;
+        if (framesElapsed > 50 || !st->have[tn]) { st->have[tn] = 0; estimateChannel = 1; }   /* :317-326 */
+        cpx ch[6];
+        float chanOffset = 0.0F;
+        memset(ch, 0, sizeof ch);
+        success = analyze_(burst, len, st->tsc, 3.0F, 1, &amplitude, &TOA, estimateChannel, ch, &chanOffset);
+        if (success) {
+          st->thr -= 1.0F;
+          if (st->thr < 0.0) st->thr = 0.0;
+          st->snr[tn] = (float)(cnorm2(amplitude) / (st->thr * st->thr + 1.0));          /* :340 */
+          if (estimateChannel) {
+            st->have[tn] = 1;
+            st->chan_off[tn] = chanOffset;
+            scale_(ch, 6, 0, cdiv(C(1.0F, 0.0F), amplitude));                            /* :346 */
+            design_dfe_(ch, 6, st->snr[tn], 7, (cpx *)st->w[tn], (cpx *)st->b[tn]);      /* :347 */
+            st->est_fn[tn] = fn;
+          }
+        } else {
+          double fe = fn_delta(fn, st->prev_false_fn);
+          st->thr += 10.0F * exp(-fe);                                                   /* :355 */
+          st->prev_false_fn = fn;
+          st->have[tn] = 0;                                                              /* :357 */
+        }
+      } else {
+        success = detect_rach_(burst, len, 5.0F, 1, &amplitude, &TOA);
+        if (success) {
+          st->thr -= 1.0F;
+          if (st->thr < 0.0) st->thr = 0.0;
+          st->have[tn] = 0;                                                              /* :371 */
+        } else {
+          double fe = fn_delta(fn, st->prev_false_fn);
+          st->thr += 10.0F * exp(-fe);
+          st->prev_false_fn = fn;
+        }
+      }
+      if (!success) continue;
+      float soft[160];
+      memset(soft, 0, sizeof soft);
+      if (corr == CORR_RACH) {
+        port_demodulate((const float *)burst, len, 1, (const float *)&amplitude, TOA, soft);
+      } else {
+        scale_(burst, len, 0, cdiv(C(1.0F, 0.0F), amplitude));                           /* :391 */
+        equalize_(burst, len, TOA - st->chan_off[tn], 1, (const cpx *)st->w[tn], 7, (const cpx *)st->b[tn], 5, soft);
+      }
+      const int RSSI = (int)floor(20.0 * log10(9450.0 / cabsf_(amplitude)));              /* :400 */
+      const int timingOffset = (int)round(TOA * 256.0 / 1);                              /* :402 */
+      valid[i] = 1;
+      dg[0] = (unsigned char)tn;                                                         /* :659-673 */
+      for (int k = 0; k < 4; k++) dg[1 + k] = (fn >> ((3 - k) * 8)) & 0x0ff;
+      dg[5] = (unsigned char)RSSI;
+      dg[6] = (timingOffset >> 8) & 0x0ff;
+      dg[7] = timingOffset & 0x0ff;
+      for (int k = 0; k < 148; k++) dg[8 + k] = (unsigned char)((int)round(soft[k] * 255.0) & 0xff);   /* what the x86 (char) cast yields */
+    }
+  }
+}

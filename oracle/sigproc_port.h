@@ -46,6 +46,12 @@ long  port_modulate_stream(const char *bits148, long nbursts, int tn0, float *ou
 void  port_rx_stream_demod(const float *resampled, long first_burst, long nbursts, const unsigned char *tsc,
                            float detect_thr, float energy_thr, int *flags, float *amp, float *toa,
                            float *soft, int soft_pitch);
+/* Transceiver::pullRadioVector policy + RX datagram (one state = one ARFCN); see sigproc_port.c */
+int   port_expected_corr_type(int chan_type, int fn);
+int   port_trx_state_bytes(void);
+void  port_trx_init(void *state, int tsc, const int *chan_type, int start_fn);
+void  port_trx_pull(void *state, const float *bursts, int pitch, int nframes, int fn0, int *valid,
+                    unsigned char *dgram, int dgram_pitch);
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,25 @@ class Emu:
                                   c_i(160), P(r["chan"]), P(r["off"]), P(r["w"]), P(r["b"]))
         return r
 
+    # ---- caller policy pipeline (trx_policy.cuh) ----
+    def trx_new(self, tsc, chan_type, start_fn=0):
+        from oracle.oracle import Oracle
+        tsc = np.ascontiguousarray(tsc, np.uint8)
+        ct = np.ascontiguousarray(chan_type, np.uint8).reshape(tsc.size, 8)
+        st = np.zeros(tsc.size, Oracle.TRX_STATE_DTYPE)
+        assert self.lib.emu_trx_state_bytes() == st.itemsize
+        self.lib.emu_trx_init(P(st), c_i(tsc.size), P(tsc), P(ct), c_i(start_fn))
+        return st
+
+    def trx_pull(self, st, bursts, fn0):
+        bursts = np.ascontiguousarray(bursts, np.complex64)
+        n, pitch = bursts.shape
+        valid = np.zeros(n, np.int32)
+        dg = np.zeros((n, 158), np.uint8)
+        self.lib.emu_trx_pull(P(st), c_i(st.size), P(bursts), c_ll(pitch), c_i(n // (8 * st.size)), c_i(fn0), P(valid),
+                              P(dg), c_i(158))
+        return valid, dg
+
     def rx_rach_batch(self, bursts, lens, detect_thr=5.0, tiles=True):
         bursts = np.ascontiguousarray(bursts, np.complex64)
         n, pitch = bursts.shape

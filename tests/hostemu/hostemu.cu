@@ -446,4 +446,111 @@ void emu_resample_tx(const float *in, int has_history, long long nchunks, short 
   }
 }
 
+// The caller-policy pipeline (trx_policy.cuh / trx_kernels.cuh) replayed on the CPU: pass 1 and pass 3 with the generic
+// single-burst device functions, pass 2 with the SAME trx_policy_arfcn the policy kernel runs.
+// state: narfcn TrxState records (in/out).  bursts laid out [frame][arfcn][tn] at `pitch`.
+int emu_trx_state_bytes(void) { return (int)sizeof(TrxState); }
+void emu_trx_init(void *state, int narfcn, const uint8_t *tsc, const uint8_t *chan_type, int start_fn) {
+  TrxState *st = (TrxState *)state;
+  memset(st, 0, sizeof(TrxState) * narfcn);
+  for (int a = 0; a < narfcn; a++) {
+    st[a].thr = 250.0; st[a].prev_false_fn = start_fn; st[a].tsc = tsc[a];
+    for (int tn = 0; tn < 8; tn++) { st[a].chan_type[tn] = chan_type[a * 8 + tn]; st[a].est_fn[tn] = start_fn; }
+  }
+}
+void emu_trx_pull(void *state, int narfcn, const float *bursts, long long pitch, int nframes, int fn0, int *valid,
+                  unsigned char *dgram, int dgram_pitch) {
+  TrxState *st = (TrxState *)state;
+  const long long n = (long long)nframes * narfcn * 8;
+  std::vector<DetRec> det(n);
+  std::vector<int> act(n), slot(n, -1), rflag, ridx;
+  std::vector<float> snr(n, 0.0F), rtoa;
+  std::vector<cf> ramp;
+  std::vector<cf> scratch(scratch_per_burst(1));
+  // pass 1
+  for (long long i = 0; i < n; i++) {
+    const int f = (int)(i / (8LL * narfcn)), a = (int)((i >> 3) % narfcn), tn = (int)(i & 7);
+    const int fn = (fn0 + f) % kHyperframe, len = (tn % 4 == 0) ? 157 : 156;
+    const int corr = expected_corr_type(st[a].chan_type[tn], fn);
+    cf *src = (cf *)bursts + i * pitch;
+    DetRec d;
+    memset(&d, 0, sizeof d);
+    energy_detect<1>(View<1>{src}, len, 20, 0.0F, &d.energy);
+    cf amp = mk(0.0F, 0.0F);
+    float toa = 0.0F, off = 0.0F;
+    if (corr == CORR_TSC) {
+      cf chan[6];
+      for (int j = 0; j < 6; j++) chan[j] = mk(0.0F, 0.0F);
+      cf *s = scratch.data();
+      const bool ok = analyze_traffic<1, true>(T, View<1>{src}, st[a].tsc, 3.0F, 1, View<1>{s}, View<1>{s + 36}, &amp, &toa, true, chan, &off);
+      d.flag = ok ? 1.0F : 0.0F; d.amp_x = amp.x; d.amp_y = amp.y; d.toa = toa; d.off = ok ? off : 0.0F;
+      for (int j = 0; j < 6; j++) d.chan[j] = ok ? chan[j] : mk(0.0F, 0.0F);
+    } else if (corr == CORR_RACH) {
+      cf *s = scratch.data();
+      const bool ok = detect_rach<1, true>(T, View<1>{src}, len, 5.0F, 1, View<1>{s}, &amp, &toa);
+      slot[i] = (int)ridx.size();
+      ridx.push_back((int)i); rflag.push_back(ok); ramp.push_back(amp); rtoa.push_back(toa);
+    }
+    det[i] = d;
+  }
+  if (rflag.empty()) { rflag.push_back(0); }
+  // pass 2
+  std::vector<int> commit(narfcn * 8);
+  for (int a = 0; a < narfcn; a++)
+    trx_policy_arfcn(st[a], nframes, fn0, narfcn, a, det.data(), slot.data(), rflag.data(), T->exp_neg, act.data(), snr.data(),
+                     commit.data() + a * 8);
+  // pass 3
+  struct Dfe { cf w[7], b[5]; float off; };
+  std::vector<Dfe> dfe(n);
+  for (long long i = 0; i < n; i++) {
+    if (act[i] != (int)i) continue;
+    const cf ia = cdiv(mk(1.0F, 0.0F), mk(det[i].amp_x, det[i].amp_y));
+    cf ch[6];
+    for (int j = 0; j < 6; j++) ch[j] = cmul(det[i].chan[j], ia);
+    design_dfe<7, 5>(ch, 5, snr[i], 7, dfe[i].w, dfe[i].b);
+    dfe[i].off = det[i].off;
+  }
+  for (long long i = 0; i < n; i++) {
+    const int f = (int)(i / (8LL * narfcn)), a = (int)((i >> 3) % narfcn), tn = (int)(i & 7);
+    const int fn = (fn0 + f) % kHyperframe, len = (tn % 4 == 0) ? 157 : 156;
+    unsigned char *dg = dgram + i * (long long)dgram_pitch;
+    memset(dg, 0, 158);
+    valid[i] = 0;
+    if (act[i] == ACT_NONE) continue;
+    cf *src = (cf *)bursts + i * pitch;
+    std::vector<cf> x(160), tmp(200);
+    float soft[160];
+    memset(soft, 0, sizeof soft);
+    cf amp;
+    float toa;
+    if (act[i] == ACT_RACH) {
+      amp = ramp[slot[i]]; toa = rtoa[slot[i]];
+      for (int m = 0; m < len; m++) x[m] = src[m];
+      demodulate_burst<1, 1>(T, View<1>{x.data()}, len, 1, amp, toa, View<1>{tmp.data()}, soft);
+    } else {
+      amp = mk(det[i].amp_x, det[i].amp_y); toa = det[i].toa;
+      const cf ia = cdiv(mk(1.0F, 0.0F), amp);
+      for (int m = 0; m < len; m++) x[m] = cmul(src[m], ia);
+      const cf *w, *b;
+      float off;
+      if (act[i] >= 0) { w = dfe[act[i]].w; b = dfe[act[i]].b; off = dfe[act[i]].off; }
+      else { w = st[a].w[tn]; b = st[a].b[tn]; off = st[a].chan_off[tn]; }   // carried over: still the pre-commit values
+      cf W[7], B[5];
+      for (int j = 0; j < 7; j++) W[j] = w[j];
+      for (int j = 0; j < 5; j++) B[j] = b[j];
+      equalize_burst<1, 1>(T, View<1>{x.data()}, len, BTS_SUB(toa, off), W, 7, B, 5, View<1>{tmp.data()}, soft);
+    }
+    trx_datagram_header(dg, tn, fn, amp, toa, 1);
+    for (int m = 0; m < 148; m++) dg[8 + m] = trx_soft_byte(soft[m]);
+    valid[i] = 1;
+  }
+  for (int k = 0; k < narfcn * 8; k++) {
+    if (commit[k] < 0) continue;
+    const int a = k >> 3, tn = k & 7;
+    for (int j = 0; j < 7; j++) st[a].w[tn][j] = dfe[commit[k]].w[j];
+    for (int j = 0; j < 5; j++) st[a].b[tn][j] = dfe[commit[k]].b[j];
+    st[a].chan_off[tn] = dfe[commit[k]].off;
+  }
+}
+
 }  // extern "C"

@@ -143,3 +143,38 @@ def make_edge_batch(o, n=70, seed=9):
         else:
             bursts[i, :lens[i]] = (rng.standard_normal(lens[i]) + 1j * rng.standard_normal(lens[i])) * rng.uniform(1, 3000)
     return bursts, lens, tsc
+
+
+def make_trx_batch(modulate, corr_type, nframes, tsc, chan_type, fn0=0, seed=5, pitch=160):
+    """Received slots for the caller-policy tests, laid out [frame][arfcn][tn]: on TSC slots mostly normal bursts of
+    the ARFCN's midamble (amplitudes straddling the 250 energy threshold, a per-timeslot 2-tap channel), sometimes
+    plain noise (false detections) or near-silence; on RACH slots access bursts or noise; junk elsewhere.
+    corr_type(chan_type, fn) -> 0 off / 1 TSC / 2 RACH / 3 idle.  Returns bursts[(nframes*narfcn*8), pitch] c64."""
+    rng = np.random.default_rng(seed)
+    tsc = np.asarray(tsc)
+    A = tsc.size
+    chan_type = np.asarray(chan_type).reshape(A, 8)
+    out = np.zeros((nframes * A * 8, pitch), np.complex64)
+    chan = 0.4 * np.exp(2j * np.pi * rng.random((A, 8))) * (rng.random((A, 8)) < 0.5)
+    for f in range(nframes):
+        for a in range(A):
+            for tn in range(8):
+                i = (f * A + a) * 8 + tn
+                n = 157 if tn % 4 == 0 else 156
+                c = corr_type(int(chan_type[a, tn]), fn0 + f)
+                u = rng.random()
+                noise = lambda p: (p * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+                if c == 1 and u < 0.7:
+                    x = modulate(normal_burst_bits(rng, int(tsc[a])), n - 148)
+                    amp = float(np.exp(rng.uniform(np.log(60), np.log(5000))))
+                    ch = chan[a, tn] if chan[a, tn] != 0 else None
+                    out[i, :n] = impair(rng, x, amp=amp, delay=rng.uniform(0, 2), chan2=ch, snr_db=rng.uniform(8, 30))
+                elif c == 2 and u < 0.5:
+                    x = modulate(access_burst_bits(rng), n - 88)
+                    amp = float(np.exp(rng.uniform(np.log(100), np.log(3000))))
+                    out[i, :n] = impair(rng, x, amp=amp, delay=rng.integers(0, 40) + rng.random(), snr_db=rng.uniform(0, 25))
+                elif u < 0.85:
+                    out[i, :n] = noise(float(np.exp(rng.uniform(np.log(30), np.log(2000)))))
+                else:
+                    out[i, :n] = noise(1.0)
+    return out

@@ -1,0 +1,129 @@
+"""Caller policy (Transceiver::pullRadioVector + driveReceiveFIFO): the oracle's restated glue
+over the real reference functions vs the plain-C port vs the product's policy code replayed on the CPU (hostemu),
+and on the GPU through the C ABI (test_gpu_parity-style, marked gpu)."""
+import numpy as np
+import pytest
+
+import synth
+from emu import Emu
+
+CHAN_TYPES = [[1, 1, 5, 4, 0, 7, 2, 8],      # I, I, V, IV, NONE, VII, II, LOOPBACK
+              [5, 1, 1, 1, 6, 3, 1, 1],
+              [1, 1, 1, 1, 1, 1, 1, 1]]
+TSC = [2, 5, 0]
+STATE_FIELDS = ("thr", "prev_false_fn", "est_fn", "have", "chan_off", "w", "b")
+
+
+def oracle_pull(o, bursts, nframes, fn0, start_fn, batches):
+    """run the oracle ARFCN by ARFCN (it holds one Transceiver's state), in `batches` consecutive pulls"""
+    A = len(TSC)
+    b4 = bursts.reshape(nframes, A, 8, -1)
+    valid = np.zeros((nframes, A, 8), np.int32)
+    dg = np.zeros((nframes, A, 8, 158), np.uint8)
+    states = []
+    for a in range(A):
+        st = o.trx_new(TSC[a], CHAN_TYPES[a], start_fn)
+        for lo, hi in batches:
+            v, d = o.trx_pull(st, np.ascontiguousarray(b4[lo:hi, a]).reshape((hi - lo) * 8, -1), fn0 + lo)
+            valid[lo:hi, a] = v.reshape(hi - lo, 8)
+            dg[lo:hi, a] = d[:, :158].reshape(hi - lo, 8, 158)
+        states.append(st)
+    return valid.reshape(-1), dg.reshape(-1, 158), np.concatenate(states)
+
+
+def check_state(got, want, where):
+    for k in STATE_FIELDS:
+        g, w = got[k], want[k]
+        if k in ("w", "b", "chan_off"):            # only meaningful where a channel estimate is cached
+            m = want["have"].astype(bool)
+            g, w = g[m], w[m]
+        assert np.ascontiguousarray(g).tobytes() == np.ascontiguousarray(w).tobytes(), (where, k, g, w)
+    m = want["have"].astype(bool)
+    assert got["snr"][m].tobytes() == want["snr"][m].tobytes(), (where, "snr")
+
+
+@pytest.fixture(scope="module")
+def batch(oracle_best):
+    nframes, fn0 = 120, 2715640                # crosses the hyperframe wrap (2715648)
+    bursts = synth.make_trx_batch(oracle_best.modulate, oracle_best.expected_corr_type, nframes, TSC, CHAN_TYPES, fn0=fn0)
+    return bursts, nframes, fn0
+
+
+def test_slot_map_port_matches_reference(oracle_best, oracle_port):
+    for ct in range(9):
+        for fn in list(range(0, 210)) + [2715647, 2715646]:
+            assert oracle_port.expected_corr_type(ct, fn) == oracle_best.expected_corr_type(ct, fn)
+
+
+def test_policy_port_matches_reference(oracle_best, oracle_port, batch):
+    bursts, nframes, fn0 = batch
+    split = [(0, 37), (37, 38), (38, nframes)]
+    v1, d1, s1 = oracle_pull(oracle_best, bursts, nframes, fn0, fn0 - 3, split)
+    v2, d2, s2 = oracle_pull(oracle_port, bursts, nframes, fn0, fn0 - 3, split)
+    assert np.array_equal(v1, v2) and np.array_equal(d1, d2)
+    check_state(s2, s1, "port")
+    # the fixture exercises every branch: gated bursts, cached and re-estimated equalisers, misses, RACH hits
+    assert 0.2 < v1.mean() < 0.9
+    assert (s1["thr"] != 250.0).all()
+
+
+def test_policy_hostemu_matches_reference(oracle_best, hostemu, batch):
+    bursts, nframes, fn0 = batch
+    A = len(TSC)
+    hostemu = Emu(hostemu)
+    for split in ([(0, nframes)], [(0, 37), (37, 38), (38, nframes)]):
+        v1, d1, s1 = oracle_pull(oracle_best, bursts, nframes, fn0, fn0 - 3, split)
+        st = hostemu.trx_new(TSC, CHAN_TYPES, fn0 - 3)
+        v2 = np.zeros_like(v1)
+        d2 = np.zeros_like(d1)
+        for lo, hi in split:
+            v, d = hostemu.trx_pull(st, bursts[lo * A * 8:hi * A * 8], fn0 + lo)
+            v2[lo * A * 8:hi * A * 8] = v
+            d2[lo * A * 8:hi * A * 8] = d
+        assert np.array_equal(v1, v2)
+        bad = np.nonzero((d1 != d2).any(axis=1))[0]
+        assert bad.size == 0, (bad[:10], d1[bad[:1]], d2[bad[:1]])
+        check_state(st, s1, "hostemu")
+
+
+@pytest.mark.gpu
+def test_policy_gpu_matches_reference(oracle_best, dsp, batch):
+    bursts, nframes, fn0 = batch
+    A = len(TSC)
+    for split in ([(0, nframes)], [(0, 37), (37, 38), (38, nframes)]):
+        v1, d1, s1 = oracle_pull(oracle_best, bursts, nframes, fn0, fn0 - 3, split)
+        trx = dsp.trx_create(TSC, CHAN_TYPES, fn0 - 3)
+        v2 = np.zeros_like(v1)
+        d2 = np.zeros_like(d1)
+        for lo, hi in split:
+            v, d = dsp.trx_pull_host(trx, bursts[lo * A * 8:hi * A * 8], fn0 + lo)
+            v2[lo * A * 8:hi * A * 8] = v
+            d2[lo * A * 8:hi * A * 8] = d
+        st = dsp.trx_state(trx)
+        dsp.trx_destroy(trx)
+        assert np.array_equal(v1, v2)
+        bad = np.nonzero((d1 != d2).any(axis=1))[0]
+        assert bad.size == 0, (bad[:10], d1[bad[:1]], d2[bad[:1]])
+        check_state(st, s1, "gpu")
+
+
+@pytest.mark.gpu
+def test_policy_gpu_large_batch(oracle_best, dsp):
+    """1024-burst frames (128 ARFCN x 8 TN): the shape the policy pass parallelises over; spot-check 3 ARFCNs"""
+    A, nframes, fn0 = 128, 60, 1000
+    tsc = np.arange(A) % 8
+    ct = np.ones((A, 8), np.uint8)
+    ct[:, 0] = 5
+    ct[1::7, 3] = 4
+    bursts = synth.make_trx_batch(oracle_best.modulate, oracle_best.expected_corr_type, nframes, tsc, ct, fn0=fn0, seed=11)
+    trx = dsp.trx_create(tsc, ct, fn0)
+    v, d = dsp.trx_pull_host(trx, bursts, fn0)
+    st = dsp.trx_state(trx)
+    dsp.trx_destroy(trx)
+    b4 = bursts.reshape(nframes, A, 8, -1)
+    for a in (0, 8, 127):
+        so = oracle_best.trx_new(int(tsc[a]), ct[a], fn0)
+        vo, do = oracle_best.trx_pull(so, np.ascontiguousarray(b4[:, a]).reshape(nframes * 8, -1), fn0)
+        assert np.array_equal(vo.reshape(nframes, 8), v.reshape(nframes, A, 8)[:, a])
+        assert np.array_equal(do[:, :158].reshape(nframes, 8, 158), d.reshape(nframes, A, 8, 158)[:, a])
+        check_state(st[a:a + 1], so, "gpu large %d" % a)
