@@ -394,6 +394,11 @@ class BtsDsp:
             self._ck(self.lib.btsdsp_trx_get_state(self.h, trx[0], a, _p(st[a:a + 1]), st.itemsize))
         return st
 
+    def trx_pull_dev(self, trx, bursts, pitch, nframes, fn0, valid, dgram, dgram_pitch=160, stream=None):
+        """device tensors/pointers; asynchronous on `stream`"""
+        self._ck(self.lib.btsdsp_trx_pull_dev(self.h, trx[0], _p(bursts), pitch, nframes, fn0, _p(valid), _p(dgram),
+                                              dgram_pitch, _stream(stream)))
+
     def trx_pull_host(self, trx, bursts, fn0):
         """bursts: (nframes*narfcn*8, pitch) complex64 laid out [frame][arfcn][tn].  Returns (valid[n], dgram[n,158])."""
         bursts = _c64(bursts)

@@ -114,6 +114,17 @@ def main():
     np.savez_compressed(os.path.join(OUT, "sps4.npz"), rx=np.stack(xs), tsc=np.array(tscs, np.uint8),
                         **{k: np.stack(v) for k, v in outs.items()})
     R.setup(1)
+    # ---- caller policy (pullRadioVector + driveReceiveFIFO): 120 frames x 3 ARFCN, in three pulls.  The 2880 input
+    #      bursts (3.7 MB) are NOT stored: tests regenerate them from the seed with tests/synth.make_trx_batch and check
+    #      the stored SHA-1 first, so a fixture mismatch cannot be mistaken for a parity failure.
+    import hashlib
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_trx_policy as tp
+    nframes, fn0 = tp.GOLDEN_SHAPE
+    bursts = synth.make_trx_batch(R.modulate, R.expected_corr_type, nframes, tp.TSC, tp.CHAN_TYPES, fn0=fn0)
+    v, d, st = tp.oracle_pull(R, bursts, nframes, fn0, fn0 - 3, tp.GOLDEN_SPLIT)
+    np.savez_compressed(os.path.join(OUT, "trx_sps1.npz"), sha1=np.frombuffer(hashlib.sha1(bursts.tobytes()).digest(), np.uint8),
+                        valid=v, dgram=d, state=st.view(np.uint8).reshape(len(tp.TSC), -1))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import synth
+from conftest import golden
 from emu import Emu
 
 CHAN_TYPES = [[1, 1, 5, 4, 0, 7, 2, 8],      # I, I, V, IV, NONE, VII, II, LOOPBACK
@@ -12,6 +13,8 @@ CHAN_TYPES = [[1, 1, 5, 4, 0, 7, 2, 8],      # I, I, V, IV, NONE, VII, II, LOOPB
               [1, 1, 1, 1, 1, 1, 1, 1]]
 TSC = [2, 5, 0]
 STATE_FIELDS = ("thr", "prev_false_fn", "est_fn", "have", "chan_off", "w", "b")
+GOLDEN_SHAPE = (120, 2715640)                # frames, first FN: crosses the hyperframe wrap (2715648)
+GOLDEN_SPLIT = [(0, 37), (37, 38), (38, 120)]
 
 
 def oracle_pull(o, bursts, nframes, fn0, start_fn, batches):
@@ -44,9 +47,26 @@ def check_state(got, want, where):
 
 @pytest.fixture(scope="module")
 def batch(oracle_best):
-    nframes, fn0 = 120, 2715640                # crosses the hyperframe wrap (2715648)
+    nframes, fn0 = GOLDEN_SHAPE
     bursts = synth.make_trx_batch(oracle_best.modulate, oracle_best.expected_corr_type, nframes, TSC, CHAN_TYPES, fn0=fn0)
     return bursts, nframes, fn0
+
+
+def golden_trx(bursts):
+    import hashlib
+    from oracle.oracle import Oracle
+    g = golden("trx_sps1.npz")
+    assert hashlib.sha1(bursts.tobytes()).digest() == g["sha1"].tobytes(), "regenerated inputs differ from the fixture's"
+    return g["valid"], g["dgram"], g["state"].reshape(-1).view(Oracle.TRX_STATE_DTYPE)
+
+
+def test_policy_port_matches_golden(oracle_port, batch):
+    """outputs of the real reference functions under the restated glue, committed by oracle/gen_golden.py"""
+    bursts, nframes, fn0 = batch
+    v1, d1, s1 = golden_trx(bursts)
+    v2, d2, s2 = oracle_pull(oracle_port, bursts, nframes, fn0, fn0 - 3, GOLDEN_SPLIT)
+    assert np.array_equal(v1, v2) and np.array_equal(d1, d2)
+    check_state(s2, s1, "port vs golden")
 
 
 def test_slot_map_port_matches_reference(oracle_best, oracle_port):
@@ -57,7 +77,7 @@ def test_slot_map_port_matches_reference(oracle_best, oracle_port):
 
 def test_policy_port_matches_reference(oracle_best, oracle_port, batch):
     bursts, nframes, fn0 = batch
-    split = [(0, 37), (37, 38), (38, nframes)]
+    split = GOLDEN_SPLIT
     v1, d1, s1 = oracle_pull(oracle_best, bursts, nframes, fn0, fn0 - 3, split)
     v2, d2, s2 = oracle_pull(oracle_port, bursts, nframes, fn0, fn0 - 3, split)
     assert np.array_equal(v1, v2) and np.array_equal(d1, d2)
@@ -71,7 +91,7 @@ def test_policy_hostemu_matches_reference(oracle_best, hostemu, batch):
     bursts, nframes, fn0 = batch
     A = len(TSC)
     hostemu = Emu(hostemu)
-    for split in ([(0, nframes)], [(0, 37), (37, 38), (38, nframes)]):
+    for split in ([(0, nframes)], GOLDEN_SPLIT):
         v1, d1, s1 = oracle_pull(oracle_best, bursts, nframes, fn0, fn0 - 3, split)
         st = hostemu.trx_new(TSC, CHAN_TYPES, fn0 - 3)
         v2 = np.zeros_like(v1)
@@ -90,7 +110,7 @@ def test_policy_hostemu_matches_reference(oracle_best, hostemu, batch):
 def test_policy_gpu_matches_reference(oracle_best, dsp, batch):
     bursts, nframes, fn0 = batch
     A = len(TSC)
-    for split in ([(0, nframes)], [(0, 37), (37, 38), (38, nframes)]):
+    for split in ([(0, nframes)], GOLDEN_SPLIT):
         v1, d1, s1 = oracle_pull(oracle_best, bursts, nframes, fn0, fn0 - 3, split)
         trx = dsp.trx_create(TSC, CHAN_TYPES, fn0 - 3)
         v2 = np.zeros_like(v1)
@@ -105,6 +125,10 @@ def test_policy_gpu_matches_reference(oracle_best, dsp, batch):
         bad = np.nonzero((d1 != d2).any(axis=1))[0]
         assert bad.size == 0, (bad[:10], d1[bad[:1]], d2[bad[:1]])
         check_state(st, s1, "gpu")
+        if split == GOLDEN_SPLIT:
+            vg, dg_, sg = golden_trx(bursts)
+            assert np.array_equal(vg, v2) and np.array_equal(dg_, d2)
+            check_state(st, sg, "gpu vs golden")
 
 
 @pytest.mark.gpu

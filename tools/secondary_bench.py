@@ -71,4 +71,21 @@ out["rach_detect_demod"] = {"bursts": nr, "ms": ms, "bursts_per_s": nr / ms * 1e
                             "gbs": nr * 1272 / ms / 1e6}
 ms = timeit(lambda: dsp.rach_dev(rb, 160, nr, rflag, ramp, rtoa, None, 160, stream=st), reps=5)
 out["rach_detect_only"] = {"bursts": nr, "ms": ms, "bursts_per_s": nr / ms * 1e3}
+# --- caller policy (pullRadioVector semantics over batches): 1024 ARFCN x 8 TN x 32 frames per pull, all TSC slots
+#     except TN0 = combination V (RACH on most frames); bursts = the pitched normal bursts above, tiled
+A, F = 1024, 32
+npol = A * 8 * F
+pb = dp.view(n4, 320).repeat(npol // n4, 1).contiguous()
+ct = np.ones((A, 8), np.uint8); ct[:, 0] = 5
+trx = dsp.trx_create(np.zeros(A, np.uint8), ct, 0)
+pvalid = torch.zeros(npol, dtype=torch.int32, device=dev)
+pdg = torch.zeros(npol * 160, dtype=torch.uint8, device=dev)
+fnc = [0]
+def pull():
+    dsp.trx_pull_dev(trx, pb, 160, F, fnc[0], pvalid, pdg, 160, stream=st)
+    fnc[0] += F
+ms = timeit(pull, reps=10)
+out["trx_pull_policy"] = {"bursts": npol, "arfcn": A, "frames_per_pull": F, "ms": ms, "bursts_per_s": npol / ms * 1e3,
+                          "valid": float(pvalid.float().mean())}
+dsp.trx_destroy(trx)
 print(json.dumps(out, indent=1))
