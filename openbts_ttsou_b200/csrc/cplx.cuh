@@ -83,6 +83,20 @@ BTS_HD cf padd(cf a, cf b) {                    // (a.x+b.x, a.y+b.y): only for 
   return mk(a.x + b.x, a.y + b.y);
 #endif
 }
+// acc + a*b for complex a (a loop-invariant tap, `as` = (-a.y, a.x) precomputed) and complex b, in FOUR instructions:
+// a*b = (a.x*b.x - a.y*b.y, a.y*b.x + a.x*b.y) = pmul0(a, b.x) + pmul0(as, b.y), each product rounded once, the
+// difference formed as x + (-y) (negating a factor negates the rounded product exactly), then one packed add into acc.
+// Values are bit-identical to cadd(acc, cmul(a, b)) / cadd(acc, cmul(b, a)) (products and sums commute); only the
+// sign of an exactly-zero product term can differ, which an accumulator that is not -0 absorbs (see pmul0).
+BTS_HD cf cswapneg(cf a) { return mk(-a.y, a.x); }
+BTS_HD cf cmac_tap(cf acc, cf a, cf as, cf b) {
+#ifdef __CUDA_ARCH__
+  return padd(acc, padd(pmul0(a, b.x), pmul0(as, b.y)));
+#else
+  (void)as;
+  return mk(acc.x + (a.x * b.x - a.y * b.y), acc.y + (a.x * b.y + a.y * b.x));
+#endif
+}
 // Complex.h:83  operator*(Complex): (r*a.r - i*a.i, r*a.i + i*a.r)
 BTS_HD cf cmul(cf a, cf b) {
   const cf t1 = pmul(a, b.x), t2 = pmul(a, b.y);        // (a.x*b.x, a.y*b.x), (a.x*b.y, a.y*b.y)

@@ -40,6 +40,9 @@ BTS_HD void load_corr_taps(const DevTables *__restrict__ T, int tsc, cf tap[16])
 // c[n] = sum_k win[n+7-k]*tap[k], window indices outside [0,36) are not part of the vector.
 template <int S>
 BTS_HD void corr36(View<S> win, View<S> out, const cf tap[16]) {
+  cf taps[16];                                           // (-im, re) copies for cmac_tap
+#pragma unroll
+  for (int k = 0; k < 16; k++) taps[k] = cswapneg(tap[k]);
   for (int n0 = 0; n0 < 36; n0 += 4) {
     cf acc[4];
 #pragma unroll
@@ -52,7 +55,7 @@ BTS_HD void corr36(View<S> win, View<S> out, const cf tap[16]) {
 #pragma unroll
         for (int r = 0; r < 4; r++) {
           const int k = j + r - 3;                       // = (n0 + r + 7) - idx
-          if (k >= 0 && k < 16) acc[r] = cadd(acc[r], cmul(v, tap[k]));
+          if (k >= 0 && k < 16) acc[r] = cmac_tap(acc[r], tap[k], taps[k], v);
         }
       }
     }
@@ -72,7 +75,7 @@ BTS_HD cf interp21(const float s[21], View<S> c, int n, int I) {
 #pragma unroll
   for (int t = 0; t < 21; t++) {
     const int i = I - 10 + t;
-    if (i >= start && i < end) p = cadd(p, cmulr(c.ld(i), s[t]));
+    if (i >= start && i < end) p = padd(p, pmul0(c.ld(i), s[t]));
   }
   return p;
 }
@@ -135,7 +138,7 @@ BTS_HD void delayed12(Grid grid, const DevTables *__restrict__ T, View<S> c, int
 #pragma unroll
         for (int q = 0; q < 12; q++) {
           const int k = q - 11 + jj;                     // = (x0 + q + 10) - row
-          if (k >= 0 && k <= 20) acc[q] = cadd(acc[q], cmulr(v, s[k]));
+          if (k >= 0 && k <= 20) acc[q] = padd(acc[q], pmul0(v, s[k]));
         }
       }
     }
@@ -212,7 +215,10 @@ BTS_HD bool analyze_fast(Grid grid, const DevTables *__restrict__ T, View<S> win
 // already scaled by 1/amplitude; rows outside the burst hold zeros).  F = delayVector's fractional FIR output,
 // D[n] = F[n - io] the delayed burst, y = feed-forward output, then decision feedback.
 // Window Fw[i] = F[q0 + i], q0 = m0 - io for the block of outputs m0..m0+3.  `base` = burst row held in tile row 0.
-constexpr int kEqRows = 72;          // rows of the rolling tile (19 KB per warp)
+#ifndef BTS_EQ_ROWS
+#define BTS_EQ_ROWS 56
+#endif
+constexpr int kEqRows = BTS_EQ_ROWS;  // rows of the rolling tile (56 rows = 14.8 KB per warp: 14-15 one-warp CTAs per SM at 128 registers)
 constexpr int kEqStart = -12;        // first pipeline step: three priming steps fill the window
 constexpr int kEqLook = 23;          // step(m0) reads burst rows m0 - io .. m0 - io + 23
 
@@ -223,6 +229,7 @@ struct EqLane {
   bool nofrac;
   float s[21];
   cf w[7], b[5], hist[5], Fw[10];
+  cf ws[7], bs[5];                                                // (-im, re) copies of the taps for cmac_tap
 
   BTS_HD void init(Grid grid, const DevTables *__restrict__ T, View<S> tile, int n, float TOA, const cf *w_, const cf *b_) {
     a = tile;
@@ -238,9 +245,9 @@ struct EqLane {
       load_delay_taps(grid, T, frac, s);
     }
 #pragma unroll
-    for (int k = 0; k < 7; k++) w[k] = w_[k];
+    for (int k = 0; k < 7; k++) { w[k] = w_[k]; ws[k] = cswapneg(w_[k]); }
 #pragma unroll
-    for (int k = 0; k < 5; k++) { b[k] = b_[k]; hist[k] = mk(0.0F, 0.0F); }
+    for (int k = 0; k < 5; k++) { b[k] = b_[k]; bs[k] = cswapneg(b_[k]); hist[k] = mk(0.0F, 0.0F); }
 #pragma unroll
     for (int i = 0; i < 10; i++) Fw[i] = mk(0.0F, 0.0F);
     // the window is primed by running the pipeline from m0 = kEqStart: compute_y(-8) and compute_y(-4) leave
@@ -262,7 +269,7 @@ struct EqLane {
 #pragma unroll
       for (int r = 0; r < 4; r++) {
         const int k = r - 3 + jj;                                 // = (x0 + r + 10) - row
-        if (k >= 0 && k <= 20) acc[r] = cadd(acc[r], cmulr(v, s[k]));
+        if (k >= 0 && k <= 20) acc[r] = padd(acc[r], pmul0(v, s[k]));
         if (k == 10) center[r] = v;                               // row == x0 + r
       }
     }
@@ -292,7 +299,7 @@ struct EqLane {
     for (int r = 0; r < 4; r++) {
       cf sum = mk(0.0F, 0.0F);
 #pragma unroll
-      for (int k = 0; k < 7; k++) sum = cadd(sum, cmul(Fw[r + 6 - k], w[k]));
+      for (int k = 0; k < 7; k++) sum = cmac_tap(sum, w[k], ws[k], Fw[r + 6 - k]);
       y[r] = sum;
     }
 #pragma unroll
@@ -312,7 +319,7 @@ struct EqLane {
       cf v = y[r];
 #pragma unroll
       for (int k = 0; k < 5; k++)
-        if (!EDGE || m - 1 - k >= 0) v = cadd(v, cmul(b[k], hist[k]));
+        if (!EDGE || m - 1 - k >= 0) v = cmac_tap(v, b[k], bs[k], hist[k]);
       const float out = BTS_SUB(BTS_MUL(v.x, revrot[r].x), BTS_MUL(v.y, revrot[r].y));   // real part of v * revrot[m]
 #pragma unroll
       for (int k = 4; k >= 1; k--) hist[k] = hist[k - 1];
@@ -364,10 +371,11 @@ BTS_HD void rach_corr4(View<S> t, int N, const cf *__restrict__ tap, int n0) {
     cf v;
     if (CHECKED) v = ((unsigned)idx < (unsigned)N) ? t.ld(idx + kRachOff) : mk(0.0F, 0.0F);
     else v = t.ld(idx + kRachOff);
+    const cf vs = cswapneg(v);
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       const int k = j + r - 3;                            // = (n0 + r + 20) - idx
-      if (k >= 0 && k <= 40) acc[r] = cadd(acc[r], cmul(v, tap[k]));
+      if (k >= 0 && k <= 40) acc[r] = cmac_tap(acc[r], v, vs, tap[k]);
     }
   }
 #pragma unroll
