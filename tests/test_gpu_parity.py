@@ -362,3 +362,43 @@ def test_cached_dfe_mode(dsp, oracle_best):
     i = int(np.flatnonzero(ok)[0])
     s1, after1 = oracle_best.equalize(scaled[i, :g["lens"][i]], float(g["toa"][i] - g["off"][i]), g["w"][i], g["b"][i])
     same(after.cpu().numpy().view(np.complex64).reshape(n, 160)[i, :g["lens"][i]], after1, "burst after equalize")
+
+
+@pytest.mark.gpu
+def test_resampler_ragged_sizes(dsp, oracle_best):
+    """RX resampler at sizes around every boundary of the tiled kernel (96 periods per step, one CTA per SM): a single
+    chunk, partial last super-tiles, more super-tiles than SMs, with and without history, float and int16 input,
+    output rows past the end untouched, and the unaligned-pointer fallback."""
+    import torch
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(77)
+    nmax = 1700                                       # 1700 chunks = 15300 periods = 160 super-tiles > 148 SMs
+    iq = rng.integers(-3000, 3000, size=(nmax * 864, 2)).astype(np.int16)
+    raw = (iq[:, 0].astype(np.float32) + 1j * iq[:, 1].astype(np.float32)).astype(np.complex64)
+    want = oracle_best.rx_resample_stream(raw, threads=8)
+    d_raw = torch.from_numpy(raw.view(np.float32).copy()).to(dev)
+    d_iq = torch.from_numpy(iq.copy()).to(dev)
+    for nch in (1, 2, 3, 10, 11, 32, 33, 107, 1579, nmax):
+        for skip in (0, 5):                          # skip > 0: start inside the stream, with real history
+            if skip + nch > nmax:
+                continue
+            res = torch.full(((nch + 1) * 585 * 2,), 7.5, device=dev)
+            dsp.resample_rx_dev(d_raw[skip * 864 * 2:], nch, res, has_history=skip > 0)
+            got = res.cpu().numpy()
+            if skip == 0:
+                same(got[:nch * 585 * 2].view(np.complex64), want[:nch * 585], "float nch=%d" % nch)
+            else:
+                # with history only the stream's very first chunk differs (zero history there), so compare from `skip`
+                same(got[:nch * 585 * 2].view(np.complex64), want[skip * 585:(skip + nch) * 585], "float hist nch=%d" % nch)
+            assert (got[nch * 585 * 2:] == 7.5).all(), "wrote past the end (nch=%d)" % nch
+            res = torch.full(((nch + 1) * 585 * 2,), 7.5, device=dev)
+            dsp.resample_rx_i16_dev(d_iq[skip * 864:], nch, res, has_history=skip > 0)
+            got = res.cpu().numpy()
+            same(got[:nch * 585 * 2].view(np.complex64), want[skip * 585:(skip + nch) * 585], "int16 nch=%d skip=%d" % (nch, skip))
+            assert (got[nch * 585 * 2:] == 7.5).all()
+    # an 8-byte-aligned (not 16) input pointer takes the one-CTA-per-chunk kernel: same results
+    shifted = torch.zeros(40 * 864 * 2 + 2, device=dev)
+    shifted[2:] = d_raw[:40 * 864 * 2]
+    res = torch.zeros(40 * 585 * 2, device=dev)
+    dsp.resample_rx_dev(shifted[2:], 40, res)
+    same(res.cpu().numpy().view(np.complex64), want[:40 * 585], "unaligned fallback")

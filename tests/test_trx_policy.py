@@ -151,3 +151,51 @@ def test_policy_gpu_large_batch(oracle_best, dsp):
         assert np.array_equal(vo.reshape(nframes, 8), v.reshape(nframes, A, 8)[:, a])
         assert np.array_equal(do[:, :158].reshape(nframes, 8, 158), d.reshape(nframes, A, 8, 158)[:, a])
         check_state(st[a:a + 1], so, "gpu large %d" % a)
+
+
+def _edge_case(o):
+    tsc, ct = [0, 7], [[0] * 8, [4, 6, 4, 4, 0, 4, 6, 4]]        # one ARFCN switched off, one with RACH-only slots
+    nframes, fn0 = 23, 100
+    bursts = synth.make_trx_batch(o.modulate, o.expected_corr_type, nframes, tsc, ct, fn0=fn0, seed=3)
+    b4 = bursts.reshape(nframes, 2, 8, -1)
+    want = []
+    for a in range(2):
+        st = o.trx_new(tsc[a], ct[a], fn0)
+        vv, dd = [], []
+        for lo, hi in [(0, 1), (1, 2), (2, nframes)]:          # single-frame pulls
+            v, d = o.trx_pull(st, np.ascontiguousarray(b4[lo:hi, a]).reshape((hi - lo) * 8, -1), fn0 + lo)
+            vv.append(v.reshape(hi - lo, 8)); dd.append(d[:, :158].reshape(hi - lo, 8, 158))
+        want.append((np.concatenate(vv), np.concatenate(dd), st))
+    valid = np.stack([w[0] for w in want], 1).reshape(-1)
+    dg = np.stack([w[1] for w in want], 1).reshape(-1, 158)
+    return tsc, ct, nframes, fn0, bursts, valid, dg, np.concatenate([w[2] for w in want])
+
+
+def test_policy_edge_cases_hostemu(oracle_best, hostemu):
+    tsc, ct, nframes, fn0, bursts, valid, dg, state = _edge_case(oracle_best)
+    emu = Emu(hostemu)
+    st = emu.trx_new(tsc, ct, fn0)
+    v2, d2 = [], []
+    for lo, hi in [(0, 1), (1, 2), (2, nframes)]:
+        v, d = emu.trx_pull(st, bursts[lo * 16:hi * 16], fn0 + lo)
+        v2.append(v); d2.append(d)
+    assert np.array_equal(np.concatenate(v2), valid) and np.array_equal(np.concatenate(d2), dg)
+    assert valid.reshape(nframes, 2, 8)[:, 0].sum() == 0 and valid.sum() > 0
+    check_state(st, state, "hostemu edge")
+
+
+@pytest.mark.gpu
+def test_policy_edge_cases_gpu(oracle_best, dsp):
+    tsc, ct, nframes, fn0, bursts, valid, dg, state = _edge_case(oracle_best)
+    trx = dsp.trx_create(tsc, ct, fn0)
+    v2, d2 = [], []
+    for lo, hi in [(0, 1), (1, 2), (2, nframes)]:
+        v, d = dsp.trx_pull_host(trx, bursts[lo * 16:hi * 16], fn0 + lo)
+        v2.append(v); d2.append(d)
+    st = dsp.trx_state(trx)
+    # SETSLOT: switch ARFCN 0 / TN 2 on as a traffic channel and pull once more; the slot must now be analysed
+    dsp.trx_set_slot(trx, 0, 2, 1)
+    assert dsp.trx_state(trx)["chan_type"][0, 2] == 1
+    dsp.trx_destroy(trx)
+    assert np.array_equal(np.concatenate(v2), valid) and np.array_equal(np.concatenate(d2), dg)
+    check_state(st, state, "gpu edge")
