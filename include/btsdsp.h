@@ -238,6 +238,17 @@ int btsdsp_trx_pull_dev(btsdsp_ctx *ctx, btsdsp_trx *trx, const btsdsp_cf32 *bur
 int btsdsp_trx_pull_host(btsdsp_ctx *ctx, btsdsp_trx *trx, const btsdsp_cf32 *bursts, long long pitch, int nframes,
                          int fn0, int32_t *valid, uint8_t *dgram, int dgram_pitch);
 
+/* TX datagrams (GSM core -> transceiver, 154 bytes: TN, FN as 4 bytes big endian, power attenuation in dB, 148 bits;
+ * Transceiver::driveTransmitPriorityQueue, Transceiver.cpp:582-632), batched: every burst is modulated with guard
+ * 8 + (TN%4==0) and scaled by pow(10, -RSSI/10) (addRadioVector, :100-114), placed at slot (FN - fn0)*8 + TN of a
+ * slot stream of nframes frames (nframes % 117 == 0: a whole number of 585-sample chunks), slots without a datagram
+ * carry `filler` (148 bits, unscaled, e.g. the dummy burst; NULL = silence), then RadioInterface::pushBuffer's
+ * 96/65 resample, x13500 and int16 conversion (radioInterface.cpp:123-168).  out: nframes*1250/585 chunks x 864
+ * int16 {I,Q} pairs.  *placed (optional) = datagrams inside the window (TN 0..7, fn0 <= FN < fn0+nframes); a later
+ * datagram for the same slot replaces an earlier one. */
+int btsdsp_tx_datagrams_host(btsdsp_ctx *ctx, const uint8_t *dgram, long long n, int dgram_pitch, int fn0, int nframes,
+                             const uint8_t *filler, int16_t *out, long long *placed);
+
 void *btsdsp_host_alloc(size_t bytes);
 void btsdsp_host_free(void *p);
 

@@ -77,6 +77,7 @@ _SIGS = {
     "btsdsp_trx_get_state": (_i, [_vp, _vp, _i, _vp, _i]),
     "btsdsp_trx_pull_dev": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i, _vp]),
     "btsdsp_trx_pull_host": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i]),
+    "btsdsp_tx_datagrams_host": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp]),
     "btsdsp_host_alloc": (_vp, [ctypes.c_size_t]),
     "btsdsp_host_free": (None, [_vp]),
 }
@@ -393,6 +394,17 @@ class BtsDsp:
         for a in range(trx[1]):
             self._ck(self.lib.btsdsp_trx_get_state(self.h, trx[0], a, _p(st[a:a + 1]), st.itemsize))
         return st
+
+    def tx_datagrams_host(self, dgram, fn0, nframes, filler=None):
+        """dgram: (n, >=154) uint8 TX datagrams.  Returns (iq[nchunks*864, 2] int16, placed)."""
+        dgram = np.ascontiguousarray(dgram, np.uint8)
+        filler = None if filler is None else np.ascontiguousarray(filler, np.uint8)
+        nchunks = nframes * 1250 // 585
+        out = np.zeros((nchunks * 864, 2), np.int16)
+        placed = ctypes.c_longlong(0)
+        self._ck(self.lib.btsdsp_tx_datagrams_host(self.h, _p(dgram), dgram.shape[0], dgram.shape[1], fn0, nframes,
+                                                   _p(filler), _p(out), ctypes.byref(placed)))
+        return out, placed.value
 
     def trx_pull_dev(self, trx, bursts, pitch, nframes, fn0, valid, dgram, dgram_pitch=160, stream=None):
         """device tensors/pointers; asynchronous on `stream`"""

@@ -1052,4 +1052,45 @@ int btsdsp_trx_pull_host(btsdsp_ctx *ctx, btsdsp_trx *t, const btsdsp_cf32 *burs
   return BTSDSP_OK;
 }
 
+/* ---- TX datagrams: Transceiver::driveTransmitPriorityQueue (:582-632) + addRadioVector (:100-114) + pushBuffer ---- */
+int btsdsp_tx_datagrams_host(btsdsp_ctx *ctx, const uint8_t *dgram, long long n, int dgram_pitch, int fn0, int nframes,
+                             const uint8_t *filler, int16_t *out, long long *placed) {
+  ARG(ctx && (dgram || n == 0) && out && n >= 0 && dgram_pitch >= 154 && fn0 >= 0 && nframes > 0 && nframes % 117 == 0);
+  if (ctx->sps != 1) return fail(ctx, BTSDSP_EUNSUPPORTED, "the TX stream path runs at sps == 1");
+  DeviceGuard g(ctx->device);
+  const long long nslots = (long long)nframes * 8, nchunks = nslots / 4 * 625 / 585;
+  std::vector<uint8_t> bits((size_t)nslots * 148, 0);
+  std::vector<float> scale((size_t)nslots, filler ? 1.0F : 0.0F);
+  if (filler) for (long long sl = 0; sl < nslots; sl++) memcpy(&bits[(size_t)sl * 148], filler, 148);
+  long long ok = 0;
+  for (long long i = 0; i < n; i++) {
+    const uint8_t *d = dgram + i * (long long)dgram_pitch;
+    const int tn = (int)(signed char)d[0];
+    long long fn = 0;
+    for (int k = 0; k < 4; k++) fn = (fn << 8) | d[1 + k];                                  // :593-595
+    const int rssi = (int)(signed char)d[5];                                                // `(int) buffer[5]`, a char
+    if (tn < 0 || tn > 7) continue;
+    const long long f = fn_delta((int)(fn % kHyperframe), fn0 % kHyperframe);
+    if (f < 0 || f >= nframes) continue;
+    const long long sl = f * 8 + tn;
+    memcpy(&bits[(size_t)sl * 148], d + 6, 148);                                            // :620-623
+    scale[(size_t)sl] = (float)pow(10, -rssi / 10);                                         // :108, integer division
+    ok++;
+  }
+  if (placed) *placed = ok;
+  GROW(B_TSC, (size_t)nslots * 148);
+  GROW(B_TOA, (size_t)nslots * 4);
+  GROW(B_RES, (size_t)nslots / 4 * 625 * sizeof(cf));
+  GROW(B_RAW, (size_t)nchunks * 864 * 2 * sizeof(int16_t));
+  cudaStream_t st = ctx->st;
+  CK(cudaMemcpyAsync(dbuf<uint8_t>(ctx, B_TSC), bits.data(), bits.size(), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dbuf<float>(ctx, B_TOA), scale.data(), scale.size() * 4, cudaMemcpyHostToDevice, st));
+  launch_modulate(ctx->T, dbuf<uint8_t>(ctx, B_TSC), 148, nslots, -1, nullptr, 0, dbuf<cf>(ctx, B_RES), 0, st, dbuf<float>(ctx, B_TOA));
+  launch_resample_tx(ctx->T, dbuf<cf>(ctx, B_RES), 0, nchunks, dbuf<int16_t>(ctx, B_RAW), st);
+  LAUNCHED("tx_datagrams", 2);
+  CK(cudaMemcpyAsync(out, dbuf<int16_t>(ctx, B_RAW), (size_t)nchunks * 864 * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));                             // also keeps `bits` / `scale` alive until the copies are done
+  return BTSDSP_OK;
+}
+
 }  // extern "C"

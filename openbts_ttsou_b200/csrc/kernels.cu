@@ -194,7 +194,7 @@ void launch_design_dfe_generic(const cf *chan, int nchan, float snr, int nf, cf 
 // ------------------------------------------------------------------------------------------------
 __global__ void k_modulate(const DevTables *__restrict__ T, const uint8_t *__restrict__ bits, int nbits,
                            long long nbursts, int guard_rule, const uint8_t *__restrict__ guards, long long first,
-                           cf *__restrict__ out, long long pitch) {
+                           cf *__restrict__ out, long long pitch, const float *__restrict__ scale) {
   const int sps = T->sps;
   const long long i = blockIdx.x;
   for (long long bi = i; bi < nbursts; bi += gridDim.x) {
@@ -208,15 +208,21 @@ __global__ void k_modulate(const DevTables *__restrict__ T, const uint8_t *__res
       start = ((g >> 2) * 625 + (q == 0 ? 0 : (q == 1 ? 157 : (q == 2 ? 313 : 469)))) * sps;
     }
     const uint8_t *bb = bits + bi * nbits;
-    for (int t = threadIdx.x; t < n; t += blockDim.x)
-      out[start + t] = modulate_at(T, bb, nbits, n, sps, T->pulse, T->pulse_len, true, t);
+    if (scale) {                                   // addRadioVector's scaleVector(*modBurst, pow(10,-RSSI/10)), Transceiver.cpp:108
+      const cf sc = mk(scale[bi], 0.0F);
+      for (int t = threadIdx.x; t < n; t += blockDim.x)
+        out[start + t] = cmul(modulate_at(T, bb, nbits, n, sps, T->pulse, T->pulse_len, true, t), sc);
+    } else {
+      for (int t = threadIdx.x; t < n; t += blockDim.x)
+        out[start + t] = modulate_at(T, bb, nbits, n, sps, T->pulse, T->pulse_len, true, t);
+    }
   }
 }
 void launch_modulate(const DevTables *T, const uint8_t *bits, int nbits, long long nbursts, int guard_rule,
-                     const uint8_t *guards, long long first, cf *out, long long pitch, cudaStream_t st) {
+                     const uint8_t *guards, long long first, cf *out, long long pitch, cudaStream_t st, const float *scale) {
   if (nbursts <= 0) return;
   const int grid = (int)(nbursts < 148 * 64 ? nbursts : 148 * 64);
-  k_modulate<<<grid, 160, 0, st>>>(T, bits, nbits, nbursts, guard_rule, guards, first, out, pitch);
+  k_modulate<<<grid, 160, 0, st>>>(T, bits, nbits, nbursts, guard_rule, guards, first, out, pitch, scale);
 }
 // the impulse-pulse variant generateMidamble needs (:794-797): pulse = {1.0} complex, guard 0
 __global__ void k_modulate_impulse(const DevTables *T, const uint8_t *bits, int nbits, cf *out) {

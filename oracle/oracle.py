@@ -266,6 +266,19 @@ class Oracle:
         self._f("trx_pull")(_ptr(st), _ptr(bursts), c_i(pitch), c_i(n // 8), c_i(fn0), _ptr(valid), _ptr(dg), c_i(160))
         return valid, dg
 
+    def tx_datagrams(self, dgram, fn0, nframes, filler=None):
+        """TX datagrams (n, >=154) uint8 -> (iq[nchunks*864, 2] int16, placed); reference glue, see ref_shim.cpp"""
+        assert self.kind == "ref", "only the compiled reference implements the TX datagram glue"
+        dgram = np.ascontiguousarray(dgram, np.uint8)
+        filler = None if filler is None else np.ascontiguousarray(filler, np.uint8)
+        nchunks = nframes * 1250 // 585
+        out = np.zeros((nchunks * 864, 2), np.int16)
+        f = self._f("tx_datagrams")
+        f.restype = ctypes.c_long
+        placed = f(_ptr(dgram), c_l(dgram.shape[0]), c_i(dgram.shape[1]), c_i(fn0), c_i(nframes),
+                   None if filler is None else _ptr(filler), _ptr(out))
+        return out, placed
+
     def rx_rach_batch(self, bursts, lens, detect_thr=5.0, sps=1, threads=1):
         bursts = _c64(bursts)
         n, pitch = bursts.shape

@@ -503,4 +503,52 @@ void ref_trx_pull(ref_trx_state *st, const float *bursts, int pitch, int nframes
   }
 }
 
+
+/* Transceiver::driveTransmitPriorityQueue (:582-632) + addRadioVector (:100-114) + RadioInterface::pushBuffer
+ * (radioInterface.cpp:123-168), batched over a window of nframes frames starting at fn0 (nframes % 117 == 0):
+ * datagram = TN, FN[4] big endian, RSSI, 148 bits.  Slots without a datagram carry `filler` (unscaled) or silence.
+ * The placement glue is restated; modulateBurst / scaleVector / polyphaseResampleVector are the reference's. */
+long ref_tx_datagrams(const unsigned char *dgram, long n, int dgram_pitch, int fn0, int nframes,
+                      const unsigned char *filler, short *out) {
+  const long nslots = (long)nframes * 8, nsamp = nslots / 4 * 625;
+  static const int slot_off[4] = {0, 157, 313, 469};
+  signalVector stream(nsamp);                    /* zero-initialised */
+  long *src = new long[nslots];
+  for (long s = 0; s < nslots; s++) src[s] = -1;
+  long placed = 0;
+  for (long i = 0; i < n; i++) {
+    const char *buffer = (const char *)(dgram + (size_t)dgram_pitch * i);
+    int timeSlot = (int)buffer[0];
+    unsigned long frameNum = 0;
+    for (int k = 0; k < 4; k++) frameNum = (frameNum << 8) | (0x0ff & buffer[k + 1]);
+    if (timeSlot < 0 || timeSlot > 7) continue;
+    int f = fn_delta((int)(frameNum % kHyper), fn0 % kHyper);
+    if (f < 0 || f >= nframes) continue;
+    src[(long)f * 8 + timeSlot] = i;
+    placed++;
+  }
+  BitVector bv(148);
+  for (long sl = 0; sl < nslots; sl++) {
+    const int tn = (int)(sl % 8);
+    signalVector *m = NULL;
+    if (src[sl] >= 0) {
+      const char *buffer = (const char *)(dgram + (size_t)dgram_pitch * src[sl]);
+      int RSSI = (int)buffer[5];
+      memcpy(bv.begin(), buffer + 6, 148);
+      m = modulateBurst(bv, *gPulse, 8 + (tn % 4 == 0), 1);
+      scaleVector(*m, pow(10, -RSSI / 10));                    /* Transceiver.cpp:108 */
+    } else if (filler) {
+      memcpy(bv.begin(), filler, 148);
+      m = modulateBurst(bv, *gPulse, 8 + (tn % 4 == 0), 1);
+    }
+    if (m) {
+      memcpy(stream.begin() + (sl / 4) * 625 + slot_off[sl % 4], m->begin(), m->size() * sizeof(complex));
+      delete m;
+    }
+  }
+  delete[] src;
+  ref_tx_resample_stream((const float *)stream.begin(), 0, nsamp / 585, out);
+  return placed;
+}
+
 }  // extern "C"

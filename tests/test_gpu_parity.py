@@ -402,3 +402,29 @@ def test_resampler_ragged_sizes(dsp, oracle_best):
     res = torch.zeros(40 * 585 * 2, device=dev)
     dsp.resample_rx_dev(shifted[2:], 40, res)
     same(res.cpu().numpy().view(np.complex64), want[:40 * 585], "unaligned fallback")
+
+
+@pytest.mark.gpu
+def test_tx_datagrams(dsp, oracle_best):
+    """GSM-core -> transceiver datagrams through modulate / power scaling / slot placement / TX resample / int16
+    (Transceiver.cpp:100-114, 582-632; radioInterface.cpp:123-168) against the reference functions under the same glue"""
+    if oracle_best.kind != "ref":
+        pytest.skip("needs the compiled reference")
+    rng = np.random.default_rng(2024)
+    nframes, fn0 = 234, 2715648 - 100                      # the window crosses the hyperframe wrap
+    n = 1500
+    dg = np.zeros((n, 156), np.uint8)                       # pitch 156 > 154
+    fn = (fn0 + rng.integers(-5, nframes + 5, n)) % 2715648
+    dg[:, 0] = rng.integers(0, 8, n)
+    dg[::97, 0] = 9                                         # bad timeslot: dropped
+    for k in range(4):
+        dg[:, 1 + k] = (fn >> ((3 - k) * 8)) & 0xff
+    dg[:, 5] = rng.choice(np.array([0, 3, 10, 19, 20, 37, 246], np.uint8), n)   # 246 = (char) -10: a gain of 10
+    dg[:, 6:154] = rng.integers(0, 2, (n, 148))
+    dummy = synth.bits_of("0001111101101110110000010100100111000001001000100000001111100011100010111000101110001010111010010100011001100111001111010011111000100101111101010000")
+    for filler in (None, dummy):
+        want, placed_ref = oracle_best.tx_datagrams(dg, fn0, nframes, filler)
+        got, placed = dsp.tx_datagrams_host(dg, fn0, nframes, filler)
+        assert placed == placed_ref and 0 < placed < n
+        same(got, want, "TX datagrams (filler=%s)" % (filler is not None))
+    assert np.abs(got).max() > 1000
