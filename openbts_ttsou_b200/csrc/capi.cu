@@ -820,12 +820,9 @@ int btsdsp_tx_stream_dev(btsdsp_ctx *ctx, const uint8_t *bits148, long long n, i
   if (ctx->sps != 1) return fail(ctx, BTSDSP_EUNSUPPORTED, "the TX stream path runs at sps == 1");
   ARG(n % 4 == 0 && (n / 4 * 625) % 585 == 0);
   DeviceGuard g(ctx->device);
-  const long long nsamp = n / 4 * 625, nchunks = nsamp / 585;
-  GROW(B_RES, (size_t)nsamp * sizeof(cf));
-  cudaStream_t st = (cudaStream_t)stream;
-  launch_modulate(ctx->T, bits148, 148, n, -1, nullptr, 0, dbuf<cf>(ctx, B_RES), 0, st);
-  launch_resample_tx(ctx->T, dbuf<cf>(ctx, B_RES), 0, nchunks, out, st);
-  LAUNCHED("tx_stream", 2);
+  // one fused kernel: the modulated stream never leaves shared memory (resample.cu: k_tx_fused)
+  launch_tx_fused(ctx->T, bits148, nullptr, n, out, (cudaStream_t)stream);
+  LAUNCHED("tx_stream", 1);
   return BTSDSP_OK;
 }
 
@@ -1080,14 +1077,12 @@ int btsdsp_tx_datagrams_host(btsdsp_ctx *ctx, const uint8_t *dgram, long long n,
   if (placed) *placed = ok;
   GROW(B_TSC, (size_t)nslots * 148);
   GROW(B_TOA, (size_t)nslots * 4);
-  GROW(B_RES, (size_t)nslots / 4 * 625 * sizeof(cf));
   GROW(B_RAW, (size_t)nchunks * 864 * 2 * sizeof(int16_t));
   cudaStream_t st = ctx->st;
   CK(cudaMemcpyAsync(dbuf<uint8_t>(ctx, B_TSC), bits.data(), bits.size(), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(dbuf<float>(ctx, B_TOA), scale.data(), scale.size() * 4, cudaMemcpyHostToDevice, st));
-  launch_modulate(ctx->T, dbuf<uint8_t>(ctx, B_TSC), 148, nslots, -1, nullptr, 0, dbuf<cf>(ctx, B_RES), 0, st, dbuf<float>(ctx, B_TOA));
-  launch_resample_tx(ctx->T, dbuf<cf>(ctx, B_RES), 0, nchunks, dbuf<int16_t>(ctx, B_RAW), st);
-  LAUNCHED("tx_datagrams", 2);
+  launch_tx_fused(ctx->T, dbuf<uint8_t>(ctx, B_TSC), dbuf<float>(ctx, B_TOA), nslots, dbuf<int16_t>(ctx, B_RAW), st);
+  LAUNCHED("tx_datagrams", 1);
   CK(cudaMemcpyAsync(out, dbuf<int16_t>(ctx, B_RAW), (size_t)nchunks * 864 * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));                             // also keeps `bits` / `scale` alive until the copies are done
   return BTSDSP_OK;

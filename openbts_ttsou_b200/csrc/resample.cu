@@ -381,6 +381,115 @@ int launch_resample_rx_i16(const int16_t *in, int swap_iq, int has_history, long
   k_resample_rx_v3<true, kRxV3TilesI16><<<rxv3_grid(ntiles), C::kThreads, C::kSmem, st>>>(map, bias, swap_iq, nperiods, out);
   return 1;
 }
+// ------------------------------------------------------------------------------------------------
+// k_tx_fused: the whole transmit chain in one kernel -- bits -> modulateBurst -> (power scaling) -> slot stream ->
+// pushBuffer's 96/65 polyphase resample -> x13500 -> int16 {I,Q}.  The modulated stream (1250 B per burst) never
+// exists in global memory: a persistent CTA per SM computes the 96 periods (6240 samples + halo) of its step straight
+// into shared memory from the 148-byte bursts (L2-resident), resamples them exactly like the RX kernel does (lane =
+// period, phase parts per warp, two-instruction taps from shared memory), and writes the 96 x 96 int16 pairs back as
+// coalesced 128-byte rows.  HBM traffic: 148 B in and 923 B out per burst instead of 1398 + 2173.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTxFusedTiles = 3, kTxFusedParts = 8;
+constexpr int kTxFusedPeriods = 32 * kTxFusedTiles;                              // periods per step
+constexpr int kTxFusedIn = kTxQ * kTxFusedPeriods + 2 * kTxHalo;               // samples in the input tile
+constexpr int kTxFusedOutPitch = kTxP + 1;                                      // 97 words: conflict-free STS.32
+constexpr int kTxFusedThreads = 32 * kTxFusedTiles * kTxFusedParts;
+constexpr int kTxFusedBursts = ((kTxFusedIn + 624) / 625 + 1) * 4;             // slots a step's tile can touch (from a group start)
+constexpr size_t kTxFusedSmem = (size_t)kTxFusedIn * sizeof(cf) + (size_t)kTxFusedPeriods * kTxFusedOutPitch * 4 + kTxP * 8 * 4 +
+                                148 * 3 * sizeof(cf) + (size_t)kTxFusedBursts * 148;
+
+__global__ void __launch_bounds__(kTxFusedThreads, 1) k_tx_fused(const DevTables *__restrict__ T, const uint8_t *__restrict__ bits,
+                                                                const float *__restrict__ scale, long long nsamples,
+                                                                long long nperiods, short2 *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf *xs = reinterpret_cast<cf *>(smem_raw);                             // xs[j] = stream sample 65*G0 - 4 + j
+  short2 *os = reinterpret_cast<short2 *>(xs + kTxFusedIn);
+  float *taps = reinterpret_cast<float *>(os + kTxFusedPeriods * kTxFusedOutPitch);
+  cf *q = reinterpret_cast<cf *>(taps + kTxP * 8);                       // rot[ai] * pulse[k]
+  unsigned char *sb = reinterpret_cast<unsigned char *>(q + 148 * 3);    // this step's bursts, 148 bytes each
+  for (int i = threadIdx.x; i < 148 * 3; i += kTxFusedThreads) tx_fill_q(T, q, i);
+  for (int i = threadIdx.x; i < kTxP * 8; i += kTxFusedThreads) {        // taps[r*8 + k] = lpf_tx[br_r + 96 k]
+    const int r = i >> 3, k = i & 7;
+    int br = (kTxQ * (r + kTxDropC + 5)) % kTxP;
+    taps[i] = T->tx_poly[br][k];
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int part = warp % kTxFusedParts, row = (warp / kTxFusedParts) * 32 + lane;
+  const long long nsteps = (nperiods + kTxFusedPeriods - 1) / kTxFusedPeriods;
+  // the bits a step needs (<= 44 bursts = 6.5 KB) are fetched one step ahead into a register per thread and parked in
+  // shared memory at the top of the step, so their latency hides under the previous step's arithmetic
+  const long long nslots = nsamples / 625 * 4;
+  const bool vec = (reinterpret_cast<uintptr_t>(bits) & 15) == 0;        // 4-slot groups are 592 B = 37 x 16 B
+  auto group_of = [](long long step_) {
+    const long long s0_ = (long long)kTxQ * step_ * kTxFusedPeriods - kTxHalo;
+    return (s0_ < 0 ? 0 : s0_) / 625;
+  };
+  auto fetch = [&](long long step_) {
+    int4 v = make_int4(0, 0, 0, 0);
+    const long long gfirst = group_of(step_) * 4;
+    long long nb = nslots - gfirst;
+    if (nb > kTxFusedBursts) nb = kTxFusedBursts;
+    if (vec && (int)threadIdx.x * 16 < (int)nb * 148) v = __ldg(reinterpret_cast<const int4 *>(bits + gfirst * 148) + threadIdx.x);
+    return v;
+  };
+  static_assert(kTxFusedBursts * 148 <= kTxFusedThreads * 16, "one 16-byte fetch per thread must cover a step's bits");
+  int4 pre = blockIdx.x < nsteps ? fetch(blockIdx.x) : make_int4(0, 0, 0, 0);
+  for (long long step = blockIdx.x; step < nsteps; step += gridDim.x) {
+    const long long G0 = step * kTxFusedPeriods;
+    __syncthreads();                                                     // previous step's tiles are free
+    // ---- park the bits of the bursts this step touches, then modulate its samples into the tile
+    const long long s0 = (long long)kTxQ * G0 - kTxHalo;
+    const long long ga4 = group_of(step);                                // staging starts at slot 4*ga4
+    if (vec) {
+      if ((int)threadIdx.x * 16 < kTxFusedBursts * 148) reinterpret_cast<int4 *>(sb)[threadIdx.x] = pre;
+    } else {
+      const long long gfirst = ga4 * 4;
+      long long nb = nslots - gfirst;
+      if (nb > kTxFusedBursts) nb = kTxFusedBursts;
+      const unsigned char *src = bits + gfirst * 148;
+      for (int i = threadIdx.x; i < (int)nb * 148; i += kTxFusedThreads) sb[i] = src[i];
+    }
+    __syncthreads();
+    if (step + gridDim.x < nsteps) pre = fetch(step + gridDim.x);        // in flight during this step
+    const int w0 = (int)(s0 - ga4 * 625);                                // in [-4, 624]
+    for (int j = threadIdx.x; j < kTxFusedIn; j += kTxFusedThreads) {
+      const int w = w0 + j;
+      cf x = mk(0.0F, 0.0F);
+      if (w >= 0 && s0 + j < nsamples) {
+        const int q4 = w / 625;
+        int sl, t;
+        tx_slot_of(w - q4 * 625, &sl, &t);
+        const int lb = q4 * 4 + sl;                                      // burst index within the staged bits
+        x = tx_burst_sample(q, sb + lb * 148, t);
+        if (scale) x = cmul(x, mk(scale[ga4 * 4 + lb], 0.0F));           // addRadioVector's scaleVector, Transceiver.cpp:108
+      }
+      xs[j] = x;
+    }
+    __syncthreads();
+    // ---- this warp's part of the 96 phases of this lane's period
+    const long long G = G0 + row;
+    tx_part<kTxFusedParts>(part, taps, xs + kTxQ * row + kTxHalo, os + row * kTxFusedOutPitch, (G % 9) == 8);
+    __syncthreads();
+    // ---- rows of 96 int16 pairs (384 B) back to global, coalesced
+    const int nper = (int)(nperiods - G0 < kTxFusedPeriods ? nperiods - G0 : kTxFusedPeriods);
+    for (int p = warp; p < nper; p += kTxFusedThreads / 32) {
+      short2 *og = out + (G0 + p) * kTxP;
+      const short2 *src = os + p * kTxFusedOutPitch;
+      og[lane] = src[lane];
+      og[lane + 32] = src[lane + 32];
+      og[lane + 64] = src[lane + 64];
+    }
+  }
+}
+// bits: nslots x 148 bytes (slot g of the stream), nslots % 4 == 0 and a whole number of 585-sample chunks
+void launch_tx_fused(const DevTables *T, const uint8_t *bits, const float *scale, long long nslots, int16_t *out, cudaStream_t st) {
+  const long long nsamples = nslots / 4 * 625, nchunks = nsamples / 585, nperiods = nchunks * 9;
+  if (nperiods <= 0) return;
+  const long long nsteps = (nperiods + kTxFusedPeriods - 1) / kTxFusedPeriods;
+  const unsigned grid = (unsigned)(nsteps < g_num_sms ? nsteps : g_num_sms);
+  k_tx_fused<<<grid, kTxFusedThreads, kTxFusedSmem, st>>>(T, bits, scale, nsamples, nperiods, reinterpret_cast<short2 *>(out));
+}
+
 int configure_resamplers() {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -392,6 +501,7 @@ int configure_resamplers() {
       g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
     if (!g_encode_tiled) return -1;
   }
+  if (cudaFuncSetAttribute(k_tx_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTxFusedSmem) != cudaSuccess) return -2;
   cudaError_t e = cudaFuncSetAttribute(k_resample_rx_v3<false, kRxV3TilesF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)RxV3<false, kRxV3TilesF32>::kSmem);
   if (e != cudaSuccess) return (int)e;

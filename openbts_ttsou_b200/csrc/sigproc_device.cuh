@@ -519,6 +519,87 @@ BTS_HD void rx_part(int warp, const float *__restrict__ taps, const cf *__restri
   if (warp == W) rx_range<kRxP * W / NW, kRxP * (W + 1) / NW>(taps, xl, ol, q8);
   else if constexpr (W + 1 < NW) rx_part<NW, W + 1>(warp, taps, xl, ol, q8);
 }
+// ---- tuned TX chain (see resample.cu: k_tx_fused) ------------------------------------------------------------------
+// Per chunk the reference resamples 130 history + 585 new samples to 1056 outputs and sends outputs 192..1055
+// (radioInterface.cpp:123-168): 864 = 9 x 96 outputs per 585 = 9 x 65 inputs, so the loop is periodic in
+// (96 outputs, 65 inputs).  For global period G = 9*chunk + q and phase r = 0..95:
+//     output 96 G + r = sum_k x[65 G - 130 + ix_r - k] * h[br_r + 96 k],  ix_r = (65 (r+197)) / 96, br_r = (65 (r+197)) % 96
+// (o = r + 192 + 5, the filter's group delay in output samples, sigProcLib.cpp:1177), k < ntaps_r (6 or 7), with the two
+// chunk effects kept: samples before the stream start are zero, and in the last period of a chunk (q == 8) phases with
+// ix_r > 194 lose their first ix_r - 194 taps (the reference cannot see the next chunk, :1183-1186).
+constexpr int kTxDropC = 192;
+__host__ __device__ constexpr int tx_ix(int r) { return (kTxQ * (r + kTxDropC + 5)) / kTxP; }
+__host__ __device__ constexpr int tx_br(int r) { return (kTxQ * (r + kTxDropC + 5)) % kTxP; }
+__host__ __device__ constexpr int tx_ntaps(int r) { return (kTxTaps - 1 - tx_br(r)) / kTxP + 1; }
+__host__ __device__ constexpr int tx_trunc(int r) { return tx_ix(r) > 194 ? tx_ix(r) - 194 : 0; }   // 714 - 65*8 = 194
+// sample offset of (phase r, tap k) relative to the first sample of the lane's period (stream sample 65 G): -3 .. 67
+__host__ __device__ constexpr int tx_c(int r, int k) { return tx_ix(r) - k - 130; }
+constexpr int kTxHalo = 4;                                             // tile starts 4 samples before its first period
+
+// NR adjacent phases of one period: xl = the lane's period start inside the tile, taps[r*8 + k] = lpf_tx[br_r + 96 k],
+// ol[r] receives the quantised output (x13500, (short) casts: tx_quantise)
+template <int R0, int NR>
+BTS_HD void tx_group(const float *__restrict__ taps, const cf *__restrict__ xl, short2 *__restrict__ ol, bool q8) {
+  constexpr int CLO = tx_c(R0, 6);                                     // lowest sample any phase of the group can read
+  constexpr int CHI = tx_c(R0 + NR - 1, 0);
+  constexpr int NW = CHI - CLO + 1;
+  cf win[NW];
+#pragma unroll
+  for (int p = 0; p < NW; p++) win[p] = xl[CLO + p];
+#pragma unroll
+  for (int d = 0; d < NR; d++) {
+    const int r = R0 + d;
+    cf sum = mk(0.0F, 0.0F);
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+      if (k < tx_ntaps(r)) {
+        cf p = pmul0(win[tx_c(r, k) - CLO], taps[r * 8 + k]);
+        if (k < tx_trunc(r)) {                                         // only phases 91..95, dropped in period q == 8
+          p.x = q8 ? 0.0F : p.x;
+          p.y = q8 ? 0.0F : p.y;
+        }
+        sum = padd(sum, p);
+      }
+    }
+    ol[r] = tx_quantise(sum);
+  }
+}
+template <int A, int B>
+BTS_HD void tx_range(const float *__restrict__ taps, const cf *__restrict__ xl, short2 *__restrict__ ol, bool q8) {
+  constexpr int n = B - A, ng = (n + 5) / 6, first = (n + ng - 1) / ng;
+  tx_group<A, first>(taps, xl, ol, q8);
+  if constexpr (n > first) tx_range<A + first, B>(taps, xl, ol, q8);
+}
+// warp `part` of NW does phases [96 part / NW, 96 (part+1) / NW)
+template <int NW, int W = 0>
+BTS_HD void tx_part(int part, const float *__restrict__ taps, const cf *__restrict__ xl, short2 *__restrict__ ol, bool q8) {
+  if (part == W) tx_range<kTxP * W / NW, kTxP * (W + 1) / NW>(taps, xl, ol, q8);
+  else if constexpr (W + 1 < NW) tx_part<NW, W + 1>(part, taps, xl, ol, q8);
+}
+// Modulated sample t of one burst (modulateBurst :521-565 at sps 1: x[n] = (2 bit - 1) rot[n], 3-tap real pulse,
+// NO_DELAY) from a table q[ai*3 + k] = rot[ai] * pulse[k] (rounded once, as the reference rounds (rot*sym)*pulse:
+// multiplying by sym = +-1 first only flips signs).  Terms with a zero symbol (guard, ai >= 148) add +-0 in the
+// reference and are skipped here; the sum starts at +0 like the reference's.
+BTS_HD cf tx_burst_sample(const cf *__restrict__ q, const unsigned char *__restrict__ bits, int t) {
+  cf sum = mk(0.0F, 0.0F);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int ai = t + 1 - k;                                         // no_delay_start(3) = 1
+    if (ai >= 0 && ai < 148) {
+      const cf v = q[ai * 3 + k];
+      sum = cadd(sum, (bits[ai] & 0x01) ? v : mk(-v.x, -v.y));
+    }
+  }
+  return sum;
+}
+BTS_HD void tx_fill_q(const DevTables *__restrict__ T, cf *__restrict__ q, int i) {   // i < 148*3
+  q[i] = cmulr(T->rot[i / 3], T->pulse[i % 3].x);
+}
+// slot and in-slot offset of sample w (0..624) of a 4-slot group (157/156/156/156)
+BTS_HD void tx_slot_of(int w, int *j, int *t) {
+  *j = w < 157 ? 0 : (w < 313 ? 1 : (w < 469 ? 2 : 3));
+  *t = w - (*j == 0 ? 0 : (*j == 1 ? 157 : (*j == 2 ? 313 : 469)));
+}
 // taps[r*16 + k] = lpf_rx[br_r + 65 k] from the [branch][k] table
 inline void rx_fill_taps(const DevTables *hostT, float *taps) {
   for (int r = 0; r < kRxP; r++)

@@ -60,6 +60,15 @@ class Emu:
                               P(dg), c_i(158))
         return valid, dg
 
+    def tx_fused(self, bits, scale=None):
+        """bits (nslots, 148) uint8 -> int16 (nchunks*864, 2): the fused TX kernel's arithmetic on the CPU"""
+        bits = np.ascontiguousarray(bits, np.uint8)
+        nslots = bits.shape[0]
+        scale = None if scale is None else np.ascontiguousarray(scale, np.float32)
+        out = np.zeros((nslots // 4 * 625 // 585 * 864, 2), np.int16)
+        self.lib.emu_tx_fused(P(bits), P(scale), c_ll(nslots), P(out))
+        return out
+
     def rx_rach_batch(self, bursts, lens, detect_thr=5.0, tiles=True):
         bursts = np.ascontiguousarray(bursts, np.complex64)
         n, pitch = bursts.shape

@@ -553,4 +553,43 @@ void emu_trx_pull(void *state, int narfcn, const float *bursts, long long pitch,
   }
 }
 
+// k_tx_fused replayed on the CPU: modulate into the step's tile, 96 phases per period through tx_part, quantise
+void emu_tx_fused(const uint8_t *bits, const float *scale, long long nslots, short *out) {
+  constexpr int PER = 96, IN = kTxQ * PER + 2 * kTxHalo, PITCH = kTxP + 1;
+  const long long nsamples = nslots / 4 * 625, nchunks = nsamples / 585, nperiods = nchunks * 9;
+  std::vector<float> taps(kTxP * 8);
+  for (int r = 0; r < kTxP; r++)
+    for (int k = 0; k < 8; k++) taps[r * 8 + k] = T->tx_poly[tx_br(r)][k];
+  std::vector<cf> xs(IN), q(148 * 3);
+  std::vector<short2> os(PER * PITCH);
+  for (int i = 0; i < 148 * 3; i++) tx_fill_q(T, q.data(), i);
+  for (long long G0 = 0; G0 < nperiods; G0 += PER) {
+    const long long s0 = (long long)kTxQ * G0 - kTxHalo;
+    const long long sa = s0 < 0 ? 0 : s0, ga4 = sa / 625;
+    const int w0 = (int)(s0 - ga4 * 625);
+    for (int j = 0; j < IN; j++) {
+      const int w = w0 + j;
+      cf x = mk(0.0F, 0.0F);
+      if (w >= 0 && s0 + j < nsamples) {
+        const int q4 = w / 625;
+        int sl, t;
+        tx_slot_of(w - q4 * 625, &sl, &t);
+        const long long g = (ga4 + q4) * 4 + sl;
+        x = tx_burst_sample(q.data(), bits + g * 148, t);
+        if (scale) x = cmul(x, mk(scale[g], 0.0F));
+      }
+      xs[j] = x;
+    }
+    for (int row = 0; row < PER; row++)
+      for (int part = 0; part < 8; part++)
+        tx_part<8>(part, taps.data(), xs.data() + kTxQ * row + kTxHalo, os.data() + row * PITCH, ((G0 + row) % 9) == 8);
+    const int nper = (int)(nperiods - G0 < PER ? nperiods - G0 : PER);
+    for (int p = 0; p < nper; p++)
+      for (int w = 0; w < kTxP; w++) {
+        out[((G0 + p) * kTxP + w) * 2] = os[p * PITCH + w].x;
+        out[((G0 + p) * kTxP + w) * 2 + 1] = os[p * PITCH + w].y;
+      }
+  }
+}
+
 }  // extern "C"

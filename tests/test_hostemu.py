@@ -158,3 +158,18 @@ def test_tuned_rx_resampler_logic(emu, oracle_port):
         assert_same(emu.rx_resample_stream_v2(raw), ref, "v2 %d chunks" % nch)
         if nch > 2:
             assert_same(emu.rx_resample_stream_v2(raw, has_history=True, offset=2 * 864), ref[2 * 585:], "v2 with history")
+
+
+def test_tx_fused_chain(emu, oracle_best):
+    """the fused TX kernel's arithmetic (modulate into the tile, 96-phase periods, quantise) == modulateBurst +
+    pushBuffer of the oracle, with and without per-slot power scaling"""
+    rng = np.random.default_rng(3)
+    nb = 936
+    bits = np.stack([synth.normal_burst_bits(rng, i % 8) for i in range(nb)])
+    want = oracle_best.tx_resample_stream(oracle_best.modulate_stream(bits, threads=4), threads=4)
+    got = emu.tx_fused(bits)
+    assert np.array_equal(got, want.reshape(got.shape))
+    ones = emu.tx_fused(bits, np.ones(nb, np.float32))
+    assert np.array_equal(ones, got)
+    half = emu.tx_fused(bits, np.full(nb, 0.1, np.float32))
+    assert np.abs(half).max() < np.abs(got).max() * 0.11

@@ -40,6 +40,8 @@ ms = timeit(lambda: dsp.modulate_dev(bits, 148, nb, stream, 0, stream=st))
 out["modulate"] = {"bursts": nb, "ms": ms, "bursts_per_s": nb / ms * 1e3, "gbs": nb * 1398 / ms / 1e6}
 ms = timeit(lambda: dsp.resample_tx_dev(stream, nch, iq, stream=st))
 out["resample_tx"] = {"chunks": nch, "ms": ms, "burst_eq_per_s": nb / ms * 1e3, "gbs": nch * 8136 / ms / 1e6}
+ms = timeit(lambda: dsp.tx_stream_dev(bits, nb, iq, stream=st))
+out["tx_fused_bits_to_int16"] = {"bursts": nb, "ms": ms, "bursts_per_s": nb / ms * 1e3, "gbs": (nb * 148 + nch * 3456) / ms / 1e6}
 # --- config 4: 8192 pitched bursts per launch (mixed TSC), from a stream demod of the TX signal re-cut to pitch 160
 raw = iq.to(torch.float32) + 400.0 * torch.randn(iq.numel(), generator=g, device=dev)
 res = torch.zeros(nch * 585 * 2, device=dev)
