@@ -242,8 +242,8 @@ void launch_modulate_impulse(const DevTables *T, const uint8_t *bits, int nbits,
 //                     gated), writes the correlation in place (45 tile rows = 12 KB per warp, 15 warps per CTA share
 //                     one shared-memory copy of the sinc grid), and leaves {1/amp, TOA - offset, w[7], b[5]} per burst
 //                     in an EqParams record;
-//   k_equalize_fast : streams the detected bursts, scaled by 1/amp on the way in, through a ROLLING 72-row tile
-//                     (19 KB per warp, re-staged every ~47 rows; 11 warps per SM) under the pipelined equaliser
+//   k_equalize_fast : streams the detected bursts, scaled by 1/amp on the way in, through a ROLLING 56-row tile
+//                     (14.8 KB per warp, re-staged every ~31 rows; 14-15 warps per SM) under the pipelined equaliser
 //                     of demod_fast.cuh.
 // Staging loads are issued in batches (36 / 20 independent loads per lane) before their shared-memory stores so a
 // warp has many requests in flight instead of one.
@@ -513,7 +513,7 @@ int launch_demod_normal(const DevTables *T, BurstSrc src, const uint8_t *tsc, lo
     k_detect_design<1><<<(unsigned)nwarps, 32, detect_smem<1>(), st>>>(T, src, tsc, n, detect_thr, gate_thr, snr_thr, out, eqp);
   if (between) cudaEventRecord(between, st);
   if (!out.soft && !out.soft_u8) return 1;
-  // one-warp CTAs: 19 KB of shared memory each, 11 resident per SM
+  // one-warp CTAs: 14.8 KB of shared memory and 128 registers per thread each, 14-15 resident per SM
   if (out.soft_u8)
     k_equalize_fast<1, true><<<(unsigned)nwarps, 32, equalize_smem<1>(), st>>>(T, src, n, eqp, out.soft_u8, out.soft_pitch);
   else

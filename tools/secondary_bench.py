@@ -42,6 +42,21 @@ ms = timeit(lambda: dsp.resample_tx_dev(stream, nch, iq, stream=st))
 out["resample_tx"] = {"chunks": nch, "ms": ms, "burst_eq_per_s": nb / ms * 1e3, "gbs": nch * 8136 / ms / 1e6}
 ms = timeit(lambda: dsp.tx_stream_dev(bits, nb, iq, stream=st))
 out["tx_fused_bits_to_int16"] = {"bursts": nb, "ms": ms, "bursts_per_s": nb / ms * 1e3, "gbs": (nb * 148 + nch * 3456) / ms / 1e6}
+# --- RX at the wire formats, device-resident: int16 ingest resample and soft-byte demod over the same 64 000 chunks
+iq_rx = (iq.to(torch.float32) + 400.0 * torch.randn(iq.numel(), generator=g, device=dev)).round().clamp_(-32768, 32767).to(torch.int16)
+res16 = torch.zeros(nch * 585 * 2, device=dev)
+ms = timeit(lambda: dsp.resample_rx_i16_dev(iq_rx, nch, res16, stream=st))
+out["resample_rx_i16"] = {"chunks": nch, "ms": ms, "gbs": nch * 8136 / ms / 1e6}
+resf = torch.zeros(nch * 585 * 2, device=dev)
+rawf = iq_rx.to(torch.float32)
+ms = timeit(lambda: dsp.resample_rx_dev(rawf, nch, resf, stream=st))
+out["resample_rx_f32"] = {"chunks": nch, "ms": ms, "gbs": nch * 11592 / ms / 1e6}
+nbw = nch * 585 // 625 * 4
+tscw = torch.zeros(nbw, dtype=torch.uint8, device=dev)
+fw = torch.zeros(nbw, dtype=torch.int32, device=dev); aw = torch.zeros(nbw * 2, device=dev); tw = torch.zeros(nbw, device=dev)
+u8w = torch.zeros(nbw * 148, dtype=torch.uint8, device=dev)
+ms = timeit(lambda: dsp.demod_normal_u8_dev(res16, 0, tscw, nbw, fw, aw, tw, u8w, 148, stream=st))
+out["demod_normal_u8_stream"] = {"bursts": nbw, "ms": ms, "bursts_per_s": nbw / ms * 1e3, "detected": float(fw.float().mean())}
 # --- config 4: 8192 pitched bursts per launch (mixed TSC), from a stream demod of the TX signal re-cut to pitch 160
 raw = iq.to(torch.float32) + 400.0 * torch.randn(iq.numel(), generator=g, device=dev)
 res = torch.zeros(nch * 585 * 2, device=dev)
