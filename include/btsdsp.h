@@ -249,6 +249,16 @@ int btsdsp_trx_pull_host(btsdsp_ctx *ctx, btsdsp_trx *trx, const btsdsp_cf32 *bu
 int btsdsp_tx_datagrams_host(btsdsp_ctx *ctx, const uint8_t *dgram, long long n, int dgram_pitch, int fn0, int nframes,
                              const uint8_t *filler, int16_t *out, long long *placed);
 
+/* ---- L1 FEC after the path: the XCCH block decoder (SACCH / SDCCH / CCCH-type channels,
+ * GSM 05.03 4.1) as XCCHL1Decoder runs it (GSML1FEC.cpp:616-660): nframes L2 frames, each from the soft bytes of four
+ * consecutive bursts (148 bytes each, burst_pitch apart, as in the RX datagram: probability = byte / 256.0F,
+ * TRXManager.cpp:230) -> deinterleave -> soft-input Viterbi (SoftVector::decode / ViterbiR2O4, BitVector.cpp:290-540)
+ * -> u[228] = d[184] : p[40] : tail[4] hard bits per frame, ok[f] = Fire-code syndrome of d : ~p is zero. ---- */
+int btsdsp_xcch_decode_dev(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pitch, long long nframes, uint8_t *u,
+                           int32_t *ok, void *stream);
+int btsdsp_xcch_decode_host(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pitch, long long nframes, uint8_t *u,
+                            int32_t *ok);
+
 void *btsdsp_host_alloc(size_t bytes);
 void btsdsp_host_free(void *p);
 

@@ -78,6 +78,8 @@ _SIGS = {
     "btsdsp_trx_pull_dev": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i, _vp]),
     "btsdsp_trx_pull_host": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i]),
     "btsdsp_tx_datagrams_host": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp]),
+    "btsdsp_xcch_decode_dev": (_i, [_vp, _vp, _i, _ll, _vp, _vp, _vp]),
+    "btsdsp_xcch_decode_host": (_i, [_vp, _vp, _i, _ll, _vp, _vp]),
     "btsdsp_host_alloc": (_vp, [ctypes.c_size_t]),
     "btsdsp_host_free": (None, [_vp]),
 }
@@ -394,6 +396,18 @@ class BtsDsp:
         for a in range(trx[1]):
             self._ck(self.lib.btsdsp_trx_get_state(self.h, trx[0], a, _p(st[a:a + 1]), st.itemsize))
         return st
+
+    def xcch_decode_host(self, soft_u8):
+        """soft_u8: (nframes*4, >=148) uint8 -> (u[nframes,228] uint8, ok[nframes] int32)"""
+        soft_u8 = np.ascontiguousarray(soft_u8, np.uint8)
+        n = soft_u8.shape[0] // 4
+        u = np.zeros((n, 228), np.uint8)
+        ok = np.zeros(n, np.int32)
+        self._ck(self.lib.btsdsp_xcch_decode_host(self.h, _p(soft_u8), soft_u8.shape[1], n, _p(u), _p(ok)))
+        return u, ok
+
+    def xcch_decode_dev(self, soft_u8, burst_pitch, nframes, u, ok, stream=None):
+        self._ck(self.lib.btsdsp_xcch_decode_dev(self.h, _p(soft_u8), burst_pitch, nframes, _p(u), _p(ok), _stream(stream)))
 
     def tx_datagrams_host(self, dgram, fn0, nframes, filler=None):
         """dgram: (n, >=154) uint8 TX datagrams.  Returns (iq[nchunks*864, 2] int16, placed)."""

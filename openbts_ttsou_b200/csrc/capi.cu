@@ -1088,4 +1088,33 @@ int btsdsp_tx_datagrams_host(btsdsp_ctx *ctx, const uint8_t *dgram, long long n,
   return BTSDSP_OK;
 }
 
+/* ---- L1 FEC after the path: XCCH deinterleave + Viterbi + Fire-code check (fec.cuh) ---- */
+int btsdsp_xcch_decode_dev(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pitch, long long nframes, uint8_t *u,
+                           int32_t *ok, void *stream) {
+  ARG(ctx && soft_u8 && u && ok && nframes >= 0 && burst_pitch >= 148);
+  DeviceGuard g(ctx->device);
+  const int nl = launch_xcch_decode(soft_u8, burst_pitch, nframes, u, ok, (cudaStream_t)stream);
+  LAUNCHED("xcch_decode", nl);
+  return BTSDSP_OK;
+}
+
+int btsdsp_xcch_decode_host(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pitch, long long nframes, uint8_t *u,
+                            int32_t *ok) {
+  ARG(ctx && soft_u8 && u && ok && nframes > 0 && burst_pitch >= 148);
+  DeviceGuard g(ctx->device);
+  size_t total = 0;
+  auto take = [&total](size_t bytes) { size_t o = (total + 255) & ~(size_t)255; total = o + bytes; return o; };
+  const size_t o_s = take((size_t)nframes * 4 * burst_pitch), o_u = take((size_t)nframes * 228), o_k = take((size_t)nframes * 4);
+  GROW(B_RAW, total);
+  uint8_t *d = dbuf<uint8_t>(ctx, B_RAW);
+  cudaStream_t st = ctx->st;
+  CK(cudaMemcpyAsync(d + o_s, soft_u8, (size_t)nframes * 4 * burst_pitch, cudaMemcpyHostToDevice, st));
+  int r = btsdsp_xcch_decode_dev(ctx, d + o_s, burst_pitch, nframes, d + o_u, (int32_t *)(d + o_k), st);
+  if (r != BTSDSP_OK) return r;
+  CK(cudaMemcpyAsync(u, d + o_u, (size_t)nframes * 228, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ok, d + o_k, (size_t)nframes * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return BTSDSP_OK;
+}
+
 }  // extern "C"

@@ -1,0 +1,97 @@
+// fec.cuh -- L1 FEC after the receive path: the XCCH block decoder of GSM 05.03 4.1 as OpenBTS runs
+// it: XCCHL1Decoder::deinterleave + decode (GSML1FEC.cpp:616-660) = deinterleave 4 x 114 e-bits -> c[456], soft-input
+// Viterbi for the rate-1/2, K = 5 code (SoftVector::decode + ViterbiR2O4, CommonLibs/BitVector.cpp:290-540) -> u[228],
+// 40-bit Fire-code syndrome over d[184]:p[40] with the parity inverted (Parity/Generator, BitVector.h:39-112).
+// Input = the RX datagrams' soft bytes; the socket side turns them into probabilities as byte / 256.0F
+// (ARFCNManager::driveRx, TRXManager.cpp:230).
+//
+// Parallel shape: one WARP per frame, one LANE per trellis candidate -- the reference's decoder keeps 16 survivors and
+// 32 candidates per step, so branch / metric / prune are one instruction each across the warp, and the path costs are
+// accumulated per lane with exactly the reference's two float additions per step (ties and the first-minimum rule
+// then resolve identically).  xcch_decode_frame_seq is the same algorithm as a plain loop (host emulation, tests).
+#pragma once
+#include <stdint.h>
+
+#include "cplx.cuh"
+
+namespace btsdsp {
+
+constexpr int kVitStates = 16, kVitCands = 32, kVitDeferral = 24;        // BitVector.h:128-138 (order 4, deferral 6*order)
+constexpr int kXcchC = 456, kXcchU = 228, kXcchSteps = kXcchU + kVitDeferral, kXcchTable = 2 * kXcchSteps;   // 504
+
+// generator output for a 5-bit input history: (g0 << 1) | g1 with g0 = 0x19, g1 = 0x1b (BitVector.cpp:290-338)
+BTS_HD unsigned vit_parity5(unsigned v) { v ^= v >> 4; v ^= v >> 2; v ^= v >> 1; return v & 1u; }
+BTS_HD unsigned vit_generator(unsigned hist5) { return (vit_parity5(hist5 & 0x19u) << 1) | vit_parity5(hist5 & 0x1bu); }
+
+// GSM 05.03 4.1.4 as the reference writes it (GSML1FEC.cpp:620-624): c[k] = i[k % 4][2*((49 k) % 57) + ((k % 8) / 4)],
+// and i[B][j] = burst B's bit 3 + j (j < 57) or 88 + (j - 57) (:603-604)
+BTS_HD int xcch_source_bit(int k, int *B) {
+  *B = k & 3;
+  const int j = 2 * ((49 * k) % 57) + ((k & 7) >> 2);
+  return j < 57 ? 3 + j : 88 + (j - 57);
+}
+
+// the per-bit tables of SoftVector::decode (BitVector.cpp:476-497) for probability p = byte / 256
+BTS_HD void vit_costs(float p, float *match, float *mismatch, unsigned *hard) {
+  *hard = p > 0.5F ? 1u : 0u;                                            // sliced(), :440-448
+  float pVal = p;
+  if (pVal > 0.5F) pVal = BTS_SUB(1.0F, pVal);
+  float ipVal = BTS_SUB(1.0F, pVal);
+  if (pVal < 0.01F) pVal = (float)0.01;
+  if (ipVal < 0.01F) ipVal = (float)0.01;
+  *match = BTS_DIV(0.25F, ipVal);
+  *mismatch = BTS_DIV(0.25F, pVal);
+}
+
+// Fire-code syndrome (Generator::syndromeShift, BitVector.h:69-74) over d[184] : inverted p[40]
+BTS_HD bool xcch_parity_ok(const unsigned char *u) {
+  const unsigned long long coeff = 0x10004820009ULL, mask = (1ULL << 40) - 1;
+  unsigned long long state = 0;
+  for (int i = 0; i < 224; i++) {
+    const unsigned bit = (i < 184 ? u[i] : ~u[i]) & 1u;                  // mP.invert(), GSML1FEC.cpp:649
+    const unsigned fb = (unsigned)(state >> 39) & 1u;
+    state = (state << 1) ^ bit;
+    if (fb) state ^= coeff;
+  }
+  return (state & mask) == 0;
+}
+
+// One frame, sequential form.  soft: the four bursts' soft bytes (burst_pitch apart).  u: 228 bits out.
+BTS_HD bool xcch_decode_frame_seq(const unsigned char *soft, int burst_pitch, unsigned char *u) {
+  float match[kXcchTable], mismatch[kXcchTable];
+  unsigned char hard[kXcchTable];
+  for (int k = 0; k < kXcchC; k++) {
+    int B;
+    const int bit = xcch_source_bit(k, &B);
+    unsigned h;
+    vit_costs((float)soft[B * burst_pitch + bit] / 256.0F, &match[k], &mismatch[k], &h);
+    hard[k] = (unsigned char)h;
+  }
+  for (int k = kXcchC; k < kXcchTable; k++) { match[k] = 0.5F; mismatch[k] = 0.5F; hard[k] = hard[kXcchC - 1]; }   // :462-466, :492-496
+  float scost[kVitStates];
+  unsigned sin_[kVitStates], sout[kVitStates];
+  for (int i = 0; i < kVitStates; i++) { scost[i] = 0.0F; sin_[i] = 0; sout[i] = 0; }
+  for (int s = 0; s < kXcchSteps; s++) {
+    float ccost[kVitCands];
+    unsigned cin[kVitCands], cout[kVitCands];
+    const unsigned in2 = ((unsigned)hard[2 * s] << 1) | hard[2 * s + 1];   // history[2s+1], low two bits
+    for (int c = 0; c < kVitCands; c++) {                                // branchCandidates + getSoftCostMetrics
+      const int sp = c >> 1;
+      cin[c] = (sin_[sp] << 1) | (unsigned)(c & 1);
+      cout[c] = (sout[sp] << 2) | vit_generator(cin[c] & 0x1fu);
+      const unsigned mm = in2 ^ cout[c];
+      const float t = BTS_ADD((mm & 1u) ? mismatch[2 * s + 1] : match[2 * s + 1], ((mm >> 1) & 1u) ? mismatch[2 * s] : match[2 * s]);
+      ccost[c] = BTS_ADD(scost[sp], t);
+    }
+    for (int i = 0; i < kVitStates; i++) {                               // pruneCandidates
+      const int w = ccost[i] < ccost[i + kVitStates] ? i : i + kVitStates;
+      scost[i] = ccost[w]; sin_[i] = cin[w]; sout[i] = cout[w];
+    }
+    int best = 0;                                                        // minCost: first strict minimum
+    for (int i = 1; i < kVitStates; i++) if (scost[i] < scost[best]) best = i;
+    if (s >= kVitDeferral) u[s - kVitDeferral] = (unsigned char)((sin_[best] >> kVitDeferral) & 1u);
+  }
+  return xcch_parity_ok(u);
+}
+
+}  // namespace btsdsp

@@ -857,6 +857,7 @@ void launch_equalize_generic(const DevTables *T, cf *burst, int n, float toa, co
 }
 
 #include "trx_kernels.cuh"
+#include "fec_kernels.cuh"
 
 int configure_kernels() {
   cudaError_t e;

@@ -125,6 +125,11 @@ def main():
     v, d, st = tp.oracle_pull(R, bursts, nframes, fn0, fn0 - 3, tp.GOLDEN_SPLIT)
     np.savez_compressed(os.path.join(OUT, "trx_sps1.npz"), sha1=np.frombuffer(hashlib.sha1(bursts.tobytes()).digest(), np.uint8),
                         valid=v, dgram=d, state=st.view(np.uint8).reshape(len(tp.TSC), -1))
+    # ---- L1 FEC (XCCH block decoder): 96 frames encoded by the reference, impaired, decoded by the reference
+    import test_fec
+    soft, d = test_fec.make_frames(R.xcch_encode, 96, 5)
+    u, ok = R.xcch_decode(soft)
+    np.savez_compressed(os.path.join(OUT, "fec_sps1.npz"), soft=soft, d=d, u=u, ok=ok)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

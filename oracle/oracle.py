@@ -279,6 +279,24 @@ class Oracle:
                    None if filler is None else _ptr(filler), _ptr(out))
         return out, placed
 
+    # ---- L1 FEC after the path: XCCH deinterleave + Viterbi + parity ----
+    def xcch_decode(self, soft_u8):
+        """soft_u8: (nframes*4, >=148) uint8 soft bytes of consecutive bursts.  Returns (u[nframes,228] uint8, ok[nframes])."""
+        soft_u8 = np.ascontiguousarray(soft_u8, np.uint8)
+        n = soft_u8.shape[0] // 4
+        u = np.zeros((n, 228), np.uint8)
+        ok = np.zeros(n, np.int32)
+        self._f("xcch_decode")(_ptr(soft_u8), c_i(soft_u8.shape[1]), c_l(n), _ptr(u), _ptr(ok))
+        return u, ok
+
+    def xcch_encode(self, d):
+        """d: (nframes, 184) bits -> e-bits (nframes*4, 114) of the four bursts (reference encoder; ref only)"""
+        assert self.kind == "ref"
+        d = np.ascontiguousarray(d, np.uint8)
+        e = np.zeros((d.shape[0] * 4, 114), np.uint8)
+        self._f("xcch_encode")(_ptr(d), c_l(d.shape[0]), _ptr(e))
+        return e
+
     def rx_rach_batch(self, bursts, lens, detect_thr=5.0, sps=1, threads=1):
         bursts = _c64(bursts)
         n, pitch = bursts.shape

@@ -551,4 +551,59 @@ long ref_tx_datagrams(const unsigned char *dgram, long n, int dgram_pitch, int f
   return placed;
 }
 
+
+/* ------------------------------------------------------------------------------------------------
+ * L1 FEC after the path: XCCHL1Decoder::deinterleave + decode (GSML1FEC.cpp:616-660) on frames of
+ * four received bursts, given as the RX datagrams' soft bytes (ARFCNManager::driveRx: byte / 256.0F,
+ * TRXManager.cpp:230); SoftVector::decode / ViterbiR2O4 / Parity are the reference's own classes
+ * (CommonLibs/BitVector.cpp:290-540).  GSML1FEC.cpp itself needs the whole GSM stack, so the ten lines of glue are
+ * restated.  u: 228 decoded bits per frame (d[184] : p[40] : tail[4], before the decoder's in-place parity
+ * inversion); ok: syndrome == 0.
+ * ------------------------------------------------------------------------------------------------ */
+void ref_xcch_decode(const unsigned char *soft, int burst_pitch, long nframes, unsigned char *u, int *ok) {
+  ViterbiR2O4 vcoder;
+  Parity blockCoder(0x10004820009ULL, 40, 224);
+  for (long f = 0; f < nframes; f++) {
+    SoftVector mI[4];
+    SoftVector mC(456);
+    BitVector mU(228);
+    for (int B = 0; B < 4; B++) {
+      const unsigned char *rp = soft + (size_t)burst_pitch * (4 * f + B);
+      float data[148];
+      for (int i = 0; i < 148; i++) data[i] = rp[i] / 256.0F;                 /* TRXManager.cpp:230 */
+      mI[B] = SoftVector(114);
+      for (int i = 0; i < 57; i++) { mI[B][i] = data[3 + i]; mI[B][57 + i] = data[88 + i]; }   /* :603-604 */
+    }
+    for (int k = 0; k < 456; k++) {                                           /* :616-630 */
+      int B = k % 4;
+      int j = 2 * ((49 * k) % 57) + ((k % 8) / 4);
+      mC[k] = mI[B][j];
+    }
+    mC.decode(vcoder, mU);                                                    /* :641 */
+    for (int i = 0; i < 228; i++) u[228 * f + i] = mU.bit(i);
+    BitVector mP(mU.segment(184, 40)), mDP(mU.head(224));
+    mP.invert();                                                              /* :649 */
+    ok[f] = blockCoder.syndrome(mDP) == 0;                                    /* :652-654 */
+  }
+}
+/* XCCHL1Encoder::encode + interleave (GSML1FEC.cpp:795-819): d[184] -> the e-bits of four bursts (114 each).
+ * Test-input generator for the decoder. */
+void ref_xcch_encode(const unsigned char *d, long nframes, unsigned char *e) {
+  ViterbiR2O4 vcoder;
+  Parity blockCoder(0x10004820009ULL, 40, 224);
+  for (long f = 0; f < nframes; f++) {
+    BitVector mU(228), mC(456);
+    mU.fill(0);
+    BitVector mD(mU.head(184)), mP(mU.segment(184, 40));
+    for (int i = 0; i < 184; i++) mD[i] = d[184 * f + i] & 1;
+    blockCoder.writeParityWord(mD, mP);
+    mU.encode(vcoder, mC);
+    for (int k = 0; k < 456; k++) {
+      int B = k % 4;
+      int j = 2 * ((49 * k) % 57) + ((k % 8) / 4);
+      e[(4 * f + B) * 114 + j] = mC.bit(k);
+    }
+  }
+}
+
 }  // extern "C"

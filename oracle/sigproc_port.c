@@ -781,3 +781,74 @@ void port_trx_pull(void *state, const float *bursts, int pitch, int nframes, int
     }
   }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * L1 FEC after the path: XCCHL1Decoder::deinterleave + decode (GSML1FEC.cpp:616-660) restated, with
+ * SoftVector::decode + ViterbiR2O4 (CommonLibs/BitVector.cpp:290-540) and the Parity/Generator syndrome
+ * (BitVector.h:39-112).  Same entry point as oracle/ref_shim.cpp's ref_xcch_decode.
+ * ------------------------------------------------------------------------------------------------ */
+static unsigned apply_poly(unsigned val, unsigned poly, unsigned order) {      /* BitVector.cpp:41-47 */
+  unsigned prod = val & poly, sum = prod;
+  for (unsigned i = 1; i < order; i++) sum ^= prod >> i;
+  return sum & 1u;
+}
+void port_xcch_decode(const unsigned char *soft, int burst_pitch, long nframes, unsigned char *u, int *ok) {
+  enum { ORDER = 4, STATES = 16, CANDS = 32, DEFER = 24, SZ = 456, CT = 456 + 2 * 24 };
+  unsigned gen[CANDS];
+  for (unsigned idx = 0; idx < CANDS; idx++) gen[idx] = (apply_poly(idx, 0x019, ORDER + 1) << 1) | apply_poly(idx, 0x01b, ORDER + 1);
+  for (long f = 0; f < nframes; f++) {
+    float c[SZ], match[CT], mismatch[CT];
+    unsigned history[CT];
+    for (int k = 0; k < SZ; k++) {                                             /* GSML1FEC.cpp:620-624, :603-604 */
+      int B = k % 4, j = 2 * ((49 * k) % 57) + ((k % 8) / 4);
+      const unsigned char *rp = soft + (size_t)burst_pitch * (4 * f + B);
+      c[k] = rp[j < 57 ? 3 + j : 88 + (j - 57)] / 256.0F;                       /* TRXManager.cpp:230 */
+    }
+    unsigned accum = 0;
+    for (int i = 0; i < SZ; i++) { accum = (accum << 1) | (c[i] > 0.5F ? 1u : 0u); history[i] = accum; }   /* :452-461 */
+    for (int i = SZ; i < CT; i++) { accum = (accum << 1) | (accum & 1u); history[i] = accum; }
+    for (int i = 0; i < SZ; i++) {                                             /* :476-490 */
+      float pVal = c[i];
+      if (pVal > 0.5F) pVal = 1.0F - pVal;
+      float ipVal = 1.0F - pVal;
+      if (pVal < 0.01F) pVal = 0.01;
+      if (ipVal < 0.01F) ipVal = 0.01;
+      match[i] = 0.25F / ipVal;
+      mismatch[i] = 0.25F / pVal;
+    }
+    for (int i = SZ; i < CT; i++) { match[i] = 0.5F; mismatch[i] = 0.5F; }
+    float scost[STATES] = {0}, ccost[CANDS];
+    unsigned sin_[STATES] = {0}, sout[STATES] = {0}, cin[CANDS], cout[CANDS];
+    unsigned char *up = u + 228 * f;
+    for (int s = 0; s < 228 + DEFER; s++) {
+      const unsigned in = history[2 * s + 1];
+      const float *m0 = match + 2 * s, *m1 = mismatch + 2 * s;
+      for (int i = 0; i < CANDS; i += 2) {                                     /* branchCandidates */
+        const int sp = i / 2;
+        const unsigned i0 = sin_[sp] << 1, i1 = i0 | 1u, osh = sout[sp] << 2;
+        ccost[i] = scost[sp]; cout[i] = osh | gen[i0 & 0x1f]; cin[i] = i0;
+        ccost[i + 1] = scost[sp]; cout[i + 1] = osh | gen[i1 & 0x1f]; cin[i + 1] = i1;
+      }
+      for (int i = 0; i < CANDS; i++) {                                        /* getSoftCostMetrics */
+        const unsigned mm = in ^ cout[i];
+        ccost[i] += ((mm & 1u) ? m1 : m0)[1] + (((mm >> 1) & 1u) ? m1 : m0)[0];
+      }
+      for (int i = 0; i < STATES; i++) {                                       /* pruneCandidates */
+        const int w = ccost[i] < ccost[i + STATES] ? i : i + STATES;
+        scost[i] = ccost[w]; sin_[i] = cin[w]; sout[i] = cout[w];
+      }
+      int best = 0;                                                            /* minCost */
+      float bc = scost[0];
+      for (int i = 1; i < STATES; i++) { if (scost[i] >= bc) continue; bc = scost[i]; best = i; }
+      if (s >= DEFER) up[s - DEFER] = (sin_[best] >> DEFER) & 1u;
+    }
+    unsigned long long state = 0;                                              /* syndrome of d : ~p */
+    for (int i = 0; i < 224; i++) {
+      const unsigned bit = (i < 184 ? up[i] : ~up[i]) & 1u;
+      const unsigned fb = (unsigned)(state >> 39) & 1u;
+      state = (state << 1) ^ bit;
+      if (fb) state ^= 0x10004820009ULL;
+    }
+    ok[f] = (state & ((1ULL << 40) - 1)) == 0;
+  }
+}

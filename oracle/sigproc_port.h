@@ -52,6 +52,8 @@ int   port_trx_state_bytes(void);
 void  port_trx_init(void *state, int tsc, const int *chan_type, int start_fn);
 void  port_trx_pull(void *state, const float *bursts, int pitch, int nframes, int fn0, int *valid,
                     unsigned char *dgram, int dgram_pitch);
+/* XCCH block decoder (deinterleave + soft Viterbi + Fire-code syndrome); see sigproc_port.c */
+void  port_xcch_decode(const unsigned char *soft, int burst_pitch, long nframes, unsigned char *u, int *ok);
 #ifdef __cplusplus
 }
 #endif

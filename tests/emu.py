@@ -69,6 +69,14 @@ class Emu:
         self.lib.emu_tx_fused(P(bits), P(scale), c_ll(nslots), P(out))
         return out
 
+    def xcch_decode(self, soft_u8):
+        soft_u8 = np.ascontiguousarray(soft_u8, np.uint8)
+        n = soft_u8.shape[0] // 4
+        u = np.zeros((n, 228), np.uint8)
+        ok = np.zeros(n, np.int32)
+        self.lib.emu_xcch_decode(P(soft_u8), c_i(soft_u8.shape[1]), c_ll(n), P(u), P(ok))
+        return u, ok
+
     def rx_rach_batch(self, bursts, lens, detect_thr=5.0, tiles=True):
         bursts = np.ascontiguousarray(bursts, np.complex64)
         n, pitch = bursts.shape

@@ -592,4 +592,10 @@ void emu_tx_fused(const uint8_t *bits, const float *scale, long long nslots, sho
   }
 }
 
+// XCCH block decoder (fec.cuh), sequential form
+void emu_xcch_decode(const unsigned char *soft, int burst_pitch, long long nframes, unsigned char *u, int *ok) {
+  for (long long f = 0; f < nframes; f++)
+    ok[f] = xcch_decode_frame_seq(soft + f * 4 * (long long)burst_pitch, burst_pitch, u + f * kXcchU) ? 1 : 0;
+}
+
 }  // extern "C"

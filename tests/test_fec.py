@@ -1,0 +1,86 @@
+"""L1 FEC after the path: XCCH deinterleave + soft Viterbi + Fire-code check.  The checker is the
+reference's own SoftVector::decode / ViterbiR2O4 / Parity classes under the restated ten lines of XCCHL1Decoder glue
+(oracle/ref_shim.cpp); inputs are frames encoded by the reference's encoder, hit with noise / erasures / bursts of
+errors and quantised to the RX datagram's soft bytes."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from emu import Emu
+
+
+def make_frames(enc, n, seed):
+    """n L2 frames -> soft bytes (n*4, 148) with a spread of channel qualities; returns (soft, d)"""
+    rng = np.random.default_rng(seed)
+    d = rng.integers(0, 2, (n, 184)).astype(np.uint8)
+    e = enc(d)                                                   # (n*4, 114) e-bits
+    soft = rng.integers(0, 256, (n * 4, 148)).astype(np.uint8)   # tails / midamble / stealing bits: irrelevant junk
+    sigma = np.repeat(rng.choice([0.05, 0.2, 0.35, 0.5, 0.7, 1.0], n), 4)[:, None]
+    x = (2.0 * e - 1.0) + sigma * rng.standard_normal(e.shape)   # BPSK + AWGN
+    p = 1.0 / (1.0 + np.exp(-2.0 * x / np.maximum(sigma, 0.3) ** 2))
+    b = np.clip(np.rint(p * 255.0), 0, 255).astype(np.uint8)
+    lost = rng.random(n * 4) < 0.08                              # a whole burst missing: 0.5 everywhere (:627)
+    b[lost] = 128
+    sat = rng.random(b.shape) < 0.1                              # saturated decisions exercise the 0.01 clamps
+    b[sat] = np.where(e[sat] > 0, 255, 0)
+    wrong = rng.random(b.shape) < 0.01                           # confident errors
+    b[wrong] = 255 - b[wrong]
+    soft[:, 3:60] = b[:, :57]
+    soft[:, 88:145] = b[:, 57:]
+    return soft, d
+
+
+@pytest.fixture(scope="module")
+def frames(oracle_best):
+    if oracle_best.kind != "ref":
+        pytest.skip("frame generation uses the reference encoder")
+    return make_frames(oracle_best.xcch_encode, 600, 21)
+
+
+def check(got_u, got_ok, want_u, want_ok, d):
+    assert np.array_equal(got_ok, want_ok)
+    assert np.array_equal(got_u, want_u)
+    good = want_ok.astype(bool)
+    assert 0.3 < good.mean() < 0.98                              # both outcomes are exercised
+    assert (want_u[good][:, :184] == d[good]).all()              # a clean syndrome means the payload is right
+
+
+def test_fec_hostemu_matches_reference(oracle_best, hostemu, frames):
+    soft, d = frames
+    want_u, want_ok = oracle_best.xcch_decode(soft)
+    got_u, got_ok = Emu(hostemu).xcch_decode(soft)
+    check(got_u, got_ok, want_u, want_ok, d)
+    # wider rows (the datagram pitch) and the golden fixture committed from the reference
+    wide = np.zeros((soft.shape[0], 160), np.uint8)
+    wide[:, 8:156] = soft
+    u2, ok2 = Emu(hostemu).xcch_decode(np.ascontiguousarray(wide[:, 8:]))
+    assert np.array_equal(u2[:, :], want_u) and np.array_equal(ok2, want_ok)
+
+
+def test_fec_port_matches_reference_and_golden(oracle_port, oracle_best, frames):
+    soft, d = frames
+    want_u, want_ok = oracle_best.xcch_decode(soft)
+    got_u, got_ok = oracle_port.xcch_decode(soft)
+    check(got_u, got_ok, want_u, want_ok, d)
+    g = golden("fec_sps1.npz")
+    u, ok = oracle_port.xcch_decode(g["soft"])
+    assert np.array_equal(u, g["u"]) and np.array_equal(ok, g["ok"])
+
+
+def test_fec_hostemu_matches_golden(hostemu):
+    g = golden("fec_sps1.npz")
+    u, ok = Emu(hostemu).xcch_decode(g["soft"])
+    assert np.array_equal(u, g["u"]) and np.array_equal(ok, g["ok"])
+
+
+@pytest.mark.gpu
+def test_fec_gpu_matches_reference(oracle_best, dsp, frames):
+    soft, d = frames
+    want_u, want_ok = oracle_best.xcch_decode(soft)
+    got_u, got_ok = dsp.xcch_decode_host(soft)
+    check(got_u, got_ok, want_u, want_ok, d)
+    g = golden("fec_sps1.npz")
+    u, ok = dsp.xcch_decode_host(g["soft"])
+    assert np.array_equal(u, g["u"]) and np.array_equal(ok, g["ok"])
+    one_u, one_ok = dsp.xcch_decode_host(soft[:4])               # a single frame
+    assert np.array_equal(one_u, want_u[:1]) and one_ok[0] == want_ok[0]

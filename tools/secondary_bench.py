@@ -105,4 +105,10 @@ ms = timeit(pull, reps=10)
 out["trx_pull_policy"] = {"bursts": npol, "arfcn": A, "frames_per_pull": F, "ms": ms, "bursts_per_s": npol / ms * 1e3,
                           "valid": float(pvalid.float().mean())}
 dsp.trx_destroy(trx)
+# --- L1 FEC after the path: XCCH block decode, 65 536 frames (262 144 bursts) of soft bytes
+nfr = 65536
+sb = torch.randint(0, 256, (nfr * 4, 148), generator=g, device=dev, dtype=torch.uint8)
+fu = torch.zeros(nfr * 228, dtype=torch.uint8, device=dev); fok = torch.zeros(nfr, dtype=torch.int32, device=dev)
+ms = timeit(lambda: dsp.xcch_decode_dev(sb, 148, nfr, fu, fok, stream=st), reps=10)
+out["xcch_decode"] = {"frames": nfr, "bursts": nfr * 4, "ms": ms, "bursts_per_s": nfr * 4 / ms * 1e3}
 print(json.dumps(out, indent=1))
