@@ -22,6 +22,17 @@ constexpr int kXcchC = 456, kXcchU = 228, kXcchSteps = kXcchU + kVitDeferral, kX
 // generator output for a 5-bit input history: (g0 << 1) | g1 with g0 = 0x19, g1 = 0x1b (BitVector.cpp:290-338)
 BTS_HD unsigned vit_parity5(unsigned v) { v ^= v >> 4; v ^= v >> 2; v ^= v >> 1; return v & 1u; }
 BTS_HD unsigned vit_generator(unsigned hist5) { return (vit_parity5(hist5 & 0x19u) << 1) | vit_parity5(hist5 & 0x1bu); }
+// the same as a 64-bit lookup word: entry h in bits [2h, 2h+2)
+__host__ __device__ constexpr unsigned long long vit_generator_lut() {
+  unsigned long long w = 0;
+  for (unsigned h = 0; h < 32; h++) {
+    unsigned a = h & 0x19u, b = h & 0x1bu;
+    a ^= a >> 4; a ^= a >> 2; a ^= a >> 1;
+    b ^= b >> 4; b ^= b >> 2; b ^= b >> 1;
+    w |= (unsigned long long)(((a & 1u) << 1) | (b & 1u)) << (2 * h);
+  }
+  return w;
+}
 
 // GSM 05.03 4.1.4 as the reference writes it (GSML1FEC.cpp:620-624): c[k] = i[k % 4][2*((49 k) % 57) + ((k % 8) / 4)],
 // and i[B][j] = burst B's bit 3 + j (j < 57) or 88 + (j - 57) (:603-604)

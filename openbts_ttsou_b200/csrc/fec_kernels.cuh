@@ -1,9 +1,10 @@
 // fec_kernels.cuh -- k_xcch_decode: one warp per L2 frame, one lane per trellis candidate (see fec.cuh); included by
 // kernels.cu.  Shared memory per warp: the frame's 504 match / mismatch costs, hard bits and the 228 decoded bits.
 constexpr int kXcchWarps = 8;
-struct XcchSmem {
+struct __align__(8) XcchSmem {
   float match[kXcchTable], mismatch[kXcchTable];
   unsigned char hard[kXcchTable];
+  unsigned char in2[kXcchSteps];        // the two received hard bits of each step
   unsigned char u[kXcchU + 4];
 };
 
@@ -30,6 +31,9 @@ __global__ void __launch_bounds__(kXcchWarps * 32) k_xcch_decode(const unsigned 
   __syncwarp();
   for (int k = kXcchC + lane; k < kXcchTable; k += 32) S.hard[k] = S.hard[kXcchC - 1];
   __syncwarp();
+  for (int k = lane; k < kXcchSteps; k += 32) S.in2[k] = (unsigned char)((S.hard[2 * k] << 1) | S.hard[2 * k + 1]);
+  __syncwarp();
+  constexpr unsigned long long GEN = vit_generator_lut();
   // ---- Viterbi: lane c = candidate c; lanes 0..15 also hold survivor `lane` between steps
   float cost = 0.0F;
   unsigned ist = 0, ost = 0;
@@ -39,26 +43,22 @@ __global__ void __launch_bounds__(kXcchWarps * 32) k_xcch_decode(const unsigned 
     const float pc = __shfl_sync(FULL, cost, sp);                        // branchCandidates :338-358
     const unsigned pi = __shfl_sync(FULL, ist, sp), po = __shfl_sync(FULL, ost, sp);
     const unsigned ci = (pi << 1) | (unsigned)(lane & 1);
-    const unsigned co = (po << 2) | vit_generator(ci & 0x1fu);
-    const unsigned in2 = ((unsigned)S.hard[2 * s] << 1) | S.hard[2 * s + 1];
-    const unsigned mm = in2 ^ co;                                        // getSoftCostMetrics :361-371
-    const float t = __fadd_rn((mm & 1u) ? S.mismatch[2 * s + 1] : S.match[2 * s + 1], ((mm >> 1) & 1u) ? S.mismatch[2 * s] : S.match[2 * s]);
+    const unsigned co = (po << 2) | (unsigned)((GEN >> (2 * (ci & 0x1fu))) & 3u);
+    const unsigned mm = (unsigned)S.in2[s] ^ co;                         // getSoftCostMetrics :361-371
+    const float2 ma = *reinterpret_cast<const float2 *>(&S.match[2 * s]), mi = *reinterpret_cast<const float2 *>(&S.mismatch[2 * s]);
+    const float t = __fadd_rn((mm & 1u) ? mi.y : ma.y, ((mm >> 1) & 1u) ? mi.x : ma.x);
     const float cc = __fadd_rn(pc, t);
     const float hc = __shfl_down_sync(FULL, cc, 16);                     // pruneCandidates :374-382
     const unsigned hi = __shfl_down_sync(FULL, ci, 16), ho = __shfl_down_sync(FULL, co, 16);
     const bool low = cc < hc;
     cost = low ? cc : hc; ist = low ? ci : hi; ost = low ? co : ho;      // meaningful in lanes 0..15
-    // minCost :385-397: first strict minimum over survivors 0..15 = lexicographic min of (cost, index)
-    float bc = lane < 16 ? cost : __int_as_float(0x7f800000);
-    int bi = lane;
-#pragma unroll
-    for (int d = 8; d >= 1; d >>= 1) {
-      const float oc = __shfl_xor_sync(FULL, bc, d);
-      const int oi = __shfl_xor_sync(FULL, bi, d);
-      if (oc < bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
-    }
+    // minCost :385-397: first strict minimum over survivors 0..15.  Path costs are sums of positive floats, so their
+    // bit patterns order like the values: one warp-wide integer min, then the lowest lane that holds it.
+    const unsigned key = lane < 16 ? __float_as_uint(cost) : 0xffffffffu;
+    const unsigned mn = __reduce_min_sync(FULL, key);
+    const int bi = __ffs(__ballot_sync(FULL, key == mn)) - 1;
     if (s >= kVitDeferral) {
-      const unsigned wi = __shfl_sync(FULL, ist, bi & 15);
+      const unsigned wi = __shfl_sync(FULL, ist, bi);
       if (lane == 0) S.u[s - kVitDeferral] = (unsigned char)((wi >> kVitDeferral) & 1u);
     }
   }
