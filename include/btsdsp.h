@@ -259,6 +259,15 @@ int btsdsp_xcch_decode_dev(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pi
 int btsdsp_xcch_decode_host(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pitch, long long nframes, uint8_t *u,
                             int32_t *ok);
 
+/* RACH block decoder (GSM 05.03 4.6; RACHL1Decoder::writeLowSide, GSML1FEC.cpp:474-515): per access burst, the 36
+ * coded soft bytes at burst bits 49..84 -> Viterbi -> u[18] = d[8] : p[6] : tail[4] (u may be NULL), and
+ * fields[i] = tail | bsic << 8 | ra << 16: tail = the 4 tail bits (a valid burst has 0), bsic = (~sent parity ^ computed
+ * parity) & 0x3f (a valid burst matches the cell's BSIC), ra = the 8-bit RA value handed to the control layer. */
+int btsdsp_rach_decode_dev(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pitch, long long n, uint8_t *u,
+                           int32_t *fields, void *stream);
+int btsdsp_rach_decode_host(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pitch, long long n, uint8_t *u,
+                            int32_t *fields);
+
 void *btsdsp_host_alloc(size_t bytes);
 void btsdsp_host_free(void *p);
 

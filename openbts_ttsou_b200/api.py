@@ -80,6 +80,8 @@ _SIGS = {
     "btsdsp_tx_datagrams_host": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp]),
     "btsdsp_xcch_decode_dev": (_i, [_vp, _vp, _i, _ll, _vp, _vp, _vp]),
     "btsdsp_xcch_decode_host": (_i, [_vp, _vp, _i, _ll, _vp, _vp]),
+    "btsdsp_rach_decode_dev": (_i, [_vp, _vp, _i, _ll, _vp, _vp, _vp]),
+    "btsdsp_rach_decode_host": (_i, [_vp, _vp, _i, _ll, _vp, _vp]),
     "btsdsp_host_alloc": (_vp, [ctypes.c_size_t]),
     "btsdsp_host_free": (None, [_vp]),
 }
@@ -405,6 +407,15 @@ class BtsDsp:
         ok = np.zeros(n, np.int32)
         self._ck(self.lib.btsdsp_xcch_decode_host(self.h, _p(soft_u8), soft_u8.shape[1], n, _p(u), _p(ok)))
         return u, ok
+
+    def rach_decode_host(self, soft_u8):
+        """soft_u8: (n, >=148) uint8 -> (u[n,18], tail[n], bsic[n], ra[n])"""
+        soft_u8 = np.ascontiguousarray(soft_u8, np.uint8)
+        n = soft_u8.shape[0]
+        u = np.zeros((n, 18), np.uint8)
+        f = np.zeros(n, np.int32)
+        self._ck(self.lib.btsdsp_rach_decode_host(self.h, _p(soft_u8), soft_u8.shape[1], n, _p(u), _p(f)))
+        return u, f & 0xff, (f >> 8) & 0xff, (f >> 16) & 0xff
 
     def xcch_decode_dev(self, soft_u8, burst_pitch, nframes, u, ok, stream=None):
         self._ck(self.lib.btsdsp_xcch_decode_dev(self.h, _p(soft_u8), burst_pitch, nframes, _p(u), _p(ok), _stream(stream)))

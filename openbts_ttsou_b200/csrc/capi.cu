@@ -1117,4 +1117,31 @@ int btsdsp_xcch_decode_host(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_p
   return BTSDSP_OK;
 }
 
+int btsdsp_rach_decode_dev(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pitch, long long n, uint8_t *u, int32_t *fields,
+                           void *stream) {
+  ARG(ctx && soft_u8 && fields && n >= 0 && burst_pitch >= 148);
+  DeviceGuard g(ctx->device);
+  const int nl = launch_rach_decode(soft_u8, burst_pitch, n, u, fields, (cudaStream_t)stream);
+  LAUNCHED("rach_decode", nl);
+  return BTSDSP_OK;
+}
+
+int btsdsp_rach_decode_host(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pitch, long long n, uint8_t *u, int32_t *fields) {
+  ARG(ctx && soft_u8 && fields && n > 0 && burst_pitch >= 148);
+  DeviceGuard g(ctx->device);
+  size_t total = 0;
+  auto take = [&total](size_t bytes) { size_t o = (total + 255) & ~(size_t)255; total = o + bytes; return o; };
+  const size_t o_s = take((size_t)n * burst_pitch), o_u = take((size_t)n * 18), o_k = take((size_t)n * 4);
+  GROW(B_RAW, total);
+  uint8_t *d = dbuf<uint8_t>(ctx, B_RAW);
+  cudaStream_t st = ctx->st;
+  CK(cudaMemcpyAsync(d + o_s, soft_u8, (size_t)n * burst_pitch, cudaMemcpyHostToDevice, st));
+  int r = btsdsp_rach_decode_dev(ctx, d + o_s, burst_pitch, n, d + o_u, (int32_t *)(d + o_k), st);
+  if (r != BTSDSP_OK) return r;
+  if (u) CK(cudaMemcpyAsync(u, d + o_u, (size_t)n * 18, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(fields, d + o_k, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return BTSDSP_OK;
+}
+
 }  // extern "C"

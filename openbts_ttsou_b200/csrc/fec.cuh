@@ -67,22 +67,22 @@ BTS_HD bool xcch_parity_ok(const unsigned char *u) {
   return (state & mask) == 0;
 }
 
-// One frame, sequential form.  soft: the four bursts' soft bytes (burst_pitch apart).  u: 228 bits out.
-BTS_HD bool xcch_decode_frame_seq(const unsigned char *soft, int burst_pitch, unsigned char *u) {
-  float match[kXcchTable], mismatch[kXcchTable];
-  unsigned char hard[kXcchTable];
-  for (int k = 0; k < kXcchC; k++) {
-    int B;
-    const int bit = xcch_source_bit(k, &B);
+// SoftVector::decode (BitVector.cpp:451-540), sequential form: NC coded probabilities -> NU = NC/2 decoded bits
+template <int NC, int NU>
+BTS_HD void viterbi_seq(const float *p, unsigned char *u) {
+  constexpr int STEPS = NU + kVitDeferral, TABLE = 2 * STEPS;
+  float match[TABLE], mismatch[TABLE];
+  unsigned char hard[TABLE];
+  for (int k = 0; k < NC; k++) {
     unsigned h;
-    vit_costs((float)soft[B * burst_pitch + bit] / 256.0F, &match[k], &mismatch[k], &h);
+    vit_costs(p[k], &match[k], &mismatch[k], &h);
     hard[k] = (unsigned char)h;
   }
-  for (int k = kXcchC; k < kXcchTable; k++) { match[k] = 0.5F; mismatch[k] = 0.5F; hard[k] = hard[kXcchC - 1]; }   // :462-466, :492-496
+  for (int k = NC; k < TABLE; k++) { match[k] = 0.5F; mismatch[k] = 0.5F; hard[k] = hard[NC - 1]; }   // :462-466, :492-496
   float scost[kVitStates];
   unsigned sin_[kVitStates], sout[kVitStates];
   for (int i = 0; i < kVitStates; i++) { scost[i] = 0.0F; sin_[i] = 0; sout[i] = 0; }
-  for (int s = 0; s < kXcchSteps; s++) {
+  for (int s = 0; s < STEPS; s++) {
     float ccost[kVitCands];
     unsigned cin[kVitCands], cout[kVitCands];
     const unsigned in2 = ((unsigned)hard[2 * s] << 1) | hard[2 * s + 1];   // history[2s+1], low two bits
@@ -102,7 +102,44 @@ BTS_HD bool xcch_decode_frame_seq(const unsigned char *soft, int burst_pitch, un
     for (int i = 1; i < kVitStates; i++) if (scost[i] < scost[best]) best = i;
     if (s >= kVitDeferral) u[s - kVitDeferral] = (unsigned char)((sin_[best] >> kVitDeferral) & 1u);
   }
+}
+
+// One XCCH frame.  soft: the four bursts' soft bytes (burst_pitch apart).  u: 228 bits out.
+BTS_HD bool xcch_decode_frame_seq(const unsigned char *soft, int burst_pitch, unsigned char *u) {
+  float p[kXcchC];
+  for (int k = 0; k < kXcchC; k++) {
+    int B;
+    const int bit = xcch_source_bit(k, &B);
+    p[k] = (float)soft[B * burst_pitch + bit] / 256.0F;
+  }
+  viterbi_seq<kXcchC, kXcchU>(p, u);
   return xcch_parity_ok(u);
+}
+
+// ---- RACH (GSM 05.03 4.6), RACHL1Decoder::writeLowSide, GSML1FEC.cpp:474-515 ----
+// e = burst bits 49..84 (36 coded bits) -> u[18] = d[8] : p[6] : tail[4].  The caller checks tail == 0 and
+// bsic == its BSIC (the parity word is sent inverted and XORed with the BSIC); ra = the 8-bit RA field.
+constexpr int kRachC = 36, kRachU = 18;
+BTS_HD void rach_fields(const unsigned char *u, int *tail, int *bsic, int *ra) {
+  int t = 0, sent = 0, r = 0;
+  for (int i = 0; i < 4; i++) t = (t << 1) | (u[14 + i] & 1);            // peekField(14,4) :485
+  for (int i = 0; i < 6; i++) sent = (sent << 1) | (u[8 + i] & 1);       // peekField(8,6)
+  unsigned state = 0;                                                    // mD.parity(Parity(0x06f,6,8)): encoderShift x 8
+  for (int i = 0; i < 8; i++) {
+    const unsigned fb = ((state >> 5) ^ u[i]) & 1u;
+    state <<= 1;
+    if (fb) state ^= 0x06fu;
+  }
+  *tail = t;
+  *bsic = (int)(((unsigned)~sent ^ (state & 0x3fu)) & 0x3fu);            // :492-494
+  for (int i = 0; i < 8; i++) r |= (u[i] & 1) << i;                      // LSB8MSB then peekField(0,8) :507-508
+  *ra = r;
+}
+BTS_HD void rach_decode_burst_seq(const unsigned char *soft, unsigned char *u, int *tail, int *bsic, int *ra) {
+  float p[kRachC];
+  for (int k = 0; k < kRachC; k++) p[k] = (float)soft[49 + k] / 256.0F;
+  viterbi_seq<kRachC, kRachU>(p, u);
+  rach_fields(u, tail, bsic, ra);
 }
 
 }  // namespace btsdsp

@@ -1,44 +1,30 @@
-// fec_kernels.cuh -- k_xcch_decode: one warp per L2 frame, one lane per trellis candidate (see fec.cuh); included by
-// kernels.cu.  Shared memory per warp: the frame's 504 match / mismatch costs, hard bits and the 228 decoded bits.
-constexpr int kXcchWarps = 8;
-struct __align__(8) XcchSmem {
-  float match[kXcchTable], mismatch[kXcchTable];
-  unsigned char hard[kXcchTable];
-  unsigned char in2[kXcchSteps];        // the two received hard bits of each step
-  unsigned char u[kXcchU + 4];
+// fec_kernels.cuh -- k_xcch_decode / k_rach_decode: one warp per code block, one lane per trellis candidate (see
+// fec.cuh); included by kernels.cu.  Shared memory per warp: the block's match / mismatch costs, received hard-bit
+// pairs and the decoded bits.
+template <int NC, int NU>
+struct __align__(8) VitSmem {
+  static constexpr int STEPS = NU + kVitDeferral, TABLE = 2 * STEPS;
+  float match[TABLE], mismatch[TABLE];
+  unsigned char hard[TABLE];
+  unsigned char in2[STEPS + 2];         // the two received hard bits of each step
+  unsigned char u[NU + 6];
 };
 
-__global__ void __launch_bounds__(kXcchWarps * 32) k_xcch_decode(const unsigned char *__restrict__ soft, int burst_pitch, long long nframes,
-                                                                unsigned char *__restrict__ u, int *__restrict__ ok) {
-  __shared__ XcchSmem sm[kXcchWarps];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long f = (long long)blockIdx.x * kXcchWarps + warp;
-  if (f >= nframes) return;
-  XcchSmem &S = sm[warp];
-  const unsigned char *fs = soft + f * 4 * (long long)burst_pitch;
-  // ---- deinterleave + cost tables (:616-630; BitVector.cpp:440-497), 456 entries over the lanes
-  for (int k = lane; k < kXcchTable; k += 32) {
-    if (k < kXcchC) {
-      int B;
-      const int bit = xcch_source_bit(k, &B);
-      unsigned h;
-      vit_costs((float)fs[B * burst_pitch + bit] / 256.0F, &S.match[k], &S.mismatch[k], &h);
-      S.hard[k] = (unsigned char)h;
-    } else {
-      S.match[k] = 0.5F; S.mismatch[k] = 0.5F;
-    }
-  }
+// tables already hold entries 0..NC-1 (match, mismatch, hard); pads them, runs the trellis, leaves u[NU] in S.u
+template <int NC, int NU>
+__device__ __forceinline__ void viterbi_warp(VitSmem<NC, NU> &S, int lane) {
+  constexpr int STEPS = NU + kVitDeferral, TABLE = 2 * STEPS;
   __syncwarp();
-  for (int k = kXcchC + lane; k < kXcchTable; k += 32) S.hard[k] = S.hard[kXcchC - 1];
+  for (int k = NC + lane; k < TABLE; k += 32) { S.match[k] = 0.5F; S.mismatch[k] = 0.5F; S.hard[k] = S.hard[NC - 1]; }
   __syncwarp();
-  for (int k = lane; k < kXcchSteps; k += 32) S.in2[k] = (unsigned char)((S.hard[2 * k] << 1) | S.hard[2 * k + 1]);
+  for (int k = lane; k < STEPS; k += 32) S.in2[k] = (unsigned char)((S.hard[2 * k] << 1) | S.hard[2 * k + 1]);
   __syncwarp();
   constexpr unsigned long long GEN = vit_generator_lut();
-  // ---- Viterbi: lane c = candidate c; lanes 0..15 also hold survivor `lane` between steps
+  // lane c = candidate c; lanes 0..15 also hold survivor `lane` between steps
   float cost = 0.0F;
   unsigned ist = 0, ost = 0;
   const unsigned FULL = 0xffffffffu;
-  for (int s = 0; s < kXcchSteps; s++) {
+  for (int s = 0; s < STEPS; s++) {
     const int sp = lane >> 1;
     const float pc = __shfl_sync(FULL, cost, sp);                        // branchCandidates :338-358
     const unsigned pi = __shfl_sync(FULL, ist, sp), po = __shfl_sync(FULL, ost, sp);
@@ -63,6 +49,26 @@ __global__ void __launch_bounds__(kXcchWarps * 32) k_xcch_decode(const unsigned 
     }
   }
   __syncwarp();
+}
+
+constexpr int kXcchWarps = 8;
+__global__ void __launch_bounds__(kXcchWarps * 32) k_xcch_decode(const unsigned char *__restrict__ soft, int burst_pitch, long long nframes,
+                                                                unsigned char *__restrict__ u, int *__restrict__ ok) {
+  __shared__ VitSmem<kXcchC, kXcchU> sm[kXcchWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long f = (long long)blockIdx.x * kXcchWarps + warp;
+  if (f >= nframes) return;
+  VitSmem<kXcchC, kXcchU> &S = sm[warp];
+  const unsigned char *fs = soft + f * 4 * (long long)burst_pitch;
+  // ---- deinterleave + cost tables (:616-630; BitVector.cpp:440-497), 456 entries over the lanes
+  for (int k = lane; k < kXcchC; k += 32) {
+    int B;
+    const int bit = xcch_source_bit(k, &B);
+    unsigned h;
+    vit_costs((float)fs[B * burst_pitch + bit] / 256.0F, &S.match[k], &S.mismatch[k], &h);
+    S.hard[k] = (unsigned char)h;
+  }
+  viterbi_warp<kXcchC, kXcchU>(S, lane);
   for (int i = lane; i < kXcchU; i += 32) u[f * kXcchU + i] = S.u[i];
   if (lane == 0) ok[f] = xcch_parity_ok(S.u) ? 1 : 0;
 }
@@ -70,5 +76,33 @@ __global__ void __launch_bounds__(kXcchWarps * 32) k_xcch_decode(const unsigned 
 int launch_xcch_decode(const unsigned char *soft, int burst_pitch, long long nframes, unsigned char *u, int *ok, cudaStream_t st) {
   if (nframes <= 0) return 0;
   k_xcch_decode<<<(unsigned)((nframes + kXcchWarps - 1) / kXcchWarps), kXcchWarps * 32, 0, st>>>(soft, burst_pitch, nframes, u, ok);
+  return 1;
+}
+
+// RACH: one warp per access burst; out[i] = {tail, bsic, ra, 0} packed in one int32: tail | bsic << 8 | ra << 16
+__global__ void __launch_bounds__(kXcchWarps * 32) k_rach_decode(const unsigned char *__restrict__ soft, int burst_pitch, long long n,
+                                                                unsigned char *__restrict__ u, int *__restrict__ fields) {
+  __shared__ VitSmem<kRachC, kRachU> sm[kXcchWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long i = (long long)blockIdx.x * kXcchWarps + warp;
+  if (i >= n) return;
+  VitSmem<kRachC, kRachU> &S = sm[warp];
+  const unsigned char *bs = soft + i * (long long)burst_pitch;
+  for (int k = lane; k < kRachC; k += 32) {
+    unsigned h;
+    vit_costs((float)bs[49 + k] / 256.0F, &S.match[k], &S.mismatch[k], &h);   // burst.segment(49,36) :478
+    S.hard[k] = (unsigned char)h;
+  }
+  viterbi_warp<kRachC, kRachU>(S, lane);
+  if (u && lane < kRachU) u[i * kRachU + lane] = S.u[lane];
+  if (lane == 0) {
+    int tail, bsic, ra;
+    rach_fields(S.u, &tail, &bsic, &ra);
+    fields[i] = tail | (bsic << 8) | (ra << 16);
+  }
+}
+int launch_rach_decode(const unsigned char *soft, int burst_pitch, long long n, unsigned char *u, int *fields, cudaStream_t st) {
+  if (n <= 0) return 0;
+  k_rach_decode<<<(unsigned)((n + kXcchWarps - 1) / kXcchWarps), kXcchWarps * 32, 0, st>>>(soft, burst_pitch, n, u, fields);
   return 1;
 }

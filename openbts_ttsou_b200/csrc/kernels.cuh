@@ -85,6 +85,7 @@ int launch_demodulate(const DevTables *T, BurstSrc src, long long n, const cf *a
 int launch_design_dfe(const cf *chan, const float *snr, long long n, cf *w, cf *b, cudaStream_t st);
 // L1 FEC after the path (fec.cuh / fec_kernels.cuh)
 int launch_xcch_decode(const unsigned char *soft, int burst_pitch, long long nframes, unsigned char *u, int *ok, cudaStream_t st);
+int launch_rach_decode(const unsigned char *soft, int burst_pitch, long long n, unsigned char *u, int *fields, cudaStream_t st);
 // the caller-policy pipeline (trx_policy.cuh / trx_kernels.cuh)
 size_t trx_scratch_bytes(long long n, long long nr, int narfcn);
 int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, int fn0, const cf *bursts, long long pitch,

@@ -297,6 +297,24 @@ class Oracle:
         self._f("xcch_encode")(_ptr(d), c_l(d.shape[0]), _ptr(e))
         return e
 
+    def rach_decode(self, soft_u8):
+        """soft_u8: (n, >=148) uint8 -> (u[n,18], tail[n], bsic[n], ra[n]); reference classes (ref only)"""
+        assert self.kind == "ref"
+        soft_u8 = np.ascontiguousarray(soft_u8, np.uint8)
+        n = soft_u8.shape[0]
+        u = np.zeros((n, 18), np.uint8)
+        tail, bsic, ra = (np.zeros(n, np.int32) for _ in range(3))
+        self._f("rach_decode")(_ptr(soft_u8), c_i(soft_u8.shape[1]), c_l(n), _ptr(u), _ptr(tail), _ptr(bsic), _ptr(ra))
+        return u, tail, bsic, ra
+
+    def rach_encode(self, ra, bsic):
+        assert self.kind == "ref"
+        ra = np.ascontiguousarray(ra, np.uint8)
+        bsic = np.ascontiguousarray(bsic, np.uint8)
+        e = np.zeros((ra.size, 36), np.uint8)
+        self._f("rach_encode")(_ptr(ra), _ptr(bsic), c_l(ra.size), _ptr(e))
+        return e
+
     def rx_rach_batch(self, bursts, lens, detect_thr=5.0, sps=1, threads=1):
         bursts = _c64(bursts)
         n, pitch = bursts.shape

@@ -606,4 +606,44 @@ void ref_xcch_encode(const unsigned char *d, long nframes, unsigned char *e) {
   }
 }
 
+
+/* RACHL1Decoder::writeLowSide (GSML1FEC.cpp:474-515) up to the BSIC comparison: per burst u[18], tail = peekField(14,4),
+ * bsic = (~sentParity ^ checkParity) & 0x3f, ra = RA after LSB8MSB.  Reference classes, restated glue. */
+void ref_rach_decode(const unsigned char *soft, int burst_pitch, long n, unsigned char *u, int *tail, int *bsic, int *ra) {
+  ViterbiR2O4 vcoder;
+  Parity parity(0x06f, 6, 8);
+  for (long i = 0; i < n; i++) {
+    const unsigned char *rp = soft + (size_t)burst_pitch * i;
+    SoftVector e(36);
+    for (int k = 0; k < 36; k++) e[k] = rp[49 + k] / 256.0F;
+    BitVector mU(18);
+    BitVector mD(mU.head(8));
+    e.decode(vcoder, mU);
+    for (int k = 0; k < 18; k++) u[18 * i + k] = mU.bit(k);
+    tail[i] = (int)mU.peekField(14, 4);
+    unsigned sentParity = ~mU.peekField(8, 6);
+    unsigned checkParity = mD.parity(parity);
+    bsic[i] = (int)((sentParity ^ checkParity) & 0x03f);
+    mD.LSB8MSB();
+    ra[i] = (int)mD.peekField(0, 8);
+  }
+}
+/* RACHL1Encoder (GSML1FEC.cpp, GSM 05.03 4.6): RA -> the 36 coded bits.  Test-input generator. */
+void ref_rach_encode(const unsigned char *ra, const unsigned char *bsic, long n, unsigned char *e) {
+  ViterbiR2O4 vcoder;
+  Parity parity(0x06f, 6, 8);
+  for (long i = 0; i < n; i++) {
+    BitVector mU(18), mC(36);
+    mU.fill(0);
+    BitVector mD(mU.head(8)), mP(mU.segment(8, 6));
+    mD.fillField(0, ra[i], 8);
+    mD.LSB8MSB();
+    parity.writeParityWord(mD, mP);                    /* inverted parity */
+    unsigned p = mP.peekField(0, 6) ^ (bsic[i] & 0x3f);
+    mP.fillField(0, p, 6);
+    mU.encode(vcoder, mC);
+    for (int k = 0; k < 36; k++) e[36 * i + k] = mC.bit(k);
+  }
+}
+
 }  // extern "C"

@@ -77,6 +77,14 @@ class Emu:
         self.lib.emu_xcch_decode(P(soft_u8), c_i(soft_u8.shape[1]), c_ll(n), P(u), P(ok))
         return u, ok
 
+    def rach_decode(self, soft_u8):
+        soft_u8 = np.ascontiguousarray(soft_u8, np.uint8)
+        n = soft_u8.shape[0]
+        u = np.zeros((n, 18), np.uint8)
+        tail, bsic, ra = (np.zeros(n, np.int32) for _ in range(3))
+        self.lib.emu_rach_decode(P(soft_u8), c_i(soft_u8.shape[1]), c_ll(n), P(u), P(tail), P(bsic), P(ra))
+        return u, tail, bsic, ra
+
     def rx_rach_batch(self, bursts, lens, detect_thr=5.0, tiles=True):
         bursts = np.ascontiguousarray(bursts, np.complex64)
         n, pitch = bursts.shape

@@ -598,4 +598,8 @@ void emu_xcch_decode(const unsigned char *soft, int burst_pitch, long long nfram
     ok[f] = xcch_decode_frame_seq(soft + f * 4 * (long long)burst_pitch, burst_pitch, u + f * kXcchU) ? 1 : 0;
 }
 
+void emu_rach_decode(const unsigned char *soft, int burst_pitch, long long n, unsigned char *u, int *tail, int *bsic, int *ra) {
+  for (long long i = 0; i < n; i++) rach_decode_burst_seq(soft + i * (long long)burst_pitch, u + i * kRachU, tail + i, bsic + i, ra + i);
+}
+
 }  // extern "C"

@@ -84,3 +84,40 @@ def test_fec_gpu_matches_reference(oracle_best, dsp, frames):
     assert np.array_equal(u, g["u"]) and np.array_equal(ok, g["ok"])
     one_u, one_ok = dsp.xcch_decode_host(soft[:4])               # a single frame
     assert np.array_equal(one_u, want_u[:1]) and one_ok[0] == want_ok[0]
+
+
+def make_access(o, n, seed):
+    """n access bursts' soft bytes: RA/BSIC encoded by the reference encoder, noise of four strengths"""
+    rng = np.random.default_rng(seed)
+    ra = rng.integers(0, 256, n).astype(np.uint8)
+    bsic = rng.integers(0, 64, n).astype(np.uint8)
+    c = o.rach_encode(ra, bsic)
+    soft = rng.integers(0, 256, (n, 148)).astype(np.uint8)
+    sig = rng.choice([0.1, 0.4, 0.8, 1.2], n)[:, None]
+    x = (2.0 * c - 1) + sig * rng.standard_normal(c.shape)
+    p = 1 / (1 + np.exp(-2 * x / np.maximum(sig, 0.3) ** 2))
+    soft[:, 49:85] = np.clip(np.rint(p * 255), 0, 255)
+    return soft, ra, bsic
+
+
+def test_rach_decode_hostemu_matches_reference(oracle_best, hostemu):
+    if oracle_best.kind != "ref":
+        pytest.skip("needs the reference classes")
+    soft, ra, bsic = make_access(oracle_best, 2000, 4)
+    want = oracle_best.rach_decode(soft)
+    got = Emu(hostemu).rach_decode(soft)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    valid = (want[1] == 0) & (want[2] == bsic)
+    assert 0.5 < valid.mean() < 0.95 and (want[3][valid] == ra[valid]).all()
+
+
+@pytest.mark.gpu
+def test_rach_decode_gpu_matches_reference(oracle_best, dsp):
+    if oracle_best.kind != "ref":
+        pytest.skip("needs the reference classes")
+    soft, ra, bsic = make_access(oracle_best, 2003, 4)           # not a multiple of the CTA's 8 warps
+    want = oracle_best.rach_decode(soft)
+    got = dsp.rach_decode_host(soft)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
