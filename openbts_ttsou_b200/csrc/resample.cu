@@ -98,29 +98,20 @@ constexpr int kRxV3Parts = BTS_RXV3_PARTS;         // warps per 32-period tile (
 #define BTS_RXV3_RING 2
 #endif
 constexpr int kRxV3Ring = BTS_RXV3_RING;           // input buffers in flight (float tiles, or int16 staging rows)
-#ifndef BTS_RXV3_SPLIT
-#define BTS_RXV3_SPLIT 1
-#endif
-// Phase split across CTAs (build-time experiment, default off): with S > 1, CTA c handles phases [65 h / S, 65 (h+1) / S),
-// h = c % S, of the super-tiles c / S, c / S + grid / S, ...; the S CTAs sharing a super-tile are independent, each
-// loads the whole input tile and writes its own 32/33-sample run of every period.  An SM then executes only 1/S of
-// the unrolled code (resident in the instruction cache), but every input byte crosses the L2 -> SM fabric S times;
-// measured at S = 2: 0.92 ms against 0.50 ms for S = 1 (per-GPC fabric bandwidth, see profiles/README.md r2).
-constexpr int kRxV3Split = BTS_RXV3_SPLIT;
-constexpr int kRxV3OutW = (kRxP + kRxV3Split - 1) / kRxV3Split;                 // output-tile row: 65 or 33 (odd: conflict-free)
-static_assert(kRxV3OutW % 2 == 1, "output tile pitch must be odd");
+// (An experiment that split the 65 phases over pairs of CTAs, so each SM runs half the unrolled code out of its
+// instruction cache, measured 0.92 ms against 0.50 ms: every input byte then crosses the L2 -> SM fabric twice and the
+// per-GPC fabric becomes the limit -- profiles/README.md r2.  It is not kept in the source.)
 template <bool I16, int T>
 struct RxV3 {
   static constexpr int kPeriods = 32 * T, kRows = kPeriods + 2;
-  static constexpr int kIn = kRows * kRxRowPitch, kOut = kPeriods * kRxV3OutW;   // samples
+  static constexpr int kIn = kRows * kRxRowPitch, kOut = kPeriods * kRxP;        // samples
   static constexpr int kInSlot = (kIn + 15) & ~15;                               // ring slots start on 128-byte lines (TMA)
   static constexpr int kThreads = 32 * kRxV3Parts * T + 32;                      // compute warps + the producer warp
   static constexpr int kStage = kRows * 96;                                      // int16 pairs per staging buffer
   static constexpr unsigned kTileBytes = I16 ? kStage * 4u : kIn * 8u;           // what one tensor copy delivers
-  static constexpr int kOutBufs = kRxV3Split == 1 ? 1 : 2;                       // see the store paths in the kernel
-  // output block(s); then float: kRxV3Ring input tiles / int16: one float tile + kRxV3Ring staging buffers
-  static constexpr size_t kSmem = 128 + (I16 ? (size_t)(kOutBufs * kOut + kInSlot) * sizeof(cf) + (size_t)kRxV3Ring * kStage * 4
-                                             : (size_t)(kOutBufs * kOut + kRxV3Ring * kInSlot) * sizeof(cf));
+  // output block; then float: kRxV3Ring input tiles / int16: one float tile + kRxV3Ring staging buffers
+  static constexpr size_t kSmem = 128 + (I16 ? (size_t)(kOut + kInSlot) * sizeof(cf) + (size_t)kRxV3Ring * kStage * 4
+                                             : (size_t)(kOut + kRxV3Ring * kInSlot) * sizeof(cf));
   static_assert((kOut * sizeof(cf)) % 128 == 0 && (kStage * 4) % 128 == 0, "TMA destinations must be 128-byte aligned");
   static_assert(kSmem + 6 * 1024 <= 227 * 1024, "resampler tile does not fit in shared memory");
 };
@@ -200,7 +191,7 @@ __global__ void __launch_bounds__(32 * kRxV3Parts * T + 32, 1) k_resample_rx_v3(
   constexpr int NW = kRxV3Parts * T, NC = 32 * NW, R = kRxV3Ring;        // compute warps / threads; warp NW is the producer
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf *obuf = reinterpret_cast<cf *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);   // 128-byte lines
-  cf *xbuf = obuf + C::kOutBufs * C::kOut;
+  cf *xbuf = obuf + C::kOut;
   short2 *stage = reinterpret_cast<short2 *>(xbuf + C::kInSlot);
   __shared__ __align__(8) unsigned long long full[R], empty[R];
   // the taps are read from shared memory (uniform-address LDS.128, ~30 cycles) rather than as constant-bank operands:
@@ -210,8 +201,7 @@ __global__ void __launch_bounds__(32 * kRxV3Parts * T + 32, 1) k_resample_rx_v3(
   for (int i = threadIdx.x; i < kRxP * 16; i += blockDim.x) s_taps[i] = c_rx_poly[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long ntiles = (nperiods + C::kPeriods - 1) / C::kPeriods;
-  const int half = blockIdx.x % kRxV3Split;                              // which share of the phases
-  const long long first = blockIdx.x / kRxV3Split, stride = gridDim.x / kRxV3Split;
+  const long long first = blockIdx.x, stride = gridDim.x;
   if (threadIdx.x == 0) {
     for (int i = 0; i < R; i++) {
       mbar_init(&full[i], 1);
@@ -238,12 +228,11 @@ __global__ void __launch_bounds__(32 * kRxV3Parts * T + 32, 1) k_resample_rx_v3(
     }
     return;
   }
-  // ---- compute warps: warp w runs phase part w % kRxV3Parts (of this CTA's share) of tile w / kRxV3Parts
-  const int part = half * kRxV3Parts + warp % kRxV3Parts;
-  const int r_lo = kRxP * half / kRxV3Split, nr = kRxP * (half + 1) / kRxV3Split - r_lo;
+  // ---- compute warps: warp w runs phase part w % kRxV3Parts of tile w / kRxV3Parts
+  const int part = warp % kRxV3Parts;
   const int tl = warp / kRxV3Parts;
   const int row = tl * 32 + lane;                                        // this lane's period within the super-tile
-  int b = 0, use = 0, ob = 0;
+  int b = 0, use = 0;
   bool store_pending = false;
   int it = 0;
 #ifdef BTS_RXV3_TRACE
@@ -251,12 +240,10 @@ __global__ void __launch_bounds__(32 * kRxV3Parts * T + 32, 1) k_resample_rx_v3(
 #endif
   for (long long tile = first; tile < ntiles; tile += stride, it++) {
     const long long G0 = tile * C::kPeriods;
-    cf *xt = xbuf, *ot = obuf + ob * C::kOut;
+    cf *xt = xbuf, *ot = obuf;
     RX_TRACE(0, it, 0);
-    if (kRxV3Split == 1) {                                               // single output block: wait until it has drained
-      if (threadIdx.x == 0 && store_pending) bulk_store_wait_read();
-      compute_warps_sync<NC>();
-    }
+    if (threadIdx.x == 0 && store_pending) bulk_store_wait_read();       // the single output block has drained
+    compute_warps_sync<NC>();
     mbar_wait(&full[b], use & 1);                                        // this step's input has landed
     RX_TRACE(0, it, 1);
     if (I16) {
@@ -270,7 +257,7 @@ __global__ void __launch_bounds__(32 * kRxV3Parts * T + 32, 1) k_resample_rx_v3(
     const long long G = G0 + row;
     const bool q8 = (G % 9) == 8;
     RX_TRACE(0, it, 2);
-    rx_part<kRxV3Split * kRxV3Parts>(part, s_taps, xt + row * kRxRowPitch, ot + row * kRxV3OutW - r_lo, q8);
+    rx_part<kRxV3Parts>(part, s_taps, xt + row * kRxRowPitch, ot + row * kRxP, q8);
     RX_TRACE(0, it, 3);
     if (!I16) {
       __syncwarp();
@@ -278,32 +265,19 @@ __global__ void __launch_bounds__(32 * kRxV3Parts * T + 32, 1) k_resample_rx_v3(
     }
     if (++b == R) { b = 0; use++; }
     const long long nper = nperiods - G0 < C::kPeriods ? nperiods - G0 : C::kPeriods;
-    if (kRxV3Split == 1) {
-      // the 32T x 65 outputs are contiguous in shared and global memory: one bulk copy, issued by one thread,
-      // that drains while the next step waits for its input
-      cf *og = out + G0 * kRxP;
-      fence_async_smem();
-      compute_warps_sync<NC>();                                          // all outputs written; all reads of xt done
-      if (nper == C::kPeriods) {
-        if (threadIdx.x == 0) bulk_store(og, ot, (unsigned)(C::kOut * sizeof(cf)));
-        store_pending = true;
-      } else {
-        for (int i = threadIdx.x; i < nper * kRxP; i += NC) og[i] = ot[i];
-        store_pending = false;
-      }
+    // the 32T x 65 outputs are contiguous in shared and global memory: one bulk copy, issued by one thread,
+    // that drains while the next step waits for its input
+    cf *og = out + G0 * kRxP;
+    fence_async_smem();
+    compute_warps_sync<NC>();                                            // all outputs written; all reads of xt done
+    RX_TRACE(0, it, 4);
+    if (nper == C::kPeriods) {
+      if (threadIdx.x == 0) bulk_store(og, ot, (unsigned)(C::kOut * sizeof(cf)));
+      store_pending = true;
     } else {
-      // each period's run of nr outputs: one coalesced 8-byte store per lane (and lane 0 again for a 33rd sample).
-      // The other output block is written next step, and this block's reads are fenced by that step's barrier.
-      compute_warps_sync<NC>();                                          // all outputs written; all reads of xt done
-      RX_TRACE(0, it, 4);
-      for (int p = warp; p < nper; p += NW) {
-        cf *og = out + (G0 + p) * kRxP + r_lo;
-        const cf *os = ot + p * kRxV3OutW;
-        og[lane] = os[lane];
-        if (lane + 32 < nr) og[lane + 32] = os[lane + 32];
-      }
+      for (int i = threadIdx.x; i < nper * kRxP; i += NC) og[i] = ot[i];
+      store_pending = false;
     }
-    ob ^= C::kOutBufs - 1;
     RX_TRACE(0, it, 5);
   }
   if (threadIdx.x == 0 && store_pending) bulk_store_wait_all();
@@ -320,9 +294,8 @@ __global__ void __launch_bounds__(32 * kRxV3Parts * T + 32, 1) k_resample_rx_v3(
 #endif
 constexpr int kRxV3TilesF32 = BTS_RXV3_TILES_F32, kRxV3TilesI16 = BTS_RXV3_TILES_I16;
 static int g_num_sms = 148;
-static unsigned rxv3_grid(long long ntiles) {        // a multiple of the phase split, at most one CTA per SM
-  const long long groups = g_num_sms / kRxV3Split;
-  return (unsigned)((ntiles < groups ? ntiles : groups) * kRxV3Split);
+static unsigned rxv3_grid(long long ntiles) {        // at most one CTA per SM
+  return (unsigned)(ntiles < g_num_sms ? ntiles : g_num_sms);
 }
 
 void upload_resampler_taps(const DevTables *hostT) {
