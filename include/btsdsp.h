@@ -234,6 +234,17 @@ int btsdsp_trx_get_state(btsdsp_ctx *ctx, btsdsp_trx *trx, int arfcn, void *dst,
 /* device pointers, asynchronous on `stream`; dgram 8-byte aligned, dgram_pitch >= 160 and a multiple of 4 */
 int btsdsp_trx_pull_dev(btsdsp_ctx *ctx, btsdsp_trx *trx, const btsdsp_cf32 *bursts, long long pitch, int nframes,
                         int fn0, int32_t *valid, uint8_t *dgram, int dgram_pitch, void *stream);
+/* the same over narfcn continuous slot streams (what the RX resampler writes), stream_pitch samples apart: stream a holds
+ * the slots of frames fn0.. back to back (157/156/156/156 samples), nframes*1250 samples each */
+int btsdsp_trx_pull_streams_dev(btsdsp_ctx *ctx, btsdsp_trx *trx, const btsdsp_cf32 *streams, long long stream_pitch,
+                                int nframes, int fn0, int32_t *valid, uint8_t *dgram, int dgram_pitch, void *stream);
+/* Radio samples in, datagrams out (host pointers, synchronous): for each of the narfcn radios, nchunks chunks of 864
+ * int16 {I,Q} samples (stream a at iq + 2*a*iq_pitch int16) -> RadioInterface::pullBuffer (unUSRPifyVector + 65/96
+ * resample with the running 192-sample history, radioInterface.cpp:197-273) -> slot cutting (:370-394) -> the pull above.
+ * nchunks % 250 == 0 (250 chunks = 117 frames exactly); the first call starts the stream (zero history) at FN fn0, TN 0,
+ * later calls continue it.  Outputs laid out [frame][arfcn][tn], nchunks/250*117 frames. */
+int btsdsp_trx_radio_host(btsdsp_ctx *ctx, btsdsp_trx *trx, const int16_t *iq, long long iq_pitch, long long nchunks,
+                          int swap_iq, int fn0, int32_t *valid, uint8_t *dgram, int dgram_pitch);
 /* host pointers, synchronous; dgram_pitch >= 158 */
 int btsdsp_trx_pull_host(btsdsp_ctx *ctx, btsdsp_trx *trx, const btsdsp_cf32 *bursts, long long pitch, int nframes,
                          int fn0, int32_t *valid, uint8_t *dgram, int dgram_pitch);

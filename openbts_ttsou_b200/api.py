@@ -77,6 +77,8 @@ _SIGS = {
     "btsdsp_trx_get_state": (_i, [_vp, _vp, _i, _vp, _i]),
     "btsdsp_trx_pull_dev": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i, _vp]),
     "btsdsp_trx_pull_host": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i]),
+    "btsdsp_trx_pull_streams_dev": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i, _vp]),
+    "btsdsp_trx_radio_host": (_i, [_vp, _vp, _vp, _ll, _ll, _i, _i, _vp, _vp, _i]),
     "btsdsp_tx_datagrams_host": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp]),
     "btsdsp_xcch_decode_dev": (_i, [_vp, _vp, _i, _ll, _vp, _vp, _vp]),
     "btsdsp_xcch_decode_host": (_i, [_vp, _vp, _i, _ll, _vp, _vp]),
@@ -435,6 +437,17 @@ class BtsDsp:
         """device tensors/pointers; asynchronous on `stream`"""
         self._ck(self.lib.btsdsp_trx_pull_dev(self.h, trx[0], _p(bursts), pitch, nframes, fn0, _p(valid), _p(dgram),
                                               dgram_pitch, _stream(stream)))
+
+    def trx_radio_host(self, trx, iq, fn0, swap_iq=False):
+        """iq: (narfcn, nchunks*864, 2) int16.  Returns (valid[n], dgram[n,158]) laid out [frame][arfcn][tn]."""
+        iq = np.ascontiguousarray(iq, np.int16)
+        A, ns, _ = iq.shape
+        nchunks = ns // 864
+        n = nchunks // 250 * 117 * A * 8
+        valid = np.zeros(n, np.int32)
+        dg = np.zeros((n, 158), np.uint8)
+        self._ck(self.lib.btsdsp_trx_radio_host(self.h, trx[0], _p(iq), ns, nchunks, int(swap_iq), fn0, _p(valid), _p(dg), 158))
+        return valid, dg
 
     def trx_pull_host(self, trx, bursts, fn0):
         """bursts: (nframes*narfcn*8, pitch) complex64 laid out [frame][arfcn][tn].  Returns (valid[n], dgram[n,158])."""

@@ -916,6 +916,8 @@ struct btsdsp_trx {
   std::vector<uint8_t> chan_type;       // [narfcn][8]
   DevBuf meta, scratch, io;             // device: per-burst kind/tsc/rach maps; pass scratch; host-API staging
   DevBuf pin;                           // pinned host staging of the maps
+  DevBuf radio, res;                    // radio chain: per-ARFCN int16 staging (history + chunks), resampled streams
+  bool have_history = false;            // the radio chain has seen earlier chunks (their last 192 samples are staged)
   cudaEvent_t meta_done = nullptr;      // the previous call's map upload has been consumed
 };
 
@@ -956,6 +958,8 @@ int btsdsp_trx_destroy(btsdsp_ctx *ctx, btsdsp_trx *t) {
   if (t->meta.p) cudaFree(t->meta.p);
   if (t->scratch.p) cudaFree(t->scratch.p);
   if (t->io.p) cudaFree(t->io.p);
+  if (t->radio.p) cudaFree(t->radio.p);
+  if (t->res.p) cudaFree(t->res.p);
   if (t->pin.p) cudaFreeHost(t->pin.p);
   if (t->meta_done) cudaEventDestroy(t->meta_done);
   delete t;
@@ -981,9 +985,10 @@ int btsdsp_trx_set_slot(btsdsp_ctx *ctx, btsdsp_trx *t, int arfcn, int tn, int c
   return BTSDSP_OK;
 }
 
-int btsdsp_trx_pull_dev(btsdsp_ctx *ctx, btsdsp_trx *t, const btsdsp_cf32 *bursts, long long pitch, int nframes, int fn0,
-                        int32_t *valid, uint8_t *dgram, int dgram_pitch, void *stream) {
-  ARG(ctx && t && bursts && valid && dgram && nframes > 0 && pitch >= 157 && fn0 >= 0);
+static int trx_pull_impl(btsdsp_ctx *ctx, btsdsp_trx *t, const btsdsp_cf32 *bursts, long long pitch, long long stream_pitch,
+                         int nframes, int fn0, int32_t *valid, uint8_t *dgram, int dgram_pitch, void *stream) {
+  ARG(ctx && t && bursts && valid && dgram && nframes > 0 && fn0 >= 0);
+  ARG(pitch >= 157 || (pitch == 0 && stream_pitch >= (long long)nframes * 1250));
   fn0 %= kHyperframe;
   ARG(dgram_pitch >= 160 && dgram_pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(dgram) & 7) == 0);
   DeviceGuard g(ctx->device);
@@ -1021,10 +1026,63 @@ int btsdsp_trx_pull_dev(btsdsp_ctx *ctx, btsdsp_trx *t, const btsdsp_cf32 *burst
   CK(cudaEventRecord(t->meta_done, st));
   r = grow_buf(t->scratch, trx_scratch_bytes(n, nr, A), false);
   if (r != BTSDSP_OK) return r;
-  const int nl = launch_trx_pull(ctx->T, t->d_state, A, nframes, fn0, (const cf *)bursts, pitch, dm + o_kind, dm + o_tsc,
-                                 (const int *)(dm + o_idx), (const int *)(dm + o_slot), nr, t->scratch.p, valid, dgram,
-                                 dgram_pitch, st);
+  const int nl = launch_trx_pull(ctx->T, t->d_state, A, nframes, fn0, (const cf *)bursts, pitch, stream_pitch, dm + o_kind,
+                                 dm + o_tsc, (const int *)(dm + o_idx), (const int *)(dm + o_slot), nr, t->scratch.p, valid,
+                                 dgram, dgram_pitch, st);
   LAUNCHED("trx_pull", nl);
+  return BTSDSP_OK;
+}
+
+int btsdsp_trx_pull_dev(btsdsp_ctx *ctx, btsdsp_trx *t, const btsdsp_cf32 *bursts, long long pitch, int nframes, int fn0,
+                        int32_t *valid, uint8_t *dgram, int dgram_pitch, void *stream) {
+  ARG(pitch >= 157);
+  return trx_pull_impl(ctx, t, bursts, pitch, 0, nframes, fn0, valid, dgram, dgram_pitch, stream);
+}
+
+int btsdsp_trx_pull_streams_dev(btsdsp_ctx *ctx, btsdsp_trx *t, const btsdsp_cf32 *streams, long long stream_pitch, int nframes,
+                                int fn0, int32_t *valid, uint8_t *dgram, int dgram_pitch, void *stream) {
+  return trx_pull_impl(ctx, t, streams, 0, stream_pitch, nframes, fn0, valid, dgram, dgram_pitch, stream);
+}
+
+/* radio samples in, datagrams out: RadioInterface::pullBuffer (int16 -> float, 65/96 resample with the running 192-sample
+ * history, radioInterface.cpp:197-273) + slot cutting (:370-394) + pullRadioVector + driveReceiveFIFO, for narfcn radios */
+int btsdsp_trx_radio_host(btsdsp_ctx *ctx, btsdsp_trx *t, const int16_t *iq, long long iq_pitch, long long nchunks, int swap_iq,
+                          int fn0, int32_t *valid, uint8_t *dgram, int dgram_pitch) {
+  ARG(ctx && t && iq && valid && dgram && nchunks > 0 && nchunks % 250 == 0 && iq_pitch >= nchunks * 864 && dgram_pitch >= 158);
+  DeviceGuard g(ctx->device);
+  const int A = t->narfcn;
+  const int nframes = (int)(nchunks / 250 * 117);
+  const long long n = (long long)nframes * A * 8;
+  const long long raw_pitch = 192 + nchunks * 864;                 // int16 pairs per ARFCN in the staging buffer
+  const long long res_pitch = nchunks * 585;                       // resampled samples per ARFCN (a multiple of 2)
+  int r = grow(ctx, t->radio, (size_t)A * raw_pitch * 4, false);
+  if (r != BTSDSP_OK) return r;
+  r = grow(ctx, t->res, (size_t)A * res_pitch * sizeof(cf), false);
+  if (r != BTSDSP_OK) return r;
+  size_t total = 0;
+  auto take = [&total](size_t bytes) { size_t o = (total + 255) & ~(size_t)255; total = o + bytes; return o; };
+  const size_t o_v = take((size_t)n * 4), o_d = take((size_t)n * 160);
+  r = grow(ctx, t->io, total, false);
+  if (r != BTSDSP_OK) return r;
+  cudaStream_t st = ctx->st;
+  int16_t *draw = (int16_t *)t->radio.p;
+  cf *dres = (cf *)t->res.p;
+  uint8_t *dio = (uint8_t *)t->io.p;
+  for (int a = 0; a < A; a++) {
+    int16_t *dst = draw + (size_t)a * raw_pitch * 2;
+    CK(cudaMemcpyAsync(dst + 192 * 2, iq + (size_t)a * iq_pitch * 2, (size_t)nchunks * 864 * 4, cudaMemcpyHostToDevice, st));
+    if (launch_resample_rx_i16(dst + 192 * 2, swap_iq, t->have_history ? 1 : 0, nchunks, dres + (size_t)a * res_pitch, st) < 0)
+      return fail(ctx, BTSDSP_EINVAL, "trx_radio: resampler rejected the staging pointers");
+    // the last 192 raw samples become the next call's history
+    CK(cudaMemcpyAsync(dst, dst + (size_t)nchunks * 864 * 2, 192 * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  LAUNCHED("trx_radio resample", A);
+  t->have_history = true;
+  r = trx_pull_impl(ctx, t, (const btsdsp_cf32 *)dres, 0, res_pitch, nframes, fn0, (int32_t *)(dio + o_v), dio + o_d, 160, st);
+  if (r != BTSDSP_OK) return r;
+  CK(cudaMemcpyAsync(valid, dio + o_v, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpy2DAsync(dgram, dgram_pitch, dio + o_d, 160, 158, (size_t)n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return BTSDSP_OK;
 }
 

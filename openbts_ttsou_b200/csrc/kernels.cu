@@ -19,7 +19,12 @@ namespace btsdsp {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void burst_loc(const BurstSrc &s, long long i, long long *start, int *len) {
   if (s.gather) i = s.gather[i];
-  const long long g = s.first + i;
+  long long g = s.first + i, stream0 = 0;
+  if (s.narfcn > 0) {                               // [frame][arfcn][tn] over per-ARFCN slot streams
+    const long long grp = i >> 3;
+    g = (grp / s.narfcn) * 8 + (i & 7);
+    stream0 = (grp % s.narfcn) * s.arfcn_pitch;
+  }
   const int q = (int)(g & 3);
   const int rule_len = (q == 0 ? 157 : 156) * s.sps;
   if (s.pitch > 0) {
@@ -27,7 +32,7 @@ __device__ __forceinline__ void burst_loc(const BurstSrc &s, long long i, long l
     *len = s.lens ? s.lens[i] : rule_len;
   } else {
     const int off = q == 0 ? 0 : (q == 1 ? 157 : (q == 2 ? 313 : 469));
-    *start = ((g >> 2) * 625 + off) * s.sps;
+    *start = stream0 + ((g >> 2) * 625 + off) * s.sps;
     *len = rule_len;
   }
 }

@@ -19,6 +19,10 @@ struct BurstSrc {
   long long first;
   int sps;
   const int *gather = nullptr;   // optional: burst i of the call is burst gather[i] of the array (outputs stay compact)
+  // optional (pitch == 0 only): narfcn parallel slot streams, arfcn_pitch samples apart, with the bursts of the call
+  // numbered [frame][arfcn][tn]: burst i lives in stream (i/8) % narfcn at slot (i / (8 narfcn)) * 8 + i % 8
+  int narfcn = 0;
+  long long arfcn_pitch = 0;
 };
 
 struct NormalOut {      // per burst; null pointers are skipped
@@ -89,8 +93,8 @@ int launch_rach_decode(const unsigned char *soft, int burst_pitch, long long n, 
 // the caller-policy pipeline (trx_policy.cuh / trx_kernels.cuh)
 size_t trx_scratch_bytes(long long n, long long nr, int narfcn);
 int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, int fn0, const cf *bursts, long long pitch,
-                    const uint8_t *kind, const uint8_t *tsc, const int *rach_idx, const int *rach_slot, long long nr,
-                    void *scratch, int *valid, unsigned char *dgram, int dgram_pitch, cudaStream_t stream);
+                    long long stream_pitch, const uint8_t *kind, const uint8_t *tsc, const int *rach_idx, const int *rach_slot,
+                    long long nr, void *scratch, int *valid, unsigned char *dgram, int dgram_pitch, cudaStream_t stream);
 
 // scratch (complex samples) the generic-sps global-memory variants need per burst
 __host__ __device__ inline size_t scratch_per_burst(int sps) { return (size_t)(2 * 157 + 36) * sps + 64; }

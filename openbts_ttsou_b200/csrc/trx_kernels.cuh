@@ -170,13 +170,16 @@ static TrxScratch trx_carve(void *base, long long n, long long nr, int narfcn) {
 
 // The whole pull for one batch.  kind / tsc: one byte per burst (CorrType, midamble code); rach_idx: the nr bursts in
 // RACH slots; rach_slot: per burst, its index in rach_idx or -1.  All device pointers.  Returns the launch count.
+// pitch > 0: bursts laid out [frame][arfcn][tn] at that pitch; pitch == 0: `bursts` holds narfcn continuous slot
+// streams, stream_pitch samples apart (what the RX resampler writes).
 int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, int fn0, const cf *bursts, long long pitch,
-                    const uint8_t *kind, const uint8_t *tsc, const int *rach_idx, const int *rach_slot, long long nr,
-                    void *scratch, int *valid, unsigned char *dgram, int dgram_pitch, cudaStream_t stream) {
+                    long long stream_pitch, const uint8_t *kind, const uint8_t *tsc, const int *rach_idx, const int *rach_slot,
+                    long long nr, void *scratch, int *valid, unsigned char *dgram, int dgram_pitch, cudaStream_t stream) {
   const long long n = (long long)nframes * narfcn * 8;
   if (n <= 0) return 0;
   const TrxScratch s = trx_carve(scratch, n, nr, narfcn);
   BurstSrc src{bursts, pitch, nullptr, 0, 1};
+  if (pitch == 0) { src.narfcn = narfcn; src.arfcn_pitch = stream_pitch; }
   int launches = 0;
   const long long nwarps = (n + 31) / 32;
   NormalOut none{};

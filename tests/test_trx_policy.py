@@ -199,3 +199,43 @@ def test_policy_edge_cases_gpu(oracle_best, dsp):
     dsp.trx_destroy(trx)
     assert np.array_equal(np.concatenate(v2), valid) and np.array_equal(np.concatenate(d2), dg)
     check_state(st, state, "gpu edge")
+
+
+@pytest.mark.gpu
+def test_radio_to_datagrams_chain(oracle_best, dsp):
+    """int16 radio samples of three ARFCNs -> datagrams, in two calls of 250 chunks (history and policy state carry over),
+    against: reference resampler over each whole stream -> slot cutting -> reference-glue pull per ARFCN"""
+    rng = np.random.default_rng(99)
+    A, nch = 3, 500
+    nframes, fn0 = nch // 250 * 117, 777
+    tsc = [1, 6, 3]
+    ct = [[1, 1, 1, 5, 1, 7, 1, 1], [1] * 8, [4, 1, 1, 1, 0, 1, 1, 2]]
+    iq = np.zeros((A, nch * 864, 2), np.int16)
+    for a in range(A):                                   # a clean downlink-style signal per ARFCN, then noise and level changes
+        bits = np.stack([synth.normal_burst_bits(rng, tsc[a]) for _ in range(nframes * 8)])
+        tx = np.zeros((nch * 864, 2), np.int16)
+        dsp.tx_stream_host(bits, nframes * 8, tx)
+        level = np.repeat(rng.choice([0.02, 0.3, 1.0], 500), nch * 864 // 500)[:, None]
+        x = tx * level + 40.0 * rng.standard_normal(tx.shape)
+        iq[a] = np.clip(np.rint(x), -32768, 32767).astype(np.int16)
+    trx = dsp.trx_create(tsc, ct, fn0)
+    v1, d1 = dsp.trx_radio_host(trx, iq[:, :250 * 864], fn0)
+    v2, d2 = dsp.trx_radio_host(trx, iq[:, 250 * 864:], fn0 + 117)
+    st = dsp.trx_state(trx)
+    dsp.trx_destroy(trx)
+    got_v = np.concatenate([v1, v2]).reshape(nframes, A, 8)
+    got_d = np.concatenate([d1, d2]).reshape(nframes, A, 8, 158)
+    off = (0, 157, 313, 469)
+    for a in range(A):
+        raw = (iq[a, :, 0].astype(np.float32) + 1j * iq[a, :, 1].astype(np.float32)).astype(np.complex64)
+        res = oracle_best.rx_resample_stream(raw, threads=4)
+        bursts = np.zeros((nframes * 8, 160), np.complex64)
+        for g in range(nframes * 8):
+            s, ln = (g // 4) * 625 + off[g % 4], (157 if g % 4 == 0 else 156)
+            bursts[g, :ln] = res[s:s + ln]
+        so = oracle_best.trx_new(tsc[a], ct[a], fn0)
+        vo, do = oracle_best.trx_pull(so, bursts, fn0)
+        assert np.array_equal(vo.reshape(nframes, 8), got_v[:, a]), a
+        assert np.array_equal(do[:, :158].reshape(nframes, 8, 158), got_d[:, a]), a
+        check_state(st[a:a + 1], so, "radio chain %d" % a)
+    assert 0.2 < got_v.mean() < 0.95
