@@ -279,6 +279,21 @@ int btsdsp_rach_decode_dev(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pi
 int btsdsp_rach_decode_host(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pitch, long long n, uint8_t *u,
                             int32_t *fields);
 
+/* ---- the reference's second transceiver variant (Transceiver52M/sigProcLib.cpp): the functions whose
+ * arithmetic differs from the main variant.  analyzeTrafficBurst there searches only +-max_toa symbols around the
+ * expected midamble position (convolve's CUSTOM span, :966-1077; max_toa < 3*sps is raised to 3*sps, max_toa <= 60) and
+ * counts TOA from the window centre; energyDetect strides its window by four samples (:944-963, needs 4*(window-1) < n).
+ * Everything else of that variant (modulate, delay, RACH, demodulate, DFE, resample) computes what the main entry points
+ * compute.  chan: 6*sps per burst. ---- */
+int btsdsp_analyze_52m_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens, long long first,
+                           const uint8_t *tsc, long long n, float detect_thr, unsigned max_toa, int request_channel,
+                           int32_t *flag, btsdsp_cf32 *amp, float *toa, btsdsp_cf32 *chan, float *chan_off, void *stream);
+int btsdsp_analyze_traffic_burst_52m(btsdsp_ctx *ctx, const btsdsp_cf32 *burst, int n, unsigned tsc, float threshold,
+                                     unsigned max_toa, int request_channel, int *detected, btsdsp_cf32 *amp, float *toa,
+                                     btsdsp_cf32 *chan, float *chan_off);
+int btsdsp_energy_detect_52m(btsdsp_ctx *ctx, const btsdsp_cf32 *v, int n, unsigned window, float threshold, float *avg_pwr,
+                             int *above);
+
 void *btsdsp_host_alloc(size_t bytes);
 void btsdsp_host_free(void *p);
 

@@ -84,6 +84,9 @@ _SIGS = {
     "btsdsp_xcch_decode_host": (_i, [_vp, _vp, _i, _ll, _vp, _vp]),
     "btsdsp_rach_decode_dev": (_i, [_vp, _vp, _i, _ll, _vp, _vp, _vp]),
     "btsdsp_rach_decode_host": (_i, [_vp, _vp, _i, _ll, _vp, _vp]),
+    "btsdsp_analyze_52m_dev": (_i, [_vp, _vp, _ll, _vp, _ll, _vp, _ll, _f, _u, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "btsdsp_analyze_traffic_burst_52m": (_i, [_vp, _vp, _i, _u, _f, _u, _i, _vp, _vp, _vp, _vp, _vp]),
+    "btsdsp_energy_detect_52m": (_i, [_vp, _vp, _i, _u, _f, _vp, _vp]),
     "btsdsp_host_alloc": (_vp, [ctypes.c_size_t]),
     "btsdsp_host_free": (None, [_vp]),
 }
@@ -400,6 +403,39 @@ class BtsDsp:
         for a in range(trx[1]):
             self._ck(self.lib.btsdsp_trx_get_state(self.h, trx[0], a, _p(st[a:a + 1]), st.itemsize))
         return st
+
+    def analyze_52m(self, burst, tsc, thr=3.0, max_toa=3, request=True):
+        """Transceiver52M's analyzeTrafficBurst on one burst -> (detected, amp, toa, chan, off)"""
+        burst = _c64(burst)
+        det = ctypes.c_int(0)
+        amp = np.zeros(1, np.complex64); toa = np.zeros(1, np.float32)
+        chan = np.zeros(6 * self.sps, np.complex64); off = np.zeros(1, np.float32)
+        self._ck(self.lib.btsdsp_analyze_traffic_burst_52m(self.h, _p(burst), burst.size, tsc, thr, max_toa, int(request),
+                                                           ctypes.byref(det), _p(amp), _p(toa), _p(chan), _p(off)))
+        return bool(det.value), amp[0], toa[0], chan, off[0]
+
+    def analyze_52m_host(self, bursts, lens, tsc, thr=3.0, max_toa=3, request=True):
+        """batched, through device buffers made here (torch-free): returns dict(flag, amp, toa, chan, off)"""
+        import torch
+        bursts = _c64(bursts)
+        n, pitch = bursts.shape
+        dev = torch.device("cuda:%d" % self.device)
+        d_b = torch.from_numpy(bursts.view(np.float32).copy()).to(dev)
+        d_l = torch.from_numpy(np.ascontiguousarray(lens, np.int32)).to(dev)
+        d_t = torch.from_numpy(np.ascontiguousarray(tsc, np.uint8)).to(dev)
+        flag = torch.zeros(n, dtype=torch.int32, device=dev); amp = torch.zeros(n * 2, device=dev)
+        toa = torch.zeros(n, device=dev); chan = torch.zeros(n * 12 * self.sps, device=dev); off = torch.zeros(n, device=dev)
+        self._ck(self.lib.btsdsp_analyze_52m_dev(self.h, _p(d_b), pitch, _p(d_l), 0, _p(d_t), n, thr, max_toa, int(request),
+                                                 _p(flag), _p(amp), _p(toa), _p(chan), _p(off), None))
+        torch.cuda.synchronize()
+        return dict(flag=flag.cpu().numpy(), amp=amp.cpu().numpy().view(np.complex64), toa=toa.cpu().numpy(),
+                    chan=chan.cpu().numpy().view(np.complex64).reshape(n, 6 * self.sps), off=off.cpu().numpy())
+
+    def energy_detect_52m(self, v, win, thr):
+        v = _c64(v)
+        avg = ctypes.c_float(0); above = ctypes.c_int(0)
+        self._ck(self.lib.btsdsp_energy_detect_52m(self.h, _p(v), v.size, win, thr, ctypes.byref(avg), ctypes.byref(above)))
+        return bool(above.value), np.float32(avg.value)
 
     def xcch_decode_host(self, soft_u8):
         """soft_u8: (nframes*4, >=148) uint8 -> (u[nframes,228] uint8, ok[nframes] int32)"""

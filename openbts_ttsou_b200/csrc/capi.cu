@@ -1202,4 +1202,72 @@ int btsdsp_rach_decode_host(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_p
   return BTSDSP_OK;
 }
 
+/* ---- the reference's second transceiver variant (Transceiver52M/sigProcLib.cpp), the functions that differ ---- */
+int btsdsp_analyze_52m_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens, long long first,
+                           const uint8_t *tsc, long long n, float detect_thr, unsigned max_toa, int request_channel,
+                           int32_t *flag, btsdsp_cf32 *amp, float *toa, btsdsp_cf32 *chan, float *chan_off, void *stream) {
+  ARG(ctx && bursts && tsc && n >= 0 && pitch >= 0 && max_toa <= 60);
+  DeviceGuard g(ctx->device);
+  GROW(B_SCRATCH, (size_t)(n > 0 ? n : 1) * analyze_52m_scratch_stride(max_toa, ctx->sps) * sizeof(cf));
+  NormalOut o = {flag, (cf *)amp, toa, (cf *)chan, chan_off, nullptr, nullptr, nullptr, 0};
+  const int nl = launch_analyze_52m(ctx->T, make_src(bursts, pitch, lens, first, ctx->sps), tsc, n, detect_thr, max_toa,
+                                    request_channel, o, dbuf<cf>(ctx, B_SCRATCH), (cudaStream_t)stream);
+  LAUNCHED("analyze_52m", nl);
+  return BTSDSP_OK;
+}
+
+int btsdsp_analyze_traffic_burst_52m(btsdsp_ctx *ctx, const btsdsp_cf32 *burst, int n, unsigned tsc, float threshold,
+                                     unsigned max_toa, int request_channel, int *detected, btsdsp_cf32 *amp, float *toa,
+                                     btsdsp_cf32 *chan, float *chan_off) {
+  ARG(ctx && burst && detected && amp && toa && tsc < 8 && n >= 148 * ctx->sps && n <= 157 * kMaxSps && max_toa <= 60);
+  ARG(!request_channel || (chan && chan_off));
+  DeviceGuard g(ctx->device);
+  const int sps = ctx->sps;
+  GROW(B_A, (size_t)n * sizeof(cf));
+  GROW(B_D, 1024);
+  cudaStream_t st = ctx->st;
+  uint8_t *d = dbuf<uint8_t>(ctx, B_D);
+  int32_t *dflag = (int32_t *)d; cf *damp = (cf *)(d + 16); float *dtoa = (float *)(d + 32), *doff = (float *)(d + 48);
+  cf *dchan = (cf *)(d + 64); uint8_t *dtsc = d + 512; int32_t *dlen = (int32_t *)(d + 528);
+  const uint8_t t8 = (uint8_t)tsc; const int32_t l32 = n;
+  CK(cudaMemcpyAsync(dbuf<cf>(ctx, B_A), burst, (size_t)n * sizeof(cf), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dtsc, &t8, 1, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dlen, &l32, 4, cudaMemcpyHostToDevice, st));
+  int r = btsdsp_analyze_52m_dev(ctx, (const btsdsp_cf32 *)dbuf<cf>(ctx, B_A), n, dlen, 0, dtsc, 1, threshold, max_toa,
+                                 request_channel, dflag, (btsdsp_cf32 *)damp, dtoa, (btsdsp_cf32 *)dchan, doff, st);
+  if (r != BTSDSP_OK) return r;
+  int32_t f = 0;
+  CK(cudaMemcpyAsync(&f, dflag, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(amp, damp, sizeof(cf), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(toa, dtoa, 4, cudaMemcpyDeviceToHost, st));
+  if (request_channel) {
+    CK(cudaMemcpyAsync(chan, dchan, (size_t)6 * sps * sizeof(cf), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(chan_off, doff, 4, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  *detected = f;
+  return BTSDSP_OK;
+}
+
+int btsdsp_energy_detect_52m(btsdsp_ctx *ctx, const btsdsp_cf32 *v, int n, unsigned window, float threshold, float *avg_pwr,
+                             int *above) {
+  ARG(ctx && v && above && n > 0 && window > 0 && 4LL * ((long long)(window < (unsigned)n ? window : n) - 1) < n);
+  DeviceGuard g(ctx->device);
+  GROW(B_A, (size_t)n * sizeof(cf));
+  GROW(B_D, 64);
+  cudaStream_t st = ctx->st;
+  CK(cudaMemcpyAsync(dbuf<cf>(ctx, B_A), v, (size_t)n * sizeof(cf), cudaMemcpyHostToDevice, st));
+  float *davg = dbuf<float>(ctx, B_D);
+  int *dflag = (int *)(davg + 4);
+  launch_energy_detect_52m(dbuf<cf>(ctx, B_A), n, window, threshold, davg, dflag, st);
+  LAUNCHED("energy_detect_52m", 1);
+  int f = 0; float a = 0.0F;
+  CK(cudaMemcpyAsync(&f, dflag, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&a, davg, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *above = f;
+  if (avg_pwr) *avg_pwr = a;
+  return BTSDSP_OK;
+}
+
 }  // extern "C"

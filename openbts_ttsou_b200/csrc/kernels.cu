@@ -861,6 +861,47 @@ void launch_equalize_generic(const DevTables *T, cf *burst, int n, float toa, co
   k_equalize_generic<<<1, 32, 0, st>>>(T, burst, n, toa, w, nw, b, nb, tmp, soft);
 }
 
+// ------------------------------------------------------------------------------------------------
+// The second transceiver variant's analyzeTrafficBurst (windowed search, Transceiver52M/sigProcLib.cpp:966-1077):
+// one thread per burst over global scratch (2 x (2*maxTOA+1) samples each); functional, any sps.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_analyze_52m(const DevTables *__restrict__ T, BurstSrc src, const uint8_t *__restrict__ tsc, long long n,
+                              float detect_thr, unsigned max_toa, int request, NormalOut out, cf *scratch, int scratch_stride) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long start; int len;
+  burst_loc(src, i, &start, &len);
+  cf amp = mk(0.0F, 0.0F), chan[6 * kMaxSps];
+  for (int j = 0; j < 6 * kMaxSps; j++) chan[j] = mk(0.0F, 0.0F);
+  float toa = 0.0F, off = 0.0F;
+  cf *s = scratch + (size_t)i * scratch_stride;
+  const bool ok = analyze_traffic_52m<1>(T, View<1>{(cf *)src.base + start}, tsc[i], detect_thr, src.sps, max_toa, View<1>{s},
+                                         View<1>{s + scratch_stride / 2}, &amp, &toa, request != 0, chan, &off);
+  if (out.flag) out.flag[i] = ok ? 1 : 0;
+  if (out.amp) out.amp[i] = amp;
+  if (out.toa) out.toa[i] = toa;
+  const bool have = ok && request;
+  if (out.off) out.off[i] = have ? off : 0.0F;
+  if (out.chan) for (int j = 0; j < 6 * src.sps; j++) out.chan[i * 6 * src.sps + j] = have ? chan[j] : mk(0.0F, 0.0F);
+}
+int analyze_52m_scratch_stride(unsigned max_toa, int sps) {
+  if (max_toa < 3u * sps) max_toa = 3 * sps;
+  return 2 * (2 * (int)max_toa + 2);
+}
+int launch_analyze_52m(const DevTables *T, BurstSrc src, const uint8_t *tsc, long long n, float detect_thr, unsigned max_toa,
+                       int request, NormalOut out, cf *scratch, cudaStream_t st) {
+  if (n <= 0) return 0;
+  k_analyze_52m<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(T, src, tsc, n, detect_thr, max_toa, request, out, scratch,
+                                                         analyze_52m_scratch_stride(max_toa, src.sps));
+  return 1;
+}
+__global__ void k_energy_detect_52m(const cf *v, int n, unsigned win, float thr, float *avg, int *flag) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *flag = energy_detect_52m<1>(View<1>{(cf *)v}, n, win, thr, avg) ? 1 : 0;
+}
+void launch_energy_detect_52m(const cf *v, int n, unsigned win, float thr, float *avg, int *flag, cudaStream_t st) {
+  k_energy_detect_52m<<<1, 32, 0, st>>>(v, n, win, thr, avg, flag);
+}
+
 #include "trx_kernels.cuh"
 #include "fec_kernels.cuh"
 

@@ -87,6 +87,11 @@ int launch_equalize(const DevTables *T, BurstSrc src, long long n, const float *
 int launch_demodulate(const DevTables *T, BurstSrc src, long long n, const cf *amp, const float *toa, float *soft,
                       int soft_pitch, cf *scratch, cudaStream_t st);
 int launch_design_dfe(const cf *chan, const float *snr, long long n, cf *w, cf *b, cudaStream_t st);
+// the second transceiver variant (Transceiver52M): windowed analyzeTrafficBurst, stride-4 energyDetect
+int analyze_52m_scratch_stride(unsigned max_toa, int sps);
+int launch_analyze_52m(const DevTables *T, BurstSrc src, const uint8_t *tsc, long long n, float detect_thr, unsigned max_toa,
+                       int request, NormalOut out, cf *scratch, cudaStream_t st);
+void launch_energy_detect_52m(const cf *v, int n, unsigned win, float thr, float *avg, int *flag, cudaStream_t st);
 // L1 FEC after the path (fec.cuh / fec_kernels.cuh)
 int launch_xcch_decode(const unsigned char *soft, int burst_pitch, long long nframes, unsigned char *u, int *ok, cudaStream_t st);
 int launch_rach_decode(const unsigned char *soft, int burst_pitch, long long n, unsigned char *u, int *fields, cudaStream_t st);

@@ -260,6 +260,77 @@ BTS_HD bool analyze_traffic(const DevTables *__restrict__ T, View<S> burst, int 
   return detected;
 }
 
+// ---- the reference's second transceiver variant (Transceiver52M/sigProcLib.cpp) -----------------
+// energyDetect there strides its window by four samples (:944-963)
+template <int S>
+BTS_HD bool energy_detect_52m(View<S> v, int n, unsigned win, float thr, float *avg) {
+  float energy = 0.0F;
+  if (win > (unsigned)n) win = n;
+  for (unsigned i = 0; i < win; i++) energy = BTS_ADD(energy, cnorm2(v.ld(4 * i)));
+  float a = BTS_DIV(energy, (float)win);
+  if (avg) *avg = a;
+  return a > BTS_MUL(thr, thr);
+}
+// analyzeTrafficBurst with a search window of +-maxTOA symbols (:966-1077): the midamble correlation is evaluated only
+// at the 2*maxTOA+1 lags around the expected peak (convolve's CUSTOM span), TOA is counted from the window centre.
+// The midamble table is the main variant's (its stored TOA is 5*sps less than this variant's, :779-828 vs 52M).
+// corr / tmp: scratch of 2*maxTOA+1 samples.  maxTOA <= 60.
+template <int S>
+BTS_HD bool analyze_traffic_52m(const DevTables *__restrict__ T, View<S> burst, int tsc, float thr, int sps, unsigned maxTOA,
+                                View<S> corr, View<S> tmp, cf *amplitude, float *TOA, bool request, cf *chan, float *chanOff) {
+  if (maxTOA < 3u * sps) maxTOA = 3 * sps;
+  unsigned spanTOA = maxTOA;
+  if (spanTOA < 5u * sps) spanTOA = 5 * sps;
+  const int startIx = (66 - (int)spanTOA) * sps, endIx = (66 + 16 + (int)spanTOA) * sps;
+  const int windowLen = endIx - startIx, corrLen = 2 * (int)maxTOA + 1, lb = 16 * sps;
+  const float midTOA = BTS_ADD(T->mid_toa[tsc], (float)(5 * sps));       // exact: undoes the main variant's "- 5*sps"
+  const unsigned expectedPeak = (unsigned)round((double)BTS_ADD(midTOA, (float)((lb - 1) / 2)));
+  View<S> seg = burst.at(startIx);
+  const cf *seq = T->mid_seq[tsc];
+  const int start = (int)expectedPeak - (int)maxTOA;
+  for (int i = 0; i < corrLen; i++) corr.st(i, conv_cc_at<S>(seg, windowLen, seq, lb, start + i, true));
+  float toa;
+  cf amp = peak_detect<S, false>(T, corr, corrLen, &toa, nullptr);
+  if ((toa < 0.0F) || (toa > (float)corrLen)) { *amplitude = mk(0.0F, 0.0F); *TOA = toa; return false; }
+  const int p = (int)rintf(toa);
+  float valley = 0.0F;
+  int numRms = 0;
+  for (int i = 2 * sps; i <= 5 * sps; i++) {
+    if (p - i >= 0)      { valley = BTS_ADD(valley, cnorm2(corr.ld(p - i))); numRms++; }
+    if (p + i < corrLen) { valley = BTS_ADD(valley, cnorm2(corr.ld(p + i))); numRms++; }
+  }
+  if (numRms < 2) { *amplitude = mk(0.0F, 0.0F); *TOA = toa; return false; }
+  const float RMS = (float)((double)BTS_SQRT(BTS_DIV(valley, (float)numRms)) + 0.00001);
+  const float peakToMean = BTS_DIV(cabs_(amp), RMS);
+  amp = cdiv(amp, T->mid_gain[tsc]);
+  toa = BTS_SUB(toa, (float)maxTOA);
+  *amplitude = amp;
+  *TOA = toa;
+  const bool detected = peakToMean > thr;
+  if (request && detected) {
+    const float TOAoffset = (float)maxTOA;
+    delay_vector<S>(T, corr, corrLen, -toa, tmp);
+    const int clen = 6 * sps;
+    float maxEnergy = -1.0F;
+    int maxI = -1;
+    for (int i = 0; i < 7; i++) {
+      const float pos = BTS_ADD(TOAoffset, (float)((i - 5) * sps));
+      if (BTS_ADD(pos, (float)clen) > (float)corrLen) continue;
+      if (pos < 0.0F) continue;
+      const int s0 = (int)floorf(pos);
+      float energy = 0.0F;
+      for (int j = 0; j < clen; j++) energy = BTS_ADD(energy, cnorm2(corr.ld(s0 + j)));
+      if ((double)energy > 0.95 * (double)maxEnergy) { maxI = i; maxEnergy = energy; }
+    }
+    // with a window narrower than 6*sps + 5*sps no position qualifies and the reference indexes with maxI = -1; keep that
+    const int s0 = (int)floorf(BTS_ADD(TOAoffset, (float)((maxI - 5) * sps)));
+    const cf g = cdiv(mk(1.0F, 0.0F), T->mid_gain[tsc]);
+    for (int j = 0; j < clen; j++) chan[j] = (s0 + j >= 0 && s0 + j < corrLen) ? cmul(corr.ld(s0 + j), g) : mk(0.0F, 0.0F);
+    *chanOff = (float)(5 * sps - maxI);
+  }
+  return detected;
+}
+
 // detectRACHBurst :860-914.  corr = scratch of n samples.
 template <int S, bool GRID>
 BTS_HD bool detect_rach(const DevTables *__restrict__ T, View<S> burst, int n, float thr, int sps, View<S> corr,

@@ -175,6 +175,28 @@ bool analyzeTrafficBurst(signalVector &rxBurst, unsigned TSC, float thr, int sps
   return det != 0;
 }
 
+/* The second transceiver variant's signature (Transceiver52M/sigProcLib.h:290-305: an extra maxTOA); C++ overload, so a
+ * Transceiver52M caller links against it unchanged. */
+bool analyzeTrafficBurst(signalVector &rxBurst, unsigned TSC, float thr, int sps, complex *amplitude, float *TOA,
+                         unsigned maxTOA, bool requestChannel, signalVector **channelResponse,
+                         float *channelResponseOffset) {                                  /* Transceiver52M/sigProcLib.cpp:966 */
+  btsdsp_cf32 a, chan[6 * 4];
+  float off = 0.0F;
+  int det = 0;
+  check(btsdsp_analyze_traffic_burst_52m(ctx(), cp(rxBurst), rxBurst.size(), TSC, thr, maxTOA, requestChannel, &det, &a, TOA,
+                                         chan, &off),
+        "analyzeTrafficBurst (52M)");
+  *amplitude = complex(a.re, a.im);
+  if (requestChannel && det) {
+    if (channelResponse) {
+      *channelResponse = new signalVector(6 * sps);
+      memcpy((*channelResponse)->begin(), chan, 6 * sps * sizeof(complex));
+    }
+    if (channelResponseOffset) *channelResponseOffset = off;
+  }
+  return det != 0;
+}
+
 signalVector *decimateVector(signalVector &wVector, int decimationFactor) {   /* :1039 */
   if (decimationFactor <= 1) return NULL;
   signalVector *d = new signalVector(wVector.size() / decimationFactor);

@@ -55,6 +55,10 @@ bool detectRACHBurst(signalVector &rxBurst, float detectThreshold, int samplesPe
 bool analyzeTrafficBurst(signalVector &rxBurst, unsigned TSC, float detectThreshold, int samplesPerSymbol,
                          complex *amplitude, float *TOA, bool requestChannel = false,
                          signalVector **channelResponse = NULL, float *channelResponseOffset = NULL);
+/* Transceiver52M's form (extra maxTOA, windowed search) */
+bool analyzeTrafficBurst(signalVector &rxBurst, unsigned TSC, float detectThreshold, int samplesPerSymbol,
+                         complex *amplitude, float *TOA, unsigned maxTOA, bool requestChannel,
+                         signalVector **channelResponse, float *channelResponseOffset);
 signalVector *decimateVector(signalVector &wVector, int decimationFactor);
 SoftVector *demodulateBurst(const signalVector &rxBurst, const signalVector &gsmPulse, int samplesPerSymbol,
                             complex channel, float TOA);

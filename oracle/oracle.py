@@ -32,7 +32,7 @@ T_COS, T_SIN, T_ROT, T_REVROT, T_PULSE, T_MID_SEQ, T_MID_META, T_RACH_SEQ, T_RAC
 
 def build(ref=True):
     """(Re)build the checkers with oracle/Makefile.  ref is skipped by make when /root/reference is absent."""
-    subprocess.run(["make", "-C", HERE, "port"] + (["ref"] if ref else []), check=True,
+    subprocess.run(["make", "-C", HERE, "port"] + (["ref", "ref52"] if ref else []), check=True,
                    stdout=subprocess.DEVNULL)
 
 
@@ -46,6 +46,34 @@ def _ptr(a):
 
 def _c64(a):
     return np.ascontiguousarray(a, dtype=np.complex64)
+
+
+class Oracle52:
+    """The reference's second transceiver variant (Transceiver52M/sigProcLib.cpp) compiled in place: only the functions
+    that differ from the main variant.  Exists only where oracle/_ref/libref52_oracle.so was built."""
+    SO = os.path.join(HERE, "_ref", "libref52_oracle.so")
+
+    def __init__(self, sps=1):
+        if not os.path.exists(self.SO):
+            raise FileNotFoundError(self.SO)
+        self.lib = ctypes.CDLL(self.SO)
+        self.sps = sps
+        self.lib.ref52_setup(c_i(sps))
+
+    def analyze(self, burst, tsc, thr=3.0, max_toa=3, request=True):
+        burst = _c64(burst)
+        amp = np.zeros(1, np.complex64); toa = np.zeros(1, np.float32)
+        chan = np.zeros(6 * self.sps, np.complex64); off = np.zeros(1, np.float32)
+        self.lib.ref52_setup(c_i(self.sps))
+        ok = self.lib.ref52_analyze(_ptr(burst), c_i(burst.size), c_i(tsc), c_f(thr), c_i(self.sps), ctypes.c_uint(max_toa),
+                                    c_i(int(request)), _ptr(amp), _ptr(toa), _ptr(chan), _ptr(off))
+        return bool(ok), amp[0], toa[0], chan, off[0]
+
+    def energy_detect(self, v, win, thr):
+        v = _c64(v)
+        avg = np.zeros(1, np.float32)
+        ok = self.lib.ref52_energy_detect(_ptr(v), c_i(v.size), ctypes.c_uint(win), c_f(thr), _ptr(avg))
+        return bool(ok), avg[0]
 
 
 class Oracle:

@@ -85,6 +85,20 @@ class Emu:
         self.lib.emu_rach_decode(P(soft_u8), c_i(soft_u8.shape[1]), c_ll(n), P(u), P(tail), P(bsic), P(ra))
         return u, tail, bsic, ra
 
+    def analyze_52m(self, burst, tsc, thr=3.0, max_toa=3, request=True):
+        burst = np.ascontiguousarray(burst, np.complex64)
+        amp = np.zeros(1, np.complex64); toa = np.zeros(1, np.float32)
+        chan = np.zeros(6 * self.sps, np.complex64); off = np.zeros(1, np.float32)
+        ok = self.lib.emu_analyze_52m(P(burst), c_i(burst.size), c_i(tsc), c_f(thr), ctypes.c_uint(max_toa), c_i(int(request)),
+                                      P(amp), P(toa), P(chan), P(off))
+        return bool(ok), amp[0], toa[0], chan, off[0]
+
+    def energy_detect_52m(self, v, win, thr):
+        v = np.ascontiguousarray(v, np.complex64)
+        avg = np.zeros(1, np.float32)
+        ok = self.lib.emu_energy_detect_52m(P(v), c_i(v.size), ctypes.c_uint(win), c_f(thr), P(avg))
+        return bool(ok), avg[0]
+
     def rx_rach_batch(self, bursts, lens, detect_thr=5.0, tiles=True):
         bursts = np.ascontiguousarray(bursts, np.complex64)
         n, pitch = bursts.shape

@@ -602,4 +602,22 @@ void emu_rach_decode(const unsigned char *soft, int burst_pitch, long long n, un
   for (long long i = 0; i < n; i++) rach_decode_burst_seq(soft + i * (long long)burst_pitch, u + i * kRachU, tail + i, bsic + i, ra + i);
 }
 
+// Transceiver52M's analyzeTrafficBurst / energyDetect (the functions that differ from the main variant)
+int emu_analyze_52m(const float *burst, int n, int tsc, float thr, unsigned max_toa, int request, float *amp, float *toa,
+                    float *chan, float *off) {
+  std::vector<cf> scratch(512);
+  cf a = mk(0.0F, 0.0F), ch[6 * kMaxSps];
+  for (int j = 0; j < 6 * kMaxSps; j++) ch[j] = mk(0.0F, 0.0F);
+  float t = 0.0F, o = 0.0F;
+  (void)n;
+  const bool ok = analyze_traffic_52m<1>(T, View<1>{(cf *)burst}, tsc, thr, T->sps, max_toa, View<1>{scratch.data()},
+                                         View<1>{scratch.data() + 256}, &a, &t, request != 0, ch, &o);
+  amp[0] = a.x; amp[1] = a.y; *toa = t;
+  if (ok && request) { memcpy(chan, ch, sizeof(cf) * 6 * T->sps); *off = o; }
+  return ok ? 1 : 0;
+}
+int emu_energy_detect_52m(const float *v, int n, unsigned win, float thr, float *avg) {
+  return energy_detect_52m<1>(View<1>{(cf *)v}, n, win, thr, avg) ? 1 : 0;
+}
+
 }  // extern "C"
