@@ -356,6 +356,51 @@ def main():
         torch.cuda.synchronize()
         gather = {"what": "all_gather of 8192 SoftVectors (148 f32) per rank over NCCL", "ms": a.elapsed_time(b) / 10}
 
+    # ---- the other entry points, live and device-resident (rank 0, N = 1 only; reported next to the headline,
+    #      not part of it): fused TX chain, caller-policy pull, XCCH block decode
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_e2e:
+        def timeit(fn, reps=5):
+            fn(); fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        secondary = {}
+        ntx = min(nb, 936 * 256)
+        iq2 = torch.empty(ntx // 4 * 625 // 585 * 864 * 2, dtype=torch.int16, device=dev)
+        ms = timeit(lambda: dsp.tx_stream_dev(bits, ntx, iq2, stream=stream))
+        secondary["tx_chain_bits_to_int16"] = {"bursts": ntx, "ms": ms, "bursts_per_s": ntx / ms * 1e3}
+        A, F = 1024, 32
+        npol = A * 8 * F
+        if nb >= npol:
+            ct = np.ones((A, 8), np.uint8)
+            ct[:, 0] = 5
+            trx = dsp.trx_create(np.zeros(A, np.uint8), ct, 0)
+            # A parallel slot streams of F frames each, cut by address out of the resampled stream (F*1250 samples apart)
+            pv = torch.zeros(npol, dtype=torch.int32, device=dev)
+            pd = torch.zeros(npol * 160, dtype=torch.uint8, device=dev)
+            fnc = [0]
+
+            def pull():
+                dsp.trx_pull_streams_dev(trx, res, F * 1250, F, fnc[0], pv, pd, 160, stream=stream)
+                fnc[0] += F
+            ms = timeit(pull)
+            secondary["policy_pull_1024_arfcn"] = {"bursts": npol, "ms": ms, "bursts_per_s": npol / ms * 1e3,
+                                                   "valid": float(pv.float().mean())}
+            # the pull's soft bytes, four bursts per frame, through the XCCH block decoder
+            nfr = npol // 4
+            fu = torch.zeros(nfr * 228, dtype=torch.uint8, device=dev)
+            fok = torch.zeros(nfr, dtype=torch.int32, device=dev)
+            ms = timeit(lambda: dsp.xcch_decode_dev(pd[8:], 160, nfr, fu, fok, stream=stream))
+            secondary["xcch_decode"] = {"frames": nfr, "ms": ms, "bursts_per_s": npol / ms * 1e3}
+            dsp.trx_destroy(trx)
+        del iq2
+
     # ---- CPU baseline on the same stream (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -393,7 +438,7 @@ def main():
                          "kernels": [k_res, k_det, k_eq, k_dem],
                          "step_frac_of_fused_hbm_roof": (nb * FUSED_BYTES_PER_BURST / (ms_step * 1e-3) / 1e9) / peak},
             "cpu_baseline": cpu, "e2e": e2e, "e2e_wire": e2e_wire, "gpu_launches": int(launches), "clocks": clocks,
-            "check": {"ber_tsc0": ber, "detected": detected}, "gather": gather,
+            "check": {"ber_tsc0": ber, "detected": detected}, "gather": gather, "secondary": secondary,
         }
         emit(json.dumps(out))
     if world > 1:

@@ -474,6 +474,11 @@ class BtsDsp:
         self._ck(self.lib.btsdsp_trx_pull_dev(self.h, trx[0], _p(bursts), pitch, nframes, fn0, _p(valid), _p(dgram),
                                               dgram_pitch, _stream(stream)))
 
+    def trx_pull_streams_dev(self, trx, streams, stream_pitch, nframes, fn0, valid, dgram, dgram_pitch=160, stream=None):
+        """per-ARFCN continuous slot streams (device), stream_pitch samples apart; asynchronous on `stream`"""
+        self._ck(self.lib.btsdsp_trx_pull_streams_dev(self.h, trx[0], _p(streams), stream_pitch, nframes, fn0, _p(valid),
+                                                      _p(dgram), dgram_pitch, _stream(stream)))
+
     def trx_radio_host(self, trx, iq, fn0, swap_iq=False):
         """iq: (narfcn, nchunks*864, 2) int16.  Returns (valid[n], dgram[n,158]) laid out [frame][arfcn][tn]."""
         iq = np.ascontiguousarray(iq, np.int16)
