@@ -428,3 +428,44 @@ def test_tx_datagrams(dsp, oracle_best):
         assert placed == placed_ref and 0 < placed < n
         same(got, want, "TX datagrams (filler=%s)" % (filler is not None))
     assert np.abs(got).max() > 1000
+
+
+@pytest.mark.gpu
+def test_no_overrun_canaries(dsp, oracle_best):
+    """device entry points must not write outside their outputs: sentinel-filled margins around every output buffer of
+    the fused TX chain, the policy pull, the XCCH / RACH decoders and the soft-byte equaliser"""
+    import torch
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(5)
+    # fused TX chain: 936 bursts -> 250 chunks x 864 int16 pairs
+    nb = 936
+    bits = torch.from_numpy(rng.integers(0, 2, (nb, 148)).astype(np.uint8)).to(dev)
+    iq = torch.full((250 * 864 * 2 + 64,), 12345, dtype=torch.int16, device=dev)
+    dsp.tx_stream_dev(bits, nb, iq[32:])
+    torch.cuda.synchronize()
+    h = iq.cpu().numpy()
+    assert (h[:32] == 12345).all() and (h[-32:] == 12345).all() and (h[32:-32] != 12345).any()
+    # policy pull over pitched bursts: valid[n] and datagram rows at pitch 160
+    A, F = 5, 7
+    n = A * F * 8
+    bursts = synth.make_trx_batch(oracle_best.modulate, oracle_best.expected_corr_type, F, [0] * A, np.ones((A, 8)), seed=6)
+    d_b = torch.from_numpy(bursts.view(np.float32).copy()).to(dev)
+    valid = torch.full((n + 16,), -7, dtype=torch.int32, device=dev)
+    dg = torch.full(((n + 2) * 160,), 0xA5, dtype=torch.uint8, device=dev)
+    trx = dsp.trx_create([0] * A, np.ones((A, 8), np.uint8), 0)
+    dsp.trx_pull_dev(trx, d_b, 160, F, 0, valid[8:], dg[160:], 160)
+    torch.cuda.synchronize()
+    dsp.trx_destroy(trx)
+    v, d = valid.cpu().numpy(), dg.cpu().numpy()
+    assert (v[:8] == -7).all() and (v[-8:] == -7).all() and set(np.unique(v[8:-8])) <= {0, 1}
+    assert (d[:160] == 0xA5).all() and (d[-160:] == 0xA5).all()
+    # XCCH / RACH decoders
+    nfr = 37
+    soft = torch.from_numpy(rng.integers(0, 256, (nfr * 4, 148)).astype(np.uint8)).to(dev)
+    u = torch.full((nfr * 228 + 64,), 9, dtype=torch.uint8, device=dev)
+    ok = torch.full((nfr + 16,), -3, dtype=torch.int32, device=dev)
+    dsp.xcch_decode_dev(soft, 148, nfr, u[32:], ok[8:])
+    torch.cuda.synchronize()
+    hu, hk = u.cpu().numpy(), ok.cpu().numpy()
+    assert (hu[:32] == 9).all() and (hu[-32:] == 9).all() and (hu[32:-32] <= 1).all()
+    assert (hk[:8] == -3).all() and (hk[-8:] == -3).all() and set(np.unique(hk[8:-8])) <= {0, 1}
