@@ -137,6 +137,11 @@ int btsdsp_resample_rx_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, int has_hist
  * 0 for the SWLOOPBACK order.  iq must be 16-byte aligned; has_history: iq[-384..-1] (192 samples) are valid. */
 int btsdsp_resample_rx_i16_dev(btsdsp_ctx *ctx, const int16_t *iq, int swap_iq, int has_history, long long nchunks,
                                btsdsp_cf32 *out, void *stream);
+/* The same for nstreams radios in ONE launch: stream a at iq + 2*a*iq_pitch int16 (iq_pitch samples, a multiple of 4),
+ * its 585*nchunks outputs at out + a*out_pitch (a multiple of 2).  Every stream has the same nchunks / history flag. */
+int btsdsp_resample_rx_i16_streams_dev(btsdsp_ctx *ctx, const int16_t *iq, long long iq_pitch, int nstreams, int swap_iq,
+                                       int has_history, long long nchunks, btsdsp_cf32 *out, long long out_pitch,
+                                       void *stream);
 /* TX resampler (radioInterface.cpp:123-168 + USRPifyVector :74-89): nchunks chunks of 585 samples ->
  * 864 int16 {I,Q} pairs each, scaled by 13500 and truncated like the reference's (short) cast. */
 int btsdsp_resample_tx_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *in, int has_history, long long nchunks, int16_t *out,

@@ -54,6 +54,7 @@ _SIGS = {
     "btsdsp_resample_rx_dev": (_i, [_vp, _vp, _i, _ll, _vp, _vp]),
     "btsdsp_resample_tx_dev": (_i, [_vp, _vp, _i, _ll, _vp, _vp]),
     "btsdsp_resample_rx_i16_dev": (_i, [_vp, _vp, _i, _i, _ll, _vp, _vp]),
+    "btsdsp_resample_rx_i16_streams_dev": (_i, [_vp, _vp, _ll, _i, _i, _i, _ll, _vp, _ll, _vp]),
     "btsdsp_demod_normal_u8_dev": (_i, [_vp, _vp, _ll, _vp, _ll, _vp, _ll, _f, _f, _f, _vp, _vp, _vp, _vp, _i, _vp]),
     "btsdsp_rx_stream_wire_host": (_i, [_vp, _vp, _i, _ll, _vp, _ll, _f, _f, _f, _vp, _vp, _vp, _vp]),
     "btsdsp_demod_normal_dev": (_i, [_vp, _vp, _ll, _vp, _ll, _vp, _ll, _f, _f, _f, _vp, _vp, _vp, _vp, _i, _vp, _vp,
@@ -300,6 +301,11 @@ class BtsDsp:
     def resample_rx_i16_dev(self, iq, nchunks, out, swap_iq=False, has_history=False, stream=None):
         self._ck(self.lib.btsdsp_resample_rx_i16_dev(self.h, _p(iq), int(swap_iq), int(has_history), nchunks, _p(out),
                                                      _stream(stream)))
+
+    def resample_rx_i16_streams_dev(self, iq, iq_pitch, nstreams, nchunks, out, out_pitch, swap_iq=False, has_history=False,
+                                    stream=None):
+        self._ck(self.lib.btsdsp_resample_rx_i16_streams_dev(self.h, _p(iq), iq_pitch, nstreams, int(swap_iq), int(has_history),
+                                                             nchunks, _p(out), out_pitch, _stream(stream)))
 
     def demod_normal_u8_dev(self, bursts, pitch, tsc, n, flag, amp, toa, soft_u8, soft_pitch=148, lens=None, first=0,
                             detect_thr=3.0, gate_thr=-1.0, snr_thr=250.0, stream=None):

@@ -1068,15 +1068,15 @@ int btsdsp_trx_radio_host(btsdsp_ctx *ctx, btsdsp_trx *t, const int16_t *iq, lon
   int16_t *draw = (int16_t *)t->radio.p;
   cf *dres = (cf *)t->res.p;
   uint8_t *dio = (uint8_t *)t->io.p;
-  for (int a = 0; a < A; a++) {
-    int16_t *dst = draw + (size_t)a * raw_pitch * 2;
-    CK(cudaMemcpyAsync(dst + 192 * 2, iq + (size_t)a * iq_pitch * 2, (size_t)nchunks * 864 * 4, cudaMemcpyHostToDevice, st));
-    if (launch_resample_rx_i16(dst + 192 * 2, swap_iq, t->have_history ? 1 : 0, nchunks, dres + (size_t)a * res_pitch, st) < 0)
-      return fail(ctx, BTSDSP_EINVAL, "trx_radio: resampler rejected the staging pointers");
-    // the last 192 raw samples become the next call's history
-    CK(cudaMemcpyAsync(dst, dst + (size_t)nchunks * 864 * 2, 192 * 4, cudaMemcpyDeviceToDevice, st));
-  }
-  LAUNCHED("trx_radio resample", A);
+  // all radios' new samples behind their 192-sample histories, ONE resampler launch over all streams, then the last
+  // 192 raw samples of every stream become the next call's history
+  CK(cudaMemcpy2DAsync(draw + 192 * 2, (size_t)raw_pitch * 4, iq, (size_t)iq_pitch * 4, (size_t)nchunks * 864 * 4, (size_t)A,
+                       cudaMemcpyHostToDevice, st));
+  if (launch_resample_rx_i16_multi(draw + 192 * 2, raw_pitch, A, swap_iq, t->have_history ? 1 : 0, nchunks, dres, res_pitch, st) < 0)
+    return fail(ctx, BTSDSP_EINVAL, "trx_radio: resampler rejected the staging pointers");
+  CK(cudaMemcpy2DAsync(draw, (size_t)raw_pitch * 4, draw + (size_t)nchunks * 864 * 2, (size_t)raw_pitch * 4, 192 * 4, (size_t)A,
+                       cudaMemcpyDeviceToDevice, st));
+  LAUNCHED("trx_radio resample", 1);
   t->have_history = true;
   r = trx_pull_impl(ctx, t, (const btsdsp_cf32 *)dres, 0, res_pitch, nframes, fn0, (int32_t *)(dio + o_v), dio + o_d, 160, st);
   if (r != BTSDSP_OK) return r;
@@ -1267,6 +1267,16 @@ int btsdsp_energy_detect_52m(btsdsp_ctx *ctx, const btsdsp_cf32 *v, int n, unsig
   CK(cudaStreamSynchronize(st));
   *above = f;
   if (avg_pwr) *avg_pwr = a;
+  return BTSDSP_OK;
+}
+
+int btsdsp_resample_rx_i16_streams_dev(btsdsp_ctx *ctx, const int16_t *iq, long long iq_pitch, int nstreams, int swap_iq,
+                                       int has_history, long long nchunks, btsdsp_cf32 *out, long long out_pitch, void *stream) {
+  ARG(ctx && iq && out && nstreams > 0 && nchunks >= 0 && iq_pitch >= nchunks * 864 && out_pitch >= nchunks * 585);
+  DeviceGuard g(ctx->device);
+  if (launch_resample_rx_i16_multi(iq, iq_pitch, nstreams, swap_iq, has_history, nchunks, (cf *)out, out_pitch, (cudaStream_t)stream) < 0)
+    return fail(ctx, BTSDSP_EINVAL, "resample_rx_i16_streams: pointers must be 16-byte aligned, pitches multiples of 4 (iq) / 2 (out) samples");
+  LAUNCHED("resample_rx_i16_streams", nchunks > 0);
   return BTSDSP_OK;
 }
 

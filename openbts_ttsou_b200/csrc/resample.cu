@@ -146,16 +146,16 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
-// One tensor (TMA) copy brings in a whole super-tile.  The tensor map describes the raw stream as rows of 96 samples;
+// One tensor (TMA) copy brings in a whole super-tile.  The tensor map describes the raw streams as [stream][row][96 samples];
 // the box is ROWS x 98 samples for float input -- two samples wider than the tensor, so the copy itself lays the rows
 // down at the 98-sample pitch that keeps the compute warps' LDS.128 conflict-free (the two extra columns are
 // out-of-bounds and arrive as zeros) -- and ROWS x 96 int16 pairs for int16 input.  Rows before the start of a
 // history-less stream and past its end are out of bounds too and arrive as zeros, which is exactly the reference's
 // zero history / truncated right edge.  One thread issues it; completion is counted in bytes on the mbarrier.
-__device__ __forceinline__ void tma_load_tile(void *sdst, const CUtensorMap *tmap, int row0, unsigned long long *bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+__device__ __forceinline__ void tma_load_tile(void *sdst, const CUtensorMap *tmap, int row0, int stream, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
                    smem_u32(sdst)),
-               "l"(tmap), "r"(0), "r"(row0), "r"(smem_u32(bar))
+               "l"(tmap), "r"(0), "r"(row0), "r"(stream), "r"(smem_u32(bar))
                : "memory");
 }
 template <int ROWS, int NTHREADS>
@@ -186,7 +186,8 @@ __device__ long long g_rx_cta[256][4];
 #endif
 template <bool I16, int T>
 __global__ void __launch_bounds__(32 * kRxV3Parts * T + 32, 1) k_resample_rx_v3(const __grid_constant__ CUtensorMap tmap, int row_bias, int swap_iq,
-                                                                             long long nperiods, cf *__restrict__ out) {
+                                                                             long long nperiods, cf *__restrict__ out, int nstreams,
+                                                                             long long out_pitch) {
   using C = RxV3<I16, T>;
   constexpr int NW = kRxV3Parts * T, NC = 32 * NW, R = kRxV3Ring;        // compute warps / threads; warp NW is the producer
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -200,7 +201,8 @@ __global__ void __launch_bounds__(32 * kRxV3Parts * T + 32, 1) k_resample_rx_v3(
   __shared__ __align__(16) float s_taps[kRxP * 16];
   for (int i = threadIdx.x; i < kRxP * 16; i += blockDim.x) s_taps[i] = c_rx_poly[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long ntiles = (nperiods + C::kPeriods - 1) / C::kPeriods;
+  // nstreams independent streams of nperiods periods each; tile t = super-tile t % tps of stream t / tps
+  const long long tps = (nperiods + C::kPeriods - 1) / C::kPeriods, ntiles = tps * nstreams;
   const long long first = blockIdx.x, stride = gridDim.x;
   if (threadIdx.x == 0) {
     for (int i = 0; i < R; i++) {
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(32 * kRxV3Parts * T + 32, 1) k_resample_rx_v3(
         // sample (G, r, k) sits at 96*l + ix_r - k - 96 from the tile origin: the tile starts one row before period G0
         mbar_expect_tx(&full[b], C::kTileBytes);
         tma_load_tile(I16 ? (void *)(stage + b * C::kStage) : (void *)(xbuf + b * C::kInSlot), &tmap,
-                      (int)(tile * C::kPeriods) - 1 + row_bias, &full[b]);
+                      (int)((tile % tps) * C::kPeriods) - 1 + row_bias, (int)(tile / tps), &full[b]);
         RX_TRACE(1, it, 2);
         if (++b == R) { b = 0; use++; }
       }
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(32 * kRxV3Parts * T + 32, 1) k_resample_rx_v3(
   if (threadIdx.x == 0) g_rx_cta[blockIdx.x][0] = clock64();
 #endif
   for (long long tile = first; tile < ntiles; tile += stride, it++) {
-    const long long G0 = tile * C::kPeriods;
+    const long long G0 = (tile % tps) * C::kPeriods;
     cf *xt = xbuf, *ot = obuf;
     RX_TRACE(0, it, 0);
     if (threadIdx.x == 0 && store_pending) bulk_store_wait_read();       // the single output block has drained
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(32 * kRxV3Parts * T + 32, 1) k_resample_rx_v3(
     const long long nper = nperiods - G0 < C::kPeriods ? nperiods - G0 : C::kPeriods;
     // the 32T x 65 outputs are contiguous in shared and global memory: one bulk copy, issued by one thread,
     // that drains while the next step waits for its input
-    cf *og = out + G0 * kRxP;
+    cf *og = out + (tile / tps) * out_pitch + G0 * kRxP;
     fence_async_smem();
     compute_warps_sync<NC>();                                            // all outputs written; all reads of xt done
     RX_TRACE(0, it, 4);
@@ -311,18 +313,22 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode_tiled = nullptr;
 template <bool I16, int T>
-static int rxv3_make_map(CUtensorMap *map, const void *in, int has_history, long long nchunks) {
+static int rxv3_make_map(CUtensorMap *map, const void *in, int has_history, long long nchunks, int nstreams = 1,
+                         long long stream_pitch = 0) {
   using C = RxV3<I16, T>;
   if (!g_encode_tiled) return -1;
   const size_t sample = I16 ? 4 : 8;
   const char *base = reinterpret_cast<const char *>(in) - (has_history ? 192 * sample : 0);
   const cuuint64_t rows = (cuuint64_t)nchunks * 9 + (has_history ? 2 : 0);
   // float: 32-bit elements, 192 per row, box 196 wide (= 98 samples); int16: one 32-bit element per I/Q pair
-  const cuuint64_t gdim[2] = {I16 ? 96u : 192u, rows};
-  const cuuint64_t gstride[1] = {(cuuint64_t)(96 * sample)};
-  const cuuint32_t box[2] = {I16 ? 96u : 2u * kRxRowPitch, (cuuint32_t)C::kRows};
-  const cuuint32_t estride[2] = {1, 1};
-  const CUresult r = g_encode_tiled(map, I16 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+  // third dimension: the streams, stream_pitch samples apart (one stream: any pitch that keeps the stride legal)
+  const cuuint64_t spitch = nstreams > 1 ? (cuuint64_t)stream_pitch * sample : rows * 96 * sample;
+  if (spitch % 16) return -1;
+  const cuuint64_t gdim[3] = {I16 ? 96u : 192u, rows, (cuuint64_t)nstreams};
+  const cuuint64_t gstride[2] = {(cuuint64_t)(96 * sample), spitch};
+  const cuuint32_t box[3] = {I16 ? 96u : 2u * kRxRowPitch, (cuuint32_t)C::kRows, 1};
+  const cuuint32_t estride[3] = {1, 1, 1};
+  const CUresult r = g_encode_tiled(map, I16 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                                     const_cast<char *>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? (has_history ? 2 : 0) : -1;
@@ -336,7 +342,7 @@ void launch_resample_rx(const DevTables *T, const cf *in, int has_history, long 
   if (bias >= 0) {
     using C = RxV3<false, kRxV3TilesF32>;
     const long long nperiods = nchunks * 9, ntiles = (nperiods + C::kPeriods - 1) / C::kPeriods;
-    k_resample_rx_v3<false, kRxV3TilesF32><<<rxv3_grid(ntiles), C::kThreads, C::kSmem, st>>>(map, bias, 0, nperiods, out);
+    k_resample_rx_v3<false, kRxV3TilesF32><<<rxv3_grid(ntiles), C::kThreads, C::kSmem, st>>>(map, bias, 0, nperiods, out, 1, 0);
   } else {
     const unsigned grid = (unsigned)(nchunks < 148 * 32 ? nchunks : 148 * 32);
     k_resample_rx<<<grid, 256, 0, st>>>(T, in, has_history, nchunks, out);
@@ -351,7 +357,22 @@ int launch_resample_rx_i16(const int16_t *in, int swap_iq, int has_history, long
   const int bias = rxv3_make_map<true, kRxV3TilesI16>(&map, in, has_history, nchunks);
   if (bias < 0) return -1;
   const long long nperiods = nchunks * 9, ntiles = (nperiods + C::kPeriods - 1) / C::kPeriods;
-  k_resample_rx_v3<true, kRxV3TilesI16><<<rxv3_grid(ntiles), C::kThreads, C::kSmem, st>>>(map, bias, swap_iq, nperiods, out);
+  k_resample_rx_v3<true, kRxV3TilesI16><<<rxv3_grid(ntiles), C::kThreads, C::kSmem, st>>>(map, bias, swap_iq, nperiods, out, 1, 0);
+  return 1;
+}
+// nstreams radios at once: stream a = in + 2*a*in_pitch int16, its outputs at out + a*out_pitch samples
+int launch_resample_rx_i16_multi(const int16_t *in, long long in_pitch, int nstreams, int swap_iq, int has_history,
+                                 long long nchunks, cf *out, long long out_pitch, cudaStream_t st) {
+  if (nchunks <= 0 || nstreams <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return -1;
+  if ((in_pitch * 4) % 16 || (out_pitch * 8) % 16) return -1;
+  using C = RxV3<true, kRxV3TilesI16>;
+  alignas(64) CUtensorMap map;
+  const int bias = rxv3_make_map<true, kRxV3TilesI16>(&map, in, has_history, nchunks, nstreams, in_pitch);
+  if (bias < 0) return -1;
+  const long long nperiods = nchunks * 9, ntiles = (nperiods + C::kPeriods - 1) / C::kPeriods * nstreams;
+  k_resample_rx_v3<true, kRxV3TilesI16><<<rxv3_grid(ntiles), C::kThreads, C::kSmem, st>>>(map, bias, swap_iq, nperiods, out, nstreams,
+                                                                                        out_pitch);
   return 1;
 }
 // ------------------------------------------------------------------------------------------------

@@ -396,6 +396,19 @@ def test_resampler_ragged_sizes(dsp, oracle_best):
             got = res.cpu().numpy()
             same(got[:nch * 585 * 2].view(np.complex64), want[skip * 585:(skip + nch) * 585], "int16 nch=%d skip=%d" % (nch, skip))
             assert (got[nch * 585 * 2:] == 7.5).all()
+    # several radios in one launch == one launch per radio (streams 5 chunks of slack apart, with and without history)
+    S, nch = 7, 37
+    pitch_in, pitch_out = (nch + 5) * 864, (nch + 5) * 585
+    for hist in (False, True):
+        base = 864 if hist else 0                     # with history, each stream starts one chunk into its slab
+        many = torch.full((S * pitch_out * 2,), 7.5, device=dev)
+        dsp.resample_rx_i16_streams_dev(d_iq[base:], pitch_in, S, nch, many, pitch_out, has_history=hist)
+        got = many.cpu().numpy().reshape(S, pitch_out * 2)
+        for a in range(S):
+            one = torch.zeros(nch * 585 * 2, device=dev)
+            dsp.resample_rx_i16_dev(d_iq[base + a * pitch_in:], nch, one, has_history=hist)
+            same(got[a, :nch * 585 * 2], one.cpu().numpy(), "multi-stream %d hist=%s" % (a, hist))
+            assert (got[a, nch * 585 * 2:] == 7.5).all()
     # an 8-byte-aligned (not 16) input pointer takes the one-CTA-per-chunk kernel: same results
     shifted = torch.zeros(40 * 864 * 2 + 2, device=dev)
     shifted[2:] = d_raw[:40 * 864 * 2]
