@@ -455,7 +455,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_equalize_fast(const DevTables *_
 #pragma unroll
   for (int r = 0; r < 4; r++) ycur[r] = mk(0.0F, 0.0F);
 
-  for (int m0 = kEqStart; m0 < nmax; m0 += 4) {
+  // Only the outputs the caller keeps are computed: the recursion is causal (soft bit m depends on decisions < m only),
+  // so stopping after the last stored symbol leaves every stored value unchanged.  The reference's caller keeps the
+  // first gSlotLen = 148 of the 156/157 (Transceiver.cpp:668); a wider soft_pitch gets them all.
+  const int mend = U8 ? (nmax < 148 ? nmax : 148) : (nmax < soft_pitch ? nmax : soft_pitch);
+  for (int m0 = kEqStart; m0 < mend; m0 += 4) {
     if (!staged || eq_needs_restage(base, m0, io_min, io_max)) {
       // ---- roll the tile: rows [base, base + kEqRows) of every detected burst (zeros outside the burst) arrive
       //      by cp.async, then each lane scales its column by 1/amplitude (scaleVector, Transceiver.cpp:391)
