@@ -5,6 +5,7 @@ errors and quantised to the RX datagram's soft bytes."""
 import numpy as np
 import pytest
 
+import synth
 from conftest import golden
 from emu import Emu
 
@@ -120,4 +121,33 @@ def test_rach_decode_gpu_matches_reference(oracle_best, dsp):
     want = oracle_best.rach_decode(soft)
     got = dsp.rach_decode_host(soft)
     for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+
+
+@pytest.mark.gpu
+def test_rach_chain_end_to_end(oracle_best, dsp):
+    """RA / BSIC -> reference RACH encoder -> access burst -> GMSK -> delay, noise -> detectRACHBurst + demodulateBurst
+    (GPU) -> datagram soft bytes -> RACH block decoder (GPU): every burst detected, tail clean, BSIC and RA recovered;
+    and the decoder agrees with the reference classes on the same bytes"""
+    if oracle_best.kind != "ref":
+        pytest.skip("needs the reference encoder")
+    rng = np.random.default_rng(12)
+    n = 512
+    ra = rng.integers(0, 256, n).astype(np.uint8)
+    bsic = rng.integers(0, 64, n).astype(np.uint8)
+    coded = oracle_best.rach_encode(ra, bsic)
+    bursts = np.zeros((n, 160), np.complex64)
+    lens = np.where(np.arange(n) % 4 == 0, 157, 156).astype(np.int32)
+    for i in range(n):
+        b = synth.access_burst_bits(rng)
+        b[49:85] = coded[i]
+        x = dsp.modulate(b, int(lens[i]) - 88)
+        bursts[i, :lens[i]] = synth.impair(rng, x, amp=1500.0, delay=rng.integers(0, 30) + rng.random(), snr_db=18.0)
+    r = dsp.rach_host(bursts, lens)
+    assert r["flag"].all()
+    soft_u8 = np.zeros((n, 148), np.uint8)
+    soft_u8[:] = np.floor(r["soft"][:, :148].astype(np.float64) * 255.0 + 0.5).astype(np.uint8)   # Transceiver.cpp:669
+    u, tail, b2, ra2 = dsp.rach_decode_host(soft_u8)
+    assert (tail == 0).all() and np.array_equal(b2, bsic) and np.array_equal(ra2, ra)
+    for g, w in zip((u, tail, b2, ra2), oracle_best.rach_decode(soft_u8)):
         assert np.array_equal(g, w)
