@@ -151,3 +151,38 @@ def test_rach_chain_end_to_end(oracle_best, dsp):
     assert (tail == 0).all() and np.array_equal(b2, bsic) and np.array_equal(ra2, ra)
     for g, w in zip((u, tail, b2, ra2), oracle_best.rach_decode(soft_u8)):
         assert np.array_equal(g, w)
+
+
+@pytest.mark.gpu
+def test_xcch_chain_end_to_end(oracle_best, dsp):
+    """L2 frames -> reference XCCH encoder -> four normal bursts each -> GMSK -> 2-tap channel, delay, noise -> fused
+    detect / DFE / equalise with soft-byte output (GPU) -> XCCH block decoder (GPU): every frame passes the Fire-code
+    check with its payload intact"""
+    if oracle_best.kind != "ref":
+        pytest.skip("needs the reference encoder")
+    import torch
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(31)
+    nfr = 128
+    d = rng.integers(0, 2, (nfr, 184)).astype(np.uint8)
+    e = oracle_best.xcch_encode(d)                                   # (nfr*4, 114)
+    n = nfr * 4
+    bursts = np.zeros((n, 160), np.complex64)
+    lens = np.where(np.arange(n) % 4 == 0, 157, 156).astype(np.int32)
+    tsc = np.full(n, 2, np.uint8)
+    for i in range(n):
+        b = synth.normal_burst_bits(rng, 2)
+        b[3:60] = e[i, :57]
+        b[88:145] = e[i, 57:]
+        x = dsp.modulate(b, int(lens[i]) - 148)
+        bursts[i, :lens[i]] = synth.impair(rng, x, amp=2000.0, delay=rng.uniform(0, 2), chan2=0.35 * np.exp(1j * i), snr_db=16.0)
+    d_b = torch.from_numpy(bursts.view(np.float32).copy()).to(dev)
+    d_l = torch.from_numpy(lens).to(dev); d_t = torch.from_numpy(tsc).to(dev)
+    flag = torch.zeros(n, dtype=torch.int32, device=dev); amp = torch.zeros(n * 2, device=dev); toa = torch.zeros(n, device=dev)
+    u8 = torch.zeros((n, 148), dtype=torch.uint8, device=dev)
+    dsp.demod_normal_u8_dev(d_b, 160, d_t, n, flag, amp, toa, u8, 148, lens=d_l)
+    fu = torch.zeros(nfr * 228, dtype=torch.uint8, device=dev); fok = torch.zeros(nfr, dtype=torch.int32, device=dev)
+    dsp.xcch_decode_dev(u8, 148, nfr, fu, fok)
+    torch.cuda.synchronize()
+    assert bool(flag.all()) and bool(fok.all())
+    assert np.array_equal(fu.cpu().numpy().reshape(nfr, 228)[:, :184], d)
