@@ -272,7 +272,11 @@ constexpr int kDetRows = 45;          // burst samples 56..91 in rows 9..44; the
 constexpr int kDetWin = 9;           // (output n only needs window samples >= n - 8, so row n is dead when c[n] is stored)
 constexpr size_t kDetTileBytes = (size_t)kDetRows * kTileStride * sizeof(cf);
 constexpr size_t kEqTileBytes = (size_t)kEqRows * kTileStride * sizeof(cf);
-template <int WARPS> constexpr size_t detect_smem() { return kGridBytes + WARPS * kDetTileBytes; }
+// WARPS == 1 (what the launchers use) reads the sinc grid from global memory (43 KB, L1/L2-resident): 12 KB of shared
+// memory per CTA lets 16 one-warp CTAs share an SM (registers then bind), 0.47 ms per 800 280 bursts.  WARPS > 1 keeps
+// a shared-memory copy of the grid per CTA (15 warps, 223 KB): 0.58 ms, and its 43 KB copy dominated small launches.
+template <int WARPS> __host__ __device__ constexpr size_t detect_grid_bytes() { return WARPS > 1 ? kGridBytes : 0; }
+template <int WARPS> constexpr size_t detect_smem() { return detect_grid_bytes<WARPS>() + WARPS * kDetTileBytes; }
 template <int WARPS> constexpr size_t equalize_smem() { return WARPS * kEqTileBytes; }
 
 // POLICY = pass 1 of the caller-policy pipeline (trx_policy.cuh): the energy is measured but not judged, the analysis
@@ -287,9 +291,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_detect_design(const DevTables *_
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float *grid = reinterpret_cast<float *>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  cf *A = reinterpret_cast<cf *>(smem_raw + kGridBytes) + (size_t)warp * kDetRows * kTileStride;
-  for (int i = threadIdx.x; i < kSincGrid * kGridPitch; i += WARPS * 32) grid[i] = T->sinc_grid[i / kGridPitch][i % kGridPitch];
-  __syncthreads();
+  cf *A = reinterpret_cast<cf *>(smem_raw + detect_grid_bytes<WARPS>()) + (size_t)warp * kDetRows * kTileStride;
+  if (WARPS > 1) {
+    for (int i = threadIdx.x; i < kSincGrid * kGridPitch; i += WARPS * 32) grid[i] = T->sinc_grid[i / kGridPitch][i % kGridPitch];
+    __syncthreads();
+  }
   const long long w0 = ((long long)blockIdx.x * WARPS + warp) * 32;
   if (w0 >= n) return;
   const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
@@ -339,7 +345,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_detect_design(const DevTables *_
   if (lane >= nv) return;
 
   const View<kTileStride> a{A + lane};
-  const Grid g{grid, kGridPitch};
+  const Grid g = WARPS > 1 ? Grid{grid, kGridPitch} : Grid{&T->sinc_grid[0][0], 24};
   bool ok = false;
   cf amp = mk(0.0F, 0.0F), ia = mk(0.0F, 0.0F), chan[6], w[7], fb[5];
   float toa = 0.0F, off = 0.0F;
@@ -515,11 +521,8 @@ int launch_demod_normal(const DevTables *T, BurstSrc src, const uint8_t *tsc, lo
   if (n <= 0) return 0;
   const long long nwarps = (n + 31) / 32;
   EqParams *eqp = (out.soft || out.soft_u8) ? reinterpret_cast<EqParams *>(scratch) : nullptr;
-  if (nwarps >= 148 * 15)
-    k_detect_design<15><<<(unsigned)((nwarps + 14) / 15), 480, detect_smem<15>(), st>>>(T, src, tsc, n, detect_thr, gate_thr,
-                                                                                 snr_thr, out, eqp);
-  else
-    k_detect_design<1><<<(unsigned)nwarps, 32, detect_smem<1>(), st>>>(T, src, tsc, n, detect_thr, gate_thr, snr_thr, out, eqp);
+  // one-warp CTAs, 12 KB of shared memory and 124 registers each: 16 resident per SM
+  k_detect_design<1><<<(unsigned)nwarps, 32, detect_smem<1>(), st>>>(T, src, tsc, n, detect_thr, gate_thr, snr_thr, out, eqp);
   if (between) cudaEventRecord(between, st);
   if (!out.soft && !out.soft_u8) return 1;
   // one-warp CTAs: 14.8 KB of shared memory and 128 registers per thread each, 14-15 resident per SM
@@ -911,11 +914,7 @@ void launch_energy_detect_52m(const cf *v, int n, unsigned win, float thr, float
 
 int configure_kernels() {
   cudaError_t e;
-  e = cudaFuncSetAttribute(k_detect_design<15, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<15>());
-  if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_detect_design<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<1>());
-  if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(k_detect_design<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<15>());
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_detect_design<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<1>());
   if (e != cudaSuccess) return (int)e;

@@ -184,11 +184,7 @@ int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, i
   const long long nwarps = (n + 31) / 32;
   NormalOut none{};
   // pass 1
-  if (nwarps >= 148 * 15)
-    k_detect_design<15, true><<<(unsigned)((nwarps + 14) / 15), 480, detect_smem<15>(), stream>>>(T, src, tsc, n, 3.0F, 0.0F, 0.0F, none,
-                                                                                             nullptr, kind, s.det);
-  else
-    k_detect_design<1, true><<<(unsigned)nwarps, 32, detect_smem<1>(), stream>>>(T, src, tsc, n, 3.0F, 0.0F, 0.0F, none, nullptr, kind, s.det);
+  k_detect_design<1, true><<<(unsigned)nwarps, 32, detect_smem<1>(), stream>>>(T, src, tsc, n, 3.0F, 0.0F, 0.0F, none, nullptr, kind, s.det);
   launches++;
   BurstSrc rsrc = src;
   rsrc.gather = rach_idx;
