@@ -244,8 +244,8 @@ void launch_modulate_impulse(const DevTables *T, const uint8_t *bits, int nbits,
 // (reference Transceiver.cpp:298-396 with estimateChannel == true for every burst); sps == 1.
 // One burst per lane.  Two kernels so that each runs at the occupancy its working set allows:
 //   k_detect_design : stages only the 36-sample midamble window (the 20-sample energy-gate window first, when
-//                     gated), writes the correlation in place (45 tile rows = 12 KB per warp, 15 warps per CTA share
-//                     one shared-memory copy of the sinc grid), and leaves {1/amp, TOA - offset, w[7], b[5]} per burst
+//                     gated), writes the correlation in place (45 tile rows = 12 KB per one-warp CTA, 16 per SM; the
+//                     sinc grid is read from global memory), and leaves {1/amp, TOA - offset, w[7], b[5]} per burst
 //                     in an EqParams record;
 //   k_equalize_fast : streams the detected bursts, scaled by 1/amp on the way in, through a ROLLING 56-row tile
 //                     (14.8 KB per warp, re-staged every ~31 rows; 14-15 warps per SM) under the pipelined equaliser
