@@ -660,7 +660,7 @@ int btsdsp_rach_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch,
   DeviceGuard g(ctx->device);
   if (ctx->sps != 1) GROW(B_SCRATCH, (size_t)n * scratch_per_burst(ctx->sps) * sizeof(cf));
   NormalOut o = {flag, (cf *)amp, toa, nullptr, nullptr, nullptr, nullptr, soft, soft_pitch};
-  GROW(B_EQP, demod_scratch_bytes(n));
+  GROW(B_EQP, rach_scratch_bytes(n));
   const int nl = launch_rach(ctx->T, make_src(bursts, pitch, lens, first, ctx->sps), n, detect_thr, soft != nullptr, o,
                              dbuf<cf>(ctx, B_SCRATCH), 0, (cudaStream_t)stream, dbuf<void>(ctx, B_EQP));
   LAUNCHED("rach", nl);

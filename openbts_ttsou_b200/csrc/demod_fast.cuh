@@ -355,51 +355,62 @@ BTS_HD bool eq_needs_restage(int base, int m0, int io_min, int io_max) {
 
 // ---- access bursts (sps == 1) -----------------------------------------------------------------------------------
 // correlate(burst, RACH sequence, NO_DELAY) (:867-869): c[n] = sum_{k=0..40} r[n+20-k] * tap[k], tap[k] =
-// conj(seq[40-k]), burst indices outside [0, N) not part of the vector.  Written IN PLACE: the burst sits in tile
-// rows 21..21+N-1 (rows 0..20 zero), c[n] goes to row n -- r[n-21] is dead by the time c[n] is stored.
-constexpr int kRachOff = 21;
-constexpr int kRachRows = 157 + kRachOff;                 // 178 rows = 47 KB per warp
+// conj(seq[40-k]), burst indices outside [0, N) not part of the vector; then detectRACHBurst (:860-914).
+// (Round 1 wrote the correlation in place over a full-burst tile: 47 KB per warp, 4 warps per SM.)
+// The warp walks the correlation in blocks of four lags over a tile of kRachRollRows burst rows (zero outside the burst, so every
+// block runs unchecked: a zero sample adds +-0 where the reference skips the tap), keeps the running first-maximum
+// of |c|^2, and parks the correlation in a global scratch row per burst (one full 32-byte sector per lane and block).
+// Afterwards each lane brings the 26 lags around its own maximum back into shared memory for the early/late search and
+// reads the 51 valley lags straight from its scratch row.  21 KB per warp: 10 warps per SM.
+constexpr int kRachRollRows = 80;                         // block n0 reads burst rows n0-20 .. n0+23
+constexpr int kRachWin = 26;                              // lags imax-12 .. imax+13 cover every read of the peak search
+BTS_HD bool rach_needs_restage(int base, int n0) { return n0 + 23 >= base + kRachRollRows; }
 
-template <int S, bool CHECKED>
-BTS_HD void rach_corr4(View<S> t, int N, const cf *__restrict__ tap, int n0) {
-  cf acc[4];
+template <int S>
+BTS_HD void rach_corr4_roll(View<S> tile, int base, const cf *__restrict__ tap, int n0, cf acc[4]) {
 #pragma unroll
   for (int r = 0; r < 4; r++) acc[r] = mk(0.0F, 0.0F);
+  const View<S> t = tile.at(n0 + 23 - base);
 #pragma unroll
   for (int j = 0; j < 44; j++) {
-    const int idx = n0 + 23 - j;                          // burst index, descending == ascending tap index
-    cf v;
-    if (CHECKED) v = ((unsigned)idx < (unsigned)N) ? t.ld(idx + kRachOff) : mk(0.0F, 0.0F);
-    else v = t.ld(idx + kRachOff);
+    const cf v = t.ld(-j);                                // burst row n0 + 23 - j
     const cf vs = cswapneg(v);
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-      const int k = j + r - 3;                            // = (n0 + r + 20) - idx
+      const int k = j + r - 3;                            // = (n0 + r + 20) - row
       if (k >= 0 && k <= 40) acc[r] = cmac_tap(acc[r], v, vs, tap[k]);
     }
   }
-#pragma unroll
-  for (int r = 0; r < 4; r++) if (n0 + r < N) t.st(n0 + r, acc[r]);
 }
-
-// detectRACHBurst (:860-914) with the correlation in place; `all_interior(n0)` tells whether every lane of the warp
-// can run block n0 unchecked (the kernel votes, the host emulation answers per lane)
-template <int S, class Vote>
-BTS_HD bool detect_rach_fast(Grid grid, const DevTables *__restrict__ T, View<S> t, int N, int nmax, float thr,
-                             const cf *__restrict__ tap, Vote all_interior, cf *amplitude, float *TOA) {
-  for (int n0 = 0; n0 < nmax; n0 += 4) {
-    // rows n0-20 .. n0+23 all inside the burst?  (rows below 0 read the zeroed pad rows, which is fine unchecked)
-    if (all_interior(n0 + 23 < N)) rach_corr4<S, false>(t, N, tap, n0);
-    else rach_corr4<S, true>(t, N, tap, n0);
+// peakDetect's early/late search (:684-700) around a maximum already found at lag imax; c must serve lags imax-12..imax+13
+template <int S>
+BTS_HD cf peak_refine_fast(Grid grid, View<S> c, int n, int imax, float *peakIndex) {
+  int e512 = (imax - 1) * kSincGrid;
+  float s[21];
+  for (int step = kSincGrid / 2; step >= 1; step >>= 1) {
+    const int I = e512 >> 9, j = e512 & (kSincGrid - 1);
+    load_grid_row(grid, j, s);
+    const float e = cnorm2(interp21<S>(s, c, n, I)), l = cnorm2(interp21<S>(s, c, n, I + 2));
+    if (e < l) e512 += step;
+    else if (e > l) e512 -= step;
+    else break;
   }
+  load_grid_row(grid, e512 & (kSincGrid - 1), s);
+  *peakIndex = BTS_ADD((float)e512 * (1.0F / kSincGrid), 1.0F);
+  return interp21<S>(s, c, n, (e512 >> 9) + 1);
+}
+// everything after the correlation sweep: win = the lane's window column (row k = lag imax-12+k), cs = its scratch row
+template <int S>
+BTS_HD bool rach_finish(Grid grid, const DevTables *__restrict__ T, View<S> win, const cf *__restrict__ cs, int N, int imax,
+                        float thr, cf *amplitude, float *TOA) {
   float toa;
-  const cf pk = peak_detect_fast<S>(grid, t, N, &toa);
+  const cf pk = peak_refine_fast<S>(grid, win.at(-(imax - 12)), N, imax, &toa);
   if ((toa < 0.0F) || (toa > (float)N)) { *amplitude = mk(0.0F, 0.0F); *TOA = toa; return false; }
   const int p = (int)rintf(toa);
   float valley = 0.0F, numSamples = 0.0F;
   for (int i = 57; i <= 107; i++) {
     if (p + i >= N) break;
-    valley = BTS_ADD(valley, cnorm2(t.ld(p + i)));
+    valley = BTS_ADD(valley, cnorm2(cs[p + i]));
     numSamples = numSamples + 1.0F;
   }
   if (numSamples < 2.0F) { *amplitude = mk(0.0F, 0.0F); *TOA = toa; return false; }

@@ -512,6 +512,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_equalize_fast(const DevTables *_
 }
 
 size_t demod_scratch_bytes(long long n) { return (size_t)n * sizeof(EqParams); }
+// access bursts: the records plus a 160-sample correlation scratch row per burst (128-byte aligned behind the records)
+size_t rach_scratch_bytes(long long n) { return (((size_t)n * sizeof(EqParams) + 127) & ~(size_t)127) + (size_t)n * 160 * sizeof(cf); }
 
 // The two launches of the normal-burst receive path; `between` (optional) is recorded between them so a caller
 // can time the kernels separately.
@@ -591,44 +593,81 @@ int launch_analyze(const DevTables *T, BurstSrc src, const uint8_t *tsc, long lo
 // __constant__ memory) then k_slicer_fast (demodulateBurst as a stream over the rolling tile).
 // ------------------------------------------------------------------------------------------------
 __constant__ cf c_rach_taps[41];                  // conj(rach_seq[40-k]) (:474-503)
-constexpr size_t kRachTileBytes = (size_t)kRachRows * kTileStride * sizeof(cf);
 
-struct WarpVote {
-  unsigned mask;
-  __device__ __forceinline__ bool operator()(bool x) const { return __all_sync(mask, x) != 0; }
-};
 
+constexpr size_t kRachRollBytes = (size_t)kRachRollRows * kTileStride * sizeof(cf);
+constexpr int kRachScratchPitch = 160;                  // complex samples of correlation scratch per burst
+
+// detectRACHBurst over a rolling 80-row tile (demod_fast.cuh: rach_corr4_roll / rach_finish); cs = n x 160 complex scratch
 __global__ void __launch_bounds__(32) k_rach_detect(const DevTables *__restrict__ T, BurstSrc src, long long n,
-                                                    float detect_thr, NormalOut out, EqParams *__restrict__ eqp) {
+                                                    float detect_thr, NormalOut out, EqParams *__restrict__ eqp,
+                                                    cf *__restrict__ cs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf *A = reinterpret_cast<cf *>(smem_raw);
   const int lane = threadIdx.x;
   const long long w0 = (long long)blockIdx.x * 32;
   const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
   const long long i = w0 + lane;
+  const bool live = lane < nv;
   long long start = 0;
   int len = 0;
-  if (lane < nv) { burst_loc(src, i, &start, &len); if (len > 157) len = 157; }
-  // ---- staging: zero pad rows 0..20, bursts (raw) in rows 21.., zeros past each burst's end; cp.async, all in flight
-  for (int r = lane; r < kRachOff * kTileStride; r += 32) A[r] = mk(0.0F, 0.0F);
-  for (int j = 0; j < nv; j++) {
-    const long long sj = __shfl_sync(0xffffffffu, start, j);
-    const int lj = __shfl_sync(0xffffffffu, len, j);
+  if (live) { burst_loc(src, i, &start, &len); if (len > 157) len = 157; }
+  const int nmax = __reduce_max_sync(0xffffffffu, len);
+  cf *row = cs + (live ? i : w0) * kRachScratchPitch;
+  int imax = -1, base = 0;
+  float maxv = 0.0F;
+  bool staged = false;
+  for (int n0 = 0; n0 < nmax; n0 += 4) {
+    if (!staged || rach_needs_restage(base, n0)) {
+      // ---- roll the tile: burst rows [n0 - 20, +80) of every burst, zeros outside the burst; cp.async, all in flight
+      base = n0 - 20;
+      staged = true;
+      __syncwarp();
+      for (int j = 0; j < nv; j++) {
+        const long long sj = __shfl_sync(0xffffffffu, start, j);
+        const int lj = __shfl_sync(0xffffffffu, len, j);
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
-      const int r = lane + 32 * k;
-      if (r < 157) cp_async8z(A + (kRachOff + r) * kTileStride + j, src.base + sj + (r < lj ? r : 0), r < lj);
+        for (int k = 0; k < 3; k++) {
+          const int tr = lane + 32 * k, r = base + tr;
+          if (tr < kRachRollRows) {
+            const bool valid = (unsigned)r < (unsigned)lj;
+            cp_async8z(A + tr * kTileStride + j, src.base + sj + (valid ? r : 0), valid);
+          }
+        }
+      }
+      cp_async_wait_all();
+      __syncwarp();
+    }
+    if (live) {
+      cf acc[4];
+      rach_corr4_roll<kTileStride>(View<kTileStride>{A + lane}, base, c_rach_taps, n0, acc);
+      if (n0 + 3 < len) {                                   // one full 32-byte sector per lane
+        float4 *q = reinterpret_cast<float4 *>(row + n0);
+        q[0] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+        q[1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; r++) if (n0 + r < len) row[n0 + r] = acc[r];
+      }
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        if (n0 + r < len) {                                 // peakDetect's first strict maximum (:673-681)
+          const float p = cnorm2(acc[r]);
+          if (p > maxv) { maxv = p; imax = n0 + r; }
+        }
+      }
     }
   }
-  cp_async_wait_all();
-  __syncwarp();
-  const unsigned active = __ballot_sync(0xffffffffu, lane < nv);
-  if (lane >= nv) return;
-  const int nmax = __reduce_max_sync(active, len);
+  __syncwarp();                                             // every lane is done with the burst rows
+  if (!live) return;
+  for (int k = 0; k < kRachWin; k++) {                      // the 26 lags around the lane's own maximum, back from scratch
+    const int idx = imax - 12 + k;
+    A[k * kTileStride + lane] = ((unsigned)idx < (unsigned)len) ? row[idx] : mk(0.0F, 0.0F);
+  }
   cf amp = mk(0.0F, 0.0F);
   float toa = 0.0F;
-  const bool ok = detect_rach_fast<kTileStride>(Grid{&T->sinc_grid[0][0], 24}, T, View<kTileStride>{A + lane}, len, nmax,
-                                                detect_thr, c_rach_taps, WarpVote{active}, &amp, &toa);
+  const bool ok = rach_finish<kTileStride>(Grid{&T->sinc_grid[0][0], 24}, T, View<kTileStride>{A + lane}, row, len, imax,
+                                           detect_thr, &amp, &toa);
   if (out.flag) out.flag[i] = ok ? 1 : 0;
   if (out.amp) out.amp[i] = amp;
   if (out.toa) out.toa[i] = toa;
@@ -764,7 +803,8 @@ int launch_rach(const DevTables *T, BurstSrc src, long long n, float detect_thr,
   const unsigned grid = (unsigned)((n + 31) / 32);
   if (src.sps == 1 && !force_generic && eq_scratch) {
     EqParams *eqp = reinterpret_cast<EqParams *>(eq_scratch);
-    k_rach_detect<<<grid, 32, kRachTileBytes, st>>>(T, src, n, detect_thr, out, (demod && out.soft) ? eqp : nullptr);
+    k_rach_detect<<<grid, 32, kRachRollBytes, st>>>(T, src, n, detect_thr, out, (demod && out.soft) ? eqp : nullptr,
+                                                    reinterpret_cast<cf *>(reinterpret_cast<char *>(eq_scratch) + (((size_t)n * sizeof(EqParams) + 127) & ~(size_t)127)));
     if (!(demod && out.soft)) return 1;
     k_slicer_fast<<<grid, 32, kEqTileBytes, st>>>(T, src, n, eqp, out.soft, out.soft_pitch);
     return 2;
@@ -924,7 +964,7 @@ int configure_kernels() {
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_analyze<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAnalyzeSmem);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(k_rach_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRachTileBytes);
+  e = cudaFuncSetAttribute(k_rach_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRachRollBytes);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_slicer_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEqTileBytes);
   if (e != cudaSuccess) return (int)e;

@@ -76,6 +76,7 @@ int launch_resample_rx_i16(const int16_t *in, int swap_iq, int has_history, long
 void launch_resample_tx(const DevTables *T, const cf *in, int has_history, long long nchunks, int16_t *out,
                         cudaStream_t st);
 size_t demod_scratch_bytes(long long n);   // per-launch scratch of launch_demod_normal (EqParams records)
+size_t rach_scratch_bytes(long long n);    // per-launch scratch of launch_rach's tuned path (records + correlation rows)
 int launch_demod_normal(const DevTables *T, BurstSrc src, const uint8_t *tsc, long long n, float detect_thr,
                         float gate_thr, float snr_thr, NormalOut out, void *scratch, cudaStream_t st,
                         cudaEvent_t between = nullptr);

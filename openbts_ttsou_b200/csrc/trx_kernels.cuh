@@ -142,13 +142,13 @@ __global__ void k_trx_commit(int narfcn, const int *__restrict__ commit, const D
 
 struct TrxScratch {                     // device scratch of one pull (caller-owned, sized by trx_scratch_bytes)
   DetRec *det; int *act; float *snr; DfeRec *dfe; EqParams *eqp; int *commit;
-  int *rach_flag; cf *rach_amp; float *rach_toa; float *rach_soft; EqParams *eqp_r;
+  int *rach_flag; cf *rach_amp; float *rach_toa; float *rach_soft; EqParams *eqp_r; cf *rach_cs;
 };
 constexpr int kTrxRachSoftPitch = 160;
 size_t trx_scratch_bytes(long long n, long long nr, int narfcn) {
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
   return up(n * sizeof(DetRec)) + up(n * 4) + up(n * 4) + up(n * sizeof(DfeRec)) + up(n * sizeof(EqParams)) + up((size_t)narfcn * 8 * 4) +
-         up(nr * 4 + 4) + up(nr * 8 + 8) + up(nr * 4 + 4) + up(nr * kTrxRachSoftPitch * 4 + 4) + up(nr * sizeof(EqParams) + 16);
+         up(nr * 4 + 4) + up(nr * 8 + 8) + up(nr * 4 + 4) + up(nr * kTrxRachSoftPitch * 4 + 4) + up(nr * sizeof(EqParams) + 16) + up(nr * 160 * sizeof(cf) + 16);
 }
 static TrxScratch trx_carve(void *base, long long n, long long nr, int narfcn) {
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -164,7 +164,8 @@ static TrxScratch trx_carve(void *base, long long n, long long nr, int narfcn) {
   s.rach_amp = (cf *)p; p += up(nr * 8 + 8);
   s.rach_toa = (float *)p; p += up(nr * 4 + 4);
   s.rach_soft = (float *)p; p += up(nr * kTrxRachSoftPitch * 4 + 4);
-  s.eqp_r = (EqParams *)p;
+  s.eqp_r = (EqParams *)p; p += up(nr * sizeof(EqParams) + 16);
+  s.rach_cs = (cf *)p;
   return s;
 }
 
@@ -191,7 +192,7 @@ int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, i
   if (nr > 0) {
     NormalOut ro{};
     ro.flag = s.rach_flag; ro.amp = s.rach_amp; ro.toa = s.rach_toa;
-    k_rach_detect<<<(unsigned)((nr + 31) / 32), 32, kRachTileBytes, stream>>>(T, rsrc, nr, 5.0F, ro, s.eqp_r);
+    k_rach_detect<<<(unsigned)((nr + 31) / 32), 32, kRachRollBytes, stream>>>(T, rsrc, nr, 5.0F, ro, s.eqp_r, s.rach_cs);
     launches++;
   }
   // pass 2

@@ -246,7 +246,6 @@ void emu_demod_normal(const float *bursts, long long pitch, const int *lens, lon
 
 // tiles != 0: k_rach_detect + k_slicer_fast (sps 1, in-place correlation, rolling-tile slicer), warp by warp;
 // tiles == 0: k_rach<false> (any sps, global scratch)
-struct LaneVote { bool operator()(bool x) const { return x; } };
 
 void emu_rach(const float *bursts, long long pitch, const int *lens, long long first, long long n, float detect_thr,
               int sps, int tiles, int *flag, float *amp, float *toa, float *soft, int soft_pitch) {
@@ -274,27 +273,62 @@ void emu_rach(const float *bursts, long long pitch, const int *lens, long long f
   const Grid ggl{&T->sinc_grid[0][0], 24};
   cf taps[41];
   for (int k = 0; k < 41; k++) taps[k] = mk(T->rach_seq[40 - k].x, -T->rach_seq[40 - k].y);
-  std::vector<cf> tileA(kRachRows * kTileStride), tileB(kEqRows * kTileStride);
-  cf *A = tileA.data(), *B = tileB.data();
+  std::vector<cf> tileB(kEqRows * kTileStride), tileR(kRachRollRows * kTileStride), cs(32 * 160);
+  cf *B = tileB.data(), *R = tileR.data();
   for (long long w0 = 0; w0 < n; w0 += 32) {
     const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
-    for (size_t k = 0; k < tileA.size(); k++) A[k] = mk(1e30F, -1e30F);
-    for (int r = 0; r < kRachOff * kTileStride; r++) A[r] = mk(0.0F, 0.0F);
     long long startv[32]; int lenv[32]; bool okv[32]; cf iav[32]; float toav[32];
     for (int j = 0; j < nv; j++) {
       burst_loc_h((const cf *)bursts, pitch, lens, first, 1, w0 + j, &startv[j], &lenv[j]);
       if (lenv[j] > 157) lenv[j] = 157;
-      const cf *g = (const cf *)bursts + startv[j];
-      for (int r = 0; r < 157; r++) A[(kRachOff + r) * kTileStride + j] = r < lenv[j] ? g[r] : mk(0.0F, 0.0F);
     }
     int nmax = 0;
     for (int j = 0; j < nv; j++) nmax = lenv[j] > nmax ? lenv[j] : nmax;
+    // the rolling-tile detector (k_rach_detect): correlation sweep with the running maximum, the correlation parked
+    // in a scratch row per burst, then the peak search on a 26-lag window
+    int imaxv[32]; float maxv[32];
+    {
+      for (int j = 0; j < 32; j++) { imaxv[j] = -1; maxv[j] = 0.0F; }
+      for (size_t k = 0; k < cs.size(); k++) cs[k] = mk(1e30F, -1e30F);
+      int base = 0;
+      bool staged = false;
+      for (int n0 = 0; n0 < nmax; n0 += 4) {
+        if (!staged || rach_needs_restage(base, n0)) {
+          base = n0 - 20;
+          staged = true;
+          for (size_t k = 0; k < tileR.size(); k++) R[k] = mk(1e30F, -1e30F);
+          for (int j = 0; j < nv; j++) {
+            const cf *g = (const cf *)bursts + startv[j];
+            for (int tr = 0; tr < kRachRollRows; tr++) {
+              const int r = base + tr;
+              R[tr * kTileStride + j] = (r >= 0 && r < lenv[j]) ? g[r] : mk(0.0F, 0.0F);
+            }
+          }
+        }
+        for (int lane = 0; lane < nv; lane++) {
+          cf acc[4];
+          rach_corr4_roll<kTileStride>(View<kTileStride>{R + lane}, base, taps, n0, acc);
+          for (int r = 0; r < 4; r++) {
+            if (n0 + r >= lenv[lane]) continue;
+            cs[lane * 160 + n0 + r] = acc[r];
+            const float p = cnorm2(acc[r]);
+            if (p > maxv[lane]) { maxv[lane] = p; imaxv[lane] = n0 + r; }
+          }
+        }
+      }
+      for (size_t k = 0; k < tileR.size(); k++) R[k] = mk(1e30F, -1e30F);
+      for (int lane = 0; lane < nv; lane++)
+        for (int k = 0; k < kRachWin; k++) {
+          const int idx = imaxv[lane] - 12 + k;
+          R[k * kTileStride + lane] = (idx >= 0 && idx < lenv[lane]) ? cs[lane * 160 + idx] : mk(0.0F, 0.0F);
+        }
+    }
     for (int lane = 0; lane < nv; lane++) {
       const long long i = w0 + lane;
       cf ampv = mk(0.0F, 0.0F);
       float tv = 0.0F;
-      okv[lane] = detect_rach_fast<kTileStride>(ggl, T, View<kTileStride>{A + lane}, lenv[lane], nmax, detect_thr, taps,
-                                                LaneVote(), &ampv, &tv);
+      okv[lane] = rach_finish<kTileStride>(ggl, T, View<kTileStride>{R + lane}, cs.data() + lane * 160, lenv[lane], imaxv[lane],
+                                           detect_thr, &ampv, &tv);
       flag[i] = okv[lane]; amp[2 * i] = ampv.x; amp[2 * i + 1] = ampv.y; toa[i] = tv;
       iav[lane] = okv[lane] ? cdiv(mk(1.0F, 0.0F), ampv) : mk(0.0F, 0.0F);
       toav[lane] = tv;

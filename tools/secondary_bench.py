@@ -75,7 +75,7 @@ toa = torch.zeros(n4, device=dev); soft = torch.zeros(n4 * 148, device=dev)
 ms = timeit(lambda: dsp.demod_normal_dev(dp, 160, tsc, n4, flag, amp, toa, soft, 148, stream=st), reps=50)
 out["demod_normal_8192_per_launch"] = {"bursts": n4, "ms": ms, "bursts_per_s": n4 / ms * 1e3, "detected": float(flag.float().mean())}
 # --- config 3: access bursts
-nr = 65536
+nr = 524288
 rb = torch.zeros(nr, 160, 2, device=dev)
 rbits = np.zeros(88, np.uint8); rbits[:8] = synth.bits_of(synth.RACH_EXT_TAIL); rbits[8:49] = synth.bits_of(synth.RACH_SYNC)
 x = dsp.modulate(rbits, 156 - 88)
