@@ -696,20 +696,46 @@ __global__ void __launch_bounds__(32) k_slicer_fast(const DevTables *__restrict_
     const float4 q0 = __ldg(reinterpret_cast<const float4 *>(eqp + i));
     ok = q0.w != 0.0F; ia = mk(q0.x, q0.y); toa = q0.z;
   }
-  float *row = soft + i * (long long)soft_pitch;
-  if (lane < nv) {                              // not detected: zeros; detected: delayVector's zero fill slices to 0.5
-    for (int m = 0; m < soft_pitch; m++) row[m] = (ok && m < len) ? 0.5F : 0.0F;
-  }
   const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+  // ---- prefill, one coalesced row at a time: not detected -> zeros; detected -> delayVector's zero fill slices to 0.5
+  for (int j = 0; j < nv; j++) {
+    const bool okj = (okmask >> j) & 1u;
+    const int lj = __shfl_sync(0xffffffffu, len, j);
+    float *rj = soft + (w0 + j) * (long long)soft_pitch;
+    for (int m = lane; m < soft_pitch; m += 32) rj[m] = (okj && m < lj) ? 0.5F : 0.0F;
+  }
   if (okmask == 0) return;
   SlicerLane<kTileStride> sl;
   if (ok) sl.init(Grid{&T->sinc_grid[0][0], 24}, T, View<kTileStride>{A + lane}, len, toa);
+  const int io = ok ? sl.f.io : 0;
   const int nmax = __reduce_max_sync(0xffffffffu, ok ? len : 0);
-  int base = 0;
+  int base = 0, xr = 0, ks = 0;                 // tile origin, filter index at the last re-stage, steps since then
   bool staged = false;
+  // A lane's soft bits go to global memory as scattered 4-byte stores if written where they are produced (each store
+  // instruction touches 32 rows).  Instead step k of a tile interval parks its four outputs in tile rows 4k..4k+3 of
+  // the lane's own column -- burst rows the walk has just left behind -- and before the tile is re-staged the warp
+  // writes every lane's run of outputs as coalesced 128-byte stores.
+  auto flush = [&]() {
+    __syncwarp();
+    const int cnt = 4 * ks;
+    for (unsigned rem = okmask; rem; rem &= rem - 1) {
+      const int j = __ffs(rem) - 1;
+      const int mj = xr + __shfl_sync(0xffffffffu, io, j);
+      float *rj = soft + (w0 + j) * (long long)soft_pitch;
+      for (int t = lane; t < cnt; t += 32) {
+        const float v = reinterpret_cast<const float *>(A + t * kTileStride + j)[0];
+        const int m = mj + t;
+        if (v >= 0.0F && (unsigned)m < (unsigned)soft_pitch) rj[m] = v;
+      }
+    }
+    __syncwarp();
+  };
   for (int x0 = 0; x0 < nmax; x0 += 4) {
     if (!staged || slicer_needs_restage(base, x0)) {
+      if (staged) flush();
       base = x0 - 10;
+      xr = x0;
+      ks = 0;
       staged = true;
       __syncwarp();
       for (unsigned rem = okmask; rem; rem &= rem - 1) {
@@ -736,14 +762,14 @@ __global__ void __launch_bounds__(32) k_slicer_fast(const DevTables *__restrict_
     if (ok) {
       float s4[4];
       bool valid[4];
-      sl.step(T, base, x0, s4, valid);
+      sl.step(T, base, x0, s4, valid);                    // reads tile rows >= 4*ks only
 #pragma unroll
-      for (int r = 0; r < 4; r++) {
-        const int m = x0 + r + sl.f.io;
-        if (valid[r] && m < soft_pitch) row[m] = s4[r];
-      }
+      for (int r = 0; r < 4; r++)                          // soft bits are in [0, 1]: -1 marks "no output here"
+        reinterpret_cast<float *>(A + (4 * ks + r) * kTileStride + lane)[0] = valid[r] ? s4[r] : -1.0F;
     }
+    ks++;
   }
+  flush();
 }
 
 void upload_rach_taps(const DevTables *hostT) {
