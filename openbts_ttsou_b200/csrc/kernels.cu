@@ -201,6 +201,15 @@ __global__ void k_modulate(const DevTables *__restrict__ T, const uint8_t *__res
                            long long nbursts, int guard_rule, const uint8_t *__restrict__ guards, long long first,
                            cf *__restrict__ out, long long pitch, const float *__restrict__ scale) {
   const int sps = T->sps;
+  // normal bursts at symbol rate: every sample is a signed sum of up to three entries of rot[n]*pulse[k]
+  // (sigproc_device.cuh: tx_burst_sample), the table and the burst's bits held in shared memory
+  const bool fast = sps == 1 && nbits == 148 && T->pulse_len == 3;
+  __shared__ cf q[148 * 3];
+  __shared__ unsigned char sb[148];
+  if (fast) {
+    for (int i = threadIdx.x; i < 148 * 3; i += blockDim.x) tx_fill_q(T, q, i);
+    __syncthreads();
+  }
   const long long i = blockIdx.x;
   for (long long bi = i; bi < nbursts; bi += gridDim.x) {
     const long long g = first + bi;
@@ -209,17 +218,20 @@ __global__ void k_modulate(const DevTables *__restrict__ T, const uint8_t *__res
     long long start;
     if (pitch > 0) start = bi * pitch;
     else {
-      const int q = (int)(g & 3);
-      start = ((g >> 2) * 625 + (q == 0 ? 0 : (q == 1 ? 157 : (q == 2 ? 313 : 469)))) * sps;
+      const int qd = (int)(g & 3);
+      start = ((g >> 2) * 625 + (qd == 0 ? 0 : (qd == 1 ? 157 : (qd == 2 ? 313 : 469)))) * sps;
     }
     const uint8_t *bb = bits + bi * nbits;
-    if (scale) {                                   // addRadioVector's scaleVector(*modBurst, pow(10,-RSSI/10)), Transceiver.cpp:108
-      const cf sc = mk(scale[bi], 0.0F);
-      for (int t = threadIdx.x; t < n; t += blockDim.x)
-        out[start + t] = cmul(modulate_at(T, bb, nbits, n, sps, T->pulse, T->pulse_len, true, t), sc);
-    } else {
-      for (int t = threadIdx.x; t < n; t += blockDim.x)
-        out[start + t] = modulate_at(T, bb, nbits, n, sps, T->pulse, T->pulse_len, true, t);
+    if (fast) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < 148; t += blockDim.x) sb[t] = bb[t];
+      __syncthreads();
+    }
+    const cf sc = mk(scale ? scale[bi] : 1.0F, 0.0F);
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+      cf x = fast ? tx_burst_sample(q, sb, t) : modulate_at(T, bb, nbits, n, sps, T->pulse, T->pulse_len, true, t);
+      if (scale) x = cmul(x, sc);                  // addRadioVector's scaleVector(*modBurst, pow(10,-RSSI/10)), Transceiver.cpp:108
+      out[start + t] = x;
     }
   }
 }
