@@ -15,7 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbtsdsp.so")
 SOURCES = ["capi.cu", "kernels.cu", "resample.cu"]
-HEADERS = ["cplx.cuh", "tables.h", "sigproc_device.cuh", "demod_fast.cuh", "kernels.cuh", "lpf_taps.inc", "tables_host.h", "../../include/btsdsp.h"]
+# every header of csrc/ (a stale-check that names them one by one misses the next one added) + the public header
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))) + ["../../include/btsdsp.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",

@@ -10,27 +10,23 @@ struct __align__(16) DfeRec {           // a designed equaliser, by the index of
 // pass 2: one thread per ARFCN walks its bursts in FIFO order
 __global__ void k_trx_policy(const DevTables *__restrict__ T, TrxState *__restrict__ st, int narfcn, int nframes, int fn0,
                              const DetRec *__restrict__ det, const int *__restrict__ rach_slot,
-                             const int *__restrict__ rach_flag, int *__restrict__ act, float *__restrict__ snr,
+                             const int *__restrict__ rach_flag, int *__restrict__ act, double *__restrict__ thr_at,
                              int *__restrict__ commit) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= narfcn) return;
-  TrxState s = st[a];
+  TrxScalars s;
+  trx_load_scalars(st[a], s);
   int cm[8];
-  trx_policy_arfcn(s, nframes, fn0, narfcn, a, det, rach_slot, rach_flag, T->exp_neg, act, snr, cm);
+  trx_policy_arfcn(s, nframes, fn0, narfcn, a, det, rach_slot, rach_flag, T->exp_neg, act, thr_at, cm);
   // w, b and chan_off of the state are committed by k_trx_commit once pass 3 has designed them
-  st[a].thr = s.thr;
-  st[a].prev_false_fn = s.prev_false_fn;
-  for (int tn = 0; tn < 8; tn++) {
-    st[a].est_fn[tn] = s.est_fn[tn];
-    st[a].have[tn] = s.have[tn];
-    st[a].snr[tn] = s.snr[tn];
-    commit[a * 8 + tn] = cm[tn];
-  }
+  trx_store_scalars(st[a], s);
+#pragma unroll
+  for (int tn = 0; tn < 8; tn++) commit[a * 8 + tn] = cm[tn];
 }
 
 // pass 3a: designDFE for the bursts that re-estimate (Transceiver.cpp:346-347)
 __global__ void k_trx_design(long long n, const DetRec *__restrict__ det, const int *__restrict__ act,
-                             const float *__restrict__ snr, DfeRec *__restrict__ dfe) {
+                             const double *__restrict__ thr_at, DfeRec *__restrict__ dfe) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || act[i] != (int)i) return;
   const DetRec d = det[i];
@@ -38,7 +34,7 @@ __global__ void k_trx_design(long long n, const DetRec *__restrict__ det, const 
   cf ch[6], w[7], fb[5];
 #pragma unroll
   for (int j = 0; j < 6; j++) ch[j] = cmul(d.chan[j], ia);                               // scaleVector :346
-  design_dfe<7, 5>(ch, 5, snr[i], 7, w, fb);                                             // :347
+  design_dfe<7, 5>(ch, 5, trx_snr_estimate(mk(d.amp_x, d.amp_y), thr_at[i]), 7, w, fb);   // :340, :347
   DfeRec r;
 #pragma unroll
   for (int j = 0; j < 7; j++) r.w[j] = w[j];
@@ -141,13 +137,13 @@ __global__ void k_trx_commit(int narfcn, const int *__restrict__ commit, const D
 }
 
 struct TrxScratch {                     // device scratch of one pull (caller-owned, sized by trx_scratch_bytes)
-  DetRec *det; int *act; float *snr; DfeRec *dfe; EqParams *eqp; int *commit;
+  DetRec *det; int *act; double *thr_at; DfeRec *dfe; EqParams *eqp; int *commit;
   int *rach_flag; cf *rach_amp; float *rach_toa; float *rach_soft; EqParams *eqp_r; cf *rach_cs;
 };
 constexpr int kTrxRachSoftPitch = 160;
 size_t trx_scratch_bytes(long long n, long long nr, int narfcn) {
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  return up(n * sizeof(DetRec)) + up(n * 4) + up(n * 4) + up(n * sizeof(DfeRec)) + up(n * sizeof(EqParams)) + up((size_t)narfcn * 8 * 4) +
+  return up(n * sizeof(DetRec)) + up(n * 4) + up(n * 8) + up(n * sizeof(DfeRec)) + up(n * sizeof(EqParams)) + up((size_t)narfcn * 8 * 4) +
          up(nr * 4 + 4) + up(nr * 8 + 8) + up(nr * 4 + 4) + up(nr * kTrxRachSoftPitch * 4 + 4) + up(nr * sizeof(EqParams) + 16) + up(nr * 160 * sizeof(cf) + 16);
 }
 static TrxScratch trx_carve(void *base, long long n, long long nr, int narfcn) {
@@ -156,7 +152,7 @@ static TrxScratch trx_carve(void *base, long long n, long long nr, int narfcn) {
   TrxScratch s;
   s.det = (DetRec *)p; p += up(n * sizeof(DetRec));
   s.act = (int *)p; p += up(n * 4);
-  s.snr = (float *)p; p += up(n * 4);
+  s.thr_at = (double *)p; p += up(n * 8);
   s.dfe = (DfeRec *)p; p += up(n * sizeof(DfeRec));
   s.eqp = (EqParams *)p; p += up(n * sizeof(EqParams));
   s.commit = (int *)p; p += up((size_t)narfcn * 8 * 4);
@@ -196,9 +192,9 @@ int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, i
     launches++;
   }
   // pass 2
-  k_trx_policy<<<(narfcn + 31) / 32, 32, 0, stream>>>(T, st, narfcn, nframes, fn0, s.det, rach_slot, s.rach_flag, s.act, s.snr, s.commit);
+  k_trx_policy<<<(narfcn + 31) / 32, 32, 0, stream>>>(T, st, narfcn, nframes, fn0, s.det, rach_slot, s.rach_flag, s.act, s.thr_at, s.commit);
   // pass 3
-  k_trx_design<<<(unsigned)((n + 63) / 64), 64, 0, stream>>>(n, s.det, s.act, s.snr, s.dfe);
+  k_trx_design<<<(unsigned)((n + 63) / 64), 64, 0, stream>>>(n, s.det, s.act, s.thr_at, s.dfe);
   k_trx_eqparams<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, narfcn, s.det, s.act, s.dfe, st, s.eqp);
   k_equalize_fast<1, true><<<(unsigned)nwarps, 32, equalize_smem<1>(), stream>>>(T, src, n, s.eqp, dgram + 8, dgram_pitch, 152);
   launches += 4;

@@ -84,25 +84,66 @@ BTS_HD double exp_neg_frames(const double *__restrict__ table, int frames) {
   return frames < kExpTable ? table[frames] : 0.0;
 }
 
+// The scalar part of a TrxState: what pass 2 reads and writes.  Kept apart so that the walk holds it in registers (the
+// timeslot loop is unrolled, every index is static) instead of dragging the 600-byte state through local memory.
+struct TrxScalars {
+  double thr;
+  int prev_false_fn;
+  int chan_type[8], est_fn[8], have[8];
+  float snr[8], chan_off[8];
+};
+BTS_HD void trx_load_scalars(const TrxState &st, TrxScalars &s) {
+  s.thr = st.thr; s.prev_false_fn = st.prev_false_fn;
+#pragma unroll
+  for (int tn = 0; tn < 8; tn++) {
+    s.chan_type[tn] = st.chan_type[tn]; s.est_fn[tn] = st.est_fn[tn]; s.have[tn] = st.have[tn];
+    s.snr[tn] = st.snr[tn]; s.chan_off[tn] = st.chan_off[tn];
+  }
+}
+// chan_off is NOT stored back here: it belongs to the cached DFE and is committed with it (k_trx_commit)
+BTS_HD void trx_store_scalars(TrxState &st, const TrxScalars &s) {
+  st.thr = s.thr; st.prev_false_fn = s.prev_false_fn;
+#pragma unroll
+  for (int tn = 0; tn < 8; tn++) { st.est_fn[tn] = s.est_fn[tn]; st.have[tn] = s.have[tn]; st.snr[tn] = s.snr[tn]; }
+}
+
 // Pass 2 for one ARFCN `a` of a batch laid out [frame][arfcn][tn] (burst i = (f*narfcn + a)*8 + tn, FN = fn0 + f).
 // rach_slot[i] = index of burst i among the batch's RACH-slot bursts (their detection results are compact), or -1.
-// Outputs: act[i], snr[i] (valid where act[i] == i); commit[tn] = the burst whose DFE is the cache entry after the
-// batch (>= 0), ACT_CARRIED (unchanged) -- the caller copies it into st.w/b/chan_off once pass 3 has designed it.
-BTS_HD void trx_policy_arfcn(TrxState &st, int nframes, int fn0, int narfcn, int a, const DetRec *__restrict__ det,
+// Outputs: act[i], thr_at[i] (the threshold right after this burst's update, valid where act[i] == i: pass 3 turns it
+// into the SNR estimate of :340 -- the double division is kept OUT of this serial walk, where its latency would be paid
+// 256 times per thread); commit[tn] = the burst whose DFE is the cache entry after the batch (>= 0), ACT_CARRIED
+// (unchanged) -- the caller copies it into st.w/b/chan_off once pass 3 has designed it.
+// A frame's eight records are fetched up front (independent loads), then walked in TN order.
+BTS_HD float trx_snr_estimate(cf amp, double thr) { return (float)((double)cnorm2(amp) / (thr * thr + 1.0)); }   // :340
+BTS_HD void trx_policy_arfcn(TrxScalars &st, int nframes, int fn0, int narfcn, int a, const DetRec *__restrict__ det,
                              const int *__restrict__ rach_slot, const int *__restrict__ rach_flag,
-                             const double *__restrict__ exp_table, int *__restrict__ act, float *__restrict__ snr,
+                             const double *__restrict__ exp_table, int *__restrict__ act, double *__restrict__ thr_at,
                              int *__restrict__ commit) {
   int src[8];
-  for (int tn = 0; tn < 8; tn++) src[tn] = ACT_CARRIED;
+  float lax[8], lay[8];                     // amplitude and threshold of the last detected TSC burst per timeslot:
+  double lthr[8];                           // SNRestimate[tn] of the state is computed from them once, at the end
+  bool lhave[8];
+#pragma unroll
+  for (int tn = 0; tn < 8; tn++) { src[tn] = ACT_CARRIED; lhave[tn] = false; lax[tn] = lay[tn] = 0.0F; lthr[tn] = 0.0; }
   for (int f = 0; f < nframes; f++) {
     const int fn = (fn0 + f) % kHyperframe;
+    const long long i0 = ((long long)f * narfcn + a) * 8;
+    float en[8], fl[8], ax[8], ay[8], of[8];
+    int rs[8], ac[8];
+#pragma unroll
     for (int tn = 0; tn < 8; tn++) {
-      const long long i = ((long long)f * narfcn + a) * 8 + tn;
-      act[i] = ACT_NONE;
+      const DetRec &d = det[i0 + tn];
+      en[tn] = d.energy; fl[tn] = d.flag; ax[tn] = d.amp_x; ay[tn] = d.amp_y; of[tn] = d.off;
+      rs[tn] = rach_slot[i0 + tn];
+    }
+#pragma unroll
+    for (int tn = 0; tn < 8; tn++) {
+      const long long i = i0 + tn;
+      ac[tn] = ACT_NONE;
       const int corr = expected_corr_type(st.chan_type[tn], fn);
       if (corr == CORR_OFF || corr == CORR_IDLE) continue;                              // :290-293
       const float thrf = (float)st.thr;                                                 // energyDetect takes a float
-      if (!(det[i].energy > BTS_MUL(thrf, thrf))) {                                     // :298, sigProcLib.cpp:931
+      if (!(en[tn] > BTS_MUL(thrf, thrf))) {                                            // :298, sigProcLib.cpp:931
         if ((double)fn_delta(fn, st.prev_false_fn) > 50) { st.thr -= 10.0; st.prev_false_fn = fn; }   // :300-304
         continue;
       }
@@ -110,40 +151,45 @@ BTS_HD void trx_policy_arfcn(TrxState &st, int nframes, int fn0, int narfcn, int
       if (corr == CORR_TSC) {
         bool estimate = false;
         if ((double)fn_delta(fn, st.est_fn[tn]) > 50 || !st.have[tn]) { st.have[tn] = 0; estimate = true; }   // :315-326
-        success = det[i].flag != 0.0F;
+        success = fl[tn] != 0.0F;
         if (success) {
           st.thr -= 1.0F;                                                               // :338-339
           if (st.thr < 0.0) st.thr = 0.0;
-          const cf amp = mk(det[i].amp_x, det[i].amp_y);
-          st.snr[tn] = (float)((double)cnorm2(amp) / (st.thr * st.thr + 1.0));          // :340
+          lax[tn] = ax[tn]; lay[tn] = ay[tn]; lthr[tn] = st.thr; lhave[tn] = true;      // :340, evaluated later
           if (estimate) {                                                               // :341-350
             st.have[tn] = 1;
-            st.chan_off[tn] = det[i].off;
+            st.chan_off[tn] = of[tn];
             st.est_fn[tn] = fn;
             src[tn] = (int)i;
-            snr[i] = st.snr[tn];
+            thr_at[i] = st.thr;
           }
-          act[i] = src[tn];
+          ac[tn] = src[tn];
         } else {
           st.thr += 10.0F * exp_neg_frames(exp_table, fn_delta(fn, st.prev_false_fn));  // :353-355
           st.prev_false_fn = fn;
           st.have[tn] = 0;                                                              // :357
         }
       } else {
-        success = rach_flag[rach_slot[i]] != 0;
+        success = rach_flag[rs[tn]] != 0;
         if (success) {
           st.thr -= 1.0F;                                                               // :369-371
           if (st.thr < 0.0) st.thr = 0.0;
           st.have[tn] = 0;
-          act[i] = ACT_RACH;
+          ac[tn] = ACT_RACH;
         } else {
           st.thr += 10.0F * exp_neg_frames(exp_table, fn_delta(fn, st.prev_false_fn));  // :374-376
           st.prev_false_fn = fn;
         }
       }
     }
+#pragma unroll
+    for (int tn = 0; tn < 8; tn++) act[i0 + tn] = ac[tn];
   }
-  for (int tn = 0; tn < 8; tn++) commit[tn] = src[tn];
+#pragma unroll
+  for (int tn = 0; tn < 8; tn++) {
+    commit[tn] = src[tn];
+    if (lhave[tn]) st.snr[tn] = trx_snr_estimate(mk(lax[tn], lay[tn]), lthr[tn]);
+  }
 }
 
 // RX datagram header, Transceiver.cpp:400-402 and :659-666.  dg[0..7]

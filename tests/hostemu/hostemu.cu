@@ -498,7 +498,8 @@ void emu_trx_pull(void *state, int narfcn, const float *bursts, long long pitch,
   const long long n = (long long)nframes * narfcn * 8;
   std::vector<DetRec> det(n);
   std::vector<int> act(n), slot(n, -1), rflag, ridx;
-  std::vector<float> snr(n, 0.0F), rtoa;
+  std::vector<double> thr_at(n, 0.0);
+  std::vector<float> rtoa;
   std::vector<cf> ramp;
   std::vector<cf> scratch(scratch_per_burst(1));
   // pass 1
@@ -530,9 +531,13 @@ void emu_trx_pull(void *state, int narfcn, const float *bursts, long long pitch,
   if (rflag.empty()) { rflag.push_back(0); }
   // pass 2
   std::vector<int> commit(narfcn * 8);
-  for (int a = 0; a < narfcn; a++)
-    trx_policy_arfcn(st[a], nframes, fn0, narfcn, a, det.data(), slot.data(), rflag.data(), T->exp_neg, act.data(), snr.data(),
+  for (int a = 0; a < narfcn; a++) {
+    TrxScalars sc;
+    trx_load_scalars(st[a], sc);
+    trx_policy_arfcn(sc, nframes, fn0, narfcn, a, det.data(), slot.data(), rflag.data(), T->exp_neg, act.data(), thr_at.data(),
                      commit.data() + a * 8);
+    trx_store_scalars(st[a], sc);
+  }
   // pass 3
   struct Dfe { cf w[7], b[5]; float off; };
   std::vector<Dfe> dfe(n);
@@ -541,7 +546,7 @@ void emu_trx_pull(void *state, int narfcn, const float *bursts, long long pitch,
     const cf ia = cdiv(mk(1.0F, 0.0F), mk(det[i].amp_x, det[i].amp_y));
     cf ch[6];
     for (int j = 0; j < 6; j++) ch[j] = cmul(det[i].chan[j], ia);
-    design_dfe<7, 5>(ch, 5, snr[i], 7, dfe[i].w, dfe[i].b);
+    design_dfe<7, 5>(ch, 5, trx_snr_estimate(mk(det[i].amp_x, det[i].amp_y), thr_at[i]), 7, dfe[i].w, dfe[i].b);
     dfe[i].off = det[i].off;
   }
   for (long long i = 0; i < n; i++) {
