@@ -90,37 +90,42 @@ __global__ void k_trx_rach_veto(long long nr, const int *__restrict__ rach_idx, 
   if (act[rach_idx[j]] != ACT_RACH) reinterpret_cast<float4 *>(eqp_r + j)[0].w = 0.0F;
 }
 
-// pass 3c: RX datagrams (Transceiver.cpp:400-402, 659-673): one warp per burst.  The equaliser has already written the
-// 148 soft bytes of the normal bursts (and zeros elsewhere) at dgram + 8; RACH soft bits come from the compact float rows.
+// pass 3c: RX datagrams (Transceiver.cpp:400-402, 659-673): one thread per burst writes the 8 header bytes as two
+// 4-byte stores.  The equaliser has already written the 148 soft bytes of the normal bursts
+// (and zeros elsewhere) at dgram + 8; the few RACH bursts convert their soft bits from the compact float rows here.
 __global__ void k_trx_datagram(long long n, int narfcn, int fn0, const DetRec *__restrict__ det, const int *__restrict__ act,
                                const int *__restrict__ rach_slot, const cf *__restrict__ rach_amp,
                                const float *__restrict__ rach_toa, const float *__restrict__ rach_soft, int rach_soft_pitch,
                                int *__restrict__ valid, unsigned char *__restrict__ dgram, int dgram_pitch) {
-  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   unsigned char *dg = dgram + i * (long long)dgram_pitch;
   const int a = act[i];
-  if (a == ACT_NONE) {                      // bytes 8..159 were zeroed by the equaliser
-    if (lane < 8) dg[lane] = 0;
-    if (lane == 8) valid[i] = 0;
-    return;
+  unsigned char hdr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (a != ACT_NONE) {
+    const int tn = (int)(i & 7), fn = (int)((fn0 + i / (8LL * narfcn)) % kHyperframe);
+    cf amp;
+    float toa;
+    if (a == ACT_RACH) {
+      const int j = rach_slot[i];
+      amp = rach_amp[j]; toa = rach_toa[j];
+      const float *sp = rach_soft + (long long)j * rach_soft_pitch;
+      for (int m = 0; m < 148; m += 4) {
+        const unsigned w = trx_soft_byte(sp[m]) | (trx_soft_byte(sp[m + 1]) << 8) | (trx_soft_byte(sp[m + 2]) << 16) |
+                           ((unsigned)trx_soft_byte(sp[m + 3]) << 24);
+        *reinterpret_cast<unsigned *>(dg + 8 + m) = w;
+      }
+    } else {
+      amp = mk(det[i].amp_x, det[i].amp_y); toa = det[i].toa;
+    }
+    trx_datagram_header(hdr, tn, fn, amp, toa, 1);
   }
-  const int tn = (int)(i & 7), fn = (int)((fn0 + i / (8LL * narfcn)) % kHyperframe);
-  cf amp;
-  float toa;
-  if (a == ACT_RACH) {
-    const int j = rach_slot[i];
-    amp = rach_amp[j]; toa = rach_toa[j];
-    const float *sp = rach_soft + (long long)j * rach_soft_pitch;
-    for (int m = lane; m < 148; m += 32) dg[8 + m] = trx_soft_byte(sp[m]);
-  } else {
-    amp = mk(det[i].amp_x, det[i].amp_y); toa = det[i].toa;
-  }
-  if (lane == 0) {
-    trx_datagram_header(dg, tn, fn, amp, toa, 1);
-    valid[i] = 1;
-  }
+  unsigned h0 = 0, h1 = 0;                                   // rows are 4-byte aligned (dgram_pitch % 4 == 0)
+#pragma unroll
+  for (int k = 0; k < 4; k++) { h0 |= (unsigned)hdr[k] << (8 * k); h1 |= (unsigned)hdr[4 + k] << (8 * k); }
+  reinterpret_cast<unsigned *>(dg)[0] = h0;
+  reinterpret_cast<unsigned *>(dg)[1] = h1;
+  valid[i] = a != ACT_NONE;
 }
 
 // after pass 3: the cache entries that changed in this batch become the state carried to the next one
@@ -203,7 +208,7 @@ int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, i
     k_slicer_fast<<<(unsigned)((nr + 31) / 32), 32, kEqTileBytes, stream>>>(T, rsrc, nr, s.eqp_r, s.rach_soft, kTrxRachSoftPitch);
     launches += 2;
   }
-  k_trx_datagram<<<(unsigned)((n * 32 + 127) / 128), 128, 0, stream>>>(n, narfcn, fn0, s.det, s.act, rach_slot, s.rach_amp, s.rach_toa,
+  k_trx_datagram<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, narfcn, fn0, s.det, s.act, rach_slot, s.rach_amp, s.rach_toa,
                                                                       s.rach_soft, kTrxRachSoftPitch, valid, dgram, dgram_pitch);
   k_trx_commit<<<(narfcn * 8 + 127) / 128, 128, 0, stream>>>(narfcn, s.commit, s.dfe, st);
   return launches + 2;
