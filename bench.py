@@ -48,6 +48,8 @@ def ncu_traffic(blocks):
             continue
         if d.get("blocks") == blocks:
             best = {k: v.get("dram_bytes") for k, v in d.get("kernels", {}).items()}
+            best["_pipes"] = {k: {m: v[m] for m in ("issue_active_pct", "fma_pipe_active_pct") if m in v}
+                              for k, v in d.get("kernels", {}).items()}
             best["_source"] = os.path.basename(f)
     return best
 
@@ -423,6 +425,8 @@ def main():
         k_res["traffic"] = traffic.get("k_resample_rx_v3")
         k_det["traffic"] = traffic.get("k_detect_design")
         k_eq["traffic"] = traffic.get("k_equalize_fast")
+        for k in (k_res, k_det, k_eq):          # FP32-pipe / issue utilisation from the committed ncu capture (static)
+            k.update({"ncu_" + m: v for m, v in traffic.get("_pipes", {}).get(k["name"], {}).items()})
         for k in (k_res, k_det, k_eq, k_dem):
             k["achieved_gbs"] = k["algorithmic_bytes"] / (k["ms"] * 1e-3) / 1e9
             k["frac"] = k["achieved_gbs"] / peak
