@@ -919,6 +919,8 @@ struct btsdsp_trx {
   DevBuf radio, res;                    // radio chain: per-ARFCN int16 staging (history + chunks), resampled streams
   bool have_history = false;            // the radio chain has seen earlier chunks (their last 192 samples are staged)
   cudaEvent_t meta_done = nullptr;      // the previous call's map upload has been consumed
+  cudaStream_t side = nullptr;          // access-burst kernels run here, next to the normal-burst kernels
+  cudaEvent_t fork_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 int btsdsp_trx_create(btsdsp_ctx *ctx, int narfcn, const uint8_t *tsc, const uint8_t *chan_type, int start_fn,
@@ -945,6 +947,8 @@ int btsdsp_trx_create(btsdsp_ctx *ctx, int narfcn, const uint8_t *tsc, const uin
   cudaError_t e = cudaMalloc(&t->d_state, h.size() * sizeof(TrxState));
   if (e == cudaSuccess) e = cudaMemcpy(t->d_state, h.data(), h.size() * sizeof(TrxState), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->meta_done, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking);
+  for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&t->fork_ev[k], cudaEventDisableTiming);
   if (e != cudaSuccess) { if (t->d_state) cudaFree(t->d_state); delete t; return fail(ctx, BTSDSP_ECUDA, "trx_create", e); }
   *out = t;
   return BTSDSP_OK;
@@ -962,6 +966,8 @@ int btsdsp_trx_destroy(btsdsp_ctx *ctx, btsdsp_trx *t) {
   if (t->res.p) cudaFree(t->res.p);
   if (t->pin.p) cudaFreeHost(t->pin.p);
   if (t->meta_done) cudaEventDestroy(t->meta_done);
+  if (t->side) cudaStreamDestroy(t->side);
+  for (int k = 0; k < 4; k++) if (t->fork_ev[k]) cudaEventDestroy(t->fork_ev[k]);
   delete t;
   return BTSDSP_OK;
 }
@@ -1028,7 +1034,7 @@ static int trx_pull_impl(btsdsp_ctx *ctx, btsdsp_trx *t, const btsdsp_cf32 *burs
   if (r != BTSDSP_OK) return r;
   const int nl = launch_trx_pull(ctx->T, t->d_state, A, nframes, fn0, (const cf *)bursts, pitch, stream_pitch, dm + o_kind,
                                  dm + o_tsc, (const int *)(dm + o_idx), (const int *)(dm + o_slot), nr, t->scratch.p, valid,
-                                 dgram, dgram_pitch, st);
+                                 dgram, dgram_pitch, st, t->side, t->fork_ev);
   LAUNCHED("trx_pull", nl);
   return BTSDSP_OK;
 }

@@ -102,7 +102,8 @@ int launch_rach_decode(const unsigned char *soft, int burst_pitch, long long n, 
 size_t trx_scratch_bytes(long long n, long long nr, int narfcn);
 int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, int fn0, const cf *bursts, long long pitch,
                     long long stream_pitch, const uint8_t *kind, const uint8_t *tsc, const int *rach_idx, const int *rach_slot,
-                    long long nr, void *scratch, int *valid, unsigned char *dgram, int dgram_pitch, cudaStream_t stream);
+                    long long nr, void *scratch, int *valid, unsigned char *dgram, int dgram_pitch, cudaStream_t stream,
+                    cudaStream_t side = nullptr, cudaEvent_t *ev = nullptr);
 
 // scratch (complex samples) the generic-sps global-memory variants need per burst
 __host__ __device__ inline size_t scratch_per_burst(int sps) { return (size_t)(2 * 157 + 36) * sps + 64; }

@@ -176,9 +176,14 @@ static TrxScratch trx_carve(void *base, long long n, long long nr, int narfcn) {
 // streams, stream_pitch samples apart (what the RX resampler writes).
 int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, int fn0, const cf *bursts, long long pitch,
                     long long stream_pitch, const uint8_t *kind, const uint8_t *tsc, const int *rach_idx, const int *rach_slot,
-                    long long nr, void *scratch, int *valid, unsigned char *dgram, int dgram_pitch, cudaStream_t stream) {
+                    long long nr, void *scratch, int *valid, unsigned char *dgram, int dgram_pitch, cudaStream_t stream,
+                    cudaStream_t side, cudaEvent_t *ev) {
   const long long n = (long long)nframes * narfcn * 8;
   if (n <= 0) return 0;
+  // The access-burst kernels work on a few percent of the slots and fill a fraction of the GPU: they run on a side
+  // stream (when the caller supplies one and four events) next to the normal-burst kernels they do not depend on.
+  const bool fork = side != nullptr && ev != nullptr && nr > 0;
+  cudaStream_t rs = fork ? side : stream;
   const TrxScratch s = trx_carve(scratch, n, nr, narfcn);
   BurstSrc src{bursts, pitch, nullptr, 0, 1};
   if (pitch == 0) { src.narfcn = narfcn; src.arfcn_pitch = stream_pitch; }
@@ -186,6 +191,7 @@ int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, i
   const long long nwarps = (n + 31) / 32;
   NormalOut none{};
   // pass 1
+  if (fork) { cudaEventRecord(ev[0], stream); cudaStreamWaitEvent(rs, ev[0], 0); }        // inputs (maps, bursts) are ready
   k_detect_design<1, true><<<(unsigned)nwarps, 32, detect_smem<1>(), stream>>>(T, src, tsc, n, 3.0F, 0.0F, 0.0F, none, nullptr, kind, s.det);
   launches++;
   BurstSrc rsrc = src;
@@ -193,19 +199,22 @@ int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, i
   if (nr > 0) {
     NormalOut ro{};
     ro.flag = s.rach_flag; ro.amp = s.rach_amp; ro.toa = s.rach_toa;
-    k_rach_detect<<<(unsigned)((nr + 31) / 32), 32, kRachRollBytes, stream>>>(T, rsrc, nr, 5.0F, ro, s.eqp_r, s.rach_cs);
+    k_rach_detect<<<(unsigned)((nr + 31) / 32), 32, kRachRollBytes, rs>>>(T, rsrc, nr, 5.0F, ro, s.eqp_r, s.rach_cs);
+    if (fork) { cudaEventRecord(ev[1], rs); cudaStreamWaitEvent(stream, ev[1], 0); }      // the policy needs the RACH flags
     launches++;
   }
   // pass 2
   k_trx_policy<<<(narfcn + 31) / 32, 32, 0, stream>>>(T, st, narfcn, nframes, fn0, s.det, rach_slot, s.rach_flag, s.act, s.thr_at, s.commit);
   // pass 3
   k_trx_design<<<(unsigned)((n + 63) / 64), 64, 0, stream>>>(n, s.det, s.act, s.thr_at, s.dfe);
+  if (fork) { cudaEventRecord(ev[2], stream); cudaStreamWaitEvent(rs, ev[2], 0); }        // act[] is final
   k_trx_eqparams<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, narfcn, s.det, s.act, s.dfe, st, s.eqp);
   k_equalize_fast<1, true><<<(unsigned)nwarps, 32, equalize_smem<1>(), stream>>>(T, src, n, s.eqp, dgram + 8, dgram_pitch, 152);
   launches += 4;
   if (nr > 0) {
-    k_trx_rach_veto<<<(unsigned)((nr + 127) / 128), 128, 0, stream>>>(nr, rach_idx, s.act, s.eqp_r);
-    k_slicer_fast<<<(unsigned)((nr + 31) / 32), 32, kEqTileBytes, stream>>>(T, rsrc, nr, s.eqp_r, s.rach_soft, kTrxRachSoftPitch);
+    k_trx_rach_veto<<<(unsigned)((nr + 127) / 128), 128, 0, rs>>>(nr, rach_idx, s.act, s.eqp_r);
+    k_slicer_fast<<<(unsigned)((nr + 31) / 32), 32, kEqTileBytes, rs>>>(T, rsrc, nr, s.eqp_r, s.rach_soft, kTrxRachSoftPitch);
+    if (fork) { cudaEventRecord(ev[3], rs); cudaStreamWaitEvent(stream, ev[3], 0); }      // the datagrams need the RACH soft bits
     launches += 2;
   }
   k_trx_datagram<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, narfcn, fn0, s.det, s.act, rach_slot, s.rach_amp, s.rach_toa,
