@@ -284,10 +284,23 @@ constexpr int kDetRows = 45;          // burst samples 56..91 in rows 9..44; the
 constexpr int kDetWin = 9;           // (output n only needs window samples >= n - 8, so row n is dead when c[n] is stored)
 constexpr size_t kDetTileBytes = (size_t)kDetRows * kTileStride * sizeof(cf);
 constexpr size_t kEqTileBytes = (size_t)kEqRows * kTileStride * sizeof(cf);
-// WARPS == 1 (what the launchers use) reads the sinc grid from global memory (43 KB, L1/L2-resident): 12 KB of shared
-// memory per CTA lets 16 one-warp CTAs share an SM (registers then bind), 0.47 ms per 800 280 bursts.  WARPS > 1 keeps
-// a shared-memory copy of the grid per CTA (15 warps, 223 KB): 0.58 ms, and its 43 KB copy dominated small launches.
-template <int WARPS> __host__ __device__ constexpr size_t detect_grid_bytes() { return WARPS > 1 ? kGridBytes : 0; }
+// Up to 8 warps per CTA read the sinc grid from global memory (43 KB, L1/L2-resident): 12 KB of shared memory per warp
+// lets 16 warps share an SM (registers then bind), 0.47 ms per 800 280 bursts as one-warp CTAs.  WARPS > 8 keeps a
+// shared-memory copy of the grid per CTA (15 warps, 223 KB): 0.58 ms, and its 43 KB copy dominated small launches.
+#ifndef BTS_DET_WARPS
+#define BTS_DET_WARPS 4
+#endif
+// Large batches run 4-warp CTAs: the kernel is ~130 KB of straight-line code, and warps that start together stay close
+// in it, so the SM's 16 resident warps touch 4 code regions instead of 16 (0.474 -> 0.455 ms per 800 280 bursts; 2: 0.462,
+// 8: 0.488).  Small batches keep one-warp CTAs so they spread over all SMs.
+constexpr int kDetWarps = BTS_DET_WARPS;
+#ifndef BTS_EQ_WARPS
+#define BTS_EQ_WARPS 1
+#endif
+constexpr int kEqWarps = BTS_EQ_WARPS;
+constexpr long long kDetWideMin = 4096;     // warps
+template <int WARPS> __host__ __device__ constexpr bool detect_grid_shared() { return WARPS > 8; }
+template <int WARPS> __host__ __device__ constexpr size_t detect_grid_bytes() { return detect_grid_shared<WARPS>() ? kGridBytes : 0; }
 template <int WARPS> constexpr size_t detect_smem() { return detect_grid_bytes<WARPS>() + WARPS * kDetTileBytes; }
 template <int WARPS> constexpr size_t equalize_smem() { return WARPS * kEqTileBytes; }
 
@@ -304,7 +317,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_detect_design(const DevTables *_
   float *grid = reinterpret_cast<float *>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   cf *A = reinterpret_cast<cf *>(smem_raw + detect_grid_bytes<WARPS>()) + (size_t)warp * kDetRows * kTileStride;
-  if (WARPS > 1) {
+  if (detect_grid_shared<WARPS>()) {
     for (int i = threadIdx.x; i < kSincGrid * kGridPitch; i += WARPS * 32) grid[i] = T->sinc_grid[i / kGridPitch][i % kGridPitch];
     __syncthreads();
   }
@@ -357,7 +370,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_detect_design(const DevTables *_
   if (lane >= nv) return;
 
   const View<kTileStride> a{A + lane};
-  const Grid g = WARPS > 1 ? Grid{grid, kGridPitch} : Grid{&T->sinc_grid[0][0], 24};
+  const Grid g = detect_grid_shared<WARPS>() ? Grid{grid, kGridPitch} : Grid{&T->sinc_grid[0][0], 24};
   bool ok = false;
   cf amp = mk(0.0F, 0.0F), ia = mk(0.0F, 0.0F), chan[6], w[7], fb[5];
   float toa = 0.0F, off = 0.0F;
@@ -536,14 +549,17 @@ int launch_demod_normal(const DevTables *T, BurstSrc src, const uint8_t *tsc, lo
   const long long nwarps = (n + 31) / 32;
   EqParams *eqp = (out.soft || out.soft_u8) ? reinterpret_cast<EqParams *>(scratch) : nullptr;
   // one-warp CTAs, 12 KB of shared memory and 124 registers each: 16 resident per SM
-  k_detect_design<1><<<(unsigned)nwarps, 32, detect_smem<1>(), st>>>(T, src, tsc, n, detect_thr, gate_thr, snr_thr, out, eqp);
+  if (nwarps >= kDetWideMin)
+    k_detect_design<kDetWarps><<<(unsigned)((nwarps + kDetWarps - 1) / kDetWarps), 32 * kDetWarps, detect_smem<kDetWarps>(), st>>>(T, src, tsc, n, detect_thr, gate_thr, snr_thr, out, eqp);
+  else
+    k_detect_design<1><<<(unsigned)nwarps, 32, detect_smem<1>(), st>>>(T, src, tsc, n, detect_thr, gate_thr, snr_thr, out, eqp);
   if (between) cudaEventRecord(between, st);
   if (!out.soft && !out.soft_u8) return 1;
   // one-warp CTAs: 14.8 KB of shared memory and 128 registers per thread each, 14-15 resident per SM
   if (out.soft_u8)
-    k_equalize_fast<1, true><<<(unsigned)nwarps, 32, equalize_smem<1>(), st>>>(T, src, n, eqp, out.soft_u8, out.soft_pitch);
+    k_equalize_fast<kEqWarps, true><<<(unsigned)((nwarps + kEqWarps - 1) / kEqWarps), 32 * kEqWarps, equalize_smem<kEqWarps>(), st>>>(T, src, n, eqp, out.soft_u8, out.soft_pitch);
   else
-    k_equalize_fast<1, false><<<(unsigned)nwarps, 32, equalize_smem<1>(), st>>>(T, src, n, eqp, out.soft, out.soft_pitch);
+    k_equalize_fast<kEqWarps, false><<<(unsigned)((nwarps + kEqWarps - 1) / kEqWarps), 32 * kEqWarps, equalize_smem<kEqWarps>(), st>>>(T, src, n, eqp, out.soft, out.soft_pitch);
   return 2;
 }
 
@@ -993,9 +1009,19 @@ void launch_energy_detect_52m(const cf *v, int n, unsigned win, float thr, float
 int configure_kernels() {
   cudaError_t e;
   e = cudaFuncSetAttribute(k_detect_design<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<1>());
-  if (e != cudaSuccess) return (int)e;
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_detect_design<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<1>());
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_detect_design<kDetWarps, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<kDetWarps>());
   if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_detect_design<kDetWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<kDetWarps>());
+  if (e != cudaSuccess) return (int)e;
+  if (kEqWarps != 1) {
+    e = cudaFuncSetAttribute(k_equalize_fast<kEqWarps, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)equalize_smem<kEqWarps>());
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_equalize_fast<kEqWarps, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)equalize_smem<kEqWarps>());
+    if (e != cudaSuccess) return (int)e;
+  }
   e = cudaFuncSetAttribute(k_equalize_fast<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)equalize_smem<1>());
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_equalize_fast<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)equalize_smem<1>());

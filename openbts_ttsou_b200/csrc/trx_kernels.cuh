@@ -192,7 +192,10 @@ int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, i
   NormalOut none{};
   // pass 1
   if (fork) { cudaEventRecord(ev[0], stream); cudaStreamWaitEvent(rs, ev[0], 0); }        // inputs (maps, bursts) are ready
-  k_detect_design<1, true><<<(unsigned)nwarps, 32, detect_smem<1>(), stream>>>(T, src, tsc, n, 3.0F, 0.0F, 0.0F, none, nullptr, kind, s.det);
+  if (nwarps >= kDetWideMin)
+    k_detect_design<kDetWarps, true><<<(unsigned)((nwarps + kDetWarps - 1) / kDetWarps), 32 * kDetWarps, detect_smem<kDetWarps>(), stream>>>(T, src, tsc, n, 3.0F, 0.0F, 0.0F, none, nullptr, kind, s.det);
+  else
+    k_detect_design<1, true><<<(unsigned)nwarps, 32, detect_smem<1>(), stream>>>(T, src, tsc, n, 3.0F, 0.0F, 0.0F, none, nullptr, kind, s.det);
   launches++;
   BurstSrc rsrc = src;
   rsrc.gather = rach_idx;
