@@ -288,7 +288,7 @@ def test_full_size_properties(dsp):
     depend on how the stream is cut into launches (device-resident call vs segmented host pipeline)."""
     import torch
     dev = torch.device("cuda:0")
-    nblocks = 64                                    # 64 * 936 = 59 904 bursts, 16 000 chunks, 110 MB of raw samples
+    nblocks = 160                                   # 160 * 936 = 149 760 bursts (4 680 warps: the wide-CTA detect launch), 40 000 chunks, 276 MB raw
     nb, nch = 936 * nblocks, 250 * nblocks
     g = torch.Generator(device=dev); g.manual_seed(2)
     bits = torch.randint(0, 2, (nb, 148), generator=g, device=dev, dtype=torch.uint8)

@@ -132,25 +132,36 @@ def test_policy_gpu_matches_reference(oracle_best, dsp, batch):
 
 
 @pytest.mark.gpu
-def test_policy_gpu_large_batch(oracle_best, dsp):
-    """1024-burst frames (128 ARFCN x 8 TN): the shape the policy pass parallelises over; spot-check 3 ARFCNs"""
-    A, nframes, fn0 = 128, 60, 1000
-    tsc = np.arange(A) % 8
-    ct = np.ones((A, 8), np.uint8)
-    ct[:, 0] = 5
-    ct[1::7, 3] = 4
-    bursts = synth.make_trx_batch(oracle_best.modulate, oracle_best.expected_corr_type, nframes, tsc, ct, fn0=fn0, seed=11)
+@pytest.mark.parametrize("copies", [1, 3])
+def test_policy_gpu_large_batch(oracle_best, dsp, copies):
+    """1024-burst frames (128 ARFCN x 8 TN): the shape the policy pass parallelises over; spot-check ARFCNs against
+    the reference glue.  copies = 3 repeats the 128 ARFCNs' slots three times over (384 ARFCNs, 184 320 bursts = 5 760
+    warps), which takes the wide-CTA launch of pass 1 (>= 4096 warps); every copy must reproduce the first."""
+    A0, nframes, fn0 = 128, 60, 1000
+    A = A0 * copies
+    tsc0 = np.arange(A0) % 8
+    ct0 = np.ones((A0, 8), np.uint8)
+    ct0[:, 0] = 5
+    ct0[1::7, 3] = 4
+    b0 = synth.make_trx_batch(oracle_best.modulate, oracle_best.expected_corr_type, nframes, tsc0, ct0, fn0=fn0, seed=11)
+    tsc, ct = np.tile(tsc0, copies), np.tile(ct0, (copies, 1))
+    b4 = np.ascontiguousarray(np.tile(b0.reshape(nframes, A0, 8, -1), (1, copies, 1, 1)))
+    bursts = b4.reshape(nframes * A * 8, -1)
     trx = dsp.trx_create(tsc, ct, fn0)
     v, d = dsp.trx_pull_host(trx, bursts, fn0)
     st = dsp.trx_state(trx)
     dsp.trx_destroy(trx)
-    b4 = bursts.reshape(nframes, A, 8, -1)
+    v4, d4 = v.reshape(nframes, A, 8), d.reshape(nframes, A, 8, -1)
     for a in (0, 8, 127):
         so = oracle_best.trx_new(int(tsc[a]), ct[a], fn0)
         vo, do = oracle_best.trx_pull(so, np.ascontiguousarray(b4[:, a]).reshape(nframes * 8, -1), fn0)
-        assert np.array_equal(vo.reshape(nframes, 8), v.reshape(nframes, A, 8)[:, a])
-        assert np.array_equal(do[:, :158].reshape(nframes, 8, 158), d.reshape(nframes, A, 8, 158)[:, a])
+        assert np.array_equal(vo.reshape(nframes, 8), v4[:, a])
+        assert np.array_equal(do[:, :158].reshape(nframes, 8, 158), d4[:, a, :, :158])
         check_state(st[a:a + 1], so, "gpu large %d" % a)
+    for c in range(1, copies):
+        assert np.array_equal(v4[:, c * A0:(c + 1) * A0], v4[:, :A0])
+        assert np.array_equal(d4[:, c * A0:(c + 1) * A0], d4[:, :A0])
+        assert st[c * A0:(c + 1) * A0].tobytes() == st[:A0].tobytes()
 
 
 def _edge_case(o):
