@@ -294,9 +294,6 @@ constexpr size_t kEqTileBytes = (size_t)kEqRows * kTileStride * sizeof(cf);
 // in it, so the SM's 16 resident warps touch 4 code regions instead of 16 (0.474 -> 0.455 ms per 800 280 bursts; 2: 0.462,
 // 8: 0.488).  Small batches keep one-warp CTAs so they spread over all SMs.
 constexpr int kDetWarps = BTS_DET_WARPS;
-#ifndef BTS_EQ_STAGE_LANE
-#define BTS_EQ_STAGE_LANE 0
-#endif
 #ifndef BTS_EQ_WARPS
 #define BTS_EQ_WARPS 1
 #endif
@@ -500,26 +497,6 @@ __global__ void __launch_bounds__(WARPS * 32) k_equalize_fast(const DevTables *_
       base = m0 - io_max;
       staged = true;
       __syncwarp();
-#if BTS_EQ_STAGE_LANE
-      // variant: every lane fetches its OWN burst's rows (strided global reads, no shuffles, no second pass): the
-      // 1/amplitude scaling happens between the load and the shared-memory store
-      if (ok) {
-        const View<kTileStride> a{A + lane};
-        const cf *g = src.base + start;
-#pragma unroll 1
-        for (int t0 = 0; t0 < kEqRows; t0 += 8) {
-          cf v[8];
-#pragma unroll
-          for (int u = 0; u < 8; u++) {
-            const int r = base + t0 + u;
-            v[u] = ((unsigned)r < (unsigned)len) ? __ldg(g + r) : mk(0.0F, 0.0F);
-          }
-#pragma unroll
-          for (int u = 0; u < 8; u++) a.st(t0 + u, cmul(v[u], ia));
-        }
-      }
-      __syncwarp();
-#else
       for (unsigned rem = okmask; rem; rem &= rem - 1) {            // raw samples, global -> shared, all in flight
         const int j = __ffs(rem) - 1;
         const long long sj = __shfl_sync(0xffffffffu, start, j);
@@ -540,7 +517,6 @@ __global__ void __launch_bounds__(WARPS * 32) k_equalize_fast(const DevTables *_
 #pragma unroll 8
         for (int tr = 0; tr < kEqRows; tr++) a.st(tr, cmul(a.ld(tr), ia));
       }
-#endif
     }
     if (ok) {
       float s4[4];
