@@ -19,8 +19,10 @@
  * soft bits are floats in [0,1] (SoftVector), hard bit = soft > 0.5F (BitVector.h:415-420).
  * All functions return BTSDSP_OK (0) or a negative error; btsdsp_last_error() gives the text.
  * There is no CPU fallback: without a CUDA device btsdsp_create() fails.
- * Contexts are per device; a context's calls must not be issued concurrently from several host threads
- * (layer-2 calls on distinct streams are asynchronous with respect to each other on the device).
+ * Contexts are per device.  Layer-1 and layer-3 calls use the context's own staging buffers and streams: one such call
+ * at a time per context (host/sigProcLib.cpp serialises them with a mutex).  Layer-2 calls may be issued from several
+ * host threads on DISTINCT streams and then overlap on the device: every caller stream gets its own scratch set
+ * (calls on one stream are ordered by the stream itself).
  */
 #ifndef BTSDSP_H
 #define BTSDSP_H
@@ -116,6 +118,23 @@ int btsdsp_demodulate_burst(btsdsp_ctx *ctx, const btsdsp_cf32 *burst, int n, bt
  * Returns the output length ceil(n*P/Q). */
 int btsdsp_polyphase_resample(btsdsp_ctx *ctx, const btsdsp_cf32 *x, int n, int P, int Q, int lpf, btsdsp_cf32 *out,
                               int cap);
+
+/* The same with the caller's own filter (any length): ntaps complex taps; lpf_real != 0 uses only their real parts
+ * (the reference's realOnly branch, :1194-1200), 0 the complex branch (:1187-1193). */
+int btsdsp_polyphase_resample_taps(btsdsp_ctx *ctx, const btsdsp_cf32 *x, int n, int P, int Q, const btsdsp_cf32 *lpf,
+                                   int ntaps, int lpf_real, btsdsp_cf32 *out, int cap);
+/* createLPF :1102-1150 (its cutoff argument is ignored there): filter_len == 651 -> the 651-tap prototype; any other
+ * filter_len <= 961 -> a 961-entry vector whose first filter_len entries are the 961-tap prototype's; all scaled by
+ * float(gain_dc / sum of the copied taps).  Returns the vector length (651 or 961).  filter_len > 961 overruns the
+ * reference's vector and table: BTSDSP_EINVAL. */
+int btsdsp_create_lpf(btsdsp_ctx *ctx, int filter_len, float gain_dc, float *taps, int cap);
+/* the element-wise helpers: addVector :746 (x += y over the shorter length), offsetVector :760, conjugateVector :733,
+ * vectorSlicer :507, GMSKRotate / GMSKReverseRotate :232-264 (n <= 157*sps) -- in place on x -- and vectorNorm2 :146
+ * (*result = sum |x|^2 in the reference's order) */
+enum { BTSDSP_VOP_ADD = 0, BTSDSP_VOP_OFFSET = 1, BTSDSP_VOP_CONJ = 2, BTSDSP_VOP_SLICE = 3, BTSDSP_VOP_NORM2 = 4,
+       BTSDSP_VOP_ROTATE = 5, BTSDSP_VOP_REVROTATE = 6 };
+int btsdsp_vector_op(btsdsp_ctx *ctx, int op, btsdsp_cf32 *x, int n, int real_only, const btsdsp_cf32 *y, int ny,
+                     btsdsp_cf32 scalar, float *result);
 
 /* ---- layer 2: batched, DEVICE pointers, asynchronous on `stream` (a cudaStream_t; NULL = default) ---- */
 /* Burst addressing shared by the batched receive calls:

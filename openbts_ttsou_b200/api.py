@@ -50,6 +50,9 @@ _SIGS = {
     "btsdsp_equalize_burst": (_i, [_vp, _vp, _i, _f, _vp, _i, _vp, _i, _vp]),
     "btsdsp_demodulate_burst": (_i, [_vp, _vp, _i, _cf32, _f, _vp]),
     "btsdsp_polyphase_resample": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i]),
+    "btsdsp_polyphase_resample_taps": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _i]),
+    "btsdsp_create_lpf": (_i, [_vp, _i, _f, _vp, _i]),
+    "btsdsp_vector_op": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _cf32, _vp]),
     "btsdsp_modulate_dev": (_i, [_vp, _vp, _i, _ll, _i, _ll, _vp, _ll, _vp]),
     "btsdsp_resample_rx_dev": (_i, [_vp, _vp, _i, _ll, _vp, _vp]),
     "btsdsp_resample_tx_dev": (_i, [_vp, _vp, _i, _ll, _vp, _vp]),
@@ -290,6 +293,28 @@ class BtsDsp:
         out = np.zeros(int(np.ceil(x.size * P / Q)) + 4, np.complex64)
         n = self._ck(self.lib.btsdsp_polyphase_resample(self.h, _p(x), x.size, P, Q, lpf, _p(out), out.size))
         return out[:n].copy()
+
+    def resample_taps(self, x, P, Q, taps, real_taps=True):
+        """polyphaseResampleVector with the caller's own filter (complex taps; real_taps: only their real parts count)"""
+        x, taps = _c64(x), _c64(taps)
+        out = np.zeros(int(np.ceil(x.size * P / Q)) + 4, np.complex64)
+        n = self._ck(self.lib.btsdsp_polyphase_resample_taps(self.h, _p(x), x.size, P, Q, _p(taps), taps.size, int(real_taps),
+                                                             _p(out), out.size))
+        return out[:n].copy()
+
+    def create_lpf(self, filter_len, gain_dc):
+        out = np.zeros(961, np.float32)
+        n = self._ck(self.lib.btsdsp_create_lpf(self.h, filter_len, gain_dc, _p(out), out.size))
+        return out[:n].copy()
+
+    def vector_op(self, op, x, real_only=False, y=None, scalar=0j):
+        """op: 0 add, 1 offset, 2 conj, 3 slice, 5 rotate, 6 reverse-rotate -> the new x; 4 norm2 -> float"""
+        x = _c64(x).copy()
+        yy = _c64(y) if y is not None else None
+        res = np.zeros(1, np.float32)
+        self._ck(self.lib.btsdsp_vector_op(self.h, op, _p(x), x.size, int(real_only), _p(yy) if yy is not None else None,
+                                           yy.size if yy is not None else 0, _cf32(scalar.real, scalar.imag), _p(res)))
+        return float(res[0]) if op == 4 else x
 
     # ---- layer 2: device pointers ------------------------------------------------------------------
     def modulate_dev(self, bits, nbits, n, out, pitch, guard=-1, first=0, stream=None):

@@ -4,6 +4,8 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -30,10 +32,15 @@ struct btsdsp_ctx {
   DevTables *hT = nullptr;      // host mirror (pinned)
   cudaStream_t st = nullptr, st_in = nullptr, st_out = nullptr;
   std::string err;
-  long long launches = 0;
+  std::atomic<long long> launches{0};
   DevBuf buf[16];               // grow-only device scratch, by role
   DevBuf pin[4];                // grow-only pinned staging
   std::vector<cudaEvent_t> events;
+  // scratch of the layer-2 calls, one set per caller stream: calls on one stream are ordered by the stream, calls on
+  // different streams may overlap on the device and must not share the EqParams records / correlation rows
+  struct StreamScratch { cudaStream_t st; DevBuf eqp, scratch, res; };
+  std::vector<StreamScratch *> per_stream;
+  std::mutex mu;                // guards per_stream / err / launches when layer-2 calls come from several host threads
   bool timing = false;          // btsdsp_set_timing: bracket the kernels of the receive path with events
   cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
   int tev_used = 0;
@@ -47,7 +54,7 @@ int fail(btsdsp_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
   char msg[512];
   if (e != cudaSuccess) snprintf(msg, sizeof msg, "%s: %s", what, cudaGetErrorString(e));
   else snprintf(msg, sizeof msg, "%s", what);
-  if (c) c->err = msg; else g_create_error = msg;
+  if (c) { std::lock_guard<std::mutex> lk(c->mu); c->err = msg; } else g_create_error = msg;
   return code;
 }
 
@@ -84,6 +91,21 @@ int grow(btsdsp_ctx *ctx, DevBuf &b, size_t bytes, bool pinned = false) {
   } while (0)
 
 template <class Tp> Tp *dbuf(btsdsp_ctx *ctx, int slot) { return (Tp *)ctx->buf[slot].p; }
+
+// the scratch set of a caller stream (created on first use; a handful of streams per context is the expected use)
+btsdsp_ctx::StreamScratch *stream_scratch(btsdsp_ctx *ctx, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  for (auto *s : ctx->per_stream) if (s->st == st) return s;
+  auto *s = new btsdsp_ctx::StreamScratch();
+  s->st = st;
+  ctx->per_stream.push_back(s);
+  return s;
+}
+#define GROWBUF(b, bytes)                                         \
+  do {                                                            \
+    int r__ = grow(ctx, (b), (bytes));                            \
+    if (r__ != BTSDSP_OK) return r__;                             \
+  } while (0)
 
 int check_launch(btsdsp_ctx *ctx, const char *what, int nlaunch = 1) {
   cudaError_t e = cudaGetLastError();
@@ -250,6 +272,7 @@ int btsdsp_destroy(btsdsp_ctx *ctx) {
   DeviceGuard g(ctx->device);
   cudaDeviceSynchronize();
   for (auto &b : ctx->buf) if (b.p) cudaFree(b.p);
+  for (auto *ss : ctx->per_stream) { if (ss->eqp.p) cudaFree(ss->eqp.p); if (ss->scratch.p) cudaFree(ss->scratch.p); if (ss->res.p) cudaFree(ss->res.p); delete ss; }
   for (auto &b : ctx->pin) if (b.p) cudaFreeHost(b.p);
   for (auto ev : ctx->events) cudaEventDestroy(ev);
   for (auto ev : ctx->tev) if (ev) cudaEventDestroy(ev);
@@ -265,7 +288,7 @@ int btsdsp_destroy(btsdsp_ctx *ctx) {
 const char *btsdsp_last_error(const btsdsp_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 int btsdsp_device(const btsdsp_ctx *ctx) { return ctx ? ctx->device : -1; }
 int btsdsp_sps(const btsdsp_ctx *ctx) { return ctx ? ctx->sps : -1; }
-long long btsdsp_launch_count(const btsdsp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+long long btsdsp_launch_count(const btsdsp_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
 /* optional per-kernel timing of btsdsp_demod_normal_dev: events around k_detect_design and k_equalize_fast */
 int btsdsp_set_timing(btsdsp_ctx *ctx, int enable) {
   ARG(ctx);
@@ -563,6 +586,60 @@ int btsdsp_polyphase_resample(btsdsp_ctx *ctx, const btsdsp_cf32 *x, int n, int 
   return outn;
 }
 
+/* polyphaseResampleVector :1157 with the caller's own filter (ntaps complex taps; lpf_real: only their real parts are
+ * used, the realOnly branch :1194-1200) */
+int btsdsp_polyphase_resample_taps(btsdsp_ctx *ctx, const btsdsp_cf32 *x, int n, int P, int Q, const btsdsp_cf32 *lpf,
+                                   int ntaps, int lpf_real, btsdsp_cf32 *out, int cap) {
+  ARG(ctx && x && lpf && n > 0 && P > 0 && Q > 0 && ntaps > 0);
+  const int outn = (int)ceil(n * (float)P / (float)Q);     // :1171
+  if (cap < outn || !out) return outn;
+  DeviceGuard g(ctx->device);
+  GROW(B_A, n * sizeof(cf)); GROW(B_B, outn * sizeof(cf)); GROW(B_C, ntaps * sizeof(cf));
+  CK(cudaMemcpyAsync(dbuf<cf>(ctx, B_A), x, n * sizeof(cf), cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(dbuf<cf>(ctx, B_C), lpf, ntaps * sizeof(cf), cudaMemcpyHostToDevice, ctx->st));
+  launch_resample_taps(dbuf<cf>(ctx, B_A), n, P, Q, dbuf<cf>(ctx, B_C), ntaps, lpf_real, dbuf<cf>(ctx, B_B), outn, ctx->st);
+  LAUNCHED("polyphase_resample_taps", 1);
+  CK(cudaMemcpyAsync(out, dbuf<cf>(ctx, B_B), outn * sizeof(cf), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return outn;
+}
+
+/* createLPF :1102-1150: filter_len == 651 gives the 651-tap prototype, anything else the 961-entry vector whose first
+ * filter_len entries are the 961-tap prototype's (the rest stay zero); scaled by float(gain_dc / sum) with the sum of the
+ * copied taps in double.  filter_len > 961 overruns both the vector and the table in the reference: EINVAL here. */
+int btsdsp_create_lpf(btsdsp_ctx *ctx, int filter_len, float gain_dc, float *taps, int cap) {
+  ARG(ctx && filter_len > 0 && filter_len <= kRxTaps);
+  const int n = (filter_len == kTxTaps) ? kTxTaps : kRxTaps;
+  if (!taps || cap < n) return n;
+  memset(taps, 0, (size_t)n * sizeof(float));
+  create_lpf(filter_len == kTxTaps ? LPF651_BITS : LPF961_BITS, filter_len, gain_dc, taps);
+  return n;
+}
+
+/* addVector :746 (x += y over the shorter length), offsetVector :760, conjugateVector :733, vectorSlicer :507, in place
+ * on x, GMSKRotate / GMSKReverseRotate :232-264 (n <= 157*sps); vectorNorm2 :146 returns sum |x|^2 in *result (x unchanged) */
+int btsdsp_vector_op(btsdsp_ctx *ctx, int op, btsdsp_cf32 *x, int n, int real_only, const btsdsp_cf32 *y, int ny,
+                     btsdsp_cf32 scalar, float *result) {
+  ARG(ctx && x && n > 0 && op >= BTSDSP_VOP_ADD && op <= BTSDSP_VOP_REVROTATE);
+  ARG((op != BTSDSP_VOP_ROTATE && op != BTSDSP_VOP_REVROTATE) || n <= 157 * ctx->sps);   /* the rotation tables' length, :215 */
+  ARG(op != BTSDSP_VOP_ADD || (y && ny > 0));
+  ARG(op != BTSDSP_VOP_NORM2 || result);
+  DeviceGuard g(ctx->device);
+  GROW(B_A, n * sizeof(cf)); GROW(B_D, 256);
+  CK(cudaMemcpyAsync(dbuf<cf>(ctx, B_A), x, n * sizeof(cf), cudaMemcpyHostToDevice, ctx->st));
+  if (op == BTSDSP_VOP_ADD) {
+    GROW(B_B, ny * sizeof(cf));
+    CK(cudaMemcpyAsync(dbuf<cf>(ctx, B_B), y, ny * sizeof(cf), cudaMemcpyHostToDevice, ctx->st));
+  }
+  launch_vector_op(ctx->T, op, dbuf<cf>(ctx, B_A), n, real_only, dbuf<cf>(ctx, B_B), ny, mk(scalar.re, scalar.im), dbuf<float>(ctx, B_D),
+                   ctx->st);
+  LAUNCHED("vector_op", 1);
+  if (op == BTSDSP_VOP_NORM2) CK(cudaMemcpyAsync(result, dbuf<float>(ctx, B_D), sizeof(float), cudaMemcpyDeviceToHost, ctx->st));
+  else CK(cudaMemcpyAsync(x, dbuf<cf>(ctx, B_A), n * sizeof(cf), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return BTSDSP_OK;
+}
+
 // ---- layer 2 ---------------------------------------------------------------------------------------
 int btsdsp_modulate_dev(btsdsp_ctx *ctx, const uint8_t *bits, int nbits, long long n, int guard, long long first,
                         btsdsp_cf32 *out, long long pitch, void *stream) {
@@ -604,9 +681,10 @@ int btsdsp_demod_normal_u8_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long 
   DeviceGuard g(ctx->device);
   NormalOut o = {flag, (cf *)amp, toa, nullptr, nullptr, nullptr, nullptr, nullptr, soft_pitch_bytes};
   o.soft_u8 = soft_u8;
-  GROW(B_EQP, demod_scratch_bytes(n));
+  auto *ss = stream_scratch(ctx, (cudaStream_t)stream);
+  GROWBUF(ss->eqp, demod_scratch_bytes(n));
   const int nl = launch_demod_normal(ctx->T, make_src(bursts, pitch, lens, first, 1), tsc, n, detect_thr, gate_thr,
-                                     snr_thr, o, dbuf<void>(ctx, B_EQP), (cudaStream_t)stream);
+                                     snr_thr, o, ss->eqp.p, (cudaStream_t)stream);
   LAUNCHED("demod_normal_u8", nl);
   return BTSDSP_OK;
 }
@@ -629,11 +707,12 @@ int btsdsp_demod_normal_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long lon
   ARG(!soft || soft_pitch >= 148);
   DeviceGuard g(ctx->device);
   NormalOut o = {flag, (cf *)amp, toa, (cf *)chan, chan_off, (cf *)w, (cf *)b, soft, soft_pitch};
-  GROW(B_EQP, demod_scratch_bytes(n));
   cudaStream_t st = (cudaStream_t)stream;
+  auto *ss = stream_scratch(ctx, st);
+  GROWBUF(ss->eqp, demod_scratch_bytes(n));
   if (ctx->timing) CK(cudaEventRecord(ctx->tev[0], st));
   const int nl = launch_demod_normal(ctx->T, make_src(bursts, pitch, lens, first, 1), tsc, n, detect_thr, gate_thr,
-                                     snr_thr, o, dbuf<void>(ctx, B_EQP), st, ctx->timing ? ctx->tev[1] : nullptr);
+                                     snr_thr, o, ss->eqp.p, st, ctx->timing ? ctx->tev[1] : nullptr);
   if (ctx->timing) { CK(cudaEventRecord(ctx->tev[2], st)); ctx->tev_used = 3; }
   LAUNCHED("demod_normal", nl);
   return BTSDSP_OK;
@@ -644,10 +723,11 @@ int btsdsp_analyze_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pit
                        int32_t *flag, btsdsp_cf32 *amp, float *toa, btsdsp_cf32 *chan, float *chan_off, void *stream) {
   ARG(ctx && bursts && tsc && n >= 0 && pitch >= 0);
   DeviceGuard g(ctx->device);
-  if (ctx->sps != 1) GROW(B_SCRATCH, (size_t)n * scratch_per_burst(ctx->sps) * sizeof(cf));
+  auto *ss = stream_scratch(ctx, (cudaStream_t)stream);
+  if (ctx->sps != 1) GROWBUF(ss->scratch, (size_t)n * scratch_per_burst(ctx->sps) * sizeof(cf));
   NormalOut o = {flag, (cf *)amp, toa, (cf *)chan, chan_off, nullptr, nullptr, nullptr, 0};
   launch_analyze(ctx->T, make_src(bursts, pitch, lens, first, ctx->sps), tsc, n, detect_thr, request_channel, o,
-                 dbuf<cf>(ctx, B_SCRATCH), 0, (cudaStream_t)stream);
+                 (cf *)ss->scratch.p, 0, (cudaStream_t)stream);
   LAUNCHED("analyze", n > 0);
   return BTSDSP_OK;
 }
@@ -658,11 +738,12 @@ int btsdsp_rach_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch,
   ARG(ctx && bursts && n >= 0 && pitch >= 0);
   ARG(!soft || soft_pitch >= 157);
   DeviceGuard g(ctx->device);
-  if (ctx->sps != 1) GROW(B_SCRATCH, (size_t)n * scratch_per_burst(ctx->sps) * sizeof(cf));
+  auto *ss = stream_scratch(ctx, (cudaStream_t)stream);
+  if (ctx->sps != 1) GROWBUF(ss->scratch, (size_t)n * scratch_per_burst(ctx->sps) * sizeof(cf));
   NormalOut o = {flag, (cf *)amp, toa, nullptr, nullptr, nullptr, nullptr, soft, soft_pitch};
-  GROW(B_EQP, rach_scratch_bytes(n));
+  GROWBUF(ss->eqp, rach_scratch_bytes(n));
   const int nl = launch_rach(ctx->T, make_src(bursts, pitch, lens, first, ctx->sps), n, detect_thr, soft != nullptr, o,
-                             dbuf<cf>(ctx, B_SCRATCH), 0, (cudaStream_t)stream, dbuf<void>(ctx, B_EQP));
+                             (cf *)ss->scratch.p, 0, (cudaStream_t)stream, ss->eqp.p);
   LAUNCHED("rach", nl);
   return BTSDSP_OK;
 }
@@ -693,9 +774,10 @@ int btsdsp_demodulate_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long 
                           int soft_pitch, void *stream) {
   ARG(ctx && bursts && amp && toa && soft && n >= 0 && pitch >= 0 && soft_pitch >= 157);
   DeviceGuard g(ctx->device);
-  GROW(B_SCRATCH, (size_t)n * scratch_per_burst(ctx->sps) * sizeof(cf));
+  auto *ss = stream_scratch(ctx, (cudaStream_t)stream);
+  GROWBUF(ss->scratch, (size_t)n * scratch_per_burst(ctx->sps) * sizeof(cf));
   launch_demodulate(ctx->T, make_src(bursts, pitch, lens, first, ctx->sps), n, (const cf *)amp, toa, soft, soft_pitch,
-                    dbuf<cf>(ctx, B_SCRATCH), (cudaStream_t)stream);
+                    (cf *)ss->scratch.p, (cudaStream_t)stream);
   LAUNCHED("demodulate", n > 0);
   return BTSDSP_OK;
 }
@@ -1214,10 +1296,11 @@ int btsdsp_analyze_52m_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long
                            int32_t *flag, btsdsp_cf32 *amp, float *toa, btsdsp_cf32 *chan, float *chan_off, void *stream) {
   ARG(ctx && bursts && tsc && n >= 0 && pitch >= 0 && max_toa <= 60);
   DeviceGuard g(ctx->device);
-  GROW(B_SCRATCH, (size_t)(n > 0 ? n : 1) * analyze_52m_scratch_stride(max_toa, ctx->sps) * sizeof(cf));
+  auto *ss = stream_scratch(ctx, (cudaStream_t)stream);
+  GROWBUF(ss->scratch, (size_t)(n > 0 ? n : 1) * analyze_52m_scratch_stride(max_toa, ctx->sps) * sizeof(cf));
   NormalOut o = {flag, (cf *)amp, toa, (cf *)chan, chan_off, nullptr, nullptr, nullptr, 0};
   const int nl = launch_analyze_52m(ctx->T, make_src(bursts, pitch, lens, first, ctx->sps), tsc, n, detect_thr, max_toa,
-                                    request_channel, o, dbuf<cf>(ctx, B_SCRATCH), (cudaStream_t)stream);
+                                    request_channel, o, (cf *)ss->scratch.p, (cudaStream_t)stream);
   LAUNCHED("analyze_52m", nl);
   return BTSDSP_OK;
 }

@@ -104,7 +104,6 @@ BTS_HD cf cmul(cf a, cf b) {
 }
 // Complex.h:84  operator*(Real)
 BTS_HD cf cmulr(cf a, float s) { return pmul(a, s); }
-BTS_HD cf cmulr_packed(cf a, float s) { return pmul(a, s); }
 // Complex.h:86  operator/(Real)
 BTS_HD cf cdivr(cf a, float s) { return mk(BTS_DIV(a.x, s), BTS_DIV(a.y, s)); }
 BTS_HD cf cconj(cf a) { return mk(a.x, -a.y); }

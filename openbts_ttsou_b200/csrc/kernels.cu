@@ -173,6 +173,35 @@ void launch_scale_vector(cf *v, int n, int real_only, cf s, cudaStream_t st) {
   k_scale_vector<<<(n + 127) / 128, 128, 0, st>>>(v, n, real_only, s);
 }
 
+// the element-wise helpers of sigProcLib.cpp: addVector :746, offsetVector :760, conjugateVector :733, vectorSlicer :507
+// GMSKRotate / GMSKReverseRotate :232-264 (one thread per element) and vectorNorm2 :146 (one thread, the reference's summation order; res[0] = sum |x|^2)
+__global__ void k_vector_op(const DevTables *__restrict__ T, int op, cf *x, int n, int real_only, const cf *y, int ny, cf s,
+                            float *res) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (op == VOP_NORM2) {
+    if (i != 0) return;
+    float e = 0.0F;
+    for (int k = 0; k < n; k++) e = BTS_ADD(e, cnorm2(x[k]));
+    *res = e;
+    return;
+  }
+  if (i >= n) return;
+  const cf v = x[i];
+  switch (op) {
+    case VOP_ADD: if (i < ny) x[i] = cadd(v, y[i]); break;
+    case VOP_OFFSET: x[i] = real_only ? mk(BTS_ADD(s.x, v.x), s.y) : cadd(v, s); break;   // `real + offset` = (offset.r + real, offset.i)
+    case VOP_CONJ: if (!real_only) x[i] = cconj(v); break;
+    case VOP_SLICE: x[i] = mk(soft_slice(v.x), 0.0F); break;
+    case VOP_ROTATE: x[i] = real_only ? cmulr(T->rot[i], v.x) : cmul(T->rot[i], v); break;          // GMSKRotate :232-247
+    case VOP_REVROTATE: x[i] = real_only ? cmulr(T->revrot[i], v.x) : cmul(T->revrot[i], v); break; // GMSKReverseRotate :249-264
+  }
+}
+void launch_vector_op(const DevTables *T, int op, cf *x, int n, int real_only, const cf *y, int ny, cf s, float *res,
+                      cudaStream_t st) {
+  if (n <= 0) return;
+  k_vector_op<<<op == VOP_NORM2 ? 1 : (n + 127) / 128, op == VOP_NORM2 ? 32 : 128, 0, st>>>(T, op, x, n, real_only, y, ny, s, res);
+}
+
 __global__ void k_energy_detect(const cf *v, int n, unsigned win, float thr, float *avg, int *flag) {
   if (threadIdx.x != 0) return;
   *flag = energy_detect<1>(View<1>{(cf *)v}, n, win, thr, avg) ? 1 : 0;

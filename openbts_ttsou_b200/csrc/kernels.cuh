@@ -58,8 +58,13 @@ void launch_interp_point(const DevTables *T, const cf *v, int n, float ix, cf *o
 void launch_delay_vector(const DevTables *T, cf *v, int n, float delay, cf *tmp, cudaStream_t st);
 void launch_scale_vector(cf *v, int n, int real_only, cf s, cudaStream_t st);
 void launch_energy_detect(const cf *v, int n, unsigned win, float thr, float *avg, int *flag, cudaStream_t st);
+enum { VOP_ADD = 0, VOP_OFFSET = 1, VOP_CONJ = 2, VOP_SLICE = 3, VOP_NORM2 = 4, VOP_ROTATE = 5, VOP_REVROTATE = 6 };
+void launch_vector_op(const DevTables *T, int op, cf *x, int n, int real_only, const cf *y, int ny, cf s, float *res, cudaStream_t st);
 void launch_resample_generic(const cf *x, int n, int P, int Q, const float *lpf, int L, cf *out, int outn,
                              cudaStream_t st);
+// the same with the caller's own filter: ctaps = L complex taps, real_taps != 0 uses only their real parts (:1187-1200)
+void launch_resample_taps(const cf *x, int n, int P, int Q, const cf *ctaps, int L, int real_taps, cf *out, int outn,
+                          cudaStream_t st);
 void launch_equalize_generic(const DevTables *T, cf *burst, int n, float toa, const cf *w, int nw, const cf *b, int nb,
                              cf *tmp, float *soft, cudaStream_t st);
 void launch_design_dfe_generic(const cf *chan, int nchan, float snr, int nf, cf *w, cf *b, cudaStream_t st);

@@ -545,4 +545,25 @@ void launch_resample_generic(const cf *x, int n, int P, int Q, const float *lpf,
   k_resample_generic<<<(outn + 127) / 128, 128, 0, st>>>(x, n, P, Q, lpf, L, out, outn);
 }
 
+// the same with a filter supplied by the caller (any length; complex taps when the LPF is not real-only, :1187-1193)
+__global__ void k_resample_taps(const cf *__restrict__ x, int n, int P, int Q, const cf *__restrict__ lpf, int L, int real_taps,
+                                cf *__restrict__ out, int outn) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= outn) return;
+  const int outputIx = (L - 1) / 2 / Q + o;
+  const int br = (outputIx * Q) % P;
+  int ix = (outputIx * Q - br) / P;
+  int f = br;
+  while (ix >= n) { ix--; f += P; }
+  cf sum = mk(0.0F, 0.0F);
+  if (real_taps) while (ix >= 0 && f < L) { sum = cadd(sum, cmulr(x[ix], lpf[f].x)); ix--; f += P; }
+  else while (ix >= 0 && f < L) { sum = cadd(sum, cmul(x[ix], lpf[f])); ix--; f += P; }
+  out[o] = sum;
+}
+void launch_resample_taps(const cf *x, int n, int P, int Q, const cf *ctaps, int L, int real_taps, cf *out, int outn,
+                          cudaStream_t st) {
+  if (outn <= 0) return;
+  k_resample_taps<<<(outn + 127) / 128, 128, 0, st>>>(x, n, P, Q, ctaps, L, real_taps, out, outn);
+}
+
 }  // namespace btsdsp

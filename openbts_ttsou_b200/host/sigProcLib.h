@@ -33,15 +33,27 @@ class signalVector : public Vector<complex> {
 void sigProcLibSetup(int samplesPerSymbol);
 void sigProcLibDestroy(void);
 
+/* not declared by the reference's header but exported by its object; defined here too so every symbol resolves */
+float cosLookup(const float x);
+float sinLookup(const float x);
+complex expjLookup(float x);
+void GMSKRotate(signalVector &x);
+void GMSKReverseRotate(signalVector &x);
+float dB(float x);
+float dBinv(float x);
 float vectorNorm2(const signalVector &x);
 float vectorPower(const signalVector &x);
 signalVector *convolve(const signalVector *a, const signalVector *b, signalVector *c, ConvType spanType);
 signalVector *correlate(signalVector *a, signalVector *b, signalVector *c, ConvType spanType);
 signalVector *generateGSMPulse(int symbolLength, int samplesPerSymbol);
+signalVector *frequencyShift(signalVector *y, signalVector *x, float freq = 0.0, float startPhase = 0.0,
+                             float *finalPhase = NULL);
 bool vectorSlicer(signalVector *x);
 signalVector *modulateBurst(const BitVector &wBurst, const signalVector &gsmPulse, int guardPeriodLength,
                             int samplesPerSymbol);
+float sinc(float x);
 void delayVector(signalVector &wBurst, float delay);
+signalVector *gaussianNoise(int length, float variance = 1.0, complex mean = complex(0.0));
 bool addVector(signalVector &x, signalVector &y);
 complex interpolatePoint(const signalVector &inSig, float ix);
 complex peakDetect(const signalVector &rxBurst, float *peakIndex, float *avgPwr);
@@ -64,6 +76,7 @@ SoftVector *demodulateBurst(const signalVector &rxBurst, const signalVector &gsm
                             complex channel, float TOA);
 signalVector *createLPF(float cutoffFreq, int filterLen, float gainDC = 1.0);
 signalVector *polyphaseResampleVector(signalVector &wVector, int P, int Q, signalVector *LPF);
+signalVector *resampleVector(signalVector &wVector, float expFactor, complex endPoint);
 bool designDFE(signalVector &channelResponse, float SNRestimate, int Nf, signalVector **feedForwardFilter,
                signalVector **feedbackFilter);
 SoftVector *equalizeBurst(signalVector &rxBurst, float TOA, int samplesPerSymbol, signalVector &w, signalVector &b);

