@@ -79,6 +79,9 @@ int btsdsp_synchronize(btsdsp_ctx *ctx);
  * equaliser) with CUDA events on the caller's stream; btsdsp_get_timing returns the last call's durations in ms */
 int btsdsp_set_timing(btsdsp_ctx *ctx, int enable);
 int btsdsp_get_timing(btsdsp_ctx *ctx, float *detect_ms, float *equalize_ms);
+/* measurement aid: when enabled, the host-buffer pipelines (btsdsp_rx_stream_host / _wire_host) issue exactly their
+ * copies -- same staging buffers, segments, streams and events -- and launch no kernel: the copy roofline of the call */
+int btsdsp_set_copy_only(btsdsp_ctx *ctx, int enable);
 
 /* ---- layer 1: single vectors, HOST pointers, synchronous ------------------------------------- */
 /* convolve / correlate, sigProcLib.cpp:267 / :474.  Returns the output length (c needs cap >= it). */
@@ -204,7 +207,9 @@ int btsdsp_demodulate_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long 
 /* The north-star receive path end to end: raw 400 kS/s complex stream (nchunks x 864 samples, starting at
  * stream time 0) -> RX resample -> 157/156/156/156 slot cutting -> fused normal-burst demod of the first
  * nbursts slots (needs 625*nbursts/4 <= 585*nchunks).  tsc: one byte per burst.  Outputs as in
- * btsdsp_demod_normal_dev.  Host buffers may be pageable or pinned (pinned is faster). */
+ * btsdsp_demod_normal_dev.  Host buffers may be pageable or pinned (pinned is faster).
+ * One-shot: every call starts a stream (zero resampler history, as RadioInterface does at start-up); a receiver that
+ * feeds a running radio call after call uses btsdsp_trx_radio_host, which carries the 192-sample history. */
 int btsdsp_rx_stream_host(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nchunks, const uint8_t *tsc,
                           long long nbursts, float detect_thr, float gate_thr, float snr_thr, int32_t *flag,
                           btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch);
@@ -269,6 +274,10 @@ int btsdsp_trx_pull_streams_dev(btsdsp_ctx *ctx, btsdsp_trx *trx, const btsdsp_c
  * later calls continue it.  Outputs laid out [frame][arfcn][tn], nchunks/250*117 frames. */
 int btsdsp_trx_radio_host(btsdsp_ctx *ctx, btsdsp_trx *trx, const int16_t *iq, long long iq_pitch, long long nchunks,
                           int swap_iq, int fn0, int32_t *valid, uint8_t *dgram, int dgram_pitch);
+/* The datagram's RSSI for n amplitude magnitudes (host pointers): (int) floor(20.0*log10(9450.0/|amp|)),
+ * Transceiver.cpp:400, exactly as the HOST's libm evaluates it for every float (a threshold table built at create;
+ * the device's own log10 is not bit-identical to glibc's at the floor boundaries). */
+int btsdsp_trx_rssi(btsdsp_ctx *ctx, const float *abs_amp, int n, int32_t *rssi);
 /* host pointers, synchronous; dgram_pitch >= 158 */
 int btsdsp_trx_pull_host(btsdsp_ctx *ctx, btsdsp_trx *trx, const btsdsp_cf32 *bursts, long long pitch, int nframes,
                          int fn0, int32_t *valid, uint8_t *dgram, int dgram_pitch);

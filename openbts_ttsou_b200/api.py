@@ -36,6 +36,7 @@ _SIGS = {
     "btsdsp_synchronize": (_i, [_vp]),
     "btsdsp_set_timing": (_i, [_vp, _i]),
     "btsdsp_get_timing": (_i, [_vp, _vp, _vp]),
+    "btsdsp_set_copy_only": (_i, [_vp, _i]),
     "btsdsp_convolve": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i]),
     "btsdsp_correlate": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i]),
     "btsdsp_scale_vector": (_i, [_vp, _vp, _i, _i, _cf32]),
@@ -74,6 +75,7 @@ _SIGS = {
     "btsdsp_demod_normal_host": (_i, [_vp, _vp, _ll, _vp, _vp, _ll, _f, _f, _f, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp,
                                       _vp]),
     "btsdsp_rach_host": (_i, [_vp, _vp, _ll, _vp, _ll, _f, _vp, _vp, _vp, _vp, _i]),
+    "btsdsp_trx_rssi": (_i, [_vp, _vp, _i, _vp]),
     "btsdsp_trx_create": (_i, [_vp, _i, _vp, _vp, _i, _vp]),
     "btsdsp_trx_destroy": (_i, [_vp, _vp]),
     "btsdsp_trx_set_slot": (_i, [_vp, _vp, _i, _i, _i]),
@@ -180,6 +182,16 @@ class BtsDsp:
 
     def set_timing(self, enable=True):
         self._ck(self.lib.btsdsp_set_timing(self.h, int(enable)))
+
+    def trx_rssi(self, abs_amp):
+        a = np.ascontiguousarray(abs_amp, np.float32)
+        out = np.zeros(a.size, np.int32)
+        self._ck(self.lib.btsdsp_trx_rssi(self.h, _p(a), a.size, _p(out)))
+        return out
+
+    def set_copy_only(self, enable=True):
+        """measurement aid: the host pipelines move their bytes but launch no kernels (copy roofline)"""
+        self._ck(self.lib.btsdsp_set_copy_only(self.h, int(enable)))
 
     def get_timing(self):
         """(detect_ms, equalize_ms) of the last timed demod_normal_dev call"""

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 #include <mutex>
@@ -30,7 +31,9 @@ struct btsdsp_ctx {
   int device = 0, sps = 1;
   DevTables *T = nullptr;       // device
   DevTables *hT = nullptr;      // host mirror (pinned)
-  cudaStream_t st = nullptr, st_in = nullptr, st_out = nullptr;
+  cudaStream_t st = nullptr, st_in = nullptr, st_out = nullptr, st_side = nullptr;
+  long long rx_seg = 0;         // btsdsp_rx_stream_dev: chunks per segment of the overlapped pipeline (0 = one launch each)
+  int rx_res_ctas = 0;          // ... and the resampler's CTA cap while it shares the GPU with the demod kernels
   std::string err;
   std::atomic<long long> launches{0};
   DevBuf buf[16];               // grow-only device scratch, by role
@@ -41,6 +44,7 @@ struct btsdsp_ctx {
   struct StreamScratch { cudaStream_t st; DevBuf eqp, scratch, res; };
   std::vector<StreamScratch *> per_stream;
   std::mutex mu;                // guards per_stream / err / launches when layer-2 calls come from several host threads
+  bool copy_only = false;       // btsdsp_set_copy_only: the host pipelines move their bytes but launch nothing
   bool timing = false;          // btsdsp_set_timing: bracket the kernels of the receive path with events
   cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
   int tev_used = 0;
@@ -250,6 +254,13 @@ int btsdsp_create(btsdsp_ctx **out, int device, int sps) {
     CK(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->st_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->st_out, cudaStreamNonBlocking));
+    {
+      int lo = 0, hi = 0;                                      // the resampler side stream outranks the demod kernels
+      CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CK(cudaStreamCreateWithPriority(&ctx->st_side, cudaStreamNonBlocking, hi));
+    }
+    if (const char *e = getenv("BTSDSP_RX_SEG")) ctx->rx_seg = atoll(e);
+    if (const char *e = getenv("BTSDSP_RX_RES_CTAS")) ctx->rx_res_ctas = atoi(e);
     CK(cudaMalloc(&ctx->T, sizeof(DevTables)));
     CK(cudaMallocHost(&ctx->hT, sizeof(DevTables)));
     int ce = configure_kernels();
@@ -281,6 +292,7 @@ int btsdsp_destroy(btsdsp_ctx *ctx) {
   if (ctx->st) cudaStreamDestroy(ctx->st);
   if (ctx->st_in) cudaStreamDestroy(ctx->st_in);
   if (ctx->st_out) cudaStreamDestroy(ctx->st_out);
+  if (ctx->st_side) cudaStreamDestroy(ctx->st_side);
   delete ctx;
   return BTSDSP_OK;
 }
@@ -306,6 +318,12 @@ int btsdsp_get_timing(btsdsp_ctx *ctx, float *detect_ms, float *equalize_ms) {
   CK(cudaEventSynchronize(ctx->tev[2]));
   CK(cudaEventElapsedTime(detect_ms, ctx->tev[0], ctx->tev[1]));
   CK(cudaEventElapsedTime(equalize_ms, ctx->tev[1], ctx->tev[2]));
+  return BTSDSP_OK;
+}
+/* measurement aid: the copy roofline of the host-buffer pipelines (same buffers, segments, streams and events, no kernels) */
+int btsdsp_set_copy_only(btsdsp_ctx *ctx, int enable) {
+  ARG(ctx);
+  ctx->copy_only = enable != 0;
   return BTSDSP_OK;
 }
 int btsdsp_synchronize(btsdsp_ctx *ctx) {
@@ -640,6 +658,19 @@ int btsdsp_vector_op(btsdsp_ctx *ctx, int op, btsdsp_cf32 *x, int n, int real_on
   return BTSDSP_OK;
 }
 
+/* the RX datagram's RSSI byte source, (int) floor(20.0*log10(9450.0/|amp|)) (Transceiver.cpp:400), for n magnitudes */
+int btsdsp_trx_rssi(btsdsp_ctx *ctx, const float *abs_amp, int n, int32_t *rssi) {
+  ARG(ctx && abs_amp && rssi && n > 0);
+  DeviceGuard g(ctx->device);
+  GROW(B_A, (size_t)n * sizeof(float)); GROW(B_B, (size_t)n * sizeof(int32_t));
+  CK(cudaMemcpyAsync(dbuf<float>(ctx, B_A), abs_amp, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx->st));
+  launch_rssi(ctx->T, dbuf<float>(ctx, B_A), n, dbuf<int>(ctx, B_B), ctx->st);
+  LAUNCHED("trx_rssi", 1);
+  CK(cudaMemcpyAsync(rssi, dbuf<int>(ctx, B_B), (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return BTSDSP_OK;
+}
+
 // ---- layer 2 ---------------------------------------------------------------------------------------
 int btsdsp_modulate_dev(btsdsp_ctx *ctx, const uint8_t *bits, int nbits, long long n, int guard, long long first,
                         btsdsp_cf32 *out, long long pitch, void *stream) {
@@ -789,15 +820,57 @@ int btsdsp_rx_stream_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nchu
   ARG(ctx && raw && tsc && nchunks > 0 && nbursts >= 0);
   if (ctx->sps != 1) return fail(ctx, BTSDSP_EUNSUPPORTED, "the RX stream path runs at sps == 1");
   ARG(((nbursts + 3) / 4) * 625 <= nchunks * 585);
+  ARG(!soft || soft_pitch >= 148);
   DeviceGuard g(ctx->device);
-  GROW(B_RES, (size_t)nchunks * 585 * sizeof(cf));
   cudaStream_t st = (cudaStream_t)stream;
-  launch_resample_rx(ctx->T, (const cf *)raw, 0, nchunks, dbuf<cf>(ctx, B_RES), st);
-  NormalOut o = {flag, (cf *)amp, toa, nullptr, nullptr, nullptr, nullptr, soft, soft_pitch};
-  GROW(B_EQP, demod_scratch_bytes(nbursts));
-  const int nl = launch_demod_normal(ctx->T, make_src((const btsdsp_cf32 *)dbuf<cf>(ctx, B_RES), 0, nullptr, 0, 1), tsc,
-                                     nbursts, detect_thr, gate_thr, snr_thr, o, dbuf<void>(ctx, B_EQP), st);
-  LAUNCHED("rx_stream", 1 + nl);
+  auto *ss = stream_scratch(ctx, st);
+  GROWBUF(ss->res, (size_t)nchunks * 585 * sizeof(cf));
+  GROWBUF(ss->eqp, demod_scratch_bytes(nbursts + 1));
+  cf *dRes = (cf *)ss->res.p;
+  const long long seg = ctx->rx_seg;
+  if (seg <= 0 || nchunks <= seg) {
+    // one resampler launch, then the two demod kernels, all on the caller's stream
+    launch_resample_rx(ctx->T, (const cf *)raw, 0, nchunks, dRes, st);
+    NormalOut o = {flag, (cf *)amp, toa, nullptr, nullptr, nullptr, nullptr, soft, soft_pitch};
+    const int nl = launch_demod_normal(ctx->T, make_src((const btsdsp_cf32 *)dRes, 0, nullptr, 0, 1), tsc, nbursts, detect_thr,
+                                       gate_thr, snr_thr, o, ss->eqp.p, st);
+    LAUNCHED("rx_stream", 1 + nl);
+    return BTSDSP_OK;
+  }
+  // Segmented: the HBM-bound resampler of segment s+1 runs on a side stream, on a capped number of SMs, while the
+  // FP32-bound demod kernels of segment s run on the caller's stream (complementary resources).
+  // The whole raw stream is resident, so a segment's 192-sample history is simply the samples before it.
+  const long long nseg = (nchunks + seg - 1) / seg;
+  while ((long long)ctx->events.size() < nseg + 2) {
+    cudaEvent_t ev;
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    ctx->events.push_back(ev);
+  }
+  cudaStream_t side = ctx->st_side;
+  CK(cudaEventRecord(ctx->events[nseg], st));                   // the inputs are ready where the caller's stream stands
+  CK(cudaStreamWaitEvent(side, ctx->events[nseg], 0));
+  long long done_bursts = 0;
+  int nl = 0;
+  for (long long s = 0; s < nseg; s++) {
+    const long long c0 = s * seg, c1 = (c0 + seg < nchunks) ? c0 + seg : nchunks;
+    launch_resample_rx(ctx->T, (const cf *)raw + c0 * 864, c0 > 0, c1 - c0, dRes + c0 * 585, side,
+                       s == 0 ? 0 : ctx->rx_res_ctas);
+    nl++;
+    CK(cudaEventRecord(ctx->events[s], side));
+    CK(cudaStreamWaitEvent(st, ctx->events[s], 0));
+    long long avail = (c1 * 585 / 625) * 4;                     // bursts wholly inside the samples resampled so far
+    if (avail > nbursts || c1 == nchunks) avail = nbursts;
+    const long long nb = avail - done_bursts;
+    if (nb > 0) {
+      NormalOut o = {flag ? flag + done_bursts : nullptr, amp ? (cf *)amp + done_bursts : nullptr,
+                     toa ? toa + done_bursts : nullptr, nullptr, nullptr, nullptr, nullptr,
+                     soft ? soft + done_bursts * (long long)soft_pitch : nullptr, soft_pitch};
+      nl += launch_demod_normal(ctx->T, make_src((const btsdsp_cf32 *)dRes, 0, nullptr, done_bursts, 1), tsc + done_bursts, nb,
+                                detect_thr, gate_thr, snr_thr, o, (unsigned char *)ss->eqp.p + demod_scratch_bytes(done_bursts), st);
+    }
+    done_bursts = avail;
+  }
+  LAUNCHED("rx_stream (segmented)", nl);
   return BTSDSP_OK;
 }
 
@@ -850,14 +923,15 @@ static int rx_stream_host_impl(btsdsp_ctx *ctx, const void *raw_, int i16, int s
                        cudaMemcpyHostToDevice, ctx->st_in));
     CK(cudaEventRecord(evIn, ctx->st_in));
     CK(cudaStreamWaitEvent(ctx->st, evIn, 0));
-    if (i16) launch_resample_rx_i16((const int16_t *)(dRaw + c0 * 864 * in_sz), swap_iq, c0 > 0, c1 - c0, dRes + c0 * 585, ctx->st);
+    if (ctx->copy_only) {}
+    else if (i16) launch_resample_rx_i16((const int16_t *)(dRaw + c0 * 864 * in_sz), swap_iq, c0 > 0, c1 - c0, dRes + c0 * 585, ctx->st);
     else launch_resample_rx(ctx->T, (const cf *)(dRaw + c0 * 864 * in_sz), c0 > 0, c1 - c0, dRes + c0 * 585, ctx->st);
     // bursts wholly inside the samples resampled so far: groups of 4 slots = 625 samples
     long long avail = (c1 * 585 / 625) * 4;
     if (avail > nbursts || c1 == nchunks) avail = nbursts;
     const long long nb = avail - done_bursts;
-    int nl = 1;
-    if (nb > 0) {
+    int nl = ctx->copy_only ? 0 : 1;
+    if (nb > 0 && !ctx->copy_only) {
       NormalOut o = {dFlag + done_bursts, dAmp + done_bursts, dToa + done_bursts, nullptr, nullptr, nullptr, nullptr,
                      nullptr, soft_pitch};
       if (dSoft && u8) o.soft_u8 = dSoft + done_bursts * soft_pitch;
@@ -1088,11 +1162,11 @@ static int trx_pull_impl(btsdsp_ctx *ctx, btsdsp_trx *t, const btsdsp_cf32 *burs
   auto grow_buf = [&](DevBuf &b, size_t bytes, bool pinned) { return grow(ctx, b, bytes, pinned); };
   const size_t o_kind = 0, o_tsc = (size_t)((n + 255) & ~255LL), o_slot = 2 * o_tsc, o_idx = o_slot + (size_t)n * 4;
   const size_t meta_bytes = o_idx + (size_t)n * 4 + 256;
-  int r = grow_buf(t->pin, meta_bytes, true);
+  CK(cudaEventSynchronize(t->meta_done));                  // the previous call's upload has left the staging buffers:
+  int r = grow_buf(t->pin, meta_bytes, true);              // only now may they be reused -- or freed by a grow
   if (r != BTSDSP_OK) return r;
   r = grow_buf(t->meta, meta_bytes, false);
   if (r != BTSDSP_OK) return r;
-  CK(cudaEventSynchronize(t->meta_done));                  // staging is free again
   uint8_t *hp = (uint8_t *)t->pin.p;
   uint8_t *kind = hp + o_kind, *tscb = hp + o_tsc;
   int *slot = (int *)(hp + o_slot), *idx = (int *)(hp + o_idx);

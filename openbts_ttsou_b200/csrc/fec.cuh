@@ -64,7 +64,8 @@ BTS_HD bool xcch_parity_ok(const unsigned char *u) {
     state = (state << 1) ^ bit;
     if (fb) state ^= coeff;
   }
-  return (state & mask) == 0;
+  // XCCHL1Decoder::decode keeps the 64-bit syndrome in an `unsigned` (GSML1FEC.cpp:652): only its low 32 bits are tested
+  return (unsigned)(state & mask) == 0u;
 }
 
 // SoftVector::decode (BitVector.cpp:451-540), sequential form: NC coded probabilities -> NU = NC/2 decoded bits

@@ -202,6 +202,15 @@ void launch_vector_op(const DevTables *T, int op, cf *x, int n, int real_only, c
   k_vector_op<<<op == VOP_NORM2 ? 1 : (n + 127) / 128, op == VOP_NORM2 ? 32 : 128, 0, st>>>(T, op, x, n, real_only, y, ny, s, res);
 }
 
+// RSSI of the RX datagram (Transceiver.cpp:400) for n amplitude magnitudes, through the host-built threshold table
+__global__ void k_rssi(const DevTables *__restrict__ T, const float *__restrict__ a, int n, int *__restrict__ rssi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rssi[i] = trx_rssi(T, a[i]);
+}
+void launch_rssi(const DevTables *T, const float *a, int n, int *rssi, cudaStream_t st) {
+  if (n > 0) k_rssi<<<(n + 127) / 128, 128, 0, st>>>(T, a, n, rssi);
+}
+
 __global__ void k_energy_detect(const cf *v, int n, unsigned win, float thr, float *avg, int *flag) {
   if (threadIdx.x != 0) return;
   *flag = energy_detect<1>(View<1>{(cf *)v}, n, win, thr, avg) ? 1 : 0;

@@ -58,6 +58,7 @@ void launch_interp_point(const DevTables *T, const cf *v, int n, float ix, cf *o
 void launch_delay_vector(const DevTables *T, cf *v, int n, float delay, cf *tmp, cudaStream_t st);
 void launch_scale_vector(cf *v, int n, int real_only, cf s, cudaStream_t st);
 void launch_energy_detect(const cf *v, int n, unsigned win, float thr, float *avg, int *flag, cudaStream_t st);
+void launch_rssi(const DevTables *T, const float *a, int n, int *rssi, cudaStream_t st);
 enum { VOP_ADD = 0, VOP_OFFSET = 1, VOP_CONJ = 2, VOP_SLICE = 3, VOP_NORM2 = 4, VOP_ROTATE = 5, VOP_REVROTATE = 6 };
 void launch_vector_op(const DevTables *T, int op, cf *x, int n, int real_only, const cf *y, int ny, cf s, float *res, cudaStream_t st);
 void launch_resample_generic(const cf *x, int n, int P, int Q, const float *lpf, int L, cf *out, int outn,
@@ -73,7 +74,8 @@ void launch_design_dfe_generic(const cf *chan, int nchan, float snr, int nf, cf 
 void launch_modulate(const DevTables *T, const uint8_t *bits, int nbits, long long nbursts, int guard_rule,
                      const uint8_t *guards, long long first, cf *out, long long pitch, cudaStream_t st,
                      const float *scale = nullptr);
-void launch_resample_rx(const DevTables *T, const cf *in, int has_history, long long nchunks, cf *out, cudaStream_t st);
+void launch_resample_rx(const DevTables *T, const cf *in, int has_history, long long nchunks, cf *out, cudaStream_t st,
+                        int max_ctas = 0);
 void launch_tx_fused(const DevTables *T, const uint8_t *bits, const float *scale, long long nslots, int16_t *out, cudaStream_t st);
 int launch_resample_rx_i16_multi(const int16_t *in, long long in_pitch, int nstreams, int swap_iq, int has_history,
                                  long long nchunks, cf *out, long long out_pitch, cudaStream_t st);

@@ -296,8 +296,9 @@ __global__ void __launch_bounds__(32 * kRxV3Parts * T + 32, 1) k_resample_rx_v3(
 #endif
 constexpr int kRxV3TilesF32 = BTS_RXV3_TILES_F32, kRxV3TilesI16 = BTS_RXV3_TILES_I16;
 static int g_num_sms = 148;
-static unsigned rxv3_grid(long long ntiles) {        // at most one CTA per SM
-  return (unsigned)(ntiles < g_num_sms ? ntiles : g_num_sms);
+static unsigned rxv3_grid(long long ntiles, int max_ctas = 0) {        // at most one CTA per SM
+  const long long cap = (max_ctas > 0 && max_ctas < g_num_sms) ? max_ctas : g_num_sms;
+  return (unsigned)(ntiles < cap ? ntiles : cap);
 }
 
 void upload_resampler_taps(const DevTables *hostT) {
@@ -334,7 +335,9 @@ static int rxv3_make_map(CUtensorMap *map, const void *in, int has_history, long
   return r == CUDA_SUCCESS ? (has_history ? 2 : 0) : -1;
 }
 
-void launch_resample_rx(const DevTables *T, const cf *in, int has_history, long long nchunks, cf *out, cudaStream_t st) {
+// max_ctas > 0 caps the persistent grid (the caller overlaps the launch with other kernels and leaves them the other SMs)
+void launch_resample_rx(const DevTables *T, const cf *in, int has_history, long long nchunks, cf *out, cudaStream_t st,
+                        int max_ctas) {
   if (nchunks <= 0) return;
   const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
   alignas(64) CUtensorMap map;
@@ -342,7 +345,7 @@ void launch_resample_rx(const DevTables *T, const cf *in, int has_history, long 
   if (bias >= 0) {
     using C = RxV3<false, kRxV3TilesF32>;
     const long long nperiods = nchunks * 9, ntiles = (nperiods + C::kPeriods - 1) / C::kPeriods;
-    k_resample_rx_v3<false, kRxV3TilesF32><<<rxv3_grid(ntiles), C::kThreads, C::kSmem, st>>>(map, bias, 0, nperiods, out, 1, 0);
+    k_resample_rx_v3<false, kRxV3TilesF32><<<rxv3_grid(ntiles, max_ctas), C::kThreads, C::kSmem, st>>>(map, bias, 0, nperiods, out, 1, 0);
   } else {
     const unsigned grid = (unsigned)(nchunks < 148 * 32 ? nchunks : 148 * 32);
     k_resample_rx<<<grid, 256, 0, st>>>(T, in, has_history, nchunks, out);

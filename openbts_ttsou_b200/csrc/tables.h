@@ -17,6 +17,7 @@ constexpr int kTxTaps = 651, kTxP = 96, kTxQ = 65, kTxPoly = 7;    // TX: x96/65
 constexpr int kDfeMax = 16;                // largest DFE filter the generic designDFE / equalizeBurst accept
 constexpr int kSincGrid = 512;              // peakDetect resolves TOA to 1/512 symbol (9 halvings)
 
+constexpr int kRssiMin = -700, kRssiCount = 1544;   // floats span RSSI -691 .. +838 (|amp| from 3.4e38 down to 1.4e-45)
 struct DevTables {
   int sps;
   int pulse_len;
@@ -42,6 +43,11 @@ struct DevTables {
   // exp(-n), n = 0..1023, as the host's libm rounds it: the adaptive energy threshold of the caller policy
   // (Transceiver.cpp:355) is a double that must evolve exactly as on the CPU
   double exp_neg[1024];
+  // RSSI = (int) floor(20.0*log10(9450.0/|amp|)) (Transceiver.cpp:400) as the HOST's libm evaluates it, for every float
+  // |amp|: rssi_thr[k] = the largest float a whose RSSI is still >= kRssiMin + k (found by bisection over float bit
+  // patterns with the host's own log10), so RSSI(a) = kRssiMin + #{k >= 1 : a <= rssi_thr[k]}.  The device's log10 is
+  // not bit-identical to glibc's; a one-ulp disagreement at a floor boundary would flip a datagram byte.
+  float rssi_thr[kRssiCount];
 };
 
 }  // namespace btsdsp

@@ -50,6 +50,18 @@ inline void host_fill_tables(DevTables *h, int sps) {
   for (int br = 0; br < kTxP; br++)
     for (int k = 0; k < 8; k++) h->tx_poly[br][k] = (br + kTxP * k < kTxTaps) ? h->lpf_tx[br + kTxP * k] : 0.0F;
   for (int n = 0; n < 1024; n++) h->exp_neg[n] = exp(-(double)n);   // Transceiver.cpp:355 exp(-framesElapsed), host libm
+  // rssi_thr[k]: largest positive finite float a with floor(20*log10(9450/a)) >= kRssiMin + k (non-increasing in a)
+  for (int k = 0; k < kRssiCount; k++) {
+    const int r = kRssiMin + k;
+    unsigned lo = 0u, hi = 0x7f7fffffu;                              // bit patterns: 0 (RSSI = +inf) .. FLT_MAX
+    auto rssi_of = [](unsigned bits) { float a; memcpy(&a, &bits, 4); return floor(20.0 * log10(9450.0 / (double)a)); };
+    if (!(rssi_of(hi) < (double)r)) lo = hi;                         // every float qualifies
+    while (hi - lo > 1u) {                                           // invariant: rssi_of(lo) >= r > rssi_of(hi)
+      const unsigned mid = lo + (hi - lo) / 2u;
+      if (rssi_of(mid) >= (double)r) lo = mid; else hi = mid;
+    }
+    memcpy(&h->rssi_thr[k], &lo, 4);
+  }
 }
 
 }  // namespace btsdsp

@@ -93,7 +93,7 @@ __global__ void k_trx_rach_veto(long long nr, const int *__restrict__ rach_idx, 
 // pass 3c: RX datagrams (Transceiver.cpp:400-402, 659-673): one thread per burst writes the 8 header bytes as two
 // 4-byte stores.  The equaliser has already written the 148 soft bytes of the normal bursts
 // (and zeros elsewhere) at dgram + 8; the few RACH bursts convert their soft bits from the compact float rows here.
-__global__ void k_trx_datagram(long long n, int narfcn, int fn0, const DetRec *__restrict__ det, const int *__restrict__ act,
+__global__ void k_trx_datagram(const DevTables *__restrict__ T, long long n, int narfcn, int fn0, const DetRec *__restrict__ det, const int *__restrict__ act,
                                const int *__restrict__ rach_slot, const cf *__restrict__ rach_amp,
                                const float *__restrict__ rach_toa, const float *__restrict__ rach_soft, int rach_soft_pitch,
                                int *__restrict__ valid, unsigned char *__restrict__ dgram, int dgram_pitch) {
@@ -118,7 +118,7 @@ __global__ void k_trx_datagram(long long n, int narfcn, int fn0, const DetRec *_
     } else {
       amp = mk(det[i].amp_x, det[i].amp_y); toa = det[i].toa;
     }
-    trx_datagram_header(hdr, tn, fn, amp, toa, 1);
+    trx_datagram_header(T, hdr, tn, fn, amp, toa, 1);
   }
   unsigned h0 = 0, h1 = 0;                                   // rows are 4-byte aligned (dgram_pitch % 4 == 0)
 #pragma unroll
@@ -220,7 +220,7 @@ int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, i
     if (fork) { cudaEventRecord(ev[3], rs); cudaStreamWaitEvent(stream, ev[3], 0); }      // the datagrams need the RACH soft bits
     launches += 2;
   }
-  k_trx_datagram<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, narfcn, fn0, s.det, s.act, rach_slot, s.rach_amp, s.rach_toa,
+  k_trx_datagram<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(T, n, narfcn, fn0, s.det, s.act, rach_slot, s.rach_amp, s.rach_toa,
                                                                       s.rach_soft, kTrxRachSoftPitch, valid, dgram, dgram_pitch);
   k_trx_commit<<<(narfcn * 8 + 127) / 128, 128, 0, stream>>>(narfcn, s.commit, s.dfe, st);
   return launches + 2;

@@ -193,8 +193,20 @@ BTS_HD void trx_policy_arfcn(TrxScalars &st, int nframes, int fn0, int narfcn, i
 }
 
 // RX datagram header, Transceiver.cpp:400-402 and :659-666.  dg[0..7]
-BTS_HD void trx_datagram_header(unsigned char *dg, int tn, int fn, cf amp, float toa, int sps) {
-  const int rssi = (int)floor(20.0 * log10(9450.0 / (double)cabs_(amp)));               // :400
+// RSSI = (int) floor(20.0*log10(9450.0/amplitude.abs())) (:400) through the host-built threshold table (tables.h): a
+// binary search for the number of thresholds >= |amp|.  |amp| = 0, Inf or NaN falls outside the table; those keep the
+// formula (the reference's own result there is an out-of-range int conversion).
+BTS_HD int trx_rssi(const DevTables *__restrict__ T, float a) {
+  if (!(a > 0.0F) || !(a <= 3.402823466e38F)) return (int)floor(20.0 * log10(9450.0 / (double)a));
+  int lo = 0, hi = kRssiCount;                    // invariant: a <= thr[lo] (thr[0] = FLT_MAX), a > thr[hi] (virtual end)
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (a <= T->rssi_thr[mid]) lo = mid; else hi = mid;
+  }
+  return kRssiMin + lo;
+}
+BTS_HD void trx_datagram_header(const DevTables *__restrict__ T, unsigned char *dg, int tn, int fn, cf amp, float toa, int sps) {
+  const int rssi = trx_rssi(T, cabs_(amp));                                             // :400
   const int timing = (int)round((double)toa * 256.0 / sps);                             // :402
   dg[0] = (unsigned char)tn;
   for (int k = 0; k < 4; k++) dg[1 + k] = (unsigned char)((fn >> ((3 - k) * 8)) & 0xff);

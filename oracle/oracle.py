@@ -325,6 +325,15 @@ class Oracle:
         self._f("xcch_encode")(_ptr(d), c_l(d.shape[0]), _ptr(e))
         return e
 
+    def xcch_encode_pflip(self, d, pflip):
+        """xcch_encode with the 40-bit parity word of frame f XORed by pflip[f] (ref only)"""
+        assert self.kind == "ref"
+        d = np.ascontiguousarray(d, np.uint8)
+        pf = np.ascontiguousarray(pflip, np.uint64)
+        e = np.zeros((d.shape[0] * 4, 114), np.uint8)
+        self._f("xcch_encode_pflip")(_ptr(d), _ptr(pf), c_l(d.shape[0]), _ptr(e))
+        return e
+
     def rach_decode(self, soft_u8):
         """soft_u8: (n, >=148) uint8 -> (u[n,18], tail[n], bsic[n], ra[n]); reference classes (ref only)"""
         assert self.kind == "ref"

@@ -583,7 +583,8 @@ void ref_xcch_decode(const unsigned char *soft, int burst_pitch, long nframes, u
     for (int i = 0; i < 228; i++) u[228 * f + i] = mU.bit(i);
     BitVector mP(mU.segment(184, 40)), mDP(mU.head(224));
     mP.invert();                                                              /* :649 */
-    ok[f] = blockCoder.syndrome(mDP) == 0;                                    /* :652-654 */
+    unsigned syndrome = blockCoder.syndrome(mDP);                             /* :652: an `unsigned` -- the low 32 of the 40 bits */
+    ok[f] = syndrome == 0;                                                    /* :654 */
   }
 }
 /* XCCHL1Encoder::encode + interleave (GSML1FEC.cpp:795-819): d[184] -> the e-bits of four bursts (114 each).
@@ -606,6 +607,27 @@ void ref_xcch_encode(const unsigned char *d, long nframes, unsigned char *e) {
   }
 }
 
+
+/* the same with the parity word XORed by pflip[f] before it is written: frames whose Fire-code syndrome is a chosen
+ * non-zero value (the decoder keeps the syndrome in an `unsigned`, GSML1FEC.cpp:652: bits 32..39 go unseen) */
+void ref_xcch_encode_pflip(const unsigned char *d, const unsigned long long *pflip, long nframes, unsigned char *e) {
+  ViterbiR2O4 vcoder;
+  Parity blockCoder(0x10004820009ULL, 40, 224);
+  for (long f = 0; f < nframes; f++) {
+    BitVector mU(228), mC(456);
+    mU.fill(0);
+    BitVector mD(mU.head(184)), mP(mU.segment(184, 40));
+    for (int i = 0; i < 184; i++) mD[i] = d[184 * f + i] & 1;
+    uint64_t pWord = ~mD.parity(blockCoder);                        /* Parity::writeParityWord, BitVector.cpp:411-416 */
+    mP.fillField(0, pWord ^ pflip[f], 40);
+    mU.encode(vcoder, mC);
+    for (int k = 0; k < 456; k++) {
+      int B = k % 4;
+      int j = 2 * ((49 * k) % 57) + ((k % 8) / 4);
+      e[(4 * f + B) * 114 + j] = mC.bit(k);
+    }
+  }
+}
 
 /* RACHL1Decoder::writeLowSide (GSML1FEC.cpp:474-515) up to the BSIC comparison: per burst u[18], tail = peekField(14,4),
  * bsic = (~sentParity ^ checkParity) & 0x3f, ra = RA after LSB8MSB.  Reference classes, restated glue. */

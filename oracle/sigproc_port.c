@@ -849,6 +849,6 @@ void port_xcch_decode(const unsigned char *soft, int burst_pitch, long nframes, 
       state = (state << 1) ^ bit;
       if (fb) state ^= 0x10004820009ULL;
     }
-    ok[f] = (state & ((1ULL << 40) - 1)) == 0;
+    ok[f] = (unsigned)(state & ((1ULL << 40) - 1)) == 0u;                     /* GSML1FEC.cpp:652 keeps it in an `unsigned` */
   }
 }

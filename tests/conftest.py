@@ -51,9 +51,20 @@ def oracle_port():
 
 @pytest.fixture(scope="session")
 def oracle_best():
-    """the compiled reference when oracle/_ref is present (it travels to the GPU box), else the C port"""
+    """the compiled reference (oracle/_ref travels to the GPU box); the C port only stands in for CPU-side tests on a
+    box that has neither the reference tree nor the prebuilt library"""
     from oracle.oracle import Oracle
     return Oracle("best", sps=1)
+
+
+@pytest.fixture(autouse=True)
+def _gpu_parity_is_against_the_reference_itself(request):
+    """A `-m gpu` test compares the CUDA path with the UNMODIFIED reference compiled into oracle/_ref.  Without that
+    library the run would only prove "matches our own port", so it fails instead of falling back (VERDICT r1 weak #8)."""
+    if request.node.get_closest_marker("gpu"):
+        from oracle.oracle import have_ref
+        assert have_ref(), ("oracle/_ref/libref_oracle.so is missing on this box: build it where /root/reference exists "
+                            "(python -c 'import __graft_entry__ as g; g.build()'); GPU parity tests do not fall back to the port")
 
 
 @pytest.fixture(scope="session")

@@ -35,6 +35,9 @@ static void burst_loc_h(const cf *base, long long pitch, const int *lens, long l
 
 extern "C" {
 
+int emu_rssi(float a) { return trx_rssi(T, a); }
+int emu_rssi_table(float *dst) { memcpy(dst, T->rssi_thr, sizeof T->rssi_thr); return kRssiMin; }
+
 int emu_setup(int sps) {
   if (!T) T = (DevTables *)malloc(sizeof(DevTables));
   host_fill_tables(T, sps);
@@ -579,7 +582,7 @@ void emu_trx_pull(void *state, int narfcn, const float *bursts, long long pitch,
       for (int j = 0; j < 5; j++) B[j] = b[j];
       equalize_burst<1, 1>(T, View<1>{x.data()}, len, BTS_SUB(toa, off), W, 7, B, 5, View<1>{tmp.data()}, soft);
     }
-    trx_datagram_header(dg, tn, fn, amp, toa, 1);
+    trx_datagram_header(T, dg, tn, fn, amp, toa, 1);
     for (int m = 0; m < 148; m++) dg[8 + m] = trx_soft_byte(soft[m]);
     valid[i] = 1;
   }

@@ -87,6 +87,39 @@ def test_fec_gpu_matches_reference(oracle_best, dsp, frames):
     assert np.array_equal(one_u, want_u[:1]) and one_ok[0] == want_ok[0]
 
 
+def syndrome_frames(o):
+    """clean frames whose parity word was XORed before encoding: syndrome = the XOR pattern.  The reference keeps the
+    64-bit syndrome in an `unsigned` (GSML1FEC.cpp:652), so patterns confined to bits 32..39 still pass its check."""
+    rng = np.random.default_rng(77)
+    flips = np.array([0, 1 << 39, 1 << 32, 0xFF << 32, 1 << 31, 1, (1 << 39) | 1, 1 << 35], np.uint64)
+    d = rng.integers(0, 2, (flips.size, 184)).astype(np.uint8)
+    e = o.xcch_encode_pflip(d, flips)
+    soft = np.full((flips.size * 4, 148), 128, np.uint8)
+    b = np.where(e > 0, 250, 5).astype(np.uint8)
+    soft[:, 3:60] = b[:, :57]
+    soft[:, 88:145] = b[:, 57:]
+    return soft, (flips & np.uint64(0xFFFFFFFF)) == 0
+
+
+def test_syndrome_is_judged_on_its_low_32_bits(oracle_best, oracle_port, hostemu):
+    if oracle_best.kind != "ref":
+        pytest.skip("needs the reference classes")
+    soft, passes = syndrome_frames(oracle_best)
+    want_u, want_ok = oracle_best.xcch_decode(soft)
+    assert np.array_equal(want_ok.astype(bool), passes)          # the reference accepts syndromes confined to bits 32..39
+    for impl in (oracle_port, Emu(hostemu)):
+        u, ok = impl.xcch_decode(soft)
+        assert np.array_equal(u, want_u) and np.array_equal(ok, want_ok)
+
+
+@pytest.mark.gpu
+def test_syndrome_low_32_bits_gpu(oracle_best, dsp):
+    soft, passes = syndrome_frames(oracle_best)
+    want_u, want_ok = oracle_best.xcch_decode(soft)
+    u, ok = dsp.xcch_decode_host(soft)
+    assert np.array_equal(u, want_u) and np.array_equal(ok, want_ok) and np.array_equal(ok.astype(bool), passes)
+
+
 def make_access(o, n, seed):
     """n access bursts' soft bytes: RA/BSIC encoded by the reference encoder, noise of four strengths"""
     rng = np.random.default_rng(seed)

@@ -91,6 +91,12 @@ def test_surface_and_threads_equal_the_reference(tmp_path):
     ref = read_dump(os.path.join(ROOT, "tests", "golden", "surface_ref.bin"))
     assert list(got) == list(ref)
     for tag in ref:
+        if tag in ("lpf961", "lpf961b"):
+            # the reference copies 961 entries out of its 960-entry sendLPF_961 table, so its last tap is whatever
+            # the linker placed behind the table (5.6e-42 in the build that wrote the golden file); the library holds 0.0f
+            assert got[tag][:-8] == ref[tag][:-8], tag
+            assert np.frombuffer(got[tag][-8:], np.float32)[0] == 0.0 and abs(np.frombuffer(ref[tag][-8:], np.float32)[0]) < 1e-30
+            continue
         if got[tag] != ref[tag]:
             a, b = np.frombuffer(got[tag], np.uint32), np.frombuffer(ref[tag], np.uint32)
             bad = np.flatnonzero(a != b)
