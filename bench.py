@@ -1,18 +1,24 @@
 #!/usr/bin/env python3
 """bench.py -- GSM bursts/s through the receive hot path (RX resample -> slot cut -> detect -> DFE).
 
-Workload (BASELINE.json configs[1]): one ARFCN x 8 timeslots, a continuous 400 kS/s complex stream of
-~10^5 TDMA frames (855 blocks of 117 frames = 100 035 frames = 800 280 normal bursts = 213 750 resampler
-chunks = 1.48 GB of complex64), TSC 0, SNR 20 dB, synthetic.  A step = one pass over that stream.
-With --gpus N every rank processes its own stream of that size (weak scaling, no data-path collective).
+Headline workload (BASELINE.json configs[1]): one ARFCN x 8 timeslots, a continuous 400 kS/s stream of ~10^5 TDMA
+frames (855 blocks of 117 frames = 100 035 frames = 800 280 normal bursts = 213 750 resampler chunks = 1.48 GB of
+complex64), TSC 0, SNR 20 dB, synthetic, every sample an int16 value as an ADC delivers it.  A step = one pass over that
+stream.  With --gpus N every rank processes its own stream of that size (weak scaling, no data-path collective).
 
-  value : whole-job bursts/s, inputs resident in HBM, timed with CUDA events on the launching stream
-  e2e   : the same through the host-buffer C-ABI call btsdsp_rx_stream_host (pinned host input,
-          H2D + kernels + D2H of soft bits inside the timed region)
-  roofline : the dominant kernel's algorithmic HBM bytes / its event-timed duration vs the measured peak;
-             `kernels` lists both kernels of the step
-  cpu_baseline : the compiled reference (oracle/_ref) or its C port on the host cores, same stream
-  --impl reference : only that CPU arm, as its own JSON line
+  value        whole-job bursts/s, complex-float input resident in HBM, CUDA events on the launching stream
+  e2e          the same through the reference-facing host-buffer call at the formats the reference's radio and socket
+               boundaries carry (int16 {I,Q} in, radioInterface.cpp:213-227; 148 soft bytes out, Transceiver.cpp:659-674):
+               btsdsp_rx_stream_wire_host, pinned host buffers, H2D + kernels + D2H inside the timed region; with the
+               copy-only time of the very same call beside it (`copy_ms`: same buffers, segments, streams, no kernels)
+  e2e_cf32     the same through btsdsp_rx_stream_host (complex-float in, float soft bits out)
+  roofline     per kernel: algorithmic HBM bytes and algorithmic unfused-FP32 lane-ops over the kernel's
+               event-timed duration, against the measured HBM peak and SMs x 128 lanes x the SM clock sampled in this run;
+               `bound` names the roof that binds the kernel; the top-level fields are the dominant kernel's
+  cpu_baseline the compiled reference (oracle/_ref) on the host cores over the same int16 stream; its outputs are compared
+               with the GPU's bit for bit (`check.vs_reference`)
+  secondary    configs 3, 4 (N = 1) and 5 (every N: ARFCN-sharded TX + RX chains, SoftVector gather, union checked)
+  --impl reference : only the CPU arm, as its own JSON line
 """
 import argparse
 import json
@@ -30,15 +36,23 @@ sys.path.insert(0, ROOT)
 BLOCK_BURSTS, BLOCK_CHUNKS = 936, 250           # 117 frames: lcm of 625-sample slot groups and 585-sample chunks
 DEFAULT_BLOCKS = 855                            # 100 035 frames ~ BASELINE's 10^5
 SOFT_PITCH = 148
-# algorithmic HBM bytes (SURVEY 8d / DESIGN.md): per chunk 864 in + 585 out complex64; per burst 1250 B of
+# ---- algorithmic HBM bytes (SURVEY 8d / DESIGN.md 5): per chunk 864 in + 585 out complex64; per burst 1250 B of
 # resampled samples in (156.25 x 8) + 148 soft f32 + flag/toa/amp (16 B) out
 RESAMPLE_BYTES_PER_CHUNK = (864 + 585) * 8
 DEMOD_BYTES_PER_BURST = 1250 + 148 * 4 + 16
 FUSED_BYTES_PER_BURST = 1846.2 + 608            # the ideal single-pass figure (raw in, soft out)
+RACH_BYTES_PER_BURST = 1256 + 16
+# ---- algorithmic FP32 lane-operations, every multiply and every add counted once (the reference rounds them
+# separately, so nothing may be contracted into an FMA; DESIGN.md 5 derives each figure)
+RESAMPLE_OPS_PER_CHUNK = 9 * 961 * 4            # every period of 65 outputs uses each of the 961 taps once, complex x real
+DETECT_OPS_PER_BURST = 13000 + 3700             # analyzeTrafficBurst + designDFE(Nf 7, nu 5)
+EQUALIZE_OPS_PER_BURST = 30000                  # 1/amp scale + 21-tap delay + 7-tap feed-forward + 5-tap feedback + rotate/slice
+RACH_OPS_PER_BURST = 55000
+LANES_PER_SM = 128
 
 
-def ncu_traffic(blocks):
-    """dram bytes per launch from the committed ncu capture of this same command (profiles/*_traffic.json), or {}"""
+def ncu_profile(blocks):
+    """figures of the committed ncu capture of this same command (profiles/*_traffic.json), or {} -- static, labelled so"""
     import glob
     best = {}
     for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))):
@@ -47,10 +61,7 @@ def ncu_traffic(blocks):
         except Exception:
             continue
         if d.get("blocks") == blocks:
-            best = {k: v.get("dram_bytes") for k, v in d.get("kernels", {}).items()}
-            best["_pipes"] = {k: {m: v[m] for m in ("issue_active_pct", "fma_pipe_active_pct") if m in v}
-                              for k, v in d.get("kernels", {}).items()}
-            best["_source"] = os.path.basename(f)
+            best = {"file": os.path.basename(f), "kernels": d.get("kernels", {})}
     return best
 
 
@@ -97,23 +108,27 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_arm(raw, nblocks, tsc, threads, repeat=1):
-    """the reference's CPU path over the first nblocks blocks of `raw` (complex64 numpy); returns (bursts/s, kind)"""
+def cpu_arm(iq, nblocks, tsc, threads, repeat=1, keep=False):
+    """the reference's CPU path over the first nblocks blocks of the int16 radio stream `iq` (n, 2): unUSRPifyVector +
+    pullBuffer's 65/96 resample, slot cutting, analyzeTrafficBurst + designDFE + equalizeBurst per burst, and the
+    datagram's soft bytes.  Returns (bursts/s, kind, seconds, outputs or None)."""
     from oracle.oracle import Oracle
     o = Oracle("best", sps=1)
     nb, nch = nblocks * BLOCK_BURSTS, nblocks * BLOCK_CHUNKS
-    best = None
+    best, out = None, None
     for _ in range(repeat):
         t0 = time.perf_counter()
-        res = o.rx_resample_stream(raw[:nch * 864], threads=threads)
-        o.rx_stream_demod(res, nb, tsc[:nb], threads=threads)
+        res = o.rx_resample_stream_i16(iq[:nch * 864], False, threads=threads)
+        r = o.rx_stream_demod(res, nb, tsc[:nb], threads=threads)
+        r["soft_u8"] = o.soft_to_wire(r["soft"], threads=threads)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return nb / best, ("reference" if o.kind == "ref" else "port"), best
+        out = r if keep else None
+    return nb / best, ("reference" if o.kind == "ref" else "port"), best, out
 
 
 def make_stream_cpu(nblocks, seed):
-    """reference arm without a GPU: build the stream with the oracle itself"""
+    """reference arm without a GPU: build the int16 stream with the oracle itself"""
     from oracle.oracle import Oracle
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import synth
@@ -124,10 +139,9 @@ def make_stream_cpu(nblocks, seed):
     bits[:, :3] = 0; bits[:, 145:] = 0
     bits[:, 61:87] = synth.bits_of(synth.TSC[0])
     th = os.cpu_count() or 1
-    iq = o.tx_resample_stream(o.modulate_stream(bits, threads=th), threads=th)
-    raw = (iq[:, 0] + 1j * iq[:, 1]).astype(np.complex64)
-    raw += (955.0 * (rng.standard_normal(raw.size) + 1j * rng.standard_normal(raw.size))).astype(np.complex64)
-    return raw
+    iq = o.tx_resample_stream(o.modulate_stream(bits, threads=th), threads=th).astype(np.float32)
+    iq += 955.0 * rng.standard_normal(iq.shape).astype(np.float32)
+    return np.clip(np.rint(iq), -32768, 32767).astype(np.int16)
 
 
 def run_reference(args, rank):
@@ -136,18 +150,19 @@ def run_reference(args, rank):
     cores = os.cpu_count() or 1
     # bounded sample: 400 blocks = 374 400 bursts ~ 12 core-seconds of the reference per step
     nblocks = max(2, min(args.blocks, 400))
-    raw = make_stream_cpu(nblocks, 0xB2000002)
+    iq = make_stream_cpu(nblocks, 0xB2000002)
     tsc = np.zeros(nblocks * BLOCK_BURSTS, np.uint8)
     for _ in range(args.warmup):
-        cpu_arm(raw, min(nblocks, 4), tsc, cores)
+        cpu_arm(iq, min(nblocks, 4), tsc, cores)
     times = []
     kind = "port"
     for _ in range(args.steps):
-        v, kind, dt = cpu_arm(raw, nblocks, tsc, cores)
+        v, kind, dt, _ = cpu_arm(iq, nblocks, tsc, cores)
         times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = nblocks * BLOCK_BURSTS / (ms / 1e3)
-    sample = "%d of %d blocks of 117 frames (%d bursts) per step" % (nblocks, args.blocks, nblocks * BLOCK_BURSTS)
+    sample = "%d of %d blocks of 117 frames (%d bursts) per step, int16 samples in, soft bytes out" % (
+        nblocks, args.blocks, nblocks * BLOCK_BURSTS)
     emit(json.dumps({
         "impl": "reference", "metric": "GSM bursts/sec (resample+detect+DFE)", "value": value, "unit": "bursts/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -175,6 +190,208 @@ _REAL_STDOUT = os.dup(1)
 os.dup2(2, 1)
 
 
+def same_bits(a, b):
+    """bit-for-bit equality of two arrays of one dtype (NaN == NaN)"""
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and bool(np.all((a == b) | ((a != a) & (b != b))))
+
+
+def timeit(torch, stream, fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(reps):
+        fn()
+    b.record(stream)
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def kernel_entry(name, ms, bytes_, ops, peak_gbs, fp32_peak, bound):
+    k = {"name": name, "ms": ms, "bound": bound, "algorithmic_bytes": int(bytes_), "algorithmic_fp32_lane_ops": int(ops)}
+    k["achieved_gbs"] = bytes_ / (ms * 1e-3) / 1e9
+    k["hbm_frac"] = k["achieved_gbs"] / peak_gbs
+    k["achieved_fp32_tops"] = ops / (ms * 1e-3) / 1e12
+    k["fp32_frac"] = k["achieved_fp32_tops"] * 1e12 / fp32_peak if fp32_peak else None
+    k["frac"] = k["hbm_frac"] if bound == "hbm" else k["fp32_frac"]
+    return k
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# secondary legs
+# ---------------------------------------------------------------------------------------------------------------------
+def leg_config3(torch, dsp, dev, stream, peak, fp32_peak, cores, quick):
+    """config 3: RACH access-burst detection sweep, 64 TOA offsets x 26 SNRs (-5..20 dB) x 601 = 1 000 064 bursts"""
+    from tools import workloads
+    bursts, d_int, snr = workloads.rach_sweep(dsp, dev, per_cell=61 if quick else 601, stream=stream)
+    n = bursts.shape[0]
+    flag = torch.zeros(n, dtype=torch.int32, device=dev)
+    amp = torch.zeros(n * 2, device=dev)
+    toa = torch.zeros(n, device=dev)
+    soft = torch.zeros(n * 160, device=dev)
+    ms_det = timeit(torch, stream, lambda: dsp.rach_dev(bursts, 160, n, flag, amp, toa, None, 160, stream=stream))
+    ms_all = timeit(torch, stream, lambda: dsp.rach_dev(bursts, 160, n, flag, amp, toa, soft, 160, stream=stream))
+    out = {"what": "detectRACHBurst sweep: 64 TOA x 26 SNR (-5..20 dB) x %d access bursts, one launch" % (n // (64 * 26)),
+           "bursts": n, "ms": ms_det, "bursts_per_s": n / ms_det * 1e3,
+           "roofline": kernel_entry("k_rach_detect", ms_det, n * RACH_BYTES_PER_BURST, n * RACH_OPS_PER_BURST, peak, fp32_peak,
+                                    "fp32-unfused"),
+           "with_demodulateBurst": {"ms": ms_all, "bursts_per_s": n / ms_all * 1e3}}
+    f = flag.bool()
+    out["detected_by_snr_db"] = {str(int(s)): float(f[snr == s].float().mean()) for s in (-5, 0, 5, 10, 20)}
+    err = (toa - (d_int.to(torch.float32) + 0.5)).abs()
+    out["toa_within_1_symbol_of_truth_when_detected_snr_ge_10"] = float((err[f & (snr >= 10)] <= 1.0).float().mean())
+    # parity with the compiled reference on a strided sample that covers every (TOA, SNR) cell
+    from oracle.oracle import Oracle
+    o = Oracle("best", sps=1)
+    ns = min(n, 65536)
+    idx = torch.arange(ns, device=dev) * (n // ns)
+    hb = torch.view_as_complex(bursts[idx]).cpu().numpy()
+    lens = np.where((idx.cpu().numpy() % 4) == 0, 157, 156).astype(np.int32)
+    r = o.rx_rach_batch(hb, lens, 5.0, threads=cores)
+    g_soft = soft.reshape(n, 160)[idx].cpu().numpy()
+    g_soft[np.arange(ns)[:, None] * 0 + np.arange(160)[None, :] >= lens[:, None]] = 0
+    r_soft = r["soft"].copy()
+    r_soft[np.arange(160)[None, :] >= lens[:, None]] = 0
+    out["check"] = {"vs": o.kind, "bursts": int(ns),
+                    "identical": bool(same_bits(flag[idx].cpu().numpy(), r["flag"]) and same_bits(toa[idx].cpu().numpy(), r["toa"])
+                                      and same_bits(amp.reshape(n, 2)[idx].cpu().numpy(), r["amp"].view(np.float32).reshape(ns, 2))
+                                      and same_bits(g_soft, r_soft))}
+    return out
+
+
+def leg_config4(torch, dsp, dev, stream, peak, fp32_peak, cores, quick):
+    """config 4: 1024 ARFCN x 8 TS normal bursts per frame, mixed TSC, 128 frames; 8192 per launch and as one launch"""
+    from tools import workloads
+    frames = 16 if quick else 128
+    bursts, tsc, bits, occ = workloads.normal_batch(dsp, dev, 1024, frames, stream=stream)
+    n = bursts.shape[0]
+    flag = torch.zeros(n, dtype=torch.int32, device=dev)
+    amp = torch.zeros(n * 2, device=dev)
+    toa = torch.zeros(n, device=dev)
+    soft = torch.zeros(n * SOFT_PITCH, device=dev)
+
+    def per_frame():
+        for f in range(frames):
+            lo = f * 8192
+            dsp.demod_normal_dev(bursts[lo:lo + 8192], 160, tsc[lo:lo + 8192], 8192, flag[lo:lo + 8192], amp[2 * lo:2 * lo + 16384],
+                                 toa[lo:lo + 8192], soft[lo * SOFT_PITCH:(lo + 8192) * SOFT_PITCH], SOFT_PITCH, first=lo, stream=stream)
+    ms_pf = timeit(torch, stream, per_frame, reps=3, warm=1)
+    ms_one = timeit(torch, stream, lambda: dsp.demod_normal_dev(bursts, 160, tsc, n, flag, amp, toa, soft, SOFT_PITCH, stream=stream))
+    dsp.set_timing(True)
+    dsp.demod_normal_dev(bursts, 160, tsc, n, flag, amp, toa, soft, SOFT_PITCH, stream=stream)
+    torch.cuda.synchronize()
+    ms_det, ms_eq = dsp.get_timing()
+    dsp.set_timing(False)
+    hard = (soft.reshape(n, SOFT_PITCH) > 0.5).to(torch.uint8)
+    det = flag.bool()
+    out = {"what": "wideband batch: %d frames x 1024 ARFCN x 8 TS normal bursts, TSC = ARFCN mod 8, amp 500..8000, delay U[0,3), "
+                   "2-tap channel on half the ARFCNs, SNR U[10,30] dB, 5 %% empty slots" % frames,
+           "bursts": n,
+           "per_frame_launches": {"bursts_per_launch": 8192, "launches": frames, "ms_per_launch": ms_pf / frames,
+                                  "bursts_per_s": n / ms_pf * 1e3},
+           "one_launch": {"ms": ms_one, "bursts_per_s": n / ms_one * 1e3, "detect_ms": ms_det, "equalize_ms": ms_eq},
+           "roofline": kernel_entry("k_detect_design + k_equalize_fast", ms_one, n * DEMOD_BYTES_PER_BURST,
+                                    n * (DETECT_OPS_PER_BURST + EQUALIZE_OPS_PER_BURST), peak, fp32_peak, "fp32-unfused"),
+           "detected_of_occupied": float(det[occ].float().mean()), "detected_of_empty": float(det[~occ].float().mean()),
+           "ber_detected": float((hard[det] != bits[det]).float().mean()),
+           # the reference's own quirk (SURVEY F6): midambles whose autocorrelation peak interpolates to 8 - 1/512 put the
+           # channel window one symbol off, and the DFE then fails on TSC 1, 3, 4, 5 -- identically in both implementations
+           "ber_detected_by_tsc": {str(t): float((hard[det & (tsc == t)] != bits[det & (tsc == t)]).float().mean()) for t in range(8)}}
+    from oracle.oracle import Oracle
+    o = Oracle("best", sps=1)
+    ns = min(n, 65536)
+    idx = torch.arange(ns, device=dev) * (n // ns) + (torch.arange(ns, device=dev) % 8)      # every TN and TSC
+    idx = idx.clamp_(max=n - 1)
+    hb = torch.view_as_complex(bursts[idx]).cpu().numpy()
+    hi = idx.cpu().numpy()
+    lens = np.where((hi % 4) == 0, 157, 156).astype(np.int32)
+    r = o.rx_normal_batch(hb, lens, tsc[idx].cpu().numpy(), threads=cores, debug=False)
+    out["check"] = {"vs": o.kind, "bursts": int(ns),
+                    "identical": bool(same_bits(flag[idx].cpu().numpy(), r["flag"]) and same_bits(toa[idx].cpu().numpy(), r["toa"])
+                                      and same_bits(amp.reshape(n, 2)[idx].cpu().numpy(), r["amp"].view(np.float32).reshape(ns, 2))
+                                      and same_bits(soft.reshape(n, SOFT_PITCH)[idx].cpu().numpy(), r["soft"][:, :SOFT_PITCH]))}
+    return out
+
+
+def leg_config5(torch, dist, dsp, dev, stream, rank, world, quick):
+    """config 5: 1024 ARFCNs, each a TX chain (148-bit bursts -> modulateBurst -> 96/65 resample -> int16) and an RX chain
+    (int16 -> 65/96 resample -> detect + DFE) over one 117-frame block, ARFCN a on rank a mod G, SoftVector gather,
+    union compared with the single-GPU run of all ARFCNs on rank 0"""
+    from tools import workloads as wl
+    from openbts_ttsou_b200 import shard
+    A = 128 if quick else 1024
+    NB, NCH = wl.BURSTS_PER_ARFCN, wl.CHUNKS_PER_ARFCN
+
+    def chains(arfcns):
+        na = len(arfcns)
+        bits, tsc = wl.arfcn_bits(arfcns, dev)
+        iq_tx = torch.zeros((na, NCH * 864 * 2), dtype=torch.int16, device=dev)
+        dsp.tx_streams_dev(bits, NB, na, iq_tx, stream=stream)
+        torch.cuda.synchronize()
+        iq_rx = wl.arfcn_air(iq_tx, arfcns, dev)
+        res = torch.zeros(na * NCH * 585 * 2, dtype=torch.float32, device=dev)
+        n = na * NB
+        o = {"flag": torch.zeros(n, dtype=torch.int32, device=dev), "amp": torch.zeros(n * 2, device=dev),
+             "toa": torch.zeros(n, device=dev), "soft": torch.zeros((n, SOFT_PITCH), device=dev)}
+
+        def step():
+            dsp.tx_streams_dev(bits, NB, na, iq_tx, stream=stream)
+            dsp.resample_rx_i16_streams_dev(iq_rx, NCH * 864, na, NCH, res, NCH * 585, stream=stream)
+            dsp.demod_normal_dev(res, 0, tsc, n, o["flag"], o["amp"], o["toa"], o["soft"], SOFT_PITCH, stream=stream)
+        return step, o, bits, n
+
+    mine = shard.arfcn_shard(A, rank, world)
+    step, o, bits, n = chains(mine)
+    step()
+    torch.cuda.synchronize()
+    wrong = ((o["soft"] > 0.5).to(torch.uint8) != bits.reshape(n, 148)).float().mean(dim=1)
+    tsc_of = torch.from_numpy(np.asarray(mine) % 8).to(dev).repeat_interleave(NB)
+    ber = {str(t): float(wrong[tsc_of == t].mean()) for t in range(8) if bool((tsc_of == t).any())}   # TSC 1,3,4,5: SURVEY F6
+    if world > 1:
+        dist.barrier()
+    l0 = dsp.launch_count
+    reps = 10
+    ms = timeit(torch, stream, step, reps=reps, warm=2)
+    launches = (dsp.launch_count - l0) // (reps + 2)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    total = A * NB
+    out = {"what": "%d ARFCNs x (fused TX chain + int16 RX resample + normal-burst demod) over 117 frames each, ARFCN a on rank "
+                   "a mod %d" % (A, world), "arfcns": A, "arfcns_per_rank": len(mine), "bursts": total, "ms": ms,
+           "bursts_per_s": total / ms * 1e3, "kernel_launches_per_step": int(launches), "ber_by_tsc": ber,
+           "detected": float(o["flag"].float().mean())}
+    if world > 1:
+        g = lambda: shard.gather_soft(o["soft"], counts="equal")      # noqa: E731
+        parts = g()
+        gms = timeit(torch, torch.cuda.current_stream(), g, reps=10, warm=2)
+        t = torch.tensor([gms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gbytes = n * SOFT_PITCH * 4
+        out["gather"] = {"what": "all_gather of every rank's SoftVectors (148 f32 per burst) over NCCL, one collective",
+                         "bytes_per_rank": gbytes, "ms": float(t.item()),
+                         "recv_gbs_per_rank": (world - 1) * gbytes / (float(t.item()) * 1e-3) / 1e9}
+        full = {k: shard.gather_soft(v.reshape(n, -1), counts="equal") for k, v in o.items() if k != "soft"}
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        if rank == 0:
+            step1, o1, _, n1 = chains(np.arange(A))
+            step1()
+            torch.cuda.synchronize()
+            same = True
+            for r in range(world):
+                rows = torch.from_numpy(shard.burst_rows_of_arfcns(shard.arfcn_shard(A, r, world), NB)).to(dev)
+                same = same and bool(torch.equal(parts[r], o1["soft"][rows]))
+                for k in ("flag", "amp", "toa"):
+                    same = same and bool(torch.equal(full[k][r], o1[k].reshape(n1, -1)[rows]))
+            out["union_equals_single_gpu_run"] = same
+            del o1
+        dist.barrier()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -184,6 +401,8 @@ def main():
     ap.add_argument("--blocks", type=int, default=DEFAULT_BLOCKS, help="117-frame blocks per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="small secondary legs (debugging aid; the default sizes are BASELINE's)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -206,9 +425,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
     dsp = pkg.BtsDsp(local, 1)
+    cores = os.cpu_count() or 1
 
     nb, nch = args.blocks * BLOCK_BURSTS, args.blocks * BLOCK_CHUNKS
-    # ---- synthetic stream, built on the device with the product's own TX path (parity-tested)
+    # ---- synthetic stream, built on the device with the product's own TX path (parity-tested); every sample is an int16
+    #      value (signal + AWGN, rounded as an ADC does), held as complex float for the device path
     g = torch.Generator(device=dev)
     g.manual_seed(0xB2000002 + rank)
     bits = torch.randint(0, 2, (nb, 148), generator=g, device=dev, dtype=torch.uint8)
@@ -222,6 +443,7 @@ def main():
     raw = iq.to(torch.float32)
     del iq
     raw.add_(torch.randn(raw.numel(), generator=g, device=dev), alpha=955.0)     # SNR 20 dB at amplitude 13500
+    raw.round_().clamp_(-32768, 32767)
     tsc = torch.zeros(nb, dtype=torch.uint8, device=dev)
     res = torch.empty(nch * 585 * 2, dtype=torch.float32, device=dev)
     flag = torch.zeros(nb, dtype=torch.int32, device=dev)
@@ -283,169 +505,145 @@ def main():
     ms_step = float(tmax.item()) / args.steps
     value = world * nb / (ms_step / 1e3)
 
-    # ---- e2e: host buffers through btsdsp_rx_stream_host
-    e2e = None
+    def host_leg(call, h2d, d2h):
+        """times `call` (a synchronous host-buffer C-ABI call) and then its copies alone, max over ranks"""
+        ke = max(3, min(args.steps, 10))
+
+        def timed():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(ke):
+                call()
+            torch.cuda.synchronize()
+            dt = torch.tensor([(time.perf_counter() - t0) / ke], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            return float(dt.item())
+        for _ in range(2):
+            call()
+        t = timed()
+        dsp.set_copy_only(True)
+        call()
+        tc = timed()
+        dsp.set_copy_only(False)
+        call()                                    # leaves real results in the host buffers
+        return {"value": world * nb / t, "unit": "bursts/s", "ms_per_step": 1e3 * t, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "copy_ms": 1e3 * tc, "frac_of_copy_roof": tc / t,
+                "copy_h2d_gbs_per_gpu": h2d / tc / 1e9, "copy_d2h_gbs_per_gpu": d2h / tc / 1e9}
+
+    # ---- e2e at the reference's wire formats: int16 {I,Q} in, 148 soft bytes out (btsdsp_rx_stream_wire_host)
+    e2e, e2e_cf32, u8_h = None, None, None
+    tsc_h = np.zeros(nb, np.uint8)
     if not args.no_e2e:
-        raw_h = torch.empty(raw.numel(), dtype=torch.float32, pin_memory=True)
-        raw_h.copy_(raw)
-        tsc_h = np.zeros(nb, np.uint8)
         flag_h = torch.empty(nb, dtype=torch.int32, pin_memory=True)
         amp_h = torch.empty(nb * 2, dtype=torch.float32, pin_memory=True)
         toa_h = torch.empty(nb, dtype=torch.float32, pin_memory=True)
-        soft_h = torch.empty(nb * SOFT_PITCH, dtype=torch.float32, pin_memory=True)
-
-        def e2e_step():
-            dsp.rx_stream_host(raw_h, nch, tsc_h, nb, flag_h, amp_h, toa_h, soft_h, SOFT_PITCH)
-        for _ in range(2):
-            e2e_step()
-        same = bool(torch.equal(soft_h, soft.cpu())) and bool(torch.equal(toa_h, toa.cpu()))
-        ke = max(3, min(args.steps, 10))
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(ke):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = torch.tensor([(time.perf_counter() - t0) / ke], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * nb / float(dt.item()), "unit": "bursts/s", "ms_per_step": 1e3 * float(dt.item()),
-               "h2d_bytes_per_step": int(raw.numel() * 4 + nb), "d2h_bytes_per_step": int(nb * (SOFT_PITCH * 4 + 16)),
-               "matches_device_path": same, "api": "btsdsp_rx_stream_host (pinned host buffers)"}
-
-    # ---- e2e at the reference's wire formats: int16 {I,Q} in, 148 soft bytes out (btsdsp_rx_stream_wire_host).
-    #      The stream is re-quantised to int16 (what an ADC delivers), so it is its own input, checked by its own BER.
-    e2e_wire = None
-    if not args.no_e2e:
         iq_h = torch.empty(raw.numel(), dtype=torch.int16, pin_memory=True)
-        iq_h.copy_(raw.round().clamp_(-32768, 32767).to(torch.int16))
+        iq_h.copy_(raw.to(torch.int16))
         u8_h = torch.empty(nb * 148, dtype=torch.uint8, pin_memory=True)
-
-        def wire_step():
-            dsp.rx_stream_wire_host(iq_h, nch, tsc_h, nb, flag_h, amp_h, toa_h, u8_h)
-        for _ in range(2):
-            wire_step()
-        wire_ber = float(((u8_h.reshape(nb, 148) > 127).to(torch.uint8) != bits.cpu()).float().mean())
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(ke):
-            wire_step()
-        torch.cuda.synchronize()
-        dt = torch.tensor([(time.perf_counter() - t0) / ke], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e_wire = {"value": world * nb / float(dt.item()), "unit": "bursts/s", "ms_per_step": 1e3 * float(dt.item()),
-                    "h2d_bytes_per_step": int(raw.numel() * 2 + nb), "d2h_bytes_per_step": int(nb * (148 + 16)),
-                    "ber_tsc0": wire_ber, "detected": float(flag_h.float().mean()),
-                    "api": "btsdsp_rx_stream_wire_host (int16 I/Q in, 148 soft bytes + flag/amp/toa out, pinned host buffers)"}
+        e2e = host_leg(lambda: dsp.rx_stream_wire_host(iq_h, nch, tsc_h, nb, flag_h, amp_h, toa_h, u8_h),
+                       raw.numel() * 2 + nb, nb * (148 + 16))
+        want_u8 = torch.floor(soft.reshape(nb, SOFT_PITCH).double() * 255.0 + 0.5).to(torch.uint8).cpu()   # (char) round(soft*255.0)
+        e2e["matches_device_path"] = bool(torch.equal(u8_h.reshape(nb, 148), want_u8) and torch.equal(toa_h, toa.cpu())
+                                          and torch.equal(flag_h, flag.cpu()) and torch.equal(amp_h, amp.cpu()))
+        e2e["api"] = ("btsdsp_rx_stream_wire_host: int16 {I,Q} samples in (radioInterface.cpp:213-227), 148 soft bytes + "
+                      "flag/amp/toa out (Transceiver.cpp:659-674), pinned host buffers")
+        del want_u8
+        # ---- the same through the complex-float call
+        raw_h = torch.empty(raw.numel(), dtype=torch.float32, pin_memory=True)
+        raw_h.copy_(raw)
+        soft_h = torch.empty(nb * SOFT_PITCH, dtype=torch.float32, pin_memory=True)
+        e2e_cf32 = host_leg(lambda: dsp.rx_stream_host(raw_h, nch, tsc_h, nb, flag_h, amp_h, toa_h, soft_h, SOFT_PITCH),
+                            raw.numel() * 4 + nb, nb * (SOFT_PITCH * 4 + 16))
+        e2e_cf32["matches_device_path"] = bool(torch.equal(soft_h, soft.cpu()) and torch.equal(toa_h, toa.cpu())
+                                               and torch.equal(flag_h, flag.cpu()) and torch.equal(amp_h, amp.cpu()))
+        e2e_cf32["api"] = "btsdsp_rx_stream_host: complex-float samples in, float soft bits out, pinned host buffers"
+        del raw_h, soft_h
     clocks = sampler.stop() if sampler else None
 
-    # ---- optional gather of SoftVectors over NCCL (outside the timed path, reported separately)
-    gather = None
-    if world > 1:
-        from openbts_ttsou_b200.shard import gather_soft
-        part = soft[:8192 * SOFT_PITCH].reshape(8192, SOFT_PITCH)
-        gather_soft(part)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(10):
-            gather_soft(part)
-        b.record()
-        torch.cuda.synchronize()
-        gather = {"what": "all_gather of 8192 SoftVectors (148 f32) per rank over NCCL", "ms": a.elapsed_time(b) / 10}
-
-    # ---- the other entry points, live and device-resident (rank 0, N = 1 only; reported next to the headline,
-    #      not part of it): fused TX chain, caller-policy pull, XCCH block decode
-    secondary = None
-    if rank == 0 and world == 1 and not args.no_e2e:
-        def timeit(fn, reps=5):
-            fn(); fn()
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            for _ in range(reps):
-                fn()
-            b.record(stream)
-            torch.cuda.synchronize()
-            return a.elapsed_time(b) / reps
-        secondary = {}
-        ntx = min(nb, 936 * 256)
-        iq2 = torch.empty(ntx // 4 * 625 // 585 * 864 * 2, dtype=torch.int16, device=dev)
-        ms = timeit(lambda: dsp.tx_stream_dev(bits, ntx, iq2, stream=stream))
-        secondary["tx_chain_bits_to_int16"] = {"bursts": ntx, "ms": ms, "bursts_per_s": ntx / ms * 1e3}
-        A, F = 1024, 32
-        npol = A * 8 * F
-        if nb >= npol:
-            ct = np.ones((A, 8), np.uint8)
-            ct[:, 0] = 5
-            trx = dsp.trx_create(np.zeros(A, np.uint8), ct, 0)
-            # A parallel slot streams of F frames each, cut by address out of the resampled stream (F*1250 samples apart)
-            pv = torch.zeros(npol, dtype=torch.int32, device=dev)
-            pd = torch.zeros(npol * 160, dtype=torch.uint8, device=dev)
-            fnc = [0]
-
-            def pull():
-                dsp.trx_pull_streams_dev(trx, res, F * 1250, F, fnc[0], pv, pd, 160, stream=stream)
-                fnc[0] += F
-            ms = timeit(pull)
-            secondary["policy_pull_1024_arfcn"] = {"bursts": npol, "ms": ms, "bursts_per_s": npol / ms * 1e3,
-                                                   "valid": float(pv.float().mean())}
-            # the pull's soft bytes, four bursts per frame, through the XCCH block decoder
-            nfr = npol // 4
-            fu = torch.zeros(nfr * 228, dtype=torch.uint8, device=dev)
-            fok = torch.zeros(nfr, dtype=torch.int32, device=dev)
-            ms = timeit(lambda: dsp.xcch_decode_dev(pd[8:], 160, nfr, fu, fok, stream=stream))
-            secondary["xcch_decode"] = {"frames": nfr, "ms": ms, "bursts_per_s": npol / ms * 1e3}
-            dsp.trx_destroy(trx)
-        del iq2
-
-    # ---- CPU baseline on the same stream (rank 0, N = 1 only)
-    cpu = None
+    # ---- CPU baseline on the same stream (rank 0, N = 1 only), its outputs compared with the GPU's
+    cpu, vs_ref = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
         nblk = max(2, min(args.blocks, int(20 * 3.0e4 * cores / BLOCK_BURSTS)))
-        raw_np = raw[:nblk * BLOCK_CHUNKS * 864 * 2].cpu().numpy().view(np.complex64)
-        v, kind, dt = cpu_arm(raw_np, nblk, np.zeros(nblk * BLOCK_BURSTS, np.uint8), cores, repeat=2)
+        n1 = nblk * BLOCK_BURSTS
+        iq_np = raw[:nblk * BLOCK_CHUNKS * 864 * 2].to(torch.int16).cpu().numpy().reshape(-1, 2)
+        v, kind, dt, r = cpu_arm(iq_np, nblk, np.zeros(n1, np.uint8), cores, repeat=2, keep=True)
         cpu = {"value": v, "unit": "bursts/s", "cores": cores, "kind": kind, "seconds": dt,
-               "sample": "first %d of %d blocks of 117 frames (%d bursts), best of 2" % (nblk, args.blocks, nblk * BLOCK_BURSTS)}
+               "sample": "first %d of %d blocks of 117 frames (%d bursts), int16 samples in, soft bytes out, best of 2" % (
+                   nblk, args.blocks, n1)}
+        vs_ref = {"vs": kind, "bursts": int(n1),
+                  "flag": same_bits(flag[:n1].cpu().numpy(), r["flag"]),
+                  "toa": same_bits(toa[:n1].cpu().numpy(), r["toa"]),
+                  "amp": same_bits(amp[:2 * n1].cpu().numpy(), r["amp"].view(np.float32)),
+                  "soft": same_bits(soft[:n1 * SOFT_PITCH].cpu().numpy().reshape(n1, SOFT_PITCH), r["soft"][:, :SOFT_PITCH])}
+        if u8_h is not None:
+            vs_ref["soft_bytes_of_the_wire_call"] = same_bits(u8_h[:n1 * 148].numpy().reshape(n1, 148), r["soft_u8"])
+        vs_ref["identical"] = all(v for k, v in vs_ref.items() if k not in ("vs", "bursts"))
+        del r, iq_np
+
+    # ---- rooflines of the step's kernels
+    peak, how = measured_peaks()
+    sm_mhz = (clocks or {}).get("sm_mhz") or 0.0
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    fp32_peak = sms * LANES_PER_SM * sm_mhz * 1e6            # unfused lane-ops per second at the clock this run held
+
+    # ---- the other configs (3 and 4 on rank 0 at N = 1; 5 at every N)
+    secondary = None
+    if not args.no_secondary:
+        del raw, res, soft
+        torch.cuda.empty_cache()
+        secondary = {}
+        if world == 1:
+            secondary["config3_rach_sweep"] = leg_config3(torch, dsp, dev, stream, peak, fp32_peak, cores, args.quick)
+            torch.cuda.empty_cache()
+            secondary["config4_wideband_batch"] = leg_config4(torch, dsp, dev, stream, peak, fp32_peak, cores, args.quick)
+            torch.cuda.empty_cache()
+        secondary["config5_arfcn_sharded_tx_rx"] = leg_config5(torch, dist, dsp, dev, stream, rank, world, args.quick)
 
     if rank == 0:
-        peak, how = measured_peaks()
-        k_res = {"name": "k_resample_rx_v3", "ms": ms_res, "algorithmic_bytes": nch * RESAMPLE_BYTES_PER_CHUNK}
+        k_res = kernel_entry("k_resample_rx_v3", ms_res, nch * RESAMPLE_BYTES_PER_CHUNK, nch * RESAMPLE_OPS_PER_CHUNK, peak,
+                             fp32_peak, "hbm")
         # k_detect_design reads the 36-sample midamble window (288 B) and writes flag/amp/toa (16 B) + the 112 B
         # EqParams record; k_equalize_fast reads the burst (1250 B) + EqParams and writes 148 soft bits
-        k_det = {"name": "k_detect_design", "ms": ms_det, "algorithmic_bytes": nb * (288 + 16 + 112)}
-        k_eq = {"name": "k_equalize_fast", "ms": ms_eq, "algorithmic_bytes": nb * (1250 + 112 + 148 * 4)}
-        k_dem = {"name": "demod (detect_design + equalize_fast)", "ms": ms_dem, "algorithmic_bytes": nb * DEMOD_BYTES_PER_BURST}
-        traffic = ncu_traffic(args.blocks)
-        k_res["traffic"] = traffic.get("k_resample_rx_v3")
-        k_det["traffic"] = traffic.get("k_detect_design")
-        k_eq["traffic"] = traffic.get("k_equalize_fast")
-        for k in (k_res, k_det, k_eq):          # FP32-pipe / issue utilisation from the committed ncu capture (static)
-            k.update({"ncu_" + m: v for m, v in traffic.get("_pipes", {}).get(k["name"], {}).items()})
-        for k in (k_res, k_det, k_eq, k_dem):
-            k["achieved_gbs"] = k["algorithmic_bytes"] / (k["ms"] * 1e-3) / 1e9
-            k["frac"] = k["achieved_gbs"] / peak
+        k_det = kernel_entry("k_detect_design", ms_det, nb * (288 + 16 + 112), nb * DETECT_OPS_PER_BURST, peak, fp32_peak,
+                             "fp32-unfused")
+        k_eq = kernel_entry("k_equalize_fast", ms_eq, nb * (1250 + 112 + 148 * 4), nb * EQUALIZE_OPS_PER_BURST, peak, fp32_peak,
+                            "fp32-unfused")
+        prof = ncu_profile(args.blocks)
+        for k in (k_res, k_det, k_eq):          # dram bytes and pipe utilisation of the committed ncu capture (static)
+            p = prof.get("kernels", {}).get(k["name"])
+            if p:
+                k["from_profile"] = {"file": prof["file"], "dram_bytes": p.get("dram_bytes"),
+                                     "issue_active_pct": p.get("issue_active_pct"), "fma_pipe_active_pct": p.get("fma_pipe_active_pct")}
         dom = max((k_res, k_det, k_eq), key=lambda k: k["ms"])
+        step_ops = nch * RESAMPLE_OPS_PER_CHUNK + nb * (DETECT_OPS_PER_BURST + EQUALIZE_OPS_PER_BURST)
+        roof = {"bound": dom["bound"], "kernel": dom["name"], "peak_source": how, "sm_clock_mhz": sm_mhz,
+                "traffic": (dom.get("from_profile") or {}).get("dram_bytes"),
+                "traffic_source": (dom.get("from_profile") or {}).get("file"),
+                "hbm": {"achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["hbm_frac"]},
+                "kernels": [k_res, k_det, k_eq],
+                "step_frac_of_fused_hbm_roof": (nb * FUSED_BYTES_PER_BURST / (ms_step * 1e-3) / 1e9) / peak,
+                "step_frac_of_fp32_unfused_roof": (step_ops / (ms_step * 1e-3)) / fp32_peak if fp32_peak else None}
+        if dom["bound"] == "hbm":
+            roof.update({"achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["hbm_frac"]})
+        else:
+            roof.update({"achieved": dom["achieved_fp32_tops"], "peak": fp32_peak / 1e12, "unit": "TFLOP/s (FP32, multiply and add "
+                         "issued separately: %d SMs x %d lanes x the sampled SM clock)" % (sms, LANES_PER_SM), "frac": dom["fp32_frac"]})
         out = {
             "metric": "GSM bursts/sec (resample+detect+DFE)", "value": value, "unit": "bursts/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, world),
-            "roofline": {"bound": "hbm", "kernel": dom["name"], "achieved": dom["achieved_gbs"], "peak": peak,
-                         "unit": "GB/s", "frac": dom["frac"], "traffic": dom.get("traffic"),
-                         "traffic_source": traffic.get("_source"), "peak_source": how,
-                         "kernels": [k_res, k_det, k_eq, k_dem],
-                         "step_frac_of_fused_hbm_roof": (nb * FUSED_BYTES_PER_BURST / (ms_step * 1e-3) / 1e9) / peak},
-            "cpu_baseline": cpu, "e2e": e2e, "e2e_wire": e2e_wire, "gpu_launches": int(launches), "clocks": clocks,
-            "check": {"ber_tsc0": ber, "detected": detected}, "gather": gather, "secondary": secondary,
+            "config": workload_config(args, world), "roofline": roof,
+            "cpu_baseline": cpu, "e2e": e2e, "e2e_cf32": e2e_cf32, "gpu_launches": int(launches), "clocks": clocks,
+            "check": {"ber_tsc0": ber, "detected": detected, "vs_reference": vs_ref},
+            "kernel_ms": {"resample": ms_res, "demod": ms_dem, "detect": ms_det, "equalize": ms_eq},
+            "secondary": secondary,
         }
         emit(json.dumps(out))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -228,6 +228,10 @@ int btsdsp_rx_stream_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nchu
  * 864*(625*n/4/585) output pairs.  Host pointers. */
 int btsdsp_tx_stream_host(btsdsp_ctx *ctx, const uint8_t *bits148, long long n, int16_t *out);
 int btsdsp_tx_stream_dev(btsdsp_ctx *ctx, const uint8_t *bits148, long long n, int16_t *out, void *stream);
+/* The same for nstreams radios (one per ARFCN, Transceiver.cpp:412-426 runs one TX chain per Transceiver object) in ONE
+ * launch: stream a's n bursts at bits148 + a*n*148, its output at out + a*2*864*(625*n/4/585) int16.  Every stream
+ * starts from zero resampler history, as each RadioInterface does. */
+int btsdsp_tx_streams_dev(btsdsp_ctx *ctx, const uint8_t *bits148, long long n, int nstreams, int16_t *out, void *stream);
 /* Batched normal-burst demod / RACH detect+demod over HOST buffers (pitched bursts). */
 int btsdsp_demod_normal_host(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long pitch, const int32_t *lens,
                              const uint8_t *tsc, long long n, float detect_thr, float gate_thr, float snr_thr,

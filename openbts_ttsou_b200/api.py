@@ -72,6 +72,7 @@ _SIGS = {
     "btsdsp_rx_stream_dev": (_i, [_vp, _vp, _ll, _vp, _ll, _f, _f, _f, _vp, _vp, _vp, _vp, _i, _vp]),
     "btsdsp_tx_stream_host": (_i, [_vp, _vp, _ll, _vp]),
     "btsdsp_tx_stream_dev": (_i, [_vp, _vp, _ll, _vp, _vp]),
+    "btsdsp_tx_streams_dev": (_i, [_vp, _vp, _ll, _i, _vp, _vp]),
     "btsdsp_demod_normal_host": (_i, [_vp, _vp, _ll, _vp, _vp, _ll, _f, _f, _f, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp,
                                       _vp]),
     "btsdsp_rach_host": (_i, [_vp, _vp, _ll, _vp, _ll, _f, _vp, _vp, _vp, _vp, _i]),
@@ -393,6 +394,10 @@ class BtsDsp:
 
     def tx_stream_dev(self, bits148, n, out, stream=None):
         self._ck(self.lib.btsdsp_tx_stream_dev(self.h, _p(bits148), n, _p(out), _stream(stream)))
+
+    def tx_streams_dev(self, bits148, n, nstreams, out, stream=None):
+        """nstreams independent TX chains of n bursts each in one launch (bits and out laid out stream after stream)"""
+        self._ck(self.lib.btsdsp_tx_streams_dev(self.h, _p(bits148), n, nstreams, _p(out), _stream(stream)))
 
     # ---- layer 3: host buffers ---------------------------------------------------------------------
     def rx_stream_host(self, raw, nchunks, tsc, nbursts, flag, amp, toa, soft, soft_pitch=148, detect_thr=3.0,

@@ -34,6 +34,7 @@ struct btsdsp_ctx {
   cudaStream_t st = nullptr, st_in = nullptr, st_out = nullptr, st_side = nullptr;
   long long rx_seg = 0;         // btsdsp_rx_stream_dev: chunks per segment of the overlapped pipeline (0 = one launch each)
   int rx_res_ctas = 0;          // ... and the resampler's CTA cap while it shares the GPU with the demod kernels
+  long long host_seg = 4000;    // layer-3 pipelines: chunks per copy/compute segment (4000 = 27.6 MB of complex64 samples)
   std::string err;
   std::atomic<long long> launches{0};
   DevBuf buf[16];               // grow-only device scratch, by role
@@ -261,6 +262,7 @@ int btsdsp_create(btsdsp_ctx **out, int device, int sps) {
     }
     if (const char *e = getenv("BTSDSP_RX_SEG")) ctx->rx_seg = atoll(e);
     if (const char *e = getenv("BTSDSP_RX_RES_CTAS")) ctx->rx_res_ctas = atoi(e);
+    if (const char *e = getenv("BTSDSP_HOST_SEG")) { const long long v = atoll(e); if (v >= 250) ctx->host_seg = v; }
     CK(cudaMalloc(&ctx->T, sizeof(DevTables)));
     CK(cudaMallocHost(&ctx->hT, sizeof(DevTables)));
     int ce = configure_kernels();
@@ -907,7 +909,7 @@ static int rx_stream_host_impl(btsdsp_ctx *ctx, const void *raw_, int i16, int s
   float *dToa = dbuf<float>(ctx, B_TOA);
   unsigned char *dSoft = soft ? dbuf<unsigned char>(ctx, B_SOFT) : nullptr;
 
-  const long long seg = 4000;                       // chunks per segment: 27.6 MB of raw samples
+  const long long seg = ctx->host_seg;              // chunks per segment (default 4000: 27.6 MB of complex64 samples)
   const long long nseg = (nchunks + seg - 1) / seg;
   while ((long long)ctx->events.size() < 2 * nseg + 2) {
     cudaEvent_t ev;
@@ -979,6 +981,16 @@ int btsdsp_tx_stream_dev(btsdsp_ctx *ctx, const uint8_t *bits148, long long n, i
   // one fused kernel: the modulated stream never leaves shared memory (resample.cu: k_tx_fused)
   launch_tx_fused(ctx->T, bits148, nullptr, n, out, (cudaStream_t)stream);
   LAUNCHED("tx_stream", 1);
+  return BTSDSP_OK;
+}
+
+int btsdsp_tx_streams_dev(btsdsp_ctx *ctx, const uint8_t *bits148, long long n, int nstreams, int16_t *out, void *stream) {
+  ARG(ctx && bits148 && out && n > 0 && nstreams > 0);
+  if (ctx->sps != 1) return fail(ctx, BTSDSP_EUNSUPPORTED, "the TX stream path runs at sps == 1");
+  ARG(n % 4 == 0 && (n / 4 * 625) % 585 == 0);
+  DeviceGuard g(ctx->device);
+  launch_tx_fused(ctx->T, bits148, nullptr, n, out, (cudaStream_t)stream, nstreams);
+  LAUNCHED("tx_streams", 1);
   return BTSDSP_OK;
 }
 

@@ -76,7 +76,8 @@ void launch_modulate(const DevTables *T, const uint8_t *bits, int nbits, long lo
                      const float *scale = nullptr);
 void launch_resample_rx(const DevTables *T, const cf *in, int has_history, long long nchunks, cf *out, cudaStream_t st,
                         int max_ctas = 0);
-void launch_tx_fused(const DevTables *T, const uint8_t *bits, const float *scale, long long nslots, int16_t *out, cudaStream_t st);
+void launch_tx_fused(const DevTables *T, const uint8_t *bits, const float *scale, long long nslots, int16_t *out, cudaStream_t st,
+                     int nstreams = 1);
 int launch_resample_rx_i16_multi(const int16_t *in, long long in_pitch, int nstreams, int swap_iq, int has_history,
                                  long long nchunks, cf *out, long long out_pitch, cudaStream_t st);
 int launch_resample_rx_i16(const int16_t *in, int swap_iq, int has_history, long long nchunks, cf *out, cudaStream_t st);

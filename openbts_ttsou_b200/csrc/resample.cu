@@ -397,7 +397,7 @@ constexpr size_t kTxFusedSmem = (size_t)kTxFusedIn * sizeof(cf) + (size_t)kTxFus
 
 __global__ void __launch_bounds__(kTxFusedThreads, 1) k_tx_fused(const DevTables *__restrict__ T, const uint8_t *__restrict__ bits,
                                                                 const float *__restrict__ scale, long long nsamples,
-                                                                long long nperiods, short2 *__restrict__ out) {
+                                                                long long nperiods, int nstreams, short2 *__restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf *xs = reinterpret_cast<cf *>(smem_raw);                             // xs[j] = stream sample 65*G0 - 4 + j
   short2 *os = reinterpret_cast<short2 *>(xs + kTxFusedIn);
@@ -412,7 +412,9 @@ __global__ void __launch_bounds__(kTxFusedThreads, 1) k_tx_fused(const DevTables
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int part = warp % kTxFusedParts, row = (warp / kTxFusedParts) * 32 + lane;
-  const long long nsteps = (nperiods + kTxFusedPeriods - 1) / kTxFusedPeriods;
+  // nstreams independent slot streams of nsamples samples each (bits, scale and out laid out stream after stream); a
+  // global step gs is step gs % nsteps of stream gs / nsteps, and every stream starts from zero filter history
+  const long long nsteps = (nperiods + kTxFusedPeriods - 1) / kTxFusedPeriods, ngsteps = nsteps * nstreams;
   // the bits a step needs (<= 44 bursts = 6.5 KB) are fetched one step ahead into a register per thread and parked in
   // shared memory at the top of the step, so their latency hides under the previous step's arithmetic
   const long long nslots = nsamples / 625 * 4;
@@ -421,17 +423,19 @@ __global__ void __launch_bounds__(kTxFusedThreads, 1) k_tx_fused(const DevTables
     const long long s0_ = (long long)kTxQ * step_ * kTxFusedPeriods - kTxHalo;
     return (s0_ < 0 ? 0 : s0_) / 625;
   };
-  auto fetch = [&](long long step_) {
+  auto fetch = [&](long long gs_) {
     int4 v = make_int4(0, 0, 0, 0);
-    const long long gfirst = group_of(step_) * 4;
+    const long long a_ = gs_ / nsteps, gfirst = group_of(gs_ - a_ * nsteps) * 4;
     long long nb = nslots - gfirst;
     if (nb > kTxFusedBursts) nb = kTxFusedBursts;
-    if (vec && (int)threadIdx.x * 16 < (int)nb * 148) v = __ldg(reinterpret_cast<const int4 *>(bits + gfirst * 148) + threadIdx.x);
+    if (vec && (int)threadIdx.x * 16 < (int)nb * 148)
+      v = __ldg(reinterpret_cast<const int4 *>(bits + (a_ * nslots + gfirst) * 148) + threadIdx.x);
     return v;
   };
   static_assert(kTxFusedBursts * 148 <= kTxFusedThreads * 16, "one 16-byte fetch per thread must cover a step's bits");
-  int4 pre = blockIdx.x < nsteps ? fetch(blockIdx.x) : make_int4(0, 0, 0, 0);
-  for (long long step = blockIdx.x; step < nsteps; step += gridDim.x) {
+  int4 pre = blockIdx.x < ngsteps ? fetch(blockIdx.x) : make_int4(0, 0, 0, 0);
+  for (long long gs = blockIdx.x; gs < ngsteps; gs += gridDim.x) {
+    const long long a = gs / nsteps, step = gs - a * nsteps;
     const long long G0 = step * kTxFusedPeriods;
     __syncthreads();                                                     // previous step's tiles are free
     // ---- park the bits of the bursts this step touches, then modulate its samples into the tile
@@ -443,11 +447,11 @@ __global__ void __launch_bounds__(kTxFusedThreads, 1) k_tx_fused(const DevTables
       const long long gfirst = ga4 * 4;
       long long nb = nslots - gfirst;
       if (nb > kTxFusedBursts) nb = kTxFusedBursts;
-      const unsigned char *src = bits + gfirst * 148;
+      const unsigned char *src = bits + (a * nslots + gfirst) * 148;
       for (int i = threadIdx.x; i < (int)nb * 148; i += kTxFusedThreads) sb[i] = src[i];
     }
     __syncthreads();
-    if (step + gridDim.x < nsteps) pre = fetch(step + gridDim.x);        // in flight during this step
+    if (gs + gridDim.x < ngsteps) pre = fetch(gs + gridDim.x);           // in flight during this step
     const int w0 = (int)(s0 - ga4 * 625);                                // in [-4, 624]
     for (int j = threadIdx.x; j < kTxFusedIn; j += kTxFusedThreads) {
       const int w = w0 + j;
@@ -458,7 +462,7 @@ __global__ void __launch_bounds__(kTxFusedThreads, 1) k_tx_fused(const DevTables
         tx_slot_of(w - q4 * 625, &sl, &t);
         const int lb = q4 * 4 + sl;                                      // burst index within the staged bits
         x = tx_burst_sample(q, sb + lb * 148, t);
-        if (scale) x = cmul(x, mk(scale[ga4 * 4 + lb], 0.0F));           // addRadioVector's scaleVector, Transceiver.cpp:108
+        if (scale) x = cmul(x, mk(scale[a * nslots + ga4 * 4 + lb], 0.0F));   // addRadioVector's scaleVector, Transceiver.cpp:108
       }
       xs[j] = x;
     }
@@ -470,7 +474,7 @@ __global__ void __launch_bounds__(kTxFusedThreads, 1) k_tx_fused(const DevTables
     // ---- rows of 96 int16 pairs (384 B) back to global, coalesced
     const int nper = (int)(nperiods - G0 < kTxFusedPeriods ? nperiods - G0 : kTxFusedPeriods);
     for (int p = warp; p < nper; p += kTxFusedThreads / 32) {
-      short2 *og = out + (G0 + p) * kTxP;
+      short2 *og = out + (a * nperiods + G0 + p) * kTxP;
       const short2 *src = os + p * kTxFusedOutPitch;
       og[lane] = src[lane];
       og[lane + 32] = src[lane + 32];
@@ -478,13 +482,15 @@ __global__ void __launch_bounds__(kTxFusedThreads, 1) k_tx_fused(const DevTables
     }
   }
 }
-// bits: nslots x 148 bytes (slot g of the stream), nslots % 4 == 0 and a whole number of 585-sample chunks
-void launch_tx_fused(const DevTables *T, const uint8_t *bits, const float *scale, long long nslots, int16_t *out, cudaStream_t st) {
+// bits: nstreams x nslots x 148 bytes (slot g of stream a), nslots % 4 == 0 and a whole number of 585-sample chunks
+void launch_tx_fused(const DevTables *T, const uint8_t *bits, const float *scale, long long nslots, int16_t *out, cudaStream_t st,
+                     int nstreams) {
   const long long nsamples = nslots / 4 * 625, nchunks = nsamples / 585, nperiods = nchunks * 9;
-  if (nperiods <= 0) return;
-  const long long nsteps = (nperiods + kTxFusedPeriods - 1) / kTxFusedPeriods;
+  if (nperiods <= 0 || nstreams <= 0) return;
+  const long long nsteps = (nperiods + kTxFusedPeriods - 1) / kTxFusedPeriods * nstreams;
   const unsigned grid = (unsigned)(nsteps < g_num_sms ? nsteps : g_num_sms);
-  k_tx_fused<<<grid, kTxFusedThreads, kTxFusedSmem, st>>>(T, bits, scale, nsamples, nperiods, reinterpret_cast<short2 *>(out));
+  k_tx_fused<<<grid, kTxFusedThreads, kTxFusedSmem, st>>>(T, bits, scale, nsamples, nperiods, nstreams,
+                                                          reinterpret_cast<short2 *>(out));
 }
 
 int configure_resamplers() {

@@ -29,18 +29,33 @@ def stream_shard(n_blocks, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_soft(soft, group=None):
+def gather_soft(soft, group=None, counts=None):
     """all_gather of per-rank soft-bit tensors (torch.distributed; NCCL over NVLink on GPUs, gloo on CPU).
-    Returns the list of every rank's tensor.  Ranks may hold different burst counts."""
+    Returns the list of every rank's tensor.
+    * ranks hold the same burst count (the ARFCN split of 1024 ARFCNs over 2/4/8 ranks): pass counts="equal" -- ONE
+      collective straight into one output tensor, no padding, no host synchronisation;
+    * counts = list of every rank's burst count, known to the caller: one padded collective, no host synchronisation;
+    * counts = None: the counts are exchanged first (a small collective and a host read)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    n = torch.tensor([soft.shape[0]], dtype=torch.int64, device=soft.device)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n, group=group)
-    nmax = int(max(int(c.item()) for c in counts))
+    if isinstance(counts, str) and counts == "equal":
+        out = torch.empty((world,) + tuple(soft.shape), dtype=soft.dtype, device=soft.device)
+        if soft.is_cuda:
+            dist.all_gather_into_tensor(out.view((world * soft.shape[0],) + tuple(soft.shape[1:])), soft.contiguous(), group=group)
+        else:
+            dist.all_gather(list(out.unbind(0)), soft.contiguous(), group=group)
+        return list(out.unbind(0))
+    if counts is None:
+        n = torch.tensor([soft.shape[0]], dtype=torch.int64, device=soft.device)
+        cl = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(cl, n, group=group)
+        counts = [int(c) for c in torch.cat(cl).tolist()]        # one host read for all ranks' counts
+    nmax = max(counts)
+    if all(c == nmax for c in counts):
+        return gather_soft(soft, group, "equal")
     pad = torch.zeros((nmax,) + tuple(soft.shape[1:]), dtype=soft.dtype, device=soft.device)
     pad[:soft.shape[0]] = soft
     outs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(outs, pad, group=group)
-    return [o[:int(c.item())] for o, c in zip(outs, counts)]
+    return [o[:c] for o, c in zip(outs, counts)]

@@ -379,6 +379,31 @@ class Oracle:
         self._run(self._shard(nch, threads), job)
         return out
 
+    def rx_resample_stream_i16(self, iq, flip_iq=False, threads=1):
+        """iq: int16 (n, 2) radio samples, n a multiple of 864, the stream starts at chunk 0 -> complex64 at 1 sps
+        (unUSRPifyVector + pullBuffer's resample, radioInterface.cpp:91-116, 238-259)."""
+        iq = np.ascontiguousarray(iq, np.int16).reshape(-1, 2)
+        nch = iq.shape[0] // 864
+        out = np.zeros(nch * 585, np.complex64)
+        f = self._f("rx_resample_stream_i16")
+
+        def job(lo, hi):
+            f(_ptr(iq[lo * 864:]), c_i(1 if flip_iq else 0), c_l(lo), c_l(hi - lo), _ptr(out[lo * 585:]))
+        self._run(self._shard(nch, threads), job)
+        return out
+
+    def soft_to_wire(self, soft, threads=1):
+        """soft (n, pitch >= 148) float32 -> (n, 148) uint8 as the RX datagram carries them (Transceiver.cpp:667-669)"""
+        soft = np.ascontiguousarray(soft, np.float32)
+        n, pitch = soft.shape
+        out = np.zeros((n, 148), np.uint8)
+        f = self._f("soft_to_wire")
+
+        def job(lo, hi):
+            f(_ptr(soft[lo:hi]), c_i(pitch), c_l(hi - lo), _ptr(out[lo:hi]))
+        self._run(self._shard(n, threads), job)
+        return out
+
     def tx_resample_stream(self, x, threads=1):
         """x: complex64 at 1 sps, length multiple of 585 -> int16 (n,2) at 400 kS/s, 864 per chunk."""
         x = _c64(x)

@@ -288,6 +288,34 @@ void ref_rx_resample_stream(const float *raw, long first_chunk, long nchunks, fl
   }
 }
 
+/* The same from the radio's own samples: RadioInterface::pullBuffer reads interleaved shorts from the device and
+ * widens them with unUSRPifyVector (radioInterface.cpp:91-116: Complex<float>(s[FLIP_IQ], s[1-FLIP_IQ]); FLIP_IQ = 1 on
+ * real hardware, 0 on the SWLOOPBACK build; usrp_to_host_short is the identity on a little-endian host) before the
+ * resample (:238-259).  iq: 2 shorts per sample; iq[-384..-1] are the previous chunk's last 192 samples. */
+void ref_rx_resample_stream_i16(const short *iq, int flip_iq, long first_chunk, long nchunks, float *out) {
+  signalVector input(192 + 864);
+  for (long c = 0; c < nchunks; c++) {
+    const short *src = iq + 2 * 864 * c;
+    const int hist = (first_chunk + c == 0) ? 0 : 192;
+    if (!hist) memset(input.begin(), 0, 192 * sizeof(complex));
+    signalVector::iterator itr = input.begin() + (192 - hist);
+    const short *sp = src - 2 * hist;
+    while (itr < input.end()) {
+      *itr++ = Complex<float>(*(sp + flip_iq), *(sp + 1 - flip_iq));
+      sp += 2;
+    }
+    signalVector *r = polyphaseResampleVector(input, 65, 96, gLpfRx);
+    memcpy(out + 2 * 585 * c, r->begin() + 130, 585 * sizeof(complex));
+    delete r;
+  }
+}
+
+/* the RX datagram's soft bytes, Transceiver.cpp:667-669: burstString[8+i] = (char) round(soft[i]*255.0), gSlotLen = 148 */
+void ref_soft_to_wire(const float *soft, int soft_pitch, long n, unsigned char *out) {
+  for (long i = 0; i < n; i++)
+    for (int k = 0; k < 148; k++) out[148 * i + k] = (unsigned char)(char)round(soft[(size_t)soft_pitch * i + k] * 255.0);
+}
+
 /* radioInterface.cpp:123-168 + USRPifyVector :74-89 (SWLOOPBACK byte order: host_to_usrp_short is
  * the identity on the loopback build; element 0 = real, 1 = imag).  Chunk c of 585 samples prefixed
  * by the previous 130, resampled 96/65 through the 651-tap filter, x13500, (short) truncation,

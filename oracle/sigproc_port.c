@@ -606,6 +606,26 @@ void port_rx_resample_stream(const float *raw, long first_chunk, long nchunks, f
   }
 }
 
+/* radioInterface.cpp:91-116 (unUSRPifyVector) in front of the same resample; see oracle/ref_shim.cpp */
+void port_rx_resample_stream_i16(const short *iq, int flip_iq, long first_chunk, long nchunks, float *out) {
+  cpx input[192 + 864], res[720];
+  for (long c = 0; c < nchunks; c++) {
+    const short *src = iq + 2 * 864 * c;
+    const int hist = (first_chunk + c == 0) ? 0 : 192;
+    if (!hist) memset(input, 0, 192 * sizeof(cpx));
+    const short *sp = src - 2 * hist;
+    for (int i = 192 - hist; i < 192 + 864; i++, sp += 2) input[i] = C((float)sp[flip_iq], (float)sp[1 - flip_iq]);
+    resample_(input, 192 + 864, 65, 96, gLpfRx, 961, res);
+    memcpy(out + 2 * 585 * c, res + 130, 585 * sizeof(cpx));
+  }
+}
+
+/* Transceiver.cpp:667-669: (char) round(soft*255.0), 148 per burst */
+void port_soft_to_wire(const float *soft, int soft_pitch, long n, unsigned char *out) {
+  for (long i = 0; i < n; i++)
+    for (int k = 0; k < 148; k++) out[148 * i + k] = (unsigned char)(char)round(soft[(size_t)soft_pitch * i + k] * 255.0);
+}
+
 void port_tx_resample_stream(const float *in, long first_chunk, long nchunks, short *out) {
   cpx input[130 + 585], res[1060];
   for (long c = 0; c < nchunks; c++) {

@@ -41,6 +41,8 @@ void  port_rx_normal_batch(const float *bursts, int pitch, const int *lens, cons
 void  port_rx_rach_batch(const float *bursts, int pitch, const int *lens, long n, float detect_thr, int sps,
                          int *flags, float *amp, float *toa, float *soft, int soft_pitch);
 void  port_rx_resample_stream(const float *raw, long first_chunk, long nchunks, float *out);
+void  port_rx_resample_stream_i16(const short *iq, int flip_iq, long first_chunk, long nchunks, float *out);
+void  port_soft_to_wire(const float *soft, int soft_pitch, long n, unsigned char *out);
 void  port_tx_resample_stream(const float *in, long first_chunk, long nchunks, short *out);
 long  port_modulate_stream(const char *bits148, long nbursts, int tn0, float *out);
 void  port_rx_stream_demod(const float *resampled, long first_burst, long nbursts, const unsigned char *tsc,

@@ -482,3 +482,25 @@ def test_no_overrun_canaries(dsp, oracle_best):
     hu, hk = u.cpu().numpy(), ok.cpu().numpy()
     assert (hu[:32] == 9).all() and (hu[-32:] == 9).all() and (hu[32:-32] <= 1).all()
     assert (hk[:8] == -3).all() and (hk[-8:] == -3).all() and set(np.unique(hk[8:-8])) <= {0, 1}
+
+
+@pytest.mark.gpu
+def test_tx_streams_equal_single_stream_calls(dsp):
+    """btsdsp_tx_streams_dev: many radios' TX chains in one launch == one btsdsp_tx_stream_dev call per radio (itself
+    checked bit for bit against the reference's modulateBurst + pushBuffer in test_stream_kernels_match_golden), every
+    stream from zero resampler history; nothing is written outside the output"""
+    import torch
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(11)
+    for nb, ns in ((468, 5), (936, 3), (936 * 2, 151)):
+        nch = nb // 4 * 625 // 585
+        bits = torch.from_numpy(rng.integers(0, 2, (ns, nb, 148)).astype(np.uint8)).to(dev)
+        multi = torch.full((ns * nch * 864 * 2 + 64,), 12345, dtype=torch.int16, device=dev)
+        dsp.tx_streams_dev(bits, nb, ns, multi[32:])
+        single = torch.zeros((ns, nch * 864 * 2), dtype=torch.int16, device=dev)
+        for a in range(ns):
+            dsp.tx_stream_dev(bits[a], nb, single[a])
+        torch.cuda.synchronize()
+        m = multi.cpu().numpy()
+        assert (m[:32] == 12345).all() and (m[-32:] == 12345).all()
+        same(m[32:-32].reshape(ns, -1), single.cpu().numpy(), "tx streams nb=%d ns=%d" % (nb, ns))

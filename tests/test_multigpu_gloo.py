@@ -25,6 +25,15 @@ def _worker(rank, world, port, q):
     rows = shard.burst_rows_of_arfcns(shard.arfcn_shard(n_arfcn, rank, world))
     r = o.rx_normal_batch(g["bursts"][rows], g["lens"][rows], g["tsc"][rows])
     parts = shard.gather_soft(torch.from_numpy(r["soft"]))
+    # the three ways to call it agree (counts exchanged / counts known / equal shards in one collective)
+    n_mine = len(rows)
+    counts = [len(shard.burst_rows_of_arfcns(shard.arfcn_shard(n_arfcn, k, world))) for k in range(world)]
+    for alt in (shard.gather_soft(torch.from_numpy(r["soft"]), counts=counts),
+                shard.gather_soft(torch.from_numpy(r["soft"]), counts="equal") if len(set(counts)) == 1 else parts):
+        assert all(torch.equal(a, b) for a, b in zip(alt, parts)) and alt[rank].shape[0] == n_mine
+    # ragged shards: rank r holds r + 3 rows
+    rag = shard.gather_soft(torch.full((rank + 3, 5), float(rank)))
+    assert [t.shape[0] for t in rag] == [k + 3 for k in range(world)] and all(bool((t == k).all()) for k, t in enumerate(rag))
     rows_all = [shard.burst_rows_of_arfcns(shard.arfcn_shard(n_arfcn, k, world)) for k in range(world)]
     full = np.zeros_like(g["soft"])
     for k in range(world):

@@ -144,3 +144,32 @@ def test_reference_oob_tap_is_negligible():
     R = orc.Oracle("ref")
     assert abs(float(R.table(orc.T_OOB)[0])) < 1e-30
     assert abs(float(R.table(orc.T_LPF_RX)[960])) < 1e-30
+
+
+@pytest.mark.parametrize("kind", ["port", pytest.param("ref", marks=needs_ref)])
+def test_wire_format_glue_of_the_oracles(kind):
+    """the int16 ingest (unUSRPifyVector + pullBuffer resample) equals the float resample of the widened samples, in both
+    I/Q orders and in any threading, and the soft-byte conversion is (char) round(soft*255.0) (Transceiver.cpp:667-669)"""
+    o = orc.Oracle(kind, sps=1)
+    rng = np.random.default_rng(21)
+    iq = rng.integers(-32768, 32768, (7 * 864, 2)).astype(np.int16)
+    for flip in (False, True):
+        wide = (iq[:, 1] + 1j * iq[:, 0] if flip else iq[:, 0] + 1j * iq[:, 1]).astype(np.complex64)
+        want = o.rx_resample_stream(wide)
+        assert_same(o.rx_resample_stream_i16(iq, flip), want, "i16 ingest, flip=%s" % flip)
+        assert_same(o.rx_resample_stream_i16(iq, flip, threads=3), want, "i16 ingest threaded")
+    soft = rng.random((33, 160)).astype(np.float32)
+    soft[0, :4] = [0.0, 1.0, 0.5, np.float32(0.5) - np.float32(2 ** -25)]
+    got = o.soft_to_wire(soft, threads=2)
+    want = np.floor(soft[:, :148].astype(np.float64) * 255.0 + 0.5).astype(np.uint8)     # round half away from zero, x >= 0
+    assert_same(got, want, "soft bytes")
+
+
+@needs_ref
+def test_port_wire_glue_matches_reference():
+    p, r = orc.Oracle("port", sps=1), orc.Oracle("ref", sps=1)
+    rng = np.random.default_rng(22)
+    iq = rng.integers(-20000, 20000, (5 * 864, 2)).astype(np.int16)
+    assert_same(p.rx_resample_stream_i16(iq, True), r.rx_resample_stream_i16(iq, True), "i16 ingest port vs ref")
+    soft = rng.random((64, 148)).astype(np.float32)
+    assert_same(p.soft_to_wire(soft), r.soft_to_wire(soft), "soft bytes port vs ref")
