@@ -331,6 +331,19 @@ int btsdsp_analyze_traffic_burst_52m(btsdsp_ctx *ctx, const btsdsp_cf32 *burst, 
 int btsdsp_energy_detect_52m(btsdsp_ctx *ctx, const btsdsp_cf32 *v, int n, unsigned window, float threshold, float *avg_pwr,
                              int *above);
 
+/* The receive policy of that variant (Transceiver52M/Transceiver.cpp:268-404) on a btsdsp_trx: enable != 0 makes every later
+ * pull use the stride-4 energy window and the windowed midamble search over +-max_expected_delay symbols (its
+ * mMaxExpectedDelay, 0..60); with max_expected_delay <= 1 the channel is never estimated and detected normal bursts are
+ * demodulated by demodulateBurst instead of the equaliser (needDFE == false, :272, :322, :382).  enable == 0 restores the
+ * main variant.  State layout, slot map, threshold adaptation and datagrams are the same. */
+int btsdsp_trx_set_variant_52m(btsdsp_ctx *ctx, btsdsp_trx *trx, int enable, int max_expected_delay);
+/* Its transmit side: bursts are scaled at modulate time -- datagram bursts by 13500 * pow(10, -RSSI/10)
+ * (Transceiver52M/Transceiver.cpp:111), `filler` slots by 13500 (:74; the filler table's initial content -- replaying the
+ * last burst sent on a slot, :145-175, is queue logic left to the caller) -- and the symbol-rate radio only casts to short
+ * (radioInterface.cpp:100-118): out gets nframes*1250 int16 {I,Q} pairs, any nframes > 0. */
+int btsdsp_tx_datagrams_52m_host(btsdsp_ctx *ctx, const uint8_t *dgram, long long n, int dgram_pitch, int fn0, int nframes,
+                                 const uint8_t *filler, int16_t *out, long long *placed);
+
 void *btsdsp_host_alloc(size_t bytes);
 void btsdsp_host_free(void *p);
 

@@ -87,6 +87,8 @@ _SIGS = {
     "btsdsp_trx_pull_streams_dev": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i, _vp]),
     "btsdsp_trx_radio_host": (_i, [_vp, _vp, _vp, _ll, _ll, _i, _i, _vp, _vp, _i]),
     "btsdsp_tx_datagrams_host": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp]),
+    "btsdsp_tx_datagrams_52m_host": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp]),
+    "btsdsp_trx_set_variant_52m": (_i, [_vp, _vp, _i, _i]),
     "btsdsp_xcch_decode_dev": (_i, [_vp, _vp, _i, _ll, _vp, _vp, _vp]),
     "btsdsp_xcch_decode_host": (_i, [_vp, _vp, _i, _ll, _vp, _vp]),
     "btsdsp_rach_decode_dev": (_i, [_vp, _vp, _i, _ll, _vp, _vp, _vp]),
@@ -446,6 +448,10 @@ class BtsDsp:
     def trx_set_slot(self, trx, arfcn, tn, chan_type):
         self._ck(self.lib.btsdsp_trx_set_slot(self.h, trx[0], arfcn, tn, chan_type))
 
+    def trx_set_variant_52m(self, trx, enable=True, max_expected_delay=0):
+        """the second transceiver variant's receive policy (Transceiver52M/Transceiver.cpp:268-404) for later pulls"""
+        self._ck(self.lib.btsdsp_trx_set_variant_52m(self.h, trx[0], int(enable), int(max_expected_delay)))
+
     def trx_state(self, trx):
         st = np.zeros(trx[1], self.TRX_STATE_DTYPE)
         for a in range(trx[1]):
@@ -515,6 +521,16 @@ class BtsDsp:
         placed = ctypes.c_longlong(0)
         self._ck(self.lib.btsdsp_tx_datagrams_host(self.h, _p(dgram), dgram.shape[0], dgram.shape[1], fn0, nframes,
                                                    _p(filler), _p(out), ctypes.byref(placed)))
+        return out, placed.value
+
+    def tx_datagrams_52m_host(self, dgram, fn0, nframes, filler=None):
+        """the second variant's transmit side: (iq[nframes*1250, 2] int16 at the symbol rate, placed)"""
+        dgram = np.ascontiguousarray(dgram, np.uint8)
+        filler = None if filler is None else np.ascontiguousarray(filler, np.uint8)
+        out = np.zeros((nframes * 1250, 2), np.int16)
+        placed = ctypes.c_longlong(0)
+        self._ck(self.lib.btsdsp_tx_datagrams_52m_host(self.h, _p(dgram), dgram.shape[0], dgram.shape[1], fn0, nframes,
+                                                       _p(filler), _p(out), ctypes.byref(placed)))
         return out, placed.value
 
     def trx_pull_dev(self, trx, bursts, pitch, nframes, fn0, valid, dgram, dgram_pitch=160, stream=None):

@@ -1089,6 +1089,7 @@ struct btsdsp_trx {
   cudaEvent_t meta_done = nullptr;      // the previous call's map upload has been consumed
   cudaStream_t side = nullptr;          // access-burst kernels run here, next to the normal-burst kernels
   cudaEvent_t fork_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  TrxVariant var;                       // main transceiver, or the second one (btsdsp_trx_set_variant_52m)
 };
 
 int btsdsp_trx_create(btsdsp_ctx *ctx, int narfcn, const uint8_t *tsc, const uint8_t *chan_type, int start_fn,
@@ -1159,6 +1160,16 @@ int btsdsp_trx_set_slot(btsdsp_ctx *ctx, btsdsp_trx *t, int arfcn, int tn, int c
   return BTSDSP_OK;
 }
 
+/* the second transceiver variant's receive policy (Transceiver52M/Transceiver.cpp:268-404); max_expected_delay is its
+ * mMaxExpectedDelay (the SETMAXDLY control command) */
+int btsdsp_trx_set_variant_52m(btsdsp_ctx *ctx, btsdsp_trx *t, int enable, int max_expected_delay) {
+  ARG(ctx && t && max_expected_delay >= 0 && max_expected_delay <= 60);
+  t->var.v52m = enable != 0;
+  t->var.max_toa = (unsigned)max_expected_delay;
+  t->var.need_dfe = !t->var.v52m || max_expected_delay > 1;                                 // :272
+  return BTSDSP_OK;
+}
+
 static int trx_pull_impl(btsdsp_ctx *ctx, btsdsp_trx *t, const btsdsp_cf32 *bursts, long long pitch, long long stream_pitch,
                          int nframes, int fn0, int32_t *valid, uint8_t *dgram, int dgram_pitch, void *stream) {
   ARG(ctx && t && bursts && valid && dgram && nframes > 0 && fn0 >= 0);
@@ -1198,11 +1209,11 @@ static int trx_pull_impl(btsdsp_ctx *ctx, btsdsp_trx *t, const btsdsp_cf32 *burs
   uint8_t *dm = (uint8_t *)t->meta.p;
   CK(cudaMemcpyAsync(dm, hp, meta_bytes, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(t->meta_done, st));
-  r = grow_buf(t->scratch, trx_scratch_bytes(n, nr, A), false);
+  r = grow_buf(t->scratch, trx_scratch_bytes(n, nr, A, t->var.v52m && !t->var.need_dfe), false);
   if (r != BTSDSP_OK) return r;
   const int nl = launch_trx_pull(ctx->T, t->d_state, A, nframes, fn0, (const cf *)bursts, pitch, stream_pitch, dm + o_kind,
                                  dm + o_tsc, (const int *)(dm + o_idx), (const int *)(dm + o_slot), nr, t->scratch.p, valid,
-                                 dgram, dgram_pitch, st, t->side, t->fork_ev);
+                                 dgram, dgram_pitch, st, t->side, t->fork_ev, t->var);
   LAUNCHED("trx_pull", nl);
   return BTSDSP_OK;
 }
@@ -1282,14 +1293,16 @@ int btsdsp_trx_pull_host(btsdsp_ctx *ctx, btsdsp_trx *t, const btsdsp_cf32 *burs
 }
 
 /* ---- TX datagrams: Transceiver::driveTransmitPriorityQueue (:582-632) + addRadioVector (:100-114) + pushBuffer ---- */
-int btsdsp_tx_datagrams_host(btsdsp_ctx *ctx, const uint8_t *dgram, long long n, int dgram_pitch, int fn0, int nframes,
-                             const uint8_t *filler, int16_t *out, long long *placed) {
-  ARG(ctx && (dgram || n == 0) && out && n >= 0 && dgram_pitch >= 154 && fn0 >= 0 && nframes > 0 && nframes % 117 == 0);
+static int tx_datagrams_impl(btsdsp_ctx *ctx, const uint8_t *dgram, long long n, int dgram_pitch, int fn0, int nframes,
+                             const uint8_t *filler, int16_t *out, long long *placed, bool v52m) {
+  ARG(ctx && (dgram || n == 0) && out && n >= 0 && dgram_pitch >= 154 && fn0 >= 0 && nframes > 0 && (v52m || nframes % 117 == 0));
   if (ctx->sps != 1) return fail(ctx, BTSDSP_EUNSUPPORTED, "the TX stream path runs at sps == 1");
   DeviceGuard g(ctx->device);
   const long long nslots = (long long)nframes * 8, nchunks = nslots / 4 * 625 / 585;
   std::vector<uint8_t> bits((size_t)nslots * 148, 0);
-  std::vector<float> scale((size_t)nslots, filler ? 1.0F : 0.0F);
+  // the second variant scales at modulate time: fillers by 13500 (Transceiver52M/Transceiver.cpp:74), bursts by
+  // 13500 * pow(10, -RSSI/10) (:111); its radio then only casts to short (no resampler, no further gain)
+  std::vector<float> scale((size_t)nslots, filler ? (v52m ? 13500.0F : 1.0F) : 0.0F);
   if (filler) for (long long sl = 0; sl < nslots; sl++) memcpy(&bits[(size_t)sl * 148], filler, 148);
   long long ok = 0;
   for (long long i = 0; i < n; i++) {
@@ -1303,10 +1316,26 @@ int btsdsp_tx_datagrams_host(btsdsp_ctx *ctx, const uint8_t *dgram, long long n,
     if (f < 0 || f >= nframes) continue;
     const long long sl = f * 8 + tn;
     memcpy(&bits[(size_t)sl * 148], d + 6, 148);                                            // :620-623
-    scale[(size_t)sl] = (float)pow(10, -rssi / 10);                                         // :108, integer division
+    scale[(size_t)sl] = v52m ? (float)(13500.0 * pow(10, -rssi / 10)) : (float)pow(10, -rssi / 10);   // :108, integer division
     ok++;
   }
   if (placed) *placed = ok;
+  if (v52m) {
+    const long long nsamp = nslots / 4 * 625;
+    GROW(B_TSC, (size_t)nslots * 148);
+    GROW(B_TOA, (size_t)nslots * 4);
+    GROW(B_RES, (size_t)nsamp * sizeof(cf));
+    GROW(B_RAW, (size_t)nsamp * 2 * sizeof(int16_t));
+    cudaStream_t st = ctx->st;
+    CK(cudaMemcpyAsync(dbuf<uint8_t>(ctx, B_TSC), bits.data(), bits.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dbuf<float>(ctx, B_TOA), scale.data(), scale.size() * 4, cudaMemcpyHostToDevice, st));
+    launch_modulate(ctx->T, dbuf<uint8_t>(ctx, B_TSC), 148, nslots, -1, nullptr, 0, dbuf<cf>(ctx, B_RES), 0, st, dbuf<float>(ctx, B_TOA));
+    launch_usrpify(dbuf<cf>(ctx, B_RES), nsamp, dbuf<int16_t>(ctx, B_RAW), st);
+    LAUNCHED("tx_datagrams_52m", 2);
+    CK(cudaMemcpyAsync(out, dbuf<int16_t>(ctx, B_RAW), (size_t)nsamp * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return BTSDSP_OK;
+  }
   GROW(B_TSC, (size_t)nslots * 148);
   GROW(B_TOA, (size_t)nslots * 4);
   GROW(B_RAW, (size_t)nchunks * 864 * 2 * sizeof(int16_t));
@@ -1318,6 +1347,15 @@ int btsdsp_tx_datagrams_host(btsdsp_ctx *ctx, const uint8_t *dgram, long long n,
   CK(cudaMemcpyAsync(out, dbuf<int16_t>(ctx, B_RAW), (size_t)nchunks * 864 * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));                             // also keeps `bits` / `scale` alive until the copies are done
   return BTSDSP_OK;
+}
+
+int btsdsp_tx_datagrams_host(btsdsp_ctx *ctx, const uint8_t *dgram, long long n, int dgram_pitch, int fn0, int nframes,
+                             const uint8_t *filler, int16_t *out, long long *placed) {
+  return tx_datagrams_impl(ctx, dgram, n, dgram_pitch, fn0, nframes, filler, out, placed, false);
+}
+int btsdsp_tx_datagrams_52m_host(btsdsp_ctx *ctx, const uint8_t *dgram, long long n, int dgram_pitch, int fn0, int nframes,
+                                 const uint8_t *filler, int16_t *out, long long *placed) {
+  return tx_datagrams_impl(ctx, dgram, n, dgram_pitch, fn0, nframes, filler, out, placed, true);
 }
 
 /* ---- L1 FEC after the path: XCCH deinterleave + Viterbi + Fire-code check (fec.cuh) ---- */

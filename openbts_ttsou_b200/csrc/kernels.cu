@@ -279,6 +279,20 @@ void launch_modulate(const DevTables *T, const uint8_t *bits, int nbits, long lo
   const int grid = (int)(nbursts < 148 * 64 ? nbursts : 148 * 64);
   k_modulate<<<grid, 160, 0, st>>>(T, bits, nbits, nbursts, guard_rule, guards, first, out, pitch, scale);
 }
+// USRPifyVector of the second variant (Transceiver52M/radioInterface.cpp:100-118, powerScaling == 1.0): (short) casts of the
+// already-scaled samples, no resampling -- that radio runs at the symbol rate
+__global__ void k_usrpify(const cf *__restrict__ x, long long n, short2 *__restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const cf v = x[i];
+  short2 o;
+  o.x = (short)(int)v.x;
+  o.y = (short)(int)v.y;
+  out[i] = o;
+}
+void launch_usrpify(const cf *x, long long n, int16_t *out, cudaStream_t st) {
+  if (n > 0) k_usrpify<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, reinterpret_cast<short2 *>(out));
+}
 // the impulse-pulse variant generateMidamble needs (:794-797): pulse = {1.0} complex, guard 0
 __global__ void k_modulate_impulse(const DevTables *T, const uint8_t *bits, int nbits, cf *out) {
   const int sps = T->sps, n = sps * nbits;
@@ -1027,9 +1041,88 @@ int analyze_52m_scratch_stride(unsigned max_toa, int sps) {
   if (max_toa < 3u * sps) max_toa = 3 * sps;
   return 2 * (2 * (int)max_toa + 2);
 }
+// The same one burst per lane over a shared-memory tile (sps == 1): the warp stages the search window of its 32 bursts
+// (burst rows 66-span .. 82+span, 16 + 2*span rows) transposed, and the correlation (2*maxTOA+1 lags) and delayVector's
+// temporary live in the rows behind it -- (windowLen + 2*corrLen) x 33 x 8 B per warp: 10.6 KB at maxTOA <= 3, 24 KB at 12,
+// 100 KB at the limit of 60.  POLICY = pass 1 of the caller-policy pipeline for this variant: the stride-4 energy of the
+// slot is measured (Transceiver52M/sigProcLib.cpp:944-963), the analysis runs on the TSC slots, results go to a DetRec.
+struct Geo52 { int startIx, windowLen, corrLen; };
+__host__ __device__ inline Geo52 geo_52m(unsigned max_toa) {
+  if (max_toa < 3u) max_toa = 3;
+  unsigned span = max_toa < 5u ? 5u : max_toa;
+  return Geo52{66 - (int)span, 16 + 2 * (int)span, 2 * (int)max_toa + 1};
+}
+size_t detect_52m_smem(unsigned max_toa) {
+  const Geo52 g = geo_52m(max_toa);
+  return (size_t)(g.windowLen + 2 * g.corrLen + 1) * kTileStride * sizeof(cf);
+}
+template <bool POLICY>
+__global__ void __launch_bounds__(32) k_detect_52m(const DevTables *__restrict__ T, BurstSrc src, const uint8_t *__restrict__ tsc,
+                                                   long long n, float detect_thr, unsigned max_toa, int request, NormalOut out,
+                                                   const uint8_t *__restrict__ kind, DetRec *__restrict__ det) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf *A = reinterpret_cast<cf *>(smem_raw);
+  const int lane = threadIdx.x;
+  const long long w0 = (long long)blockIdx.x * 32;
+  if (w0 >= n) return;
+  const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
+  const long long i = w0 + lane;
+  const Geo52 g = geo_52m(max_toa);
+  long long start = 0;
+  int len = 0;
+  if (lane < nv) burst_loc(src, i, &start, &len);
+  for (int e = lane; e < 32 * g.windowLen; e += 32) {          // element e: burst e / windowLen, window row e % windowLen
+    const int j = e / g.windowLen, r = e - j * g.windowLen;
+    const long long sj = __shfl_sync(0xffffffffu, start, j);
+    const int lj = __shfl_sync(0xffffffffu, len, j);
+    A[r * kTileStride + j] = (j < nv && g.startIx + r < lj) ? __ldg(src.base + sj + g.startIx + r) : mk(0.0F, 0.0F);
+  }
+  __syncwarp();
+  if (lane >= nv) return;
+  const View<kTileStride> win{A + lane};
+  bool ok = false, run = true;
+  float avg_pwr = 0.0F;
+  if (POLICY) {
+    energy_detect_52m<1>(View<1>{(cf *)src.base + start}, len, 20, 0.0F, &avg_pwr);
+    run = kind[i] == CORR_TSC;
+  }
+  cf amp = mk(0.0F, 0.0F), chan[6];
+#pragma unroll
+  for (int j = 0; j < 6; j++) chan[j] = mk(0.0F, 0.0F);
+  float toa = 0.0F, off = 0.0F;
+  // analyze_traffic_52m indexes the burst from its start: hand it a view whose row startIx is tile row 0
+  if (run) ok = analyze_traffic_52m<kTileStride>(T, win.at(-g.startIx), tsc[i], detect_thr, 1, max_toa, win.at(g.windowLen),
+                                                 win.at(g.windowLen + g.corrLen), &amp, &toa, request != 0, chan, &off);
+  const bool have = ok && request;
+  if (POLICY) {
+    float4 *q = reinterpret_cast<float4 *>(det + i);
+    q[0] = make_float4(avg_pwr, ok ? 1.0F : 0.0F, amp.x, amp.y);
+    q[1] = make_float4(toa, have ? off : 0.0F, 0.0F, 0.0F);
+    q[2] = have ? make_float4(chan[0].x, chan[0].y, chan[1].x, chan[1].y) : make_float4(0.F, 0.F, 0.F, 0.F);
+    q[3] = have ? make_float4(chan[2].x, chan[2].y, chan[3].x, chan[3].y) : make_float4(0.F, 0.F, 0.F, 0.F);
+    q[4] = have ? make_float4(chan[4].x, chan[4].y, chan[5].x, chan[5].y) : make_float4(0.F, 0.F, 0.F, 0.F);
+    return;
+  }
+  if (out.flag) out.flag[i] = ok ? 1 : 0;
+  if (out.amp) out.amp[i] = amp;
+  if (out.toa) out.toa[i] = toa;
+  if (out.off) out.off[i] = have ? off : 0.0F;
+  if (out.chan) for (int j = 0; j < 6; j++) out.chan[i * 6 + j] = have ? chan[j] : mk(0.0F, 0.0F);
+}
+int configure_detect_52m() {
+  const int bytes = (int)detect_52m_smem(60);
+  cudaError_t e = cudaFuncSetAttribute(k_detect_52m<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaFuncSetAttribute(k_detect_52m<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
 int launch_analyze_52m(const DevTables *T, BurstSrc src, const uint8_t *tsc, long long n, float detect_thr, unsigned max_toa,
                        int request, NormalOut out, cf *scratch, cudaStream_t st) {
   if (n <= 0) return 0;
+  if (src.sps == 1 && max_toa <= 60) {                  // tile-staged: the global scratch is not touched
+    k_detect_52m<false><<<(unsigned)((n + 31) / 32), 32, detect_52m_smem(max_toa), st>>>(T, src, tsc, n, detect_thr, max_toa, request, out,
+                                                                                        nullptr, nullptr);
+    return 1;
+  }
   k_analyze_52m<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(T, src, tsc, n, detect_thr, max_toa, request, out, scratch,
                                                          analyze_52m_scratch_stride(max_toa, src.sps));
   return 1;
@@ -1070,6 +1163,7 @@ int configure_kernels() {
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_slicer_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEqTileBytes);
   if (e != cudaSuccess) return (int)e;
+  if (configure_detect_52m() != 0) return -52;
   e = cudaFuncSetAttribute(k_equalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRachSmem);
   return (int)e;
 }

@@ -25,6 +25,14 @@ struct BurstSrc {
   long long arfcn_pitch = 0;
 };
 
+// which of the reference's two transceivers a caller-policy pull follows: the main one (Transceiver/), or the second
+// (Transceiver52M/): windowed midamble search over +-max_toa symbols, stride-4 energy window, and -- when need_dfe is false
+// (mMaxExpectedDelay <= 1, Transceiver52M/Transceiver.cpp:272) -- no channel estimate and no equaliser
+struct TrxVariant {
+  bool v52m = false, need_dfe = true;
+  unsigned max_toa = 0;
+};
+
 struct NormalOut {      // per burst; null pointers are skipped
   int *flag;            // detection flag                                   (analyzeTrafficBurst return)
   cf *amp;              // amplitude estimate
@@ -107,11 +115,12 @@ void launch_energy_detect_52m(const cf *v, int n, unsigned win, float thr, float
 int launch_xcch_decode(const unsigned char *soft, int burst_pitch, long long nframes, unsigned char *u, int *ok, cudaStream_t st);
 int launch_rach_decode(const unsigned char *soft, int burst_pitch, long long n, unsigned char *u, int *fields, cudaStream_t st);
 // the caller-policy pipeline (trx_policy.cuh / trx_kernels.cuh)
-size_t trx_scratch_bytes(long long n, long long nr, int narfcn);
+size_t trx_scratch_bytes(long long n, long long nr, int narfcn, bool slice_all = false);
+void launch_usrpify(const cf *x, long long n, int16_t *out, cudaStream_t st);
 int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, int fn0, const cf *bursts, long long pitch,
                     long long stream_pitch, const uint8_t *kind, const uint8_t *tsc, const int *rach_idx, const int *rach_slot,
                     long long nr, void *scratch, int *valid, unsigned char *dgram, int dgram_pitch, cudaStream_t stream,
-                    cudaStream_t side = nullptr, cudaEvent_t *ev = nullptr);
+                    cudaStream_t side = nullptr, cudaEvent_t *ev = nullptr, TrxVariant var = TrxVariant());
 
 // scratch (complex samples) the generic-sps global-memory variants need per burst
 __host__ __device__ inline size_t scratch_per_burst(int sps) { return (size_t)(2 * 157 + 36) * sps + 64; }

@@ -11,13 +11,13 @@ struct __align__(16) DfeRec {           // a designed equaliser, by the index of
 __global__ void k_trx_policy(const DevTables *__restrict__ T, TrxState *__restrict__ st, int narfcn, int nframes, int fn0,
                              const DetRec *__restrict__ det, const int *__restrict__ rach_slot,
                              const int *__restrict__ rach_flag, int *__restrict__ act, double *__restrict__ thr_at,
-                             int *__restrict__ commit) {
+                             int *__restrict__ commit, int need_dfe) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= narfcn) return;
   TrxScalars s;
   trx_load_scalars(st[a], s);
   int cm[8];
-  trx_policy_arfcn(s, nframes, fn0, narfcn, a, det, rach_slot, rach_flag, T->exp_neg, act, thr_at, cm);
+  trx_policy_arfcn(s, nframes, fn0, narfcn, a, det, rach_slot, rach_flag, T->exp_neg, act, thr_at, cm, need_dfe != 0);
   // w, b and chan_off of the state are committed by k_trx_commit once pass 3 has designed them
   trx_store_scalars(st[a], s);
 #pragma unroll
@@ -82,6 +82,26 @@ __global__ void k_trx_eqparams(long long n, int narfcn, const DetRec *__restrict
   eqp[i] = e;
 }
 
+// pass 3b without the equaliser (second variant, need_dfe == false): every accepted burst -- normal or access -- goes through
+// demodulateBurst with its own amplitude and TOA (Transceiver52M/Transceiver.cpp:382-386); one record per burst of the batch
+__global__ void k_trx_slice_params(long long n, const DetRec *__restrict__ det, const int *__restrict__ act,
+                                   const int *__restrict__ rach_slot, const cf *__restrict__ rach_amp,
+                                   const float *__restrict__ rach_toa, EqParams *__restrict__ eqp) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int a = act[i];
+  float4 q = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
+  if (a == ACT_SLICE || a == ACT_RACH) {
+    cf amp;
+    float toa;
+    if (a == ACT_RACH) { const int j = rach_slot[i]; amp = rach_amp[j]; toa = rach_toa[j]; }
+    else { amp = mk(det[i].amp_x, det[i].amp_y); toa = det[i].toa; }
+    const cf ia = cdiv(mk(1.0F, 0.0F), amp);                                             // ((complex) 1.0)/channel
+    q = make_float4(ia.x, ia.y, toa, 1.0F);
+  }
+  reinterpret_cast<float4 *>(eqp + i)[0] = q;
+}
+
 // RACH bursts the policy did not accept (energy gate) must not be demodulated
 __global__ void k_trx_rach_veto(long long nr, const int *__restrict__ rach_idx, const int *__restrict__ act,
                                 EqParams *__restrict__ eqp_r) {
@@ -96,7 +116,8 @@ __global__ void k_trx_rach_veto(long long nr, const int *__restrict__ rach_idx, 
 __global__ void k_trx_datagram(const DevTables *__restrict__ T, long long n, int narfcn, int fn0, const DetRec *__restrict__ det, const int *__restrict__ act,
                                const int *__restrict__ rach_slot, const cf *__restrict__ rach_amp,
                                const float *__restrict__ rach_toa, const float *__restrict__ rach_soft, int rach_soft_pitch,
-                               int *__restrict__ valid, unsigned char *__restrict__ dgram, int dgram_pitch) {
+                               int *__restrict__ valid, unsigned char *__restrict__ dgram, int dgram_pitch,
+                               const float *__restrict__ soft_by_burst = nullptr) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   unsigned char *dg = dgram + i * (long long)dgram_pitch;
@@ -106,19 +127,21 @@ __global__ void k_trx_datagram(const DevTables *__restrict__ T, long long n, int
     const int tn = (int)(i & 7), fn = (int)((fn0 + i / (8LL * narfcn)) % kHyperframe);
     cf amp;
     float toa;
-    if (a == ACT_RACH) {
-      const int j = rach_slot[i];
-      amp = rach_amp[j]; toa = rach_toa[j];
-      const float *sp = rach_soft + (long long)j * rach_soft_pitch;
+    if (a == ACT_RACH) { const int j = rach_slot[i]; amp = rach_amp[j]; toa = rach_toa[j]; }
+    else { amp = mk(det[i].amp_x, det[i].amp_y); toa = det[i].toa; }
+    if (a == ACT_RACH || soft_by_burst) {
+      // soft floats -> datagram bytes: the compact access-burst rows, or (no-equaliser mode) this burst's own row
+      const float *sp = soft_by_burst ? soft_by_burst + i * rach_soft_pitch : rach_soft + (long long)rach_slot[i] * rach_soft_pitch;
       for (int m = 0; m < 148; m += 4) {
         const unsigned w = trx_soft_byte(sp[m]) | (trx_soft_byte(sp[m + 1]) << 8) | (trx_soft_byte(sp[m + 2]) << 16) |
                            ((unsigned)trx_soft_byte(sp[m + 3]) << 24);
         *reinterpret_cast<unsigned *>(dg + 8 + m) = w;
       }
-    } else {
-      amp = mk(det[i].amp_x, det[i].amp_y); toa = det[i].toa;
+      if (soft_by_burst) *reinterpret_cast<unsigned *>(dg + 156) = 0u;                  // bytes 156..159 (the equaliser's job otherwise)
     }
     trx_datagram_header(T, hdr, tn, fn, amp, toa, 1);
+  } else if (soft_by_burst) {
+    for (int m = 8; m < 160; m += 4) *reinterpret_cast<unsigned *>(dg + m) = 0u;       // rows of invalid bursts are zero
   }
   unsigned h0 = 0, h1 = 0;                                   // rows are 4-byte aligned (dgram_pitch % 4 == 0)
 #pragma unroll
@@ -146,13 +169,16 @@ struct TrxScratch {                     // device scratch of one pull (caller-ow
   int *rach_flag; cf *rach_amp; float *rach_toa; float *rach_soft; EqParams *eqp_r; cf *rach_cs;
 };
 constexpr int kTrxRachSoftPitch = 160;
-size_t trx_scratch_bytes(long long n, long long nr, int narfcn) {
+// slice_all: the no-equaliser mode demodulates every accepted burst into a float row of its own (n rows instead of nr)
+size_t trx_scratch_bytes(long long n, long long nr, int narfcn, bool slice_all) {
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  if (slice_all) nr = n;
   return up(n * sizeof(DetRec)) + up(n * 4) + up(n * 8) + up(n * sizeof(DfeRec)) + up(n * sizeof(EqParams)) + up((size_t)narfcn * 8 * 4) +
          up(nr * 4 + 4) + up(nr * 8 + 8) + up(nr * 4 + 4) + up(nr * kTrxRachSoftPitch * 4 + 4) + up(nr * sizeof(EqParams) + 16) + up(nr * 160 * sizeof(cf) + 16);
 }
-static TrxScratch trx_carve(void *base, long long n, long long nr, int narfcn) {
+static TrxScratch trx_carve(void *base, long long n, long long nr, int narfcn, bool slice_all) {
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  if (slice_all) nr = n;
   char *p = reinterpret_cast<char *>(base);
   TrxScratch s;
   s.det = (DetRec *)p; p += up(n * sizeof(DetRec));
@@ -177,14 +203,15 @@ static TrxScratch trx_carve(void *base, long long n, long long nr, int narfcn) {
 int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, int fn0, const cf *bursts, long long pitch,
                     long long stream_pitch, const uint8_t *kind, const uint8_t *tsc, const int *rach_idx, const int *rach_slot,
                     long long nr, void *scratch, int *valid, unsigned char *dgram, int dgram_pitch, cudaStream_t stream,
-                    cudaStream_t side, cudaEvent_t *ev) {
+                    cudaStream_t side, cudaEvent_t *ev, TrxVariant var) {
   const long long n = (long long)nframes * narfcn * 8;
   if (n <= 0) return 0;
+  const bool slice_all = var.v52m && !var.need_dfe;
   // The access-burst kernels work on a few percent of the slots and fill a fraction of the GPU: they run on a side
   // stream (when the caller supplies one and four events) next to the normal-burst kernels they do not depend on.
   const bool fork = side != nullptr && ev != nullptr && nr > 0;
   cudaStream_t rs = fork ? side : stream;
-  const TrxScratch s = trx_carve(scratch, n, nr, narfcn);
+  const TrxScratch s = trx_carve(scratch, n, nr, narfcn, slice_all);
   BurstSrc src{bursts, pitch, nullptr, 0, 1};
   if (pitch == 0) { src.narfcn = narfcn; src.arfcn_pitch = stream_pitch; }
   int launches = 0;
@@ -192,7 +219,9 @@ int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, i
   NormalOut none{};
   // pass 1
   if (fork) { cudaEventRecord(ev[0], stream); cudaStreamWaitEvent(rs, ev[0], 0); }        // inputs (maps, bursts) are ready
-  if (nwarps >= kDetWideMin)
+  if (var.v52m)      // the second variant's pass 1: stride-4 energy, windowed midamble search (channel only when it can be used)
+    k_detect_52m<true><<<(unsigned)nwarps, 32, detect_52m_smem(var.max_toa), stream>>>(T, src, tsc, n, 3.0F, var.max_toa, var.need_dfe ? 1 : 0, none, kind, s.det);
+  else if (nwarps >= kDetWideMin)
     k_detect_design<kDetWarps, true><<<(unsigned)((nwarps + kDetWarps - 1) / kDetWarps), 32 * kDetWarps, detect_smem<kDetWarps>(), stream>>>(T, src, tsc, n, 3.0F, 0.0F, 0.0F, none, nullptr, kind, s.det);
   else
     k_detect_design<1, true><<<(unsigned)nwarps, 32, detect_smem<1>(), stream>>>(T, src, tsc, n, 3.0F, 0.0F, 0.0F, none, nullptr, kind, s.det);
@@ -207,7 +236,17 @@ int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, i
     launches++;
   }
   // pass 2
-  k_trx_policy<<<(narfcn + 31) / 32, 32, 0, stream>>>(T, st, narfcn, nframes, fn0, s.det, rach_slot, s.rach_flag, s.act, s.thr_at, s.commit);
+  k_trx_policy<<<(narfcn + 31) / 32, 32, 0, stream>>>(T, st, narfcn, nframes, fn0, s.det, rach_slot, s.rach_flag, s.act, s.thr_at, s.commit,
+                                                      slice_all ? 0 : 1);
+  if (slice_all) {
+    // pass 3 without the equaliser: one demodulateBurst pass over the whole batch (accepted normal AND access bursts),
+    // then the datagrams from each burst's own soft row
+    k_trx_slice_params<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, s.det, s.act, rach_slot, s.rach_amp, s.rach_toa, s.eqp);
+    k_slicer_fast<<<(unsigned)nwarps, 32, kEqTileBytes, stream>>>(T, src, n, s.eqp, s.rach_soft, kTrxRachSoftPitch);
+    k_trx_datagram<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(T, n, narfcn, fn0, s.det, s.act, rach_slot, s.rach_amp, s.rach_toa,
+                                                                        s.rach_soft, kTrxRachSoftPitch, valid, dgram, dgram_pitch, s.rach_soft);
+    return launches + 4;
+  }
   // pass 3
   k_trx_design<<<(unsigned)((n + 63) / 64), 64, 0, stream>>>(n, s.det, s.act, s.thr_at, s.dfe);
   if (fork) { cudaEventRecord(ev[2], stream); cudaStreamWaitEvent(rs, ev[2], 0); }        // act[] is final

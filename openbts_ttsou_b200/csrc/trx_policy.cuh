@@ -25,7 +25,8 @@ namespace btsdsp {
 constexpr int kHyperframe = 2048 * 26 * 51;                     // GSMCommon.h:306
 enum ChanType { CT_NONE = 0, CT_I, CT_II, CT_III, CT_IV, CT_V, CT_VI, CT_VII, CT_LOOPBACK };   // Transceiver.h ChannelCombination
 enum CorrType { CORR_OFF = 0, CORR_TSC = 1, CORR_RACH = 2, CORR_IDLE = 3 };                      // Transceiver.h CorrType
-enum TrxAct { ACT_NONE = -3, ACT_CARRIED = -2, ACT_RACH = -1 };   // >= 0: equalise with the DFE designed from that burst
+enum TrxAct { ACT_SLICE = -4, ACT_NONE = -3, ACT_CARRIED = -2, ACT_RACH = -1 };   // >= 0: equalise with the DFE designed from that burst
+// ACT_SLICE: a normal burst demodulated without the equaliser (the second variant's short-range mode, see need_dfe below)
 constexpr int kExpTable = 1024;                                   // exp(-n), n = 0..1023, from the host's libm
 
 struct TrxState {                       // layout is part of the ABI (btsdsp_trx_get_state)
@@ -115,10 +116,12 @@ BTS_HD void trx_store_scalars(TrxState &st, const TrxScalars &s) {
 // (unchanged) -- the caller copies it into st.w/b/chan_off once pass 3 has designed it.
 // A frame's eight records are fetched up front (independent loads), then walked in TN order.
 BTS_HD float trx_snr_estimate(cf amp, double thr) { return (float)((double)cnorm2(amp) / (thr * thr + 1.0)); }   // :340
+// need_dfe = false is the second transceiver variant with mMaxExpectedDelay <= 1 (Transceiver52M/Transceiver.cpp:272): the
+// channel is never estimated (:322) and detected normal bursts go through demodulateBurst like access bursts (:382).
 BTS_HD void trx_policy_arfcn(TrxScalars &st, int nframes, int fn0, int narfcn, int a, const DetRec *__restrict__ det,
                              const int *__restrict__ rach_slot, const int *__restrict__ rach_flag,
                              const double *__restrict__ exp_table, int *__restrict__ act, double *__restrict__ thr_at,
-                             int *__restrict__ commit) {
+                             int *__restrict__ commit, bool need_dfe = true) {
   int src[8];
   float lax[8], lay[8];                     // amplitude and threshold of the last detected TSC burst per timeslot:
   double lthr[8];                           // SNRestimate[tn] of the state is computed from them once, at the end
@@ -151,6 +154,7 @@ BTS_HD void trx_policy_arfcn(TrxScalars &st, int nframes, int fn0, int narfcn, i
       if (corr == CORR_TSC) {
         bool estimate = false;
         if ((double)fn_delta(fn, st.est_fn[tn]) > 50 || !st.have[tn]) { st.have[tn] = 0; estimate = true; }   // :315-326
+        if (!need_dfe) estimate = false;                                                 // Transceiver52M/Transceiver.cpp:322
         success = fl[tn] != 0.0F;
         if (success) {
           st.thr -= 1.0F;                                                               // :338-339
@@ -163,7 +167,7 @@ BTS_HD void trx_policy_arfcn(TrxScalars &st, int nframes, int fn0, int narfcn, i
             src[tn] = (int)i;
             thr_at[i] = st.thr;
           }
-          ac[tn] = src[tn];
+          ac[tn] = need_dfe ? src[tn] : (int)ACT_SLICE;
         } else {
           st.thr += 10.0F * exp_neg_frames(exp_table, fn_delta(fn, st.prev_false_fn));  // :353-355
           st.prev_false_fn = fn;

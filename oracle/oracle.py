@@ -69,6 +69,37 @@ class Oracle52:
                                     c_i(int(request)), _ptr(amp), _ptr(toa), _ptr(chan), _ptr(off))
         return bool(ok), amp[0], toa[0], chan, off[0]
 
+    # ---- that variant's caller policy and transmit side (Transceiver52M/Transceiver.cpp) ----
+    def trx_new(self, tsc, chan_type, start_fn=0):
+        self.lib.ref52_setup(c_i(1))
+        assert self.lib.ref52_trx_state_bytes() == Oracle.TRX_STATE_DTYPE.itemsize
+        st = np.zeros(1, Oracle.TRX_STATE_DTYPE)
+        ct = np.ascontiguousarray(chan_type, np.int32)
+        self.lib.ref52_trx_init(_ptr(st), c_i(tsc), _ptr(ct), c_i(start_fn))
+        return st
+
+    def trx_pull(self, st, bursts, fn0, max_expected_delay):
+        """bursts: (nframes*8, pitch) complex64 of one ARFCN in FIFO order.  Returns (valid[n], dgram[n,160])."""
+        bursts = _c64(bursts)
+        n, pitch = bursts.shape
+        valid = np.zeros(n, np.int32)
+        dg = np.zeros((n, 160), np.uint8)
+        self.lib.ref52_setup(c_i(1))
+        self.lib.ref52_trx_pull(_ptr(st), _ptr(bursts), c_i(pitch), c_i(n // 8), c_i(fn0), c_i(max_expected_delay), _ptr(valid),
+                                _ptr(dg), c_i(160))
+        return valid, dg
+
+    def tx_datagrams(self, dgram, fn0, nframes, filler=None):
+        """TX datagrams (n, >=154) uint8 -> (iq[nframes*1250, 2] int16 at the symbol rate, placed)"""
+        dgram = np.ascontiguousarray(dgram, np.uint8)
+        filler = None if filler is None else np.ascontiguousarray(filler, np.uint8)
+        out = np.zeros((nframes * 1250, 2), np.int16)
+        self.lib.ref52_setup(c_i(1))
+        self.lib.ref52_tx_datagrams.restype = ctypes.c_long
+        placed = self.lib.ref52_tx_datagrams(_ptr(dgram), c_l(dgram.shape[0]), c_i(dgram.shape[1]), c_i(fn0), c_i(nframes),
+                                             None if filler is None else _ptr(filler), _ptr(out))
+        return out, placed
+
     def energy_detect(self, v, win, thr):
         v = _c64(v)
         avg = np.zeros(1, np.float32)

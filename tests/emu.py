@@ -60,6 +60,15 @@ class Emu:
                               P(dg), c_i(158))
         return valid, dg
 
+    def trx_pull_52m(self, st, bursts, fn0, max_delay):
+        bursts = np.ascontiguousarray(bursts, np.complex64)
+        n, pitch = bursts.shape
+        valid = np.zeros(n, np.int32)
+        dg = np.zeros((n, 158), np.uint8)
+        self.lib.emu_trx_pull_52m(P(st), c_i(st.size), P(bursts), c_ll(pitch), c_i(n // (8 * st.size)), c_i(fn0), c_i(max_delay),
+                                  P(valid), P(dg), c_i(158))
+        return valid, dg
+
     def tx_fused(self, bits, scale=None):
         """bits (nslots, 148) uint8 -> int16 (nchunks*864, 2): the fused TX kernel's arithmetic on the CPU"""
         bits = np.ascontiguousarray(bits, np.uint8)

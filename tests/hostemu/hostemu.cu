@@ -495,9 +495,10 @@ void emu_trx_init(void *state, int narfcn, const uint8_t *tsc, const uint8_t *ch
     for (int tn = 0; tn < 8; tn++) { st[a].chan_type[tn] = chan_type[a * 8 + tn]; st[a].est_fn[tn] = start_fn; }
   }
 }
-void emu_trx_pull(void *state, int narfcn, const float *bursts, long long pitch, int nframes, int fn0, int *valid,
-                  unsigned char *dgram, int dgram_pitch) {
+static void emu_trx_pull_impl(void *state, int narfcn, const float *bursts, long long pitch, int nframes, int fn0, int *valid,
+                              unsigned char *dgram, int dgram_pitch, bool v52m, unsigned max_delay) {
   TrxState *st = (TrxState *)state;
+  const bool need_dfe = !v52m || max_delay > 1;
   const long long n = (long long)nframes * narfcn * 8;
   std::vector<DetRec> det(n);
   std::vector<int> act(n), slot(n, -1), rflag, ridx;
@@ -513,16 +514,25 @@ void emu_trx_pull(void *state, int narfcn, const float *bursts, long long pitch,
     cf *src = (cf *)bursts + i * pitch;
     DetRec d;
     memset(&d, 0, sizeof d);
-    energy_detect<1>(View<1>{src}, len, 20, 0.0F, &d.energy);
+    if (v52m) energy_detect_52m<1>(View<1>{src}, len, 20, 0.0F, &d.energy);
+    else energy_detect<1>(View<1>{src}, len, 20, 0.0F, &d.energy);
     cf amp = mk(0.0F, 0.0F);
     float toa = 0.0F, off = 0.0F;
     if (corr == CORR_TSC) {
       cf chan[6];
       for (int j = 0; j < 6; j++) chan[j] = mk(0.0F, 0.0F);
       cf *s = scratch.data();
-      const bool ok = analyze_traffic<1, true>(T, View<1>{src}, st[a].tsc, 3.0F, 1, View<1>{s}, View<1>{s + 36}, &amp, &toa, true, chan, &off);
+      bool ok;
+      if (v52m) {
+        std::vector<cf> s52(2 * 130);
+        ok = analyze_traffic_52m<1>(T, View<1>{src}, st[a].tsc, 3.0F, 1, max_delay, View<1>{s52.data()}, View<1>{s52.data() + 130},
+                                    &amp, &toa, need_dfe, chan, &off);
+        if (!need_dfe) off = 0.0F;
+      } else {
+        ok = analyze_traffic<1, true>(T, View<1>{src}, st[a].tsc, 3.0F, 1, View<1>{s}, View<1>{s + 36}, &amp, &toa, true, chan, &off);
+      }
       d.flag = ok ? 1.0F : 0.0F; d.amp_x = amp.x; d.amp_y = amp.y; d.toa = toa; d.off = ok ? off : 0.0F;
-      for (int j = 0; j < 6; j++) d.chan[j] = ok ? chan[j] : mk(0.0F, 0.0F);
+      for (int j = 0; j < 6; j++) d.chan[j] = (ok && need_dfe) ? chan[j] : mk(0.0F, 0.0F);
     } else if (corr == CORR_RACH) {
       cf *s = scratch.data();
       const bool ok = detect_rach<1, true>(T, View<1>{src}, len, 5.0F, 1, View<1>{s}, &amp, &toa);
@@ -538,7 +548,7 @@ void emu_trx_pull(void *state, int narfcn, const float *bursts, long long pitch,
     TrxScalars sc;
     trx_load_scalars(st[a], sc);
     trx_policy_arfcn(sc, nframes, fn0, narfcn, a, det.data(), slot.data(), rflag.data(), T->exp_neg, act.data(), thr_at.data(),
-                     commit.data() + a * 8);
+                     commit.data() + a * 8, need_dfe);
     trx_store_scalars(st[a], sc);
   }
   // pass 3
@@ -565,8 +575,9 @@ void emu_trx_pull(void *state, int narfcn, const float *bursts, long long pitch,
     memset(soft, 0, sizeof soft);
     cf amp;
     float toa;
-    if (act[i] == ACT_RACH) {
-      amp = ramp[slot[i]]; toa = rtoa[slot[i]];
+    if (act[i] == ACT_RACH || act[i] == ACT_SLICE) {
+      if (act[i] == ACT_RACH) { amp = ramp[slot[i]]; toa = rtoa[slot[i]]; }
+      else { amp = mk(det[i].amp_x, det[i].amp_y); toa = det[i].toa; }
       for (int m = 0; m < len; m++) x[m] = src[m];
       demodulate_burst<1, 1>(T, View<1>{x.data()}, len, 1, amp, toa, View<1>{tmp.data()}, soft);
     } else {
@@ -593,6 +604,16 @@ void emu_trx_pull(void *state, int narfcn, const float *bursts, long long pitch,
     for (int j = 0; j < 5; j++) st[a].b[tn][j] = dfe[commit[k]].b[j];
     st[a].chan_off[tn] = dfe[commit[k]].off;
   }
+}
+
+void emu_trx_pull(void *state, int narfcn, const float *bursts, long long pitch, int nframes, int fn0, int *valid,
+                  unsigned char *dgram, int dgram_pitch) {
+  emu_trx_pull_impl(state, narfcn, bursts, pitch, nframes, fn0, valid, dgram, dgram_pitch, false, 0);
+}
+// the second transceiver variant's policy (Transceiver52M/Transceiver.cpp:268-404)
+void emu_trx_pull_52m(void *state, int narfcn, const float *bursts, long long pitch, int nframes, int fn0, int max_delay,
+                      int *valid, unsigned char *dgram, int dgram_pitch) {
+  emu_trx_pull_impl(state, narfcn, bursts, pitch, nframes, fn0, valid, dgram, dgram_pitch, true, (unsigned)max_delay);
 }
 
 // k_tx_fused replayed on the CPU: modulate into the step's tile, 96 phases per period through tx_part, quantise
