@@ -219,6 +219,7 @@ BTS_HD bool analyze_fast(Grid grid, const DevTables *__restrict__ T, View<S> win
 #define BTS_EQ_ROWS 56
 #endif
 constexpr int kEqRows = BTS_EQ_ROWS;  // rows of the rolling tile (56 rows = 14.8 KB per warp: 14-15 one-warp CTAs per SM at 128 registers)
+constexpr int kEqRing = 32;          // rows of the ring tile (k_equalize_ring): a step reads 24, four more arrive, four are free
 constexpr int kEqStart = -12;        // first pipeline step: three priming steps fill the window
 constexpr int kEqLook = 23;          // step(m0) reads burst rows m0 - io .. m0 - io + 23
 
@@ -284,6 +285,41 @@ struct EqLane {
     }
   }
 
+  // The same over a RING of kEqRing tile rows indexed by mu = burst row + io -- the lane's own output timeline: block mb
+  // (F[x0..x0+3], x0 = mb - io + 6) reads burst rows x0-10 .. x0+13, i.e. mu = mb-4 .. mb+19, which sit in the same ring
+  // slots for every lane of the warp whatever its integer delay.  mb is a multiple of 4, so the 24 rows are six groups of
+  // four consecutive slots: six wrapped base addresses, compile-time offsets inside a group.
+  template <bool CHECKED>
+  BTS_HD void newF4_ring(int mb, cf out[4]) const {
+    cf acc[4], center[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) { acc[r] = mk(0.0F, 0.0F); center[r] = mk(0.0F, 0.0F); }
+    View<S> grp[6];
+#pragma unroll
+    for (int g = 0; g < 6; g++) grp[g] = a.at((mb - 4 + 4 * g) & (kEqRing - 1));
+#pragma unroll
+    for (int jj = 0; jj < 24; jj++) {
+      const int c = 23 - jj;                                       // row mu = mb - 4 + c = burst row x0 + 13 - jj
+      const cf v = grp[c >> 2].ld(c & 3);
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int k = r - 3 + jj;
+        if (k >= 0 && k <= 20) acc[r] = padd(acc[r], pmul0(v, s[k]));
+        if (k == 10) center[r] = v;
+      }
+    }
+    const int x0 = mb - io + 6;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      cf f = nofrac ? center[r] : acc[r];
+      if (CHECKED) {
+        const int x = x0 + r;
+        if (!((unsigned)x < (unsigned)N && (unsigned)(x + io) < (unsigned)N)) f = mk(0.0F, 0.0F);
+      }
+      out[r] = f;
+    }
+  }
+
   // step(m0 - 4) may take the unchecked path: every F of block m0 is a sample of the delayed burst, and the block
   // fed back in that step (m0 - 4) has five past decisions (m0 - 4 >= 8 keeps the EDGE feedback for the first blocks)
   BTS_HD bool interior(int m0) const {
@@ -292,9 +328,10 @@ struct EqLane {
   }
 
   // feed-forward outputs y[m0..m0+3] (consumes the window, then slides it by 4)
-  template <bool CHECKED>
+  template <bool CHECKED, bool RING = false>
   BTS_HD void compute_y(int base, int m0, cf y[4]) {
-    newF4<CHECKED>(base, m0 - io + 6, &Fw[6]);
+    if (RING) newF4_ring<CHECKED>(m0, &Fw[6]);
+    else newF4<CHECKED>(base, m0 - io + 6, &Fw[6]);
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       cf sum = mk(0.0F, 0.0F);
@@ -329,7 +366,7 @@ struct EqLane {
   }
 
   // one pipeline step: feed-forward for the NEXT block (independent work) + feedback for the current one
-  template <bool CHECKED>
+  template <bool CHECKED, bool RING = false>
   BTS_HD void step(const DevTables *__restrict__ T, int base, int m0, cf ycur[4], float soft[4]) {
     cf rot[4], revrot[4];                                         // fetched first: off the feedback chain's critical path
 #pragma unroll
@@ -339,7 +376,7 @@ struct EqLane {
       revrot[r] = T->revrot[mi];
     }
     cf ynext[4];
-    compute_y<CHECKED>(base, m0 + 4, ynext);
+    compute_y<CHECKED, RING>(base, m0 + 4, ynext);
     if (CHECKED && m0 < 8) feedback4<true>(m0, ycur, rot, revrot, soft);
     else feedback4<false>(m0, ycur, rot, revrot, soft);
 #pragma unroll

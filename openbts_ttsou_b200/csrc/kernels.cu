@@ -8,6 +8,7 @@
 // runs the reference's scalar algorithm over its own column (sigproc_device.cuh).  That keeps each
 // comparison bit-identical to the reference while all 32 lanes of every instruction do useful work;
 // throughput comes from bursts in flight, not from splitting one burst across lanes.
+#include <stdlib.h>
 #include "kernels.cuh"
 #include "sigproc_device.cuh"
 #include "demod_fast.cuh"
@@ -588,6 +589,141 @@ __global__ void __launch_bounds__(WARPS * 32) k_equalize_fast(const DevTables *_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// k_equalize_ring: the same equaliser over a RING tile fed by a software pipeline instead of a rolling tile that is
+// re-staged every eight steps.
+//   * tile = kEqRing (32) rows per lane, row slot = (burst row + io) & 31: indexed on each lane's own output timeline,
+//     so a step's 24 rows are in the same slots for every lane whatever its integer delay (no io_min/io_max policy,
+//     no spread limit), 8.4 KB per warp instead of 14.8 KB (registers, not shared memory, now bound residency: 16/SM);
+//   * every step the warp brings in the four rows the NEXT step newly needs, for all 32 bursts: lane L loads row
+//     (L & 3) of bursts (L >> 2) + 8t, t = 0..3 -- 32-byte runs of eight bursts per instruction -- into registers at the
+//     top of step s, and at the top of step s + 1 scales them by that burst's 1/amplitude (scaleVector,
+//     Transceiver.cpp:391) and stores them.  The loads have a whole step (~700 instructions) to land; nothing waits;
+//   * each burst row is fetched and scaled exactly once (the rolling tile re-fetched 24 of every 56 rows).
+// Per-burst source records (pointer already offset by -io, valid mu range, 1/amp) sit in a 1 KB shared-memory table.
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) EqSrc {
+  const cf *p;          // burst base - io: sample of timeline index mu is p[mu]
+  int lo, hi;           // mu in [lo, hi) exists in the burst; elsewhere the tile holds zeros
+  float iax, iay;       // 1/amplitude
+  int pad0, pad1;
+};
+constexpr size_t kEqRingBytes = (size_t)kEqRing * kTileStride * sizeof(cf) + 32 * sizeof(EqSrc);
+
+__device__ __forceinline__ void eq_ring_fetch(const EqSrc *__restrict__ tab, int lane, int mu0, cf v[4]) {
+  const int mu = mu0 + (lane & 3);
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    const int4 e = *reinterpret_cast<const int4 *>(&tab[(lane >> 2) + 8 * t]);       // p, lo, hi
+    const cf *p = reinterpret_cast<const cf *>((unsigned long long)(unsigned)e.x | ((unsigned long long)(unsigned)e.y << 32));
+    v[t] = (mu >= e.z && mu < e.w) ? __ldg(p + mu) : mk(0.0F, 0.0F);
+  }
+}
+__device__ __forceinline__ void eq_ring_store(cf *__restrict__ A, const EqSrc *__restrict__ tab, int lane, int mu0, const cf v[4]) {
+  cf *dst = A + ((mu0 + (lane & 3)) & (kEqRing - 1)) * kTileStride + (lane >> 2);
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    const float2 ia = *reinterpret_cast<const float2 *>(&tab[(lane >> 2) + 8 * t].iax);
+    dst[8 * t] = cmul(v[t], mk(ia.x, ia.y));
+  }
+}
+
+template <bool U8>
+__global__ void __launch_bounds__(32, 16) k_equalize_ring(const DevTables *__restrict__ T, BurstSrc src, long long n,
+                                                      const EqParams *__restrict__ eqp, void *__restrict__ soft_,
+                                                      int soft_pitch, int row_bytes = 0) {
+  const int row_words = (row_bytes > 0 ? row_bytes : soft_pitch) / 4;
+  float *soft = reinterpret_cast<float *>(soft_);
+  unsigned char *soft8 = reinterpret_cast<unsigned char *>(soft_);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x;
+  cf *A = reinterpret_cast<cf *>(smem_raw);
+  EqSrc *tab = reinterpret_cast<EqSrc *>(A + kEqRing * kTileStride);
+  const long long w0 = (long long)blockIdx.x * 32;
+  if (w0 >= n) return;
+  const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
+  const long long i = w0 + lane;
+  long long start = 0;
+  int len = 0;
+  bool ok = false;
+  cf ia = mk(0.0F, 0.0F), w[7], fb[5];
+  float toa_eq = 0.0F;
+  if (lane < nv) {
+    burst_loc(src, i, &start, &len);
+    if (len > kBurstRows - 3) len = kBurstRows - 3;
+    const float4 *q = reinterpret_cast<const float4 *>(eqp + i);
+    const float4 q0 = __ldg(q);
+    ok = q0.w != 0.0F;
+    if (ok) {
+      const float4 q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4), q5 = __ldg(q + 5), q6 = __ldg(q + 6);
+      ia = mk(q0.x, q0.y); toa_eq = q0.z;
+      w[0] = mk(q1.x, q1.y); w[1] = mk(q1.z, q1.w); w[2] = mk(q2.x, q2.y); w[3] = mk(q2.z, q2.w);
+      w[4] = mk(q3.x, q3.y); w[5] = mk(q3.z, q3.w); w[6] = mk(q4.x, q4.y);
+      fb[0] = mk(q4.z, q4.w); fb[1] = mk(q5.x, q5.y); fb[2] = mk(q5.z, q5.w); fb[3] = mk(q6.x, q6.y); fb[4] = mk(q6.z, q6.w);
+    }
+  }
+  float *row = soft + i * (long long)soft_pitch;
+  unsigned *row8 = reinterpret_cast<unsigned *>(soft8 + i * (long long)soft_pitch);
+  const bool vec = ((reinterpret_cast<uintptr_t>(row) | (uintptr_t)(soft_pitch * 4)) & 15) == 0;
+  if (!ok && lane < nv) {                       // undetected: the row is all zeros
+    if (U8) for (int m = 0; m < row_words; m++) row8[m] = 0u;
+    else if (vec) for (int m = 0; m < soft_pitch; m += 4) *reinterpret_cast<float4 *>(row + m) = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
+    else for (int m = 0; m < soft_pitch; m++) row[m] = 0.0F;
+  }
+  const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+  if (okmask == 0) return;
+
+  EqLane<kTileStride> eq;
+  if (ok) eq.init(Grid{&T->sinc_grid[0][0], 24}, T, View<kTileStride>{A + lane}, len, toa_eq, w, fb);      // :392-396
+  else eq.io = 0;
+  {
+    EqSrc e;
+    e.p = src.base + start - eq.io;             // never dereferenced outside [lo, hi)
+    e.lo = ok ? eq.io : 0;
+    e.hi = ok ? len + eq.io : 0;
+    e.iax = ia.x; e.iay = ia.y; e.pad0 = e.pad1 = 0;
+    tab[lane] = e;
+  }
+  __syncwarp();
+  const int nmax = __reduce_max_sync(0xffffffffu, ok ? len : 0);
+  const int mend = U8 ? (nmax < 148 ? nmax : 148) : (nmax < soft_pitch ? nmax : soft_pitch);
+  cf ycur[4], pend[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) ycur[r] = mk(0.0F, 0.0F);
+  // prologue: step(kEqStart) reads mu = kEqStart .. kEqStart+23; its first five groups are stored here, the sixth is
+  // left pending in registers exactly as every later step finds it
+#pragma unroll 1
+  for (int g = 0; g < 5; g++) {
+    eq_ring_fetch(tab, lane, kEqStart + 4 * g, pend);
+    eq_ring_store(A, tab, lane, kEqStart + 4 * g, pend);
+  }
+  eq_ring_fetch(tab, lane, kEqStart + 20, pend);
+#pragma unroll 1
+  for (int m0 = kEqStart; m0 < mend; m0 += 4) {
+    eq_ring_store(A, tab, lane, m0 + 20, pend);            // the rows this step newly needs (fetched during the previous step)
+    __syncwarp();
+    eq_ring_fetch(tab, lane, m0 + 24, pend);               // ... and the next step's, in flight under this step's arithmetic
+    if (ok) {
+      float s4[4];
+      if (__all_sync(okmask, eq.interior(m0 + 4))) eq.template step<false, true>(T, 0, m0, ycur, s4);
+      else eq.template step<true, true>(T, 0, m0, ycur, s4);
+      if (U8) {
+        if (m0 >= 0 && m0 + 3 < 148)
+          row8[m0 >> 2] = soft_u8(s4[0]) | (soft_u8(s4[1]) << 8) | (soft_u8(s4[2]) << 16) | (soft_u8(s4[3]) << 24);
+      } else {
+        store_soft4(row, vec, soft_pitch, m0, s4, len);
+      }
+    }
+    // (no second barrier: the next step's store goes to the slots of rows mu < m0 - 4, which no lane still reads)
+  }
+  if (ok) {
+    if (U8) for (int m = 37; m < row_words; m++) row8[m] = 0u;
+    else for (int m = len; m < soft_pitch; m++) row[m] = 0.0F;
+  }
+}
+
+static bool g_eq_ring = true;
 size_t demod_scratch_bytes(long long n) { return (size_t)n * sizeof(EqParams); }
 // access bursts: the records plus a 160-sample correlation scratch row per burst (128-byte aligned behind the records)
 size_t rach_scratch_bytes(long long n) { return (((size_t)n * sizeof(EqParams) + 127) & ~(size_t)127) + (size_t)n * 160 * sizeof(cf); }
@@ -607,6 +743,11 @@ int launch_demod_normal(const DevTables *T, BurstSrc src, const uint8_t *tsc, lo
     k_detect_design<1><<<(unsigned)nwarps, 32, detect_smem<1>(), st>>>(T, src, tsc, n, detect_thr, gate_thr, snr_thr, out, eqp);
   if (between) cudaEventRecord(between, st);
   if (!out.soft && !out.soft_u8) return 1;
+  if (g_eq_ring) {     // ring tile + software-pipelined loads (default); BTSDSP_EQ_RING=0 selects the rolling-tile kernel
+    if (out.soft_u8) k_equalize_ring<true><<<(unsigned)nwarps, 32, kEqRingBytes, st>>>(T, src, n, eqp, out.soft_u8, out.soft_pitch);
+    else k_equalize_ring<false><<<(unsigned)nwarps, 32, kEqRingBytes, st>>>(T, src, n, eqp, out.soft, out.soft_pitch);
+    return 2;
+  }
   // one-warp CTAs: 14.8 KB of shared memory and 128 registers per thread each, 14-15 resident per SM
   if (out.soft_u8)
     k_equalize_fast<kEqWarps, true><<<(unsigned)((nwarps + kEqWarps - 1) / kEqWarps), 32 * kEqWarps, equalize_smem<kEqWarps>(), st>>>(T, src, n, eqp, out.soft_u8, out.soft_pitch);
@@ -1164,6 +1305,7 @@ int configure_kernels() {
   e = cudaFuncSetAttribute(k_slicer_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEqTileBytes);
   if (e != cudaSuccess) return (int)e;
   if (configure_detect_52m() != 0) return -52;
+  if (const char *e = getenv("BTSDSP_EQ_RING")) g_eq_ring = atoi(e) != 0;
   e = cudaFuncSetAttribute(k_equalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRachSmem);
   return (int)e;
 }

@@ -251,7 +251,8 @@ int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, i
   k_trx_design<<<(unsigned)((n + 63) / 64), 64, 0, stream>>>(n, s.det, s.act, s.thr_at, s.dfe);
   if (fork) { cudaEventRecord(ev[2], stream); cudaStreamWaitEvent(rs, ev[2], 0); }        // act[] is final
   k_trx_eqparams<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, narfcn, s.det, s.act, s.dfe, st, s.eqp);
-  k_equalize_fast<1, true><<<(unsigned)nwarps, 32, equalize_smem<1>(), stream>>>(T, src, n, s.eqp, dgram + 8, dgram_pitch, 152);
+  if (g_eq_ring) k_equalize_ring<true><<<(unsigned)nwarps, 32, kEqRingBytes, stream>>>(T, src, n, s.eqp, dgram + 8, dgram_pitch, 152);
+  else k_equalize_fast<1, true><<<(unsigned)nwarps, 32, equalize_smem<1>(), stream>>>(T, src, n, s.eqp, dgram + 8, dgram_pitch, 152);
   launches += 4;
   if (nr > 0) {
     k_trx_rach_veto<<<(unsigned)((nr + 127) / 128), 128, 0, rs>>>(nr, rach_idx, s.act, s.eqp_r);
