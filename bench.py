@@ -292,7 +292,7 @@ def leg_config4(torch, dsp, dev, stream, peak, fp32_peak, cores, quick):
            "per_frame_launches": {"bursts_per_launch": 8192, "launches": frames, "ms_per_launch": ms_pf / frames,
                                   "bursts_per_s": n / ms_pf * 1e3},
            "one_launch": {"ms": ms_one, "bursts_per_s": n / ms_one * 1e3, "detect_ms": ms_det, "equalize_ms": ms_eq},
-           "roofline": kernel_entry("k_detect_design + k_equalize_fast", ms_one, n * DEMOD_BYTES_PER_BURST,
+           "roofline": kernel_entry("k_detect_design + k_equalize_ring", ms_one, n * DEMOD_BYTES_PER_BURST,
                                     n * (DETECT_OPS_PER_BURST + EQUALIZE_OPS_PER_BURST), peak, fp32_peak, "fp32-unfused"),
            "detected_of_occupied": float(det[occ].float().mean()), "detected_of_empty": float(det[~occ].float().mean()),
            "ber_detected": float((hard[det] != bits[det]).float().mean()),
@@ -606,10 +606,10 @@ def main():
         k_res = kernel_entry("k_resample_rx_v3", ms_res, nch * RESAMPLE_BYTES_PER_CHUNK, nch * RESAMPLE_OPS_PER_CHUNK, peak,
                              fp32_peak, "hbm")
         # k_detect_design reads the 36-sample midamble window (288 B) and writes flag/amp/toa (16 B) + the 112 B
-        # EqParams record; k_equalize_fast reads the burst (1250 B) + EqParams and writes 148 soft bits
+        # EqParams record; k_equalize_ring reads the burst (1250 B) + EqParams and writes 148 soft bits
         k_det = kernel_entry("k_detect_design", ms_det, nb * (288 + 16 + 112), nb * DETECT_OPS_PER_BURST, peak, fp32_peak,
                              "fp32-unfused")
-        k_eq = kernel_entry("k_equalize_fast", ms_eq, nb * (1250 + 112 + 148 * 4), nb * EQUALIZE_OPS_PER_BURST, peak, fp32_peak,
+        k_eq = kernel_entry("k_equalize_ring", ms_eq, nb * (1250 + 112 + 148 * 4), nb * EQUALIZE_OPS_PER_BURST, peak, fp32_peak,
                             "fp32-unfused")
         prof = ncu_profile(args.blocks)
         for k in (k_res, k_det, k_eq):          # dram bytes and pipe utilisation of the committed ncu capture (static)

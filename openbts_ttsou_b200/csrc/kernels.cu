@@ -609,6 +609,12 @@ struct __align__(16) EqSrc {
   float iax, iay;       // 1/amplitude
   int pad0, pad1;
 };
+#ifndef BTS_EQ_PROLOGUE
+#define BTS_EQ_PROLOGUE 1
+#endif
+#ifndef BTS_EQ_MINCTAS
+#define BTS_EQ_MINCTAS 16
+#endif
 constexpr size_t kEqRingBytes = (size_t)kEqRing * kTileStride * sizeof(cf) + 32 * sizeof(EqSrc);
 
 __device__ __forceinline__ void eq_ring_fetch(const EqSrc *__restrict__ tab, int lane, int mu0, cf v[4]) {
@@ -630,7 +636,7 @@ __device__ __forceinline__ void eq_ring_store(cf *__restrict__ A, const EqSrc *_
 }
 
 template <bool U8>
-__global__ void __launch_bounds__(32, 16) k_equalize_ring(const DevTables *__restrict__ T, BurstSrc src, long long n,
+__global__ void __launch_bounds__(32, BTS_EQ_MINCTAS) k_equalize_ring(const DevTables *__restrict__ T, BurstSrc src, long long n,
                                                       const EqParams *__restrict__ eqp, void *__restrict__ soft_,
                                                       int soft_pitch, int row_bytes = 0) {
   const int row_words = (row_bytes > 0 ? row_bytes : soft_pitch) / 4;
@@ -674,31 +680,46 @@ __global__ void __launch_bounds__(32, 16) k_equalize_ring(const DevTables *__res
   const unsigned okmask = __ballot_sync(0xffffffffu, ok);
   if (okmask == 0) return;
 
-  EqLane<kTileStride> eq;
-  if (ok) eq.init(Grid{&T->sinc_grid[0][0], 24}, T, View<kTileStride>{A + lane}, len, toa_eq, w, fb);      // :392-396
-  else eq.io = 0;
+  const int io = ok ? (int)floorf(-toa_eq) : 0;              // EqLane::init's integer delay, needed before it for the table
   {
     EqSrc e;
-    e.p = src.base + start - eq.io;             // never dereferenced outside [lo, hi)
-    e.lo = ok ? eq.io : 0;
-    e.hi = ok ? len + eq.io : 0;
+    e.p = src.base + start - io;                // never dereferenced outside [lo, hi)
+    e.lo = ok ? io : 0;
+    e.hi = ok ? len + io : 0;
     e.iax = ia.x; e.iay = ia.y; e.pad0 = e.pad1 = 0;
     tab[lane] = e;
   }
   __syncwarp();
-  const int nmax = __reduce_max_sync(0xffffffffu, ok ? len : 0);
-  const int mend = U8 ? (nmax < 148 ? nmax : 148) : (nmax < soft_pitch ? nmax : soft_pitch);
-  cf ycur[4], pend[4];
+  // prologue: step(kEqStart) reads mu = kEqStart .. kEqStart+23.  All six groups are requested at once (their latency
+  // overlaps the rotation-table copy and the lane's own set-up); five are stored before the loop, the sixth stays
+  // pending in registers exactly as every later step finds it
+  cf pend[4];
+#if BTS_EQ_PROLOGUE
+  cf pro[5][4];
 #pragma unroll
-  for (int r = 0; r < 4; r++) ycur[r] = mk(0.0F, 0.0F);
-  // prologue: step(kEqStart) reads mu = kEqStart .. kEqStart+23; its first five groups are stored here, the sixth is
-  // left pending in registers exactly as every later step finds it
+  for (int g = 0; g < 5; g++) eq_ring_fetch(tab, lane, kEqStart + 4 * g, pro[g]);
+#else
 #pragma unroll 1
   for (int g = 0; g < 5; g++) {
     eq_ring_fetch(tab, lane, kEqStart + 4 * g, pend);
     eq_ring_store(A, tab, lane, kEqStart + 4 * g, pend);
   }
+#endif
   eq_ring_fetch(tab, lane, kEqStart + 20, pend);
+  // (A shared-memory copy of the rotation tables in place of the per-step global loads measured 1.40 ms against
+  // 0.96 ms: profiles/README.md r3b.)
+  EqLane<kTileStride> eq;
+  if (ok) eq.init(Grid{&T->sinc_grid[0][0], 24}, T, View<kTileStride>{A + lane}, len, toa_eq, w, fb);      // :392-396
+  else eq.io = 0;
+  const int nmax = __reduce_max_sync(0xffffffffu, ok ? len : 0);
+  const int mend = U8 ? (nmax < 148 ? nmax : 148) : (nmax < soft_pitch ? nmax : soft_pitch);
+  cf ycur[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) ycur[r] = mk(0.0F, 0.0F);
+#if BTS_EQ_PROLOGUE
+#pragma unroll
+  for (int g = 0; g < 5; g++) eq_ring_store(A, tab, lane, kEqStart + 4 * g, pro[g]);
+#endif
 #pragma unroll 1
   for (int m0 = kEqStart; m0 < mend; m0 += 4) {
     eq_ring_store(A, tab, lane, m0 + 20, pend);            // the rows this step newly needs (fetched during the previous step)

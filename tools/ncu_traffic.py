@@ -15,7 +15,7 @@ for r in rows[1:]:
     d = per.setdefault(r[ix["ID"]], {"name": r[ix["Kernel Name"]], "grid": r[ix["Grid Size"]]})
     d[r[ix["Metric Name"]]] = float(r[ix["Metric Value"]].replace(",", "")) * UNIT.get(r[ix["Metric Unit"]], 1.0)
 kern = {}
-for key in ("k_resample_rx_v3", "k_detect_design", "k_equalize_fast"):
+for key in ("k_resample_rx_v3", "k_detect_design", "k_equalize_ring"):
     ls = [d for d in per.values() if key in d["name"]]
     big = max(d["gpu__time_duration.sum"] for d in ls)
     ls = [d for d in ls if d["gpu__time_duration.sum"] > 0.5 * big]          # the full-size launches of the step
