@@ -424,6 +424,10 @@ BTS_HD void design_dfe(const cf *chan, int nu_rt, float SNR, int nf_rt, cf *w, c
   }
 }
 
+// (designDFE with its outer iteration kept as a loop -- L rows parked in the lane's tile column, ~500-instruction body run seven
+// times instead of ~4000 straight-line instructions -- was measured: 0.484 ms against 0.457 ms per 800 280 bursts for the
+// detect kernel, bit-identical; the serial G0/G1 chain no longer overlaps across iterations.  profiles/README.md r3d.)
+
 // equalizeBurst :1343-1399.  burst is delayed in place (as the reference does), tmp = scratch of n
 // samples that ends up holding the post-feedback symbols; soft[m*SS] receives the n soft bits.
 template <int S, int SS>
