@@ -223,6 +223,13 @@ int btsdsp_rx_stream_wire_host(btsdsp_ctx *ctx, const int16_t *iq, int swap_iq, 
 int btsdsp_rx_stream_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nchunks, const uint8_t *tsc,
                          long long nbursts, float detect_thr, float gate_thr, float snr_thr, int32_t *flag,
                          btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch, void *stream);
+/* The same for a piece of a RUNNING stream: has_history != 0 says raw[-192..-1] hold the stream's previous 192 samples, the
+ * state RadioInterface::pullBuffer carries from call to call (rcvHistory, radioInterface.cpp:238-259).  A piece must begin
+ * on a 117-frame boundary of the stream (a multiple of 250 chunks = 936 bursts from its start), so that slot 0 of the piece
+ * is a 157-sample slot.  Pieces processed call after call give exactly the one-call result. */
+int btsdsp_rx_stream_cont_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, int has_history, long long nchunks, const uint8_t *tsc,
+                              long long nbursts, float detect_thr, float gate_thr, float snr_thr, int32_t *flag,
+                              btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch, void *stream);
 /* The transmit path: n x 148 bits -> modulateBurst (guard 8/9 by slot) -> slot stream -> TX resample ->
  * int16 {I,Q}.  n must be a multiple of 4 and 625*n/4 a multiple of 585 (n % 468 == 0), giving
  * 864*(625*n/4/585) output pairs.  Host pointers. */

@@ -70,6 +70,7 @@ _SIGS = {
     "btsdsp_demodulate_dev": (_i, [_vp, _vp, _ll, _vp, _ll, _ll, _vp, _vp, _vp, _i, _vp]),
     "btsdsp_rx_stream_host": (_i, [_vp, _vp, _ll, _vp, _ll, _f, _f, _f, _vp, _vp, _vp, _vp, _i]),
     "btsdsp_rx_stream_dev": (_i, [_vp, _vp, _ll, _vp, _ll, _f, _f, _f, _vp, _vp, _vp, _vp, _i, _vp]),
+    "btsdsp_rx_stream_cont_dev": (_i, [_vp, _vp, _i, _ll, _vp, _ll, _f, _f, _f, _vp, _vp, _vp, _vp, _i, _vp]),
     "btsdsp_tx_stream_host": (_i, [_vp, _vp, _ll, _vp]),
     "btsdsp_tx_stream_dev": (_i, [_vp, _vp, _ll, _vp, _vp]),
     "btsdsp_tx_streams_dev": (_i, [_vp, _vp, _ll, _i, _vp, _vp]),
@@ -393,6 +394,12 @@ class BtsDsp:
                       gate_thr=-1.0, snr_thr=250.0, stream=None):
         self._ck(self.lib.btsdsp_rx_stream_dev(self.h, _p(raw), nchunks, _p(tsc), nbursts, detect_thr, gate_thr, snr_thr,
                                                _p(flag), _p(amp), _p(toa), _p(soft), soft_pitch, _stream(stream)))
+
+    def rx_stream_cont_dev(self, raw, has_history, nchunks, tsc, nbursts, flag, amp, toa, soft, soft_pitch=148, detect_thr=3.0,
+                           gate_thr=-1.0, snr_thr=250.0, stream=None):
+        """a piece of a running stream (raw may be an address: the 192 samples before it must be valid when has_history)"""
+        self._ck(self.lib.btsdsp_rx_stream_cont_dev(self.h, _p(raw), int(has_history), nchunks, _p(tsc), nbursts, detect_thr, gate_thr,
+                                                    snr_thr, _p(flag), _p(amp), _p(toa), _p(soft), soft_pitch, _stream(stream)))
 
     def tx_stream_dev(self, bits148, n, out, stream=None):
         self._ck(self.lib.btsdsp_tx_stream_dev(self.h, _p(bits148), n, _p(out), _stream(stream)))

@@ -34,6 +34,7 @@ struct btsdsp_ctx {
   cudaStream_t st = nullptr, st_in = nullptr, st_out = nullptr, st_side = nullptr;
   long long rx_seg = 0;         // btsdsp_rx_stream_dev: chunks per segment of the overlapped pipeline (0 = one launch each)
   int rx_res_ctas = 0;          // ... and the resampler's CTA cap while it shares the GPU with the demod kernels
+  int rx_light = 1;             // ... and whether those launches use the resampler's light (one-tile) configuration
   long long host_seg = 4000;    // layer-3 pipelines: chunks per copy/compute segment (4000 = 27.6 MB of complex64 samples)
   std::string err;
   std::atomic<long long> launches{0};
@@ -262,6 +263,7 @@ int btsdsp_create(btsdsp_ctx **out, int device, int sps) {
     }
     if (const char *e = getenv("BTSDSP_RX_SEG")) ctx->rx_seg = atoll(e);
     if (const char *e = getenv("BTSDSP_RX_RES_CTAS")) ctx->rx_res_ctas = atoi(e);
+    if (const char *e = getenv("BTSDSP_RX_LIGHT")) ctx->rx_light = atoi(e);
     if (const char *e = getenv("BTSDSP_HOST_SEG")) { const long long v = atoll(e); if (v >= 250) ctx->host_seg = v; }
     CK(cudaMalloc(&ctx->T, sizeof(DevTables)));
     CK(cudaMallocHost(&ctx->hT, sizeof(DevTables)));
@@ -816,9 +818,9 @@ int btsdsp_demodulate_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long long 
 }
 
 // ---- layer 3 ---------------------------------------------------------------------------------------
-int btsdsp_rx_stream_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nchunks, const uint8_t *tsc,
-                         long long nbursts, float detect_thr, float gate_thr, float snr_thr, int32_t *flag,
-                         btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch, void *stream) {
+static int rx_stream_dev_impl(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, int has_history, long long nchunks, const uint8_t *tsc,
+                              long long nbursts, float detect_thr, float gate_thr, float snr_thr, int32_t *flag,
+                              btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch, void *stream) {
   ARG(ctx && raw && tsc && nchunks > 0 && nbursts >= 0);
   if (ctx->sps != 1) return fail(ctx, BTSDSP_EUNSUPPORTED, "the RX stream path runs at sps == 1");
   ARG(((nbursts + 3) / 4) * 625 <= nchunks * 585);
@@ -832,7 +834,7 @@ int btsdsp_rx_stream_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nchu
   const long long seg = ctx->rx_seg;
   if (seg <= 0 || nchunks <= seg) {
     // one resampler launch, then the two demod kernels, all on the caller's stream
-    launch_resample_rx(ctx->T, (const cf *)raw, 0, nchunks, dRes, st);
+    launch_resample_rx(ctx->T, (const cf *)raw, has_history, nchunks, dRes, st);
     NormalOut o = {flag, (cf *)amp, toa, nullptr, nullptr, nullptr, nullptr, soft, soft_pitch};
     const int nl = launch_demod_normal(ctx->T, make_src((const btsdsp_cf32 *)dRes, 0, nullptr, 0, 1), tsc, nbursts, detect_thr,
                                        gate_thr, snr_thr, o, ss->eqp.p, st);
@@ -853,12 +855,19 @@ int btsdsp_rx_stream_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nchu
   CK(cudaStreamWaitEvent(side, ctx->events[nseg], 0));
   long long done_bursts = 0;
   int nl = 0;
+  // resampler launches run one segment AHEAD of the demod kernels (R(0), R(1), D(0), R(2), D(1), ...): R(s+1) is queued
+  // before D(s), so its CTAs (one per SM, the light configuration) are resident when D(s)'s CTAs fill the rest of the SMs
+  auto resample_seg = [&](long long s) {
+    const long long c0 = s * seg, c1 = (c0 + seg < nchunks) ? c0 + seg : nchunks;
+    launch_resample_rx(ctx->T, (const cf *)raw + c0 * 864, has_history || c0 > 0, c1 - c0, dRes + c0 * 585, side,
+                       s == 0 ? 0 : ctx->rx_res_ctas, s == 0 ? 0 : ctx->rx_light);
+    nl++;
+    cudaEventRecord(ctx->events[s], side);
+  };
+  resample_seg(0);
   for (long long s = 0; s < nseg; s++) {
     const long long c0 = s * seg, c1 = (c0 + seg < nchunks) ? c0 + seg : nchunks;
-    launch_resample_rx(ctx->T, (const cf *)raw + c0 * 864, c0 > 0, c1 - c0, dRes + c0 * 585, side,
-                       s == 0 ? 0 : ctx->rx_res_ctas);
-    nl++;
-    CK(cudaEventRecord(ctx->events[s], side));
+    if (s + 1 < nseg) resample_seg(s + 1);
     CK(cudaStreamWaitEvent(st, ctx->events[s], 0));
     long long avail = (c1 * 585 / 625) * 4;                     // bursts wholly inside the samples resampled so far
     if (avail > nbursts || c1 == nchunks) avail = nbursts;
@@ -874,6 +883,20 @@ int btsdsp_rx_stream_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nchu
   }
   LAUNCHED("rx_stream (segmented)", nl);
   return BTSDSP_OK;
+}
+
+int btsdsp_rx_stream_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, long long nchunks, const uint8_t *tsc,
+                         long long nbursts, float detect_thr, float gate_thr, float snr_thr, int32_t *flag,
+                         btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch, void *stream) {
+  return rx_stream_dev_impl(ctx, raw, 0, nchunks, tsc, nbursts, detect_thr, gate_thr, snr_thr, flag, amp, toa, soft, soft_pitch, stream);
+}
+/* a later piece of a running stream: raw[-192..-1] hold the previous samples (RadioInterface::pullBuffer keeps them in
+ * rcvHistory, radioInterface.cpp:238-259); the piece must begin on a 117-frame boundary of the stream */
+int btsdsp_rx_stream_cont_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *raw, int has_history, long long nchunks, const uint8_t *tsc,
+                              long long nbursts, float detect_thr, float gate_thr, float snr_thr, int32_t *flag,
+                              btsdsp_cf32 *amp, float *toa, float *soft, int soft_pitch, void *stream) {
+  return rx_stream_dev_impl(ctx, raw, has_history != 0, nchunks, tsc, nbursts, detect_thr, gate_thr, snr_thr, flag, amp, toa, soft,
+                            soft_pitch, stream);
 }
 
 // Host-buffer receive pipeline: the stream is cut into segments of whole frame groups; segment s is

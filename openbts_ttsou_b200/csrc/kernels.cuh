@@ -83,7 +83,7 @@ void launch_modulate(const DevTables *T, const uint8_t *bits, int nbits, long lo
                      const uint8_t *guards, long long first, cf *out, long long pitch, cudaStream_t st,
                      const float *scale = nullptr);
 void launch_resample_rx(const DevTables *T, const cf *in, int has_history, long long nchunks, cf *out, cudaStream_t st,
-                        int max_ctas = 0);
+                        int max_ctas = 0, int light = 0);
 void launch_tx_fused(const DevTables *T, const uint8_t *bits, const float *scale, long long nslots, int16_t *out, cudaStream_t st,
                      int nstreams = 1);
 int launch_resample_rx_i16_multi(const int16_t *in, long long in_pitch, int nstreams, int swap_iq, int has_history,

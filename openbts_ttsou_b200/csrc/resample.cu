@@ -336,11 +336,22 @@ static int rxv3_make_map(CUtensorMap *map, const void *in, int has_history, long
 }
 
 // max_ctas > 0 caps the persistent grid (the caller overlaps the launch with other kernels and leaves them the other SMs)
+// light != 0 runs the one-tile configuration (9 warps, 21 K registers, 70 KB per CTA instead of 26 warps / 60 K / 204 KB): it
+// leaves most of every SM to kernels of another stream (the segmented btsdsp_rx_stream_dev overlaps it with the demod kernels)
 void launch_resample_rx(const DevTables *T, const cf *in, int has_history, long long nchunks, cf *out, cudaStream_t st,
-                        int max_ctas) {
+                        int max_ctas, int light) {
   if (nchunks <= 0) return;
   const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
   alignas(64) CUtensorMap map;
+  if (light && aligned) {
+    using C = RxV3<false, 1>;
+    const int bias = rxv3_make_map<false, 1>(&map, in, has_history, nchunks);
+    if (bias >= 0) {
+      const long long nperiods = nchunks * 9, ntiles = (nperiods + C::kPeriods - 1) / C::kPeriods;
+      k_resample_rx_v3<false, 1><<<rxv3_grid(ntiles, max_ctas), C::kThreads, C::kSmem, st>>>(map, bias, 0, nperiods, out, 1, 0);
+      return;
+    }
+  }
   const int bias = aligned ? rxv3_make_map<false, kRxV3TilesF32>(&map, in, has_history, nchunks) : -1;
   if (bias >= 0) {
     using C = RxV3<false, kRxV3TilesF32>;
@@ -507,6 +518,8 @@ int configure_resamplers() {
   if (cudaFuncSetAttribute(k_tx_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTxFusedSmem) != cudaSuccess) return -2;
   cudaError_t e = cudaFuncSetAttribute(k_resample_rx_v3<false, kRxV3TilesF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)RxV3<false, kRxV3TilesF32>::kSmem);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_resample_rx_v3<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RxV3<false, 1>::kSmem);
   if (e != cudaSuccess) return (int)e;
   return (int)cudaFuncSetAttribute(k_resample_rx_v3<true, kRxV3TilesI16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)RxV3<true, kRxV3TilesI16>::kSmem);

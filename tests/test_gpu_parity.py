@@ -504,3 +504,37 @@ def test_tx_streams_equal_single_stream_calls(dsp):
         m = multi.cpu().numpy()
         assert (m[:32] == 12345).all() and (m[-32:] == 12345).all()
         same(m[32:-32].reshape(ns, -1), single.cpu().numpy(), "tx streams nb=%d ns=%d" % (nb, ns))
+
+
+@pytest.mark.gpu
+def test_rx_stream_in_pieces_equals_one_call(dsp):
+    """btsdsp_rx_stream_cont_dev: a running stream handed over in 117-frame pieces, each seeing the 192 samples before it
+    (RadioInterface::pullBuffer's rcvHistory), gives exactly the one-call result; without the history flag the first
+    outputs of a later piece differ (the stream would restart from zeros)"""
+    import torch
+    dev = torch.device("cuda:0")
+    nblocks = 6
+    nb, nch = 936 * nblocks, 250 * nblocks
+    g = torch.Generator(device=dev); g.manual_seed(4)
+    bits = torch.randint(0, 2, (nb, 148), generator=g, device=dev, dtype=torch.uint8)
+    bits[:, :3] = 0; bits[:, 145:] = 0
+    bits[:, 61:87] = torch.from_numpy(synth.bits_of(synth.TSC[0]).copy()).to(dev)
+    iq = torch.zeros(nch * 864 * 2, dtype=torch.int16, device=dev)
+    dsp.tx_stream_dev(bits, nb, iq)
+    raw = iq.to(torch.float32) + 300.0 * torch.randn(iq.numel(), generator=g, device=dev)
+    tsc = torch.zeros(nb, dtype=torch.uint8, device=dev)
+
+    def outs():
+        return (torch.zeros(nb, dtype=torch.int32, device=dev), torch.zeros(nb * 2, device=dev), torch.zeros(nb, device=dev),
+                torch.zeros(nb * 148, device=dev))
+    f1, a1, t1, s1 = outs()
+    dsp.rx_stream_dev(raw, nch, tsc, nb, f1, a1, t1, s1, 148)
+    for hist in (True, False):
+        f2, a2, t2, s2 = outs()
+        for lo, hi in ((0, 1), (1, 4), (4, 6)):                       # pieces of 1, 3 and 2 blocks
+            b0, n = lo * 936, (hi - lo) * 936
+            dsp.rx_stream_cont_dev(raw.data_ptr() + lo * 250 * 864 * 8, hist and lo > 0, (hi - lo) * 250, tsc[b0:], n,
+                                   f2[b0:], a2[2 * b0:], t2[b0:], s2[b0 * 148:], 148)
+        torch.cuda.synchronize()
+        equal = all(torch.equal(x, y) for x, y in ((f1, f2), (a1, a2), (t1, t2), (s1, s2)))
+        assert equal == hist

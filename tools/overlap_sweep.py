@@ -36,9 +36,10 @@ def make(dsp):
     return raw
 
 
-def run(seg, ctas, raw=None, ref=None):
+def run(seg, ctas, raw=None, ref=None, light=1):
     os.environ["BTSDSP_RX_SEG"] = str(seg)
     os.environ["BTSDSP_RX_RES_CTAS"] = str(ctas)
+    os.environ["BTSDSP_RX_LIGHT"] = str(light)
     dsp = pkg.BtsDsp(0, 1)
     if raw is None:
         raw = make(dsp)
@@ -62,7 +63,7 @@ def run(seg, ctas, raw=None, ref=None):
         best = min(best, a.elapsed_time(b) / 10)
     out = (flag.clone(), amp.clone(), toa.clone(), soft.clone())
     same = None if ref is None else all(torch.equal(x, y) for x, y in zip(out, ref))
-    print(json.dumps({"seg_chunks": seg, "res_ctas": ctas, "ms_per_step": round(best, 4), "bursts_per_s": nb / best * 1e3,
+    print(json.dumps({"seg_chunks": seg, "res_ctas": ctas, "light": light, "ms_per_step": round(best, 4), "bursts_per_s": nb / best * 1e3,
                       "identical_to_unsegmented": same}), flush=True)
     dsp.close()
     return raw, out
@@ -72,6 +73,6 @@ raw, ref = run(0, 0)
 points = [(s, c) for s in (8000, 16000, 32000) for c in (0, 96, 64, 48, 32, 24)]
 if len(sys.argv) > 2:
     points = [tuple(int(v) for v in p.split(":")) for p in sys.argv[2].split(",")]
-for seg, ctas in points:
-    run(seg, ctas, raw, ref)
+for p in points:
+    run(p[0], p[1], raw, ref, p[2] if len(p) > 2 else 1)
 run(0, 0, raw, ref)
