@@ -314,6 +314,20 @@ int btsdsp_xcch_decode_dev(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pi
 int btsdsp_xcch_decode_host(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pitch, long long nframes, uint8_t *u,
                             int32_t *ok);
 
+/* TCH/FACCH block decoder (GSM 05.03 3.1 / 4.2; TCHFACCHL1Decoder::processBurst + deinterleave + decodeTCH + decode,
+ * GSML1FEC.cpp:1031-1210) over the soft bytes of ONE traffic channel's consecutive traffic bursts (the 26-multiframe's
+ * SACCH / idle frames already taken out by the caller's demultiplexer): 4*nblocks + 4 bursts, burst_pitch apart; block q
+ * is diagonally interleaved over bursts 4q .. 4q+7 and completes with burst 4q+7, whose stealing flag Hl (bit 60) says
+ * what it is.  stolen[q] == 0: a speech frame -- d[q][260] = the class-1 (Viterbi-decoded, reordered) and class-2 (sliced)
+ * bits of GSM 05.03 3.1.2, good[q] = the 3-bit class-1A parity matches and the tail bits are zero.  stolen[q] != 0: a
+ * FACCH frame -- facch_u[q][228] and facch_ok[q] exactly as btsdsp_xcch_decode gives them; good[q] = 0 (the reference feeds
+ * bad-frame substitution then).  Rows of the other kind are zero.  Any output may be NULL.  GSM 06.10 frame formatting
+ * and bad-frame substitution (:1161-1190) are the speech layer's. */
+int btsdsp_tch_decode_dev(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pitch, long long nblocks, uint8_t *d, int32_t *good,
+                          int32_t *stolen, uint8_t *facch_u, int32_t *facch_ok, void *stream);
+int btsdsp_tch_decode_host(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pitch, long long nblocks, uint8_t *d, int32_t *good,
+                           int32_t *stolen, uint8_t *facch_u, int32_t *facch_ok);
+
 /* RACH block decoder (GSM 05.03 4.6; RACHL1Decoder::writeLowSide, GSML1FEC.cpp:474-515): per access burst, the 36
  * coded soft bytes at burst bits 49..84 -> Viterbi -> u[18] = d[8] : p[6] : tail[4] (u may be NULL), and
  * fields[i] = tail | bsic << 8 | ra << 16: tail = the 4 tail bits (a valid burst has 0), bsic = (~sent parity ^ computed

@@ -87,6 +87,8 @@ _SIGS = {
     "btsdsp_trx_pull_host": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i]),
     "btsdsp_trx_pull_streams_dev": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i, _vp]),
     "btsdsp_trx_radio_host": (_i, [_vp, _vp, _vp, _ll, _ll, _i, _i, _vp, _vp, _i]),
+    "btsdsp_tch_decode_dev": (_i, [_vp, _vp, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "btsdsp_tch_decode_host": (_i, [_vp, _vp, _i, _ll, _vp, _vp, _vp, _vp, _vp]),
     "btsdsp_tx_datagrams_host": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp]),
     "btsdsp_tx_datagrams_52m_host": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp]),
     "btsdsp_trx_set_variant_52m": (_i, [_vp, _vp, _i, _i]),
@@ -515,6 +517,20 @@ class BtsDsp:
         f = np.zeros(n, np.int32)
         self._ck(self.lib.btsdsp_rach_decode_host(self.h, _p(soft_u8), soft_u8.shape[1], n, _p(u), _p(f)))
         return u, f & 0xff, (f >> 8) & 0xff, (f >> 16) & 0xff
+
+    def tch_decode_host(self, soft_u8):
+        """soft_u8 (4*nblocks + 4, pitch >= 148) -> dict(d[nblocks,260], good, stolen, fu[nblocks,228], fok)"""
+        soft_u8 = np.ascontiguousarray(soft_u8, np.uint8)
+        n = soft_u8.shape[0] // 4 - 1
+        r = dict(d=np.zeros((n, 260), np.uint8), good=np.zeros(n, np.int32), stolen=np.zeros(n, np.int32),
+                 fu=np.zeros((n, 228), np.uint8), fok=np.zeros(n, np.int32))
+        self._ck(self.lib.btsdsp_tch_decode_host(self.h, _p(soft_u8), soft_u8.shape[1], n, _p(r["d"]), _p(r["good"]), _p(r["stolen"]),
+                                                 _p(r["fu"]), _p(r["fok"])))
+        return r
+
+    def tch_decode_dev(self, soft_u8, burst_pitch, nblocks, d, good, stolen, fu, fok, stream=None):
+        self._ck(self.lib.btsdsp_tch_decode_dev(self.h, _p(soft_u8), burst_pitch, nblocks, _p(d), _p(good), _p(stolen), _p(fu), _p(fok),
+                                                _stream(stream)))
 
     def xcch_decode_dev(self, soft_u8, burst_pitch, nframes, u, ok, stream=None):
         self._ck(self.lib.btsdsp_xcch_decode_dev(self.h, _p(soft_u8), burst_pitch, nframes, _p(u), _p(ok), _stream(stream)))

@@ -1410,6 +1410,40 @@ int btsdsp_xcch_decode_host(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_p
   return BTSDSP_OK;
 }
 
+int btsdsp_tch_decode_dev(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pitch, long long nblocks, uint8_t *d, int32_t *good,
+                          int32_t *stolen, uint8_t *facch_u, int32_t *facch_ok, void *stream) {
+  ARG(ctx && soft_u8 && nblocks >= 0 && burst_pitch >= 148);
+  DeviceGuard g(ctx->device);
+  const int nl = launch_tch_decode(soft_u8, burst_pitch, nblocks, d, good, stolen, facch_u, facch_ok, (cudaStream_t)stream);
+  LAUNCHED("tch_decode", nl);
+  return BTSDSP_OK;
+}
+
+int btsdsp_tch_decode_host(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pitch, long long nblocks, uint8_t *d, int32_t *good,
+                           int32_t *stolen, uint8_t *facch_u, int32_t *facch_ok) {
+  ARG(ctx && soft_u8 && nblocks > 0 && burst_pitch >= 148);
+  DeviceGuard g(ctx->device);
+  size_t total = 0;
+  auto take = [&total](size_t bytes) { size_t o = (total + 255) & ~(size_t)255; total = o + bytes; return o; };
+  const size_t nbytes = (size_t)(4 * nblocks + 4) * burst_pitch;
+  const size_t o_s = take(nbytes), o_d = take((size_t)nblocks * 260), o_g = take((size_t)nblocks * 4), o_t = take((size_t)nblocks * 4),
+               o_u = take((size_t)nblocks * 228), o_k = take((size_t)nblocks * 4);
+  GROW(B_RAW, total);
+  uint8_t *b = dbuf<uint8_t>(ctx, B_RAW);
+  cudaStream_t st = ctx->st;
+  CK(cudaMemcpyAsync(b + o_s, soft_u8, nbytes, cudaMemcpyHostToDevice, st));
+  int r = btsdsp_tch_decode_dev(ctx, b + o_s, burst_pitch, nblocks, b + o_d, (int32_t *)(b + o_g), (int32_t *)(b + o_t), b + o_u,
+                                (int32_t *)(b + o_k), st);
+  if (r != BTSDSP_OK) return r;
+  if (d) CK(cudaMemcpyAsync(d, b + o_d, (size_t)nblocks * 260, cudaMemcpyDeviceToHost, st));
+  if (good) CK(cudaMemcpyAsync(good, b + o_g, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, st));
+  if (stolen) CK(cudaMemcpyAsync(stolen, b + o_t, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, st));
+  if (facch_u) CK(cudaMemcpyAsync(facch_u, b + o_u, (size_t)nblocks * 228, cudaMemcpyDeviceToHost, st));
+  if (facch_ok) CK(cudaMemcpyAsync(facch_ok, b + o_k, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return BTSDSP_OK;
+}
+
 int btsdsp_rach_decode_dev(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pitch, long long n, uint8_t *u, int32_t *fields,
                            void *stream) {
   ARG(ctx && soft_u8 && fields && n >= 0 && burst_pitch >= 148);

@@ -117,6 +117,62 @@ BTS_HD bool xcch_decode_frame_seq(const unsigned char *soft, int burst_pitch, un
   return xcch_parity_ok(u);
 }
 
+// ---- TCH/FACCH (GSM 05.03 3.1, 4.2), TCHFACCHL1Decoder::processBurst / deinterleave / decodeTCH, GSML1FEC.cpp:1031-1210 ----
+// A traffic channel's bursts are diagonally interleaved over EIGHT bursts: block q takes the even-position e-bits of the
+// four bursts that complete it and the odd-position e-bits of the four before (deinterleave(blockOffset), :1102-1110:
+// c[k] = i[(k + off) % 8][2*((49 k) % 57) + ((k % 8)/4)]; with the reference's B numbering this is burst 4q + (k % 8) of a
+// stream in which block q occupies bursts 4q .. 4q+7).  The burst that completes the block carries the stealing flag Hl
+// (bit 60, :1073): set -> the 456 bits are a FACCH frame, decoded exactly like an XCCH block (:1075-1084); clear -> a speech
+// frame (:1129-1160): class 1 = c[0..378) through the same Viterbi -> u[189], class 2 = c[378..456) sliced; d[2k] = u[k],
+// d[2k+1] = u[184-k] (k <= 90), d[182..260) = class 2; good = 3-bit parity of d[0..50) (generator 0x0b, sent inverted in
+// u[91..94)) matches AND the four tail bits u[185..189) are zero.  The GSM 06.10 frame formatting and the bad-frame
+// substitution that follow (:1161-1190, the latter draws from random()) belong to the speech layer and are not part of this.
+constexpr int kTchC1 = 378, kTchU = 189, kTchC2 = 78, kTchD = 260;
+BTS_HD int tch_source_bit(int k, int *burst) {
+  const int r = k & 7;
+  *burst = r;
+  const int j = 2 * ((49 * k) % 57) + (r >> 2);
+  return j < 57 ? 3 + j : 88 + (j - 57);
+}
+BTS_HD bool tch_fields(const unsigned char *u, const unsigned char *c2, unsigned char *d) {
+  for (int k = 0; k <= 90; k++) { d[2 * k] = u[k] & 1; d[2 * k + 1] = u[184 - k] & 1; }   // :1141-1144
+  for (int i = 0; i < kTchC2; i++) d[182 + i] = c2[i] & 1;                                 // :1137
+  const unsigned sent = (~(((unsigned)(u[91] & 1) << 2) | ((unsigned)(u[92] & 1) << 1) | (unsigned)(u[93] & 1))) & 7u;   // :1148
+  unsigned state = 0;                                                                      // mClass1A_d.parity(Parity(0x0b,3,50))
+  for (int i = 0; i < 50; i++) {
+    const unsigned fb = ((state >> 2) ^ d[i]) & 1u;
+    state <<= 1;
+    if (fb) state ^= 0x0bu;
+  }
+  unsigned tail = 0;
+  for (int i = 0; i < 4; i++) tail = (tail << 1) | (u[185 + i] & 1u);                      // :1153
+  return sent == (state & 7u) && tail == 0;                                                // :1160
+}
+// One block, sequential form (host emulation, tests).  soft: the block's eight bursts.  Outputs: d[260] + *good when the
+// frame is not stolen; fu[228] + *fok when it is (the other pair is zeroed).  Returns the stolen flag.
+BTS_HD bool tch_decode_block_seq(const unsigned char *soft, int burst_pitch, unsigned char *d, int *good, unsigned char *fu, int *fok) {
+  float p[kXcchC];
+  for (int k = 0; k < kXcchC; k++) {
+    int B;
+    const int bit = tch_source_bit(k, &B);
+    p[k] = (float)soft[B * burst_pitch + bit] / 256.0F;
+  }
+  const bool stolen = (float)soft[7 * burst_pitch + 60] / 256.0F > 0.5F;                   // inBurst.Hl(), bit(gHlIndex)
+  for (int i = 0; i < kTchD; i++) d[i] = 0;
+  for (int i = 0; i < kXcchU; i++) fu[i] = 0;
+  *good = 0; *fok = 0;
+  if (stolen) {
+    viterbi_seq<kXcchC, kXcchU>(p, fu);
+    *fok = xcch_parity_ok(fu) ? 1 : 0;
+  } else {
+    unsigned char u[kTchU], c2[kTchC2];
+    viterbi_seq<kTchC1, kTchU>(p, u);
+    for (int i = 0; i < kTchC2; i++) c2[i] = p[kTchC1 + i] > 0.5F ? 1 : 0;                 // sliced()
+    *good = tch_fields(u, c2, d) ? 1 : 0;
+  }
+  return stolen;
+}
+
 // ---- RACH (GSM 05.03 4.6), RACHL1Decoder::writeLowSide, GSML1FEC.cpp:474-515 ----
 // e = burst bits 49..84 (36 coded bits) -> u[18] = d[8] : p[6] : tail[4].  The caller checks tail == 0 and
 // bsic == its BSIC (the parity word is sent inverted and XORed with the BSIC); ra = the 8-bit RA field.

@@ -11,8 +11,8 @@ struct __align__(8) VitSmem {
 };
 
 // tables already hold entries 0..NC-1 (match, mismatch, hard); pads them, runs the trellis, leaves u[NU] in S.u
-template <int NC, int NU>
-__device__ __forceinline__ void viterbi_warp(VitSmem<NC, NU> &S, int lane) {
+template <int NC, int NU, typename ST = VitSmem<NC, NU>>       // ST: storage with arrays at least as large as VitSmem<NC, NU>'s
+__device__ __forceinline__ void viterbi_warp(ST &S, int lane) {
   constexpr int STEPS = NU + kVitDeferral, TABLE = 2 * STEPS;
   __syncwarp();
   for (int k = NC + lane; k < TABLE; k += 32) { S.match[k] = 0.5F; S.mismatch[k] = 0.5F; S.hard[k] = S.hard[NC - 1]; }
@@ -76,6 +76,53 @@ __global__ void __launch_bounds__(kXcchWarps * 32) k_xcch_decode(const unsigned 
 int launch_xcch_decode(const unsigned char *soft, int burst_pitch, long long nframes, unsigned char *u, int *ok, cudaStream_t st) {
   if (nframes <= 0) return 0;
   k_xcch_decode<<<(unsigned)((nframes + kXcchWarps - 1) / kXcchWarps), kXcchWarps * 32, 0, st>>>(soft, burst_pitch, nframes, u, ok);
+  return 1;
+}
+
+// TCH/FACCH: one warp per block of a traffic channel's burst stream (block q = bursts 4q .. 4q+7, fec.cuh); a stolen block
+// runs the 456-bit FACCH (XCCH) decode, the others the 378-bit class-1 decode + class-2 slice + parity / tail checks
+__global__ void __launch_bounds__(kXcchWarps * 32) k_tch_decode(const unsigned char *__restrict__ soft, int burst_pitch, long long nblocks,
+                                                               unsigned char *__restrict__ d, int *__restrict__ good, int *__restrict__ stolen_o,
+                                                               unsigned char *__restrict__ fu, int *__restrict__ fok) {
+  __shared__ VitSmem<kXcchC, kXcchU> sm[kXcchWarps];
+  __shared__ unsigned char c2[kXcchWarps][kTchC2 + 2];
+  __shared__ unsigned char dd[kXcchWarps][kTchD + 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long q = (long long)blockIdx.x * kXcchWarps + warp;
+  if (q >= nblocks) return;
+  VitSmem<kXcchC, kXcchU> &S = sm[warp];
+  const unsigned char *bs = soft + q * 4 * (long long)burst_pitch;
+  for (int k = lane; k < kXcchC; k += 32) {
+    int B;
+    const int bit = tch_source_bit(k, &B);
+    unsigned h;
+    vit_costs((float)bs[B * burst_pitch + bit] / 256.0F, &S.match[k], &S.mismatch[k], &h);
+    S.hard[k] = (unsigned char)h;
+    if (k >= kTchC1) c2[warp][k - kTchC1] = (unsigned char)h;                  // class 2, before the trellis pads over it
+  }
+  const bool stolen = (float)bs[7 * burst_pitch + 60] / 256.0F > 0.5F;         // warp-uniform
+  if (lane == 0 && stolen_o) stolen_o[q] = stolen ? 1 : 0;
+  if (stolen) {
+    viterbi_warp<kXcchC, kXcchU>(S, lane);
+    if (fu) for (int i = lane; i < kXcchU; i += 32) fu[q * kXcchU + i] = S.u[i];
+    if (lane == 0 && fok) fok[q] = xcch_parity_ok(S.u) ? 1 : 0;
+    if (d) for (int i = lane; i < kTchD; i += 32) d[q * kTchD + i] = 0;
+    if (lane == 0 && good) good[q] = 0;
+  } else {
+    viterbi_warp<kTchC1, kTchU, VitSmem<kXcchC, kXcchU>>(S, lane);
+    int g = 0;
+    if (lane == 0) g = tch_fields(S.u, c2[warp], dd[warp]) ? 1 : 0;
+    __syncwarp();
+    if (d) for (int i = lane; i < kTchD; i += 32) d[q * kTchD + i] = dd[warp][i];
+    if (lane == 0 && good) good[q] = g;
+    if (fu) for (int i = lane; i < kXcchU; i += 32) fu[q * kXcchU + i] = 0;
+    if (lane == 0 && fok) fok[q] = 0;
+  }
+}
+int launch_tch_decode(const unsigned char *soft, int burst_pitch, long long nblocks, unsigned char *d, int *good, int *stolen,
+                      unsigned char *fu, int *fok, cudaStream_t st) {
+  if (nblocks <= 0) return 0;
+  k_tch_decode<<<(unsigned)((nblocks + kXcchWarps - 1) / kXcchWarps), kXcchWarps * 32, 0, st>>>(soft, burst_pitch, nblocks, d, good, stolen, fu, fok);
   return 1;
 }
 

@@ -114,6 +114,8 @@ void launch_energy_detect_52m(const cf *v, int n, unsigned win, float thr, float
 // L1 FEC after the path (fec.cuh / fec_kernels.cuh)
 int launch_xcch_decode(const unsigned char *soft, int burst_pitch, long long nframes, unsigned char *u, int *ok, cudaStream_t st);
 int launch_rach_decode(const unsigned char *soft, int burst_pitch, long long n, unsigned char *u, int *fields, cudaStream_t st);
+int launch_tch_decode(const unsigned char *soft, int burst_pitch, long long nblocks, unsigned char *d, int *good, int *stolen,
+                      unsigned char *fu, int *fok, cudaStream_t st);
 // the caller-policy pipeline (trx_policy.cuh / trx_kernels.cuh)
 size_t trx_scratch_bytes(long long n, long long nr, int narfcn, bool slice_all = false);
 void launch_usrpify(const cf *x, long long n, int16_t *out, cudaStream_t st);

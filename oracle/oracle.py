@@ -365,6 +365,28 @@ class Oracle:
         self._f("xcch_encode_pflip")(_ptr(d), _ptr(pf), c_l(d.shape[0]), _ptr(e))
         return e
 
+    def tch_decode(self, soft_u8):
+        """soft_u8: (4*nblocks + 4, >=148) soft bytes of one traffic channel's consecutive bursts (ref only).
+        Returns dict(d[nblocks,260], good, stolen, fu[nblocks,228], fok)."""
+        assert self.kind == "ref"
+        soft_u8 = np.ascontiguousarray(soft_u8, np.uint8)
+        n = soft_u8.shape[0] // 4 - 1
+        r = dict(d=np.zeros((n, 260), np.uint8), good=np.zeros(n, np.int32), stolen=np.zeros(n, np.int32),
+                 fu=np.zeros((n, 228), np.uint8), fok=np.zeros(n, np.int32))
+        self._f("tch_decode")(_ptr(soft_u8), c_i(soft_u8.shape[1]), c_l(n), _ptr(r["d"]), _ptr(r["good"]), _ptr(r["stolen"]),
+                              _ptr(r["fu"]), _ptr(r["fok"]))
+        return r
+
+    def tch_encode(self, d260, f184, steal):
+        """nblocks speech frames d260 / FACCH payloads f184 (used where steal) -> burst bits (4*nblocks + 4, 148) (ref only)"""
+        assert self.kind == "ref"
+        d260 = np.ascontiguousarray(d260, np.uint8); f184 = np.ascontiguousarray(f184, np.uint8)
+        steal = np.ascontiguousarray(steal, np.uint8)
+        n = d260.shape[0]
+        out = np.zeros((4 * n + 4, 148), np.uint8)
+        self._f("tch_encode")(_ptr(d260), _ptr(f184), _ptr(steal), c_l(n), _ptr(out))
+        return out
+
     def rach_decode(self, soft_u8):
         """soft_u8: (n, >=148) uint8 -> (u[n,18], tail[n], bsic[n], ra[n]); reference classes (ref only)"""
         assert self.kind == "ref"

@@ -696,4 +696,114 @@ void ref_rach_encode(const unsigned char *ra, const unsigned char *bsic, long n,
   }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * TCH/FACCH (GSML1FEC.cpp:1031-1210): TCHFACCHL1Decoder::processBurst + deinterleave + decodeTCH, and XCCHL1Decoder::decode
+ * for a stolen (FACCH) block, over one traffic channel's consecutive traffic bursts given as RX-datagram soft bytes.
+ * A decoder object is fed 4*nblocks + 4 bursts with B = 0, 1, 2, ... (mod 8); the first completion (B == 3, which would mix
+ * in the object's initial zeros) is skipped, so block q is the one completed by burst 4q + 7 -- bursts 4q .. 4q+7.
+ * The reference's classes do the work; the glue around them is restated line by line.
+ * ------------------------------------------------------------------------------------------------ */
+void ref_tch_decode(const unsigned char *soft, int burst_pitch, long nblocks, unsigned char *d, int *good, int *stolen_o,
+                    unsigned char *fu, int *fok) {
+  ViterbiR2O4 vcoder;
+  Parity blockCoder(0x10004820009ULL, 40, 224);
+  Parity tchParity(0x0b, 3, 50);
+  SoftVector mI[8];
+  for (int i = 0; i < 8; i++) { mI[i] = SoftVector(114); mI[i].fill(.0); }       /* :1008-1012 */
+  SoftVector mC(456);
+  for (long n = 0; n < 4 * nblocks + 4; n++) {
+    const unsigned char *rp = soft + (size_t)burst_pitch * n;
+    SoftVector burst(148);
+    for (int i = 0; i < 148; i++) burst[i] = rp[i] / 256.0F;                     /* TRXManager.cpp:230 */
+    const int B = (int)(n % 8);
+    burst.segment(3, 57).copyToSegment(mI[B], 0);                                /* data1(), :1062 */
+    burst.segment(88, 57).copyToSegment(mI[B], 57);                              /* data2(), :1063 */
+    if (B % 4 != 3) continue;                                                    /* :1067 */
+    const int blockOffset = (B == 3) ? 4 : 0;                                    /* :1071-1072 */
+    for (int k = 0; k < 456; k++) {                                              /* deinterleave, :1102-1110 */
+      int Bk = (k + blockOffset) % 8;
+      int j = 2 * ((49 * k) % 57) + ((k % 8) / 4);
+      mC[k] = mI[Bk][j];
+      mI[Bk][j] = 0.5F;
+    }
+    const long q = n / 4 - 1;
+    if (q < 0) continue;                                                         /* the start-up block that reads the initial zeros */
+    const bool stolen = burst.bit(60);                                           /* inBurst.Hl(), :1075 */
+    stolen_o[q] = stolen;
+    memset(d + 260 * q, 0, 260);
+    memset(fu + 228 * q, 0, 228);
+    good[q] = 0; fok[q] = 0;
+    if (stolen) {                                                                /* XCCHL1Decoder::decode, :636-660 */
+      BitVector mU(228);
+      mC.decode(vcoder, mU);
+      for (int i = 0; i < 228; i++) fu[228 * q + i] = mU.bit(i);
+      BitVector mP(mU.segment(184, 40)), mDP(mU.head(224));
+      mP.invert();
+      unsigned syndrome = blockCoder.syndrome(mDP);
+      fok[q] = syndrome == 0;
+    } else {                                                                     /* decodeTCH(false), :1129-1160 */
+      BitVector mTCHU(189), mTCHD(260);
+      SoftVector mClass1_c(mC.head(378)), mClass2_c(mC.segment(378, 78));
+      BitVector mClass1A_d(mTCHD.head(50));
+      mClass1_c.decode(vcoder, mTCHU);
+      mClass2_c.sliced().copyToSegment(mTCHD, 182);
+      for (unsigned k = 0; k <= 90; k++) {
+        mTCHD[2 * k] = mTCHU[k];
+        mTCHD[2 * k + 1] = mTCHU[184 - k];
+      }
+      unsigned sentParity = (~mTCHU.peekField(91, 3)) & 0x07;
+      unsigned calcParity = mClass1A_d.parity(tchParity) & 0x07;
+      unsigned tail = mTCHU.peekField(185, 4);
+      good[q] = (sentParity == calcParity) && (tail == 0);
+      for (int i = 0; i < 260; i++) d[260 * q + i] = mTCHD.bit(i);
+    }
+  }
+}
+/* TCHFACCHL1Encoder::encodeTCH (:1248-1279) / XCCHL1Encoder::encode for a FACCH frame (:795-808) + the diagonal interleaver
+ * (:1384-1392) + the stealing flags: nblocks blocks -> the 148 burst bits of 4*nblocks + 4 bursts (tails and midamble left
+ * zero).  Test-input generator for the decoder: block q (speech d260[q], or, when steal[q], the FACCH payload f184[q]) goes to
+ * bursts 4q .. 4q+7; Hl (bit 60) of bursts 4q+4 .. 4q+7 and Hu (bit 87) of bursts 4q .. 4q+3 carry steal[q]. */
+void ref_tch_encode(const unsigned char *d260, const unsigned char *f184, const unsigned char *steal, long nblocks,
+                    unsigned char *bursts) {
+  ViterbiR2O4 vcoder;
+  Parity blockCoder(0x10004820009ULL, 40, 224);
+  Parity tchParity(0x0b, 3, 50);
+  memset(bursts, 0, (size_t)(4 * nblocks + 4) * 148);
+  for (long q = 0; q < nblocks; q++) {
+    BitVector mC(456);
+    if (steal[q]) {
+      BitVector mU(228);
+      mU.fill(0);
+      BitVector mD(mU.head(184)), mP(mU.segment(184, 40));
+      for (int i = 0; i < 184; i++) mD[i] = f184[184 * q + i] & 1;
+      blockCoder.writeParityWord(mD, mP);
+      mU.encode(vcoder, mC);
+    } else {
+      BitVector mTCHU(189), mTCHD(260);
+      mTCHU.fill(0);
+      for (int i = 0; i < 260; i++) mTCHD[i] = d260[260 * q + i] & 1;
+      BitVector mClass1A_d(mTCHD.head(50)), mClass2_d(mTCHD.segment(182, 78));
+      BitVector p = mTCHU.segment(91, 3);
+      tchParity.writeParityWord(mClass1A_d, p);
+      for (unsigned k = 0; k <= 90; k++) {
+        mTCHU[k] = mTCHD[2 * k];
+        mTCHU[184 - k] = mTCHD[2 * k + 1];
+      }
+      for (unsigned k = 185; k <= 188; k++) mTCHU[k] = 0;
+      BitVector mClass1_c(mC.head(378));
+      mTCHU.encode(vcoder, mClass1_c);
+      mClass2_d.copyToSegment(mC, 378);
+    }
+    for (int k = 0; k < 456; k++) {
+      const int r = k % 8;
+      const int j = 2 * ((49 * k) % 57) + (r / 4);
+      bursts[(size_t)(4 * q + r) * 148 + (j < 57 ? 3 + j : 88 + (j - 57))] = mC.bit(k);
+    }
+    for (int b = 0; b < 4; b++) {
+      bursts[(size_t)(4 * q + 4 + b) * 148 + 60] = steal[q] ? 1 : 0;
+      bursts[(size_t)(4 * q + b) * 148 + 87] = steal[q] ? 1 : 0;
+    }
+  }
+}
+
 }  // extern "C"

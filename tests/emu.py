@@ -78,6 +78,14 @@ class Emu:
         self.lib.emu_tx_fused(P(bits), P(scale), c_ll(nslots), P(out))
         return out
 
+    def tch_decode(self, soft_u8):
+        soft_u8 = np.ascontiguousarray(soft_u8, np.uint8)
+        n = soft_u8.shape[0] // 4 - 1
+        r = dict(d=np.zeros((n, 260), np.uint8), good=np.zeros(n, np.int32), stolen=np.zeros(n, np.int32),
+                 fu=np.zeros((n, 228), np.uint8), fok=np.zeros(n, np.int32))
+        self.lib.emu_tch_decode(P(soft_u8), c_i(soft_u8.shape[1]), c_ll(n), P(r["d"]), P(r["good"]), P(r["stolen"]), P(r["fu"]), P(r["fok"]))
+        return r
+
     def xcch_decode(self, soft_u8):
         soft_u8 = np.ascontiguousarray(soft_u8, np.uint8)
         n = soft_u8.shape[0] // 4

@@ -606,6 +606,13 @@ static void emu_trx_pull_impl(void *state, int narfcn, const float *bursts, long
   }
 }
 
+// k_tch_decode's arithmetic, block by block (fec.cuh: tch_decode_block_seq)
+void emu_tch_decode(const unsigned char *soft, int burst_pitch, long long nblocks, unsigned char *d, int *good, int *stolen,
+                    unsigned char *fu, int *fok) {
+  for (long long q = 0; q < nblocks; q++)
+    stolen[q] = tch_decode_block_seq(soft + q * 4 * (long long)burst_pitch, burst_pitch, d + 260 * q, good + q, fu + 228 * q, fok + q) ? 1 : 0;
+}
+
 void emu_trx_pull(void *state, int narfcn, const float *bursts, long long pitch, int nframes, int fn0, int *valid,
                   unsigned char *dgram, int dgram_pitch) {
   emu_trx_pull_impl(state, narfcn, bursts, pitch, nframes, fn0, valid, dgram, dgram_pitch, false, 0);

@@ -219,3 +219,96 @@ def test_xcch_chain_end_to_end(oracle_best, dsp):
     torch.cuda.synchronize()
     assert bool(flag.all()) and bool(fok.all())
     assert np.array_equal(fu.cpu().numpy().reshape(nfr, 228)[:, :184], d)
+
+
+# ---- TCH/FACCH block decoder (GSML1FEC.cpp:1031-1210): 8-burst diagonal interleave, class-1 Viterbi + class-2 slice + parity /
+#      tail checks for speech frames, the XCCH decode for stolen (FACCH) blocks ----
+def make_tch_stream(o, nblocks, seed):
+    """one traffic channel: nblocks blocks (a quarter of them stolen by FACCH), encoded by the reference's own encoder
+    classes, through BPSK + AWGN of varying quality, erasures, saturated and wrong-confident soft bytes"""
+    rng = np.random.default_rng(seed)
+    d = rng.integers(0, 2, (nblocks, 260)).astype(np.uint8)
+    f = rng.integers(0, 2, (nblocks, 184)).astype(np.uint8)
+    steal = (rng.random(nblocks) < 0.25).astype(np.uint8)
+    bits = o.tch_encode(d, f, steal).astype(np.float64)                # (4n+4, 148)
+    nb = bits.shape[0]
+    sigma = np.repeat(rng.choice([0.05, 0.2, 0.35, 0.5, 0.7, 1.0], (nb + 7) // 8), 8)[:nb, None]
+    x = (2.0 * bits - 1.0) + sigma * rng.standard_normal(bits.shape)
+    p = 1.0 / (1.0 + np.exp(-2.0 * x / np.maximum(sigma, 0.3) ** 2))
+    soft = np.clip(np.rint(p * 255.0), 0, 255).astype(np.uint8)
+    soft[rng.random(nb) < 0.05] = 128                                  # a burst lost entirely
+    sat = rng.random(soft.shape) < 0.1
+    soft[sat] = np.where(bits[sat] > 0, 255, 0)
+    wrong = rng.random(soft.shape) < 0.01
+    soft[wrong] = 255 - soft[wrong]
+    return soft, d, f, steal
+
+
+def check_tch(got, want, d, f, steal):
+    for k in ("stolen", "good", "fok", "d", "fu"):
+        assert np.array_equal(got[k], want[k]), k
+    st = want["stolen"].astype(bool)
+    assert 0.1 < st.mean() < 0.45 and (st == steal.astype(bool)).mean() > 0.9          # the flag itself rides a noisy bit
+    g = want["good"].astype(bool)
+    assert 0.3 < g[~st].mean() < 0.99 and not g[st].any()
+    ok_speech = g & ~steal.astype(bool)
+    # a good speech frame carries the right class-1A bits (what its parity protects); most are right everywhere in class 1
+    assert (want["d"][ok_speech][:, :50] == d[ok_speech][:, :50]).mean() > 0.995
+    fk = want["fok"].astype(bool) & steal.astype(bool)
+    assert fk.any() and (want["fu"][fk][:, :184] == f[fk]).all()
+
+
+@pytest.fixture(scope="module")
+def tch_stream(oracle_best):
+    if oracle_best.kind != "ref":
+        pytest.skip("stream generation uses the reference encoder")
+    return make_tch_stream(oracle_best, 500, 33)
+
+
+def test_tch_hostemu_matches_reference(oracle_best, hostemu, tch_stream):
+    soft, d, f, steal = tch_stream
+    want = oracle_best.tch_decode(soft)
+    check_tch(Emu(hostemu).tch_decode(soft), want, d, f, steal)
+    wide = np.zeros((soft.shape[0], 160), np.uint8)                    # the RX datagram's row pitch
+    wide[:, 8:156] = soft
+    got = Emu(hostemu).tch_decode(np.ascontiguousarray(wide[:, 8:]))
+    assert all(np.array_equal(got[k], want[k]) for k in want)
+
+
+def test_tch_clean_channel_round_trip(oracle_best, hostemu):
+    """noise-free: every speech frame comes back whole and good, every FACCH payload too"""
+    if oracle_best.kind != "ref":
+        pytest.skip("needs the reference encoder")
+    rng = np.random.default_rng(5)
+    n = 40
+    d = rng.integers(0, 2, (n, 260)).astype(np.uint8)
+    f = rng.integers(0, 2, (n, 184)).astype(np.uint8)
+    steal = (np.arange(n) % 5 == 2).astype(np.uint8)
+    soft = (oracle_best.tch_encode(d, f, steal) * 255).astype(np.uint8)
+    for r in (oracle_best.tch_decode(soft), Emu(hostemu).tch_decode(soft)):
+        st = steal.astype(bool)
+        assert np.array_equal(r["stolen"], steal) and r["good"][~st].all() and r["fok"][st].all()
+        assert np.array_equal(r["d"][~st], d[~st]) and np.array_equal(r["fu"][st][:, :184], f[st])
+
+
+@pytest.mark.gpu
+def test_tch_gpu_matches_reference(oracle_best, dsp, tch_stream):
+    import torch
+    soft, d, f, steal = tch_stream
+    want = oracle_best.tch_decode(soft)
+    check_tch(dsp.tch_decode_host(soft), want, d, f, steal)
+    # device entry point on datagram-pitched rows, outputs behind canaries
+    dev = torch.device("cuda:0")
+    n = soft.shape[0] // 4 - 1
+    wide = torch.zeros((soft.shape[0], 160), dtype=torch.uint8, device=dev)
+    wide[:, 8:156] = torch.from_numpy(soft).to(dev)
+    dd = torch.full((n * 260 + 64,), 9, dtype=torch.uint8, device=dev)
+    fu = torch.full((n * 228 + 64,), 9, dtype=torch.uint8, device=dev)
+    gi = torch.full((3, n + 16), -3, dtype=torch.int32, device=dev)
+    dsp.tch_decode_dev(wide.data_ptr() + 8, 160, n, dd[32:], gi[0, 8:], gi[1, 8:], fu[32:], gi[2, 8:])
+    torch.cuda.synchronize()
+    hd, hf, hg = dd.cpu().numpy(), fu.cpu().numpy(), gi.cpu().numpy()
+    assert (hd[:32] == 9).all() and (hd[-32:] == 9).all() and (hf[:32] == 9).all() and (hf[-32:] == 9).all()
+    assert (hg[:, :8] == -3).all() and (hg[:, -8:] == -3).all()
+    assert np.array_equal(hd[32:-32].reshape(n, 260), want["d"]) and np.array_equal(hf[32:-32].reshape(n, 228), want["fu"])
+    assert np.array_equal(hg[0, 8:-8], want["good"]) and np.array_equal(hg[1, 8:-8], want["stolen"]) and np.array_equal(hg[2, 8:-8], want["fok"])
