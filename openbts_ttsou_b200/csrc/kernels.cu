@@ -830,9 +830,10 @@ int launch_analyze(const DevTables *T, BurstSrc src, const uint8_t *tsc, long lo
 }
 
 // ------------------------------------------------------------------------------------------------
-// access bursts, sps == 1, tuned: k_rach_detect (detectRACHBurst, one burst per lane, 157 x 41 correlation
-// register-blocked and written in place over the burst: 178-row tile = 47 KB per warp, taps warp-uniform from
-// __constant__ memory) then k_slicer_fast (demodulateBurst as a stream over the rolling tile).
+// access bursts, sps == 1, tuned: k_rach_detect (detectRACHBurst, one burst per lane: the 157 x 41 correlation
+// register-blocked in blocks of four lags over a ROLLING 80-row tile -- 21 KB per warp, 10 warps per SM -- with the
+// correlation parked in a global scratch row per burst; taps warp-uniform from __constant__ memory) then
+// k_slicer_fast (demodulateBurst as a stream over the rolling tile).
 // ------------------------------------------------------------------------------------------------
 __constant__ cf c_rach_taps[41];                  // conj(rach_seq[40-k]) (:474-503)
 

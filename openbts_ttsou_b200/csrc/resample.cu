@@ -13,9 +13,11 @@
 //   TX: branch = (65 o) mod 96, in = (65 o - branch)/96, y = sum_k x[in-k] * h[branch + 96 k]
 // accumulated in k order, complex x real, every product and sum rounded separately.
 //
-// Kernel shape: one CTA per chunk; the 1056 (715) input samples are staged in shared memory with
-// coalesced 16-byte loads, the polyphase taps sit in shared memory transposed [k][branch] so that a
-// warp's tap reads are spread over the banks; each thread produces outputs n, n+256, ...
+// Kernels: k_resample_rx_v3 (RX, the hot one: persistent warp-specialised CTA per SM, TMA tensor copies in, bulk copies
+// out, lane = 65-output period, straight-line 65-phase body -- described where it is defined) and k_tx_fused (the whole
+// TX chain, same shape, its input tile computed from the bits).  k_resample_rx / k_resample_tx are the plain
+// one-CTA-per-chunk forms (chunk staged in shared memory, taps transposed [k][branch], a thread per output): the
+// fallback for unaligned pointers and the stand-alone TX resampler entry point.
 #include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through the runtime, no -lcuda)
 
 #include "kernels.cuh"

@@ -137,6 +137,8 @@ int emu_check_sinc_grid(void) {
 // k_detect_design + k_equalize_fast (kernels.cu / demod_fast.cuh), warp by warp, lane by lane:
 // phase 1 on a 45-row tile (burst samples 56..91 in rows 9..44, the correlation written in place to rows 0..35,
 // the energy-gate window staged into rows 0..19 and evaluated first), phase 2 on a 160-row tile holding the detected bursts scaled by 1/amp.
+static int g_eq_ring = 1;          // which equaliser kernel's tile policy emu_demod_normal replays: ring (default) or rolling
+void emu_set_eq_ring(int on) { g_eq_ring = on; }
 void emu_demod_normal(const float *bursts, long long pitch, const int *lens, long long first, const uint8_t *tsc,
                       long long n, float detect_thr, float gate_thr, float snr_thr, int *flag, float *amp, float *toa,
                       float *soft, int soft_pitch, float *chan_o, float *off_o, float *w_o, float *b_o) {
@@ -217,6 +219,44 @@ void emu_demod_normal(const float *bursts, long long pitch, const int *lens, lon
       for (int r = 0; r < 4; r++) ycur[lane][r] = mk(0.0F, 0.0F);
     }
     if (!any) continue;
+    if (g_eq_ring) {
+      // ---- k_equalize_ring: 32-row ring indexed on each lane's output timeline (slot = (burst row + io) & 31); a group of
+      //      four rows is stored at the top of the step that first needs it; slots never stored hold poison
+      std::vector<cf> R(kEqRing * kTileStride);
+      for (auto &x : R) x = mk(1e30F, -1e30F);
+      auto store_group = [&](int mu0) {
+        for (int j = 0; j < 32; j++)
+          for (int qq = 0; qq < 4; qq++) {
+            const int mu = mu0 + qq;
+            cf v = mk(0.0F, 0.0F), ia = mk(0.0F, 0.0F);
+            if (j < nv && okv[j]) {
+              const int r = mu - eq[j].io;
+              ia = iav[j];
+              if (r >= 0 && r < lenv[j]) v = ((const cf *)bursts + startv[j])[r];
+            }
+            R[(mu & (kEqRing - 1)) * kTileStride + j] = cmul(v, ia);
+          }
+      };
+      for (int lane = 0; lane < nv; lane++) if (okv[lane]) eq[lane].a = View<kTileStride>{R.data() + lane};
+      for (int g = 0; g < 5; g++) store_group(kEqStart + 4 * g);
+      for (int m0 = kEqStart; m0 < nmax; m0 += 4) {
+        store_group(m0 + 20);
+        // the slots of rows below this step's window are the ones the NEXT store overwrites: poison them now, so a read of a
+        // row the kernel no longer holds shows up
+        for (int j = 0; j < 32; j++) for (int qq = 0; qq < 4; qq++) R[((m0 - 4 + qq) & (kEqRing - 1)) * kTileStride + j] = mk(1e30F, -1e30F);
+        bool all_int = true;
+        for (int lane = 0; lane < nv; lane++) if (okv[lane]) all_int = all_int && eq[lane].interior(m0 + 4);
+        for (int lane = 0; lane < nv; lane++) {
+          if (!okv[lane]) continue;
+          float s4[4];
+          if (all_int) eq[lane].template step<false, true>(T, 0, m0, ycur[lane], s4);
+          else eq[lane].template step<true, true>(T, 0, m0, ycur[lane], s4);
+          float *row = soft + (w0 + lane) * soft_pitch;
+          for (int r = 0; r < 4; r++) if (m0 + r >= 0 && m0 + r < lenv[lane] && m0 + r < soft_pitch) row[m0 + r] = s4[r];
+        }
+      }
+      continue;
+    }
     int base = 0;
     bool staged = false;
     for (int m0 = kEqStart; m0 < nmax; m0 += 4) {

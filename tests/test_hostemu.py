@@ -89,14 +89,23 @@ def test_design_dfe_and_equalize(emu, oracle_port):
                 assert_same(a[0], b[0], "soft"); assert_same(a[1], b[1], "burst after")
 
 
-def test_demod_normal_kernel_logic_matches_golden(emu):
+@pytest.fixture(params=["ring", "rolling"])
+def eq_tile(request, hostemu):
+    """which equaliser kernel's tile policy the emulation replays: k_equalize_ring (shipped) or k_equalize_fast (the A/B);
+    either way rows the kernel does not hold at that step read as poison"""
+    hostemu.emu_set_eq_ring(1 if request.param == "ring" else 0)
+    yield request.param
+    hostemu.emu_set_eq_ring(1)
+
+
+def test_demod_normal_kernel_logic_matches_golden(emu, eq_tile):
     g = golden("normal_sps1.npz")
     r = emu.rx_normal_batch(g["bursts"], g["lens"], g["tsc"])
     for k in ("flag", "amp", "toa", "chan", "off", "w", "b", "soft"):
         assert_same(r[k], g[k], k)
 
 
-def test_demod_normal_kernel_logic_random(emu, oracle_port):
+def test_demod_normal_kernel_logic_random(emu, oracle_port, eq_tile):
     mod = lambda b, gd: oracle_port.modulate(b, gd)  # noqa: E731
     bursts, lens, tsc, _ = synth.make_normal_batch(mod, 600, seed=21, noise_only=0.1, snr=(0, 30))
     a, b = emu.rx_normal_batch(bursts, lens, tsc), oracle_port.rx_normal_batch(bursts, lens, tsc, threads=2)
@@ -108,7 +117,7 @@ def test_demod_normal_kernel_logic_random(emu, oracle_port):
     assert (a["flag"] == (b["flag"] & gate)).all() and 0 < gate.sum() < gate.size
 
 
-def test_demod_normal_kernel_logic_edge_cases(emu, oracle_port):
+def test_demod_normal_kernel_logic_edge_cases(emu, oracle_port, eq_tile):
     bursts, lens, tsc = synth.make_edge_batch(oracle_port)
     a, b = emu.rx_normal_batch(bursts, lens, tsc), oracle_port.rx_normal_batch(bursts, lens, tsc)
     assert b["flag"].sum() > 10
