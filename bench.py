@@ -278,6 +278,18 @@ def leg_config4(torch, dsp, dev, stream, peak, fp32_peak, cores, quick):
             dsp.demod_normal_dev(bursts[lo:lo + 8192], 160, tsc[lo:lo + 8192], 8192, flag[lo:lo + 8192], amp[2 * lo:2 * lo + 16384],
                                  toa[lo:lo + 8192], soft[lo * SOFT_PITCH:(lo + 8192) * SOFT_PITCH], SOFT_PITCH, first=lo, stream=stream)
     ms_pf = timeit(torch, stream, per_frame, reps=3, warm=1)
+    # the same 128 launch pairs recorded once into a CUDA graph (btsdsp_graph_*) and replayed: the GPU-side time per frame batch
+    side = torch.cuda.Stream()
+    side.wait_stream(stream)
+    stream_saved, stream = stream, side
+    per_frame()                                   # sizes that stream's scratch before the capture
+    side.synchronize()
+    gr = dsp.graph_begin(side)
+    per_frame()
+    dsp.graph_end(gr, side)
+    stream = stream_saved
+    ms_graph = timeit(torch, side, lambda: dsp.graph_launch(gr, side), reps=3, warm=1)
+    dsp.graph_destroy(gr)
     ms_one = timeit(torch, stream, lambda: dsp.demod_normal_dev(bursts, 160, tsc, n, flag, amp, toa, soft, SOFT_PITCH, stream=stream))
     dsp.set_timing(True)
     dsp.demod_normal_dev(bursts, 160, tsc, n, flag, amp, toa, soft, SOFT_PITCH, stream=stream)
@@ -290,7 +302,8 @@ def leg_config4(torch, dsp, dev, stream, peak, fp32_peak, cores, quick):
                    "2-tap channel on half the ARFCNs, SNR U[10,30] dB, 5 %% empty slots" % frames,
            "bursts": n,
            "per_frame_launches": {"bursts_per_launch": 8192, "launches": frames, "ms_per_launch": ms_pf / frames,
-                                  "bursts_per_s": n / ms_pf * 1e3},
+                                  "bursts_per_s": n / ms_pf * 1e3,
+                                  "as_one_cuda_graph": {"ms_per_launch": ms_graph / frames, "bursts_per_s": n / ms_graph * 1e3}},
            "one_launch": {"ms": ms_one, "bursts_per_s": n / ms_one * 1e3, "detect_ms": ms_det, "equalize_ms": ms_eq},
            "roofline": kernel_entry("k_detect_design + k_equalize_ring", ms_one, n * DEMOD_BYTES_PER_BURST,
                                     n * (DETECT_OPS_PER_BURST + EQUALIZE_OPS_PER_BURST), peak, fp32_peak, "fp32-unfused"),

@@ -83,6 +83,18 @@ int btsdsp_get_timing(btsdsp_ctx *ctx, float *detect_ms, float *equalize_ms);
  * copies -- same staging buffers, segments, streams and events -- and launch no kernel: the copy roofline of the call */
 int btsdsp_set_copy_only(btsdsp_ctx *ctx, int enable);
 
+/* CUDA graphs for callers with small batches (one frame of 1024 ARFCN x 8 TS is two short kernels: launch overhead and
+ * the host's call path are a visible part of it).  Between begin and end, layer-2 calls on `stream` (not the default
+ * stream) are RECORDED instead of run; graph_launch replays the whole sequence -- same pointers, same sizes -- with one
+ * launch.  The context's scratch buffers are pinned while a graph lives: issue the largest call once before capturing,
+ * or a later, larger call fails with BTSDSP_EINVAL instead of moving a buffer the graph refers to.  The timing aid
+ * (btsdsp_set_timing) must be off during capture. */
+typedef struct btsdsp_graph btsdsp_graph;
+int btsdsp_graph_begin(btsdsp_ctx *ctx, void *stream, btsdsp_graph **graph);
+int btsdsp_graph_end(btsdsp_ctx *ctx, void *stream, btsdsp_graph *graph);
+int btsdsp_graph_launch(btsdsp_ctx *ctx, btsdsp_graph *graph, void *stream);
+int btsdsp_graph_destroy(btsdsp_ctx *ctx, btsdsp_graph *graph);
+
 /* ---- layer 1: single vectors, HOST pointers, synchronous ------------------------------------- */
 /* convolve / correlate, sigProcLib.cpp:267 / :474.  Returns the output length (c needs cap >= it). */
 int btsdsp_convolve(btsdsp_ctx *ctx, const btsdsp_cf32 *a, int la, int a_real, const btsdsp_cf32 *b, int lb,

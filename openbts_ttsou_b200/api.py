@@ -87,6 +87,10 @@ _SIGS = {
     "btsdsp_trx_pull_host": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i]),
     "btsdsp_trx_pull_streams_dev": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i, _vp]),
     "btsdsp_trx_radio_host": (_i, [_vp, _vp, _vp, _ll, _ll, _i, _i, _vp, _vp, _i]),
+    "btsdsp_graph_begin": (_i, [_vp, _vp, _vp]),
+    "btsdsp_graph_end": (_i, [_vp, _vp, _vp]),
+    "btsdsp_graph_launch": (_i, [_vp, _vp, _vp]),
+    "btsdsp_graph_destroy": (_i, [_vp, _vp]),
     "btsdsp_tch_decode_dev": (_i, [_vp, _vp, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp]),
     "btsdsp_tch_decode_host": (_i, [_vp, _vp, _i, _ll, _vp, _vp, _vp, _vp, _vp]),
     "btsdsp_tx_datagrams_host": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp]),
@@ -517,6 +521,21 @@ class BtsDsp:
         f = np.zeros(n, np.int32)
         self._ck(self.lib.btsdsp_rach_decode_host(self.h, _p(soft_u8), soft_u8.shape[1], n, _p(u), _p(f)))
         return u, f & 0xff, (f >> 8) & 0xff, (f >> 16) & 0xff
+
+    # ---- CUDA graphs: record layer-2 calls on `stream`, replay them with one launch ----
+    def graph_begin(self, stream):
+        g = ctypes.c_void_p()
+        self._ck(self.lib.btsdsp_graph_begin(self.h, _stream(stream), ctypes.byref(g)))
+        return g
+
+    def graph_end(self, graph, stream):
+        self._ck(self.lib.btsdsp_graph_end(self.h, _stream(stream), graph))
+
+    def graph_launch(self, graph, stream):
+        self._ck(self.lib.btsdsp_graph_launch(self.h, graph, _stream(stream)))
+
+    def graph_destroy(self, graph):
+        self._ck(self.lib.btsdsp_graph_destroy(self.h, graph))
 
     def tch_decode_host(self, soft_u8):
         """soft_u8 (4*nblocks + 4, pitch >= 148) -> dict(d[nblocks,260], good, stolen, fu[nblocks,228], fok)"""

@@ -46,6 +46,7 @@ struct btsdsp_ctx {
   struct StreamScratch { cudaStream_t st; DevBuf eqp, scratch, res; };
   std::vector<StreamScratch *> per_stream;
   std::mutex mu;                // guards per_stream / err / launches when layer-2 calls come from several host threads
+  std::atomic<int> graphs_alive{0};   // btsdsp_graph objects not yet destroyed (they pin the scratch buffers' addresses)
   bool copy_only = false;       // btsdsp_set_copy_only: the host pipelines move their bytes but launch nothing
   bool timing = false;          // btsdsp_set_timing: bracket the kernels of the receive path with events
   cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -83,6 +84,10 @@ struct DeviceGuard {
 
 int grow(btsdsp_ctx *ctx, DevBuf &b, size_t bytes, bool pinned = false) {
   if (bytes <= b.cap) return BTSDSP_OK;
+  // a captured graph holds the addresses of the scratch buffers its calls used: they must not move while it lives
+  if (b.p && ctx->graphs_alive.load() > 0)
+    return fail(ctx, BTSDSP_EINVAL, "a scratch buffer would have to grow while a captured graph refers to it: destroy the graph, "
+                                    "or issue the largest call once before capturing");
   size_t want = bytes + bytes / 8 + 256;
   if (b.p) { if (pinned) cudaFreeHost(b.p); else cudaFree(b.p); b.p = nullptr; b.cap = 0; }
   cudaError_t e = pinned ? cudaMallocHost(&b.p, want) : cudaMalloc(&b.p, want);
@@ -330,6 +335,52 @@ int btsdsp_set_copy_only(btsdsp_ctx *ctx, int enable) {
   ctx->copy_only = enable != 0;
   return BTSDSP_OK;
 }
+/* ---- CUDA graphs for small-batch callers: record a sequence of layer-2 calls once, replay it with one launch ---- */
+struct btsdsp_graph {
+  cudaGraphExec_t exec = nullptr;
+  long long launches = 0;       // kernels in the captured sequence
+  long long mark = 0;           // launch counter at capture begin
+};
+int btsdsp_graph_begin(btsdsp_ctx *ctx, void *stream, btsdsp_graph **out) {
+  ARG(ctx && out && stream);    // the legacy default stream cannot be captured
+  DeviceGuard g(ctx->device);
+  auto *gr = new btsdsp_graph();
+  gr->mark = ctx->launches.load();
+  cudaError_t e = cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeRelaxed);
+  if (e != cudaSuccess) { delete gr; return fail(ctx, BTSDSP_ECUDA, "cudaStreamBeginCapture", e); }
+  ctx->graphs_alive++;
+  *out = gr;
+  return BTSDSP_OK;
+}
+int btsdsp_graph_end(btsdsp_ctx *ctx, void *stream, btsdsp_graph *gr) {
+  ARG(ctx && gr && !gr->exec);
+  DeviceGuard g(ctx->device);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture((cudaStream_t)stream, &graph);
+  if (e != cudaSuccess || !graph) return fail(ctx, BTSDSP_ECUDA, "cudaStreamEndCapture", e);
+  gr->launches = ctx->launches.load() - gr->mark;
+  ctx->launches = gr->mark;     // nothing has run yet: the kernels are counted when the graph is launched
+  e = cudaGraphInstantiate(&gr->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { gr->exec = nullptr; return fail(ctx, BTSDSP_ECUDA, "cudaGraphInstantiate", e); }
+  return BTSDSP_OK;
+}
+int btsdsp_graph_launch(btsdsp_ctx *ctx, btsdsp_graph *gr, void *stream) {
+  ARG(ctx && gr && gr->exec);
+  DeviceGuard g(ctx->device);
+  CK(cudaGraphLaunch(gr->exec, (cudaStream_t)stream));
+  ctx->launches += gr->launches;
+  return BTSDSP_OK;
+}
+int btsdsp_graph_destroy(btsdsp_ctx *ctx, btsdsp_graph *gr) {
+  ARG(ctx && gr);
+  DeviceGuard g(ctx->device);
+  if (gr->exec) cudaGraphExecDestroy(gr->exec);
+  delete gr;
+  ctx->graphs_alive--;
+  return BTSDSP_OK;
+}
+
 int btsdsp_synchronize(btsdsp_ctx *ctx) {
   ARG(ctx);
   DeviceGuard g(ctx->device);

@@ -538,3 +538,54 @@ def test_rx_stream_in_pieces_equals_one_call(dsp):
         torch.cuda.synchronize()
         equal = all(torch.equal(x, y) for x, y in ((f1, f2), (a1, a2), (t1, t2), (s1, s2)))
         assert equal == hist
+
+
+@pytest.mark.gpu
+def test_cuda_graph_replay_of_small_batches(dsp, oracle_best):
+    """btsdsp_graph_*: three small demod calls recorded once and replayed give the directly-launched results (after the
+    inputs change, too); a call that would move a scratch buffer a live graph refers to is refused"""
+    import torch
+    dev = torch.device("cuda:0")
+    n = 96 * 3
+    bursts, lens, tsc, _ = synth.make_normal_batch(oracle_best.modulate, n, seed=31)
+    d_b = torch.from_numpy(bursts.view(np.float32).copy()).to(dev)
+    d_t = torch.from_numpy(tsc).to(dev)
+    d_l = torch.from_numpy(lens).to(dev)
+    st = torch.cuda.Stream()
+
+    def outs():
+        return (torch.zeros(n, dtype=torch.int32, device=dev), torch.zeros(n * 2, device=dev), torch.zeros(n, device=dev),
+                torch.zeros(n * 148, device=dev))
+
+    def calls(o, s):
+        for k in range(3):
+            lo = 96 * k
+            dsp.demod_normal_dev(d_b[lo:], 160, d_t[lo:], 96, o[0][lo:], o[1][2 * lo:], o[2][lo:], o[3][lo * 148:], 148, lens=d_l[lo:],
+                                 first=lo, stream=s)
+    ref = outs()
+    calls(ref, st)                               # direct launches (also sizes the stream's scratch before the capture)
+    st.synchronize()
+    got = outs()
+    l0 = dsp.launch_count
+    g = dsp.graph_begin(st)
+    calls(got, st)
+    dsp.graph_end(g, st)
+    assert dsp.launch_count == l0                # recorded, not run
+    st.synchronize()
+    assert not got[0].any()
+    dsp.graph_launch(g, st)
+    st.synchronize()
+    assert dsp.launch_count == l0 + 6
+    assert all(torch.equal(a, b) for a, b in zip(got, ref))
+    d_b[:96] = d_b[96:192].clone()               # same graph, new samples in the same buffers
+    calls(ref, st)
+    dsp.graph_launch(g, st)
+    st.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(got, ref))
+    big = 40000                                  # a call on that stream that needs more scratch than the graph's calls had
+    with pytest.raises(Exception):
+        dsp.demod_normal_dev(torch.zeros(big * 160 * 2, device=dev), 160, torch.zeros(big, dtype=torch.uint8, device=dev), big,
+                             torch.zeros(big, dtype=torch.int32, device=dev), torch.zeros(big * 2, device=dev), torch.zeros(big, device=dev),
+                             torch.zeros(big * 148, device=dev), 148, stream=st)
+    dsp.graph_destroy(g)
+    st.synchronize()
