@@ -359,7 +359,9 @@ template <int WARPS> constexpr size_t equalize_smem() { return WARPS * kEqTileBy
 
 // POLICY = pass 1 of the caller-policy pipeline (trx_policy.cuh): the energy is measured but not judged, the analysis
 // runs on the slots `kind` marks as TSC, and the results go to a DetRec instead of into a DFE design.
-template <int WARPS, bool POLICY = false>
+// SPLIT = the stateless path with designDFE left to a second launch (k_design_eqp): this kernel stops after the analysis
+// and parks {flag, amp, TOA, offset, channel} in a DetRec.
+template <int WARPS, bool POLICY = false, bool SPLIT = false>
 __global__ void __launch_bounds__(WARPS * 32) k_detect_design(const DevTables *__restrict__ T, BurstSrc src,
                                                               const uint8_t *__restrict__ tsc, long long n,
                                                               float detect_thr, float gate_thr, float snr_thr,
@@ -428,7 +430,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_detect_design(const DevTables *_
   cf amp = mk(0.0F, 0.0F), ia = mk(0.0F, 0.0F), chan[6], w[7], fb[5];
   float toa = 0.0F, off = 0.0F;
   if (pass) ok = analyze_fast<kTileStride>(g, T, a.at(kDetWin), a, tsc[i], detect_thr, &amp, &toa, chan, &off);
-  if (POLICY) {
+  if (POLICY || SPLIT) {
     float4 *q = reinterpret_cast<float4 *>(det + i);
     q[0] = make_float4(avg_pwr, ok ? 1.0F : 0.0F, amp.x, amp.y);
     q[1] = make_float4(toa, ok ? off : 0.0F, 0.0F, 0.0F);
@@ -744,8 +746,56 @@ __global__ void __launch_bounds__(32, BTS_EQ_MINCTAS) k_equalize_ring(const DevT
   }
 }
 
+// second half of the split stateless path: designDFE from the parked records, then the same outputs as the fused kernel
+__global__ void __launch_bounds__(64) k_design_eqp(long long n, const DetRec *__restrict__ det, float snr_thr, NormalOut out,
+                                                   EqParams *__restrict__ eqp) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 *dq = reinterpret_cast<const float4 *>(det + i);
+  const float4 d0 = __ldg(dq), d1 = __ldg(dq + 1);
+  const bool ok = d0.y != 0.0F;
+  const cf amp = mk(d0.z, d0.w);
+  const float toa = d1.x, off = d1.y;
+  cf ia = mk(0.0F, 0.0F), chan[6], w[7], fb[5];
+  if (ok) {
+    const float4 c0 = __ldg(dq + 2), c1 = __ldg(dq + 3), c2 = __ldg(dq + 4);
+    chan[0] = mk(c0.x, c0.y); chan[1] = mk(c0.z, c0.w); chan[2] = mk(c1.x, c1.y);
+    chan[3] = mk(c1.z, c1.w); chan[4] = mk(c2.x, c2.y); chan[5] = mk(c2.z, c2.w);
+    const float SNR = (float)((double)cnorm2(amp) / ((double)BTS_MUL(snr_thr, snr_thr) + 1.0));   // Transceiver.cpp:340
+    ia = cdiv(mk(1.0F, 0.0F), amp);
+#pragma unroll
+    for (int j = 0; j < 6; j++) chan[j] = cmul(chan[j], ia);                                    // :346
+    design_dfe<7, 5>(chan, 5, SNR, 7, w, fb);                                                   // :347
+  } else {
+#pragma unroll
+    for (int j = 0; j < 6; j++) chan[j] = mk(0.0F, 0.0F);
+#pragma unroll
+    for (int j = 0; j < 7; j++) w[j] = mk(0.0F, 0.0F);
+#pragma unroll
+    for (int j = 0; j < 5; j++) fb[j] = mk(0.0F, 0.0F);
+  }
+  if (out.flag) out.flag[i] = ok ? 1 : 0;
+  if (out.amp) out.amp[i] = amp;
+  if (out.toa) out.toa[i] = toa;
+  if (out.off) out.off[i] = ok ? off : 0.0F;
+  if (out.chan) for (int j = 0; j < 6; j++) out.chan[i * 6 + j] = chan[j];
+  if (out.w) for (int j = 0; j < 7; j++) out.w[i * 7 + j] = w[j];
+  if (out.b) for (int j = 0; j < 5; j++) out.b[i * 5 + j] = fb[j];
+  if (eqp) {
+    float4 *q = reinterpret_cast<float4 *>(eqp + i);
+    q[0] = make_float4(ia.x, ia.y, BTS_SUB(toa, off), ok ? 1.0F : 0.0F);
+    q[1] = make_float4(w[0].x, w[0].y, w[1].x, w[1].y);
+    q[2] = make_float4(w[2].x, w[2].y, w[3].x, w[3].y);
+    q[3] = make_float4(w[4].x, w[4].y, w[5].x, w[5].y);
+    q[4] = make_float4(w[6].x, w[6].y, fb[0].x, fb[0].y);
+    q[5] = make_float4(fb[1].x, fb[1].y, fb[2].x, fb[2].y);
+    q[6] = make_float4(fb[3].x, fb[3].y, fb[4].x, fb[4].y);
+  }
+}
 static bool g_eq_ring = true;
-size_t demod_scratch_bytes(long long n) { return (size_t)n * sizeof(EqParams); }
+static bool g_det_split = false;
+// EqParams records, then (split path) DetRec records behind them
+size_t demod_scratch_bytes(long long n) { return (size_t)n * (sizeof(EqParams) + sizeof(DetRec)); }
 // access bursts: the records plus a 160-sample correlation scratch row per burst (128-byte aligned behind the records)
 size_t rach_scratch_bytes(long long n) { return (((size_t)n * sizeof(EqParams) + 127) & ~(size_t)127) + (size_t)n * 160 * sizeof(cf); }
 
@@ -757,6 +807,15 @@ int launch_demod_normal(const DevTables *T, BurstSrc src, const uint8_t *tsc, lo
   if (n <= 0) return 0;
   const long long nwarps = (n + 31) / 32;
   EqParams *eqp = (out.soft || out.soft_u8) ? reinterpret_cast<EqParams *>(scratch) : nullptr;
+  if (g_det_split) {    // analysis and designDFE as two launches (BTSDSP_DET_SPLIT=1): measurement variant
+    DetRec *det = reinterpret_cast<DetRec *>(reinterpret_cast<EqParams *>(scratch) + n);
+    NormalOut none{};
+    if (nwarps >= kDetWideMin)
+      k_detect_design<kDetWarps, false, true><<<(unsigned)((nwarps + kDetWarps - 1) / kDetWarps), 32 * kDetWarps, detect_smem<kDetWarps>(), st>>>(T, src, tsc, n, detect_thr, gate_thr, snr_thr, none, nullptr, nullptr, det);
+    else
+      k_detect_design<1, false, true><<<(unsigned)nwarps, 32, detect_smem<1>(), st>>>(T, src, tsc, n, detect_thr, gate_thr, snr_thr, none, nullptr, nullptr, det);
+    k_design_eqp<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, det, snr_thr, out, eqp);
+  } else
   // one-warp CTAs, 12 KB of shared memory and 124 registers each: 16 resident per SM
   if (nwarps >= kDetWideMin)
     k_detect_design<kDetWarps><<<(unsigned)((nwarps + kDetWarps - 1) / kDetWarps), 32 * kDetWarps, detect_smem<kDetWarps>(), st>>>(T, src, tsc, n, detect_thr, gate_thr, snr_thr, out, eqp);
@@ -1328,6 +1387,11 @@ int configure_kernels() {
   if (e != cudaSuccess) return (int)e;
   if (configure_detect_52m() != 0) return -52;
   if (const char *e = getenv("BTSDSP_EQ_RING")) g_eq_ring = atoi(e) != 0;
+  if (const char *e = getenv("BTSDSP_DET_SPLIT")) g_det_split = atoi(e) != 0;
+  e = cudaFuncSetAttribute(k_detect_design<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<1>());
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_detect_design<kDetWarps, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<kDetWarps>());
+  if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_equalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRachSmem);
   return (int)e;
 }
