@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise an ncu launch list (--metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv) of
-`bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline` into profiles/<round>_traffic.json (what bench.py reads for
+`bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-secondary` into profiles/<round>_traffic.json (what bench.py reads for
 roofline.traffic).  usage: tools/ncu_traffic.py launches.csv out.json blocks [full_raw.csv]"""
 import csv, json, sys
 
@@ -38,6 +38,6 @@ if full:
                 break
 json.dump({"what": "dram__bytes_read.sum + dram__bytes_write.sum and gpu__time_duration.sum per launch (mean over the full-size "
                    "launches of the three kernels) from ncu (--clock-control none) on `python bench.py --steps 2 --warmup 3 "
-                   "--no-e2e --no-cpu-baseline`; raw list: %s%s" % (launches.split("/")[-1], "; issue/fma pipe pcts from " + full.split("/")[-1] if full else ""),
+                   "--no-e2e --no-cpu-baseline --no-secondary`; raw list: %s%s" % (launches.split("/")[-1], "; issue/fma pipe pcts from " + full.split("/")[-1] if full else ""),
            "blocks": blocks, "kernels": kern}, open(out, "w"), indent=1)
 print(json.dumps(kern, indent=1))
