@@ -245,13 +245,13 @@ def leg_config3(torch, dsp, dev, stream, peak, fp32_peak, cores, quick):
     # parity with the compiled reference on a strided sample that covers every (TOA, SNR) cell
     from oracle.oracle import Oracle
     o = Oracle("best", sps=1)
-    ns = min(n, 65536)
+    ns = n if cores >= 8 else min(n, 65536)          # every burst (about 1.5 s of the reference on 16 cores), else a strided sample
     idx = torch.arange(ns, device=dev) * (n // ns)
     hb = torch.view_as_complex(bursts[idx]).cpu().numpy()
     lens = np.where((idx.cpu().numpy() % 4) == 0, 157, 156).astype(np.int32)
     r = o.rx_rach_batch(hb, lens, 5.0, threads=cores)
     g_soft = soft.reshape(n, 160)[idx].cpu().numpy()
-    g_soft[np.arange(ns)[:, None] * 0 + np.arange(160)[None, :] >= lens[:, None]] = 0
+    g_soft[np.arange(160)[None, :] >= lens[:, None]] = 0
     r_soft = r["soft"].copy()
     r_soft[np.arange(160)[None, :] >= lens[:, None]] = 0
     out["check"] = {"vs": o.kind, "bursts": int(ns),
@@ -314,8 +314,8 @@ def leg_config4(torch, dsp, dev, stream, peak, fp32_peak, cores, quick):
            "ber_detected_by_tsc": {str(t): float((hard[det & (tsc == t)] != bits[det & (tsc == t)]).float().mean()) for t in range(8)}}
     from oracle.oracle import Oracle
     o = Oracle("best", sps=1)
-    ns = min(n, 65536)
-    idx = torch.arange(ns, device=dev) * (n // ns) + (torch.arange(ns, device=dev) % 8)      # every TN and TSC
+    ns = n if cores >= 8 else min(n, 65536)          # every burst (about 2 s of the reference on 16 cores), else a strided sample
+    idx = torch.arange(ns, device=dev) * (n // ns) + ((torch.arange(ns, device=dev) % 8) if ns < n else 0)   # every TN and TSC
     idx = idx.clamp_(max=n - 1)
     hb = torch.view_as_complex(bursts[idx]).cpu().numpy()
     hi = idx.cpu().numpy()
