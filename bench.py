@@ -599,6 +599,8 @@ def main():
     # ---- rooflines of the step's kernels
     peak, how = measured_peaks()
     sm_mhz = (clocks or {}).get("sm_mhz") or 0.0
+    if not sm_mhz:                                           # ranks > 0 and boxes without nvidia-smi: the device's rated clock
+        sm_mhz = float(getattr(torch.cuda.get_device_properties(dev), "clock_rate", 0)) / 1e3
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     fp32_peak = sms * LANES_PER_SM * sm_mhz * 1e6            # unfused lane-ops per second at the clock this run held
 

@@ -361,8 +361,11 @@ template <int WARPS> constexpr size_t equalize_smem() { return WARPS * kEqTileBy
 // runs on the slots `kind` marks as TSC, and the results go to a DetRec instead of into a DFE design.
 // SPLIT = the stateless path with designDFE left to a second launch (k_design_eqp): this kernel stops after the analysis
 // and parks {flag, amp, TOA, offset, channel} in a DetRec.
+#ifndef BTS_DET_MINWARPS
+#define BTS_DET_MINWARPS 0            // > 0: ask ptxas for that many resident warps per SM (caps the registers)
+#endif
 template <int WARPS, bool POLICY = false, bool SPLIT = false>
-__global__ void __launch_bounds__(WARPS * 32) k_detect_design(const DevTables *__restrict__ T, BurstSrc src,
+__global__ void __launch_bounds__(WARPS * 32, BTS_DET_MINWARPS ? BTS_DET_MINWARPS / WARPS : 1) k_detect_design(const DevTables *__restrict__ T, BurstSrc src,
                                                               const uint8_t *__restrict__ tsc, long long n,
                                                               float detect_thr, float gate_thr, float snr_thr,
                                                               NormalOut out, EqParams *__restrict__ eqp,

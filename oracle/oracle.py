@@ -366,9 +366,8 @@ class Oracle:
         return e
 
     def tch_decode(self, soft_u8):
-        """soft_u8: (4*nblocks + 4, >=148) soft bytes of one traffic channel's consecutive bursts (ref only).
+        """soft_u8: (4*nblocks + 4, >=148) soft bytes of one traffic channel's consecutive bursts.
         Returns dict(d[nblocks,260], good, stolen, fu[nblocks,228], fok)."""
-        assert self.kind == "ref"
         soft_u8 = np.ascontiguousarray(soft_u8, np.uint8)
         n = soft_u8.shape[0] // 4 - 1
         r = dict(d=np.zeros((n, 260), np.uint8), good=np.zeros(n, np.int32), stolen=np.zeros(n, np.int32),

@@ -812,63 +812,112 @@ static unsigned apply_poly(unsigned val, unsigned poly, unsigned order) {      /
   for (unsigned i = 1; i < order; i++) sum ^= prod >> i;
   return sum & 1u;
 }
+/* SoftVector::decode (BitVector.cpp:451-540) for nc coded probabilities c[] -> nc/2 decoded bits u[] */
+static void viterbi_decode(const float *c, int nc, unsigned char *up) {
+  enum { ORDER = 4, STATES = 16, CANDS = 32, DEFER = 24, MAXC = 456, CT = 456 + 2 * 24 };
+  static unsigned gen[CANDS];
+  static int have_gen = 0;
+  if (!have_gen) {
+    for (unsigned idx = 0; idx < CANDS; idx++) gen[idx] = (apply_poly(idx, 0x019, ORDER + 1) << 1) | apply_poly(idx, 0x01b, ORDER + 1);
+    have_gen = 1;
+  }
+  const int nu = nc / 2, ct = nc + 2 * DEFER;
+  float match[CT], mismatch[CT];
+  unsigned history[CT];
+  unsigned accum = 0;
+  for (int i = 0; i < nc; i++) { accum = (accum << 1) | (c[i] > 0.5F ? 1u : 0u); history[i] = accum; }   /* :452-461 */
+  for (int i = nc; i < ct; i++) { accum = (accum << 1) | (accum & 1u); history[i] = accum; }
+  for (int i = 0; i < nc; i++) {                                               /* :476-490 */
+    float pVal = c[i];
+    if (pVal > 0.5F) pVal = 1.0F - pVal;
+    float ipVal = 1.0F - pVal;
+    if (pVal < 0.01F) pVal = 0.01;
+    if (ipVal < 0.01F) ipVal = 0.01;
+    match[i] = 0.25F / ipVal;
+    mismatch[i] = 0.25F / pVal;
+  }
+  for (int i = nc; i < ct; i++) { match[i] = 0.5F; mismatch[i] = 0.5F; }
+  float scost[STATES] = {0}, ccost[CANDS];
+  unsigned sin_[STATES] = {0}, sout[STATES] = {0}, cin[CANDS], cout[CANDS];
+  for (int s = 0; s < nu + DEFER; s++) {
+    const unsigned in = history[2 * s + 1];
+    const float *m0 = match + 2 * s, *m1 = mismatch + 2 * s;
+    for (int i = 0; i < CANDS; i += 2) {                                       /* branchCandidates */
+      const int sp = i / 2;
+      const unsigned i0 = sin_[sp] << 1, i1 = i0 | 1u, osh = sout[sp] << 2;
+      ccost[i] = scost[sp]; cout[i] = osh | gen[i0 & 0x1f]; cin[i] = i0;
+      ccost[i + 1] = scost[sp]; cout[i + 1] = osh | gen[i1 & 0x1f]; cin[i + 1] = i1;
+    }
+    for (int i = 0; i < CANDS; i++) {                                          /* getSoftCostMetrics */
+      const unsigned mm = in ^ cout[i];
+      ccost[i] += ((mm & 1u) ? m1 : m0)[1] + (((mm >> 1) & 1u) ? m1 : m0)[0];
+    }
+    for (int i = 0; i < STATES; i++) {                                         /* pruneCandidates */
+      const int w = ccost[i] < ccost[i + STATES] ? i : i + STATES;
+      scost[i] = ccost[w]; sin_[i] = cin[w]; sout[i] = cout[w];
+    }
+    int best = 0;                                                              /* minCost */
+    float bc = scost[0];
+    for (int i = 1; i < STATES; i++) { if (scost[i] >= bc) continue; bc = scost[i]; best = i; }
+    if (s >= DEFER) up[s - DEFER] = (sin_[best] >> DEFER) & 1u;
+  }
+}
+/* Fire-code syndrome of d[184] : ~p[40], kept in an `unsigned` as GSML1FEC.cpp:652 does */
+static int xcch_syndrome_ok(const unsigned char *up) {
+  unsigned long long state = 0;
+  for (int i = 0; i < 224; i++) {
+    const unsigned bit = (i < 184 ? up[i] : ~up[i]) & 1u;
+    const unsigned fb = (unsigned)(state >> 39) & 1u;
+    state = (state << 1) ^ bit;
+    if (fb) state ^= 0x10004820009ULL;
+  }
+  return (unsigned)(state & ((1ULL << 40) - 1)) == 0u;
+}
 void port_xcch_decode(const unsigned char *soft, int burst_pitch, long nframes, unsigned char *u, int *ok) {
-  enum { ORDER = 4, STATES = 16, CANDS = 32, DEFER = 24, SZ = 456, CT = 456 + 2 * 24 };
-  unsigned gen[CANDS];
-  for (unsigned idx = 0; idx < CANDS; idx++) gen[idx] = (apply_poly(idx, 0x019, ORDER + 1) << 1) | apply_poly(idx, 0x01b, ORDER + 1);
   for (long f = 0; f < nframes; f++) {
-    float c[SZ], match[CT], mismatch[CT];
-    unsigned history[CT];
-    for (int k = 0; k < SZ; k++) {                                             /* GSML1FEC.cpp:620-624, :603-604 */
+    float c[456];
+    for (int k = 0; k < 456; k++) {                                            /* GSML1FEC.cpp:620-624, :603-604 */
       int B = k % 4, j = 2 * ((49 * k) % 57) + ((k % 8) / 4);
       const unsigned char *rp = soft + (size_t)burst_pitch * (4 * f + B);
       c[k] = rp[j < 57 ? 3 + j : 88 + (j - 57)] / 256.0F;                       /* TRXManager.cpp:230 */
     }
-    unsigned accum = 0;
-    for (int i = 0; i < SZ; i++) { accum = (accum << 1) | (c[i] > 0.5F ? 1u : 0u); history[i] = accum; }   /* :452-461 */
-    for (int i = SZ; i < CT; i++) { accum = (accum << 1) | (accum & 1u); history[i] = accum; }
-    for (int i = 0; i < SZ; i++) {                                             /* :476-490 */
-      float pVal = c[i];
-      if (pVal > 0.5F) pVal = 1.0F - pVal;
-      float ipVal = 1.0F - pVal;
-      if (pVal < 0.01F) pVal = 0.01;
-      if (ipVal < 0.01F) ipVal = 0.01;
-      match[i] = 0.25F / ipVal;
-      mismatch[i] = 0.25F / pVal;
+    viterbi_decode(c, 456, u + 228 * f);
+    ok[f] = xcch_syndrome_ok(u + 228 * f);
+  }
+}
+/* TCHFACCHL1Decoder::processBurst / deinterleave / decodeTCH + XCCHL1Decoder::decode for stolen blocks (GSML1FEC.cpp:1031-1210),
+ * same entry point and block numbering as oracle/ref_shim.cpp's ref_tch_decode (block q = bursts 4q .. 4q+7). */
+void port_tch_decode(const unsigned char *soft, int burst_pitch, long nblocks, unsigned char *d, int *good, int *stolen_o,
+                     unsigned char *fu, int *fok) {
+  for (long q = 0; q < nblocks; q++) {
+    float c[456];
+    for (int k = 0; k < 456; k++) {                                            /* :1102-1110 */
+      const int r = k % 8, j = 2 * ((49 * k) % 57) + (r / 4);
+      const unsigned char *rp = soft + (size_t)burst_pitch * (4 * q + r);
+      c[k] = rp[j < 57 ? 3 + j : 88 + (j - 57)] / 256.0F;
     }
-    for (int i = SZ; i < CT; i++) { match[i] = 0.5F; mismatch[i] = 0.5F; }
-    float scost[STATES] = {0}, ccost[CANDS];
-    unsigned sin_[STATES] = {0}, sout[STATES] = {0}, cin[CANDS], cout[CANDS];
-    unsigned char *up = u + 228 * f;
-    for (int s = 0; s < 228 + DEFER; s++) {
-      const unsigned in = history[2 * s + 1];
-      const float *m0 = match + 2 * s, *m1 = mismatch + 2 * s;
-      for (int i = 0; i < CANDS; i += 2) {                                     /* branchCandidates */
-        const int sp = i / 2;
-        const unsigned i0 = sin_[sp] << 1, i1 = i0 | 1u, osh = sout[sp] << 2;
-        ccost[i] = scost[sp]; cout[i] = osh | gen[i0 & 0x1f]; cin[i] = i0;
-        ccost[i + 1] = scost[sp]; cout[i + 1] = osh | gen[i1 & 0x1f]; cin[i + 1] = i1;
+    const int stolen = (soft[(size_t)burst_pitch * (4 * q + 7) + 60] / 256.0F) > 0.5F;   /* inBurst.Hl(), :1075 */
+    stolen_o[q] = stolen;
+    memset(d + 260 * q, 0, 260);
+    memset(fu + 228 * q, 0, 228);
+    good[q] = 0; fok[q] = 0;
+    if (stolen) {
+      viterbi_decode(c, 456, fu + 228 * q);
+      fok[q] = xcch_syndrome_ok(fu + 228 * q);
+    } else {                                                                   /* decodeTCH(false), :1129-1160 */
+      unsigned char u[189], *dd = d + 260 * q;
+      viterbi_decode(c, 378, u);
+      for (int i = 0; i < 78; i++) dd[182 + i] = c[378 + i] > 0.5F;
+      for (int k = 0; k <= 90; k++) { dd[2 * k] = u[k]; dd[2 * k + 1] = u[184 - k]; }
+      const unsigned sent = (~((u[91] << 2) | (u[92] << 1) | u[93])) & 7u;
+      unsigned state = 0;
+      for (int i = 0; i < 50; i++) {
+        const unsigned fb = ((state >> 2) ^ dd[i]) & 1u;
+        state <<= 1;
+        if (fb) state ^= 0x0bu;
       }
-      for (int i = 0; i < CANDS; i++) {                                        /* getSoftCostMetrics */
-        const unsigned mm = in ^ cout[i];
-        ccost[i] += ((mm & 1u) ? m1 : m0)[1] + (((mm >> 1) & 1u) ? m1 : m0)[0];
-      }
-      for (int i = 0; i < STATES; i++) {                                       /* pruneCandidates */
-        const int w = ccost[i] < ccost[i + STATES] ? i : i + STATES;
-        scost[i] = ccost[w]; sin_[i] = cin[w]; sout[i] = cout[w];
-      }
-      int best = 0;                                                            /* minCost */
-      float bc = scost[0];
-      for (int i = 1; i < STATES; i++) { if (scost[i] >= bc) continue; bc = scost[i]; best = i; }
-      if (s >= DEFER) up[s - DEFER] = (sin_[best] >> DEFER) & 1u;
+      const unsigned tail = (u[185] << 3) | (u[186] << 2) | (u[187] << 1) | u[188];
+      good[q] = sent == (state & 7u) && tail == 0;
     }
-    unsigned long long state = 0;                                              /* syndrome of d : ~p */
-    for (int i = 0; i < 224; i++) {
-      const unsigned bit = (i < 184 ? up[i] : ~up[i]) & 1u;
-      const unsigned fb = (unsigned)(state >> 39) & 1u;
-      state = (state << 1) ^ bit;
-      if (fb) state ^= 0x10004820009ULL;
-    }
-    ok[f] = (unsigned)(state & ((1ULL << 40) - 1)) == 0u;                     /* GSML1FEC.cpp:652 keeps it in an `unsigned` */
   }
 }

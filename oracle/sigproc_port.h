@@ -56,6 +56,8 @@ void  port_trx_pull(void *state, const float *bursts, int pitch, int nframes, in
                     unsigned char *dgram, int dgram_pitch);
 /* XCCH block decoder (deinterleave + soft Viterbi + Fire-code syndrome); see sigproc_port.c */
 void  port_xcch_decode(const unsigned char *soft, int burst_pitch, long nframes, unsigned char *u, int *ok);
+void  port_tch_decode(const unsigned char *soft, int burst_pitch, long nblocks, unsigned char *d, int *good, int *stolen,
+                      unsigned char *fu, int *fok);
 #ifdef __cplusplus
 }
 #endif

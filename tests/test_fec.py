@@ -275,6 +275,12 @@ def test_tch_hostemu_matches_reference(oracle_best, hostemu, tch_stream):
     assert all(np.array_equal(got[k], want[k]) for k in want)
 
 
+def test_tch_port_matches_reference(oracle_port, oracle_best, tch_stream):
+    soft, d, f, steal = tch_stream
+    want, got = oracle_best.tch_decode(soft), oracle_port.tch_decode(soft)
+    assert all(np.array_equal(got[k], want[k]) for k in want)
+
+
 def test_tch_clean_channel_round_trip(oracle_best, hostemu):
     """noise-free: every speech frame comes back whole and good, every FACCH payload too"""
     if oracle_best.kind != "ref":
