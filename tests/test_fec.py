@@ -318,3 +318,12 @@ def test_tch_gpu_matches_reference(oracle_best, dsp, tch_stream):
     assert (hg[:, :8] == -3).all() and (hg[:, -8:] == -3).all()
     assert np.array_equal(hd[32:-32].reshape(n, 260), want["d"]) and np.array_equal(hf[32:-32].reshape(n, 228), want["fu"])
     assert np.array_equal(hg[0, 8:-8], want["good"]) and np.array_equal(hg[1, 8:-8], want["stolen"]) and np.array_equal(hg[2, 8:-8], want["fok"])
+
+
+def test_tch_port_and_hostemu_match_golden(oracle_port, hostemu):
+    """fixture written by the compiled reference (oracle/gen_golden_r3.py): holds on a box without the reference too"""
+    g = golden("tch_sps1.npz")
+    for r in (oracle_port.tch_decode(g["soft"]), Emu(hostemu).tch_decode(g["soft"])):
+        for k in ("d", "good", "stolen", "fu", "fok"):
+            assert np.array_equal(r[k], g[k]), k
+    assert 0 < g["stolen"].sum() < g["stolen"].size and g["good"].any()

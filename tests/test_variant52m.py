@@ -180,3 +180,26 @@ def test_tx_datagrams_52m_gpu(o52, dsp):
         got, gp = dsp.tx_datagrams_52m_host(dg, fn0, nframes, fl)
         assert wp == gp and 0 < gp < n
         same(got, want, "52M tx datagrams, filler %s" % (fl is not None))
+
+
+def test_policy_52m_hostemu_matches_golden(oracle_best, hostemu):
+    """the second variant's policy against the fixture the compiled 52M reference wrote (oracle/gen_golden_r3.py)"""
+    import hashlib
+    from conftest import golden
+    from oracle.oracle import Oracle
+    from test_trx_policy import check_state
+    g = golden("trx52_sps1.npz")
+    bursts = synth.make_trx_batch(oracle_best.modulate, oracle_best.expected_corr_type, NFRAMES, TSC, CHAN_TYPES, fn0=FN0, seed=52)
+    if hashlib.sha1(bursts.tobytes()).digest() != g["sha1"].tobytes():
+        pytest.skip("regenerated inputs differ from the fixture's (different modulator build)")
+    emu = Emu(hostemu)
+    A = len(TSC)
+    for md in (1, 4):
+        st = emu.trx_new(TSC, CHAN_TYPES, FN0 - 3)
+        v2, d2 = np.zeros_like(g["valid%d" % md]), np.zeros_like(g["dgram%d" % md])
+        for lo, hi in [(0, 29), (29, 30), (30, NFRAMES)]:
+            v, d = emu.trx_pull_52m(st, bursts[lo * A * 8:hi * A * 8], FN0 + lo, md)
+            v2[lo * A * 8:hi * A * 8] = v
+            d2[lo * A * 8:hi * A * 8] = d[:, :158]
+        assert np.array_equal(v2, g["valid%d" % md]) and np.array_equal(d2, g["dgram%d" % md])
+        check_state(st, g["state%d" % md].reshape(-1).view(Oracle.TRX_STATE_DTYPE), "52M golden maxdly %d" % md)
