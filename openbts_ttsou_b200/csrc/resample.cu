@@ -18,6 +18,7 @@
 // TX chain, same shape, its input tile computed from the bits).  k_resample_rx / k_resample_tx are the plain
 // one-CTA-per-chunk forms (chunk staged in shared memory, taps transposed [k][branch], a thread per output): the
 // fallback for unaligned pointers and the stand-alone TX resampler entry point.
+#include <stdlib.h>
 #include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through the runtime, no -lcuda)
 
 #include "kernels.cuh"
@@ -408,16 +409,20 @@ constexpr int kTxFusedBursts = ((kTxFusedIn + 624) / 625 + 1) * 4;             /
 constexpr size_t kTxFusedSmem = (size_t)kTxFusedIn * sizeof(cf) + (size_t)kTxFusedPeriods * kTxFusedOutPitch * 4 + kTxP * 8 * 4 +
                                 148 * 3 * sizeof(cf) + (size_t)kTxFusedBursts * 148;
 
+// BITS = false: the same resampler over an already modulated stream `samples` (the stand-alone pushBuffer entry point,
+// btsdsp_resample_tx_dev): the tile is loaded instead of computed; has_history says samples[-4..-1] are real stream samples
+template <bool BITS>
 __global__ void __launch_bounds__(kTxFusedThreads, 1) k_tx_fused(const DevTables *__restrict__ T, const uint8_t *__restrict__ bits,
                                                                 const float *__restrict__ scale, long long nsamples,
-                                                                long long nperiods, int nstreams, short2 *__restrict__ out) {
+                                                                long long nperiods, int nstreams, short2 *__restrict__ out,
+                                                                const cf *__restrict__ samples = nullptr, int has_history = 0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf *xs = reinterpret_cast<cf *>(smem_raw);                             // xs[j] = stream sample 65*G0 - 4 + j
   short2 *os = reinterpret_cast<short2 *>(xs + kTxFusedIn);
   float *taps = reinterpret_cast<float *>(os + kTxFusedPeriods * kTxFusedOutPitch);
   cf *q = reinterpret_cast<cf *>(taps + kTxP * 8);                       // rot[ai] * pulse[k]
   unsigned char *sb = reinterpret_cast<unsigned char *>(q + 148 * 3);    // this step's bursts, 148 bytes each
-  for (int i = threadIdx.x; i < 148 * 3; i += kTxFusedThreads) tx_fill_q(T, q, i);
+  if (BITS) for (int i = threadIdx.x; i < 148 * 3; i += kTxFusedThreads) tx_fill_q(T, q, i);
   for (int i = threadIdx.x; i < kTxP * 8; i += kTxFusedThreads) {        // taps[r*8 + k] = lpf_tx[br_r + 96 k]
     const int r = i >> 3, k = i & 7;
     int br = (kTxQ * (r + kTxDropC + 5)) % kTxP;
@@ -446,38 +451,47 @@ __global__ void __launch_bounds__(kTxFusedThreads, 1) k_tx_fused(const DevTables
     return v;
   };
   static_assert(kTxFusedBursts * 148 <= kTxFusedThreads * 16, "one 16-byte fetch per thread must cover a step's bits");
-  int4 pre = blockIdx.x < ngsteps ? fetch(blockIdx.x) : make_int4(0, 0, 0, 0);
+  int4 pre = (BITS && blockIdx.x < ngsteps) ? fetch(blockIdx.x) : make_int4(0, 0, 0, 0);
   for (long long gs = blockIdx.x; gs < ngsteps; gs += gridDim.x) {
     const long long a = gs / nsteps, step = gs - a * nsteps;
     const long long G0 = step * kTxFusedPeriods;
     __syncthreads();                                                     // previous step's tiles are free
     // ---- park the bits of the bursts this step touches, then modulate its samples into the tile
     const long long s0 = (long long)kTxQ * G0 - kTxHalo;
-    const long long ga4 = group_of(step);                                // staging starts at slot 4*ga4
-    if (vec) {
-      if ((int)threadIdx.x * 16 < kTxFusedBursts * 148) reinterpret_cast<int4 *>(sb)[threadIdx.x] = pre;
-    } else {
-      const long long gfirst = ga4 * 4;
-      long long nb = nslots - gfirst;
-      if (nb > kTxFusedBursts) nb = kTxFusedBursts;
-      const unsigned char *src = bits + (a * nslots + gfirst) * 148;
-      for (int i = threadIdx.x; i < (int)nb * 148; i += kTxFusedThreads) sb[i] = src[i];
-    }
-    __syncthreads();
-    if (gs + gridDim.x < ngsteps) pre = fetch(gs + gridDim.x);           // in flight during this step
-    const int w0 = (int)(s0 - ga4 * 625);                                // in [-4, 624]
-    for (int j = threadIdx.x; j < kTxFusedIn; j += kTxFusedThreads) {
-      const int w = w0 + j;
-      cf x = mk(0.0F, 0.0F);
-      if (w >= 0 && s0 + j < nsamples) {
-        const int q4 = w / 625;
-        int sl, t;
-        tx_slot_of(w - q4 * 625, &sl, &t);
-        const int lb = q4 * 4 + sl;                                      // burst index within the staged bits
-        x = tx_burst_sample(q, sb + lb * 148, t);
-        if (scale) x = cmul(x, mk(scale[a * nslots + ga4 * 4 + lb], 0.0F));   // addRadioVector's scaleVector, Transceiver.cpp:108
+    if (!BITS) {
+      // ---- the stand-alone resampler: the step's 6248 samples come from the modulated stream (coalesced 8-byte loads)
+      const cf *sp = samples + a * nsamples;
+      for (int j = threadIdx.x; j < kTxFusedIn; j += kTxFusedThreads) {
+        const long long t = s0 + j;
+        xs[j] = ((t >= 0 || (has_history && a == 0)) && t < nsamples) ? __ldg(sp + t) : mk(0.0F, 0.0F);
       }
-      xs[j] = x;
+    } else {
+      const long long ga4 = group_of(step);                              // staging starts at slot 4*ga4
+      if (vec) {
+        if ((int)threadIdx.x * 16 < kTxFusedBursts * 148) reinterpret_cast<int4 *>(sb)[threadIdx.x] = pre;
+      } else {
+        const long long gfirst = ga4 * 4;
+        long long nb = nslots - gfirst;
+        if (nb > kTxFusedBursts) nb = kTxFusedBursts;
+        const unsigned char *src = bits + (a * nslots + gfirst) * 148;
+        for (int i = threadIdx.x; i < (int)nb * 148; i += kTxFusedThreads) sb[i] = src[i];
+      }
+      __syncthreads();
+      if (gs + gridDim.x < ngsteps) pre = fetch(gs + gridDim.x);           // in flight during this step
+      const int w0 = (int)(s0 - ga4 * 625);                                // in [-4, 624]
+      for (int j = threadIdx.x; j < kTxFusedIn; j += kTxFusedThreads) {
+        const int w = w0 + j;
+        cf x = mk(0.0F, 0.0F);
+        if (w >= 0 && s0 + j < nsamples) {
+          const int q4 = w / 625;
+          int sl, t;
+          tx_slot_of(w - q4 * 625, &sl, &t);
+          const int lb = q4 * 4 + sl;                                      // burst index within the staged bits
+          x = tx_burst_sample(q, sb + lb * 148, t);
+          if (scale) x = cmul(x, mk(scale[a * nslots + ga4 * 4 + lb], 0.0F));   // addRadioVector's scaleVector, Transceiver.cpp:108
+        }
+        xs[j] = x;
+      }
     }
     __syncthreads();
     // ---- this warp's part of the 96 phases of this lane's period
@@ -502,8 +516,8 @@ void launch_tx_fused(const DevTables *T, const uint8_t *bits, const float *scale
   if (nperiods <= 0 || nstreams <= 0) return;
   const long long nsteps = (nperiods + kTxFusedPeriods - 1) / kTxFusedPeriods * nstreams;
   const unsigned grid = (unsigned)(nsteps < g_num_sms ? nsteps : g_num_sms);
-  k_tx_fused<<<grid, kTxFusedThreads, kTxFusedSmem, st>>>(T, bits, scale, nsamples, nperiods, nstreams,
-                                                          reinterpret_cast<short2 *>(out));
+  k_tx_fused<true><<<grid, kTxFusedThreads, kTxFusedSmem, st>>>(T, bits, scale, nsamples, nperiods, nstreams,
+                                                                reinterpret_cast<short2 *>(out));
 }
 
 int configure_resamplers() {
@@ -517,7 +531,8 @@ int configure_resamplers() {
       g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
     if (!g_encode_tiled) return -1;
   }
-  if (cudaFuncSetAttribute(k_tx_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTxFusedSmem) != cudaSuccess) return -2;
+  if (cudaFuncSetAttribute(k_tx_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTxFusedSmem) != cudaSuccess) return -2;
+  if (cudaFuncSetAttribute(k_tx_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTxFusedSmem) != cudaSuccess) return -2;
   cudaError_t e = cudaFuncSetAttribute(k_resample_rx_v3<false, kRxV3TilesF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)RxV3<false, kRxV3TilesF32>::kSmem);
   if (e != cudaSuccess) return (int)e;
@@ -542,9 +557,22 @@ __global__ void __launch_bounds__(256) k_resample_tx(const DevTables *__restrict
           tx_quantise(resample_at<kTxP, kTxQ, kTxTaps, kTxPoly, kTxP + 1>(x, kTxIn, &hp[0][0], kTxDrop, m));
   }
 }
+#ifndef BTS_TX_TUNED_DEFAULT
+#define BTS_TX_TUNED_DEFAULT false      // flipped once the GPU parity run of the loaded-tile variant is in (profiles/README.md r3e)
+#endif
 void launch_resample_tx(const DevTables *T, const cf *in, int has_history, long long nchunks, int16_t *out,
                         cudaStream_t st) {
   if (nchunks <= 0) return;
+  static const bool tuned = [] { const char *e = getenv("BTSDSP_TX_TUNED"); return e ? atoi(e) != 0 : BTS_TX_TUNED_DEFAULT; }();
+  if (tuned && ((reinterpret_cast<uintptr_t>(in) & 7) | (reinterpret_cast<uintptr_t>(out) & 3)) == 0) {
+    // the tuned shape (persistent CTA per SM, lane = period, two-instruction taps): k_tx_fused with a loaded input tile
+    const long long nsamples = nchunks * 585, nperiods = nchunks * 9;
+    const long long nsteps = (nperiods + kTxFusedPeriods - 1) / kTxFusedPeriods;
+    const unsigned grid = (unsigned)(nsteps < g_num_sms ? nsteps : g_num_sms);
+    k_tx_fused<false><<<grid, kTxFusedThreads, kTxFusedSmem, st>>>(T, nullptr, nullptr, nsamples, nperiods, 1, reinterpret_cast<short2 *>(out),
+                                                                 in, has_history);
+    return;
+  }
   const unsigned grid = (unsigned)(nchunks < 148 * 32 ? nchunks : 148 * 32);
   k_resample_tx<<<grid, 256, 0, st>>>(T, in, has_history, nchunks, out);
 }

@@ -589,3 +589,27 @@ def test_cuda_graph_replay_of_small_batches(dsp, oracle_best):
                              torch.zeros(big * 148, device=dev), 148, stream=st)
     dsp.graph_destroy(g)
     st.synchronize()
+
+
+@pytest.mark.gpu
+def test_resample_tx_with_history_and_unaligned(dsp):
+    """btsdsp_resample_tx_dev (the tuned kernel with a loaded input tile): a later part of a stream, seeing the samples
+    before it, equals the same chunks computed from the start; an odd output address takes the plain kernel, same result"""
+    import torch
+    g = golden("stream_sps1.npz")
+    dev = torch.device("cuda:0")
+    x = torch.from_numpy(g["stream_head"].view(np.float32).copy()).to(dev)
+    want = g["iq_head"]
+    full = torch.zeros(20 * 864 * 2, dtype=torch.int16, device=dev)
+    dsp.resample_tx_dev(x, 20, full)
+    same(full.cpu().numpy().reshape(-1, 2), want, "TX resample from the stream start")
+    part = torch.zeros(15 * 864 * 2, dtype=torch.int16, device=dev)
+    dsp.resample_tx_dev(x[5 * 585 * 2:], 15, part, has_history=True)
+    same(part.cpu().numpy().reshape(-1, 2), want[5 * 864:], "TX resample, chunks 5..19 with history")
+    cold = torch.zeros(15 * 864 * 2, dtype=torch.int16, device=dev)
+    dsp.resample_tx_dev(x[5 * 585 * 2:], 15, cold, has_history=False)
+    assert not np.array_equal(cold.cpu().numpy().reshape(-1, 2)[:8], want[5 * 864:5 * 864 + 8])   # zeros before the part
+    same(cold.cpu().numpy().reshape(-1, 2)[864:], want[6 * 864:], "chunks after the first no longer see the cut")
+    odd = torch.zeros(20 * 864 * 2 + 1, dtype=torch.int16, device=dev)
+    dsp.resample_tx_dev(x, 20, odd[1:])                                   # 2-byte aligned output: the fallback kernel
+    same(odd[1:].cpu().numpy().reshape(-1, 2), want, "TX resample, unaligned output")
