@@ -177,7 +177,7 @@ int btsdsp_resample_rx_i16_streams_dev(btsdsp_ctx *ctx, const int16_t *iq, long 
                                        int has_history, long long nchunks, btsdsp_cf32 *out, long long out_pitch,
                                        void *stream);
 /* TX resampler (radioInterface.cpp:123-168 + USRPifyVector :74-89): nchunks chunks of 585 samples ->
- * 864 int16 {I,Q} pairs each, scaled by 13500 and truncated like the reference's (short) cast. */
+ * 864 int16 {I,Q} pairs each, scaled by 13500 and truncated like the reference's (short) cast.  out must be 4-byte aligned. */
 int btsdsp_resample_tx_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *in, int has_history, long long nchunks, int16_t *out,
                            void *stream);
 /* Normal bursts, fused energy gate -> analyzeTrafficBurst(request channel) -> designDFE(Nf 7) ->

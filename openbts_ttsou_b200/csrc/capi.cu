@@ -778,6 +778,7 @@ int btsdsp_demod_normal_u8_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *bursts, long 
 int btsdsp_resample_tx_dev(btsdsp_ctx *ctx, const btsdsp_cf32 *in, int has_history, long long nchunks, int16_t *out,
                            void *stream) {
   ARG(ctx && in && out && nchunks >= 0);
+  ARG((reinterpret_cast<uintptr_t>(out) & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0);   // {I,Q} pairs are stored as 4-byte units
   DeviceGuard g(ctx->device);
   launch_resample_tx(ctx->T, (const cf *)in, has_history, nchunks, out, (cudaStream_t)stream);
   LAUNCHED("resample_tx", nchunks > 0);

@@ -361,11 +361,10 @@ template <int WARPS> constexpr size_t equalize_smem() { return WARPS * kEqTileBy
 // runs on the slots `kind` marks as TSC, and the results go to a DetRec instead of into a DFE design.
 // SPLIT = the stateless path with designDFE left to a second launch (k_design_eqp): this kernel stops after the analysis
 // and parks {flag, amp, TOA, offset, channel} in a DetRec.
-#ifndef BTS_DET_MINWARPS
-#define BTS_DET_MINWARPS 0            // > 0: ask ptxas for that many resident warps per SM (caps the registers)
-#endif
+// (Asking ptxas for 18-19 resident warps per SM -- 113 / 107 registers -- measured 0.50 ms against 0.457: profiles/README.md r3e.
+// No min-blocks argument here: even "1" changes the register allocation and costs 40 %.)
 template <int WARPS, bool POLICY = false, bool SPLIT = false>
-__global__ void __launch_bounds__(WARPS * 32, BTS_DET_MINWARPS ? BTS_DET_MINWARPS / WARPS : 1) k_detect_design(const DevTables *__restrict__ T, BurstSrc src,
+__global__ void __launch_bounds__(WARPS * 32) k_detect_design(const DevTables *__restrict__ T, BurstSrc src,
                                                               const uint8_t *__restrict__ tsc, long long n,
                                                               float detect_thr, float gate_thr, float snr_thr,
                                                               NormalOut out, EqParams *__restrict__ eqp,
@@ -614,6 +613,9 @@ struct __align__(16) EqSrc {
   float iax, iay;       // 1/amplitude
   int pad0, pad1;
 };
+#ifndef BTS_SLICER_RING_DEFAULT
+#define BTS_SLICER_RING_DEFAULT false   // flipped once the GPU parity run of k_slicer_ring is in (profiles/README.md r3e)
+#endif
 #ifndef BTS_EQ_PROLOGUE
 #define BTS_EQ_PROLOGUE 1
 #endif
@@ -1077,6 +1079,99 @@ __global__ void __launch_bounds__(32) k_slicer_fast(const DevTables *__restrict_
   flush();
 }
 
+// demodulateBurst (:1056-1097) over the same ring tile and software pipeline as k_equalize_ring: each lane walks its OWN
+// output index m (the tile is indexed on the lane's timeline, so lanes with TOAs anywhere in the slot read the same slots),
+// soft[m] = slice(Re(revrot[m] * F[m - io])), F zeroed outside the burst (delayVector's zero fill slices to 0.5).  Blocks
+// start at m = -2 (mod 4 == 2) so that the filter block index m - 6 is a multiple of four, as the ring's groups require;
+// a lane's four outputs leave as two 8-byte stores.  Replaces k_slicer_fast's rolling tile + parked-output flush.
+__global__ void __launch_bounds__(32) k_slicer_ring(const DevTables *__restrict__ T, BurstSrc src, long long n,
+                                                    const EqParams *__restrict__ eqp, float *__restrict__ soft, int soft_pitch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x;
+  cf *A = reinterpret_cast<cf *>(smem_raw);
+  EqSrc *tab = reinterpret_cast<EqSrc *>(A + kEqRing * kTileStride);
+  const long long w0 = (long long)blockIdx.x * 32;
+  if (w0 >= n) return;
+  const int nv = (int)((n - w0) < 32 ? (n - w0) : 32);
+  const long long i = w0 + lane;
+  long long start = 0;
+  int len = 0;
+  bool ok = false;
+  cf ia = mk(0.0F, 0.0F);
+  float toa = 0.0F;
+  if (lane < nv) {
+    burst_loc(src, i, &start, &len);
+    if (len > 157) len = 157;
+    const float4 q0 = __ldg(reinterpret_cast<const float4 *>(eqp + i));
+    ok = q0.w != 0.0F; ia = mk(q0.x, q0.y); toa = q0.z;
+  }
+  float *row = soft + i * (long long)soft_pitch;
+  if (!ok && lane < nv) for (int m = 0; m < soft_pitch; m++) row[m] = 0.0F;
+  const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+  if (okmask == 0) return;
+  const int io = ok ? (int)floorf(-toa) : 0;
+  {
+    EqSrc e;
+    e.p = src.base + start - io;
+    e.lo = ok ? io : 0;
+    e.hi = ok ? len + io : 0;
+    e.iax = ia.x; e.iay = ia.y; e.pad0 = e.pad1 = 0;
+    tab[lane] = e;
+  }
+  __syncwarp();
+  constexpr int kM0 = -2;                                   // first block; its filter block kM0 - 6 reads mu = kM0-10 .. kM0+13
+  cf pend[4], pro[5][4];
+#pragma unroll
+  for (int g = 0; g < 5; g++) eq_ring_fetch(tab, lane, kM0 - 10 + 4 * g, pro[g]);
+  eq_ring_fetch(tab, lane, kM0 + 10, pend);
+  EqLane<kTileStride> f;
+  {
+    cf zw[7], zb[5];
+#pragma unroll
+    for (int k = 0; k < 7; k++) zw[k] = mk(0.0F, 0.0F);
+#pragma unroll
+    for (int k = 0; k < 5; k++) zb[k] = mk(0.0F, 0.0F);
+    if (ok) f.init(Grid{&T->sinc_grid[0][0], 24}, T, View<kTileStride>{A + lane}, len, toa, zw, zb);
+    else f.io = 0;
+  }
+  const int nmax = __reduce_max_sync(0xffffffffu, ok ? len : 0);
+  const int mend = nmax < soft_pitch ? nmax : soft_pitch;
+#pragma unroll
+  for (int g = 0; g < 5; g++) eq_ring_store(A, tab, lane, kM0 - 10 + 4 * g, pro[g]);
+#pragma unroll 1
+  for (int m0 = kM0; m0 < mend; m0 += 4) {
+    eq_ring_store(A, tab, lane, m0 + 10, pend);
+    __syncwarp();
+    eq_ring_fetch(tab, lane, m0 + 14, pend);
+    if (ok) {
+      cf d[4];
+      f.template newF4_ring<true>(m0 - 6, d);
+      float s4[4];
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int m = m0 + r;
+        const cf rr = T->revrot[m < 0 ? 0 : (m > 156 ? 156 : m)];
+        s4[r] = soft_slice(BTS_SUB(BTS_MUL(rr.x, d[r].x), BTS_MUL(rr.y, d[r].y)));     // Re(revrot[m] * D[m]) :232-264
+      }
+      if (m0 >= 0 && m0 + 3 < len && m0 + 3 < soft_pitch && ((reinterpret_cast<uintptr_t>(row + m0) & 7) == 0)) {
+        *reinterpret_cast<float2 *>(row + m0) = make_float2(s4[0], s4[1]);
+        *reinterpret_cast<float2 *>(row + m0 + 2) = make_float2(s4[2], s4[3]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; r++) if (m0 + r >= 0 && m0 + r < len && m0 + r < soft_pitch) row[m0 + r] = s4[r];
+      }
+    }
+  }
+  if (ok) for (int m = len; m < soft_pitch; m++) row[m] = 0.0F;
+}
+static bool g_slicer_ring = BTS_SLICER_RING_DEFAULT;
+void launch_slicer(const DevTables *T, BurstSrc src, long long n, const EqParams *eqp, float *soft, int soft_pitch, cudaStream_t st) {
+  if (n <= 0) return;
+  const unsigned grid = (unsigned)((n + 31) / 32);
+  if (g_slicer_ring) k_slicer_ring<<<grid, 32, kEqRingBytes, st>>>(T, src, n, eqp, soft, soft_pitch);
+  else k_slicer_fast<<<grid, 32, kEqTileBytes, st>>>(T, src, n, eqp, soft, soft_pitch);
+}
+
 void upload_rach_taps(const DevTables *hostT) {
   cf h[41];
   for (int k = 0; k < 41; k++) h[k] = mk(hostT->rach_seq[40 - k].x, -hostT->rach_seq[40 - k].y);
@@ -1137,7 +1232,7 @@ int launch_rach(const DevTables *T, BurstSrc src, long long n, float detect_thr,
     k_rach_detect<<<grid, 32, kRachRollBytes, st>>>(T, src, n, detect_thr, out, (demod && out.soft) ? eqp : nullptr,
                                                     reinterpret_cast<cf *>(reinterpret_cast<char *>(eq_scratch) + (((size_t)n * sizeof(EqParams) + 127) & ~(size_t)127)));
     if (!(demod && out.soft)) return 1;
-    k_slicer_fast<<<grid, 32, kEqTileBytes, st>>>(T, src, n, eqp, out.soft, out.soft_pitch);
+    launch_slicer(T, src, n, eqp, out.soft, out.soft_pitch, st);
     return 2;
   }
   k_rach<false><<<grid, 32, 0, st>>>(T, src, n, detect_thr, demod, out, scratch);
@@ -1391,6 +1486,9 @@ int configure_kernels() {
   if (configure_detect_52m() != 0) return -52;
   if (const char *e = getenv("BTSDSP_EQ_RING")) g_eq_ring = atoi(e) != 0;
   if (const char *e = getenv("BTSDSP_DET_SPLIT")) g_det_split = atoi(e) != 0;
+  if (const char *e = getenv("BTSDSP_SLICER_RING")) g_slicer_ring = atoi(e) != 0;
+  e = cudaFuncSetAttribute(k_slicer_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEqRingBytes);
+  if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_detect_design<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<1>());
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_detect_design<kDetWarps, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<kDetWarps>());

@@ -242,7 +242,7 @@ int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, i
     // pass 3 without the equaliser: one demodulateBurst pass over the whole batch (accepted normal AND access bursts),
     // then the datagrams from each burst's own soft row
     k_trx_slice_params<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, s.det, s.act, rach_slot, s.rach_amp, s.rach_toa, s.eqp);
-    k_slicer_fast<<<(unsigned)nwarps, 32, kEqTileBytes, stream>>>(T, src, n, s.eqp, s.rach_soft, kTrxRachSoftPitch);
+    launch_slicer(T, src, n, s.eqp, s.rach_soft, kTrxRachSoftPitch, stream);
     k_trx_datagram<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(T, n, narfcn, fn0, s.det, s.act, rach_slot, s.rach_amp, s.rach_toa,
                                                                         s.rach_soft, kTrxRachSoftPitch, valid, dgram, dgram_pitch, s.rach_soft);
     return launches + 4;
@@ -256,7 +256,7 @@ int launch_trx_pull(const DevTables *T, TrxState *st, int narfcn, int nframes, i
   launches += 4;
   if (nr > 0) {
     k_trx_rach_veto<<<(unsigned)((nr + 127) / 128), 128, 0, rs>>>(nr, rach_idx, s.act, s.eqp_r);
-    k_slicer_fast<<<(unsigned)((nr + 31) / 32), 32, kEqTileBytes, rs>>>(T, rsrc, nr, s.eqp_r, s.rach_soft, kTrxRachSoftPitch);
+    launch_slicer(T, rsrc, nr, s.eqp_r, s.rach_soft, kTrxRachSoftPitch, rs);
     if (fork) { cudaEventRecord(ev[3], rs); cudaStreamWaitEvent(stream, ev[3], 0); }      // the datagrams need the RACH soft bits
     launches += 2;
   }

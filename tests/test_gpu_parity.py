@@ -594,7 +594,7 @@ def test_cuda_graph_replay_of_small_batches(dsp, oracle_best):
 @pytest.mark.gpu
 def test_resample_tx_with_history_and_unaligned(dsp):
     """btsdsp_resample_tx_dev (the tuned kernel with a loaded input tile): a later part of a stream, seeing the samples
-    before it, equals the same chunks computed from the start; an odd output address takes the plain kernel, same result"""
+    before it, equals the same chunks computed from the start; an output that is not 4-byte aligned is refused"""
     import torch
     g = golden("stream_sps1.npz")
     dev = torch.device("cuda:0")
@@ -611,5 +611,5 @@ def test_resample_tx_with_history_and_unaligned(dsp):
     assert not np.array_equal(cold.cpu().numpy().reshape(-1, 2)[:8], want[5 * 864:5 * 864 + 8])   # zeros before the part
     same(cold.cpu().numpy().reshape(-1, 2)[864:], want[6 * 864:], "chunks after the first no longer see the cut")
     odd = torch.zeros(20 * 864 * 2 + 1, dtype=torch.int16, device=dev)
-    dsp.resample_tx_dev(x, 20, odd[1:])                                   # 2-byte aligned output: the fallback kernel
-    same(odd[1:].cpu().numpy().reshape(-1, 2), want, "TX resample, unaligned output")
+    with pytest.raises(Exception):                                        # {I,Q} pairs are written as 4-byte units
+        dsp.resample_tx_dev(x, 20, odd[1:])
