@@ -391,6 +391,44 @@ void emu_rach(const float *bursts, long long pitch, const int *lens, long long f
       for (int m = 0; m < soft_pitch; m++) row[m] = m < lenv[lane] ? 0.5F : 0.0F;
     }
     if (!any) continue;
+    if (g_eq_ring) {
+      // ---- k_slicer_ring: the ring tile on each lane's output timeline, blocks m0 = -2, 2, 6, ...; dead rows poisoned
+      std::vector<cf> Rg(kEqRing * kTileStride);
+      for (auto &x : Rg) x = mk(1e30F, -1e30F);
+      auto store_group = [&](int mu0) {
+        for (int j = 0; j < 32; j++)
+          for (int qq = 0; qq < 4; qq++) {
+            const int mu = mu0 + qq;
+            cf v = mk(0.0F, 0.0F), ia = mk(0.0F, 0.0F);
+            if (j < nv && okv[j]) {
+              const int r = mu - sl[j].f.io;
+              ia = iav[j];
+              if (r >= 0 && r < lenv[j]) v = ((const cf *)bursts + startv[j])[r];
+            }
+            Rg[(mu & (kEqRing - 1)) * kTileStride + j] = cmul(v, ia);
+          }
+      };
+      for (int lane = 0; lane < nv; lane++) if (okv[lane]) sl[lane].f.a = View<kTileStride>{Rg.data() + lane};
+      const int kM0 = -2;
+      for (int g = 0; g < 5; g++) store_group(kM0 - 10 + 4 * g);
+      for (int m0 = kM0; m0 < nm; m0 += 4) {
+        store_group(m0 + 10);
+        for (int j = 0; j < 32; j++) for (int qq = 0; qq < 4; qq++) Rg[((m0 - 14 + qq) & (kEqRing - 1)) * kTileStride + j] = mk(1e30F, -1e30F);
+        for (int lane = 0; lane < nv; lane++) {
+          if (!okv[lane]) continue;
+          cf d[4];
+          sl[lane].f.template newF4_ring<true>(m0 - 6, d);
+          float *row = soft + (w0 + lane) * soft_pitch;
+          for (int r = 0; r < 4; r++) {
+            const int m = m0 + r;
+            if (m < 0 || m >= lenv[lane] || m >= soft_pitch) continue;
+            const cf rr = T->revrot[m > 156 ? 156 : m];
+            row[m] = soft_slice(BTS_SUB(BTS_MUL(rr.x, d[r].x), BTS_MUL(rr.y, d[r].y)));
+          }
+        }
+      }
+      continue;
+    }
     int base = 0;
     bool staged = false;
     for (int x0 = 0; x0 < nm; x0 += 4) {

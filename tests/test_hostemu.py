@@ -125,7 +125,7 @@ def test_demod_normal_kernel_logic_edge_cases(emu, oracle_port, eq_tile):
         assert_same(a[k], b[k], k)
 
 
-def test_rach_kernel_logic(emu, oracle_port):
+def test_rach_kernel_logic(emu, oracle_port, eq_tile):
     g = golden("rach_sps1.npz")
     for tiles in (True, False):
         r = emu.rx_rach_batch(g["bursts"], g["lens"], tiles=tiles)
