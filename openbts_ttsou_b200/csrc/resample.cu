@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(256) k_resample_tx(const DevTables *__restrict
   }
 }
 #ifndef BTS_TX_TUNED_DEFAULT
-#define BTS_TX_TUNED_DEFAULT false      // flipped once the GPU parity run of the loaded-tile variant is in (profiles/README.md r3e)
+#define BTS_TX_TUNED_DEFAULT true       // GPU parity run: all tests pass with it, 0.229 ms against 0.306 ms per 64 000 chunks (profiles/README.md r3e)
 #endif
 void launch_resample_tx(const DevTables *T, const cf *in, int has_history, long long nchunks, int16_t *out,
                         cudaStream_t st) {

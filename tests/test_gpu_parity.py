@@ -613,3 +613,30 @@ def test_resample_tx_with_history_and_unaligned(dsp):
     odd = torch.zeros(20 * 864 * 2 + 1, dtype=torch.int16, device=dev)
     with pytest.raises(Exception):                                        # {I,Q} pairs are written as 4-byte units
         dsp.resample_tx_dev(x, 20, odd[1:])
+
+
+@pytest.mark.gpu
+def test_copy_only_mode_moves_bytes_and_launches_nothing(dsp):
+    """btsdsp_set_copy_only (bench.py's copy roofline leg): the host pipeline issues its copies and no kernel, results stay
+    untouched; switching it off restores the normal call"""
+    g = golden("stream_sps1.npz")
+    raw = g["raw_head"]
+    nch = raw.size // 864
+    nb = (nch * 585 // 625) * 4
+    tsc = np.zeros(nb, np.uint8)
+
+    def run():
+        f, a, t = np.full(nb, -5, np.int32), np.zeros(nb, np.complex64), np.zeros(nb, np.float32)
+        s = np.full((nb, 148), -1.0, np.float32)
+        dsp.rx_stream_host(raw, nch, tsc, nb, f, a, t, s, 148)
+        return f, s
+    f0, s0 = run()
+    assert (f0 >= 0).all() and (s0 >= 0).all()
+    dsp.set_copy_only(True)
+    l0 = dsp.launch_count
+    f1, s1 = run()
+    assert dsp.launch_count == l0                    # not one kernel
+    dsp.set_copy_only(False)
+    f2, s2 = run()
+    assert dsp.launch_count > l0
+    same(f2, f0, "flags after copy-only mode"); same(s2, s0, "soft bits after copy-only mode")
