@@ -1150,7 +1150,12 @@ __global__ void __launch_bounds__(32) k_slicer_ring(const DevTables *__restrict_
 #pragma unroll
       for (int r = 0; r < 4; r++) {
         const int m = m0 + r;
+#if BTS_EQ_CROT
+        const float4 q = c_eq_rr[m < 0 ? 0 : (m > 156 ? 156 : m)];
+        const cf rr = mk(q.z, q.w);
+#else
         const cf rr = T->revrot[m < 0 ? 0 : (m > 156 ? 156 : m)];
+#endif
         s4[r] = soft_slice(BTS_SUB(BTS_MUL(rr.x, d[r].x), BTS_MUL(rr.y, d[r].y)));     // Re(revrot[m] * D[m]) :232-264
       }
       if (m0 >= 0 && m0 + 3 < len && m0 + 3 < soft_pitch && ((reinterpret_cast<uintptr_t>(row + m0) & 7) == 0)) {
@@ -1173,6 +1178,16 @@ void launch_slicer(const DevTables *T, BurstSrc src, long long n, const EqParams
 }
 
 void upload_rach_taps(const DevTables *hostT) {
+#if BTS_EQ_CROT
+  {
+    float4 rr[160];
+    for (int m = 0; m < 160; m++) {
+      const int k = m < 157 ? m : 156;
+      rr[m] = make_float4(hostT->rot[k].x, hostT->rot[k].y, hostT->revrot[k].x, hostT->revrot[k].y);
+    }
+    cudaMemcpyToSymbol(c_eq_rr, rr, sizeof rr);
+  }
+#endif
   cf h[41];
   for (int k = 0; k < 41; k++) h[k] = mk(hostT->rach_seq[40 - k].x, -hostT->rach_seq[40 - k].y);
   cudaMemcpyToSymbol(c_rach_taps, h, sizeof h);
