@@ -23,9 +23,21 @@ constexpr int kGridPitch = 21;      // floats per sinc-grid row in the compact (
 struct Grid {
   const float *p;
   int pitch;
+  bool vec = false;     // rows are 16-byte aligned at pitch 24 and may be fetched as six 16-byte loads (the search kernels, which
+                        // fetch ten rows per burst; the equaliser's single row per burst measured better as scalar loads)
 };
 
 BTS_HD void load_grid_row(Grid grid, int j, float s[21]) {
+#ifdef __CUDA_ARCH__
+  if (grid.vec) {                               // DevTables::sinc_grid: 96-byte rows, 16-byte aligned -> six vector loads
+    const float4 *p = reinterpret_cast<const float4 *>(grid.p + j * 24);
+    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4), f = __ldg(p + 5);
+    s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+    s[8] = c.x; s[9] = c.y; s[10] = c.z; s[11] = c.w; s[12] = d.x; s[13] = d.y; s[14] = d.z; s[15] = d.w;
+    s[16] = e.x; s[17] = e.y; s[18] = e.z; s[19] = e.w; s[20] = f.x;
+    return;
+  }
+#endif
 #pragma unroll
   for (int t = 0; t < 21; t++) s[t] = grid.p[j * grid.pitch + t];
 }

@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_detect_design(const DevTables *_
   if (lane >= nv) return;
 
   const View<kTileStride> a{A + lane};
-  const Grid g = detect_grid_shared<WARPS>() ? Grid{grid, kGridPitch} : Grid{&T->sinc_grid[0][0], 24};
+  const Grid g = detect_grid_shared<WARPS>() ? Grid{grid, kGridPitch} : Grid{&T->sinc_grid[0][0], 24, true};
   bool ok = false;
   cf amp = mk(0.0F, 0.0F), ia = mk(0.0F, 0.0F), chan[6], w[7], fb[5];
   float toa = 0.0F, off = 0.0F;
@@ -973,7 +973,7 @@ __global__ void __launch_bounds__(32) k_rach_detect(const DevTables *__restrict_
   }
   cf amp = mk(0.0F, 0.0F);
   float toa = 0.0F;
-  const bool ok = rach_finish<kTileStride>(Grid{&T->sinc_grid[0][0], 24}, T, View<kTileStride>{A + lane}, row, len, imax,
+  const bool ok = rach_finish<kTileStride>(Grid{&T->sinc_grid[0][0], 24, true}, T, View<kTileStride>{A + lane}, row, len, imax,
                                            detect_thr, &amp, &toa);
   if (out.flag) out.flag[i] = ok ? 1 : 0;
   if (out.amp) out.amp[i] = amp;

@@ -39,7 +39,7 @@ struct DevTables {
   // sinc(pi*(m - j/512)) for m = -10..10 (index m+10), j = 0..511: every fractional delay the path
   // itself produces lies on the 1/512 grid (peakDetect's early-late search), so these 21-tap rows
   // are the only interpolators the batched kernels ever need.  Row pitch 24 floats (96 B).
-  float sinc_grid[kSincGrid][24];
+  alignas(16) float sinc_grid[kSincGrid][24];       // 16-byte aligned rows: the kernels fetch a row as six 16-byte loads
   // exp(-n), n = 0..1023, as the host's libm rounds it: the adaptive energy threshold of the caller policy
   // (Transceiver.cpp:355) is a double that must evolve exactly as on the CPU
   double exp_neg[1024];
