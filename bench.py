@@ -405,6 +405,54 @@ def leg_config5(torch, dist, dsp, dev, stream, rank, world, quick):
     return out
 
 
+def leg_other(torch, dsp, dev, stream):
+    """the entry points either side of the path, device-resident (N = 1): fused TX chain, the caller-policy pull with RX
+    datagrams, and the L1 block decoders (XCCH, TCH/FACCH) on the pull's soft bytes"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import synth
+    out = {}
+    blocks = 281                                   # 263 016 bursts >= 1024 ARFCN x 8 TN x 32 frames
+    nb, nch = blocks * BLOCK_BURSTS, blocks * BLOCK_CHUNKS
+    g = torch.Generator(device=dev)
+    g.manual_seed(77)
+    bits = torch.randint(0, 2, (nb, 148), generator=g, device=dev, dtype=torch.uint8)
+    bits[:, :3] = 0
+    bits[:, 145:] = 0
+    bits[:, 61:87] = torch.from_numpy(synth.bits_of(synth.TSC[0]).copy()).to(dev)
+    iq = torch.empty(nch * 864 * 2, dtype=torch.int16, device=dev)
+    ms = timeit(torch, stream, lambda: dsp.tx_stream_dev(bits, nb, iq, stream=stream))
+    out["tx_chain_bits_to_int16"] = {"bursts": nb, "ms": ms, "bursts_per_s": nb / ms * 1e3}
+    iq_rx = (iq.to(torch.float32) + 955.0 * torch.randn(iq.numel(), generator=g, device=dev)).round_().clamp_(-32768, 32767).to(torch.int16)
+    res = torch.empty(nch * 585 * 2, dtype=torch.float32, device=dev)
+    dsp.resample_rx_i16_dev(iq_rx, nch, res, stream=stream)
+    A, F = 1024, 32
+    npol = A * 8 * F
+    ct = np.ones((A, 8), np.uint8)
+    ct[:, 0] = 5                                   # TN 0: combination V (access bursts on most frames)
+    trx = dsp.trx_create(np.zeros(A, np.uint8), ct, 0)
+    pv = torch.zeros(npol, dtype=torch.int32, device=dev)
+    pd = torch.zeros(npol * 160, dtype=torch.uint8, device=dev)
+    fnc = [0]
+
+    def pull():
+        dsp.trx_pull_streams_dev(trx, res, F * 1250, F, fnc[0], pv, pd, 160, stream=stream)
+        fnc[0] += F
+    ms = timeit(torch, stream, pull)
+    out["policy_pull_1024_arfcn_x_32_frames"] = {"bursts": npol, "ms": ms, "bursts_per_s": npol / ms * 1e3, "valid": float(pv.float().mean())}
+    dsp.trx_destroy(trx)
+    nfr = npol // 4
+    fu = torch.zeros(nfr * 228, dtype=torch.uint8, device=dev)
+    fok = torch.zeros(nfr, dtype=torch.int32, device=dev)
+    ms = timeit(torch, stream, lambda: dsp.xcch_decode_dev(pd[8:], 160, nfr, fu, fok, stream=stream))
+    out["xcch_decode"] = {"frames": nfr, "ms": ms, "bursts_per_s": npol / ms * 1e3}
+    nblk = npol // 4 - 1
+    td = torch.zeros(nblk * 260, dtype=torch.uint8, device=dev)
+    ti = torch.zeros((3, nblk), dtype=torch.int32, device=dev)
+    ms = timeit(torch, stream, lambda: dsp.tch_decode_dev(pd[8:], 160, nblk, td, ti[0], ti[1], fu, ti[2], stream=stream))
+    out["tch_facch_decode"] = {"blocks": nblk, "ms": ms, "bursts_per_s": 4 * nblk / ms * 1e3, "stolen": float(ti[1].float().mean())}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -610,12 +658,21 @@ def main():
         del raw, res, soft
         torch.cuda.empty_cache()
         secondary = {}
+
+        def leg(name, fn, *a):
+            """a secondary leg must never cost the headline line: a failure is reported in place of its numbers"""
+            try:
+                secondary[name] = fn(*a)
+            except Exception as e:       # noqa: BLE001
+                if world > 1:
+                    raise                # a rank that skips a collective would hang the others: fail loudly instead
+                secondary[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+            torch.cuda.empty_cache()
         if world == 1:
-            secondary["config3_rach_sweep"] = leg_config3(torch, dsp, dev, stream, peak, fp32_peak, cores, args.quick)
-            torch.cuda.empty_cache()
-            secondary["config4_wideband_batch"] = leg_config4(torch, dsp, dev, stream, peak, fp32_peak, cores, args.quick)
-            torch.cuda.empty_cache()
-        secondary["config5_arfcn_sharded_tx_rx"] = leg_config5(torch, dist, dsp, dev, stream, rank, world, args.quick)
+            leg("config3_rach_sweep", leg_config3, torch, dsp, dev, stream, peak, fp32_peak, cores, args.quick)
+            leg("config4_wideband_batch", leg_config4, torch, dsp, dev, stream, peak, fp32_peak, cores, args.quick)
+            leg("other_entry_points", leg_other, torch, dsp, dev, stream)
+        leg("config5_arfcn_sharded_tx_rx", leg_config5, torch, dist, dsp, dev, stream, rank, world, args.quick)
 
     if rank == 0:
         k_res = kernel_entry("k_resample_rx_v3", ms_res, nch * RESAMPLE_BYTES_PER_CHUNK, nch * RESAMPLE_OPS_PER_CHUNK, peak,
