@@ -1381,12 +1381,6 @@ int analyze_52m_scratch_stride(unsigned max_toa, int sps) {
 // temporary live in the rows behind it -- (windowLen + 2*corrLen) x 33 x 8 B per warp: 10.6 KB at maxTOA <= 3, 24 KB at 12,
 // 100 KB at the limit of 60.  POLICY = pass 1 of the caller-policy pipeline for this variant: the stride-4 energy of the
 // slot is measured (Transceiver52M/sigProcLib.cpp:944-963), the analysis runs on the TSC slots, results go to a DetRec.
-struct Geo52 { int startIx, windowLen, corrLen; };
-__host__ __device__ inline Geo52 geo_52m(unsigned max_toa) {
-  if (max_toa < 3u) max_toa = 3;
-  unsigned span = max_toa < 5u ? 5u : max_toa;
-  return Geo52{66 - (int)span, 16 + 2 * (int)span, 2 * (int)max_toa + 1};
-}
 size_t detect_52m_smem(unsigned max_toa) {
   const Geo52 g = geo_52m(max_toa);
   return (size_t)(g.windowLen + 2 * g.corrLen + 1) * kTileStride * sizeof(cf);

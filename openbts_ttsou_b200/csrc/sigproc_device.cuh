@@ -331,6 +331,15 @@ BTS_HD bool analyze_traffic_52m(const DevTables *__restrict__ T, View<S> burst, 
   return detected;
 }
 
+// what analyze_traffic_52m touches at sps == 1: burst rows [startIx, startIx + windowLen) and corrLen lags (the tile-staged
+// kernel k_detect_52m stages exactly these; tests/hostemu poisons everything else)
+struct Geo52 { int startIx, windowLen, corrLen; };
+BTS_HD Geo52 geo_52m(unsigned max_toa) {
+  if (max_toa < 3u) max_toa = 3;
+  unsigned span = max_toa < 5u ? 5u : max_toa;
+  return Geo52{66 - (int)span, 16 + 2 * (int)span, 2 * (int)max_toa + 1};
+}
+
 // detectRACHBurst :860-914.  corr = scratch of n samples.
 template <int S, bool GRID>
 BTS_HD bool detect_rach(const DevTables *__restrict__ T, View<S> burst, int n, float thr, int sps, View<S> corr,

@@ -110,6 +110,15 @@ class Emu:
                                       P(amp), P(toa), P(chan), P(off))
         return bool(ok), amp[0], toa[0], chan, off[0]
 
+    def analyze_52m_tiled(self, burst, tsc, thr=3.0, max_toa=3, request=True):
+        """the same through k_detect_52m's tile layout (only the search window staged, everything else poisoned); sps 1"""
+        burst = np.ascontiguousarray(burst, np.complex64)
+        amp = np.zeros(1, np.complex64); toa = np.zeros(1, np.float32)
+        chan = np.zeros(6, np.complex64); off = np.zeros(1, np.float32)
+        ok = self.lib.emu_analyze_52m_tiled(P(burst), c_i(burst.size), c_i(tsc), c_f(thr), ctypes.c_uint(max_toa), c_i(int(request)),
+                                            P(amp), P(toa), P(chan), P(off))
+        return bool(ok), amp[0], toa[0], chan, off[0]
+
     def energy_detect_52m(self, v, win, thr):
         v = np.ascontiguousarray(v, np.complex64)
         avg = np.zeros(1, np.float32)

@@ -764,6 +764,26 @@ int emu_analyze_52m(const float *burst, int n, int tsc, float thr, unsigned max_
   if (ok && request) { memcpy(chan, ch, sizeof(cf) * 6 * T->sps); *off = o; }
   return ok ? 1 : 0;
 }
+// k_detect_52m's tile: only the search window is staged (tile rows 0 .. windowLen-1 of the lane's column), the correlation and
+// delayVector's temporary live in the rows behind it, the burst view is offset so that row startIx is tile row 0; every other
+// row of the tile holds poison
+int emu_analyze_52m_tiled(const float *burst, int n, int tsc, float thr, unsigned max_toa, int request, float *amp, float *toa,
+                          float *chan, float *off) {
+  const Geo52 g = geo_52m(max_toa);
+  const int rows = g.windowLen + 2 * g.corrLen + 1, lane = 5;
+  std::vector<cf> tile((size_t)(rows + 8) * kTileStride, mk(1e30F, -1e30F));
+  cf *A = tile.data() + 4 * kTileStride;                                 // poisoned margin rows before and after
+  for (int r = 0; r < g.windowLen; r++) A[r * kTileStride + lane] = (g.startIx + r < n) ? ((const cf *)burst)[g.startIx + r] : mk(0.0F, 0.0F);
+  const View<kTileStride> win{A + lane};
+  cf a = mk(0.0F, 0.0F), ch[6];
+  for (int j = 0; j < 6; j++) ch[j] = mk(0.0F, 0.0F);
+  float t = 0.0F, o = 0.0F;
+  const bool ok = analyze_traffic_52m<kTileStride>(T, win.at(-g.startIx), tsc, thr, 1, max_toa, win.at(g.windowLen),
+                                                   win.at(g.windowLen + g.corrLen), &a, &t, request != 0, ch, &o);
+  amp[0] = a.x; amp[1] = a.y; *toa = t;
+  if (ok && request) { memcpy(chan, ch, sizeof(cf) * 6); *off = o; }
+  return ok ? 1 : 0;
+}
 int emu_energy_detect_52m(const float *v, int n, unsigned win, float thr, float *avg) {
   return energy_detect_52m<1>(View<1>{(cf *)v}, n, win, thr, avg) ? 1 : 0;
 }

@@ -54,6 +54,8 @@ def test_analyze_52m_hostemu(oracle_best, o52, hostemu):
     emu = Emu(hostemu)
     nd = run_analyze(o52.analyze, emu.analyze_52m, bursts, lens, tsc)
     assert nd > 300
+    # the tile-staged kernel's layout: only the search window is in the tile, the rest is poison
+    assert run_analyze(o52.analyze, emu.analyze_52m_tiled, bursts, lens, tsc) == nd
     rng = np.random.default_rng(1)
     for _ in range(50):
         v = (rng.standard_normal(156) + 1j * rng.standard_normal(156)).astype(np.complex64) * rng.uniform(1, 500)
