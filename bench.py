@@ -437,8 +437,10 @@ def leg_other(torch, dsp, dev, stream):
     def pull():
         dsp.trx_pull_streams_dev(trx, res, F * 1250, F, fnc[0], pv, pd, 160, stream=stream)
         fnc[0] += F
-    ms = timeit(torch, stream, pull)
-    out["policy_pull_1024_arfcn_x_32_frames"] = {"bursts": npol, "ms": ms, "bursts_per_s": npol / ms * 1e3, "valid": float(pv.float().mean())}
+    ms_cold = timeit(torch, stream, pull, reps=5, warm=2)        # every pull at a new FN phase: the slot map is built and uploaded
+    ms = timeit(torch, stream, pull, reps=20, warm=55)           # steady state: the 51 phases of FN0 = 32 k (mod 102) are cached
+    out["policy_pull_1024_arfcn_x_32_frames"] = {"bursts": npol, "ms": ms, "bursts_per_s": npol / ms * 1e3,
+                                                 "ms_first_visit_of_a_frame_phase": ms_cold, "valid": float(pv.float().mean())}
     dsp.trx_destroy(trx)
     nfr = npol // 4
     fu = torch.zeros(nfr * 228, dtype=torch.uint8, device=dev)

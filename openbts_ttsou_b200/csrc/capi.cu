@@ -8,6 +8,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/btsdsp.h"
@@ -1165,7 +1166,18 @@ struct btsdsp_trx {
   cudaStream_t side = nullptr;          // access-burst kernels run here, next to the normal-burst kernels
   cudaEvent_t fork_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   TrxVariant var;                       // main transceiver, or the second one (btsdsp_trx_set_variant_52m)
+  // The slot map of a pull (per burst: correlator type, TSC, access-burst numbering) depends on FN only through FN mod 102
+  // (expectedCorrType looks at FN % 51 and FN % 2; the hyperframe is a multiple of 102), so a receiver that pulls batch
+  // after batch sees the same few maps again and again: they are kept on the device, keyed by (fn0 % 102, nframes).
+  struct SlotMap { void *dev = nullptr; long long nr = 0; };
+  std::unordered_map<long long, SlotMap> maps;
+  size_t map_bytes = 0;
 };
+static void trx_drop_maps(btsdsp_trx *t) {
+  for (auto &kv : t->maps) if (kv.second.dev) cudaFree(kv.second.dev);
+  t->maps.clear();
+  t->map_bytes = 0;
+}
 
 int btsdsp_trx_create(btsdsp_ctx *ctx, int narfcn, const uint8_t *tsc, const uint8_t *chan_type, int start_fn,
                       btsdsp_trx **out) {
@@ -1202,6 +1214,7 @@ int btsdsp_trx_destroy(btsdsp_ctx *ctx, btsdsp_trx *t) {
   ARG(ctx && t);
   DeviceGuard g(ctx->device);
   cudaDeviceSynchronize();
+  trx_drop_maps(t);
   if (t->d_state) cudaFree(t->d_state);
   if (t->meta.p) cudaFree(t->meta.p);
   if (t->scratch.p) cudaFree(t->scratch.p);
@@ -1230,6 +1243,7 @@ int btsdsp_trx_set_slot(btsdsp_ctx *ctx, btsdsp_trx *t, int arfcn, int tn, int c
   ARG(ctx && t && arfcn >= 0 && arfcn < t->narfcn && tn >= 0 && tn < 8 && chan_type >= 0 && chan_type <= CT_LOOPBACK);
   DeviceGuard g(ctx->device);
   CK(cudaDeviceSynchronize());
+  trx_drop_maps(t);                                           // the cached slot maps were built from the old combination
   t->chan_type[(size_t)arfcn * 8 + tn] = (uint8_t)chan_type;
   CK(cudaMemcpy(&t->d_state[arfcn].chan_type[tn], &chan_type, sizeof(int), cudaMemcpyHostToDevice));
   return BTSDSP_OK;
@@ -1260,30 +1274,46 @@ static int trx_pull_impl(btsdsp_ctx *ctx, btsdsp_trx *t, const btsdsp_cf32 *burs
   auto grow_buf = [&](DevBuf &b, size_t bytes, bool pinned) { return grow(ctx, b, bytes, pinned); };
   const size_t o_kind = 0, o_tsc = (size_t)((n + 255) & ~255LL), o_slot = 2 * o_tsc, o_idx = o_slot + (size_t)n * 4;
   const size_t meta_bytes = o_idx + (size_t)n * 4 + 256;
-  CK(cudaEventSynchronize(t->meta_done));                  // the previous call's upload has left the staging buffers:
-  int r = grow_buf(t->pin, meta_bytes, true);              // only now may they be reused -- or freed by a grow
-  if (r != BTSDSP_OK) return r;
-  r = grow_buf(t->meta, meta_bytes, false);
-  if (r != BTSDSP_OK) return r;
-  uint8_t *hp = (uint8_t *)t->pin.p;
-  uint8_t *kind = hp + o_kind, *tscb = hp + o_tsc;
-  int *slot = (int *)(hp + o_slot), *idx = (int *)(hp + o_idx);
+  const long long key = (long long)(fn0 % 102) * (1LL << 32) + nframes;
+  auto hit = t->maps.find(key);
+  uint8_t *dm = nullptr;
   long long nr = 0;
-  for (int f = 0; f < nframes; f++) {
-    const int fn = (int)(((long long)fn0 + f) % kHyperframe);
-    for (int a = 0; a < A; a++) {
-      const long long i0 = ((long long)f * A + a) * 8;
-      for (int tn = 0; tn < 8; tn++) {
-        const int c = expected_corr_type(t->chan_type[(size_t)a * 8 + tn], fn);
-        kind[i0 + tn] = (uint8_t)c;
-        tscb[i0 + tn] = t->tsc[a];
-        if (c == CORR_RACH) { slot[i0 + tn] = (int)nr; idx[nr++] = (int)(i0 + tn); } else slot[i0 + tn] = -1;
+  int r = BTSDSP_OK;
+  if (hit != t->maps.end()) {
+    dm = (uint8_t *)hit->second.dev;
+    nr = hit->second.nr;
+    CK(cudaStreamWaitEvent(st, t->meta_done, 0));          // the latest map upload (possibly issued on another stream) has landed
+  } else {
+    CK(cudaEventSynchronize(t->meta_done));                // the previous upload has left the pinned staging buffer:
+    r = grow_buf(t->pin, meta_bytes, true);                // only now may it be reused -- or freed by a grow
+    if (r != BTSDSP_OK) return r;
+    uint8_t *hp = (uint8_t *)t->pin.p;
+    uint8_t *kind = hp + o_kind, *tscb = hp + o_tsc;
+    int *slot = (int *)(hp + o_slot), *idx = (int *)(hp + o_idx);
+    for (int f = 0; f < nframes; f++) {
+      const int fn = (int)(((long long)fn0 + f) % kHyperframe);
+      for (int a = 0; a < A; a++) {
+        const long long i0 = ((long long)f * A + a) * 8;
+        for (int tn = 0; tn < 8; tn++) {
+          const int c = expected_corr_type(t->chan_type[(size_t)a * 8 + tn], fn);
+          kind[i0 + tn] = (uint8_t)c;
+          tscb[i0 + tn] = t->tsc[a];
+          if (c == CORR_RACH) { slot[i0 + tn] = (int)nr; idx[nr++] = (int)(i0 + tn); } else slot[i0 + tn] = -1;
+        }
       }
     }
+    if (t->map_bytes + meta_bytes > (size_t)512 << 20) trx_drop_maps(t);     // a caller that never repeats a phase: start over
+    void *dev = nullptr;
+    cudaError_t e = cudaMalloc(&dev, meta_bytes);
+    if (e != cudaSuccess) return fail(ctx, BTSDSP_ENOMEM, "cudaMalloc (slot map)", e);
+    CK(cudaMemcpyAsync(dev, hp, meta_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(t->meta_done, st));
+    btsdsp_trx::SlotMap m;
+    m.dev = dev; m.nr = nr;
+    t->maps[key] = m;
+    t->map_bytes += meta_bytes;
+    dm = (uint8_t *)dev;
   }
-  uint8_t *dm = (uint8_t *)t->meta.p;
-  CK(cudaMemcpyAsync(dm, hp, meta_bytes, cudaMemcpyHostToDevice, st));
-  CK(cudaEventRecord(t->meta_done, st));
   r = grow_buf(t->scratch, trx_scratch_bytes(n, nr, A, t->var.v52m && !t->var.need_dfe), false);
   if (r != BTSDSP_OK) return r;
   const int nl = launch_trx_pull(ctx->T, t->d_state, A, nframes, fn0, (const cf *)bursts, pitch, stream_pitch, dm + o_kind,
