@@ -250,3 +250,39 @@ def test_radio_to_datagrams_chain(oracle_best, dsp):
         assert np.array_equal(do[:, :158].reshape(nframes, 8, 158), got_d[:, a]), a
         check_state(st[a:a + 1], so, "radio chain %d" % a)
     assert 0.2 < got_v.mean() < 0.95
+
+
+@pytest.mark.gpu
+def test_setslot_between_pulls_at_the_same_frame_phase(oracle_best, dsp):
+    """the per-phase slot maps cached on the device must follow a SETSLOT: pull, change a slot's channel combination, pull
+    again at the same FN phase (FN0 + 102) -- the second pull is judged under the new combination, like the reference
+    object whose mChanType was changed between the two calls"""
+    A, nframes, fn0 = 2, 102, 510
+    tsc = [3, 6]
+    ct = np.array([[1, 1, 0, 1, 5, 1, 1, 1], [1, 4, 1, 1, 1, 1, 7, 1]], np.uint8)
+    ct2 = ct.copy()
+    ct2[0, 2] = 1                      # NONE -> I: the slot is analysed from now on
+    ct2[1, 1] = 1                      # IV (RACH) -> I
+    # the slots that get switched on must carry traffic from the start: generate with the final combinations
+    bursts = synth.make_trx_batch(oracle_best.modulate, oracle_best.expected_corr_type, 2 * nframes, tsc, ct2, fn0=fn0, seed=77)
+    trx = dsp.trx_create(tsc, ct, fn0)
+    half = nframes * A * 8
+    v1, d1 = dsp.trx_pull_host(trx, bursts[:half], fn0)
+    v1b, d1b = dsp.trx_pull_host(trx, bursts[:half], fn0 + 102 * 7)          # same phase again: served from the cached map
+    dsp.trx_set_slot(trx, 0, 2, 1)
+    dsp.trx_set_slot(trx, 1, 1, 1)
+    v2, d2 = dsp.trx_pull_host(trx, bursts[half:], fn0 + 102 * 8)            # same phase, new combinations
+    st = dsp.trx_state(trx)
+    dsp.trx_destroy(trx)
+    b4 = bursts.reshape(2 * nframes, A, 8, -1)
+    for a in range(A):
+        so = oracle_best.trx_new(tsc[a], ct[a], fn0)
+        vo1, do1 = oracle_best.trx_pull(so, np.ascontiguousarray(b4[:nframes, a]).reshape(nframes * 8, -1), fn0)
+        vo1b, do1b = oracle_best.trx_pull(so, np.ascontiguousarray(b4[:nframes, a]).reshape(nframes * 8, -1), fn0 + 102 * 7)
+        so["chan_type"][0] = ct2[a]
+        vo2, do2 = oracle_best.trx_pull(so, np.ascontiguousarray(b4[nframes:, a]).reshape(nframes * 8, -1), fn0 + 102 * 8)
+        for got_v, got_d, vo, do in ((v1, d1, vo1, do1), (v1b, d1b, vo1b, do1b), (v2, d2, vo2, do2)):
+            assert np.array_equal(vo.reshape(nframes, 8), got_v.reshape(nframes, A, 8)[:, a]), a
+            assert np.array_equal(do[:, :158].reshape(nframes, 8, 158), got_d.reshape(nframes, A, 8, -1)[:, a, :, :158]), a
+        check_state(st[a:a + 1], so, "setslot %d" % a)
+    assert v1.reshape(nframes, A, 8)[:, 0, 2].sum() == 0 and v2.reshape(nframes, A, 8)[:, 0, 2].sum() > 0
