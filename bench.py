@@ -108,6 +108,9 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+_CPU_BUFS = {}
+
+
 def cpu_arm(iq, nblocks, tsc, threads, repeat=1, keep=False):
     """the reference's CPU path over the first nblocks blocks of the int16 radio stream `iq` (n, 2): unUSRPifyVector +
     pullBuffer's 65/96 resample, slot cutting, analyzeTrafficBurst + designDFE + equalizeBurst per burst, and the
@@ -116,11 +119,21 @@ def cpu_arm(iq, nblocks, tsc, threads, repeat=1, keep=False):
     o = Oracle("best", sps=1)
     nb, nch = nblocks * BLOCK_BURSTS, nblocks * BLOCK_CHUNKS
     best, out = None, None
+    # result buffers are allocated (and touched) once, outside the timed region, as a resident receiver would hold them
+    key = (nb, nch)
+    buf = _CPU_BUFS.get(key)
+    if buf is None:
+        buf = {"res": np.zeros(nch * 585, np.complex64),
+               "r": dict(flag=np.zeros(nb, np.int32), amp=np.zeros(nb, np.complex64), toa=np.zeros(nb, np.float32),
+                         soft=np.zeros((nb, 160), np.float32)),
+               "u8": np.zeros((nb, 148), np.uint8)}
+        _CPU_BUFS.clear()
+        _CPU_BUFS[key] = buf
     for _ in range(repeat):
         t0 = time.perf_counter()
-        res = o.rx_resample_stream_i16(iq[:nch * 864], False, threads=threads)
-        r = o.rx_stream_demod(res, nb, tsc[:nb], threads=threads)
-        r["soft_u8"] = o.soft_to_wire(r["soft"], threads=threads)
+        res = o.rx_resample_stream_i16(iq[:nch * 864], False, threads=threads, out=buf["res"])
+        r = o.rx_stream_demod(res, nb, tsc[:nb], threads=threads, out=buf["r"])
+        r["soft_u8"] = o.soft_to_wire(r["soft"], threads=threads, out=buf["u8"])
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
         out = r if keep else None
@@ -152,8 +165,8 @@ def run_reference(args, rank):
     nblocks = max(2, min(args.blocks, 400))
     iq = make_stream_cpu(nblocks, 0xB2000002)
     tsc = np.zeros(nblocks * BLOCK_BURSTS, np.uint8)
-    for _ in range(args.warmup):
-        cpu_arm(iq, min(nblocks, 4), tsc, cores)
+    for _ in range(max(args.warmup, 1)):
+        cpu_arm(iq, nblocks, tsc, cores)             # full size: also allocates and touches the result buffers
     times = []
     kind = "port"
     for _ in range(args.steps):

@@ -431,12 +431,14 @@ class Oracle:
         self._run(self._shard(nch, threads), job)
         return out
 
-    def rx_resample_stream_i16(self, iq, flip_iq=False, threads=1):
+    def rx_resample_stream_i16(self, iq, flip_iq=False, threads=1, out=None):
         """iq: int16 (n, 2) radio samples, n a multiple of 864, the stream starts at chunk 0 -> complex64 at 1 sps
-        (unUSRPifyVector + pullBuffer's resample, radioInterface.cpp:91-116, 238-259)."""
+        (unUSRPifyVector + pullBuffer's resample, radioInterface.cpp:91-116, 238-259).  out: optional preallocated result."""
         iq = np.ascontiguousarray(iq, np.int16).reshape(-1, 2)
         nch = iq.shape[0] // 864
-        out = np.zeros(nch * 585, np.complex64)
+        if out is None:
+            out = np.zeros(nch * 585, np.complex64)
+        assert out.dtype == np.complex64 and out.size >= nch * 585
         f = self._f("rx_resample_stream_i16")
 
         def job(lo, hi):
@@ -444,11 +446,12 @@ class Oracle:
         self._run(self._shard(nch, threads), job)
         return out
 
-    def soft_to_wire(self, soft, threads=1):
+    def soft_to_wire(self, soft, threads=1, out=None):
         """soft (n, pitch >= 148) float32 -> (n, 148) uint8 as the RX datagram carries them (Transceiver.cpp:667-669)"""
         soft = np.ascontiguousarray(soft, np.float32)
         n, pitch = soft.shape
-        out = np.zeros((n, 148), np.uint8)
+        if out is None:
+            out = np.zeros((n, 148), np.uint8)
         f = self._f("soft_to_wire")
 
         def job(lo, hi):
@@ -482,12 +485,12 @@ class Oracle:
         self._run([j for j in jobs if j[1] > j[0]], job)
         return out
 
-    def rx_stream_demod(self, resampled, nbursts, tsc, detect_thr=3.0, energy_thr=250.0, threads=1):
+    def rx_stream_demod(self, resampled, nbursts, tsc, detect_thr=3.0, energy_thr=250.0, threads=1, out=None):
         res = _c64(resampled)
         tsc = np.ascontiguousarray(tsc, np.uint8)
         assert stream_offset(nbursts) <= res.size
-        r = dict(flag=np.zeros(nbursts, np.int32), amp=np.zeros(nbursts, np.complex64),
-                 toa=np.zeros(nbursts, np.float32), soft=np.zeros((nbursts, 160), np.float32))
+        r = out if out is not None else dict(flag=np.zeros(nbursts, np.int32), amp=np.zeros(nbursts, np.complex64),
+                                             toa=np.zeros(nbursts, np.float32), soft=np.zeros((nbursts, 160), np.float32))
         f = self._f("rx_stream_demod")
 
         def job(lo, hi):
