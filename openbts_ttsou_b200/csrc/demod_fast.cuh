@@ -55,6 +55,7 @@ BTS_HD void corr36(View<S> win, View<S> out, const cf tap[16]) {
   cf taps[16];                                           // (-im, re) copies for cmac_tap
 #pragma unroll
   for (int k = 0; k < 16; k++) taps[k] = cswapneg(tap[k]);
+#pragma unroll 3                                         // 9 blocks: rolled 0.444 ms, three at a time 0.436, fully unrolled 0.487 (code size)
   for (int n0 = 0; n0 < 36; n0 += 4) {
     cf acc[4];
 #pragma unroll
