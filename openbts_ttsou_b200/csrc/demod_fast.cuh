@@ -93,7 +93,20 @@ BTS_HD cf interp21(const float s[21], View<S> c, int n, int I) {
   return p;
 }
 
-// peakDetect (:663-711) on the 1/512 grid; avgPwr is not needed by analyzeTrafficBurst
+// interpolatePoint when none of its 21 taps is clipped (0 <= I - 10 and I + 11 <= n - 1): no bounds logic
+template <int S>
+BTS_HD cf interp21_interior(const float s[21], View<S> c, int I) {
+  const View<S> t0 = c.at(I - 10);
+  cf p = mk(0.0F, 0.0F);
+#pragma unroll
+  for (int t = 0; t < 21; t++) p = padd(p, pmul0(t0.ld(t), s[t]));
+  return p;
+}
+
+// peakDetect (:663-711) on the 1/512 grid; avgPwr is not needed by analyzeTrafficBurst.
+// The early/late search interpolates at I, I + 2 and finally I + 1 with I in [imax - 2, imax - 1]: when 12 <= imax <= n - 13 no
+// tap of any of them is clipped, and when that holds for every active lane of the warp the search runs without bounds logic
+// (the same products and sums, so the same bits).
 template <int S>
 BTS_HD cf peak_detect_fast(Grid grid, View<S> c, int n, float *peakIndex) {
   float maxVal = 0.0F;
@@ -102,8 +115,27 @@ BTS_HD cf peak_detect_fast(Grid grid, View<S> c, int n, float *peakIndex) {
     const float p = cnorm2(c.ld(i));
     if (p > maxVal) { maxVal = p; imax = i; }
   }
+  const bool interior = imax >= 12 && imax <= n - 13;
+#if defined(__CUDA_ARCH__) && !defined(BTS_NO_INTERIOR_SEARCH)
+  const bool fast = __all_sync(__activemask(), interior);
+#else
+  const bool fast = false && interior;
+#endif
   int e512 = (imax - 1) * kSincGrid;                     // earlyIndex * 512
   float s[21];
+  if (fast) {
+    for (int step = kSincGrid / 2; step >= 1; step >>= 1) {
+      const int I = e512 >> 9, j = e512 & (kSincGrid - 1);
+      load_grid_row(grid, j, s);
+      const float e = cnorm2(interp21_interior<S>(s, c, I)), l = cnorm2(interp21_interior<S>(s, c, I + 2));
+      if (e < l) e512 += step;
+      else if (e > l) e512 -= step;
+      else break;
+    }
+    load_grid_row(grid, e512 & (kSincGrid - 1), s);
+    *peakIndex = BTS_ADD((float)e512 * (1.0F / kSincGrid), 1.0F);
+    return interp21_interior<S>(s, c, (e512 >> 9) + 1);
+  }
   for (int step = kSincGrid / 2; step >= 1; step >>= 1) {
     const int I = e512 >> 9, j = e512 & (kSincGrid - 1);
     load_grid_row(grid, j, s);
@@ -448,8 +480,27 @@ BTS_HD void rach_corr4_roll(View<S> tile, int base, const cf *__restrict__ tap, 
 // peakDetect's early/late search (:684-700) around a maximum already found at lag imax; c must serve lags imax-12..imax+13
 template <int S>
 BTS_HD cf peak_refine_fast(Grid grid, View<S> c, int n, int imax, float *peakIndex) {
+  const bool interior = imax >= 12 && imax <= n - 13;     // no tap of any interpolation is clipped (see peak_detect_fast)
+#if defined(__CUDA_ARCH__) && !defined(BTS_NO_INTERIOR_SEARCH)
+  const bool fast = __all_sync(__activemask(), interior);
+#else
+  const bool fast = false && interior;
+#endif
   int e512 = (imax - 1) * kSincGrid;
   float s[21];
+  if (fast) {
+    for (int step = kSincGrid / 2; step >= 1; step >>= 1) {
+      const int I = e512 >> 9, j = e512 & (kSincGrid - 1);
+      load_grid_row(grid, j, s);
+      const float e = cnorm2(interp21_interior<S>(s, c, I)), l = cnorm2(interp21_interior<S>(s, c, I + 2));
+      if (e < l) e512 += step;
+      else if (e > l) e512 -= step;
+      else break;
+    }
+    load_grid_row(grid, e512 & (kSincGrid - 1), s);
+    *peakIndex = BTS_ADD((float)e512 * (1.0F / kSincGrid), 1.0F);
+    return interp21_interior<S>(s, c, (e512 >> 9) + 1);
+  }
   for (int step = kSincGrid / 2; step >= 1; step >>= 1) {
     const int I = e512 >> 9, j = e512 & (kSincGrid - 1);
     load_grid_row(grid, j, s);
