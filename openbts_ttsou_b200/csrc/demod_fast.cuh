@@ -198,16 +198,17 @@ BTS_HD void delayed12(Grid grid, const DevTables *__restrict__ T, View<S> c, int
 // analyzeTrafficBurst (:935-1037) at sps == 1 with requestChannel == true.  win = burst rows 56..91,
 // corr = 36 scratch rows.  Same outputs as analyze_traffic<S, true>.
 template <int S>
-BTS_HD bool analyze_fast(Grid grid, const DevTables *__restrict__ T, View<S> win, View<S> corr,
-                         int tsc, float thr, cf *amplitude, float *TOA, cf chan[6], float *chanOff) {
+BTS_HD void analyze_corr(const DevTables *__restrict__ T, View<S> win, View<S> corr, int tsc) {
+  cf tap[16];
+  load_corr_taps(T, tsc, tap);
+  corr36<S>(win, corr, tap);
+}
+
+// everything of analyzeTrafficBurst behind the peak search: valley RMS, threshold, channel estimate
+template <int S>
+BTS_HD bool analyze_tail(Grid grid, const DevTables *__restrict__ T, View<S> corr, int tsc, float thr, cf amp, float toa,
+                         cf *amplitude, float *TOA, cf chan[6], float *chanOff) {
   constexpr int L = 36;
-  {
-    cf tap[16];
-    load_corr_taps(T, tsc, tap);
-    corr36<S>(win, corr, tap);
-  }
-  float toa;
-  cf amp = peak_detect_fast<S>(grid, corr, L, &toa);
   if ((toa < 0.0F) || (toa > (float)L)) { *amplitude = mk(0.0F, 0.0F); *TOA = toa; return false; }
   const int p = (int)rintf(toa);
   float valley = 0.0F;
@@ -254,6 +255,15 @@ BTS_HD bool analyze_fast(Grid grid, const DevTables *__restrict__ T, View<S> win
   }
   *chanOff = (float)(5 - maxI);
   return true;
+}
+
+template <int S>
+BTS_HD bool analyze_fast(Grid grid, const DevTables *__restrict__ T, View<S> win, View<S> corr,
+                         int tsc, float thr, cf *amplitude, float *TOA, cf chan[6], float *chanOff) {
+  analyze_corr<S>(T, win, corr, tsc);
+  float toa;
+  const cf amp = peak_detect_fast<S>(grid, corr, 36, &toa);
+  return analyze_tail<S>(grid, T, corr, tsc, thr, amp, toa, amplitude, TOA, chan, chanOff);
 }
 
 // equalizeBurst (:1343-1399) as a streaming pipeline over one lane's column of a ROLLING tile (the burst,

@@ -337,22 +337,28 @@ constexpr int kDetRows = 45;          // burst samples 56..91 in rows 9..44; the
 constexpr int kDetWin = 9;           // (output n only needs window samples >= n - 8, so row n is dead when c[n] is stored)
 constexpr size_t kDetTileBytes = (size_t)kDetRows * kTileStride * sizeof(cf);
 constexpr size_t kEqTileBytes = (size_t)kEqRows * kTileStride * sizeof(cf);
-// Up to 8 warps per CTA read the sinc grid from global memory (43 KB, L1/L2-resident): 12 KB of shared memory per warp
-// lets 16 warps share an SM (registers then bind), 0.47 ms per 800 280 bursts as one-warp CTAs.  WARPS > 8 keeps a
-// shared-memory copy of the grid per CTA (15 warps, 223 KB): 0.58 ms, and its 43 KB copy dominated small launches.
+// Up to 16 warps per CTA read the sinc grid from global memory (43 KB, L1/L2-resident): 12 KB of shared memory per warp
+// lets 16 warps share an SM (registers then bind), 0.47 ms per 800 280 bursts as one-warp CTAs.  WARPS > 16 keeps a
+// shared-memory copy of the grid per CTA (measured at 15 warps, 223 KB: 0.58 ms, and its 43 KB copy dominated small launches).
 #ifndef BTS_DET_WARPS
-#define BTS_DET_WARPS 4
+#define BTS_DET_WARPS 5
 #endif
-// Large batches run 4-warp CTAs: the kernel is ~130 KB of straight-line code, and warps that start together stay close
-// in it, so the SM's 16 resident warps touch 4 code regions instead of 16 (0.474 -> 0.455 ms per 800 280 bursts; 2: 0.462,
-// 8: 0.488).  Small batches keep one-warp CTAs so they spread over all SMs.
+#ifndef BTS_DET_SYNC
+#define BTS_DET_SYNC 1
+#endif
+// Large batches run 5-warp CTAs (three resident per SM = 15 warps, what 128-130 registers allow) whose warps re-join at
+// the phase boundaries: the kernel is ~140 KB of straight-line code that every warp walks once, its top stall is
+// instruction fetch, and warps that stay together touch 3 code regions per SM instead of 15.  Per 800 280 bursts:
+// one-warp CTAs 0.442 ms, 4 warps 0.408 (with barriers 0.413), 5 warps 0.487 without / 0.400 with barriers,
+// 2/3/6/7 with barriers 0.411/0.445/0.443/0.448, 12/15 0.52/0.51 (profiles/README.md r3h).
+// Small batches keep one-warp CTAs so they spread over all SMs.
 constexpr int kDetWarps = BTS_DET_WARPS;
 #ifndef BTS_EQ_WARPS
 #define BTS_EQ_WARPS 1
 #endif
 constexpr int kEqWarps = BTS_EQ_WARPS;
 constexpr long long kDetWideMin = 4096;     // warps
-template <int WARPS> __host__ __device__ constexpr bool detect_grid_shared() { return WARPS > 8; }
+template <int WARPS> __host__ __device__ constexpr bool detect_grid_shared() { return WARPS > 16; }
 template <int WARPS> __host__ __device__ constexpr size_t detect_grid_bytes() { return detect_grid_shared<WARPS>() ? kGridBytes : 0; }
 template <int WARPS> constexpr size_t detect_smem() { return detect_grid_bytes<WARPS>() + WARPS * kDetTileBytes; }
 template <int WARPS> constexpr size_t equalize_smem() { return WARPS * kEqTileBytes; }
@@ -431,7 +437,22 @@ __global__ void __launch_bounds__(WARPS * 32) k_detect_design(const DevTables *_
   bool ok = false;
   cf amp = mk(0.0F, 0.0F), ia = mk(0.0F, 0.0F), chan[6], w[7], fb[5];
   float toa = 0.0F, off = 0.0F;
+#if BTS_DET_SYNC
+  // The CTA's warps re-join at the phase boundaries, so they stay in the same region of the straight-line code and share
+  // its instruction-cache lines (exited warps and lanes do not count for the barrier).
+  {
+    if (pass) analyze_corr<kTileStride>(T, a.at(kDetWin), a, tsc[i]);
+    __syncthreads();
+    cf pk = mk(0.0F, 0.0F);
+    float pt = 0.0F;
+    if (pass) pk = peak_detect_fast<kTileStride>(g, a, 36, &pt);
+    __syncthreads();
+    if (pass) ok = analyze_tail<kTileStride>(g, T, a, tsc[i], detect_thr, pk, pt, &amp, &toa, chan, &off);
+    __syncthreads();
+  }
+#else
   if (pass) ok = analyze_fast<kTileStride>(g, T, a.at(kDetWin), a, tsc[i], detect_thr, &amp, &toa, chan, &off);
+#endif
   if (POLICY || SPLIT) {
     float4 *q = reinterpret_cast<float4 *>(det + i);
     q[0] = make_float4(avg_pwr, ok ? 1.0F : 0.0F, amp.x, amp.y);
