@@ -163,7 +163,11 @@ BTS_HD void load_delay_taps(Grid grid, const DevTables *__restrict__ T, float fr
 // delayVector(corr, delay) (:573-616) evaluated only at the 12 positions [smin, smin+12) the channel-window
 // search of analyzeTrafficBurst reads: out[n] = F[n - io] with F = the 21-tap filtered vector (or corr itself
 // when the fraction is <= 0.01), zero where n - io falls outside the vector.
-template <int S>
+// PAD = rows L .. L+8 of c are scratch the caller no longer needs: when every active lane's 32 input rows
+// [x0 - 10, x0 + 21] lie inside [0, L + 8] those rows are zeroed and the sweep runs without bounds logic.  A zero sample
+// contributes a +-0 product, and an accumulator that started at +0 is never -0, so the sums are the same bits as with
+// the out-of-range taps skipped.
+template <int S, bool PAD = false>
 BTS_HD void delayed12(Grid grid, const DevTables *__restrict__ T, View<S> c, int L, float delay,
                       int smin, cf dl[12]) {
   const int io = (int)floorf(delay);
@@ -175,6 +179,25 @@ BTS_HD void delayed12(Grid grid, const DevTables *__restrict__ T, View<S> c, int
     cf acc[12];
 #pragma unroll
     for (int q = 0; q < 12; q++) acc[q] = mk(0.0F, 0.0F);
+#if defined(__CUDA_ARCH__) && !defined(BTS_NO_PAD_DELAY)
+    if (PAD && __all_sync(__activemask(), x0 >= 10 && x0 + 21 <= L + 8)) {
+#pragma unroll
+      for (int r = 0; r < 9; r++) c.st(L + r, mk(0.0F, 0.0F));
+      const View<S> t0 = c.at(x0 - 10);
+#pragma unroll
+      for (int jj = 0; jj < 32; jj++) {
+        const cf v = t0.ld(31 - jj);
+#pragma unroll
+        for (int q = 0; q < 12; q++) {
+          const int k = q - 11 + jj;
+          if (k >= 0 && k <= 20) acc[q] = padd(acc[q], pmul0(v, s[k]));
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 12; q++) dl[q] = (x0 + q < L) ? acc[q] : mk(0.0F, 0.0F);
+      return;
+    }
+#endif
 #pragma unroll
     for (int jj = 0; jj < 32; jj++) {
       const int row = x0 + 21 - jj;
@@ -205,7 +228,7 @@ BTS_HD void analyze_corr(const DevTables *__restrict__ T, View<S> win, View<S> c
 }
 
 // everything of analyzeTrafficBurst behind the peak search: valley RMS, threshold, channel estimate
-template <int S>
+template <int S, bool PAD = false>
 BTS_HD bool analyze_tail(Grid grid, const DevTables *__restrict__ T, View<S> corr, int tsc, float thr, cf amp, float toa,
                          cf *amplitude, float *TOA, cf chan[6], float *chanOff) {
   constexpr int L = 36;
@@ -232,7 +255,7 @@ BTS_HD bool analyze_tail(Grid grid, const DevTables *__restrict__ T, View<S> cor
   const float TOAoffset = BTS_ADD(mtoa, 10.0F);
   const int smin = (int)floorf(BTS_ADD(TOAoffset, -5.0F));          // window i starts at smin + i (mtoa = 8 +- k/512)
   cf dl[12];
-  delayed12<S>(grid, T, corr, L, -toa, smin, dl);
+  delayed12<S, PAD>(grid, T, corr, L, -toa, smin, dl);
   float maxEnergy = -1.0F;
   int maxI = -1;
 #pragma unroll

@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_detect_design(const DevTables *_
     float pt = 0.0F;
     if (pass) pk = peak_detect_fast<kTileStride>(g, a, 36, &pt);
     __syncthreads();
-    if (pass) ok = analyze_tail<kTileStride>(g, T, a, tsc[i], detect_thr, pk, pt, &amp, &toa, chan, &off);
+    if (pass) ok = analyze_tail<kTileStride, true>(g, T, a, tsc[i], detect_thr, pk, pt, &amp, &toa, chan, &off);
     __syncthreads();
   }
 #else
