@@ -314,6 +314,41 @@ def test_full_size_properties(dsp):
     same(t2, toa.cpu().numpy(), "toa"); same(a2.view(np.float32), amp.cpu().numpy(), "amp")
 
 
+def test_wide_detect_launch_equals_narrow_launches(dsp):
+    """Batches of >= 4096 warps run detect as multi-warp CTAs whose warps meet at barriers (kernels.cu: BTS_DET_WARPS,
+    BTS_DET_SYNC); smaller ones as one-warp CTAs, the form every oracle comparison above exercises.  Same bursts, both ways,
+    with a ragged last CTA, a partial last warp, empty (gated) slots, mixed TSCs and channels: identical outputs."""
+    import torch
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from tools import workloads
+    dev = torch.device("cuda:0")
+    bursts, tsc, _, occ = workloads.normal_batch(dsp, dev, n_arfcn=1025, frames=16, seed=77, empty=0.1)
+    n = 4096 * 32 + 3 * 32 + 7                        # 4100 warps (820 five-warp CTAs), the last one 7 bursts wide
+    assert n <= bursts.shape[0]
+
+    def run(lo, hi, out):
+        m = hi - lo
+        flag, amp, toa, soft = out
+        dsp.demod_normal_dev(bursts[lo:hi], 160, tsc[lo:hi], m, flag[lo:hi], amp[2 * lo:2 * hi], toa[lo:hi],
+                             soft[lo * 148:hi * 148], 148, first=lo, gate_thr=5.0)
+    def outs():
+        return (torch.zeros(n, dtype=torch.int32, device=dev), torch.zeros(n * 2, device=dev), torch.zeros(n, device=dev),
+                torch.full((n * 148,), -1.0, device=dev))
+    wide, narrow = outs(), outs()
+    run(0, n, wide)
+    step = 1024 * 32
+    for lo in range(0, n, step):
+        run(lo, min(n, lo + step), narrow)
+    torch.cuda.synchronize()
+    assert 0 < int(wide[0].sum()) < n                  # some slots detected, some gated or missed
+    for a, b, what in zip(wide, narrow, ("flag", "amp", "toa", "soft")):
+        same(a.cpu().numpy(), b.cpu().numpy(), what)
+
+
 def test_cached_dfe_mode(dsp, oracle_best):
     """analyze -> designDFE -> equalize as three batched device calls (the cached-filter mode of
     Transceiver.cpp:315-396) gives the same result as the fused kernel"""
