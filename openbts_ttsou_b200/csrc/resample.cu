@@ -77,20 +77,29 @@ __constant__ float c_rx_poly[kRxP * 16];          // [r][k] = lpf_rx[br_r + 65 k
 // ------------------------------------------------------------------------------------------------
 // k_resample_rx_v3: one persistent, warp-specialised CTA per SM.
 //   * T consecutive tiles per step (a "super-tile" of 32T periods, 32T + 2 input rows).
-//   * producer: ONE thread issues ONE 2-D tensor (TMA) copy per super-tile into a ring of input buffers, gated by
-//     full/empty mbarriers.  The tensor map describes the stream as rows of 96 samples and the box is 98 samples
-//     wide, so the copy engine itself writes the rows at the conflict-free pitch; rows outside the stream arrive as
-//     zeros (= the reference's zero history and nothing past the end).
-//   * compute warps: warp w runs phase part w % P of tile w / P; they synchronise among themselves on a named
-//     barrier.  Warps of one SM sub-partition (w % 4) run the same part of the unrolled code, released together, so
-//     they share its instruction fetches.  The taps come from shared memory (uniform-address LDS.128): as constant-
-//     bank operands the 4 KB table thrashes the per-SM constant cache and every miss stalls a warp for ~100 cycles.
+//   * mover: ONE thread drives the copy engine in both directions.  In: ONE 2-D tensor (TMA) copy per super-tile into a
+//     ring of input buffers, completion counted on a `full` mbarrier.  The tensor map describes the stream as rows of 96
+//     samples and the box is 98 samples wide, so the copy engine itself writes the rows at the conflict-free pitch; rows
+//     outside the stream arrive as zeros (= the reference's zero history and nothing past the end).  Out: the finished
+//     32T x 65 block is contiguous in shared AND global memory and leaves as one bulk async copy (cp.async.bulk).
+//   * compute warps: warp w runs phase part w % P of tile w / P.  Warps of one SM sub-partition (w % 4) run the same part
+//     of the unrolled code, so they share its instruction fetches.  The taps come from shared memory (uniform-address
+//     LDS.128): as constant-bank operands the 4 KB table thrashes the per-SM constant cache and every miss stalls a warp
+//     for ~100 cycles.
+//   * float input: no CTA barrier in the loop.  A warp that has delivered its part arrives on `outfull`; when all have, the
+//     mover issues the store, THEN the refill of the input slot that step read (the copy engine serves its queue in order:
+//     a 77 KB refill queued ahead of the store kept the output block busy ~1 us longer), waits until the block has been
+//     read out of shared memory and reports it on `drained`.  A compute warp starts the next step as soon as its input has
+//     landed and checks `drained` only before its first store (rx_group's gate), so about half of the block's drain time
+//     is covered by arithmetic.  Per-step tile bookkeeping is 32-bit and division-free (RxTileIter): three 64-bit
+//     divisions per step used to sit on every warp's critical path.
 //   * int16 input (the radio's format): the raw rows land in a staging ring and are widened to float
-//     (unUSRPifyVector, radioInterface.cpp:94-110) into the single float tile at the start of each step.
-//   * output: the finished 32T x 65 block is contiguous in shared AND global memory and leaves as one bulk async
-//     copy (cp.async.bulk) that drains while the next step waits for its input.
+//     (unUSRPifyVector, radioInterface.cpp:94-110) into the single float tile at the start of each step; this path keeps
+//     the barrier-per-step flow (producer thread + full/empty mbarriers, the compute warps meet on a named barrier).
 // History (profiles/README.md, r2): five independent 2-warp CTAs per SM 0.714 ms -> lock-step quarters 0.65 ->
-// 2-instruction taps 0.615 -> producer warp 0.52 -> shared-memory taps + tensor copy ~0.50 ms (213 750 chunks).
+// 2-instruction taps 0.615 -> producer warp 0.52 -> shared-memory taps + tensor copy 0.553 -> barrier-free flow, store
+// ahead of the refill, division-free bookkeeping 0.490 ms (213 750 chunks; the copy pipeline alone, arithmetic removed,
+// runs 0.399 ms = 0.94 of the measured HBM peak: -DBTS_RXV3_NOMATH).
 // tools/rxv3_trace.cu prints per-step timestamps of one CTA (build with -DBTS_RXV3_TRACE).
 // ------------------------------------------------------------------------------------------------
 #ifndef BTS_RXV3_PARTS
@@ -101,20 +110,32 @@ constexpr int kRxV3Parts = BTS_RXV3_PARTS;         // warps per 32-period tile (
 #define BTS_RXV3_RING 2
 #endif
 constexpr int kRxV3Ring = BTS_RXV3_RING;           // input buffers in flight (float tiles, or int16 staging rows)
+#ifndef BTS_RXV3_OBUFS
+#define BTS_RXV3_OBUFS 1
+#endif
+constexpr int kRxV3Obufs = BTS_RXV3_OBUFS;         // output blocks: with one, every step waits for the previous block to drain
 // (An experiment that split the 65 phases over pairs of CTAs, so each SM runs half the unrolled code out of its
 // instruction cache, measured 0.92 ms against 0.50 ms: every input byte then crosses the L2 -> SM fabric twice and the
 // per-GPC fabric becomes the limit -- profiles/README.md r2.  It is not kept in the source.)
+#ifndef BTS_RXV3_DECOUPLED
+#define BTS_RXV3_DECOUPLED 1
+#endif
+// float input: the compute warps never meet at a CTA barrier -- the mover thread issues the output block's bulk copy when the
+// last warp has delivered its part, refills the input slot and reports when the block has been read out; each compute
+// warp checks that report only before its first store of the next step (see the kernel)
+constexpr bool kRxV3Decoupled = BTS_RXV3_DECOUPLED != 0;
 template <bool I16, int T>
 struct RxV3 {
   static constexpr int kPeriods = 32 * T, kRows = kPeriods + 2;
   static constexpr int kIn = kRows * kRxRowPitch, kOut = kPeriods * kRxP;        // samples
   static constexpr int kInSlot = (kIn + 15) & ~15;                               // ring slots start on 128-byte lines (TMA)
-  static constexpr int kThreads = 32 * kRxV3Parts * T + 32;                      // compute warps + the producer warp
+  static constexpr bool kDec = !I16 && kRxV3Decoupled;
+  static constexpr int kThreads = 32 * kRxV3Parts * T + 32;                      // compute warps + the warp that drives the copy engine
   static constexpr int kStage = kRows * 96;                                      // int16 pairs per staging buffer
   static constexpr unsigned kTileBytes = I16 ? kStage * 4u : kIn * 8u;           // what one tensor copy delivers
   // output block; then float: kRxV3Ring input tiles / int16: one float tile + kRxV3Ring staging buffers
-  static constexpr size_t kSmem = 128 + (I16 ? (size_t)(kOut + kInSlot) * sizeof(cf) + (size_t)kRxV3Ring * kStage * 4
-                                             : (size_t)(kOut + kRxV3Ring * kInSlot) * sizeof(cf));
+  static constexpr size_t kSmem = 128 + (I16 ? (size_t)(kRxV3Obufs * kOut + kInSlot) * sizeof(cf) + (size_t)kRxV3Ring * kStage * 4
+                                             : (size_t)(kRxV3Obufs * kOut + kRxV3Ring * kInSlot) * sizeof(cf));
   static_assert((kOut * sizeof(cf)) % 128 == 0 && (kStage * 4) % 128 == 0, "TMA destinations must be 128-byte aligned");
   static_assert(kSmem + 6 * 1024 <= 227 * 1024, "resampler tile does not fit in shared memory");
 };
@@ -123,7 +144,8 @@ __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigne
   const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\ncp.async.bulk.commit_group;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int PENDING>           // returns when at most PENDING of the newest bulk stores are still reading shared memory
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory"); }
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -142,6 +164,28 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
       "r"(parity)
       : "memory");
 }
+// A persistent CTA's walk over the super-tiles (tile t = super-tile t % tps of stream t / tps, t = first, first + stride, ...)
+// without a 64-bit division per step: those sat on every warp's critical path, several hundred cycles per step.
+struct RxTileIter {
+  unsigned tl, tps, stride;      // super-tile within the stream; super-tiles per stream; grid size
+  int st;                        // stream
+  __device__ __forceinline__ RxTileIter(unsigned first, unsigned tps_, unsigned stride_)
+      : tl(first % tps_), tps(tps_), stride(stride_), st((int)(first / tps_)) {}
+  __device__ __forceinline__ void next() {
+    tl += stride;
+    if (tl >= tps) { const unsigned q = tl / tps; tl -= q * tps; st += (int)q; }
+  }
+  // is period (tl * PERIODS + row) the last of its 9-period chunk?
+  template <int PERIODS>
+  __device__ __forceinline__ bool q8(int row) const { return ((tl % 9u) * (unsigned)(PERIODS % 9) + (unsigned)row) % 9u == 8u; }
+};
+// rx_group's gate: wait (once per step) until the previous step's output block has been read out of shared memory
+struct RxDrainGate {
+  unsigned long long *bar;
+  unsigned parity;
+  bool on;
+  __device__ __forceinline__ void operator()() const { if (on) mbar_wait(bar, parity); }
+};
 template <int NTHREADS>
 __device__ __forceinline__ void compute_warps_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
@@ -195,9 +239,10 @@ __global__ void __launch_bounds__(32 * kRxV3Parts * T + 32, 1) k_resample_rx_v3(
   constexpr int NW = kRxV3Parts * T, NC = 32 * NW, R = kRxV3Ring;        // compute warps / threads; warp NW is the producer
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf *obuf = reinterpret_cast<cf *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);   // 128-byte lines
-  cf *xbuf = obuf + C::kOut;
+  cf *xbuf = obuf + kRxV3Obufs * C::kOut;
   short2 *stage = reinterpret_cast<short2 *>(xbuf + C::kInSlot);
-  __shared__ __align__(8) unsigned long long full[R], empty[R];
+  constexpr bool DEC = C::kDec;
+  __shared__ __align__(8) unsigned long long full[R], empty[R], outfull, drained;
   // the taps are read from shared memory (uniform-address LDS.128, ~30 cycles) rather than as constant-bank operands:
   // 4 KB of taps cycled through by 12+ warps misses the small per-SM constant cache and each miss stalls a warp ~100s
   // of cycles on the LDCU that feeds its next four multiplies
@@ -212,21 +257,57 @@ __global__ void __launch_bounds__(32 * kRxV3Parts * T + 32, 1) k_resample_rx_v3(
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], NW);
     }
+    mbar_init(&outfull, NW);
+    mbar_init(&drained, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (warp == NW) {
-    // ---- producer: one thread keeps up to R super-tiles in flight ahead of the compute warps
-    if (lane == 0) {
+    if (lane != 0) return;
+    if constexpr (DEC) {
+      // ---- mover (float input): ONE thread runs both directions of the copy engine.  R super-tiles are requested up front;
+      //      then, per step, when every compute warp has delivered its part: the output block's bulk copy, the refill of the
+      //      input slot that step read (after the store, so the copy engine sees the store first), and -- once the block has
+      //      been read out of shared memory -- the `drained` report the compute warps check before their next first store.
+      RxTileIter tl_((unsigned)first, (unsigned)tps, (unsigned)stride);      // the tile whose input is requested next
+      long long ltile = first;
+      for (int i = 0; i < R && ltile < ntiles; i++, ltile += stride, tl_.next()) {
+        mbar_expect_tx(&full[i], C::kTileBytes);
+        tma_load_tile(xbuf + i * C::kInSlot, &tmap, (int)(tl_.tl * C::kPeriods) - 1 + row_bias, tl_.st, &full[i]);
+      }
+      int b = 0, it = 0;
+      RxTileIter ti((unsigned)first, (unsigned)tps, (unsigned)stride);
+      for (long long tile = first; tile < ntiles; tile += stride, it++, ti.next()) {
+        const long long G0 = (long long)ti.tl * C::kPeriods;
+        RX_TRACE(1, it, 0);
+        mbar_wait(&outfull, it & 1);
+        RX_TRACE(1, it, 1);
+        const bool whole = nperiods - G0 >= C::kPeriods;
+        if (whole) bulk_store(out + ti.st * out_pitch + G0 * kRxP, obuf, (unsigned)(C::kOut * sizeof(cf)));
+        if (ltile < ntiles) {                                              // every warp has left slot b: refill it
+          mbar_expect_tx(&full[b], C::kTileBytes);
+          tma_load_tile(xbuf + b * C::kInSlot, &tmap, (int)(tl_.tl * C::kPeriods) - 1 + row_bias, tl_.st, &full[b]);
+          ltile += stride;
+          tl_.next();
+        }
+        RX_TRACE(1, it, 2);
+        if (++b == R) b = 0;
+        if (whole) bulk_store_wait_read<0>();                              // (a ragged block is copied out by the compute warps)
+        mbar_arrive(&drained);                                             // one phase per step
+      }
+      bulk_store_wait_all();
+    } else {
+      // ---- producer: one thread keeps up to R super-tiles in flight ahead of the compute warps
       int b = 0, use = 0, it = 0;                                        // ring slot and how many times it has been used
-      for (long long tile = first; tile < ntiles; tile += stride, it++) {
+      RxTileIter ti((unsigned)first, (unsigned)tps, (unsigned)stride);
+      for (long long tile = first; tile < ntiles; tile += stride, it++, ti.next()) {
         RX_TRACE(1, it, 0);
         if (use > 0) mbar_wait(&empty[b], (use - 1) & 1);                // the compute warps are done with this slot
         RX_TRACE(1, it, 1);
         // sample (G, r, k) sits at 96*l + ix_r - k - 96 from the tile origin: the tile starts one row before period G0
         mbar_expect_tx(&full[b], C::kTileBytes);
         tma_load_tile(I16 ? (void *)(stage + b * C::kStage) : (void *)(xbuf + b * C::kInSlot), &tmap,
-                      (int)((tile % tps) * C::kPeriods) - 1 + row_bias, (int)(tile / tps), &full[b]);
+                      (int)(ti.tl * C::kPeriods) - 1 + row_bias, ti.st, &full[b]);
         RX_TRACE(1, it, 2);
         if (++b == R) { b = 0; use++; }
       }
@@ -243,11 +324,44 @@ __global__ void __launch_bounds__(32 * kRxV3Parts * T + 32, 1) k_resample_rx_v3(
 #ifdef BTS_RXV3_TRACE
   if (threadIdx.x == 0) g_rx_cta[blockIdx.x][0] = clock64();
 #endif
-  for (long long tile = first; tile < ntiles; tile += stride, it++) {
-    const long long G0 = (tile % tps) * C::kPeriods;
-    cf *xt = xbuf, *ot = obuf;
+  if constexpr (DEC) {
+    RxTileIter ti((unsigned)first, (unsigned)tps, (unsigned)stride);
+    for (long long tile = first; tile < ntiles; tile += stride, it++, ti.next()) {
+      const long long G0 = (long long)ti.tl * C::kPeriods;
+      RX_TRACE(0, it, 0);
+      mbar_wait(&full[b], use & 1);                                      // this step's input has landed
+      RX_TRACE(0, it, 1);
+      const cf *xt = xbuf + b * C::kInSlot;
+      const bool q8 = ti.template q8<C::kPeriods>(row);
+      RX_TRACE(0, it, 2);
+      rx_part<kRxV3Parts, 0, RxDrainGate>(part, s_taps, xt + row * kRxRowPitch, obuf + row * kRxP, q8,
+                                           RxDrainGate{&drained, (unsigned)(it - 1) & 1u, it > 0});
+      RX_TRACE(0, it, 3);
+      fence_async_smem();                                                // outputs visible to the copy engine
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&outfull);                              // this warp's part is in the block; its reads of xt are done
+      if (++b == R) { b = 0; use++; }
+      const long long nper = nperiods - G0 < C::kPeriods ? nperiods - G0 : C::kPeriods;
+      RX_TRACE(0, it, 4);
+      if (nper != C::kPeriods) {                                         // ragged end of a stream: plain stores by all compute warps
+        mbar_wait(&outfull, it & 1);
+        cf *og = out + ti.st * out_pitch + G0 * kRxP;
+        for (int i = threadIdx.x; i < nper * kRxP; i += NC) og[i] = obuf[i];
+        compute_warps_sync<NC>();                                        // nobody writes the block before everybody has read it
+      }
+      RX_TRACE(0, it, 5);
+    }
+#ifdef BTS_RXV3_TRACE
+    if (threadIdx.x == 0) { g_rx_cta[blockIdx.x][1] = clock64(); g_rx_cta[blockIdx.x][2] = it; unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); g_rx_cta[blockIdx.x][3] = sm; }
+#endif
+    return;
+  } else {
+  RxTileIter ti((unsigned)first, (unsigned)tps, (unsigned)stride);
+  for (long long tile = first; tile < ntiles; tile += stride, it++, ti.next()) {
+    const long long G0 = (long long)ti.tl * C::kPeriods;
+    cf *xt = xbuf, *ot = obuf + (it % kRxV3Obufs) * C::kOut;
     RX_TRACE(0, it, 0);
-    if (threadIdx.x == 0 && store_pending) bulk_store_wait_read();       // the single output block has drained
+    if (threadIdx.x == 0 && store_pending) bulk_store_wait_read<kRxV3Obufs - 1>();   // the block this step writes has drained
     compute_warps_sync<NC>();
     mbar_wait(&full[b], use & 1);                                        // this step's input has landed
     RX_TRACE(0, it, 1);
@@ -259,20 +373,26 @@ __global__ void __launch_bounds__(32 * kRxV3Parts * T + 32, 1) k_resample_rx_v3(
     } else {
       xt = xbuf + b * C::kInSlot;
     }
-    const long long G = G0 + row;
-    const bool q8 = (G % 9) == 8;
+    const bool q8 = ti.template q8<C::kPeriods>(row);
     RX_TRACE(0, it, 2);
+#ifndef BTS_RXV3_NOMATH          // (defined: the memory pipeline alone -- tensor copies in, bulk copies out -- for profiles/README.md r3j)
     rx_part<kRxV3Parts>(part, s_taps, xt + row * kRxRowPitch, ot + row * kRxP, q8);
+#endif
     RX_TRACE(0, it, 3);
+#ifndef BTS_RXV3_LATE_RELEASE
     if (!I16) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[b]);
     }
+#endif
+#ifdef BTS_RXV3_LATE_RELEASE
+    const int bdone = b;
+#endif
     if (++b == R) { b = 0; use++; }
     const long long nper = nperiods - G0 < C::kPeriods ? nperiods - G0 : C::kPeriods;
     // the 32T x 65 outputs are contiguous in shared and global memory: one bulk copy, issued by one thread,
     // that drains while the next step waits for its input
-    cf *og = out + (tile / tps) * out_pitch + G0 * kRxP;
+    cf *og = out + ti.st * out_pitch + G0 * kRxP;
     fence_async_smem();
     compute_warps_sync<NC>();                                            // all outputs written; all reads of xt done
     RX_TRACE(0, it, 4);
@@ -284,11 +404,19 @@ __global__ void __launch_bounds__(32 * kRxV3Parts * T + 32, 1) k_resample_rx_v3(
       store_pending = false;
     }
     RX_TRACE(0, it, 5);
+#ifdef BTS_RXV3_LATE_RELEASE
+    // (measurement variant of this barrier-per-step flow: hand the input slot back only after the store has been issued)
+    if (!I16) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[bdone]);
+    }
+#endif
   }
-  if (threadIdx.x == 0 && store_pending) bulk_store_wait_all();
+  if (threadIdx.x == 0) bulk_store_wait_all();                            // nothing may still read this CTA's shared memory
 #ifdef BTS_RXV3_TRACE
   if (threadIdx.x == 0) { g_rx_cta[blockIdx.x][1] = clock64(); g_rx_cta[blockIdx.x][2] = it; unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); g_rx_cta[blockIdx.x][3] = sm; }
 #endif
+  }
 }
 
 #ifndef BTS_RXV3_TILES_F32
@@ -437,13 +565,14 @@ __global__ void __launch_bounds__(kTxFusedThreads, 1) k_tx_fused(const DevTables
   // shared memory at the top of the step, so their latency hides under the previous step's arithmetic
   const long long nslots = nsamples / 625 * 4;
   const bool vec = (reinterpret_cast<uintptr_t>(bits) & 15) == 0;        // 4-slot groups are 592 B = 37 x 16 B
+  const unsigned nst32 = (unsigned)nsteps;                               // 32-bit division per step (2^31 steps would be 79 TB of output)
   auto group_of = [](long long step_) {
     const long long s0_ = (long long)kTxQ * step_ * kTxFusedPeriods - kTxHalo;
     return (s0_ < 0 ? 0 : s0_) / 625;
   };
   auto fetch = [&](long long gs_) {
     int4 v = make_int4(0, 0, 0, 0);
-    const long long a_ = gs_ / nsteps, gfirst = group_of(gs_ - a_ * nsteps) * 4;
+    const long long a_ = (unsigned)gs_ / nst32, gfirst = group_of(gs_ - a_ * nsteps) * 4;
     long long nb = nslots - gfirst;
     if (nb > kTxFusedBursts) nb = kTxFusedBursts;
     if (vec && (int)threadIdx.x * 16 < (int)nb * 148)
@@ -453,7 +582,7 @@ __global__ void __launch_bounds__(kTxFusedThreads, 1) k_tx_fused(const DevTables
   static_assert(kTxFusedBursts * 148 <= kTxFusedThreads * 16, "one 16-byte fetch per thread must cover a step's bits");
   int4 pre = (BITS && blockIdx.x < ngsteps) ? fetch(blockIdx.x) : make_int4(0, 0, 0, 0);
   for (long long gs = blockIdx.x; gs < ngsteps; gs += gridDim.x) {
-    const long long a = gs / nsteps, step = gs - a * nsteps;
+    const long long a = (unsigned)gs / nst32, step = gs - a * nsteps;
     const long long G0 = step * kTxFusedPeriods;
     __syncthreads();                                                     // previous step's tiles are free
     // ---- park the bits of the bursts this step touches, then modulate its samples into the tile
@@ -495,8 +624,8 @@ __global__ void __launch_bounds__(kTxFusedThreads, 1) k_tx_fused(const DevTables
     }
     __syncthreads();
     // ---- this warp's part of the 96 phases of this lane's period
-    const long long G = G0 + row;
-    tx_part<kTxFusedParts>(part, taps, xs + kTxQ * row + kTxHalo, os + row * kTxFusedOutPitch, (G % 9) == 8);
+    const bool q8 = (((unsigned)(step % 9) * (unsigned)(kTxFusedPeriods % 9) + (unsigned)row) % 9u) == 8u;   // (G0 + row) % 9 == 8
+    tx_part<kTxFusedParts>(part, taps, xs + kTxQ * row + kTxHalo, os + row * kTxFusedOutPitch, q8);
     __syncthreads();
     // ---- rows of 96 int16 pairs (384 B) back to global, coalesced
     const int nper = (int)(nperiods - G0 < kTxFusedPeriods ? nperiods - G0 : kTxFusedPeriods);

@@ -12,6 +12,7 @@
 //
 // Reference lines are cited per function (Transceiver/sigProcLib.cpp unless another file is named).
 #pragma once
+#include <type_traits>
 #include "cplx.cuh"
 #include "tables.h"
 
@@ -541,8 +542,11 @@ constexpr int kRxTileRows = 34, kRxRowPitch = 98;                      // sample
 constexpr int kRxTileIn = kRxTileRows * kRxRowPitch;                   // 3332 samples
 constexpr int kRxTileOut = 32 * kRxP;                                  // 2080 samples
 
-template <int R0, int NR = 5>
-BTS_HD void rx_group(const float *__restrict__ taps, const cf *__restrict__ xl, cf *__restrict__ ol, bool q8) {
+// GATE: called once, after the group's sums are complete and before the first of them is written to ol -- the kernel
+// uses it to wait until the output block may be overwritten (resample.cu); the default does nothing.
+struct RxNoGate { BTS_HD void operator()() const {} };
+template <int R0, int NR = 5, class GATE = RxNoGate>
+BTS_HD void rx_group(const float *__restrict__ taps, const cf *__restrict__ xl, cf *__restrict__ ol, bool q8, GATE gate = GATE()) {
   constexpr int CLO = (rx_c(R0, 14)) & ~1;                             // even-aligned lowest sample offset
   constexpr int CHI = rx_c(R0 + NR - 1, 0);
   constexpr int NP = (CHI - CLO) / 2 + 1;                              // 16-byte pairs
@@ -553,6 +557,8 @@ BTS_HD void rx_group(const float *__restrict__ taps, const cf *__restrict__ xl, 
     win[2 * p] = mk(v.x, v.y);
     win[2 * p + 1] = mk(v.z, v.w);
   }
+  constexpr bool kGated = !std::is_same<GATE, RxNoGate>::value;         // ungated: each sum is stored as soon as it is complete
+  cf sums[kGated ? NR : 1];
 #pragma unroll
   for (int d = 0; d < NR; d++) {
     const int r = R0 + d;
@@ -569,7 +575,13 @@ BTS_HD void rx_group(const float *__restrict__ taps, const cf *__restrict__ xl, 
         sum = padd(sum, p);
       }
     }
-    ol[r] = sum;
+    if constexpr (kGated) sums[d] = sum;
+    else ol[r] = sum;
+  }
+  if constexpr (kGated) {
+    gate();
+#pragma unroll
+    for (int d = 0; d < NR; d++) ol[R0 + d] = sums[d];
   }
 }
 
@@ -592,16 +604,16 @@ BTS_HD void rx_half(const float *__restrict__ taps, const cf *__restrict__ xl, c
   }
 }
 // ... or across NW warps: warp w does phases [65 w / NW, 65 (w+1) / NW), cut into register-blocked groups of <= 6
-template <int A, int B>
-BTS_HD void rx_range(const float *__restrict__ taps, const cf *__restrict__ xl, cf *__restrict__ ol, bool q8) {
+template <int A, int B, class GATE = RxNoGate>
+BTS_HD void rx_range(const float *__restrict__ taps, const cf *__restrict__ xl, cf *__restrict__ ol, bool q8, GATE gate = GATE()) {
   constexpr int n = B - A, ng = (n + 5) / 6, first = (n + ng - 1) / ng;
-  rx_group<A, first>(taps, xl, ol, q8);
+  rx_group<A, first, GATE>(taps, xl, ol, q8, gate);                    // the gate opens once, before the part's first store
   if constexpr (n > first) rx_range<A + first, B>(taps, xl, ol, q8);
 }
-template <int NW, int W = 0>
-BTS_HD void rx_part(int warp, const float *__restrict__ taps, const cf *__restrict__ xl, cf *__restrict__ ol, bool q8) {
-  if (warp == W) rx_range<kRxP * W / NW, kRxP * (W + 1) / NW>(taps, xl, ol, q8);
-  else if constexpr (W + 1 < NW) rx_part<NW, W + 1>(warp, taps, xl, ol, q8);
+template <int NW, int W = 0, class GATE = RxNoGate>
+BTS_HD void rx_part(int warp, const float *__restrict__ taps, const cf *__restrict__ xl, cf *__restrict__ ol, bool q8, GATE gate = GATE()) {
+  if (warp == W) rx_range<kRxP * W / NW, kRxP * (W + 1) / NW, GATE>(taps, xl, ol, q8, gate);
+  else if constexpr (W + 1 < NW) rx_part<NW, W + 1, GATE>(warp, taps, xl, ol, q8, gate);
 }
 // ---- tuned TX chain (see resample.cu: k_tx_fused) ------------------------------------------------------------------
 // Per chunk the reference resamples 130 history + 585 new samples to 1056 outputs and sends outputs 192..1055

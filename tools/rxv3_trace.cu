@@ -29,7 +29,7 @@ int main(int argc, char **argv) {
   static long long tr[2][64][8];
   cudaMemcpyFromSymbol(tr, g_rx_trace, sizeof tr);
   const long long t0 = tr[1][0][0];
-  printf("it | compute warp0: wait_full_start full_ok compute_start compute_end barrier_end store_end | producer: start empty_ok issued\n");
+  printf("it | compute warp0: step_top input_landed compute_start compute_end(incl. drain gate) arrived step_end | mover: step_top all_parts_in store+refill_issued\n");
   for (int it = 0; it < 24; it++) {
     printf("%2d |", it);
     for (int k = 0; k < 6; k++) printf(" %7lld", tr[0][it][k] - t0);
