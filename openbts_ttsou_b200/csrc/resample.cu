@@ -90,8 +90,8 @@ __constant__ float c_rx_poly[kRxP * 16];          // [r][k] = lpf_rx[br_r + 65 k
 //     mover issues the store, THEN the refill of the input slot that step read (the copy engine serves its queue in order:
 //     a 77 KB refill queued ahead of the store kept the output block busy ~1 us longer), waits until the block has been
 //     read out of shared memory and reports it on `drained`.  A compute warp starts the next step as soon as its input has
-//     landed and checks `drained` only before its first store (rx_group's gate), so about half of the block's drain time
-//     is covered by arithmetic.  Per-step tile bookkeeping is 32-bit and division-free (RxTileIter): three 64-bit
+//     landed and checks `drained` only before its stores (rx_range's gate: a part keeps its sums in registers until
+//     then), so the block's drain time is covered by arithmetic.  Per-step tile bookkeeping is 32-bit and division-free (RxTileIter): three 64-bit
 //     divisions per step used to sit on every warp's critical path.
 //   * int16 input (the radio's format): the raw rows land in a staging ring and are widened to float
 //     (unUSRPifyVector, radioInterface.cpp:94-110) into the single float tile at the start of each step; this path keeps
@@ -122,7 +122,7 @@ constexpr int kRxV3Obufs = BTS_RXV3_OBUFS;         // output blocks: with one, e
 #endif
 // float input: the compute warps never meet at a CTA barrier -- the mover thread issues the output block's bulk copy when the
 // last warp has delivered its part, refills the input slot and reports when the block has been read out; each compute
-// warp checks that report only before its first store of the next step (see the kernel)
+// warp checks that report only before the stores of its next step (see the kernel)
 constexpr bool kRxV3Decoupled = BTS_RXV3_DECOUPLED != 0;
 template <bool I16, int T>
 struct RxV3 {
@@ -179,7 +179,7 @@ struct RxTileIter {
   template <int PERIODS>
   __device__ __forceinline__ bool q8(int row) const { return ((tl % 9u) * (unsigned)(PERIODS % 9) + (unsigned)row) % 9u == 8u; }
 };
-// rx_group's gate: wait (once per step) until the previous step's output block has been read out of shared memory
+// rx_range's gate: wait (once per step) until the previous step's output block has been read out of shared memory
 struct RxDrainGate {
   unsigned long long *bar;
   unsigned parity;

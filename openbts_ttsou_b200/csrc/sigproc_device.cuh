@@ -542,11 +542,8 @@ constexpr int kRxTileRows = 34, kRxRowPitch = 98;                      // sample
 constexpr int kRxTileIn = kRxTileRows * kRxRowPitch;                   // 3332 samples
 constexpr int kRxTileOut = 32 * kRxP;                                  // 2080 samples
 
-// GATE: called once, after the group's sums are complete and before the first of them is written to ol -- the kernel
-// uses it to wait until the output block may be overwritten (resample.cu); the default does nothing.
-struct RxNoGate { BTS_HD void operator()() const {} };
-template <int R0, int NR = 5, class GATE = RxNoGate>
-BTS_HD void rx_group(const float *__restrict__ taps, const cf *__restrict__ xl, cf *__restrict__ ol, bool q8, GATE gate = GATE()) {
+template <int R0, int NR = 5>
+BTS_HD void rx_group(const float *__restrict__ taps, const cf *__restrict__ xl, cf *__restrict__ ol, bool q8) {
   constexpr int CLO = (rx_c(R0, 14)) & ~1;                             // even-aligned lowest sample offset
   constexpr int CHI = rx_c(R0 + NR - 1, 0);
   constexpr int NP = (CHI - CLO) / 2 + 1;                              // 16-byte pairs
@@ -557,8 +554,6 @@ BTS_HD void rx_group(const float *__restrict__ taps, const cf *__restrict__ xl, 
     win[2 * p] = mk(v.x, v.y);
     win[2 * p + 1] = mk(v.z, v.w);
   }
-  constexpr bool kGated = !std::is_same<GATE, RxNoGate>::value;         // ungated: each sum is stored as soon as it is complete
-  cf sums[kGated ? NR : 1];
 #pragma unroll
   for (int d = 0; d < NR; d++) {
     const int r = R0 + d;
@@ -575,13 +570,7 @@ BTS_HD void rx_group(const float *__restrict__ taps, const cf *__restrict__ xl, 
         sum = padd(sum, p);
       }
     }
-    if constexpr (kGated) sums[d] = sum;
-    else ol[r] = sum;
-  }
-  if constexpr (kGated) {
-    gate();
-#pragma unroll
-    for (int d = 0; d < NR; d++) ol[R0 + d] = sums[d];
+    ol[r] = sum;
   }
 }
 
@@ -604,11 +593,60 @@ BTS_HD void rx_half(const float *__restrict__ taps, const cf *__restrict__ xl, c
   }
 }
 // ... or across NW warps: warp w does phases [65 w / NW, 65 (w+1) / NW), cut into register-blocked groups of <= 6
+// The same sums kept in registers instead of stored: the gated form of rx_range holds a whole part's outputs back until its
+// GATE has been called -- the kernel uses that to wait, as late as possible, until the output block may be overwritten
+// (resample.cu); the default gate does nothing and stores each sum as soon as it is complete.
+struct RxNoGate { BTS_HD void operator()() const {} };
+template <int R0, int NR>
+BTS_HD void rx_group_acc(const float *__restrict__ taps, const cf *__restrict__ xl, bool q8, cf *sums) {
+  constexpr int CLO = (rx_c(R0, 14)) & ~1;
+  constexpr int CHI = rx_c(R0 + NR - 1, 0);
+  constexpr int NP = (CHI - CLO) / 2 + 1;
+  cf win[2 * NP];
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    const float4 v = *reinterpret_cast<const float4 *>(xl + rx_pad(CLO + 2 * p));
+    win[2 * p] = mk(v.x, v.y);
+    win[2 * p + 1] = mk(v.z, v.w);
+  }
+#pragma unroll
+  for (int d = 0; d < NR; d++) {
+    const int r = R0 + d;
+    cf sum = mk(0.0F, 0.0F);
+#pragma unroll
+    for (int k = 0; k < 15; k++) {
+      if (k < rx_ntaps(r)) {
+        const cf x = win[rx_c(r, k) - CLO];
+        cf p = pmul0(x, taps[r * 16 + k]);
+        if (k < rx_trunc(r)) {
+          p.x = q8 ? 0.0F : p.x;
+          p.y = q8 ? 0.0F : p.y;
+        }
+        sum = padd(sum, p);
+      }
+    }
+    sums[d] = sum;
+  }
+}
+template <int A, int B>
+BTS_HD void rx_range_acc(const float *__restrict__ taps, const cf *__restrict__ xl, bool q8, cf *sums) {
+  constexpr int n = B - A, ng = (n + 5) / 6, first = (n + ng - 1) / ng;
+  rx_group_acc<A, first>(taps, xl, q8, sums);
+  if constexpr (n > first) rx_range_acc<A + first, B>(taps, xl, q8, sums + first);
+}
 template <int A, int B, class GATE = RxNoGate>
 BTS_HD void rx_range(const float *__restrict__ taps, const cf *__restrict__ xl, cf *__restrict__ ol, bool q8, GATE gate = GATE()) {
   constexpr int n = B - A, ng = (n + 5) / 6, first = (n + ng - 1) / ng;
-  rx_group<A, first, GATE>(taps, xl, ol, q8, gate);                    // the gate opens once, before the part's first store
-  if constexpr (n > first) rx_range<A + first, B>(taps, xl, ol, q8);
+  if constexpr (!std::is_same<GATE, RxNoGate>::value) {                // all of the part's sums, then the gate, then the stores
+    cf sums[n];
+    rx_range_acc<A, B>(taps, xl, q8, sums);
+    gate();
+#pragma unroll
+    for (int d = 0; d < n; d++) ol[A + d] = sums[d];
+  } else {
+    rx_group<A, first>(taps, xl, ol, q8);
+    if constexpr (n > first) rx_range<A + first, B>(taps, xl, ol, q8);
+  }
 }
 template <int NW, int W = 0, class GATE = RxNoGate>
 BTS_HD void rx_part(int warp, const float *__restrict__ taps, const cf *__restrict__ xl, cf *__restrict__ ol, bool q8, GATE gate = GATE()) {
