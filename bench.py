@@ -404,6 +404,8 @@ def leg_config5(torch, dist, dsp, dev, stream, rank, world, quick):
     out = {"what": "%d ARFCNs x (fused TX chain + int16 RX resample + normal-burst demod) over 117 frames each, ARFCN a on rank "
                    "a mod %d" % (A, world), "arfcns": A, "arfcns_per_rank": len(mine), "bursts": total, "ms": ms,
            "bursts_per_s": total / ms * 1e3, "kernel_launches_per_step": int(launches), "ber_by_tsc": ber,
+           "ber_note": "TSC 1, 3, 4, 5 decode one symbol off in the REFERENCE at sps = 1 (SURVEY F6: midamble TOA = 8 - 1/512 "
+                       "makes channelResponseOffset -1); parity means reproducing it bit for bit",
            "detected": float(o["flag"].float().mean())}
     if world > 1:
         g = lambda: shard.gather_soft(o["soft"], counts="equal")      # noqa: E731
