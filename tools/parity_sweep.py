@@ -10,6 +10,7 @@ from oracle.oracle import Oracle
 import synth
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 40000
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0          # shifts both generators' seeds (default: the r2v/r4 sweep)
 o = Oracle("best")
 dsp = pkg.BtsDsp(0, 1)
 def bits(a):
@@ -22,15 +23,15 @@ def cmp(name, got, want):
     return same_val
 ok = True
 t = time.time()
-bursts, lens, tsc, _ = synth.make_normal_batch(o.modulate, n, seed=101, noise_only=0.1)
-print("made %d normal bursts in %.1f s" % (n, time.time() - t))
+bursts, lens, tsc, _ = synth.make_normal_batch(o.modulate, n, seed=101 + seed, noise_only=0.1)
+print("made %d normal bursts in %.1f s (seed shift %d)" % (n, time.time() - t, seed))
 ref = o.rx_normal_batch(bursts, lens, tsc, threads=16)
 got = dsp.demod_normal_host(bursts, lens, tsc, debug=True) if hasattr(dsp, "demod_normal_host") else None
 for k in ("flag", "amp", "toa", "chan", "off", "w", "b", "soft"):
     g = got[k] if k != "soft" else got[k][:, :ref[k].shape[1]]
     w = ref[k] if k != "soft" else ref[k][:, :g.shape[1]]
     ok &= cmp("normal " + k, g, w)
-rb, rl, _, _ = synth.make_rach_batch(o.modulate, n // 2, seed=202)
+rb, rl, _, _ = synth.make_rach_batch(o.modulate, n // 2, seed=202 + seed)
 ref = o.rx_rach_batch(rb, rl, threads=16)
 got = dsp.rach_host(rb, rl)
 for k in ("flag", "amp", "toa", "soft"):
