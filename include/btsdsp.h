@@ -340,6 +340,32 @@ int btsdsp_tch_decode_dev(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pit
 int btsdsp_tch_decode_host(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pitch, long long nblocks, uint8_t *d, int32_t *good,
                            int32_t *stolen, uint8_t *facch_u, int32_t *facch_ok);
 
+/* ---- L1 encoders on the TRANSMIT side: the producers of the 148-bit bursts modulateBurst is called with (the callers on the
+ * other side of the path).  Bits are one byte each, value in bit 0; bursts are 148 bytes, burst_pitch (>= 148) apart; tsc = 0..7
+ * writes that training sequence at bits 61..86 (gTrainingSequence[mTSC].copyToSegment(mBurst, 61), GSML1FEC.cpp:740), -1 leaves
+ * them zero; tails are zero.  lsb8msb != 0 applies BitVector::LSB8MSB to the 184-bit frame first, as sendFrame does (:781).
+ *
+ * btsdsp_xcch_encode: XCCHL1Encoder::sendFrame = encode + interleave + transmit (GSML1FEC.cpp:763-850; GSM 05.03 4.1): frame
+ * d[184] -> inverted 40-bit Fire-code word (Parity 0x10004820009) -> four tail zeros -> rate-1/2 K = 5 convolutional code
+ * (BitVector::encode, BitVector.cpp:217-238) -> 456 bits block-interleaved over FOUR bursts, both stealing flags set
+ * (:735-736).  frames: nframes x 184; bursts: 4 * nframes. */
+int btsdsp_xcch_encode_dev(btsdsp_ctx *ctx, const uint8_t *frames, long long nframes, int lsb8msb, int tsc, uint8_t *bursts,
+                           int burst_pitch, void *stream);
+int btsdsp_xcch_encode_host(btsdsp_ctx *ctx, const uint8_t *frames, long long nframes, int lsb8msb, int tsc, uint8_t *bursts,
+                            int burst_pitch);
+/* btsdsp_tch_encode: TCHFACCHL1Encoder::encodeTCH / dispatch / interleave (GSML1FEC.cpp:1248-1392; GSM 05.03 3.1, 4.2) over ONE
+ * traffic channel's block stream.  Block q is a speech frame d260[q] (260 bits in class order, i.e. after the g610BitOrder map of
+ * :1255: 3-bit class-1A parity, reordering, four tail zeros, class 1 coded, class 2 appended) or, when steal[q] != 0, the FACCH
+ * frame f184[q] coded like an XCCH block; its 456 bits are diagonally interleaved: the even e-bits and Hu (bit 87) of bursts
+ * 4q .. 4q+3, the odd e-bits and Hl (bit 60) of bursts 4q+4 .. 4q+7.  bursts: 4 * nblocks + 4 -- the last four are half filled
+ * (what the reference keeps in mI[] / mPreviousFACCH for its next dispatch); pass them as `carry` to the next call, which
+ * completes them in its first four bursts.  carry == NULL: the channel starts here (zero-filled interleaver, :1219-1224).
+ * The reference's idle filler pattern (:1347-1350) is a constant of the caller, sent as any other block. */
+int btsdsp_tch_encode_dev(btsdsp_ctx *ctx, const uint8_t *d260, const uint8_t *f184, const uint8_t *steal, long long nblocks, int lsb8msb,
+                          int tsc, const uint8_t *carry, uint8_t *bursts, int burst_pitch, void *stream);
+int btsdsp_tch_encode_host(btsdsp_ctx *ctx, const uint8_t *d260, const uint8_t *f184, const uint8_t *steal, long long nblocks, int lsb8msb,
+                           int tsc, const uint8_t *carry, uint8_t *bursts, int burst_pitch);
+
 /* RACH block decoder (GSM 05.03 4.6; RACHL1Decoder::writeLowSide, GSML1FEC.cpp:474-515): per access burst, the 36
  * coded soft bytes at burst bits 49..84 -> Viterbi -> u[18] = d[8] : p[6] : tail[4] (u may be NULL), and
  * fields[i] = tail | bsic << 8 | ra << 16: tail = the 4 tail bits (a valid burst has 0), bsic = (~sent parity ^ computed

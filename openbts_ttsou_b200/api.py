@@ -97,6 +97,10 @@ _SIGS = {
     "btsdsp_tx_datagrams_52m_host": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp]),
     "btsdsp_trx_set_variant_52m": (_i, [_vp, _vp, _i, _i]),
     "btsdsp_xcch_decode_dev": (_i, [_vp, _vp, _i, _ll, _vp, _vp, _vp]),
+    "btsdsp_xcch_encode_dev": (_i, [_vp, _vp, _ll, _i, _i, _vp, _i, _vp]),
+    "btsdsp_xcch_encode_host": (_i, [_vp, _vp, _ll, _i, _i, _vp, _i]),
+    "btsdsp_tch_encode_dev": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i, _vp]),
+    "btsdsp_tch_encode_host": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i]),
     "btsdsp_xcch_decode_host": (_i, [_vp, _vp, _i, _ll, _vp, _vp]),
     "btsdsp_rach_decode_dev": (_i, [_vp, _vp, _i, _ll, _vp, _vp, _vp]),
     "btsdsp_rach_decode_host": (_i, [_vp, _vp, _i, _ll, _vp, _vp]),
@@ -546,6 +550,33 @@ class BtsDsp:
         self._ck(self.lib.btsdsp_tch_decode_host(self.h, _p(soft_u8), soft_u8.shape[1], n, _p(r["d"]), _p(r["good"]), _p(r["stolen"]),
                                                  _p(r["fu"]), _p(r["fok"])))
         return r
+
+    # ---- L1 encoders on the transmit side: L2 / speech frames -> 148-bit normal bursts ----
+    def xcch_encode_host(self, frames, lsb8msb=True, tsc=-1, burst_pitch=148):
+        """frames (n, 184) bits -> bursts (4n, burst_pitch) bits (XCCHL1Encoder::sendFrame)"""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n = frames.shape[0]
+        out = np.zeros((4 * n, burst_pitch), np.uint8)
+        self._ck(self.lib.btsdsp_xcch_encode_host(self.h, _p(frames), n, int(bool(lsb8msb)), tsc, _p(out), burst_pitch))
+        return out
+
+    def xcch_encode_dev(self, frames, nframes, lsb8msb, tsc, bursts, burst_pitch, stream=None):
+        self._ck(self.lib.btsdsp_xcch_encode_dev(self.h, _p(frames), nframes, int(bool(lsb8msb)), tsc, _p(bursts), burst_pitch, _stream(stream)))
+
+    def tch_encode_host(self, d260, f184, steal, lsb8msb=True, tsc=-1, carry=None, burst_pitch=148):
+        """one traffic channel's blocks -> (4*nblocks + 4, burst_pitch) burst bits; the last four rows are the next call's carry"""
+        d260 = np.ascontiguousarray(d260, np.uint8); f184 = np.ascontiguousarray(f184, np.uint8)
+        steal = np.ascontiguousarray(steal, np.uint8)
+        n = steal.shape[0]
+        carry = None if carry is None else np.ascontiguousarray(carry, np.uint8)
+        out = np.zeros((4 * n + 4, burst_pitch), np.uint8)
+        self._ck(self.lib.btsdsp_tch_encode_host(self.h, _p(d260), _p(f184), _p(steal), n, int(bool(lsb8msb)), tsc,
+                                                 None if carry is None else _p(carry), _p(out), burst_pitch))
+        return out
+
+    def tch_encode_dev(self, d260, f184, steal, nblocks, lsb8msb, tsc, carry, bursts, burst_pitch, stream=None):
+        self._ck(self.lib.btsdsp_tch_encode_dev(self.h, _p(d260), _p(f184), _p(steal), nblocks, int(bool(lsb8msb)), tsc,
+                                                None if carry is None else _p(carry), _p(bursts), burst_pitch, _stream(stream)))
 
     def tch_decode_dev(self, soft_u8, burst_pitch, nblocks, d, good, stolen, fu, fok, stream=None):
         self._ck(self.lib.btsdsp_tch_decode_dev(self.h, _p(soft_u8), burst_pitch, nblocks, _p(d), _p(good), _p(stolen), _p(fu), _p(fok),

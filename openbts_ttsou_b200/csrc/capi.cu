@@ -1526,6 +1526,73 @@ int btsdsp_tch_decode_host(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pi
   return BTSDSP_OK;
 }
 
+/* ---- L1 encoders on the transmit side (fec.cuh): L2 frames / speech frames -> the 148-bit normal bursts modulateBurst takes ---- */
+static unsigned tsc_word_of(int tsc) {               /* midamble bit i (GSM 05.02 5.2.3) in bit 25 - i */
+  unsigned w = 0;
+  if (tsc >= 0 && tsc < 8)
+    for (int i = 0; i < 26; i++) w |= (unsigned)(kTSC[tsc][i] == '1') << (25 - i);
+  return w;
+}
+int btsdsp_xcch_encode_dev(btsdsp_ctx *ctx, const uint8_t *frames, long long nframes, int lsb8msb, int tsc, uint8_t *bursts,
+                           int burst_pitch, void *stream) {
+  ARG(ctx && frames && bursts && nframes >= 0 && burst_pitch >= 148 && tsc >= -1 && tsc < 8);
+  DeviceGuard g(ctx->device);
+  const int nl = launch_xcch_encode(frames, nframes, lsb8msb != 0, tsc_word_of(tsc), tsc >= 0, bursts, burst_pitch, (cudaStream_t)stream);
+  LAUNCHED("xcch_encode", nl);
+  return BTSDSP_OK;
+}
+int btsdsp_xcch_encode_host(btsdsp_ctx *ctx, const uint8_t *frames, long long nframes, int lsb8msb, int tsc, uint8_t *bursts,
+                            int burst_pitch) {
+  ARG(ctx && frames && bursts && nframes > 0 && burst_pitch >= 148 && tsc >= -1 && tsc < 8);
+  DeviceGuard g(ctx->device);
+  size_t total = 0;
+  auto take = [&total](size_t bytes) { size_t o = (total + 255) & ~(size_t)255; total = o + bytes; return o; };
+  const size_t nout = (size_t)nframes * 4 * burst_pitch;
+  const size_t o_f = take((size_t)nframes * 184), o_b = take(nout);
+  GROW(B_RAW, total);
+  uint8_t *d = dbuf<uint8_t>(ctx, B_RAW);
+  cudaStream_t st = ctx->st;
+  CK(cudaMemcpyAsync(d + o_f, frames, (size_t)nframes * 184, cudaMemcpyHostToDevice, st));
+  if (burst_pitch > 148) CK(cudaMemsetAsync(d + o_b, 0, nout, st));          /* bytes between the bursts: defined */
+  int r = btsdsp_xcch_encode_dev(ctx, d + o_f, nframes, lsb8msb, tsc, d + o_b, burst_pitch, st);
+  if (r != BTSDSP_OK) return r;
+  CK(cudaMemcpyAsync(bursts, d + o_b, nout, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return BTSDSP_OK;
+}
+int btsdsp_tch_encode_dev(btsdsp_ctx *ctx, const uint8_t *d260, const uint8_t *f184, const uint8_t *steal, long long nblocks, int lsb8msb,
+                          int tsc, const uint8_t *carry, uint8_t *bursts, int burst_pitch, void *stream) {
+  ARG(ctx && d260 && f184 && steal && bursts && nblocks >= 0 && burst_pitch >= 148 && tsc >= -1 && tsc < 8);
+  DeviceGuard g(ctx->device);
+  const int nl = launch_tch_encode(d260, f184, steal, nblocks, lsb8msb != 0, tsc_word_of(tsc), tsc >= 0, carry, bursts, burst_pitch,
+                                   (cudaStream_t)stream);
+  LAUNCHED("tch_encode", nl);
+  return BTSDSP_OK;
+}
+int btsdsp_tch_encode_host(btsdsp_ctx *ctx, const uint8_t *d260, const uint8_t *f184, const uint8_t *steal, long long nblocks, int lsb8msb,
+                           int tsc, const uint8_t *carry, uint8_t *bursts, int burst_pitch) {
+  ARG(ctx && d260 && f184 && steal && bursts && nblocks > 0 && burst_pitch >= 148 && tsc >= -1 && tsc < 8);
+  DeviceGuard g(ctx->device);
+  size_t total = 0;
+  auto take = [&total](size_t bytes) { size_t o = (total + 255) & ~(size_t)255; total = o + bytes; return o; };
+  const size_t nout = (size_t)(4 * nblocks + 4) * burst_pitch, ncar = (size_t)4 * burst_pitch;
+  const size_t o_d = take((size_t)nblocks * 260), o_f = take((size_t)nblocks * 184), o_s = take((size_t)nblocks), o_c = take(ncar),
+               o_b = take(nout);
+  GROW(B_RAW, total);
+  uint8_t *d = dbuf<uint8_t>(ctx, B_RAW);
+  cudaStream_t st = ctx->st;
+  CK(cudaMemcpyAsync(d + o_d, d260, (size_t)nblocks * 260, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_f, f184, (size_t)nblocks * 184, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_s, steal, (size_t)nblocks, cudaMemcpyHostToDevice, st));
+  if (carry) CK(cudaMemcpyAsync(d + o_c, carry, ncar, cudaMemcpyHostToDevice, st));
+  if (burst_pitch > 148) CK(cudaMemsetAsync(d + o_b, 0, nout, st));
+  int r = btsdsp_tch_encode_dev(ctx, d + o_d, d + o_f, d + o_s, nblocks, lsb8msb, tsc, carry ? d + o_c : nullptr, d + o_b, burst_pitch, st);
+  if (r != BTSDSP_OK) return r;
+  CK(cudaMemcpyAsync(bursts, d + o_b, nout, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return BTSDSP_OK;
+}
+
 int btsdsp_rach_decode_dev(btsdsp_ctx *ctx, const uint8_t *soft_u8, int burst_pitch, long long n, uint8_t *u, int32_t *fields,
                            void *stream) {
   ARG(ctx && soft_u8 && fields && n >= 0 && burst_pitch >= 148);

@@ -199,4 +199,110 @@ BTS_HD void rach_decode_burst_seq(const unsigned char *soft, unsigned char *u, i
   rach_fields(u, tail, bsic, ra);
 }
 
+// ---- L1 encoders on the transmit side: what produces the 148-bit bursts modulateBurst is called with -----------------
+// XCCHL1Encoder::sendFrame / encode / interleave / transmit (GSML1FEC.cpp:763-850) and TCHFACCHL1Encoder::encodeTCH / dispatch /
+// interleave (:1248-1392).  Building blocks as the reference's classes compute them: BitVector::LSB8MSB (BitVector.cpp:189-195,
+// every whole byte bit-reversed), Generator::encoderShift + Parity::writeParityWord (BitVector.h:80-85, BitVector.cpp:411-416: the
+// remainder, inverted, written MSB first), BitVector::encode (BitVector.cpp:217-238: c[2i], c[2i+1] = the two generator outputs for
+// the five-bit history ending at u[i]), the block (XCCH) or diagonal (TCH) interleaver, and the normal burst's fixed fields
+// (GSMTransfer.h:47-48: Hl = bit 60, Hu = bit 87; midamble at 61..86; tails and guard zero).
+BTS_HD int lsb8msb_src(int i) { return (i & ~7) + 7 - (i & 7); }          // source index of bit i after LSB8MSB (whole bytes only)
+BTS_HD unsigned long long fec_parity_seq(const unsigned char *d, int n, unsigned long long coeff, int len) {
+  unsigned long long state = 0;
+  for (int i = 0; i < n; i++) {
+    const unsigned fb = ((unsigned)(state >> (len - 1)) ^ d[i]) & 1u;
+    state <<= 1;
+    if (fb) state ^= coeff;
+  }
+  return state;
+}
+BTS_HD void conv_encode_seq(const unsigned char *u, int n, unsigned char *c) {
+  unsigned acc = 0;
+  for (int i = 0; i < n; i++) {
+    acc = (acc << 1) | (u[i] & 1u);
+    const unsigned g = vit_generator(acc & 0x1fu);
+    c[2 * i] = (unsigned char)(g >> 1);
+    c[2 * i + 1] = (unsigned char)(g & 1u);
+  }
+}
+// tsc_word: midamble bit i (burst bit 61 + i) in bit 25 - i; have_tsc == 0 leaves 61..86 zero for the caller to fill
+BTS_HD unsigned char burst_tsc_bit(unsigned tsc_word, int have_tsc, int pos) {
+  return (unsigned char)(have_tsc ? (tsc_word >> (25 - (pos - 61))) & 1u : 0u);
+}
+// u[228] of an XCCH / FACCH block from its 184-bit L2 frame: d (optionally LSB8MSB), inverted Fire-code parity, four tail zeros
+BTS_HD void xcch_build_u_seq(const unsigned char *frame, int lsb8msb, unsigned char *u) {
+  for (int i = 0; i < 184; i++) u[i] = frame[lsb8msb ? lsb8msb_src(i) : i] & 1;
+  const unsigned long long p = ~fec_parity_seq(u, 184, 0x10004820009ULL, 40);
+  for (int j = 0; j < 40; j++) u[184 + j] = (unsigned char)((p >> (39 - j)) & 1ULL);
+  for (int j = 224; j < 228; j++) u[j] = 0;
+}
+// One XCCH frame -> four normal bursts (148 bits each, burst_pitch apart), stealing flags set (:735-738), sequential form
+BTS_HD void xcch_encode_frame_seq(const unsigned char *frame, int lsb8msb, unsigned tsc_word, int have_tsc, unsigned char *bursts,
+                                  int burst_pitch) {
+  unsigned char u[kXcchU], c[kXcchC];
+  xcch_build_u_seq(frame, lsb8msb, u);
+  conv_encode_seq(u, kXcchU, c);
+  for (int B = 0; B < 4; B++) {
+    unsigned char *b = bursts + B * burst_pitch;
+    for (int i = 0; i < 148; i++) b[i] = (i >= 61 && i < 87) ? burst_tsc_bit(tsc_word, have_tsc, i) : 0;
+    b[60] = 1; b[87] = 1;
+  }
+  for (int k = 0; k < kXcchC; k++) {
+    int B;
+    const int pos = xcch_source_bit(k, &B);
+    bursts[B * burst_pitch + pos] = c[k];
+  }
+}
+// c[456] of one traffic-channel block: a speech frame d[260] (class order, encodeTCH :1248-1279) or a FACCH frame f[184] (:1323-1333)
+BTS_HD void tch_encode_c_seq(int stolen, const unsigned char *d, const unsigned char *f, int lsb8msb, unsigned char *c) {
+  if (stolen) {
+    unsigned char u[kXcchU];
+    xcch_build_u_seq(f, lsb8msb, u);
+    conv_encode_seq(u, kXcchU, c);
+    return;
+  }
+  unsigned char u[kTchU];
+  for (int k = 0; k <= 90; k++) { u[k] = d[2 * k] & 1; u[184 - k] = d[2 * k + 1] & 1; }
+  const unsigned p = ~(unsigned)fec_parity_seq(d, 50, 0x0bULL, 3);            // d holds bits (0/1) -- masked below
+  for (int j = 0; j < 3; j++) u[91 + j] = (unsigned char)((p >> (2 - j)) & 1u);
+  for (int k = 185; k <= 188; k++) u[k] = 0;
+  conv_encode_seq(u, kTchU, c);
+  for (int i = 0; i < kTchC2; i++) c[kTchC1 + i] = d[182 + i] & 1;
+}
+// A traffic channel's block stream, sequential form: nblocks blocks -> 4*nblocks + 4 bursts.  Block q fills the even e-bits and Hu
+// of bursts 4q..4q+3 and the odd e-bits and Hl of bursts 4q+4..4q+7 (dispatch :1355-1381 with mOffset alternating, Hu = this
+// block's stealing flag, Hl = the previous block's).  carry = the four half-filled closing bursts of the previous call (their odd
+// e-bits and Hl are taken over) or NULL for a channel that starts here (the constructor's zero-filled interleaver, :1219-1224).
+BTS_HD void tch_encode_stream_seq(const unsigned char *d260, const unsigned char *f184, const unsigned char *steal, long long nblocks,
+                                  int lsb8msb, unsigned tsc_word, int have_tsc, const unsigned char *carry, unsigned char *bursts,
+                                  int burst_pitch) {
+  for (long long b = 0; b < 4 * nblocks + 4; b++) {
+    unsigned char *bp = bursts + b * burst_pitch;
+    for (int i = 0; i < 148; i++) bp[i] = (i >= 61 && i < 87) ? burst_tsc_bit(tsc_word, have_tsc, i) : 0;
+  }
+  if (carry)
+    for (int B = 0; B < 4; B++) {
+      bursts[B * burst_pitch + 60] = carry[B * burst_pitch + 60] & 1;
+      for (int k = 0; k < kXcchC; k++) {
+        int r;
+        const int pos = tch_source_bit(k, &r);
+        if (r == B + 4) bursts[B * burst_pitch + pos] = carry[B * burst_pitch + pos] & 1;
+      }
+    }
+  for (long long q = 0; q < nblocks; q++) {
+    unsigned char c[kXcchC];
+    const int st = steal[q] ? 1 : 0;
+    tch_encode_c_seq(st, d260 + q * kTchD, f184 + q * 184, lsb8msb, c);
+    for (int k = 0; k < kXcchC; k++) {
+      int r;
+      const int pos = tch_source_bit(k, &r);
+      bursts[(4 * q + r) * burst_pitch + pos] = c[k];
+    }
+    for (int B = 0; B < 4; B++) {
+      bursts[(4 * q + B) * burst_pitch + 87] = (unsigned char)st;
+      bursts[(4 * q + 4 + B) * burst_pitch + 60] = (unsigned char)st;
+    }
+  }
+}
+
 }  // namespace btsdsp

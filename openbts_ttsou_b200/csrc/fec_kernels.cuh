@@ -153,3 +153,158 @@ int launch_rach_decode(const unsigned char *soft, int burst_pitch, long long n, 
   k_rach_decode<<<(unsigned)((n + kXcchWarps - 1) / kXcchWarps), kXcchWarps * 32, 0, st>>>(soft, burst_pitch, n, u, fields);
   return 1;
 }
+
+// ---- L1 encoders on the transmit side (fec.cuh): one warp per XCCH frame / per traffic-channel block ----------------------
+// Parity words are remainders of a linear code: the word of a frame is the XOR of the words of its set bits.  r[i] = the
+// encoder state a single 1 at position i of an n-bit message leaves behind (Generator::encoderShift run over the rest as zeros),
+// built at compile time; a lane XORs the entries of its bits and the warp combines them with shuffles.
+template <int N>
+struct ParityTable { unsigned long long r[N]; };
+template <int N>
+__host__ __device__ constexpr ParityTable<N> make_parity_table(unsigned long long coeff, int len) {
+  ParityTable<N> t{};
+  const unsigned long long mask = (1ULL << len) - 1;
+  for (int i = 0; i < N; i++) {
+    unsigned long long state = coeff & mask;                             // the 1 at position i meets a zero state: fb = 1
+    for (int s = i + 1; s < N; s++) {
+      const unsigned long long fb = (state >> (len - 1)) & 1ULL;
+      state = (state << 1) & mask;
+      if (fb) state ^= coeff & mask;
+    }
+    t.r[i] = state;
+  }
+  return t;
+}
+__constant__ ParityTable<184> c_fire_par = make_parity_table<184>(0x10004820009ULL, 40);
+__constant__ ParityTable<50> c_tch_par = make_parity_table<50>(0x0bULL, 3);
+__device__ __forceinline__ unsigned long long warp_xor64(unsigned long long v) {
+  unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+  lo = __reduce_xor_sync(0xffffffffu, lo);
+  hi = __reduce_xor_sync(0xffffffffu, hi);
+  return ((unsigned long long)hi << 32) | lo;
+}
+// u[0..184) = the frame (optionally LSB8MSB), then the inverted Fire-code word and four tail zeros; c = its 456 coded bits
+__device__ __forceinline__ void xcch_encode_warp(const unsigned char *__restrict__ frame, int lsb8msb, unsigned char *u, unsigned char *c,
+                                                 int lane) {
+  unsigned long long acc = 0;
+  for (int i = lane; i < 184; i += 32) {
+    const unsigned char b = frame[lsb8msb ? lsb8msb_src(i) : i] & 1;
+    u[i] = b;
+    if (b) acc ^= c_fire_par.r[i];
+  }
+  const unsigned long long p = ~warp_xor64(acc);
+  for (int j = lane; j < 44; j += 32) u[184 + j] = j < 40 ? (unsigned char)((p >> (39 - j)) & 1ULL) : 0;
+  __syncwarp();
+  constexpr unsigned long long GEN = vit_generator_lut();
+  for (int k = lane; k < kXcchU; k += 32) {
+    unsigned h = 0;
+#pragma unroll
+    for (int t = 0; t < 5; t++) if (k - t >= 0) h |= (unsigned)u[k - t] << t;
+    const unsigned g = (unsigned)((GEN >> (2 * h)) & 3u);
+    c[2 * k] = (unsigned char)(g >> 1);
+    c[2 * k + 1] = (unsigned char)(g & 1u);
+  }
+  __syncwarp();
+}
+struct EncSmem { unsigned char u[232], c[kXcchC]; };
+
+__global__ void __launch_bounds__(kXcchWarps * 32) k_xcch_encode(const unsigned char *__restrict__ frames, long long nframes, int lsb8msb,
+                                                                unsigned tsc_word, int have_tsc, unsigned char *__restrict__ bursts,
+                                                                int burst_pitch) {
+  __shared__ EncSmem sm[kXcchWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long f = (long long)blockIdx.x * kXcchWarps + warp;
+  if (f >= nframes) return;
+  EncSmem &S = sm[warp];
+  xcch_encode_warp(frames + f * 184, lsb8msb, S.u, S.c, lane);
+  unsigned char *out = bursts + f * 4 * (long long)burst_pitch;
+  for (int idx = lane; idx < 4 * 148; idx += 32) {                       // fixed fields: tails, stealing flags (both set), midamble
+    const int B = idx / 148, pos = idx - B * 148;
+    if (pos < 3 || pos >= 145) out[B * burst_pitch + pos] = 0;
+    else if (pos == 60 || pos == 87) out[B * burst_pitch + pos] = 1;
+    else if (pos >= 61 && pos < 87) out[B * burst_pitch + pos] = burst_tsc_bit(tsc_word, have_tsc, pos);
+  }
+  for (int k = lane; k < kXcchC; k += 32) {                              // interleave :811-819 + mapping on the bursts :842-843
+    int B;
+    const int pos = xcch_source_bit(k, &B);
+    out[B * burst_pitch + pos] = S.c[k];
+  }
+}
+int launch_xcch_encode(const unsigned char *frames, long long nframes, int lsb8msb, unsigned tsc_word, int have_tsc, unsigned char *bursts,
+                       int burst_pitch, cudaStream_t st) {
+  if (nframes <= 0) return 0;
+  k_xcch_encode<<<(unsigned)((nframes + kXcchWarps - 1) / kXcchWarps), kXcchWarps * 32, 0, st>>>(frames, nframes, lsb8msb, tsc_word, have_tsc,
+                                                                                              bursts, burst_pitch);
+  return 1;
+}
+
+// Warp q in [-1, nblocks]: block q writes its own bytes of bursts 4q..4q+7 -- the first four bursts' tails, midamble, Hu and even
+// e-bits, the last four bursts' Hl and odd e-bits -- so no two warps write the same byte.  q = -1 stands for the previous call's
+// last block (`carry`, or a channel that starts here: zeros), q = nblocks for the block that is not there yet (zeros).
+__global__ void __launch_bounds__(kXcchWarps * 32) k_tch_encode(const unsigned char *__restrict__ d260, const unsigned char *__restrict__ f184,
+                                                               const unsigned char *__restrict__ steal, long long nblocks, int lsb8msb,
+                                                               unsigned tsc_word, int have_tsc, const unsigned char *__restrict__ carry,
+                                                               unsigned char *__restrict__ bursts, int burst_pitch) {
+  __shared__ EncSmem sm[kXcchWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long q = (long long)blockIdx.x * kXcchWarps + warp - 1;
+  if (q > nblocks) return;
+  EncSmem &S = sm[warp];
+  const bool real = q >= 0 && q < nblocks;
+  int st = 0;
+  if (real) {
+    st = steal[q] ? 1 : 0;
+    if (st) {
+      xcch_encode_warp(f184 + q * 184, lsb8msb, S.u, S.c, lane);
+    } else {
+      const unsigned char *d = d260 + q * kTchD;
+      unsigned long long acc = 0;
+      for (int i = lane; i < 50; i += 32) if (d[i] & 1) acc ^= c_tch_par.r[i];
+      const unsigned p = ~(unsigned)warp_xor64(acc);
+      for (int k = lane; k <= 90; k += 32) { S.u[k] = d[2 * k] & 1; S.u[184 - k] = d[2 * k + 1] & 1; }   // :1262-1265
+      if (lane < 3) S.u[91 + lane] = (unsigned char)((p >> (2 - lane)) & 1u);                              // :1258-1259
+      if (lane >= 4 && lane < 8) S.u[185 + lane - 4] = 0;                                                  // :1269
+      __syncwarp();
+      constexpr unsigned long long GEN = vit_generator_lut();
+      for (int k = lane; k < kTchU; k += 32) {
+        unsigned h = 0;
+#pragma unroll
+        for (int t = 0; t < 5; t++) if (k - t >= 0) h |= (unsigned)S.u[k - t] << t;
+        const unsigned g = (unsigned)((GEN >> (2 * h)) & 3u);
+        S.c[2 * k] = (unsigned char)(g >> 1);
+        S.c[2 * k + 1] = (unsigned char)(g & 1u);
+      }
+      for (int i = lane; i < kTchC2; i += 32) S.c[kTchC1 + i] = d[182 + i] & 1;                           // :1275
+      __syncwarp();
+    }
+  }
+  unsigned char *lo = bursts + 4 * q * (long long)burst_pitch;           // bursts 4q .. 4q+3 (q >= 0)
+  unsigned char *hi = lo + 4 * (long long)burst_pitch;                   // bursts 4q+4 .. 4q+7 (q < nblocks)
+  if (q >= 0) {
+    for (int idx = lane; idx < 4 * 148; idx += 32) {
+      const int B = idx / 148, pos = idx - B * 148;
+      if (pos < 3 || pos >= 145) lo[B * burst_pitch + pos] = 0;
+      else if (pos == 87) lo[B * burst_pitch + pos] = (unsigned char)st;
+      else if (pos >= 61 && pos < 87) lo[B * burst_pitch + pos] = burst_tsc_bit(tsc_word, have_tsc, pos);
+    }
+  }
+  if (q < nblocks && lane < 4)
+    hi[lane * burst_pitch + 60] = q >= 0 ? (unsigned char)st : (carry ? (unsigned char)(carry[lane * burst_pitch + 60] & 1) : 0);
+  for (int k = lane; k < kXcchC; k += 32) {
+    int r;
+    const int pos = tch_source_bit(k, &r);
+    if (r < 4) {
+      if (q >= 0) lo[r * burst_pitch + pos] = real ? S.c[k] : 0;
+    } else if (q < nblocks) {
+      hi[(r - 4) * burst_pitch + pos] = real ? S.c[k] : (carry ? (unsigned char)(carry[(r - 4) * burst_pitch + pos] & 1) : 0);
+    }
+  }
+}
+int launch_tch_encode(const unsigned char *d260, const unsigned char *f184, const unsigned char *steal, long long nblocks, int lsb8msb,
+                      unsigned tsc_word, int have_tsc, const unsigned char *carry, unsigned char *bursts, int burst_pitch, cudaStream_t st) {
+  if (nblocks < 0) return 0;
+  const long long warps = nblocks + 2;
+  k_tch_encode<<<(unsigned)((warps + kXcchWarps - 1) / kXcchWarps), kXcchWarps * 32, 0, st>>>(d260, f184, steal, nblocks, lsb8msb, tsc_word,
+                                                                                           have_tsc, carry, bursts, burst_pitch);
+  return 1;
+}

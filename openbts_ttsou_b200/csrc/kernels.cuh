@@ -116,6 +116,11 @@ int launch_xcch_decode(const unsigned char *soft, int burst_pitch, long long nfr
 int launch_rach_decode(const unsigned char *soft, int burst_pitch, long long n, unsigned char *u, int *fields, cudaStream_t st);
 int launch_tch_decode(const unsigned char *soft, int burst_pitch, long long nblocks, unsigned char *d, int *good, int *stolen,
                       unsigned char *fu, int *fok, cudaStream_t st);
+// L1 encoders on the transmit side (the producers of modulateBurst's bits)
+int launch_xcch_encode(const unsigned char *frames, long long nframes, int lsb8msb, unsigned tsc_word, int have_tsc, unsigned char *bursts,
+                       int burst_pitch, cudaStream_t st);
+int launch_tch_encode(const unsigned char *d260, const unsigned char *f184, const unsigned char *steal, long long nblocks, int lsb8msb,
+                      unsigned tsc_word, int have_tsc, const unsigned char *carry, unsigned char *bursts, int burst_pitch, cudaStream_t st);
 // the caller-policy pipeline (trx_policy.cuh / trx_kernels.cuh)
 size_t trx_scratch_bytes(long long n, long long nr, int narfcn, bool slice_all = false);
 void launch_usrpify(const cf *x, long long n, int16_t *out, cudaStream_t st);

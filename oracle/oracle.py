@@ -386,6 +386,27 @@ class Oracle:
         self._f("tch_encode")(_ptr(d260), _ptr(f184), _ptr(steal), c_l(n), _ptr(out))
         return out
 
+    # ---- L1 encoders on the transmit side, the reference's own flow (ref only) ----
+    def xcch_send_frames(self, frames, lsb8msb=True, tsc=-1):
+        """frames (n, 184) bits -> (4n, 148) burst bits: XCCHL1Encoder::sendFrame .. transmit"""
+        assert self.kind == "ref"
+        frames = np.ascontiguousarray(frames, np.uint8)
+        out = np.zeros((4 * frames.shape[0], 148), np.uint8)
+        self._f("xcch_send_frames")(_ptr(frames), c_l(frames.shape[0]), c_i(int(bool(lsb8msb))), c_i(tsc), _ptr(out))
+        return out
+
+    def tch_dispatch(self, d260, f184, steal, lsb8msb=True, tsc=-1, state=None):
+        """one TCHFACCHL1Encoder::dispatch per block -> ((4*nblocks, 148) burst bits, state); state = the encoder's members
+        (interleaver rows still to be sent, mPreviousFACCH, mOffset) carried to the next call, None = a fresh encoder"""
+        assert self.kind == "ref"
+        d260 = np.ascontiguousarray(d260, np.uint8); f184 = np.ascontiguousarray(f184, np.uint8)
+        steal = np.ascontiguousarray(steal, np.uint8)
+        n = steal.shape[0]
+        state = np.zeros(458, np.uint8) if state is None else np.ascontiguousarray(state, np.uint8).copy()
+        out = np.zeros((4 * n, 148), np.uint8)
+        self._f("tch_dispatch")(_ptr(d260), _ptr(f184), _ptr(steal), c_l(n), c_i(int(bool(lsb8msb))), c_i(tsc), _ptr(state), _ptr(out))
+        return out, state
+
     def rach_decode(self, soft_u8):
         """soft_u8: (n, >=148) uint8 -> (u[n,18], tail[n], bsic[n], ra[n]); reference classes (ref only)"""
         assert self.kind == "ref"

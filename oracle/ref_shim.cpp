@@ -806,4 +806,110 @@ void ref_tch_encode(const unsigned char *d260, const unsigned char *f184, const 
   }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * L1 encoders on the transmit side, in the reference's own flow and with its own classes (BitVector::LSB8MSB, Parity,
+ * BitVector::encode, gTrainingSequence); the glue of GSML1FEC.cpp (which needs the whole GSM stack to compile) is restated.
+ * XCCHL1Encoder: constructor :716-745 (stealing bits, midamble), sendFrame :763-790, encode :795-808, interleave :811-819,
+ * transmit :823-850.  bursts: 4 * nframes x 148 bits.  tsc < 0: no midamble written.
+ * ------------------------------------------------------------------------------------------------ */
+void ref_xcch_send_frames(const unsigned char *frames, long nframes, int lsb8msb, int tsc, unsigned char *bursts) {
+  ViterbiR2O4 vcoder;
+  Parity blockCoder(0x10004820009ULL, 40, 224);
+  BitVector mBurst(148);
+  mBurst.fill(0);
+  mBurst[60] = 1;                                                      /* mBurst.Hl(1), GSMTransfer.h:47,120 */
+  mBurst[87] = 1;                                                      /* mBurst.Hu(1), :48,117 */
+  if (tsc >= 0) GSM::gTrainingSequence[tsc].copyToSegment(mBurst, 61);
+  BitVector mC(456), mU(228);
+  BitVector mD(mU.head(184)), mP(mU.segment(184, 40));
+  mU.zero();
+  BitVector mI[4];
+  for (int k = 0; k < 4; k++) { mI[k] = BitVector(114); mI[k].fill(0); }
+  for (long f = 0; f < nframes; f++) {
+    BitVector frame(184);
+    for (int i = 0; i < 184; i++) frame[i] = frames[184 * f + i] & 1;
+    frame.copyToSegment(mU, 0);                                        /* :779, headerOffset() == 0 */
+    if (lsb8msb) mD.LSB8MSB();                                         /* :781 */
+    blockCoder.writeParityWord(mD, mP);                                /* :801 */
+    mU.encode(vcoder, mC);                                             /* :805 */
+    for (int k = 0; k < 456; k++) {                                    /* :814-818 */
+      int B = k % 4;
+      int j = 2 * ((49 * k) % 57) + ((k % 8) / 4);
+      mI[B][j] = mC[k];
+    }
+    for (int B = 0; B < 4; B++) {                                      /* :837-848 */
+      mI[B].segment(0, 57).copyToSegment(mBurst, 3);
+      mI[B].segment(57, 57).copyToSegment(mBurst, 88);
+      for (int i = 0; i < 148; i++) bursts[(size_t)(4 * f + B) * 148 + i] = mBurst.bit(i);
+    }
+  }
+}
+
+/* TCHFACCHL1Encoder: encodeTCH :1248-1279 (from the class-ordered d[260]; the g610BitOrder map of :1255 is the caller's),
+ * dispatch :1299-1381 (FACCH branch :1323-1333, stealing flags :1365-1366, mOffset toggling :1373-1374), interleave :1384-1392.
+ * One dispatch() per block sends four bursts; `state` (4 x 114 interleaver rows still to be sent, then mPreviousFACCH, then
+ * mOffset: 458 bytes) carries the encoder's members across calls -- all zeros for a channel that starts here.
+ * bursts: 4 * nblocks x 148 bits. */
+void ref_tch_dispatch(const unsigned char *d260, const unsigned char *f184, const unsigned char *steal, long nblocks, int lsb8msb,
+                      int tsc, unsigned char *state, unsigned char *bursts) {
+  ViterbiR2O4 vcoder;
+  Parity blockCoder(0x10004820009ULL, 40, 224);
+  Parity tchParity(0x0b, 3, 50);
+  BitVector mBurst(148);
+  mBurst.fill(0);
+  if (tsc >= 0) GSM::gTrainingSequence[tsc].copyToSegment(mBurst, 61);
+  BitVector mC(456), mU(228), mTCHU(189), mTCHD(260);
+  BitVector mD(mU.head(184)), mP(mU.segment(184, 40));
+  BitVector mClass1_c(mC.head(378)), mClass1A_d(mTCHD.head(50)), mClass2_d(mTCHD.segment(182, 78));
+  mU.zero();
+  mTCHU.fill(0);
+  int mOffset = state[457] ? 4 : 0;
+  bool mPreviousFACCH = state[456] != 0;
+  BitVector mI[8];
+  for (int k = 0; k < 8; k++) { mI[k] = BitVector(114); mI[k].fill(0); }
+  for (int B = 0; B < 4; B++)
+    for (int j = 0; j < 114; j++) mI[B + mOffset][j] = state[114 * B + j] & 1;
+  for (long q = 0; q < nblocks; q++) {
+    bool currentFACCH = false;
+    if (steal[q]) {
+      currentFACCH = true;
+      BitVector fFrame(184);
+      for (int i = 0; i < 184; i++) fFrame[i] = f184[184 * q + i] & 1;
+      if (lsb8msb) fFrame.LSB8MSB();                                   /* :1327 */
+      fFrame.copyTo(mU);                                               /* :1328 */
+      blockCoder.writeParityWord(mD, mP);                              /* encode(), :801-805 */
+      mU.encode(vcoder, mC);
+    } else {
+      for (int i = 0; i < 260; i++) mTCHD[i] = d260[260 * q + i] & 1;
+      BitVector p = mTCHU.segment(91, 3);
+      tchParity.writeParityWord(mClass1A_d, p);
+      for (unsigned k = 0; k <= 90; k++) {
+        mTCHU[k] = mTCHD[2 * k];
+        mTCHU[184 - k] = mTCHD[2 * k + 1];
+      }
+      for (unsigned k = 185; k <= 188; k++) mTCHU[k] = 0;
+      mTCHU.encode(vcoder, mClass1_c);
+      mClass2_d.copyToSegment(mC, 378);
+    }
+    for (int k = 0; k < 456; k++) {                                    /* interleave(mOffset) :1384-1392 */
+      int B = (k + mOffset) % 8;
+      int j = 2 * ((49 * k) % 57) + ((k % 8) / 4);
+      mI[B][j] = mC[k];
+    }
+    for (int B = 0; B < 4; B++) {                                      /* :1358-1370 */
+      mI[B + mOffset].segment(0, 57).copyToSegment(mBurst, 3);
+      mI[B + mOffset].segment(57, 57).copyToSegment(mBurst, 88);
+      mBurst[87] = currentFACCH;
+      mBurst[60] = mPreviousFACCH;
+      for (int i = 0; i < 148; i++) bursts[(size_t)(4 * q + B) * 148 + i] = mBurst.bit(i);
+    }
+    if (mOffset == 0) mOffset = 4; else mOffset = 0;                   /* :1373-1374 */
+    mPreviousFACCH = currentFACCH;
+  }
+  for (int B = 0; B < 4; B++)
+    for (int j = 0; j < 114; j++) state[114 * B + j] = mI[B + mOffset].bit(j);
+  state[456] = mPreviousFACCH ? 1 : 0;
+  state[457] = mOffset ? 1 : 0;
+}
+
 }  // extern "C"

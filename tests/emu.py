@@ -86,6 +86,21 @@ class Emu:
         self.lib.emu_tch_decode(P(soft_u8), c_i(soft_u8.shape[1]), c_ll(n), P(r["d"]), P(r["good"]), P(r["stolen"]), P(r["fu"]), P(r["fok"]))
         return r
 
+    def xcch_encode(self, frames, lsb8msb=True, tsc=-1, burst_pitch=148):
+        frames = np.ascontiguousarray(frames, np.uint8)
+        out = np.zeros((4 * frames.shape[0], burst_pitch), np.uint8)
+        self.lib.emu_xcch_encode(P(frames), c_ll(frames.shape[0]), c_i(int(bool(lsb8msb))), c_i(tsc), P(out), c_i(burst_pitch))
+        return out
+
+    def tch_encode(self, d260, f184, steal, lsb8msb=True, tsc=-1, carry=None, burst_pitch=148):
+        d260 = np.ascontiguousarray(d260, np.uint8); f184 = np.ascontiguousarray(f184, np.uint8)
+        steal = np.ascontiguousarray(steal, np.uint8)
+        carry = None if carry is None else np.ascontiguousarray(carry, np.uint8)
+        out = np.zeros((4 * steal.shape[0] + 4, burst_pitch), np.uint8)
+        self.lib.emu_tch_encode(P(d260), P(f184), P(steal), c_ll(steal.shape[0]), c_i(int(bool(lsb8msb))), c_i(tsc),
+                                None if carry is None else P(carry), P(out), c_i(burst_pitch))
+        return out
+
     def xcch_decode(self, soft_u8):
         soft_u8 = np.ascontiguousarray(soft_u8, np.uint8)
         n = soft_u8.shape[0] // 4

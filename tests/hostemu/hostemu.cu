@@ -746,6 +746,21 @@ void emu_xcch_decode(const unsigned char *soft, int burst_pitch, long long nfram
     ok[f] = xcch_decode_frame_seq(soft + f * 4 * (long long)burst_pitch, burst_pitch, u + f * kXcchU) ? 1 : 0;
 }
 
+// L1 encoders on the transmit side (fec.cuh, sequential forms); tsc < 0: no midamble
+static unsigned emu_tsc_word(int tsc) {
+  unsigned w = 0;
+  if (tsc >= 0 && tsc < 8) for (int i = 0; i < 26; i++) w |= (unsigned)(kTSC[tsc][i] == '1') << (25 - i);
+  return w;
+}
+void emu_xcch_encode(const unsigned char *frames, long long nframes, int lsb8msb, int tsc, unsigned char *bursts, int burst_pitch) {
+  for (long long f = 0; f < nframes; f++)
+    xcch_encode_frame_seq(frames + f * 184, lsb8msb, emu_tsc_word(tsc), tsc >= 0, bursts + f * 4 * (long long)burst_pitch, burst_pitch);
+}
+void emu_tch_encode(const unsigned char *d260, const unsigned char *f184, const unsigned char *steal, long long nblocks, int lsb8msb,
+                    int tsc, const unsigned char *carry, unsigned char *bursts, int burst_pitch) {
+  tch_encode_stream_seq(d260, f184, steal, nblocks, lsb8msb, emu_tsc_word(tsc), tsc >= 0, carry, bursts, burst_pitch);
+}
+
 void emu_rach_decode(const unsigned char *soft, int burst_pitch, long long n, unsigned char *u, int *tail, int *bsic, int *ra) {
   for (long long i = 0; i < n; i++) rach_decode_burst_seq(soft + i * (long long)burst_pitch, u + i * kRachU, tail + i, bsic + i, ra + i);
 }
