@@ -229,6 +229,12 @@ BTS_HD void conv_encode_seq(const unsigned char *u, int n, unsigned char *c) {
 BTS_HD unsigned char burst_tsc_bit(unsigned tsc_word, int have_tsc, int pos) {
   return (unsigned char)(have_tsc ? (tsc_word >> (25 - (pos - 61))) & 1u : 0u);
 }
+// the fixed-field word of the table-driven kernels (fec_kernels.cuh): bit 1 = a one, bits 4 + i = midamble bit i (Hl, Hu: bits 2, 3)
+BTS_HD unsigned enc_sp_base(unsigned tsc_word, int have_tsc) {
+  unsigned sp = 1u << 1;
+  if (have_tsc) for (int i = 0; i < 26; i++) sp |= ((tsc_word >> (25 - i)) & 1u) << (4 + i);
+  return sp;
+}
 // u[228] of an XCCH / FACCH block from its 184-bit L2 frame: d (optionally LSB8MSB), inverted Fire-code parity, four tail zeros
 BTS_HD void xcch_build_u_seq(const unsigned char *frame, int lsb8msb, unsigned char *u) {
   for (int i = 0; i < 184; i++) u[i] = frame[lsb8msb ? lsb8msb_src(i) : i] & 1;

@@ -154,10 +154,14 @@ int launch_rach_decode(const unsigned char *soft, int burst_pitch, long long n, 
   return 1;
 }
 
-// ---- L1 encoders on the transmit side (fec.cuh): one warp per XCCH frame / per traffic-channel block ----------------------
+// ---- L1 encoders on the transmit side (fec.cuh) --------------------------------------------------------------------------
+// HBM-bound byte work (184 bytes in, 4 x 148 out per frame), so the shape is: coded bits of a frame in shared memory, then every
+// output byte fetched through a compile-time permutation table (interleaver + mapping on the burst + fixed fields folded into one
+// index per output byte) and the bursts written as coalesced 32-bit words.
+//
 // Parity words are remainders of a linear code: the word of a frame is the XOR of the words of its set bits.  r[i] = the
 // encoder state a single 1 at position i of an n-bit message leaves behind (Generator::encoderShift run over the rest as zeros),
-// built at compile time; a lane XORs the entries of its bits and the warp combines them with shuffles.
+// built at compile time; a lane XORs the entries of its bits and the warp combines them.
 template <int N>
 struct ParityTable { unsigned long long r[N]; };
 template <int N>
@@ -175,13 +179,64 @@ __host__ __device__ constexpr ParityTable<N> make_parity_table(unsigned long lon
   }
   return t;
 }
-__constant__ ParityTable<184> c_fire_par = make_parity_table<184>(0x10004820009ULL, 40);
-__constant__ ParityTable<50> c_tch_par = make_parity_table<50>(0x0bULL, 3);
+__device__ const ParityTable<184> d_fire_par = make_parity_table<184>(0x10004820009ULL, 40);   // lane-indexed reads: global, not __constant__
+__device__ const ParityTable<50> d_tch_par = make_parity_table<50>(0x0bULL, 3);
+
+// Output byte o = B * 148 + pos of a group of four bursts -> where its bit comes from: an index into the coded bits, or
+// kEncSpecial | s for the fixed fields -- bit s of a per-group word: s = 0 a zero (tails), 1 a one, 2 Hl, 3 Hu, 4 + i midamble bit i.
+constexpr unsigned short kEncSpecial = 0x8000;
+struct alignas(16) EncTable { unsigned short idx[4 * 148]; };
+__host__ __device__ constexpr unsigned short enc_fixed_field(int pos) {
+  if (pos < 3 || pos >= 145) return kEncSpecial | 0;
+  if (pos == 60) return kEncSpecial | 2;
+  if (pos == 87) return kEncSpecial | 3;
+  if (pos >= 61 && pos < 87) return (unsigned short)(kEncSpecial | (4 + pos - 61));
+  return 0xffff;                                                         // an e-bit
+}
+// XCCH: c[k] goes to burst k % 4, e-bit 2*((49 k) % 57) + (k % 8)/4 (interleave :811-819)
+__host__ __device__ constexpr EncTable make_xcch_table() {
+  EncTable t{};
+  for (int B = 0; B < 4; B++)
+    for (int pos = 0; pos < 148; pos++) t.idx[B * 148 + pos] = enc_fixed_field(pos);
+  for (int k = 0; k < 456; k++) {
+    const int B = k % 4, j = 2 * ((49 * k) % 57) + ((k % 8) / 4);
+    t.idx[B * 148 + (j < 57 ? 3 + j : 88 + (j - 57))] = (unsigned short)k;
+  }
+  return t;
+}
+// TCH: burst B of group g takes the even e-bits from block g (c[k], k % 8 == B: index 456 + k) and the odd ones from block g - 1
+// (k % 8 == B + 4: index k) -- the previous block's coded bits sit right below this block's in shared memory
+__host__ __device__ constexpr EncTable make_tch_table() {
+  EncTable t{};
+  for (int B = 0; B < 4; B++)
+    for (int pos = 0; pos < 148; pos++) t.idx[B * 148 + pos] = enc_fixed_field(pos);
+  for (int k = 0; k < 456; k++) {
+    const int r = k % 8, j = 2 * ((49 * k) % 57) + (r / 4);
+    const int pos = j < 57 ? 3 + j : 88 + (j - 57);
+    if (r < 4) t.idx[r * 148 + pos] = (unsigned short)(456 + k);
+    else t.idx[(r - 4) * 148 + pos] = (unsigned short)k;
+  }
+  return t;
+}
+__device__ const EncTable d_xcch_table = make_xcch_table();
+__device__ const EncTable d_tch_table = make_tch_table();
+
 __device__ __forceinline__ unsigned long long warp_xor64(unsigned long long v) {
   unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
   lo = __reduce_xor_sync(0xffffffffu, lo);
   hi = __reduce_xor_sync(0xffffffffu, hi);
   return ((unsigned long long)hi << 32) | lo;
+}
+// the rate-1/2 K = 5 code over u[0..n): c[2k], c[2k+1] (BitVector::encode)
+__device__ __forceinline__ void conv_encode_warp(const unsigned char *u, int n, unsigned char *c, int lane) {
+  constexpr unsigned long long GEN = vit_generator_lut();
+  for (int k = lane; k < n; k += 32) {
+    unsigned h = 0;
+#pragma unroll
+    for (int t = 0; t < 5; t++) if (k - t >= 0) h |= (unsigned)u[k - t] << t;
+    const unsigned g = (unsigned)((GEN >> (2 * h)) & 3u);
+    *reinterpret_cast<unsigned short *>(c + 2 * k) = (unsigned short)((g >> 1) | ((g & 1u) << 8));
+  }
 }
 // u[0..184) = the frame (optionally LSB8MSB), then the inverted Fire-code word and four tail zeros; c = its 456 coded bits
 __device__ __forceinline__ void xcch_encode_warp(const unsigned char *__restrict__ frame, int lsb8msb, unsigned char *u, unsigned char *c,
@@ -190,121 +245,113 @@ __device__ __forceinline__ void xcch_encode_warp(const unsigned char *__restrict
   for (int i = lane; i < 184; i += 32) {
     const unsigned char b = frame[lsb8msb ? lsb8msb_src(i) : i] & 1;
     u[i] = b;
-    if (b) acc ^= c_fire_par.r[i];
+    if (b) acc ^= d_fire_par.r[i];
   }
   const unsigned long long p = ~warp_xor64(acc);
   for (int j = lane; j < 44; j += 32) u[184 + j] = j < 40 ? (unsigned char)((p >> (39 - j)) & 1ULL) : 0;
   __syncwarp();
-  constexpr unsigned long long GEN = vit_generator_lut();
-  for (int k = lane; k < kXcchU; k += 32) {
-    unsigned h = 0;
-#pragma unroll
-    for (int t = 0; t < 5; t++) if (k - t >= 0) h |= (unsigned)u[k - t] << t;
-    const unsigned g = (unsigned)((GEN >> (2 * h)) & 3u);
-    c[2 * k] = (unsigned char)(g >> 1);
-    c[2 * k + 1] = (unsigned char)(g & 1u);
-  }
+  conv_encode_warp(u, kXcchU, c, lane);
   __syncwarp();
 }
-struct EncSmem { unsigned char u[232], c[kXcchC]; };
+// a traffic channel's speech frame d[260] -> c[456] (encodeTCH :1248-1279)
+__device__ __forceinline__ void tch_speech_encode_warp(const unsigned char *__restrict__ d, unsigned char *u, unsigned char *c, int lane) {
+  unsigned long long acc = 0;
+  for (int i = lane; i < 50; i += 32) if (d[i] & 1) acc ^= d_tch_par.r[i];
+  const unsigned p = ~(unsigned)warp_xor64(acc);
+  for (int k = lane; k <= 90; k += 32) { u[k] = d[2 * k] & 1; u[184 - k] = d[2 * k + 1] & 1; }       // :1262-1265
+  if (lane < 3) u[91 + lane] = (unsigned char)((p >> (2 - lane)) & 1u);                               // :1258-1259
+  if (lane >= 4 && lane < 8) u[185 + lane - 4] = 0;                                                   // :1269
+  __syncwarp();
+  conv_encode_warp(u, kTchU, c, lane);
+  for (int i = lane; i < kTchC2; i += 32) c[kTchC1 + i] = d[182 + i] & 1;                             // :1275
+  __syncwarp();
+}
+// four bursts out: every byte through the table, from the coded bits at `src` or the group's fixed-field word `sp`
+__device__ __forceinline__ unsigned enc_byte(const unsigned char *src, unsigned sp, unsigned idx) {
+  return (idx & kEncSpecial) ? (sp >> (idx & 31u)) & 1u : (unsigned)src[idx];
+}
+__device__ __forceinline__ void enc_write_group(const EncTable &tab, const unsigned char *src, unsigned sp, unsigned char *out, int burst_pitch,
+                                                int lane) {
+  if (((reinterpret_cast<uintptr_t>(out) | (uintptr_t)burst_pitch) & 3) == 0) {
+    for (int w = lane; w < 148; w += 32) {
+      const int B = w / 37, wi = w - 37 * B;
+      const uint2 t = __ldg(reinterpret_cast<const uint2 *>(&tab.idx[4 * w]));
+      const unsigned v = enc_byte(src, sp, t.x & 0xffffu) | (enc_byte(src, sp, t.x >> 16) << 8) | (enc_byte(src, sp, t.y & 0xffffu) << 16) |
+                         (enc_byte(src, sp, t.y >> 16) << 24);
+      *reinterpret_cast<unsigned *>(out + (long long)B * burst_pitch + 4 * wi) = v;
+    }
+  } else {
+    for (int o = lane; o < 4 * 148; o += 32) {
+      const int B = o / 148, pos = o - 148 * B;
+      out[(long long)B * burst_pitch + pos] = (unsigned char)enc_byte(src, sp, tab.idx[o]);
+    }
+  }
+}
+struct alignas(8) EncSmem { unsigned char u[232]; };
 
+// one warp per frame
 __global__ void __launch_bounds__(kXcchWarps * 32) k_xcch_encode(const unsigned char *__restrict__ frames, long long nframes, int lsb8msb,
-                                                                unsigned tsc_word, int have_tsc, unsigned char *__restrict__ bursts,
-                                                                int burst_pitch) {
+                                                                unsigned sp_base, unsigned char *__restrict__ bursts, int burst_pitch) {
   __shared__ EncSmem sm[kXcchWarps];
+  __shared__ __align__(8) unsigned char cs[kXcchWarps][kXcchC];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long f = (long long)blockIdx.x * kXcchWarps + warp;
   if (f >= nframes) return;
-  EncSmem &S = sm[warp];
-  xcch_encode_warp(frames + f * 184, lsb8msb, S.u, S.c, lane);
-  unsigned char *out = bursts + f * 4 * (long long)burst_pitch;
-  for (int idx = lane; idx < 4 * 148; idx += 32) {                       // fixed fields: tails, stealing flags (both set), midamble
-    const int B = idx / 148, pos = idx - B * 148;
-    if (pos < 3 || pos >= 145) out[B * burst_pitch + pos] = 0;
-    else if (pos == 60 || pos == 87) out[B * burst_pitch + pos] = 1;
-    else if (pos >= 61 && pos < 87) out[B * burst_pitch + pos] = burst_tsc_bit(tsc_word, have_tsc, pos);
-  }
-  for (int k = lane; k < kXcchC; k += 32) {                              // interleave :811-819 + mapping on the bursts :842-843
-    int B;
-    const int pos = xcch_source_bit(k, &B);
-    out[B * burst_pitch + pos] = S.c[k];
-  }
+  xcch_encode_warp(frames + f * 184, lsb8msb, sm[warp].u, cs[warp], lane);
+  enc_write_group(d_xcch_table, cs[warp], sp_base | (1u << 2) | (1u << 3), bursts + f * 4 * (long long)burst_pitch, burst_pitch, lane);   // Hl = Hu = 1 :735-736
 }
 int launch_xcch_encode(const unsigned char *frames, long long nframes, int lsb8msb, unsigned tsc_word, int have_tsc, unsigned char *bursts,
                        int burst_pitch, cudaStream_t st) {
   if (nframes <= 0) return 0;
-  k_xcch_encode<<<(unsigned)((nframes + kXcchWarps - 1) / kXcchWarps), kXcchWarps * 32, 0, st>>>(frames, nframes, lsb8msb, tsc_word, have_tsc,
-                                                                                              bursts, burst_pitch);
+  k_xcch_encode<<<(unsigned)((nframes + kXcchWarps - 1) / kXcchWarps), kXcchWarps * 32, 0, st>>>(frames, nframes, lsb8msb,
+                                                                                              enc_sp_base(tsc_word, have_tsc), bursts, burst_pitch);
   return 1;
 }
 
-// Warp q in [-1, nblocks]: block q writes its own bytes of bursts 4q..4q+7 -- the first four bursts' tails, midamble, Hu and even
-// e-bits, the last four bursts' Hl and odd e-bits -- so no two warps write the same byte.  q = -1 stands for the previous call's
-// last block (`carry`, or a channel that starts here: zeros), q = nblocks for the block that is not there yet (zeros).
-__global__ void __launch_bounds__(kXcchWarps * 32) k_tch_encode(const unsigned char *__restrict__ d260, const unsigned char *__restrict__ f184,
-                                                               const unsigned char *__restrict__ steal, long long nblocks, int lsb8msb,
-                                                               unsigned tsc_word, int have_tsc, const unsigned char *__restrict__ carry,
-                                                               unsigned char *__restrict__ bursts, int burst_pitch) {
-  __shared__ EncSmem sm[kXcchWarps];
+// A CTA of kTchGroups + 1 warps makes kTchGroups consecutive groups of four bursts: warp w codes block G0 - 1 + w into row w of
+// the shared array; after the CTA barrier warp w >= 1 assembles group g = G0 + w - 1 from rows w - 1 (block g - 1: odd e-bits, Hl)
+// and w (block g: even e-bits, Hu) -- adjacent rows, so one table index reaches both.  Block -1 is the previous call's last block
+// (`carry`: its odd e-bits and Hl are read back from the four half-filled bursts) or nothing (zeros); block nblocks is not
+// there yet (zeros): group nblocks is the half-filled carry of the next call.  One block in kTchGroups is coded twice.
+constexpr int kTchGroups = 8;
+__global__ void __launch_bounds__((kTchGroups + 1) * 32) k_tch_encode(const unsigned char *__restrict__ d260, const unsigned char *__restrict__ f184,
+                                                                      const unsigned char *__restrict__ steal, long long nblocks, int lsb8msb,
+                                                                      unsigned sp_base, const unsigned char *__restrict__ carry,
+                                                                      unsigned char *__restrict__ bursts, int burst_pitch) {
+  __shared__ EncSmem sm[kTchGroups + 1];
+  __shared__ __align__(8) unsigned char cs[kTchGroups + 1][kXcchC];
+  __shared__ unsigned char stolen[kTchGroups + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long q = (long long)blockIdx.x * kXcchWarps + warp - 1;
-  if (q > nblocks) return;
-  EncSmem &S = sm[warp];
-  const bool real = q >= 0 && q < nblocks;
+  const long long q = (long long)blockIdx.x * kTchGroups - 1 + warp;                  // the block this warp codes
+  unsigned char *c = cs[warp];
   int st = 0;
-  if (real) {
+  if (q >= 0 && q < nblocks) {
     st = steal[q] ? 1 : 0;
-    if (st) {
-      xcch_encode_warp(f184 + q * 184, lsb8msb, S.u, S.c, lane);
-    } else {
-      const unsigned char *d = d260 + q * kTchD;
-      unsigned long long acc = 0;
-      for (int i = lane; i < 50; i += 32) if (d[i] & 1) acc ^= c_tch_par.r[i];
-      const unsigned p = ~(unsigned)warp_xor64(acc);
-      for (int k = lane; k <= 90; k += 32) { S.u[k] = d[2 * k] & 1; S.u[184 - k] = d[2 * k + 1] & 1; }   // :1262-1265
-      if (lane < 3) S.u[91 + lane] = (unsigned char)((p >> (2 - lane)) & 1u);                              // :1258-1259
-      if (lane >= 4 && lane < 8) S.u[185 + lane - 4] = 0;                                                  // :1269
-      __syncwarp();
-      constexpr unsigned long long GEN = vit_generator_lut();
-      for (int k = lane; k < kTchU; k += 32) {
-        unsigned h = 0;
-#pragma unroll
-        for (int t = 0; t < 5; t++) if (k - t >= 0) h |= (unsigned)S.u[k - t] << t;
-        const unsigned g = (unsigned)((GEN >> (2 * h)) & 3u);
-        S.c[2 * k] = (unsigned char)(g >> 1);
-        S.c[2 * k + 1] = (unsigned char)(g & 1u);
-      }
-      for (int i = lane; i < kTchC2; i += 32) S.c[kTchC1 + i] = d[182 + i] & 1;                           // :1275
-      __syncwarp();
+    if (st) xcch_encode_warp(f184 + q * 184, lsb8msb, sm[warp].u, c, lane);           // dispatch :1323-1333
+    else tch_speech_encode_warp(d260 + q * kTchD, sm[warp].u, c, lane);
+  } else if (q == -1 && carry) {
+    for (int k = lane; k < kXcchC; k += 32) {
+      int r;
+      const int pos = tch_source_bit(k, &r);
+      c[k] = r >= 4 ? (unsigned char)(carry[(long long)(r - 4) * burst_pitch + pos] & 1) : 0;
     }
+    st = carry[60] & 1;                                                               // mPreviousFACCH
+  } else {
+    for (int k = lane; k < kXcchC; k += 32) c[k] = 0;
   }
-  unsigned char *lo = bursts + 4 * q * (long long)burst_pitch;           // bursts 4q .. 4q+3 (q >= 0)
-  unsigned char *hi = lo + 4 * (long long)burst_pitch;                   // bursts 4q+4 .. 4q+7 (q < nblocks)
-  if (q >= 0) {
-    for (int idx = lane; idx < 4 * 148; idx += 32) {
-      const int B = idx / 148, pos = idx - B * 148;
-      if (pos < 3 || pos >= 145) lo[B * burst_pitch + pos] = 0;
-      else if (pos == 87) lo[B * burst_pitch + pos] = (unsigned char)st;
-      else if (pos >= 61 && pos < 87) lo[B * burst_pitch + pos] = burst_tsc_bit(tsc_word, have_tsc, pos);
-    }
-  }
-  if (q < nblocks && lane < 4)
-    hi[lane * burst_pitch + 60] = q >= 0 ? (unsigned char)st : (carry ? (unsigned char)(carry[lane * burst_pitch + 60] & 1) : 0);
-  for (int k = lane; k < kXcchC; k += 32) {
-    int r;
-    const int pos = tch_source_bit(k, &r);
-    if (r < 4) {
-      if (q >= 0) lo[r * burst_pitch + pos] = real ? S.c[k] : 0;
-    } else if (q < nblocks) {
-      hi[(r - 4) * burst_pitch + pos] = real ? S.c[k] : (carry ? (unsigned char)(carry[(r - 4) * burst_pitch + pos] & 1) : 0);
-    }
-  }
+  if (lane == 0) stolen[warp] = (unsigned char)st;
+  __syncthreads();
+  const long long g = q;                                                              // warp w >= 1 assembles group g = its own block's index
+  if (warp == 0 || g > nblocks) return;
+  const unsigned sp = sp_base | ((unsigned)stolen[warp - 1] << 2) | ((unsigned)stolen[warp] << 3);   // Hl = previous, Hu = current :1365-1366
+  enc_write_group(d_tch_table, cs[warp - 1], sp, bursts + g * 4 * (long long)burst_pitch, burst_pitch, lane);
 }
 int launch_tch_encode(const unsigned char *d260, const unsigned char *f184, const unsigned char *steal, long long nblocks, int lsb8msb,
                       unsigned tsc_word, int have_tsc, const unsigned char *carry, unsigned char *bursts, int burst_pitch, cudaStream_t st) {
   if (nblocks < 0) return 0;
-  const long long warps = nblocks + 2;
-  k_tch_encode<<<(unsigned)((warps + kXcchWarps - 1) / kXcchWarps), kXcchWarps * 32, 0, st>>>(d260, f184, steal, nblocks, lsb8msb, tsc_word,
-                                                                                           have_tsc, carry, bursts, burst_pitch);
+  const long long groups = nblocks + 1;
+  k_tch_encode<<<(unsigned)((groups + kTchGroups - 1) / kTchGroups), (kTchGroups + 1) * 32, 0, st>>>(d260, f184, steal, nblocks, lsb8msb,
+                                                                                                  enc_sp_base(tsc_word, have_tsc), carry, bursts,
+                                                                                                  burst_pitch);
   return 1;
 }
