@@ -437,7 +437,7 @@ def leg_config5(torch, dist, dsp, dev, stream, rank, world, quick):
 
 def leg_other(torch, dsp, dev, stream):
     """the entry points either side of the path, device-resident (N = 1): fused TX chain, the caller-policy pull with RX
-    datagrams, and the L1 block decoders (XCCH, TCH/FACCH) on the pull's soft bytes"""
+    datagrams, the L1 block decoders (XCCH, TCH/FACCH) on the pull's soft bytes, and the transmit-side L1 encoders"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import synth
     out = {}
@@ -482,6 +482,28 @@ def leg_other(torch, dsp, dev, stream):
     ti = torch.zeros((3, nblk), dtype=torch.int32, device=dev)
     ms = timeit(torch, stream, lambda: dsp.tch_decode_dev(pd[8:], 160, nblk, td, ti[0], ti[1], fu, ti[2], stream=stream))
     out["tch_facch_decode"] = {"blocks": nblk, "ms": ms, "bursts_per_s": 4 * nblk / ms * 1e3, "stolen": float(ti[1].float().mean())}
+    # the transmit-side L1 encoders (frames -> 148-bit bursts) and their round trip through the block decoders above
+    frames = torch.randint(0, 2, (nfr, 184), generator=g, device=dev, dtype=torch.uint8)
+    eb = torch.zeros((4 * nfr, 148), dtype=torch.uint8, device=dev)
+    ms = timeit(torch, stream, lambda: dsp.xcch_encode_dev(frames, nfr, 0, 2, eb, 148, stream=stream))
+    soft = (eb * 255).contiguous()
+    dsp.xcch_decode_dev(soft, 148, nfr, fu, fok, stream=stream)
+    torch.cuda.synchronize()
+    back = bool(fok.bool().all()) and bool(torch.equal(fu.view(nfr, 228)[:, :184], frames))
+    out["xcch_encode"] = {"frames": nfr, "ms": ms, "bursts_per_s": 4 * nfr / ms * 1e3, "algorithmic_gbs": nfr * (184 + 592) / ms / 1e6,
+                          "decodes_back_to_the_frames": back}
+    d260 = torch.randint(0, 2, (nblk, 260), generator=g, device=dev, dtype=torch.uint8)
+    steal = (torch.rand(nblk, generator=g, device=dev) < 0.1).to(torch.uint8)
+    tb = torch.zeros((4 * nblk + 4, 148), dtype=torch.uint8, device=dev)
+    ms = timeit(torch, stream, lambda: dsp.tch_encode_dev(d260, frames, steal, nblk, 0, 5, None, tb, 148, stream=stream))
+    soft = (tb * 255).contiguous()
+    dsp.tch_decode_dev(soft, 148, nblk, td, ti[0], ti[1], fu, ti[2], stream=stream)
+    torch.cuda.synchronize()
+    sp = steal == 0
+    back = (bool(torch.equal(ti[1] != 0, ~sp)) and bool(ti[0][sp].bool().all()) and bool(torch.equal(td.view(nblk, 260)[sp], d260[sp]))
+            and bool(ti[2][~sp].bool().all()) and bool(torch.equal(fu.view(-1, 228)[:nblk][~sp][:, :184], frames[:nblk][~sp])))
+    out["tch_facch_encode"] = {"blocks": nblk, "ms": ms, "bursts_per_s": 4 * nblk / ms * 1e3,
+                               "algorithmic_gbs": nblk * (260 + 184 + 1 + 592) / ms / 1e6, "decodes_back_to_the_frames": back}
     return out
 
 
