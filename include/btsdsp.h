@@ -360,7 +360,8 @@ int btsdsp_xcch_encode_host(btsdsp_ctx *ctx, const uint8_t *frames, long long nf
  * 4q .. 4q+3, the odd e-bits and Hl (bit 60) of bursts 4q+4 .. 4q+7.  bursts: 4 * nblocks + 4 -- the last four are half filled
  * (what the reference keeps in mI[] / mPreviousFACCH for its next dispatch); pass them as `carry` to the next call, which
  * completes them in its first four bursts.  carry == NULL: the channel starts here (zero-filled interleaver, :1219-1224).
- * The reference's idle filler pattern (:1347-1350) is a constant of the caller, sent as any other block. */
+ * d260, f184 and steal must all be valid (rows of the kind a block is not are never read).  nblocks == 0 (device entry point) just
+ * completes the carry: four bursts out.  The reference's idle filler pattern (:1347-1350) is a constant of the caller. */
 int btsdsp_tch_encode_dev(btsdsp_ctx *ctx, const uint8_t *d260, const uint8_t *f184, const uint8_t *steal, long long nblocks, int lsb8msb,
                           int tsc, const uint8_t *carry, uint8_t *bursts, int burst_pitch, void *stream);
 int btsdsp_tch_encode_host(btsdsp_ctx *ctx, const uint8_t *d260, const uint8_t *f184, const uint8_t *steal, long long nblocks, int lsb8msb,

@@ -132,6 +132,30 @@ def test_tch_encode_gpu_matches_reference(ref, dsp):
 
 
 @pytest.mark.gpu
+def test_tch_encode_edges_gpu(ref, dsp):
+    """no blocks at all (the carry is completed with an empty block), one block, and a CTA boundary (8 groups per CTA)"""
+    import torch
+    d, f, steal = make_tch(17, 79)
+    want = ref_tch(ref, d, f, steal, True, 5, [(0, 17)])
+    first = dsp.tch_encode_host(d[:9], f[:9], steal[:9], True, 5)            # 10 groups: two CTAs
+    assert np.array_equal(first[:-4], want[:36])
+    dev = torch.device("cuda:0")
+    carry = torch.from_numpy(first[-4:].copy()).to(dev)
+    out = torch.full((4, 148), 7, dtype=torch.uint8, device=dev)
+    z = torch.zeros((1, 260), dtype=torch.uint8, device=dev)
+    dsp.tch_encode_dev(z, z, z, 0, 1, 5, carry, out, 148)
+    torch.cuda.synchronize()
+    o = out.cpu().numpy()
+    # closing the carry with nothing: the odd half and Hl of the carry, midamble, everything else zero
+    exp = first[-4:].copy()
+    assert np.array_equal(o, exp)
+    rest = dsp.tch_encode_host(d[9:], f[9:], steal[9:], True, 5, carry=first[-4:])
+    assert np.array_equal(rest[:-4], want[36:])
+    one = dsp.tch_encode_host(d[:1], f[:1], steal[:1], False, -1)
+    assert np.array_equal(one[:4], ref_tch(ref, d[:1], f[:1], steal[:1], False, -1, [(0, 1)]))
+
+
+@pytest.mark.gpu
 def test_encode_modulate_demod_decode_chain(ref, dsp):
     """L2 frames -> GPU encoder -> GPU modulator -> (clean channel) GPU normal-burst demod -> GPU block decoder: the frames
     come back, and the bursts in the middle are the reference encoder's"""
