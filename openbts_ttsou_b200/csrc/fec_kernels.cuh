@@ -182,42 +182,6 @@ __host__ __device__ constexpr ParityTable<N> make_parity_table(unsigned long lon
 __device__ const ParityTable<184> d_fire_par = make_parity_table<184>(0x10004820009ULL, 40);   // lane-indexed reads: global, not __constant__
 __device__ const ParityTable<50> d_tch_par = make_parity_table<50>(0x0bULL, 3);
 
-// Output byte o = B * 148 + pos of a group of four bursts -> where its bit comes from: an index into the coded bits, or
-// kEncSpecial | s for the fixed fields -- bit s of a per-group word: s = 0 a zero (tails), 1 a one, 2 Hl, 3 Hu, 4 + i midamble bit i.
-constexpr unsigned short kEncSpecial = 0x8000;
-struct alignas(16) EncTable { unsigned short idx[4 * 148]; };
-__host__ __device__ constexpr unsigned short enc_fixed_field(int pos) {
-  if (pos < 3 || pos >= 145) return kEncSpecial | 0;
-  if (pos == 60) return kEncSpecial | 2;
-  if (pos == 87) return kEncSpecial | 3;
-  if (pos >= 61 && pos < 87) return (unsigned short)(kEncSpecial | (4 + pos - 61));
-  return 0xffff;                                                         // an e-bit
-}
-// XCCH: c[k] goes to burst k % 4, e-bit 2*((49 k) % 57) + (k % 8)/4 (interleave :811-819)
-__host__ __device__ constexpr EncTable make_xcch_table() {
-  EncTable t{};
-  for (int B = 0; B < 4; B++)
-    for (int pos = 0; pos < 148; pos++) t.idx[B * 148 + pos] = enc_fixed_field(pos);
-  for (int k = 0; k < 456; k++) {
-    const int B = k % 4, j = 2 * ((49 * k) % 57) + ((k % 8) / 4);
-    t.idx[B * 148 + (j < 57 ? 3 + j : 88 + (j - 57))] = (unsigned short)k;
-  }
-  return t;
-}
-// TCH: burst B of group g takes the even e-bits from block g (c[k], k % 8 == B: index 456 + k) and the odd ones from block g - 1
-// (k % 8 == B + 4: index k) -- the previous block's coded bits sit right below this block's in shared memory
-__host__ __device__ constexpr EncTable make_tch_table() {
-  EncTable t{};
-  for (int B = 0; B < 4; B++)
-    for (int pos = 0; pos < 148; pos++) t.idx[B * 148 + pos] = enc_fixed_field(pos);
-  for (int k = 0; k < 456; k++) {
-    const int r = k % 8, j = 2 * ((49 * k) % 57) + (r / 4);
-    const int pos = j < 57 ? 3 + j : 88 + (j - 57);
-    if (r < 4) t.idx[r * 148 + pos] = (unsigned short)(456 + k);
-    else t.idx[(r - 4) * 148 + pos] = (unsigned short)k;
-  }
-  return t;
-}
 __device__ const EncTable d_xcch_table = make_xcch_table();
 __device__ const EncTable d_tch_table = make_tch_table();
 
@@ -300,9 +264,65 @@ __global__ void __launch_bounds__(kXcchWarps * 32) k_xcch_encode(const unsigned 
   xcch_encode_warp(frames + f * 184, lsb8msb, sm[warp].u, cs[warp], lane);
   enc_write_group(d_xcch_table, cs[warp], sp_base | (1u << 2) | (1u << 3), bursts + f * 4 * (long long)burst_pitch, burst_pitch, lane);   // Hl = Hu = 1 :735-736
 }
+// lane form (fec_lane.cuh): one lane per frame, the block in registers as bit-packed words
+__device__ const CrcTable d_fire_crc = make_fire_crc_table();
+constexpr int kEncLaneThreads = 128;
+__global__ void __launch_bounds__(kEncLaneThreads) k_xcch_encode_lanes(const unsigned char *__restrict__ frames, long long nframes, int lsb8msb,
+                                                                     unsigned sp_base, unsigned char *__restrict__ bursts) {
+  __shared__ unsigned long long crc[256];
+  for (int i = threadIdx.x; i < 256; i += kEncLaneThreads) crc[i] = d_fire_crc.t[i];
+  __syncthreads();
+  const long long f = (long long)blockIdx.x * kEncLaneThreads + threadIdx.x;
+  if (f >= nframes) return;
+  xcch_encode_frame_lane(frames + f * 184, lsb8msb, crc, sp_base, bursts + f * 592);
+}
+// The same with the warp's 32 frames staged through shared memory: the 5888 input bytes arrive with coalesced 16-byte loads
+// (lane-strided 4-byte loads of 184-byte rows touched every sector eight times), and every lane assembles its four bursts in its
+// own 592-byte row and sends the row to global memory as ONE bulk async copy (cp.async.bulk, 592 contiguous bytes) instead of 37
+// stores of 16 bytes at a 592-byte lane stride.  Row pitch 592 B = 148 words keeps a quarter-warp's 16-byte stores on distinct banks.
+constexpr int kEncTileWarps = 4;
+constexpr size_t kEncTileIn = 32 * 184, kEncTileOut = 32 * 592, kEncTileSmem = kEncTileWarps * (kEncTileIn + kEncTileOut) + 2048;
+__device__ __forceinline__ void enc_bulk_store(void *gdst, const void *ssrc, unsigned bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\ncp.async.bulk.commit_group;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+__global__ void __launch_bounds__(kEncTileWarps * 32) k_xcch_encode_tiles(const unsigned char *__restrict__ frames, long long nframes, int lsb8msb,
+                                                                        unsigned sp_base, unsigned char *__restrict__ bursts) {
+  extern __shared__ __align__(16) unsigned char enc_smem[];
+  unsigned long long *crc = reinterpret_cast<unsigned long long *>(enc_smem);
+  for (int i = threadIdx.x; i < 256; i += kEncTileWarps * 32) crc[i] = d_fire_crc.t[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char *in = enc_smem + 2048 + warp * (kEncTileIn + kEncTileOut), *out = in + kEncTileIn;
+  const long long f0 = ((long long)blockIdx.x * kEncTileWarps + warp) * 32;
+  if (f0 >= nframes) return;
+  if (nframes - f0 >= 32) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(frames + f0 * 184);
+    for (int i = lane; i < (int)(kEncTileIn / 16); i += 32) reinterpret_cast<uint4 *>(in)[i] = __ldg(src + i);
+    __syncwarp();
+    xcch_encode_frame_lane(in + lane * 184, lsb8msb, crc, sp_base, out + lane * 592);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // the row is visible to the copy engine
+    enc_bulk_store(bursts + (f0 + lane) * 592, out + lane * 592, 592u);
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");        // the row has been read before the CTA's memory goes away
+  } else if (f0 + lane < nframes) {                                      // the ragged last warp: straight from and to global memory
+    xcch_encode_frame_lane(frames + (f0 + lane) * 184, lsb8msb, crc, sp_base, bursts + (f0 + lane) * 592);
+  }
+}
+static int g_enc_lanes = 2;              // BTSDSP_ENC_LANES: 0 = the warp-per-block kernels everywhere, 1 = lane form on global memory, 2 = staged
 int launch_xcch_encode(const unsigned char *frames, long long nframes, int lsb8msb, unsigned tsc_word, int have_tsc, unsigned char *bursts,
                        int burst_pitch, cudaStream_t st) {
   if (nframes <= 0) return 0;
+  if (g_enc_lanes && burst_pitch == 148 && (reinterpret_cast<uintptr_t>(frames) & 3) == 0 && (reinterpret_cast<uintptr_t>(bursts) & 15) == 0) {
+    if (g_enc_lanes == 2 && (reinterpret_cast<uintptr_t>(frames) & 15) == 0) {
+      const long long tiles = (nframes + 31) / 32;
+      k_xcch_encode_tiles<<<(unsigned)((tiles + kEncTileWarps - 1) / kEncTileWarps), kEncTileWarps * 32, kEncTileSmem, st>>>(
+          frames, nframes, lsb8msb, enc_sp_base(tsc_word, have_tsc), bursts);
+      return 1;
+    }
+    k_xcch_encode_lanes<<<(unsigned)((nframes + kEncLaneThreads - 1) / kEncLaneThreads), kEncLaneThreads, 0, st>>>(
+        frames, nframes, lsb8msb, enc_sp_base(tsc_word, have_tsc), bursts);
+    return 1;
+  }
   k_xcch_encode<<<(unsigned)((nframes + kXcchWarps - 1) / kXcchWarps), kXcchWarps * 32, 0, st>>>(frames, nframes, lsb8msb,
                                                                                               enc_sp_base(tsc_word, have_tsc), bursts, burst_pitch);
   return 1;

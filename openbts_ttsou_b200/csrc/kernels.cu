@@ -12,6 +12,7 @@
 #include "kernels.cuh"
 #include "sigproc_device.cuh"
 #include "demod_fast.cuh"
+#include "fec_lane.cuh"
 
 namespace btsdsp {
 
@@ -1517,6 +1518,9 @@ int configure_kernels() {
   if (const char *e = getenv("BTSDSP_EQ_RING")) g_eq_ring = atoi(e) != 0;
   if (const char *e = getenv("BTSDSP_DET_SPLIT")) g_det_split = atoi(e) != 0;
   if (const char *e = getenv("BTSDSP_SLICER_RING")) g_slicer_ring = atoi(e) != 0;
+  if (const char *e = getenv("BTSDSP_ENC_LANES")) g_enc_lanes = atoi(e);
+  e = cudaFuncSetAttribute(k_xcch_encode_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncTileSmem);
+  if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_slicer_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEqRingBytes);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_detect_design<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)detect_smem<1>());

@@ -92,6 +92,12 @@ class Emu:
         self.lib.emu_xcch_encode(P(frames), c_ll(frames.shape[0]), c_i(int(bool(lsb8msb))), c_i(tsc), P(out), c_i(burst_pitch))
         return out
 
+    def xcch_encode_lanes(self, frames, lsb8msb=True, tsc=-1):
+        frames = np.ascontiguousarray(frames, np.uint8)
+        out = np.zeros((4 * frames.shape[0], 148), np.uint8)
+        self.lib.emu_xcch_encode_lanes(P(frames), c_ll(frames.shape[0]), c_i(int(bool(lsb8msb))), c_i(tsc), P(out))
+        return out
+
     def tch_encode(self, d260, f184, steal, lsb8msb=True, tsc=-1, carry=None, burst_pitch=148):
         d260 = np.ascontiguousarray(d260, np.uint8); f184 = np.ascontiguousarray(f184, np.uint8)
         steal = np.ascontiguousarray(steal, np.uint8)

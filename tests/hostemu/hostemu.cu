@@ -16,6 +16,7 @@
 #include "../../openbts_ttsou_b200/csrc/sigproc_device.cuh"
 #include "../../openbts_ttsou_b200/csrc/demod_fast.cuh"
 #include "../../openbts_ttsou_b200/csrc/tables_host.h"
+#include "../../openbts_ttsou_b200/csrc/fec_lane.cuh"
 
 using namespace btsdsp;
 
@@ -755,6 +756,12 @@ static unsigned emu_tsc_word(int tsc) {
 void emu_xcch_encode(const unsigned char *frames, long long nframes, int lsb8msb, int tsc, unsigned char *bursts, int burst_pitch) {
   for (long long f = 0; f < nframes; f++)
     xcch_encode_frame_seq(frames + f * 184, lsb8msb, emu_tsc_word(tsc), tsc >= 0, bursts + f * 4 * (long long)burst_pitch, burst_pitch);
+}
+// the lane form of the encoder kernels (fec_lane.cuh): bit-packed words, compile-time positions; pitch 148 only
+void emu_xcch_encode_lanes(const unsigned char *frames, long long nframes, int lsb8msb, int tsc, unsigned char *bursts) {
+  static const CrcTable crc = make_fire_crc_table();
+  const unsigned sp = enc_sp_base(emu_tsc_word(tsc), tsc >= 0);
+  for (long long f = 0; f < nframes; f++) xcch_encode_frame_lane(frames + f * 184, lsb8msb, crc.t, sp, bursts + f * 592);
 }
 void emu_tch_encode(const unsigned char *d260, const unsigned char *f184, const unsigned char *steal, long long nblocks, int lsb8msb,
                     int tsc, const unsigned char *carry, unsigned char *bursts, int burst_pitch) {

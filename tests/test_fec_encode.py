@@ -65,6 +65,13 @@ def test_xcch_encode_hostemu_matches_reference(ref, hostemu, lsb, tsc):
     assert np.array_equal(wide[:, :148], want) and not wide[:, 148:].any()
 
 
+@pytest.mark.parametrize("lsb,tsc", [(True, 2), (False, -1), (False, 5)])
+def test_xcch_encode_lane_form_matches_reference(ref, hostemu, lsb, tsc):
+    """the kernels' lane form (bit-packed words, compile-time bit positions, byte-wise CRC table) on the CPU"""
+    f = make_xcch(300, 32)
+    assert np.array_equal(Emu(hostemu).xcch_encode_lanes(f, lsb, tsc), ref.xcch_send_frames(f, lsb, tsc))
+
+
 def test_xcch_encode_agrees_with_the_decoder_test_generator(ref, hostemu):
     """the e-bits are the ones the (older) decoder-side generator ref_xcch_encode makes from the same d"""
     f = make_xcch(50, 5)
@@ -104,6 +111,7 @@ def test_encode_hostemu_matches_golden(hostemu):
     g = golden("fec_encode.npz")
     emu = Emu(hostemu)
     assert np.array_equal(emu.xcch_encode(g["frames"], True, 2), g["xcch_bursts"])
+    assert np.array_equal(emu.xcch_encode_lanes(g["frames"], True, 2), g["xcch_bursts"])
     got, _ = our_tch(emu.tch_encode, g["d"], g["f"], g["steal"], True, 5, [(0, 10), (10, 48)])
     assert np.array_equal(got, g["tch_bursts"])
 
