@@ -276,12 +276,13 @@ __global__ void __launch_bounds__(kEncLaneThreads) k_xcch_encode_lanes(const uns
   if (f >= nframes) return;
   xcch_encode_frame_lane(frames + f * 184, lsb8msb, crc, sp_base, bursts + f * 592);
 }
-// The same with the warp's 32 frames staged through shared memory: the 5888 input bytes arrive with coalesced 16-byte loads
-// (lane-strided 4-byte loads of 184-byte rows touched every sector eight times), and every lane assembles its four bursts in its
-// own 592-byte row and sends the row to global memory as ONE bulk async copy (cp.async.bulk, 592 contiguous bytes) instead of 37
-// stores of 16 bytes at a 592-byte lane stride.  Row pitch 592 B = 148 words keeps a quarter-warp's 16-byte stores on distinct banks.
+// The same with the OUTPUT rows staged through shared memory: every lane assembles its four bursts in its own 592-byte row and
+// sends the row to global memory as ONE bulk async copy (cp.async.bulk, 592 contiguous bytes) instead of 37 stores of 16 bytes at a
+// 592-byte lane stride (0.61 -> 0.22 ms per 2^20 frames).  Row pitch 592 B = 148 words keeps a quarter-warp's 16-byte stores on
+// distinct banks.  The frames are read straight from global memory: staging them too (coalesced 16-byte loads into a 5.9 KB tile
+// per warp) measured 0.31 ms -- the extra shared memory costs more residency than the lane-strided loads cost bandwidth.
 constexpr int kEncTileWarps = 4;
-constexpr size_t kEncTileIn = 32 * 184, kEncTileOut = 32 * 592, kEncTileSmem = kEncTileWarps * (kEncTileIn + kEncTileOut) + 2048;
+constexpr size_t kEncTileOut = 32 * 592, kEncTileSmem = kEncTileWarps * kEncTileOut + 2048;
 __device__ __forceinline__ void enc_bulk_store(void *gdst, const void *ssrc, unsigned bytes) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\ncp.async.bulk.commit_group;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
@@ -292,30 +293,21 @@ __global__ void __launch_bounds__(kEncTileWarps * 32) k_xcch_encode_tiles(const 
   unsigned long long *crc = reinterpret_cast<unsigned long long *>(enc_smem);
   for (int i = threadIdx.x; i < 256; i += kEncTileWarps * 32) crc[i] = d_fire_crc.t[i];
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char *in = enc_smem + 2048 + warp * (kEncTileIn + kEncTileOut), *out = in + kEncTileIn;
-  const long long f0 = ((long long)blockIdx.x * kEncTileWarps + warp) * 32;
-  if (f0 >= nframes) return;
-  if (nframes - f0 >= 32) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(frames + f0 * 184);
-    for (int i = lane; i < (int)(kEncTileIn / 16); i += 32) reinterpret_cast<uint4 *>(in)[i] = __ldg(src + i);
-    __syncwarp();
-    xcch_encode_frame_lane(in + lane * 184, lsb8msb, crc, sp_base, out + lane * 592);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // the row is visible to the copy engine
-    enc_bulk_store(bursts + (f0 + lane) * 592, out + lane * 592, 592u);
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");        // the row has been read before the CTA's memory goes away
-  } else if (f0 + lane < nframes) {                                      // the ragged last warp: straight from and to global memory
-    xcch_encode_frame_lane(frames + (f0 + lane) * 184, lsb8msb, crc, sp_base, bursts + (f0 + lane) * 592);
-  }
+  const long long f = (long long)blockIdx.x * (kEncTileWarps * 32) + threadIdx.x;
+  if (f >= nframes) return;
+  unsigned char *row = enc_smem + 2048 + threadIdx.x * 592;
+  xcch_encode_frame_lane(frames + f * 184, lsb8msb, crc, sp_base, row);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // the row is visible to the copy engine
+  enc_bulk_store(bursts + f * 592, row, 592u);
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");          // the row has been read before the CTA's memory goes away
 }
-static int g_enc_lanes = 2;              // BTSDSP_ENC_LANES: 0 = the warp-per-block kernels everywhere, 1 = lane form on global memory, 2 = staged
+static int g_enc_lanes = 2;              // BTSDSP_ENC_LANES: 0 = the warp-per-block kernels everywhere, 1 = lane form storing straight to global memory, 2 = rows out through shared memory
 int launch_xcch_encode(const unsigned char *frames, long long nframes, int lsb8msb, unsigned tsc_word, int have_tsc, unsigned char *bursts,
                        int burst_pitch, cudaStream_t st) {
   if (nframes <= 0) return 0;
   if (g_enc_lanes && burst_pitch == 148 && (reinterpret_cast<uintptr_t>(frames) & 3) == 0 && (reinterpret_cast<uintptr_t>(bursts) & 15) == 0) {
-    if (g_enc_lanes == 2 && (reinterpret_cast<uintptr_t>(frames) & 15) == 0) {
-      const long long tiles = (nframes + 31) / 32;
-      k_xcch_encode_tiles<<<(unsigned)((tiles + kEncTileWarps - 1) / kEncTileWarps), kEncTileWarps * 32, kEncTileSmem, st>>>(
+    if (g_enc_lanes == 2) {
+      k_xcch_encode_tiles<<<(unsigned)((nframes + kEncTileWarps * 32 - 1) / (kEncTileWarps * 32)), kEncTileWarps * 32, kEncTileSmem, st>>>(
           frames, nframes, lsb8msb, enc_sp_base(tsc_word, have_tsc), bursts);
       return 1;
     }
@@ -366,9 +358,53 @@ __global__ void __launch_bounds__((kTchGroups + 1) * 32) k_tch_encode(const unsi
   const unsigned sp = sp_base | ((unsigned)stolen[warp - 1] << 2) | ((unsigned)stolen[warp] << 3);   // Hl = previous, Hu = current :1365-1366
   enc_write_group(d_tch_table, cs[warp - 1], sp, bursts + g * 4 * (long long)burst_pitch, burst_pitch, lane);
 }
+// Lane form for the traffic channel (fec_lane.cuh): lane L of a warp codes block b0 + L into bit-packed code planes, takes the
+// planes of block b0 + L - 1 from its neighbour by shuffle, and lanes 1..31 assemble groups b0 + 1 .. b0 + 31 (31 groups per warp:
+// one block in 32 is coded twice), each in its own 592-byte shared-memory row that leaves as one bulk async copy.  Groups
+// 0 .. kTchLaneFirst - 1 (group 0 needs the previous call's carry) stay with the first CTA of k_tch_encode.
+constexpr int kTchLaneFirst = kTchGroups, kTchLaneGroups = 31;
+__global__ void __launch_bounds__(kEncTileWarps * 32) k_tch_encode_tiles(const unsigned char *__restrict__ d260, const unsigned char *__restrict__ f184,
+                                                                       const unsigned char *__restrict__ steal, long long nblocks, int lsb8msb,
+                                                                       unsigned sp_base, unsigned char *__restrict__ bursts) {
+  extern __shared__ __align__(16) unsigned char enc_smem[];
+  unsigned long long *crc = reinterpret_cast<unsigned long long *>(enc_smem);
+  for (int i = threadIdx.x; i < 256; i += kEncTileWarps * 32) crc[i] = d_fire_crc.t[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long G = kTchLaneFirst + ((long long)blockIdx.x * kEncTileWarps + warp) * kTchLaneGroups;   // the warp's first group
+  if (G > nblocks) return;
+  const long long b = G - 1 + lane;                                      // the block this lane codes = the group it assembles
+  unsigned pl[32];
+  int st = 0;
+  if (b < nblocks) {
+    st = steal[b] ? 1 : 0;
+    tch_block_planes(st, d260 + b * kTchD, f184 + b * 184, lsb8msb, crc, pl + 16, pl + 24);
+  } else {
+#pragma unroll
+    for (int i = 16; i < 32; i++) pl[i] = 0;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i++) pl[i] = __shfl_up_sync(0xffffffffu, pl[16 + i], 1);
+  const int pst = __shfl_up_sync(0xffffffffu, st, 1);
+  if (lane == 0 || b > nblocks) return;
+  unsigned char *row = enc_smem + 2048 + (warp * 32 + lane) * 592;
+  tch_encode_group_lane(pl, pst, st, sp_base, row);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  enc_bulk_store(bursts + b * 592, row, 592u);
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 int launch_tch_encode(const unsigned char *d260, const unsigned char *f184, const unsigned char *steal, long long nblocks, int lsb8msb,
                       unsigned tsc_word, int have_tsc, const unsigned char *carry, unsigned char *bursts, int burst_pitch, cudaStream_t st) {
   if (nblocks < 0) return 0;
+  if (g_enc_lanes && nblocks >= kTchLaneFirst && burst_pitch == 148 && (reinterpret_cast<uintptr_t>(bursts) & 15) == 0 &&
+      ((reinterpret_cast<uintptr_t>(d260) | reinterpret_cast<uintptr_t>(f184)) & 3) == 0) {
+    // groups 0 .. 7 (blocks -1 .. 7): the first CTA of the warp-per-block kernel; the rest: lanes
+    k_tch_encode<<<1, (kTchGroups + 1) * 32, 0, st>>>(d260, f184, steal, nblocks, lsb8msb, enc_sp_base(tsc_word, have_tsc), carry, bursts, burst_pitch);
+    const long long warps = (nblocks - kTchLaneFirst + kTchLaneGroups) / kTchLaneGroups;      // groups kTchLaneFirst .. nblocks
+    k_tch_encode_tiles<<<(unsigned)((warps + kEncTileWarps - 1) / kEncTileWarps), kEncTileWarps * 32, kEncTileSmem, st>>>(
+        d260, f184, steal, nblocks, lsb8msb, enc_sp_base(tsc_word, have_tsc), bursts);
+    return 2;
+  }
   const long long groups = nblocks + 1;
   k_tch_encode<<<(unsigned)((groups + kTchGroups - 1) / kTchGroups), (kTchGroups + 1) * 32, 0, st>>>(d260, f184, steal, nblocks, lsb8msb,
                                                                                                   enc_sp_base(tsc_word, have_tsc), carry, bursts,

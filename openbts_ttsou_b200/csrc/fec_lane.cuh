@@ -170,6 +170,95 @@ BTS_HD void enc_out_group(const unsigned *pl, unsigned sp, unsigned char *out) {
   enc_out_all<TAB>(pl, sp, out, std::make_integer_sequence<int, 37>());
 }
 
+// ---- traffic channel ----
+// 3-bit class-1A parity (Parity(0x0b, 3, 50)) as three masks: state bit j = parity of the d bits selected by mask j (the code is
+// linear; mask bit i = bit j of the state a lone 1 at position i leaves behind)
+struct TchParMasks { unsigned m[3][2]; };
+__host__ __device__ constexpr TchParMasks make_tch_par_masks() {
+  TchParMasks t{};
+  for (int i = 0; i < 50; i++) {
+    unsigned state = 0x0bu & 7u;
+    for (int s = i + 1; s < 50; s++) {
+      const unsigned fb = (state >> 2) & 1u;
+      state = (state << 1) & 7u;
+      if (fb) state ^= 0x0bu & 7u;
+    }
+    for (int j = 0; j < 3; j++) if ((state >> j) & 1u) t.m[j][i >> 5] |= 1u << (i & 31);
+  }
+  return t;
+}
+BTS_HD unsigned popc32(unsigned x) {
+#ifdef __CUDA_ARCH__
+  return (unsigned)__popc(x);
+#else
+  return (unsigned)__builtin_popcount(x);
+#endif
+}
+// the even-position bits of x, packed into the low 16 bits
+BTS_HD unsigned even16(unsigned x) {
+  x &= 0x55555555u;
+  x = (x | (x >> 1)) & 0x33333333u;
+  x = (x | (x >> 2)) & 0x0f0f0f0fu;
+  x = (x | (x >> 4)) & 0x00ff00ffu;
+  return (x | (x >> 8)) & 0xffffu;
+}
+// code planes of one speech frame d[260] (class order; encodeTCH, GSML1FEC.cpp:1248-1279): u[k] = d[2k], u[184-k] = d[2k+1]
+// (k <= 90), u[91..94) = the inverted 3-bit parity of d[0..50) MSB first, four tail zeros, class 1 coded; the class-2 bits
+// d[182..260) follow uncoded as c[378..456).  All of it on words: e / o = the even / odd bits of d.  d must be 4-byte aligned.
+BTS_HD void tch_speech_planes(const unsigned char *d, unsigned G0[8], unsigned G1[8]) {
+  unsigned D[10];
+#pragma unroll
+  for (int j = 0; j < 10; j++) D[j] = 0;
+#pragma unroll
+  for (int i = 0; i < 65; i++) D[i >> 3] |= pack4(load32(d + 4 * i)) << (4 * (i & 7));
+  unsigned E[5], O[5];
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    E[j] = even16(D[2 * j]) | (even16(D[2 * j + 1]) << 16);
+    O[j] = even16(D[2 * j] >> 1) | (even16(D[2 * j + 1] >> 1) << 16);
+  }
+  constexpr TchParMasks PM = make_tch_par_masks();
+  unsigned state = 0;
+#pragma unroll
+  for (int j = 0; j < 3; j++) state |= ((popc32(D[0] & PM.m[j][0]) ^ popc32(D[1] & PM.m[j][1])) & 1u) << j;
+  const unsigned p = ~state & 7u;
+  constexpr unsigned LOW27 = (1u << 27) - 1;
+  const unsigned R0 = rev32(O[2] & LOW27), R1 = rev32(O[1]), R2 = rev32(O[0]);      // o[0..91) reversed over 96 bits
+  unsigned W[8];
+  W[0] = E[0];
+  W[1] = E[1];
+  W[2] = (E[2] & LOW27) | (((p >> 2) & 1u) << 27) | (((p >> 1) & 1u) << 28) | ((p & 1u) << 29) | (R0 << 25);
+  W[3] = (R1 << 25) | (R0 >> 7);
+  W[4] = (R2 << 25) | (R1 >> 7);
+  W[5] = R2 >> 7;
+  W[6] = 0;
+  W[7] = 0;
+  conv_planes(W, G0, G1);
+  // class 2: plane bit 189 + m = e[91 + m] / o[91 + m], m < 39: the bits from 91 up, moved up by 98
+  const unsigned e2 = E[2] & ~LOW27, o2 = O[2] & ~LOW27;
+  G0[5] |= e2 << 2;
+  G0[6] |= (E[3] << 2) | (e2 >> 30);
+  G0[7] |= (E[4] << 2) | (E[3] >> 30);
+  G1[5] |= o2 << 2;
+  G1[6] |= (O[3] << 2) | (o2 >> 30);
+  G1[7] |= (O[4] << 2) | (O[3] >> 30);
+}
+// code planes of block q of a traffic channel: a stolen block is a FACCH frame coded like an XCCH block (dispatch :1323-1333)
+BTS_HD void tch_block_planes(int stolen, const unsigned char *d, const unsigned char *f, int lsb8msb, const unsigned long long *crc,
+                             unsigned G0[8], unsigned G1[8]) {
+  if (stolen) {
+    unsigned W[8];
+    xcch_u_words(f, lsb8msb, crc, W);
+    conv_planes(W, G0, G1);
+  } else {
+    tch_speech_planes(d, G0, G1);
+  }
+}
+// group g of four bursts from the planes of block g - 1 (pl[0..16): odd e-bits, Hl) and block g (pl[16..32): even e-bits, Hu)
+BTS_HD void tch_encode_group_lane(const unsigned *pl, int prev_stolen, int cur_stolen, unsigned sp_base, unsigned char *bursts) {
+  enc_out_group<TchTab>(pl, sp_base | ((unsigned)(prev_stolen != 0) << 2) | ((unsigned)(cur_stolen != 0) << 3), bursts);
+}
+
 // one XCCH frame, lane form
 BTS_HD void xcch_encode_frame_lane(const unsigned char *frame, int lsb8msb, const unsigned long long *crc, unsigned sp_base,
                                    unsigned char *bursts) {

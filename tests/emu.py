@@ -98,6 +98,14 @@ class Emu:
         self.lib.emu_xcch_encode_lanes(P(frames), c_ll(frames.shape[0]), c_i(int(bool(lsb8msb))), c_i(tsc), P(out))
         return out
 
+    def tch_encode_lanes(self, d260, f184, steal, lsb8msb=True, tsc=-1):
+        """lane form: rows 4 .. of the (4*nblocks + 4, 148) output (groups 1 .. nblocks); rows 0..3 stay zero"""
+        d260 = np.ascontiguousarray(d260, np.uint8); f184 = np.ascontiguousarray(f184, np.uint8)
+        steal = np.ascontiguousarray(steal, np.uint8)
+        out = np.zeros((4 * steal.shape[0] + 4, 148), np.uint8)
+        self.lib.emu_tch_encode_lanes(P(d260), P(f184), P(steal), c_ll(steal.shape[0]), c_i(int(bool(lsb8msb))), c_i(tsc), P(out))
+        return out
+
     def tch_encode(self, d260, f184, steal, lsb8msb=True, tsc=-1, carry=None, burst_pitch=148):
         d260 = np.ascontiguousarray(d260, np.uint8); f184 = np.ascontiguousarray(f184, np.uint8)
         steal = np.ascontiguousarray(steal, np.uint8)

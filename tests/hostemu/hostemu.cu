@@ -763,6 +763,19 @@ void emu_xcch_encode_lanes(const unsigned char *frames, long long nframes, int l
   const unsigned sp = enc_sp_base(emu_tsc_word(tsc), tsc >= 0);
   for (long long f = 0; f < nframes; f++) xcch_encode_frame_lane(frames + f * 184, lsb8msb, crc.t, sp, bursts + f * 592);
 }
+// traffic channel, lane form: groups 1 .. nblocks (group 0 needs the carry: the warp-per-block kernel's job); bursts = 4*nblocks+4 rows of 148
+void emu_tch_encode_lanes(const unsigned char *d260, const unsigned char *f184, const unsigned char *steal, long long nblocks, int lsb8msb,
+                          int tsc, unsigned char *bursts) {
+  static const CrcTable crc = make_fire_crc_table();
+  const unsigned sp = enc_sp_base(emu_tsc_word(tsc), tsc >= 0);
+  for (long long g = 1; g <= nblocks; g++) {
+    unsigned pl[32];
+    for (int i = 0; i < 32; i++) pl[i] = 0;
+    tch_block_planes(steal[g - 1], d260 + (g - 1) * 260, f184 + (g - 1) * 184, lsb8msb, crc.t, pl, pl + 8);
+    if (g < nblocks) tch_block_planes(steal[g], d260 + g * 260, f184 + g * 184, lsb8msb, crc.t, pl + 16, pl + 24);
+    tch_encode_group_lane(pl, steal[g - 1], g < nblocks ? steal[g] : 0, sp, bursts + g * 592);
+  }
+}
 void emu_tch_encode(const unsigned char *d260, const unsigned char *f184, const unsigned char *steal, long long nblocks, int lsb8msb,
                     int tsc, const unsigned char *carry, unsigned char *bursts, int burst_pitch) {
   tch_encode_stream_seq(d260, f184, steal, nblocks, lsb8msb, emu_tsc_word(tsc), tsc >= 0, carry, bursts, burst_pitch);

@@ -91,6 +91,17 @@ def test_tch_encode_hostemu_matches_reference(ref, hostemu, splits):
         assert not carry[:, 87].any() and (carry[:, 60] == steal[-1]).all()
 
 
+def test_tch_encode_lane_form_matches_reference(ref, hostemu):
+    """the traffic-channel kernels' lane form on the CPU: every group but the first (which needs the carry) against the reference"""
+    d, f, steal = make_tch(96, 80)
+    for lsb, tsc in ((True, 5), (False, -1)):
+        want = ref_tch(ref, d, f, steal, lsb, tsc, [(0, 96)])
+        seq = Emu(hostemu).tch_encode(d, f, steal, lsb, tsc)
+        got = Emu(hostemu).tch_encode_lanes(d, f, steal, lsb, tsc)
+        assert np.array_equal(got[4:-4], want[4:])
+        assert np.array_equal(got[-4:], seq[-4:])                        # the closing (carry) group
+
+
 def test_encode_decode_round_trip(hostemu):
     """encoder -> ideal soft bytes -> the receive-side block decoders give the frames back (no reference needed)"""
     emu = Emu(hostemu)

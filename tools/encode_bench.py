@@ -38,4 +38,4 @@ def timeit(fn, reps=10):
 x = timeit(lambda: dsp.xcch_encode_dev(frames, n, 1, 2, bursts, 148, st))
 t = timeit(lambda: dsp.tch_encode_dev(d260, frames, steal, n, 1, 5, None, tb, 148, st))
 print(json.dumps({"xcch_encode": {"frames": n, "ms": x, "bursts_per_s": 4 * n / x * 1e3, "gbs": n * (184 + 592) / x / 1e6},
-                  "tch_encode": {"blocks": n, "ms": t, "bursts_per_s": 4 * n / t * 1e3, "gbs": n * (260 + 184 + 1 + 592) / t / 1e6}}))
+                  "tch_encode": {"blocks": n, "ms": t, "bursts_per_s": 4 * n / t * 1e3, "gbs": (float((steal == 0).sum()) * 260 + float((steal != 0).sum()) * 184 + n * (1 + 592)) / t / 1e6}}))
