@@ -282,10 +282,30 @@ __global__ void __launch_bounds__(kEncLaneThreads) k_xcch_encode_lanes(const uns
 // distinct banks.  The frames are read straight from global memory: staging them too (coalesced 16-byte loads into a 5.9 KB tile
 // per warp) measured 0.31 ms -- the extra shared memory costs more residency than the lane-strided loads cost bandwidth.
 constexpr int kEncTileWarps = 4;
-constexpr size_t kEncTileOut = 32 * 592, kEncTileSmem = kEncTileWarps * kEncTileOut + 2048;
+constexpr size_t kEncTileSmem = kEncTileWarps * 32 * 592 + 2048, kTchTileSmem = kEncTileWarps * 32 * 304 + 2048;
 __device__ __forceinline__ void enc_bulk_store(void *gdst, const void *ssrc, unsigned bytes) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\ncp.async.bulk.commit_group;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+// HALVES: the group leaves in two pieces (quads 0..18 and 19..36: 304 + 288 bytes) through one 304-byte row per lane -- half the
+// shared memory, twice the resident warps, one more wait on the copy engine.  Measured per 2^20 blocks: traffic channel 0.278 ->
+// 0.234 ms (kept), XCCH 0.212 -> 0.293 ms (its lanes sit on the serial CRC chain already; it keeps the whole-group row).
+template <class TAB, bool HALVES>
+__device__ __forceinline__ void enc_store_group(const unsigned *pl, unsigned sp, unsigned char *row, unsigned char *gdst) {
+  if (HALVES) {
+    enc_out_range<TAB, 0, 19>(pl, sp, row);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // the row is visible to the copy engine
+    enc_bulk_store(gdst, row, 304u);
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");        // ... and has been read: it can be written again
+    enc_out_range<TAB, 19, 18>(pl, sp, row);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    enc_bulk_store(gdst + 304, row, 288u);
+  } else {
+    enc_out_range<TAB, 0, 37>(pl, sp, row);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    enc_bulk_store(gdst, row, 592u);
+  }
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");          // before the CTA's memory goes away
 }
 __global__ void __launch_bounds__(kEncTileWarps * 32) k_xcch_encode_tiles(const unsigned char *__restrict__ frames, long long nframes, int lsb8msb,
                                                                         unsigned sp_base, unsigned char *__restrict__ bursts) {
@@ -295,11 +315,10 @@ __global__ void __launch_bounds__(kEncTileWarps * 32) k_xcch_encode_tiles(const 
   __syncthreads();
   const long long f = (long long)blockIdx.x * (kEncTileWarps * 32) + threadIdx.x;
   if (f >= nframes) return;
-  unsigned char *row = enc_smem + 2048 + threadIdx.x * 592;
-  xcch_encode_frame_lane(frames + f * 184, lsb8msb, crc, sp_base, row);
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // the row is visible to the copy engine
-  enc_bulk_store(bursts + f * 592, row, 592u);
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");          // the row has been read before the CTA's memory goes away
+  unsigned W[8], pl[16];
+  xcch_u_words(frames + f * 184, lsb8msb, crc, W);
+  conv_planes(W, pl, pl + 8);
+  enc_store_group<XcchTab, false>(pl, sp_base | (1u << 2) | (1u << 3), enc_smem + 2048 + threadIdx.x * 592, bursts + f * 592);   // Hl = Hu = 1 :735-736
 }
 static int g_enc_lanes = 2;              // BTSDSP_ENC_LANES: 0 = the warp-per-block kernels everywhere, 1 = lane form storing straight to global memory, 2 = rows out through shared memory
 int launch_xcch_encode(const unsigned char *frames, long long nframes, int lsb8msb, unsigned tsc_word, int have_tsc, unsigned char *bursts,
@@ -387,11 +406,8 @@ __global__ void __launch_bounds__(kEncTileWarps * 32) k_tch_encode_tiles(const u
   for (int i = 0; i < 16; i++) pl[i] = __shfl_up_sync(0xffffffffu, pl[16 + i], 1);
   const int pst = __shfl_up_sync(0xffffffffu, st, 1);
   if (lane == 0 || b > nblocks) return;
-  unsigned char *row = enc_smem + 2048 + (warp * 32 + lane) * 592;
-  tch_encode_group_lane(pl, pst, st, sp_base, row);
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  enc_bulk_store(bursts + b * 592, row, 592u);
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  enc_store_group<TchTab, true>(pl, sp_base | ((unsigned)pst << 2) | ((unsigned)st << 3), enc_smem + 2048 + (warp * 32 + lane) * 304,
+                          bursts + b * 592);                             // Hl = the previous block's flag, Hu = this block's :1365-1366
 }
 int launch_tch_encode(const unsigned char *d260, const unsigned char *f184, const unsigned char *steal, long long nblocks, int lsb8msb,
                       unsigned tsc_word, int have_tsc, const unsigned char *carry, unsigned char *bursts, int burst_pitch, cudaStream_t st) {
@@ -401,7 +417,7 @@ int launch_tch_encode(const unsigned char *d260, const unsigned char *f184, cons
     // groups 0 .. 7 (blocks -1 .. 7): the first CTA of the warp-per-block kernel; the rest: lanes
     k_tch_encode<<<1, (kTchGroups + 1) * 32, 0, st>>>(d260, f184, steal, nblocks, lsb8msb, enc_sp_base(tsc_word, have_tsc), carry, bursts, burst_pitch);
     const long long warps = (nblocks - kTchLaneFirst + kTchLaneGroups) / kTchLaneGroups;      // groups kTchLaneFirst .. nblocks
-    k_tch_encode_tiles<<<(unsigned)((warps + kEncTileWarps - 1) / kEncTileWarps), kEncTileWarps * 32, kEncTileSmem, st>>>(
+    k_tch_encode_tiles<<<(unsigned)((warps + kEncTileWarps - 1) / kEncTileWarps), kEncTileWarps * 32, kTchTileSmem, st>>>(
         d260, f184, steal, nblocks, lsb8msb, enc_sp_base(tsc_word, have_tsc), bursts);
     return 2;
   }

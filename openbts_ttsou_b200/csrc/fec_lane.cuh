@@ -164,6 +164,15 @@ template <class TAB, int... Q>
 BTS_HD void enc_out_all(const unsigned *pl, unsigned sp, unsigned char *out, std::integer_sequence<int, Q...>) {
   (enc_out_quad<TAB, Q>(pl, sp, out), ...);
 }
+// quads Q0 .. Q0 + N - 1 of a group (16 bytes each), written to out[0 .. 16 N): a piece of the group for a staging row
+template <class TAB, int Q0, int... I>
+BTS_HD void enc_out_range_(const unsigned *pl, unsigned sp, unsigned char *out, std::integer_sequence<int, I...>) {
+  (enc_out_quad<TAB, Q0 + I>(pl, sp, out - 16 * Q0), ...);
+}
+template <class TAB, int Q0, int N>
+BTS_HD void enc_out_range(const unsigned *pl, unsigned sp, unsigned char *out) {
+  enc_out_range_<TAB, Q0>(pl, sp, out, std::make_integer_sequence<int, N>());
+}
 // the four bursts of a group (592 contiguous bytes: burst pitch 148), out 16-byte aligned
 template <class TAB>
 BTS_HD void enc_out_group(const unsigned *pl, unsigned sp, unsigned char *out) {

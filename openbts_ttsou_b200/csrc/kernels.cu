@@ -1521,7 +1521,7 @@ int configure_kernels() {
   if (const char *e = getenv("BTSDSP_ENC_LANES")) g_enc_lanes = atoi(e);
   e = cudaFuncSetAttribute(k_xcch_encode_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncTileSmem);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(k_tch_encode_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncTileSmem);
+  e = cudaFuncSetAttribute(k_tch_encode_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTchTileSmem);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_slicer_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEqRingBytes);
   if (e != cudaSuccess) return (int)e;
