@@ -92,10 +92,10 @@ class Emu:
         self.lib.emu_xcch_encode(P(frames), c_ll(frames.shape[0]), c_i(int(bool(lsb8msb))), c_i(tsc), P(out), c_i(burst_pitch))
         return out
 
-    def xcch_encode_lanes(self, frames, lsb8msb=True, tsc=-1):
+    def xcch_encode_lanes(self, frames, lsb8msb=True, tsc=-1, popc=False):
         frames = np.ascontiguousarray(frames, np.uint8)
         out = np.zeros((4 * frames.shape[0], 148), np.uint8)
-        self.lib.emu_xcch_encode_lanes(P(frames), c_ll(frames.shape[0]), c_i(int(bool(lsb8msb))), c_i(tsc), P(out))
+        (self.lib.emu_xcch_encode_lanes_popc if popc else self.lib.emu_xcch_encode_lanes)(P(frames), c_ll(frames.shape[0]), c_i(int(bool(lsb8msb))), c_i(tsc), P(out))
         return out
 
     def tch_encode_lanes(self, d260, f184, steal, lsb8msb=True, tsc=-1):

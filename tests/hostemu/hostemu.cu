@@ -763,6 +763,15 @@ void emu_xcch_encode_lanes(const unsigned char *frames, long long nframes, int l
   const unsigned sp = enc_sp_base(emu_tsc_word(tsc), tsc >= 0);
   for (long long f = 0; f < nframes; f++) xcch_encode_frame_lane(frames + f * 184, lsb8msb, crc.t, sp, bursts + f * 592);
 }
+void emu_xcch_encode_lanes_popc(const unsigned char *frames, long long nframes, int lsb8msb, int tsc, unsigned char *bursts) {
+  const unsigned sp = enc_sp_base(emu_tsc_word(tsc), tsc >= 0);
+  for (long long f = 0; f < nframes; f++) {
+    unsigned W[8], pl[16];
+    xcch_u_words_popc(frames + f * 184, lsb8msb, W);
+    conv_planes(W, pl, pl + 8);
+    enc_out_group<XcchTab>(pl, sp | (1u << 2) | (1u << 3), bursts + f * 592);
+  }
+}
 // traffic channel, lane form: groups 1 .. nblocks (group 0 needs the carry: the warp-per-block kernel's job); bursts = 4*nblocks+4 rows of 148
 void emu_tch_encode_lanes(const unsigned char *d260, const unsigned char *f184, const unsigned char *steal, long long nblocks, int lsb8msb,
                           int tsc, unsigned char *bursts) {

@@ -70,6 +70,7 @@ def test_xcch_encode_lane_form_matches_reference(ref, hostemu, lsb, tsc):
     """the kernels' lane form (bit-packed words, compile-time bit positions, byte-wise CRC table) on the CPU"""
     f = make_xcch(300, 32)
     assert np.array_equal(Emu(hostemu).xcch_encode_lanes(f, lsb, tsc), ref.xcch_send_frames(f, lsb, tsc))
+    assert np.array_equal(Emu(hostemu).xcch_encode_lanes(f, lsb, tsc, popc=True), ref.xcch_send_frames(f, lsb, tsc))   # parity by masks
 
 
 def test_xcch_encode_agrees_with_the_decoder_test_generator(ref, hostemu):
